@@ -1,0 +1,113 @@
+"""Pins the CPU oracles (oracle/mpc_oracle.py, oracle/abr_oracle.c) to the reference.
+
+Fixtures in tests/golden/mpc_ref_golden.json were produced by importing the
+unmodified /root/reference/mpc.py (oracle/gen_golden.py).  The reference's one
+golden is mpc_test.py:52-86 -> "Test next bitrate: 2".
+"""
+import numpy as np
+import pytest
+
+from oracle import mpc_oracle as mo
+from oracle import oracle as orc
+
+
+def _py_decide(sc, want_grid=False, history=None):
+    return mo.decide_ref(sc["k"], sc["prev_q"], sc["buffer"], sc["history"] if history is None else history,
+                         sc["H"], sc["bitrates"], sc["sizes"], sc["chunk_length"], sc["max_buffer"],
+                         sc["vw"], sc["rw"], want_grid=want_grid)
+
+
+def _c_decide(sc, K=None):
+    sizes = np.array(sc["sizes"], float)
+    util = np.array(sc["bitrates"], float)          # identity utility (mpc.py:95-97)
+    hist = list(sc["history"])
+    K = K or max(1, len(hist))
+    ring = np.zeros((1, K))
+    ring[0, :len(hist)] = hist
+    p = orc.make_params(chunk_length=sc["chunk_length"], max_buffer=sc["max_buffer"], rebuf_penalty=sc["rw"],
+                        smooth_penalty=sc["vw"], utility_scale=1.0)
+    return orc.mpc_decide(sizes, util, [sc["k"]], [sc["prev_q"]], [sc["buffer"]], ring, [len(hist)], sc["H"], 0, p)
+
+
+def test_reference_golden_mpc_test_scenario(golden):
+    """mpc_test.py:81-86 prints 'Test next bitrate: 2'; survey KATs for the same scenario."""
+    c = golden["cases"][0]
+    assert c["scenario"]["name"] == "mpc_test"
+    assert c["ref"]["actions"] == [2, 2, 2]
+    assert c["ref"]["hist_len_after"] == [10, 15, 20]        # D10 list mutation
+    assert c["ref"]["best_seq"] == [2, 1, 3, 3, 3]
+    assert c["ref"]["best_J"] == -117.56833333333331
+    r = _py_decide(c["scenario"], want_grid=True)
+    assert r["action"] == 2 and r["best_seq"] == [2, 1, 3, 3, 3]
+    assert r["best_J"] == -117.56833333333331
+    assert r["preds"] == c["ref"]["preds"]
+    assert r["J"] == c["ref"]["J"]                            # all 1 024 scores bit-identical
+    assert len(r["history_after"]) == 10
+    rc = _c_decide(c["scenario"])
+    assert rc["action"][0] == 2 and list(rc["best_seq"][0]) == [2, 1, 3, 3, 3]
+    assert rc["best_J"][0] == -117.56833333333331
+    assert list(rc["preds"][0]) == c["ref"]["preds"]
+
+
+def test_kats(golden):
+    k = golden["kat"]
+    preds, after = mo.predict_harmonic_ref(3, [1, 2, 3, 4])
+    assert preds == k["predict_3_1234"] and len(after) == k["predict_3_1234_len_after"] == 7
+    assert preds == [1.9200000000000004, 1.9200000000000004, 1.9200000000000006]
+    bw = 3.468208092485549
+    assert mo.next_buffer_ref(1, 20, bw, 1, 20) == k["next_buffer_a"] == 20.0
+    assert mo.next_buffer_ref(8, 0.3, bw, 1, 20) == k["next_buffer_b"] == 1.0
+    assert k["calc_wait"] == 0.711666666666666
+
+
+def test_python_oracle_matches_reference_everywhere(golden):
+    n_grid = 0
+    for c in golden["cases"]:
+        sc, ref = c["scenario"], c["ref"]
+        r = _py_decide(sc, want_grid="J" in ref)
+        assert r["preds"] == ref["preds"], sc["name"]
+        assert r["best_seq"] == ref["best_seq"], sc["name"]
+        assert r["best_J"] == ref["best_J"], sc["name"]
+        assert r["action"] == ref["actions"][0], sc["name"]
+        if "J" in ref:
+            assert r["J"] == ref["J"], sc["name"]
+            n_grid += 1
+        # repeated calls on the same player see the polluted history (D10)
+        hist = list(sc["history"])
+        for i, a in enumerate(ref["actions"]):
+            rr = _py_decide(sc, history=hist)
+            assert rr["action"] == a, (sc["name"], i)
+            hist = rr["history_after"]
+            assert len(hist) == ref["hist_len_after"][i]
+    assert n_grid >= 20 and len(golden["cases"]) >= 160
+
+
+def test_c_oracle_matches_reference_everywhere(golden):
+    for c in golden["cases"]:
+        sc, ref = c["scenario"], c["ref"]
+        r = _c_decide(sc)
+        assert r["n_errors"] == 0
+        assert list(r["preds"][0]) == ref["preds"], sc["name"]
+        assert list(r["best_seq"][0]) == ref["best_seq"], sc["name"]
+        assert r["best_J"][0] == ref["best_J"], sc["name"]
+        assert r["action"][0] == ref["actions"][0], sc["name"]
+        # ring storage with a larger capacity must not change anything
+        r2 = _c_decide(sc, K=len(sc["history"]) + 3)
+        assert r2["action"][0] == ref["actions"][0] and r2["best_J"][0] == ref["best_J"]
+
+
+def test_reference_error_behaviour(golden):
+    by = {e["scenario"]["name"]: e for e in golden["errors"]}
+    assert by["index_error_k56"]["raises"] == "IndexError"
+    assert by["empty_history"]["raises"] == "ZeroDivisionError"
+    assert by["zero_sample"]["raises"] == "ZeroDivisionError"
+    assert by["horizon_1"]["raises"] == "IndexError"       # brute returns a 0-d array at H=1 (mpc.py:186)
+    with pytest.raises(IndexError):
+        _py_decide(by["index_error_k56"]["scenario"])
+    with pytest.raises(ZeroDivisionError):
+        _py_decide(by["empty_history"]["scenario"])
+    with pytest.raises(ZeroDivisionError):
+        _py_decide(by["zero_sample"]["scenario"])
+    for name in ("index_error_k56", "empty_history", "zero_sample"):
+        r = _c_decide(by[name]["scenario"])
+        assert r["action"][0] == -1 and r["n_errors"] == 1
