@@ -1,0 +1,533 @@
+// C-ABI of libabr_b200.so (declared in include/abr_b200.h): handle management, validation,
+// host<->device plumbing.  No compute happens on the CPU here: every entry point either launches
+// the sm_100a kernels of abr_step.cu / abr_mpc.cu or fails with ABR_ERR_CUDA.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "abr_common.cuh"
+
+namespace abr {
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace abr
+
+using namespace abr;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                 \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) return fail(ABR_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                           __FILE__, __LINE__);                                        \
+    } while (0)
+
+struct AbrEnv {
+    EnvView v{};
+    int device = 0;
+    std::vector<void*> allocs;
+    double* d_stats_partials = nullptr;
+    int n_partials_cap = 0;
+    double* d_stats_out = nullptr;
+    // scratch for the *_host entry points
+    int32_t* d_trace_id = nullptr;
+    double* d_offset = nullptr;
+    int32_t* d_actions = nullptr;
+    size_t d_actions_cap = 0;
+    double* d_reward_traj = nullptr;
+    size_t d_reward_cap = 0;
+
+    ~AbrEnv() {
+        for (void* p : allocs) cudaFree(p);
+        if (d_actions) cudaFree(d_actions);
+        if (d_reward_traj) cudaFree(d_reward_traj);
+    }
+    template <typename T>
+    cudaError_t alloc(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) { allocs.push_back(p); *out = (T*)p; }
+        return e;
+    }
+};
+
+extern "C" {
+
+int abr_version(void) { return ABR_VERSION; }
+const char* abr_last_error(void) { return g_err; }
+long long abr_launch_count(void) { return g_launches.load(); }
+
+int abr_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* total_mem_bytes) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (total_mem_bytes) *total_mem_bytes = (long long)prop.totalGlobalMem;
+    return ABR_OK;
+}
+
+void abr_params_default(AbrParams* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->chunk_length = 4.0; p->max_buffer = 60.0; p->rtt = 0.08; p->payload = 0.95; p->sleep_quantum = 0.5;
+    p->rebuf_penalty = 4.3; p->smooth_penalty = 1.0; p->utility_scale = 0.001;
+    p->bba_reservoir = 5.0; p->bba_cushion = 10.0;
+    p->utility_mode = 0; p->default_quality = 1; p->auto_reset = 1; p->hist_k = 5;
+    p->track_history = 0; p->track_acc = 0;
+}
+
+static int check_params(const AbrParams* p, int A) {
+    if (!p) return fail(ABR_ERR_INVALID, "params is NULL");
+    if (!(p->chunk_length > 0.0) || !std::isfinite(p->chunk_length)) return fail(ABR_ERR_INVALID, "chunk_length must be > 0");
+    if (!(p->max_buffer > 0.0)) return fail(ABR_ERR_INVALID, "max_buffer must be > 0");
+    if (!(p->payload > 0.0) || !std::isfinite(p->payload)) return fail(ABR_ERR_INVALID, "payload must be > 0");
+    if (!(p->rtt >= 0.0) || !std::isfinite(p->rtt)) return fail(ABR_ERR_INVALID, "rtt must be >= 0");
+    if (!(p->sleep_quantum > 0.0)) return fail(ABR_ERR_INVALID, "sleep_quantum must be > 0");
+    if (p->hist_k < 1 || p->hist_k > 64) return fail(ABR_ERR_RANGE, "hist_k must be in [1, 64]");
+    if (p->default_quality >= A) return fail(ABR_ERR_RANGE, "default_quality %d out of range for A=%d", p->default_quality, A);
+    if (p->utility_mode != 0 && p->utility_mode != 1) return fail(ABR_ERR_INVALID, "utility_mode must be 0 or 1");
+    if (!(p->bba_cushion > 0.0)) return fail(ABR_ERR_INVALID, "bba_cushion must be > 0");
+    return ABR_OK;
+}
+
+static void utility_table(const double* bitrates, int V, int A, const AbrParams* p, std::vector<double>& util) {
+    util.resize((size_t)V * A);
+    for (int v = 0; v < V; ++v)
+        for (int a = 0; a < A; ++a) {
+            const double b = bitrates[(size_t)v * A + a];
+            util[(size_t)v * A + a] = p->utility_mode == 1 ? std::log(b / bitrates[(size_t)v * A + A - 1])  // mpc.py:99-102
+                                                           : b * p->utility_scale;                        // mpc.py:95-97
+        }
+}
+
+static int check_tables(const double* sizes, const double* bitrates, int V, int A) {
+    if (!sizes || !bitrates) return fail(ABR_ERR_INVALID, "sizes/bitrates is NULL");
+    if (V < 1 || A < 1 || A > 16) return fail(ABR_ERR_RANGE, "need V >= 1 and 1 <= A <= 16 (got V=%d A=%d)", V, A);
+    for (size_t i = 0; i < (size_t)V * A; ++i) {
+        if (!std::isfinite(sizes[i]) || sizes[i] < 0.0) return fail(ABR_ERR_INVALID, "sizes[%zu] = %g is not finite and >= 0", i, sizes[i]);
+        if (!std::isfinite(bitrates[i])) return fail(ABR_ERR_INVALID, "bitrates[%zu] is not finite", i);
+    }
+    return ABR_OK;
+}
+
+int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const double* h_trace_interval, int n_traces,
+                   int T_max, const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params,
+                   int max_sessions, AbrEnv** out) {
+    if (!out) return fail(ABR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!h_trace_bw || !h_trace_len || !h_trace_interval) return fail(ABR_ERR_INVALID, "trace table is NULL");
+    if (n_traces < 1 || T_max < 1 || max_sessions < 1) return fail(ABR_ERR_RANGE, "n_traces, T_max, max_sessions must be >= 1");
+    int rc = check_tables(h_sizes, h_bitrates, V, A);
+    if (rc) return rc;
+    rc = check_params(params, A);
+    if (rc) return rc;
+    for (int t = 0; t < n_traces; ++t) {
+        const int len = h_trace_len[t];
+        if (len < 1 || len > T_max) return fail(ABR_ERR_RANGE, "trace_len[%d] = %d not in [1, %d]", t, len, T_max);
+        if (!(h_trace_interval[t] > 0.0) || !std::isfinite(h_trace_interval[t]))
+            return fail(ABR_ERR_INVALID, "trace_interval[%d] must be finite and > 0", t);
+        for (int i = 0; i < len; ++i) {
+            const double b = h_trace_bw[(size_t)t * T_max + i];
+            if (!(b > 0.0) || !std::isfinite(b))  // the reference would divide by zero / never finish (D14)
+                return fail(ABR_ERR_INVALID, "trace %d segment %d: bandwidth %g must be finite and > 0", t, i, b);
+        }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ABR_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    AbrEnv* e = new (std::nothrow) AbrEnv();
+    if (!e) return fail(ABR_ERR_INVALID, "out of host memory");
+    struct Guard { AbrEnv* e; ~Guard() { delete e; } } guard{e};
+    CUDA_TRY(cudaGetDevice(&e->device));
+    EnvView& v = e->v;
+    v.n_traces = n_traces; v.T_max = T_max; v.V = V; v.A = A; v.K = params->hist_k; v.cap = max_sessions; v.n = 0;
+    v.session_base = 0; v.p = *params;
+    const size_t cap = (size_t)max_sessions;
+    double *d_bw, *d_int, *d_sizes, *d_util;
+    int32_t* d_len;
+    CUDA_TRY(e->alloc(&d_bw, (size_t)n_traces * T_max));
+    CUDA_TRY(e->alloc(&d_len, n_traces));
+    CUDA_TRY(e->alloc(&d_int, n_traces));
+    CUDA_TRY(e->alloc(&d_sizes, (size_t)V * A));
+    CUDA_TRY(e->alloc(&d_util, (size_t)V * A));
+    std::vector<double> util;
+    utility_table(h_bitrates, V, A, params, util);
+    CUDA_TRY(cudaMemcpy(d_bw, h_trace_bw, sizeof(double) * n_traces * T_max, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_len, h_trace_len, sizeof(int32_t) * n_traces, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_int, h_trace_interval, sizeof(double) * n_traces, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_sizes, h_sizes, sizeof(double) * V * A, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice));
+    v.trace_bw = d_bw; v.trace_len = d_len; v.trace_interval = d_int; v.sizes = d_sizes; v.util = d_util;
+    CUDA_TRY(e->alloc(&v.seg, cap)); CUDA_TRY(e->alloc(&v.chunk, cap)); CUDA_TRY(e->alloc(&v.last_q, cap));
+    CUDA_TRY(e->alloc(&v.trace_id, cap)); CUDA_TRY(e->alloc(&v.hist_len, cap)); CUDA_TRY(e->alloc(&v.err_len, cap));
+    CUDA_TRY(e->alloc(&v.done, cap)); CUDA_TRY(e->alloc(&v.tau, cap)); CUDA_TRY(e->alloc(&v.buffer, cap));
+    CUDA_TRY(e->alloc(&v.bw_hist, cap * v.K)); CUDA_TRY(e->alloc(&v.last_pred, cap));
+    CUDA_TRY(e->alloc(&v.err_ring, cap * v.K)); CUDA_TRY(e->alloc(&v.acc, cap * ABR_NUM_ACC));
+    CUDA_TRY(e->alloc(&v.errors, 1));
+    CUDA_TRY(cudaMemset(v.errors, 0, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(v.bw_hist, 0, sizeof(double) * cap * v.K));
+    CUDA_TRY(cudaMemset(v.err_ring, 0, sizeof(double) * cap * v.K));
+    e->n_partials_cap = stats_num_partials(max_sessions);
+    CUDA_TRY(e->alloc(&e->d_stats_partials, (size_t)e->n_partials_cap * ABR_NUM_ACC));
+    CUDA_TRY(e->alloc(&e->d_stats_out, ABR_NUM_STATS));
+    CUDA_TRY(e->alloc(&e->d_trace_id, cap));
+    CUDA_TRY(e->alloc(&e->d_offset, cap));
+    guard.e = nullptr;
+    *out = e;
+    return ABR_OK;
+}
+
+void abr_env_destroy(AbrEnv* env) { delete env; }
+
+int abr_env_num_sessions(const AbrEnv* env) { return env ? env->v.n : 0; }
+
+int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_offset, int n_sessions,
+                  long long session_base, void* stream) {
+    if (!env || !d_trace_id) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
+    if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
+    env->v.n = n_sessions;
+    env->v.session_base = session_base;
+    CUDA_TRY(launch_reset(env->v, d_trace_id, d_start_offset, (cudaStream_t)stream));
+    return ABR_OK;
+}
+
+int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_start_offset, int n_sessions,
+                       long long session_base, void* stream) {
+    if (!env || !h_trace_id) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
+    if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(env->d_trace_id, h_trace_id, sizeof(int32_t) * n_sessions, cudaMemcpyHostToDevice, st));
+    if (h_start_offset)
+        CUDA_TRY(cudaMemcpyAsync(env->d_offset, h_start_offset, sizeof(double) * n_sessions, cudaMemcpyHostToDevice, st));
+    return abr_env_reset(env, env->d_trace_id, h_start_offset ? env->d_offset : nullptr, n_sessions, session_base, stream);
+}
+
+int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
+                 double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_end_of_video, double* d_throughput,
+                 void* stream) {
+    if (!env || !d_action) return fail(ABR_ERR_INVALID, "env or action is NULL");
+    if (env->v.n <= 0) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    CUDA_TRY(launch_step(env->v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_next_sizes, d_end_of_video,
+                         d_throughput, (cudaStream_t)stream));
+    return ABR_OK;
+}
+
+int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                          double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
+                          uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream) {
+    if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
+    if (env->v.n <= 0) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    if (steps < 0) return fail(ABR_ERR_RANGE, "steps must be >= 0");
+    if (policy < ABR_POLICY_FIXED || policy > ABR_POLICY_BBA) return fail(ABR_ERR_INVALID, "unknown policy %d", policy);
+    if (policy == ABR_POLICY_FIXED && !d_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs d_actions_in");
+    CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_delay, d_sleep, d_buffer, d_rebuf, d_reward,
+                            d_end_of_video, d_actions_out, (cudaStream_t)stream));
+    return ABR_OK;
+}
+
+static int check_mpc_shape(int A, int H) {
+    if (H < 1 || H > 8) return fail(ABR_ERR_RANGE, "horizon must be in [1, 8] (got %d)", H);
+    if (A < 1 || A > 16) return fail(ABR_ERR_RANGE, "A must be in [1, 16]");
+    double combos = 1;
+    for (int i = 0; i < H; ++i) combos *= A;
+    if (combos > 2147483647.0) return fail(ABR_ERR_RANGE, "A^H = %g sequences exceed the 2^31-1 index range", combos);
+    return ABR_OK;
+}
+
+int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, double* d_best_j, void* stream) {
+    if (!env || !d_action) return fail(ABR_ERR_INVALID, "env or action is NULL");
+    if (env->v.n <= 0) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    if (mode != ABR_MPC_REF && mode != ABR_MPC_ROBUST) return fail(ABR_ERR_INVALID, "unknown MPC mode %d", mode);
+    int rc = check_mpc_shape(env->v.A, horizon);
+    if (rc) return rc;
+    const EnvView& v = env->v;
+    MpcArgs a{};
+    a.sizes = v.sizes; a.util = v.util; a.V = v.V; a.A = v.A; a.p = v.p; a.N = v.n;
+    a.chunk_idx = v.chunk; a.prev_q = v.last_q; a.buffer = v.buffer; a.done = v.p.auto_reset ? nullptr : v.done;
+    a.bw_hist = v.bw_hist; a.hist_len = v.hist_len; a.K = v.K;
+    a.hist_session_stride = 1; a.hist_slot_stride = v.cap;     // env rings are [K][cap]
+    a.last_pred = v.last_pred; a.err_ring = v.err_ring; a.err_len = v.err_len;
+    a.H = horizon; a.mode = mode; a.flags = ABR_MPC_TRUNCATE | ABR_MPC_EMPTY_DEFAULT;
+    a.action = d_action; a.best_j = d_best_j; a.best_seq = nullptr; a.preds = nullptr;
+    a.error_count64 = v.errors; a.error_count32 = nullptr;
+    CUDA_TRY(launch_mpc(a, (cudaStream_t)stream));
+    return ABR_OK;
+}
+
+int abr_stats_partial(AbrEnv* env, double* d_out, void* stream) {
+    if (!env || !d_out) return fail(ABR_ERR_INVALID, "env or out is NULL");
+    const int np = stats_num_partials(env->v.n);
+    CUDA_TRY(launch_stats(env->v, env->d_stats_partials, np, d_out, (cudaStream_t)stream));
+    return ABR_OK;
+}
+
+int abr_env_state_ptr(AbrEnv* env, int field, void** d_ptr) {
+    if (!env || !d_ptr) return fail(ABR_ERR_INVALID, "env or d_ptr is NULL");
+    const EnvView& v = env->v;
+    switch (field) {
+        case ABR_F_SEG: *d_ptr = v.seg; break;
+        case ABR_F_CHUNK: *d_ptr = v.chunk; break;
+        case ABR_F_LAST_Q: *d_ptr = v.last_q; break;
+        case ABR_F_TRACE_ID: *d_ptr = v.trace_id; break;
+        case ABR_F_HIST_LEN: *d_ptr = v.hist_len; break;
+        case ABR_F_DONE: *d_ptr = v.done; break;
+        case ABR_F_ERR_LEN: *d_ptr = v.err_len; break;
+        case ABR_F_TAU: *d_ptr = v.tau; break;
+        case ABR_F_BUFFER: *d_ptr = v.buffer; break;
+        case ABR_F_BW_HIST: *d_ptr = v.bw_hist; break;
+        case ABR_F_LAST_PRED: *d_ptr = v.last_pred; break;
+        case ABR_F_ERR_RING: *d_ptr = v.err_ring; break;
+        case ABR_F_ACC: *d_ptr = v.acc; break;
+        case ABR_F_SIZES: *d_ptr = (void*)v.sizes; break;
+        case ABR_F_UTILITY: *d_ptr = (void*)v.util; break;
+        case ABR_F_TRACE_BW: *d_ptr = (void*)v.trace_bw; break;
+        default: return fail(ABR_ERR_INVALID, "unknown state field %d", field);
+    }
+    return ABR_OK;
+}
+
+int abr_env_error_count(AbrEnv* env, long long* out, void* stream) {
+    if (!env || !out) return fail(ABR_ERR_INVALID, "env or out is NULL");
+    unsigned long long h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, env->v.errors, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    *out = (long long)h;
+    return ABR_OK;
+}
+
+int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* h_trace_id,
+                     const double* h_start_offset, int n_sessions, long long session_base, const int32_t* h_actions_in,
+                     double* h_acc, double* h_stats, double* h_reward_traj, void* stream) {
+    if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
+    if (steps < 0) return fail(ABR_ERR_RANGE, "steps must be >= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = abr_env_reset_host(env, h_trace_id, h_start_offset, n_sessions, session_base, stream);
+    if (rc) return rc;
+    const size_t traj = (size_t)steps * n_sessions;
+    if (policy == ABR_POLICY_FIXED) {
+        if (!h_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs h_actions_in");
+        if (traj > env->d_actions_cap) {
+            if (env->d_actions) cudaFree(env->d_actions);
+            env->d_actions = nullptr; env->d_actions_cap = 0;
+            CUDA_TRY(cudaMalloc(&env->d_actions, sizeof(int32_t) * (traj ? traj : 1)));
+            env->d_actions_cap = traj;
+        }
+        CUDA_TRY(cudaMemcpyAsync(env->d_actions, h_actions_in, sizeof(int32_t) * traj, cudaMemcpyHostToDevice, st));
+    }
+    if (h_reward_traj && traj > env->d_reward_cap) {
+        if (env->d_reward_traj) cudaFree(env->d_reward_traj);
+        env->d_reward_traj = nullptr; env->d_reward_cap = 0;
+        CUDA_TRY(cudaMalloc(&env->d_reward_traj, sizeof(double) * (traj ? traj : 1)));
+        env->d_reward_cap = traj;
+    }
+    rc = abr_env_rollout_fused(env, policy, seed, steps, policy == ABR_POLICY_FIXED ? env->d_actions : nullptr, nullptr,
+                               nullptr, nullptr, nullptr, h_reward_traj ? env->d_reward_traj : nullptr, nullptr, nullptr,
+                               stream);
+    if (rc) return rc;
+    if (h_stats) {
+        rc = abr_stats_partial(env, env->d_stats_out, stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_stats, env->d_stats_out, sizeof(double) * ABR_NUM_STATS, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_acc) {
+        // acc rows are strided by the capacity on the device; the host table is dense [ABR_NUM_ACC][N]
+        CUDA_TRY(cudaMemcpy2DAsync(h_acc, sizeof(double) * n_sessions, env->v.acc, sizeof(double) * env->v.cap,
+                                   sizeof(double) * n_sessions, ABR_NUM_ACC, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_reward_traj)
+        CUDA_TRY(cudaMemcpyAsync(h_reward_traj, env->d_reward_traj, sizeof(double) * traj, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ABR_OK;
+}
+
+int abr_mpc_decide(const double* d_sizes, const double* d_utility, int V, int A, const AbrParams* params, int N,
+                   const int32_t* d_chunk_idx, const int32_t* d_prev_q, const double* d_buffer, const double* d_bw_hist,
+                   const int32_t* d_hist_len, int K, double* d_last_pred, double* d_err_ring, int32_t* d_err_len,
+                   int horizon, int mode, int flags, int32_t* d_action, double* d_best_j, int32_t* d_best_seq,
+                   double* d_preds, int32_t* d_error_count, void* stream) {
+    if (!d_sizes || !d_utility || !d_chunk_idx || !d_prev_q || !d_buffer || !d_bw_hist || !d_hist_len || !d_action)
+        return fail(ABR_ERR_INVALID, "a required pointer is NULL");
+    if (!params) return fail(ABR_ERR_INVALID, "params is NULL");
+    if (N < 0 || V < 1) return fail(ABR_ERR_RANGE, "N must be >= 0 and V >= 1");
+    if (K < 1) return fail(ABR_ERR_RANGE, "K must be >= 1");
+    if (mode != ABR_MPC_REF && mode != ABR_MPC_ROBUST) return fail(ABR_ERR_INVALID, "unknown MPC mode %d", mode);
+    if ((d_last_pred || d_err_ring || d_err_len) && !(d_last_pred && d_err_ring && d_err_len))
+        return fail(ABR_ERR_INVALID, "last_pred, err_ring and err_len must be given together");
+    int rc = check_mpc_shape(A, horizon);
+    if (rc) return rc;
+    MpcArgs a{};
+    a.sizes = d_sizes; a.util = d_utility; a.V = V; a.A = A; a.p = *params; a.N = N;
+    a.chunk_idx = d_chunk_idx; a.prev_q = d_prev_q; a.buffer = d_buffer; a.done = nullptr;
+    a.bw_hist = d_bw_hist; a.hist_len = d_hist_len; a.K = K;
+    a.hist_session_stride = K; a.hist_slot_stride = 1;        // standalone rings are [N][K]
+    a.last_pred = d_last_pred; a.err_ring = d_err_ring; a.err_len = d_err_len;
+    a.H = horizon; a.mode = mode; a.flags = flags;
+    a.action = d_action; a.best_j = d_best_j; a.best_seq = d_best_seq; a.preds = d_preds;
+    a.error_count64 = nullptr; a.error_count32 = d_error_count;
+    CUDA_TRY(launch_mpc(a, (cudaStream_t)stream));
+    return ABR_OK;
+}
+
+int abr_mpc_decide_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params, int N,
+                        const int32_t* h_chunk_idx, const int32_t* h_prev_q, const double* h_buffer,
+                        const double* h_bw_hist, const int32_t* h_hist_len, int K, double* h_last_pred,
+                        double* h_err_ring, int32_t* h_err_len, int horizon, int mode, int flags, int32_t* h_action,
+                        double* h_best_j, int32_t* h_best_seq, double* h_preds, int32_t* h_error_count) {
+    if (!h_chunk_idx || !h_prev_q || !h_buffer || !h_bw_hist || !h_hist_len || !h_action)
+        return fail(ABR_ERR_INVALID, "a required pointer is NULL");
+    int rc = check_tables(h_sizes, h_bitrates, V, A);
+    if (rc) return rc;
+    if (!params) return fail(ABR_ERR_INVALID, "params is NULL");
+    if (N < 0 || K < 1) return fail(ABR_ERR_RANGE, "N must be >= 0 and K >= 1");
+    rc = check_mpc_shape(A, horizon);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ABR_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    std::vector<double> util;
+    utility_table(h_bitrates, V, A, params, util);
+    const size_t n = (size_t)(N > 0 ? N : 1), H = (size_t)horizon;
+    // one device arena: [sizes | util | buffer | hist | last_pred | err_ring | best_j | preds | ints...]
+    const size_t n_d = 2 * (size_t)V * A + n + n * K + n + n * K + n + n * H;
+    const size_t n_i = 3 * n + n + n + n * H + 1;  // chunk, prev_q, hist_len, err_len, action, best_seq, errcount
+    double* dd = nullptr;
+    int32_t* di = nullptr;
+    CUDA_TRY(cudaMalloc(&dd, sizeof(double) * n_d));
+    if (cudaMalloc(&di, sizeof(int32_t) * n_i) != cudaSuccess) { cudaFree(dd); return fail(ABR_ERR_CUDA, "cudaMalloc failed"); }
+    struct Free { double* a; int32_t* b; ~Free() { cudaFree(a); cudaFree(b); } } fr{dd, di};
+    double* d_sizes = dd; double* d_util = d_sizes + (size_t)V * A; double* d_buffer = d_util + (size_t)V * A;
+    double* d_hist = d_buffer + n; double* d_lp = d_hist + n * K; double* d_er = d_lp + n; double* d_bj = d_er + n * K;
+    double* d_pr = d_bj + n;
+    int32_t* d_chunk = di; int32_t* d_pq = d_chunk + n; int32_t* d_hl = d_pq + n; int32_t* d_el = d_hl + n;
+    int32_t* d_act = d_el + n; int32_t* d_seq = d_act + n; int32_t* d_ec = d_seq + n * H;
+    const bool robust_state = h_last_pred && h_err_ring && h_err_len;
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_sizes, h_sizes, sizeof(double) * V * A, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_buffer, h_buffer, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_hist, h_bw_hist, sizeof(double) * (size_t)N * K, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_chunk, h_chunk_idx, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_pq, h_prev_q, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_hl, h_hist_len, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    if (robust_state) {
+        CUDA_TRY(cudaMemcpyAsync(d_lp, h_last_pred, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_er, h_err_ring, sizeof(double) * (size_t)N * K, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_el, h_err_len, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemsetAsync(d_ec, 0, sizeof(int32_t), st));
+    rc = abr_mpc_decide(d_sizes, d_util, V, A, params, N, d_chunk, d_pq, d_buffer, d_hist, d_hl, K,
+                        robust_state ? d_lp : nullptr, robust_state ? d_er : nullptr, robust_state ? d_el : nullptr,
+                        horizon, mode, flags, d_act, d_bj, d_seq, d_pr, d_ec, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_action, d_act, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+    if (h_best_j) CUDA_TRY(cudaMemcpyAsync(h_best_j, d_bj, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    if (h_best_seq) CUDA_TRY(cudaMemcpyAsync(h_best_seq, d_seq, sizeof(int32_t) * (size_t)N * H, cudaMemcpyDeviceToHost, st));
+    if (h_preds) CUDA_TRY(cudaMemcpyAsync(h_preds, d_pr, sizeof(double) * (size_t)N * H, cudaMemcpyDeviceToHost, st));
+    if (h_error_count) CUDA_TRY(cudaMemcpyAsync(h_error_count, d_ec, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (robust_state) {
+        CUDA_TRY(cudaMemcpyAsync(h_last_pred, d_lp, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_err_ring, d_er, sizeof(double) * (size_t)N * K, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_err_len, d_el, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ABR_OK;
+}
+
+int abr_mpc_score_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params,
+                       int chunk_idx, int prev_q, double buffer, const double* h_history, int n_history, int horizon,
+                       int mode, double max_err, const int32_t* h_sequences, int M, double* h_scores) {
+    if (!h_history || !h_sequences || !h_scores) return fail(ABR_ERR_INVALID, "a required pointer is NULL");
+    int rc = check_tables(h_sizes, h_bitrates, V, A);
+    if (rc) return rc;
+    if (!params) return fail(ABR_ERR_INVALID, "params is NULL");
+    rc = check_mpc_shape(A, horizon);
+    if (rc) return rc;
+    if (mode != ABR_MPC_REF && mode != ABR_MPC_ROBUST) return fail(ABR_ERR_INVALID, "unknown MPC mode %d", mode);
+    if (M < 0) return fail(ABR_ERR_RANGE, "M must be >= 0");
+    if (n_history < 1) return fail(ABR_ERR_RANGE, "empty throughput history (ZeroDivisionError in mpc.py:90)");
+    for (int j = 0; j < n_history; ++j)
+        if (h_history[j] == 0.0) return fail(ABR_ERR_RANGE, "zero throughput sample (ZeroDivisionError in mpc.py:88)");
+    if (chunk_idx < 0 || chunk_idx + horizon > V) return fail(ABR_ERR_RANGE, "chunk_idx + horizon exceeds the video (IndexError in mpc.py:125-128)");
+    if (prev_q >= A) return fail(ABR_ERR_RANGE, "prev_q out of range");
+    for (size_t i = 0; i < (size_t)M * horizon; ++i)
+        if (h_sequences[i] < 0 || h_sequences[i] >= A) return fail(ABR_ERR_RANGE, "sequence entry %zu out of range", i);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ABR_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    std::vector<double> util;
+    utility_table(h_bitrates, V, A, params, util);
+    const size_t m = (size_t)(M > 0 ? M : 1);
+    double* dd = nullptr;
+    int32_t* di = nullptr;
+    CUDA_TRY(cudaMalloc(&dd, sizeof(double) * (2 * (size_t)V * A + n_history + m)));
+    if (cudaMalloc(&di, sizeof(int32_t) * m * horizon) != cudaSuccess) { cudaFree(dd); return fail(ABR_ERR_CUDA, "cudaMalloc failed"); }
+    struct Free { double* a; int32_t* b; ~Free() { cudaFree(a); cudaFree(b); } } fr{dd, di};
+    double* d_sizes = dd; double* d_util = d_sizes + (size_t)V * A; double* d_hist = d_util + (size_t)V * A;
+    double* d_scores = d_hist + n_history;
+    cudaStream_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_sizes, h_sizes, sizeof(double) * V * A, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_hist, h_history, sizeof(double) * n_history, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(di, h_sequences, sizeof(int32_t) * (size_t)M * horizon, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(launch_mpc_score(d_sizes, d_util, V, A, *params, chunk_idx, prev_q, buffer, d_hist, n_history, horizon, mode,
+                              max_err, di, M, d_scores, st));
+    CUDA_TRY(cudaMemcpyAsync(h_scores, d_scores, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ABR_OK;
+}
+
+int abr_fp64_probe(int kind, int iters, double* gops_per_s, float* ms, void* stream) {
+    if (iters < 1) return fail(ABR_ERR_RANGE, "iters must be >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* d_sink = nullptr;
+    CUDA_TRY(cudaMalloc(&d_sink, sizeof(double) * (size_t)sms * 8 * 256));
+    struct Free { double* p; ~Free() { cudaFree(p); } } fr{d_sink};
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int threads = 0;
+    long long ops = 0;
+    CUDA_TRY(launch_fp64_probe(kind, iters, d_sink, &threads, &ops, st));  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, st));
+        CUDA_TRY(launch_fp64_probe(kind, iters, d_sink, &threads, &ops, st));
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+        if (t < best) best = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = best;
+    if (gops_per_s) *gops_per_s = (double)threads * (double)ops / ((double)best * 1e-3) * 1e-9;
+    return ABR_OK;
+}
+
+}  // extern "C"

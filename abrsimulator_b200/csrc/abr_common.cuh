@@ -1,0 +1,98 @@
+// Internal definitions shared by the sm_100a kernels (abr_step.cu, abr_mpc.cu) and the C-ABI (abr_capi.cu).
+// Arithmetic contract: SPEC.md.  All fp64 arithmetic goes through the _rn intrinsics below so that no
+// FMA contraction or reassociation can happen regardless of compiler flags.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/abr_b200.h"
+
+namespace abr {
+
+// ---------------------------------------------------------------------------------------------
+// exact fp64 helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// Python `max(0, x)` (mpc.py:107): x if x > 0 else +0.  Done on the integer pipe (sign-bit mask) so
+// that it does not take an FP64 issue slot: 1 shift + 2 logic ops instead of DSETP + 2 selects.
+// Differs from the comparison form only for NaN inputs, which SPEC-valid inputs cannot produce.
+__device__ __forceinline__ double max0(double x) {
+    int hi = __double2hiint(x);
+    int lo = __double2loint(x);
+    int keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, lo & keep);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (SPEC §4); identical to oracle/abr_oracle.c:orc_philox4x32_10
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    return c0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side view of an environment (passed by value to kernels)
+// ---------------------------------------------------------------------------------------------
+struct EnvView {
+    // read-only tables
+    const double* __restrict__ trace_bw;        // [n_traces][T_max]
+    const int32_t* __restrict__ trace_len;      // [n_traces]
+    const double* __restrict__ trace_interval;  // [n_traces]
+    const double* __restrict__ sizes;           // [V][A]
+    const double* __restrict__ util;            // [V][A]
+    // SoA session state, capacity = cap
+    int32_t* seg; int32_t* chunk; int32_t* last_q; int32_t* trace_id; int32_t* hist_len; int32_t* err_len;
+    uint8_t* done;
+    double* tau; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
+    unsigned long long* errors;                 // device counter of flagged sessions
+    int n_traces, T_max, V, A, K, cap, n;       // n = active sessions
+    long long session_base;
+    AbrParams p;
+};
+
+// launchers implemented in abr_step.cu / abr_mpc.cu (C++ linkage, internal)
+cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st);
+cudaError_t launch_step(const EnvView& v, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
+                        double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_eov, double* d_thr,
+                        cudaStream_t st);
+cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                           double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
+                           uint8_t* d_eov, int32_t* d_actions_out, cudaStream_t st);
+cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, double* d_out, cudaStream_t st);
+int stats_num_partials(int n);
+
+struct MpcArgs {
+    const double* sizes; const double* util; int V, A;
+    AbrParams p;
+    int N;
+    const int32_t* chunk_idx; const int32_t* prev_q; const double* buffer; const uint8_t* done;  // done nullable
+    const double* bw_hist; const int32_t* hist_len; int K;
+    long long hist_session_stride, hist_slot_stride;       // element (s, slot) at s*session_stride + slot*slot_stride
+    double* last_pred; double* err_ring; int32_t* err_len; // nullable; err ring uses the same strides
+    int H, mode, flags;
+    int32_t* action; double* best_j; int32_t* best_seq; double* preds;
+    unsigned long long* error_count64; int32_t* error_count32; // either may be null
+};
+cudaError_t launch_mpc(const MpcArgs& a, cudaStream_t st);
+cudaError_t launch_mpc_score(const double* d_sizes, const double* d_util, int V, int A, const AbrParams& p, int k,
+                             int prev_q, double buffer, const double* d_hist, int n, int H, int mode, double max_err,
+                             const int32_t* d_seqs, int M, double* d_scores, cudaStream_t st);
+cudaError_t launch_fp64_probe(int kind, int iters, double* d_sink, int* threads_total, long long* ops_per_thread,
+                              cudaStream_t st);
+
+void count_launch(int n = 1);
+
+}  // namespace abr

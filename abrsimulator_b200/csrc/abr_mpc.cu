@@ -1,0 +1,455 @@
+// MPC decision kernel (SPEC.md §5): exhaustive A^h lookahead with tie-exact first-minimum.
+//
+// Replaces MPCBitrateController.next_bitrate (mpc.py:181-186) = predict_throughput (mpc.py:81-93) +
+// scipy.optimize.brute over objective (mpc.py:120-162, buffer model mpc.py:104-118).
+//
+// Mapping: WPS warps (32·WPS threads) per session.
+//   1. predictor: lanes invert the history samples in parallel, the harmonic sum is then accumulated
+//      oldest-first in the reference's order (warp shuffles), every lane redundantly.
+//   2. tables RB/DL/U[h][A] (the 2·h·A divisions the reference repeats A^h·3 times) -> shared memory.
+//   3. search: the A^h sequences form a prefix tree.  All partial sums of mpc.py:144-156 after step i
+//      depend only on a_0..a_i and are accumulated left to right, so carrying them down the tree executes
+//      bit-identical fp64 operations to the reference's independent rollouts.  Each thread owns the
+//      prefixes p = tid, tid+32·WPS, ... of depth h-2 (ascending, so its own scan order is lexicographic),
+//      recomputes that prefix's state (h-2 interior steps) and then walks the last two levels fully
+//      unrolled (A interior + A² leaf evaluations) with the last two table rows held in registers.
+//   4. argmin: per-thread strict '<' keeps the first minimum; across threads the key (J, linear index)
+//      is reduced with warp shuffles (and shared memory across warps), linear index = Σ a_i·A^(h-1-i),
+//      i.e. scipy.optimize.brute's C-order first minimum (mpc.py:171-179).
+//
+// Bound by FP64 issue (DADD/DMUL/DSETP), not by memory: ~100 B read per decision vs ~1e5 fp64 ops.
+#include "abr_common.cuh"
+
+namespace abr {
+
+namespace {
+
+constexpr int kMaxH = 8;
+constexpr int kMaxA = 16;
+constexpr int kMpcWarpsPerBlock = 4;
+
+struct SearchOut { double q; int idx; };
+
+// Interior step i of mpc.py:144-156 (+ next_buffer, mpc.py:111-118) on the running state.
+template <bool CLAMP>
+__device__ __forceinline__ void interior(double& vq, double& qv, double& rt, double& b, const double u,
+                                         const double absdu, const double rbv, const double dlv, const double L,
+                                         const double B) {
+    vq = dadd(vq, u);
+    qv = dadd(qv, absdu);
+    const double d = dsub(rbv, b);
+    rt = dadd(rt, CLAMP ? max0(d) : d);
+    const double t = max0(dsub(b, dlv));
+    const double tl = dadd(t, L);
+    const double w = max0(dsub(tl, B));
+    b = max0(dsub(tl, w));
+}
+
+// Search all A^h sequences for one session; h >= 2.  sU/sRB/sDL are [h][A] tables in shared memory,
+// sAD is |U[h-1][a] - U[h-1][a']| as [a][a'] (the leaf-level smoothness term).
+// AT > 0: compile-time ladder size (loops fully unrolled); AT == 0: runtime A (generic path).
+template <int AT, bool CLAMP>
+__device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const double* __restrict__ sRB,
+                                            const double* __restrict__ sDL, const double* __restrict__ sAD,
+                                            const int a_rt, const int h, const int prev_q, const double buf0,
+                                            const double vw, const double rw, const double L, const double B,
+                                            const int tid, const int nthreads) {
+    const int A = AT > 0 ? AT : a_rt;
+    constexpr bool REGTAB = AT > 0 && AT <= 6;   // larger ladders keep the rows in shared memory
+    constexpr int AR = REGTAB ? AT : 1;         // register-array extent
+    const int P = h - 2;
+    int n_prefix = 1;
+    for (int i = 0; i < P; ++i) n_prefix *= A;
+    const int i4 = h - 2, i5 = h - 1;
+    // last two table rows are uniform across threads and prefixes: keep them in registers
+    double U4[AR], RB4[AR], DL4[AR], U5[AR], RB5[AR];
+    if (REGTAB) {
+#pragma unroll
+        for (int a = 0; a < AR; ++a) {
+            U4[a] = sU[i4 * A + a]; RB4[a] = sRB[i4 * A + a]; DL4[a] = sDL[i4 * A + a];
+            U5[a] = sU[i5 * A + a]; RB5[a] = sRB[i5 * A + a];
+        }
+    }
+    double best_q = __longlong_as_double(0xfff0000000000000ll);  // -inf
+    int best_idx = 0x7fffffff;
+    for (int p = tid; p < n_prefix; p += nthreads) {
+        // decode the prefix digits (most significant first) and roll the state through levels 0..P-1
+        int dig[kMaxH];
+        {
+            int rem = p;
+#pragma unroll
+            for (int i = kMaxH - 3; i >= 0; --i) {
+                if (i < P) { dig[i] = rem % A; rem /= A; }
+            }
+        }
+        double vq = 0.0, qv = 0.0, rt = 0.0, b = buf0;
+        int ap = prev_q;
+#pragma unroll
+        for (int i = 0; i < kMaxH - 2; ++i) {
+            if (i < P) {
+                const int a = dig[i];
+                const double u = sU[i * A + a];
+                const double up = ap >= 0 ? sU[i * A + ap] : u;
+                interior<CLAMP>(vq, qv, rt, b, u, fabs(dsub(u, up)), sRB[i * A + a], sDL[i * A + a], L, B);
+                ap = a;
+            }
+        }
+        const double up4 = ap >= 0 ? sU[i4 * A + ap] : 0.0;
+        const int base = p * A * A;
+#pragma unroll
+        for (int a4 = 0; a4 < A; ++a4) {
+            const double u4 = REGTAB ? U4[a4] : sU[i4 * A + a4];
+            double vq4 = vq, qv4 = qv, rt4 = rt, b4 = b;
+            interior<CLAMP>(vq4, qv4, rt4, b4, u4, ap >= 0 ? fabs(dsub(u4, up4)) : 0.0,
+                            REGTAB ? RB4[a4] : sRB[i4 * A + a4], REGTAB ? DL4[a4] : sDL[i4 * A + a4], L, B);
+#pragma unroll
+            for (int a5 = 0; a5 < A; ++a5) {
+                const double vq5 = dadd(vq4, REGTAB ? U5[a5] : sU[i5 * A + a5]);
+                const double qv5 = dadd(qv4, sAD[a5 * A + a4]);
+                const double d = dsub(REGTAB ? RB5[a5] : sRB[i5 * A + a5], b4);
+                const double rt5 = dadd(rt4, CLAMP ? max0(d) : d);
+                const double q = dsub(dsub(vq5, dmul(vw, qv5)), dmul(rw, rt5));  // J = -q, mpc.py:158-162
+                if (q > best_q) { best_q = q; best_idx = base + a4 * A + a5; }  // strict: first minimum of J
+            }
+        }
+    }
+    SearchOut o; o.q = best_q; o.idx = best_idx;
+    return o;
+}
+
+__device__ __forceinline__ void better(double& q, int& idx, const double oq, const int oi) {
+    if (oq > q || (oq == q && oi < idx)) { q = oq; idx = oi; }
+}
+
+struct __align__(8) SessShared {
+    double U[kMaxH * kMaxA], RB[kMaxH * kMaxA], DL[kMaxH * kMaxA], AD[kMaxA * kMaxA];
+    double redq[kMpcWarpsPerBlock];
+    int redi[kMpcWarpsPerBlock];
+};
+
+// WPS warps per session; blockDim.x = 32 * kMpcWarpsPerBlock; sessions per block = kMpcWarpsPerBlock / WPS.
+// AT = compile-time ladder size (0 = runtime A), CLAMP = robust mode (SPEC §5.2) — one kernel per shape so
+// that each gets its own register allocation.
+template <int WPS, int AT, bool CLAMP>
+__global__ void __launch_bounds__(32 * kMpcWarpsPerBlock)
+abr_mpc_kernel(const MpcArgs a) {
+    constexpr int SPB = kMpcWarpsPerBlock / WPS;
+    __shared__ SessShared sh[SPB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp / WPS;                 // session slot inside the block
+    const int wis = warp % WPS;                  // warp index inside the session
+    const int tid = wis * 32 + lane;             // thread index inside the session
+    constexpr int NT = 32 * WPS;
+    SessShared& S = sh[slot];
+    const AbrParams& p = a.p;
+    const int A = AT > 0 ? AT : a.A, H = a.H, K = a.K;
+    const double L = p.chunk_length, B = p.max_buffer;
+
+    for (long long s = (long long)blockIdx.x * SPB + slot; s < a.N; s += (long long)gridDim.x * SPB) {
+        // Every thread of a session computes the quantities below redundantly and identically, so control flow
+        // (and, for WPS > 1 where one block serves one session, every __syncthreads) is uniform.
+        const int k = a.chunk_idx[s];
+        const int prev_q = a.prev_q[s];
+        const double buf0 = a.buffer[s];
+        const int hlen = a.hist_len[s];
+        const int n = hlen < K ? hlen : K;
+        const int start = hlen <= K ? 0 : hlen % K;
+        const bool inert = a.done && a.done[s];
+        int h = H;
+        int status = 0;  // 0 search, 1 fixed action (act), 2 error
+        int act = -1;
+        if (inert) { status = 1; act = 0; }
+        else if (k < 0 || prev_q >= A) status = 2;
+        else if (n <= 0) {
+            if (a.mode == ABR_MPC_ROBUST || (a.flags & ABR_MPC_EMPTY_DEFAULT)) { status = 1; act = p.default_quality > 0 ? p.default_quality : 0; }
+            else status = 2;                                               // ZeroDivisionError, mpc.py:90
+        }
+        if (status == 0) {
+            if (k + H > a.V) {
+                if (a.mode == ABR_MPC_ROBUST || (a.flags & ABR_MPC_TRUNCATE)) h = a.V - k;
+                else status = 2;                                           // IndexError, mpc.py:125-128
+                if (status == 0 && h <= 0) { status = 1; act = 0; }
+            }
+        }
+        double c_rob = 0.0;
+        if (status == 0) {
+            // ---- predictor: S = sum of 1/x oldest first (mpc.py:84-88) ----
+            double Ssum = 0.0;
+            bool bad = false;
+            double newest = 0.0;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                double x = 1.0;
+                if (j < n) x = a.bw_hist[s * a.hist_session_stride + (long long)((start + j) % K) * a.hist_slot_stride];
+                const bool xbad = (a.mode == ABR_MPC_REF) ? (x == 0.0) : !(x > 0.0);
+                bad |= (__ballot_sync(0xffffffffu, xbad && j < n) != 0u);
+                const double inv = ddiv(1.0, x);
+                const int m = min(32, n - j0);
+                for (int jj = 0; jj < m; ++jj) Ssum = dadd(Ssum, __shfl_sync(0xffffffffu, inv, jj));
+                if (j0 + 32 >= n) newest = __shfl_sync(0xffffffffu, x, m - 1);
+            }
+            if (bad) status = 2;                                           // ZeroDivisionError, mpc.py:88
+            else if (a.mode == ABR_MPC_REF) {
+                // p_i = (n+i)/S ; S += 1/p_i   (mpc.py:83-92 incl. the list mutation D10)
+                for (int i = 0; i < h; ++i) {
+                    const double pi = ddiv((double)(n + i), Ssum);
+                    Ssum = dadd(Ssum, ddiv(1.0, pi));
+                    if (a.preds && tid == 0) a.preds[s * H + i] = pi;
+                    // tables for step i: each thread of the session fills entries a = tid, tid+NT, ...
+                    for (int aa = tid; aa < A; aa += NT) {
+                        const double sz = a.sizes[(k + i) * A + aa];
+                        double m = sz > 0.0 ? sz : 0.0;                    // max(0, size, L), mpc.py:151 (D11)
+                        if (L > m) m = L;
+                        S.RB[i * A + aa] = ddiv(m, pi);
+                        S.DL[i * A + aa] = ddiv(a.sizes[k * A + aa], pi);  // D12: chunk k's sizes
+                        S.U[i * A + aa] = a.util[(k + i) * A + aa];
+                    }
+                }
+            } else {
+                const double hm = ddiv((double)n, Ssum);
+                double max_err = 0.0;
+                if (a.last_pred) {
+                    const double lp = a.last_pred[s];
+                    int el = a.err_len[s];
+                    double* ring = a.err_ring + s * a.hist_session_stride;
+                    double e_new = 0.0;
+                    const bool push = lp > 0.0;
+                    if (push) e_new = ddiv(fabs(dsub(lp, newest)), newest);
+                    const int slot_new = el % K;
+                    const int m = (el + (push ? 1 : 0)) < K ? (el + (push ? 1 : 0)) : K;
+                    for (int j = 0; j < m; ++j) {
+                        const double e = (push && j == slot_new) ? e_new : ring[(long long)j * a.hist_slot_stride];
+                        if (e > max_err) max_err = e;
+                    }
+                    __syncwarp();
+                    if (WPS > 1) __syncthreads();   // every thread has read the old state before it is replaced
+                    if (tid == 0) {
+                        if (push) { ring[(long long)slot_new * a.hist_slot_stride] = e_new; a.err_len[s] = el + 1; }
+                        a.last_pred[s] = hm;
+                    }
+                }
+                c_rob = ddiv(hm, dadd(1.0, max_err));
+                if (a.preds && tid < H) a.preds[s * H + tid] = c_rob;
+                for (int e = tid; e < h * A; e += NT) {
+                    const int i = e / A, aa = e - i * A;
+                    const double dl = ddiv(a.sizes[(k + i) * A + aa], c_rob);
+                    S.RB[e] = dl; S.DL[e] = dl;
+                    S.U[e] = a.util[(k + i) * A + aa];
+                }
+            }
+        }
+        // NOTE: status is identical in every thread of the session (all inputs are session-uniform).
+        if (WPS > 1) __syncthreads(); else __syncwarp();
+        SearchOut o; o.q = 0.0; o.idx = 0;
+        if (status == 0) {
+            const int i5 = h - 1;
+            for (int e = tid; e < A * A; e += NT) {
+                const int a5 = e / A, a4 = e - a5 * A;
+                S.AD[e] = fabs(dsub(S.U[i5 * A + a5], S.U[i5 * A + a4]));
+            }
+            if (WPS > 1) __syncthreads(); else __syncwarp();
+            if (h == 1) {
+                // single level: A leaves, thread 0 of the session scans them in order
+                double bq = __longlong_as_double(0xfff0000000000000ll);
+                int bi = 0x7fffffff;
+                if (tid == 0) {
+                    for (int a0 = 0; a0 < A; ++a0) {
+                        const double u = S.U[a0];
+                        const double qv = prev_q >= 0 ? fabs(dsub(u, S.U[prev_q])) : 0.0;
+                        const double d = dsub(S.RB[a0], buf0);
+                        const double rt = CLAMP ? max0(d) : d;
+                        // 0 + x is exact, so the running sums of mpc.py:146-152 reduce to the terms themselves
+                        const double q = dsub(dsub(u, dmul(p.smooth_penalty, qv)), dmul(p.rebuf_penalty, rt));
+                        if (q > bq) { bq = q; bi = a0; }
+                    }
+                }
+                o.q = bq; o.idx = bi;
+            } else {
+                o = search<AT, CLAMP>(S.U, S.RB, S.DL, S.AD, A, h, prev_q, buf0, p.smooth_penalty, p.rebuf_penalty, L, B,
+                                      tid, NT);
+            }
+            // ---- argmin over the session's threads: key (J, linear index) ----
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double oq = __shfl_xor_sync(0xffffffffu, o.q, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, o.idx, off);
+                better(o.q, o.idx, oq, oi);
+            }
+            if (WPS > 1) {
+                if (lane == 0) { S.redq[wis] = o.q; S.redi[wis] = o.idx; }
+                __syncthreads();
+                o.q = S.redq[0]; o.idx = S.redi[0];
+                for (int w = 1; w < WPS; ++w) better(o.q, o.idx, S.redq[w], S.redi[w]);
+            }
+        }
+        if (tid == 0) {
+            if (status == 0) {
+                int idx = o.idx == 0x7fffffff ? 0 : o.idx;   // all scores -inf/NaN: first sequence
+                int div = 1;
+                for (int i = 1; i < h; ++i) div *= A;
+                a.action[s] = idx / div;
+                if (a.best_j) a.best_j[s] = -o.q;
+                if (a.best_seq) {
+                    int rem = idx, d = div;
+                    for (int i = 0; i < H; ++i) {
+                        if (i < h) { a.best_seq[s * H + i] = rem / d; rem %= d; d = d > 1 ? d / A : 1; }
+                        else a.best_seq[s * H + i] = -1;
+                    }
+                }
+            } else {
+                a.action[s] = status == 1 ? act : -1;
+                if (a.best_j) a.best_j[s] = __longlong_as_double(0x7ff8000000000000ll);
+                if (a.best_seq) for (int i = 0; i < H; ++i) a.best_seq[s * H + i] = -1;
+                if (a.preds && status == 2) for (int i = 0; i < H; ++i) a.preds[s * H + i] = 0.0;
+                if (status == 2) {
+                    if (a.error_count64) atomicAdd(a.error_count64, 1ull);
+                    if (a.error_count32) atomicAdd(a.error_count32, 1);
+                }
+            }
+        }
+        if (WPS > 1) __syncthreads(); else __syncwarp();  // tables are reused by the next session of this slot
+    }
+}
+
+// ---- objective() of given sequences (mpc.py:120-162): one thread per sequence, each rolled out independently
+//      from scratch exactly like the reference does.  Used by MPCBitrateController.objective and by the parity
+//      tests that compare the whole score grid against the reference's. ----
+__global__ void __launch_bounds__(128)
+abr_mpc_score_kernel(const double* __restrict__ sizes, const double* __restrict__ util, int V, int A, AbrParams p,
+                     int k, int prev_q, double buffer, const double* __restrict__ hist, int n, int H, int mode,
+                     double max_err, const int32_t* __restrict__ seqs, int M, double* __restrict__ scores) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double L = p.chunk_length, B = p.max_buffer;
+    double S = 0.0;
+    for (int j = 0; j < n; ++j) S = dadd(S, ddiv(1.0, hist[j]));
+    const double c = mode == ABR_MPC_ROBUST ? ddiv(ddiv((double)n, S), dadd(1.0, max_err)) : 0.0;
+    double vq = 0.0, qv = 0.0, rt = 0.0, b = buffer;
+    int ap = prev_q;
+    for (int i = 0; i < H; ++i) {
+        const int a = seqs[(size_t)m * H + i];
+        double pi = c;
+        if (mode == ABR_MPC_REF) { pi = ddiv((double)(n + i), S); S = dadd(S, ddiv(1.0, pi)); }
+        const double u = util[(k + i) * A + a];
+        vq = dadd(vq, u);
+        if (ap >= 0) qv = dadd(qv, fabs(dsub(u, util[(k + i) * A + ap])));
+        double d, dl;
+        if (mode == ABR_MPC_REF) {
+            const double sz = sizes[(k + i) * A + a];
+            double mx = sz > 0.0 ? sz : 0.0;
+            if (L > mx) mx = L;
+            d = dsub(ddiv(mx, pi), b);
+            dl = ddiv(sizes[k * A + a], pi);
+        } else {
+            dl = ddiv(sizes[(k + i) * A + a], pi);
+            d = max0(dsub(dl, b));
+        }
+        rt = dadd(rt, d);
+        if (i != H - 1) {
+            const double t = max0(dsub(b, dl));
+            const double tl = dadd(t, L);
+            const double w = max0(dsub(tl, B));
+            b = max0(dsub(tl, w));
+        }
+        ap = a;
+    }
+    scores[m] = -dsub(dsub(vq, dmul(p.smooth_penalty, qv)), dmul(p.rebuf_penalty, rt));
+}
+
+// ---- FP64 issue-rate probe (roofline denominator of the MPC kernel) ----
+template <int KIND>
+__global__ void __launch_bounds__(256) abr_fp64_probe_kernel(int iters, double* sink) {
+    double x0 = 1.0 + threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3;
+    double x4 = x0 + 4e-3, x5 = x0 + 5e-3, x6 = x0 + 6e-3, x7 = x0 + 7e-3;
+    const double c = 1.0000001, d = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (KIND == 0) {        // 8 independent DADD chains
+                x0 = dadd(x0, d); x1 = dadd(x1, d); x2 = dadd(x2, d); x3 = dadd(x3, d);
+                x4 = dadd(x4, d); x5 = dadd(x5, d); x6 = dadd(x6, d); x7 = dadd(x7, d);
+            } else if (KIND == 1) { // 8 independent DFMA chains
+                x0 = __fma_rn(x0, c, d); x1 = __fma_rn(x1, c, d); x2 = __fma_rn(x2, c, d); x3 = __fma_rn(x3, c, d);
+                x4 = __fma_rn(x4, c, d); x5 = __fma_rn(x5, c, d); x6 = __fma_rn(x6, c, d); x7 = __fma_rn(x7, c, d);
+            } else {                // DADD + DMUL + compare/select mix (4 + 2 + 2 fp64-pipe ops)
+                x0 = dadd(x0, d); x1 = dmul(x1, c); x2 = dadd(x2, x0); x3 = dadd(x3, d);
+                x4 = dmul(x4, c); x5 = dadd(x5, d);
+                if (x2 > x6) x6 = x2;
+                if (x3 > x7) x7 = x3;
+            }
+        }
+    }
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace
+
+cudaError_t launch_mpc(const MpcArgs& a, cudaStream_t st) {
+    if (a.N <= 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // threads per session: one warp when there are enough sessions to fill the GPU, otherwise a whole block
+    long long combos = 1;
+    for (int i = 0; i < a.H; ++i) combos *= a.A;
+    const long long warps_needed_full = (long long)sms * 16;
+    const int wps = (a.N >= warps_needed_full || combos < 32 * 36 * 4) ? 1 : kMpcWarpsPerBlock;
+    const int spb = kMpcWarpsPerBlock / wps;
+    long long blocks = (a.N + spb - 1) / spb;
+    const long long max_blocks = (long long)sms * 64;
+    if (blocks > max_blocks) blocks = max_blocks;
+    const bool clamp = a.mode == ABR_MPC_ROBUST;
+    const unsigned g = (unsigned)blocks, t = 32 * kMpcWarpsPerBlock;
+#define ABR_MPC_LAUNCH(AT_)                                                                        \
+    do {                                                                                           \
+        if (wps == 1) {                                                                            \
+            if (clamp) abr_mpc_kernel<1, AT_, true><<<g, t, 0, st>>>(a);                           \
+            else abr_mpc_kernel<1, AT_, false><<<g, t, 0, st>>>(a);                                \
+        } else {                                                                                   \
+            if (clamp) abr_mpc_kernel<kMpcWarpsPerBlock, AT_, true><<<g, t, 0, st>>>(a);           \
+            else abr_mpc_kernel<kMpcWarpsPerBlock, AT_, false><<<g, t, 0, st>>>(a);                \
+        }                                                                                          \
+    } while (0)
+    switch (a.A) {
+        case 2: ABR_MPC_LAUNCH(2); break;
+        case 3: ABR_MPC_LAUNCH(3); break;
+        case 4: ABR_MPC_LAUNCH(4); break;
+        case 5: ABR_MPC_LAUNCH(5); break;
+        case 6: ABR_MPC_LAUNCH(6); break;
+        case 8: ABR_MPC_LAUNCH(8); break;
+        default: ABR_MPC_LAUNCH(0); break;
+    }
+#undef ABR_MPC_LAUNCH
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mpc_score(const double* d_sizes, const double* d_util, int V, int A, const AbrParams& p, int k,
+                             int prev_q, double buffer, const double* d_hist, int n, int H, int mode, double max_err,
+                             const int32_t* d_seqs, int M, double* d_scores, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    abr_mpc_score_kernel<<<(M + 127) / 128, 128, 0, st>>>(d_sizes, d_util, V, A, p, k, prev_q, buffer, d_hist, n, H,
+                                                          mode, max_err, d_seqs, M, d_scores);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_probe(int kind, int iters, double* d_sink, int* threads_total, long long* ops_per_thread,
+                              cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256;
+    *threads_total = blocks * threads;
+    *ops_per_thread = (long long)iters * 64;
+    switch (kind) {
+        case 0: abr_fp64_probe_kernel<0><<<blocks, threads, 0, st>>>(iters, d_sink); break;
+        case 1: abr_fp64_probe_kernel<1><<<blocks, threads, 0, st>>>(iters, d_sink); break;
+        case 2: abr_fp64_probe_kernel<2><<<blocks, threads, 0, st>>>(iters, d_sink); break;
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace abr

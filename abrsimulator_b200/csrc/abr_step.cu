@@ -1,0 +1,354 @@
+// Chunk-step kernels (SPEC.md §2-§4, §6): one thread per session.
+//
+// Replaces the per-session fixed-dt Python loop of the reference (Simulator.py:135-208: download block
+// :152-170, playback/buffer block :137-140,174-202, pause gate :143-145) with an analytic walk over the
+// square-wave trace segments (NetworkInfo, Simulator.py:37-42).
+//
+//  * abr_step_kernel     one chunk step per launch, SoA state in HBM (RL harness form).  HBM-bound:
+//                        36 B read + 28 B state write + 41 B outputs per session-step.
+//  * abr_rollout_kernel  `steps` chunk steps per launch with the state in registers and the trajectory
+//                        streamed out with st.global.cs (41 B/step) — the fused-episode form.
+//  * abr_reset_kernel, abr_stats_* helpers.
+//
+// Trace bandwidths are read through the read-only path (ld.global.nc): a session re-reads consecutive
+// segments of one trace, so one 128 B line (16 segments) serves ~16 walk iterations out of L1, and the
+// whole trace table (<= 16 MB at the benchmark shape) stays resident in the 126 MB L2.
+#include "abr_common.cuh"
+
+namespace abr {
+
+namespace {
+
+constexpr int kStepBlock = 256;
+constexpr int kRolloutBlock = 128;
+constexpr int kStatsBlock = 256;
+constexpr int kStatsSessionsPerBlock = 8192;
+
+struct Sess {
+    const double* __restrict__ bw;
+    double I, tau, buffer;
+    int T, seg, chunk, last_q, hist_len;
+    bool done;
+};
+
+struct StepRes {
+    double delay, sleep, buffer, rebuf, reward, thr, u, smooth;
+    bool eov, inert, walk_error, reset_mpc;
+};
+
+// SPEC §3 for one session held in registers.  `q` must already be a valid index.
+__device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, StepRes& r) {
+    const AbrParams& p = v.p;
+    r.walk_error = false;
+    r.reset_mpc = false;
+    if (s.done) {  // only reachable with auto_reset == 0
+        r.delay = r.sleep = r.rebuf = r.reward = r.thr = r.u = r.smooth = 0.0;
+        r.buffer = s.buffer;
+        r.eov = true;
+        r.inert = true;
+        return;
+    }
+    r.inert = false;
+    const int A = v.A;
+    const double size = __ldg(v.sizes + s.chunk * A + q);
+    // 3.1 segment walk (Simulator.py:158-163 in closed form, with wrap-around)
+    double sent = 0.0, delay = 0.0, tau = s.tau;
+    int seg = s.seg;
+    int guard = 1 << 20;  // safety net only: every bandwidth is > 0, so the walk terminates
+    double bwv = __ldg(s.bw + seg);
+    for (;;) {
+        const double rate = dmul(bwv, p.payload);
+        const double room = dsub(s.I, tau);
+        const double cap = dmul(rate, room);
+        if (dadd(sent, cap) >= size) {
+            const double dt = ddiv(dsub(size, sent), rate);
+            delay = dadd(delay, dt);
+            tau = dadd(tau, dt);
+            break;
+        }
+        sent = dadd(sent, cap);
+        delay = dadd(delay, room);
+        seg = (seg + 1 == s.T) ? 0 : seg + 1;
+        tau = 0.0;
+        bwv = __ldg(s.bw + seg);
+        if (--guard <= 0) { r.walk_error = true; break; }
+    }
+    delay = dadd(delay, p.rtt);
+    r.thr = ddiv(size, delay);
+    // 3.2 buffer drain / rebuffer
+    const double rebuf = max0(dsub(delay, s.buffer));
+    double buffer = dadd(max0(dsub(s.buffer, delay)), p.chunk_length);
+    // 3.3 sleep cap
+    double sleep = 0.0;
+    if (buffer > p.max_buffer) {
+        sleep = dmul(ceil(ddiv(dsub(buffer, p.max_buffer), p.sleep_quantum)), p.sleep_quantum);
+        buffer = dsub(buffer, sleep);
+        const double x = dadd(tau, sleep);
+        const double n = floor(ddiv(x, s.I));
+        tau = dsub(x, dmul(n, s.I));
+        seg = (int)(((long long)seg + (long long)n) % (long long)s.T);
+        if (tau < 0.0) tau = 0.0;
+        if (tau >= s.I) { tau = 0.0; seg = (seg + 1 == s.T) ? 0 : seg + 1; }
+    }
+    // 3.4 reward
+    const double u = __ldg(v.util + s.chunk * A + q);
+    const double smooth = (s.last_q >= 0) ? fabs(dsub(u, __ldg(v.util + s.chunk * A + s.last_q))) : 0.0;
+    r.reward = dsub(dsub(u, dmul(p.rebuf_penalty, rebuf)), dmul(p.smooth_penalty, smooth));
+    r.delay = delay; r.sleep = sleep; r.buffer = buffer; r.rebuf = rebuf; r.u = u; r.smooth = smooth;
+    // 3.5 advance
+    s.hist_len += 1;
+    s.last_q = q;
+    s.chunk += 1;
+    s.seg = seg;
+    s.tau = tau;
+    s.buffer = buffer;
+    r.eov = (s.chunk >= v.V);
+    if (r.eov) {
+        if (p.auto_reset) {
+            s.chunk = 0; s.buffer = 0.0; s.last_q = p.default_quality; s.hist_len = 0;
+            r.reset_mpc = true;
+        } else {
+            s.done = true;
+        }
+    }
+}
+
+__device__ __forceinline__ int policy_action(const EnvView& v, const Sess& s, int policy, uint32_t seed_lo,
+                                             uint32_t seed_hi, unsigned long long gsession, int step,
+                                             const int32_t* __restrict__ actions_in, int sidx) {
+    const int A = v.A;
+    if (policy == ABR_POLICY_FIXED) return __ldg(actions_in + (size_t)step * v.n + sidx);
+    if (policy == ABR_POLICY_RANDOM) {
+        const uint32_t x = philox_first((uint32_t)gsession, (uint32_t)(gsession >> 32), (uint32_t)step, 0u, seed_lo,
+                                        seed_hi);
+        return (int)__umulhi(x, (uint32_t)A);
+    }
+    const double b = s.buffer;  // BBA
+    if (b < v.p.bba_reservoir) return 0;
+    if (b >= dadd(v.p.bba_reservoir, v.p.bba_cushion)) return A - 1;
+    const int q = (int)floor(ddiv(dmul((double)(A - 1), dsub(b, v.p.bba_reservoir)), v.p.bba_cushion));
+    return q > A - 1 ? A - 1 : q;
+}
+
+__device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
+    const int tr = v.trace_id[i];
+    s.bw = v.trace_bw + (size_t)tr * v.T_max;
+    s.T = __ldg(v.trace_len + tr);
+    s.I = __ldg(v.trace_interval + tr);
+    s.seg = v.seg[i];
+    s.chunk = v.chunk[i];
+    s.last_q = v.last_q[i];
+    s.tau = v.tau[i];
+    s.buffer = v.buffer[i];
+    s.done = v.p.auto_reset ? false : (v.done[i] != 0);
+    s.hist_len = v.p.track_history ? v.hist_len[i] : 0;
+}
+
+__global__ void __launch_bounds__(kStepBlock)
+abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* __restrict__ start_offset) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    int tr = trace_id[i];
+    if (tr < 0 || tr >= v.n_traces) { atomicAdd(v.errors, 1ull); tr = 0; }
+    const int T = v.trace_len[tr];
+    const double I = v.trace_interval[tr];
+    const double off = start_offset ? start_offset[i] : 0.0;
+    const double n = floor(ddiv(off, I));
+    int seg = (int)fmod(n, (double)T);
+    double tau = dsub(off, dmul(n, I));
+    if (tau < 0.0) tau = 0.0;
+    if (tau >= I) { tau = 0.0; seg = (seg + 1 == T) ? 0 : seg + 1; }
+    if (seg < 0 || seg >= T) { atomicAdd(v.errors, 1ull); seg = 0; }
+    v.trace_id[i] = tr; v.seg[i] = seg; v.tau[i] = tau; v.buffer[i] = 0.0; v.chunk[i] = 0;
+    v.last_q[i] = v.p.default_quality; v.done[i] = 0; v.hist_len[i] = 0; v.last_pred[i] = 0.0; v.err_len[i] = 0;
+#pragma unroll
+    for (int j = 0; j < ABR_NUM_ACC; ++j) v.acc[(size_t)j * v.cap + i] = 0.0;
+}
+
+__global__ void __launch_bounds__(kStepBlock)
+abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restrict__ o_delay,
+                double* __restrict__ o_sleep, double* __restrict__ o_buffer, double* __restrict__ o_rebuf,
+                double* __restrict__ o_reward, double* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov,
+                double* __restrict__ o_thr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    Sess s;
+    load_sess(v, i, s);
+    int q = action[i];
+    if (q < 0 || q >= v.A) { atomicAdd(v.errors, 1ull); q = q < 0 ? 0 : v.A - 1; }
+    StepRes r;
+    step_core(v, s, q, r);
+    if (r.walk_error) atomicAdd(v.errors, 1ull);
+    if (!r.inert) {
+        v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
+        if (v.p.track_history) {
+            // ring slot of this sample = (hist_len before the step) mod K; after an auto-reset hist_len is 0
+            const int prev_len = r.reset_mpc ? 0 : s.hist_len - 1;
+            if (!r.reset_mpc) v.bw_hist[(size_t)(prev_len % v.K) * v.cap + i] = r.thr;
+            v.hist_len[i] = s.hist_len;
+        }
+        if (r.reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
+        if (s.done) v.done[i] = 1;
+        if (v.p.track_acc) {
+            double* a = v.acc + i;
+            const size_t c = v.cap;
+            a[0 * c] = dadd(a[0 * c], r.reward); a[1 * c] = dadd(a[1 * c], r.rebuf); a[2 * c] = dadd(a[2 * c], r.u);
+            a[3 * c] = dadd(a[3 * c], r.smooth); a[4 * c] = dadd(a[4 * c], r.sleep); a[5 * c] = dadd(a[5 * c], r.delay);
+            a[6 * c] = dadd(a[6 * c], 1.0);
+            if (r.eov) a[7 * c] = dadd(a[7 * c], 1.0);
+        }
+    }
+    if (o_delay) __stcs(o_delay + i, r.delay);
+    if (o_sleep) __stcs(o_sleep + i, r.sleep);
+    if (o_buffer) __stcs(o_buffer + i, r.buffer);
+    if (o_rebuf) __stcs(o_rebuf + i, r.rebuf);
+    if (o_reward) __stcs(o_reward + i, r.reward);
+    if (o_eov) o_eov[i] = r.eov ? 1 : 0;
+    if (o_thr) __stcs(o_thr + i, r.thr);
+    if (o_next_sizes) {
+        const int A = v.A;
+        for (int a = 0; a < A; ++a)
+            o_next_sizes[(size_t)i * A + a] = s.done ? 0.0 : __ldg(v.sizes + s.chunk * A + a);
+    }
+}
+
+template <int POLICY>
+__global__ void __launch_bounds__(kRolloutBlock)
+abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
+                   double* __restrict__ o_delay, double* __restrict__ o_sleep, double* __restrict__ o_buffer,
+                   double* __restrict__ o_rebuf, double* __restrict__ o_reward, uint8_t* __restrict__ o_eov,
+                   int32_t* __restrict__ o_actions) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    Sess s;
+    load_sess(v, i, s);
+    const unsigned long long gsession = (unsigned long long)(v.session_base + i);
+    double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_steps = 0.0, a_eps = 0.0;
+    bool flagged = false, reset_mpc = false;
+    const int n = v.n;
+    for (int t = 0; t < steps; ++t) {
+        int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t, actions_in, i);
+        if (q < 0 || q >= v.A) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
+        StepRes r;
+        step_core(v, s, q, r);
+        flagged |= r.walk_error;
+        const size_t ix = (size_t)t * n + i;
+        if (o_delay) __stcs(o_delay + ix, r.delay);
+        if (o_sleep) __stcs(o_sleep + ix, r.sleep);
+        if (o_buffer) __stcs(o_buffer + ix, r.buffer);
+        if (o_rebuf) __stcs(o_rebuf + ix, r.rebuf);
+        if (o_reward) __stcs(o_reward + ix, r.reward);
+        if (o_eov) o_eov[ix] = r.eov ? 1 : 0;
+        if (o_actions) __stcs(o_actions + ix, q);
+        if (!r.inert) {
+            a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
+            a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
+            a_steps += 1.0;
+            if (r.eov) a_eps += 1.0;
+            if (v.p.track_history) {
+                if (r.reset_mpc) reset_mpc = true;
+                else v.bw_hist[(size_t)((s.hist_len - 1) % v.K) * v.cap + i] = r.thr;
+            }
+        }
+    }
+    if (flagged) atomicAdd(v.errors, 1ull);
+    v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
+    if (v.p.track_history) v.hist_len[i] = s.hist_len;
+    if (reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
+    if (s.done) v.done[i] = 1;
+    double* a = v.acc + i;
+    const size_t c = v.cap;
+    a[0 * c] = dadd(a[0 * c], a_rew); a[1 * c] = dadd(a[1 * c], a_reb); a[2 * c] = dadd(a[2 * c], a_u);
+    a[3 * c] = dadd(a[3 * c], a_sm); a[4 * c] = dadd(a[4 * c], a_sl); a[5 * c] = dadd(a[5 * c], a_dl);
+    a[6 * c] = dadd(a[6 * c], a_steps); a[7 * c] = dadd(a[7 * c], a_eps);
+}
+
+// ---- statistics: deterministic two-stage reduction of acc[ABR_NUM_ACC][n] (SPEC §6) ----
+__device__ __forceinline__ double block_sum(double x, double* sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = dadd(x, __shfl_down_sync(0xffffffffu, x, o));
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sm[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        x = (l < (int)(blockDim.x >> 5)) ? sm[l] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x = dadd(x, __shfl_down_sync(0xffffffffu, x, o));
+    }
+    return x;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kStatsBlock)
+abr_stats_stage1(EnvView v, double* __restrict__ partials) {
+    __shared__ double sm[32];
+    const int lo = blockIdx.x * kStatsSessionsPerBlock;
+    const int hi = min(v.n, lo + kStatsSessionsPerBlock);
+    for (int j = 0; j < ABR_NUM_ACC; ++j) {
+        double x = 0.0;
+        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) x = dadd(x, v.acc[(size_t)j * v.cap + i]);
+        x = block_sum(x, sm);
+        if (threadIdx.x == 0) partials[(size_t)blockIdx.x * ABR_NUM_ACC + j] = x;
+    }
+}
+
+__global__ void __launch_bounds__(kStatsBlock)
+abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __restrict__ out) {
+    __shared__ double sm[32];
+    for (int j = 0; j < ABR_NUM_ACC; ++j) {
+        double x = 0.0;
+        for (int i = threadIdx.x; i < n_partials; i += blockDim.x) x = dadd(x, partials[(size_t)i * ABR_NUM_ACC + j]);
+        x = block_sum(x, sm);
+        if (threadIdx.x == 0) out[j] = x;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st) {
+    if (v.n == 0) return cudaSuccess;
+    abr_reset_kernel<<<(v.n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_trace_id, d_start_offset);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step(const EnvView& v, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
+                        double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_eov, double* d_thr,
+                        cudaStream_t st) {
+    if (v.n == 0) return cudaSuccess;
+    abr_step_kernel<<<(v.n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(
+        v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_next_sizes, d_eov, d_thr);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                           double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
+                           uint8_t* d_eov, int32_t* d_actions_out, cudaStream_t st) {
+    if (v.n == 0 || steps <= 0) return cudaSuccess;
+    const dim3 grid((v.n + kRolloutBlock - 1) / kRolloutBlock), block(kRolloutBlock);
+    const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+#define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
+    abr_rollout_kernel<P><<<grid, block, 0, st>>>(v, lo, hi, steps, d_actions_in, d_delay, d_sleep, d_buffer,       \
+                                                  d_rebuf, d_reward, d_eov, d_actions_out)
+    switch (policy) {
+        case ABR_POLICY_FIXED: ABR_LAUNCH_ROLLOUT(ABR_POLICY_FIXED); break;
+        case ABR_POLICY_RANDOM: ABR_LAUNCH_ROLLOUT(ABR_POLICY_RANDOM); break;
+        case ABR_POLICY_BBA: ABR_LAUNCH_ROLLOUT(ABR_POLICY_BBA); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef ABR_LAUNCH_ROLLOUT
+    count_launch();
+    return cudaGetLastError();
+}
+
+int stats_num_partials(int n) { return n <= 0 ? 1 : (n + kStatsSessionsPerBlock - 1) / kStatsSessionsPerBlock; }
+
+cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, double* d_out, cudaStream_t st) {
+    abr_stats_stage1<<<n_partials, kStatsBlock, 0, st>>>(v, d_partials);
+    abr_stats_stage2<<<1, kStatsBlock, 0, st>>>(d_partials, n_partials, d_out);
+    count_launch(2);
+    return cudaGetLastError();
+}
+
+}  // namespace abr

@@ -1,0 +1,41 @@
+"""Multi-GPU sharding: sessions are independent, so ranks own contiguous blocks and never exchange
+data while stepping; the only collective is the final QoE/statistics reduction (SPEC.md §6).
+
+The per-rank statistic vectors are all-gathered and summed in rank order on every rank, so the
+result is bit-reproducible run to run (an fp64 SUM inside NCCL's ring/tree has no fixed order).
+Works with NCCL (one process per GPU over NVLink) and gloo (CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of rank; the first n_total % world ranks own one extra session."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum a per-rank statistics vector over all ranks, deterministically (rank order)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats.clone()
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(parts, stats.contiguous(), group=group)
+    total = parts[0].clone()
+    for p in parts[1:]:
+        total += p
+    return total
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    """Max of a scalar (e.g. elapsed milliseconds) over ranks."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

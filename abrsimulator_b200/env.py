@@ -1,0 +1,283 @@
+"""Batched ABR environment: N independent streaming sessions stepped on one B200.
+
+Host-side mirror of the reference's environment API (``Simulator.py:45-210``): construct from
+bandwidth traces and per-bitrate chunk sizes, step with a bitrate index, get back download delay /
+sleep / buffer / rebuffer / reward / next-chunk sizes / end-of-video.  All arithmetic happens in
+the sm_100a kernels behind the C-ABI of ``include/abr_b200.h`` (semantics: SPEC.md); PyTorch is
+used only for device memory and streams.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (AbrError, MPC_REF, MPC_ROBUST, NUM_ACC, NUM_STATS, POLICY_BBA, POLICY_FIXED,  # noqa: F401
+                   POLICY_RANDOM)
+from .datamodel import MPD, NetworkInfo, QOEMetric, pack_traces
+
+StepResult = namedtuple("StepResult", "delay sleep buffer rebuffer reward next_sizes end_of_video throughput")
+
+_POLICIES = {"fixed": POLICY_FIXED, "random": POLICY_RANDOM, "bba": POLICY_BBA, "buffer": POLICY_BBA}
+_MODES = {"reference": MPC_REF, "ref": MPC_REF, "robust": MPC_ROBUST}
+
+
+def _policy_id(policy):
+    if isinstance(policy, str):
+        return _POLICIES[policy]
+    return int(policy)
+
+
+def _mode_id(mode):
+    if isinstance(mode, str):
+        return _MODES[mode]
+    return int(mode)
+
+
+class _DevPtr:
+    """Minimal __cuda_array_interface__ holder so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr, strides=None):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False),
+                                             version=3, strides=strides)
+
+
+_TYPESTR = {"int32": "<i4", "uint8": "|u1", "float64": "<f8"}
+_ITEMSIZE = {"int32": 4, "uint8": 1, "float64": 8}
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class BatchedABREnv:
+    """N sessions over shared trace / video tables.
+
+    Parameters
+    ----------
+    trace_bw : [n_traces, T_max] float64 (host) — bandwidth per segment, same units as sizes/second
+    trace_len : [n_traces] int (default: T_max for every trace)
+    trace_interval : scalar or [n_traces] — segment duration in seconds (``NetworkInfo.interval``)
+    sizes, bitrates : [V, A] float64 — per-chunk payload and ladder (``Chunk.sizes`` / ``Chunk.bitrates``)
+    max_sessions : capacity of the SoA state
+    **params : fields of ``AbrParams`` (chunk_length, max_buffer, rtt, payload, ...)
+    """
+
+    def __init__(self, trace_bw, sizes, bitrates, max_sessions, trace_len=None, trace_interval=1.0,
+                 device=None, **params):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedABREnv needs a CUDA device (B200); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._lib = _lib.load()
+        bw = np.ascontiguousarray(trace_bw, dtype=np.float64)
+        if bw.ndim == 1:
+            bw = bw[None, :]
+        self.n_traces, self.T_max = bw.shape
+        tl = np.full(self.n_traces, self.T_max, np.int32) if trace_len is None else \
+            np.ascontiguousarray(trace_len, dtype=np.int32)
+        ti = np.ascontiguousarray(np.broadcast_to(np.asarray(trace_interval, dtype=np.float64), (self.n_traces,)))
+        sz = np.ascontiguousarray(sizes, dtype=np.float64)
+        br = np.ascontiguousarray(bitrates, dtype=np.float64)
+        if sz.shape != br.shape or sz.ndim != 2:
+            raise ValueError("sizes and bitrates must both be [V, A]")
+        self.V, self.A = sz.shape
+        self.params = _lib.default_params(**params)
+        self.K = int(self.params.hist_k)
+        self.capacity = int(max_sessions)
+        self.n = 0
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.abr_env_create(
+                bw.ctypes.data_as(C.c_void_p), tl.ctypes.data_as(C.c_void_p), ti.ctypes.data_as(C.c_void_p),
+                C.c_int(self.n_traces), C.c_int(self.T_max), sz.ctypes.data_as(C.c_void_p),
+                br.ctypes.data_as(C.c_void_p), C.c_int(self.V), C.c_int(self.A), C.byref(self.params),
+                C.c_int(self.capacity), C.byref(self._h)))
+        self._stats = torch.empty(NUM_STATS, dtype=torch.float64, device=self.device)
+
+    # -- construction from the reference's objects (Simulator.set_network_info / set_mpd / set_qoe_metric) --
+    @classmethod
+    def from_objects(cls, network_infos, mpd: MPD, qoe: QOEMetric = None, max_sessions=1, **params):
+        if isinstance(network_infos, NetworkInfo):
+            network_infos = [network_infos]
+        bw, tl, ti = pack_traces(network_infos)
+        bitrates, sizes = mpd.tables()
+        kw = dict(chunk_length=float(mpd.chunk_length), max_buffer=float(mpd.max_buffer))
+        if qoe is not None:
+            kw.update(rebuf_penalty=float(qoe.rebuffer_weight), smooth_penalty=float(qoe.variance_weight))
+        kw.update(params)
+        return cls(bw, sizes, bitrates, max_sessions, trace_len=tl, trace_interval=ti, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.abr_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers --
+    def _dev(self, x, dtype):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(self.device)
+
+    def _empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    # -- SPEC §2 --
+    def reset(self, trace_id, start_offset=None, session_base=0):
+        tid = self._dev(trace_id, torch.int32)
+        off = None if start_offset is None else self._dev(start_offset, torch.float64)
+        n = tid.numel()
+        if off is not None and off.numel() != n:
+            raise ValueError("start_offset must have one entry per session")
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.abr_env_reset(self._h, _ptr(tid), _ptr(off), C.c_int(n), C.c_longlong(session_base),
+                                               _stream()))
+        self.n = n
+        self.session_base = int(session_base)
+
+    # -- SPEC §3 --
+    def step(self, action, want_next_sizes=True, want_throughput=False, out=None) -> StepResult:
+        """One chunk step for every session.  ``action``: int32 [N] on the device (or array-like)."""
+        a = self._dev(action, torch.int32)
+        if a.numel() != self.n:
+            raise ValueError(f"action has {a.numel()} entries for {self.n} sessions")
+        n = self.n
+        if out is None:
+            out = StepResult(self._empty(n), self._empty(n), self._empty(n), self._empty(n), self._empty(n),
+                             self._empty(n, self.A) if want_next_sizes else None,
+                             self._empty(n, dtype=torch.uint8),
+                             self._empty(n) if want_throughput else None)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.abr_env_step(self._h, _ptr(a), _ptr(out.delay), _ptr(out.sleep), _ptr(out.buffer),
+                                              _ptr(out.rebuffer), _ptr(out.reward), _ptr(out.next_sizes),
+                                              _ptr(out.end_of_video), _ptr(out.throughput), _stream()))
+        return out
+
+    # -- SPEC §3+§4 --
+    def rollout(self, policy, steps, seed=0, actions=None, want=("delay", "sleep", "buffer", "rebuffer", "reward",
+                                                                "end_of_video", "actions"), out=None):
+        """`steps` chunk steps in one fused launch.  Returns a dict of [steps, N] device tensors."""
+        pid = _policy_id(policy)
+        n = self.n
+        a_in = None
+        if pid == POLICY_FIXED:
+            if actions is None:
+                raise ValueError("policy 'fixed' needs an actions table [steps, N]")
+            a_in = self._dev(actions, torch.int32)
+            if a_in.numel() != steps * n:
+                raise ValueError("actions must be [steps, N]")
+        if out is None:
+            out = {}
+            for k in want:
+                dt = torch.uint8 if k == "end_of_video" else torch.int32 if k == "actions" else torch.float64
+                out[k] = self._empty(steps, n, dtype=dt)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.abr_env_rollout_fused(
+                self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), _ptr(a_in), _ptr(out.get("delay")),
+                _ptr(out.get("sleep")), _ptr(out.get("buffer")), _ptr(out.get("rebuffer")), _ptr(out.get("reward")),
+                _ptr(out.get("end_of_video")), _ptr(out.get("actions")), _stream()))
+        return out
+
+    # -- SPEC §5 --
+    def mpc_decide(self, horizon=5, mode="robust", want_score=False, out=None):
+        act = self._empty(self.n, dtype=torch.int32) if out is None else out
+        bj = self._empty(self.n) if want_score else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.abr_env_mpc_decide(self._h, C.c_int(horizon), C.c_int(_mode_id(mode)), _ptr(act),
+                                                    _ptr(bj), _stream()))
+        return (act, bj) if want_score else act
+
+    def mpc_episode(self, steps, horizon=5, mode="robust"):
+        """decide -> step for `steps` chunks (needs track_history=1, track_acc=1 for statistics)."""
+        act = self._empty(self.n, dtype=torch.int32)
+        for _ in range(steps):
+            self.mpc_decide(horizon, mode, out=act)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.abr_env_step(self._h, _ptr(act), None, None, None, None, None, None, None, None,
+                                                  _stream()))
+        return act
+
+    # -- SPEC §6 --
+    def stats(self) -> torch.Tensor:
+        """[Σreward, Σrebuffer, Σutility, Σsmooth, Σsleep, Σdelay, steps, episodes] over this env's sessions."""
+        out = torch.empty(NUM_STATS, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.abr_stats_partial(self._h, _ptr(out), _stream()))
+        return out
+
+    def state(self, name) -> torch.Tensor:
+        """Zero-copy view of a state field (library-owned device memory)."""
+        fid, dt = _lib.FIELDS[name]
+        p = C.c_void_p()
+        _lib.check(self._lib.abr_env_state_ptr(self._h, C.c_int(fid), C.byref(p)))
+        cap = self.capacity
+        if name in ("bw_hist", "err_ring"):
+            shape = (self.K, cap)
+        elif name == "acc":
+            shape = (NUM_ACC, cap)
+        elif name in ("sizes", "utility"):
+            shape = (self.V, self.A)
+        elif name == "trace_bw":
+            shape = (self.n_traces, self.T_max)
+        else:
+            shape = (cap,)
+        t = torch.as_tensor(_DevPtr(p.value, shape, _TYPESTR[dt]), device=self.device)
+        if name in ("bw_hist", "err_ring", "acc"):
+            return t[:, :self.n]
+        if name in ("sizes", "utility", "trace_bw"):
+            return t
+        return t[:self.n]
+
+    def session_acc(self) -> torch.Tensor:
+        """[8, N] per-session sums (rows: reward, rebuffer, utility, smooth, sleep, delay, steps, episodes)."""
+        return self.state("acc")
+
+    def error_count(self) -> int:
+        out = C.c_longlong(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.abr_env_error_count(self._h, C.byref(out), _stream()))
+        return int(out.value)
+
+    # -- host-buffer path (what Simulator.run() uses; e2e benchmark leg) --
+    def run_host(self, policy, steps, trace_id, start_offset=None, seed=0, session_base=0, actions=None,
+                 want_acc=True, want_stats=True, want_reward_traj=False, out=None):
+        """Reset + fused episode + statistics with HOST (numpy) inputs and outputs.
+        Returns dict(acc=[8,N], stats=[8], reward=[steps,N])."""
+        pid = _policy_id(policy)
+        tid = np.ascontiguousarray(trace_id, dtype=np.int32)
+        n = tid.size
+        off = None if start_offset is None else np.ascontiguousarray(start_offset, dtype=np.float64)
+        a_in = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
+        out = {} if out is None else out
+        if want_acc and "acc" not in out:
+            out["acc"] = np.empty((NUM_ACC, n))
+        if want_stats and "stats" not in out:
+            out["stats"] = np.empty(NUM_STATS)
+        if want_reward_traj and "reward" not in out:
+            out["reward"] = np.empty((steps, n))
+
+        def hp(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.abr_env_run_host(
+                self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), hp(tid), hp(off), C.c_int(n),
+                C.c_longlong(session_base), hp(a_in), hp(out.get("acc")), hp(out.get("stats")), hp(out.get("reward")),
+                _stream()))
+        self.n = n
+        self.session_base = int(session_base)
+        return out

@@ -1,0 +1,464 @@
+#!/usr/bin/env python
+"""bench.py — ABR chunk-steps/s (headline) and MPC decisions/s on N B200s, beside the CPU reference path.
+
+Contract: ``python bench.py --gpus N --steps K --warmup W`` (under torchrun for N > 1) prints ONE JSON line on
+rank 0.  A "step" is one pass of the hot path over one batch: reset + one fused 48-chunk episode of
+``--sessions`` sessions per GPU (BASELINE.json configs[1]: random-policy chunk-step sweep, 65 536 sessions x 48
+chunks on synthetic traces) + the statistics reduction.  Sessions shard across GPUs with no data-path
+collective (weak scaling); the only collective is the final statistics all-gather.
+
+``--impl reference`` times the reference's CPU path instead: the reference is pure Python and cannot travel to
+the GPU box, so this runs the pure-Python port in ``oracle/`` (statement-level restatement, pinned to the
+reference by tests/golden) on all host cores over a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V, A = 48, 6
+N_TRACES, T_TRACE = 1024, 2048
+SEED = 7
+BYTES_PER_STEP = 5 * 8 + 1          # delay, sleep, buffer, rebuf, reward (f64) + end_of_video (u8)
+BYTES_PER_SESSION = 32 + 28 + 128   # state load + state store + accumulator read-modify-write, once per episode
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sessions", type=int, default=65536, help="sessions per GPU (configs[1])")
+    ap.add_argument("--mpc-sessions", type=int, default=131072, help="MPC sessions per GPU (configs[2] / 8)")
+    ap.add_argument("--mpc-horizon", type=int, default=5)
+    ap.add_argument("--no-mpc", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of each cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port) — the only places bench.py executes oracle/
+# ------------------------------------------------------------------------------------------------
+def _py_step_worker(job):
+    """Pure-Python port of the chunk step (oracle/step_oracle.py) over a block of sessions."""
+    import numpy as np
+    from abrsimulator_b200 import synth
+    from oracle import oracle as orc, step_oracle as so
+    lo, hi, budget_s = job
+    bitrates, sizes = synth.make_video(V)
+    bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
+    tid, off = synth.make_sessions(hi - lo, N_TRACES, T_TRACE, session_base=lo)
+    P = dict(orc.DEFAULTS)
+    util = (bitrates * P["utility_scale"]).tolist()
+    sz = sizes.tolist()
+    t0 = time.perf_counter()
+    done_steps = 0
+    tot = 0.0
+    for s in range(hi - lo):
+        sess = so.Session(bw[tid[s]].tolist(), float(ti[tid[s]]), sz, util, P, float(off[s]))
+        g = lo + s
+        for t in range(V):
+            x0 = orc.philox(g & 0xffffffff, g >> 32, t, 0, SEED, 0)[0]
+            tot += sess.step((x0 * A) >> 32)["reward"]
+        done_steps += V
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done_steps, time.perf_counter() - t0, tot
+
+
+def cpu_python_steps(n_procs, budget_s, sessions_per_proc=100000):
+    import multiprocessing as mp
+    jobs = [(i * sessions_per_proc, (i + 1) * sessions_per_proc, budget_s) for i in range(n_procs)]
+    t0 = time.perf_counter()
+    if n_procs == 1:
+        res = [_py_step_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(n_procs) as pool:
+            res = pool.map(_py_step_worker, jobs)
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return steps / busy, steps, busy, wall
+
+
+def cpu_c_oracle_steps(n_sessions=8192):
+    import numpy as np
+    from abrsimulator_b200 import synth
+    from oracle import oracle as orc
+    bitrates, sizes = synth.make_video(V)
+    bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
+    tid, off = synth.make_sessions(n_sessions, N_TRACES, T_TRACE)
+    env = orc.OracleEnv(bw, tl, ti, sizes, bitrates, n_sessions)
+    env.reset(tid, off)
+    t0 = time.perf_counter()
+    env.rollout(orc.POLICY_RANDOM, V, seed=SEED, want_traj=True)
+    dt = time.perf_counter() - t0
+    return n_sessions * V / dt, n_sessions, dt
+
+
+def _py_mpc_worker(job):
+    import numpy as np
+    from abrsimulator_b200 import synth
+    from oracle import mpc_oracle as mo
+    idx0, count, H, budget_s = job
+    bitrates, sizes = synth.make_video(V)
+    util = (bitrates * 0.001).tolist()
+    sz = sizes.tolist()
+    rng = np.random.default_rng(1000 + idx0)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(count):
+        st = mo.RobustState(5)
+        hist = [float(x) for x in rng.uniform(0.2, 6.0, size=5)]
+        mo.decide_robust(int(rng.integers(0, V - H)), int(rng.integers(0, A)), float(rng.uniform(0, 30)), hist, st, H,
+                         util, sz, 4.0, 60.0, 1.0, 4.3)
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return n, time.perf_counter() - t0
+
+
+def cpu_python_mpc(n_procs, H, budget_s):
+    import multiprocessing as mp
+    jobs = [(i, 100000, H, budget_s) for i in range(n_procs)]
+    if n_procs == 1:
+        res = [_py_mpc_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(n_procs) as pool:
+            res = pool.map(_py_mpc_worker, jobs)
+    n = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return n / busy, n, busy
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step_budget = max(1.0, min(6.0, 60.0 / max(1, args.steps + args.warmup)))
+    rates = []
+    for i in range(args.warmup + args.steps):
+        rate, steps, busy, wall = cpu_python_steps(cores, per_step_budget)
+        if i >= args.warmup:
+            rates.append((rate, steps, busy))
+    tot_steps = sum(r[1] for r in rates)
+    tot_busy = sum(r[2] for r in rates)
+    value = tot_steps / tot_busy
+    sample = (f"pure-Python port of the chunk step (oracle/step_oracle.py; the reference's own loop does not run, "
+              f"SURVEY D1-D6) on {cores} processes, ~{per_step_budget:.1f} s of sessions x 48 chunks per step, "
+              f"{tot_steps} chunk-steps in total")
+    line = dict(impl="reference", metric="chunk_steps_per_sec", value=value, unit="chunk-steps/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * tot_busy / max(1, args.steps),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=workload_config(args),
+                cpu_baseline=dict(value=value, unit="chunk-steps/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="chunk-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    if not args.no_mpc:
+        r, n, busy = cpu_python_mpc(cores, args.mpc_horizon, min(10.0, args.cpu_seconds))
+        line["mpc"] = dict(metric="mpc_decisions_per_sec", value=r, unit="decisions/s", horizon=args.mpc_horizon,
+                           cores=cores, sample=f"{n} robust-MPC decisions (oracle/mpc_oracle.py port of mpc.py)")
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return dict(workload="configs[1]: random-policy chunk-step sweep, fused 48-chunk episodes",
+                sessions_per_gpu=args.sessions, chunks=V, bitrates=A, n_traces=N_TRACES, trace_segments=T_TRACE,
+                policy="random(philox)", outputs="delay,sleep,buffer,rebuffer,reward,end_of_video",
+                l2="256 MiB buffer rewritten between timed steps (outside the timed region)")
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from abrsimulator_b200 import synth, _lib
+    from abrsimulator_b200.env import BatchedABREnv
+    from abrsimulator_b200.distributed import allreduce_stats, max_over_ranks
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    N = args.sessions
+    base = rank * N
+    bitrates, sizes = synth.make_video(V)
+    bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
+    tid_h, off_h = synth.make_sessions(N, N_TRACES, T_TRACE, session_base=base)
+    env = BatchedABREnv(bw, sizes, bitrates, max(N, args.mpc_sessions), trace_len=tl, trace_interval=ti)
+    tid_d = torch.from_numpy(tid_h).to(dev)
+    off_d = torch.from_numpy(off_h).to(dev)
+    out = {k: torch.empty(V, N, dtype=torch.float64, device=dev) for k in ("delay", "sleep", "buffer", "rebuffer", "reward")}
+    out["end_of_video"] = torch.empty(V, N, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def one_step(ev=None):
+        env.reset(tid_d, off_d, session_base=base)
+        if ev:
+            ev[0].record(stream)
+        env.rollout("random", V, seed=SEED, out=out)
+        if ev:
+            ev[1].record(stream)
+        return env.stats()
+
+    for _ in range(max(3, args.warmup)):
+        flush.fill_(1)
+        stats = one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    step_ms, kern_ms = [], []
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)                                         # evict L2 (outside the timed region)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        stats = one_step((k0, k1))
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        kern_ms.append(k0.elapsed_time(k1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.launch_count() - launches0
+    total_ms = max_over_ranks(sum(step_ms), dev)
+    kern_avg_ms = sum(kern_ms) / len(kern_ms)
+    tot_stats = allreduce_stats(stats)                          # the one collective: final QoE statistics
+    torch.cuda.synchronize()
+    chunk_steps = world * N * V * args.steps
+    value = chunk_steps / (total_ms * 1e-3)
+    errors = env.error_count()
+
+    # ---- e2e: the host-buffer call (Simulator.run semantics: per-session QoE sums + statistics to the host) ----
+    tid_p = torch.from_numpy(tid_h).pin_memory().numpy()
+    off_p = torch.from_numpy(off_h).pin_memory().numpy()
+    acc_p = torch.empty(8, N, dtype=torch.float64).pin_memory().numpy()
+    st_p = torch.empty(8, dtype=torch.float64).pin_memory().numpy()
+    host_out = dict(acc=acc_p, stats=st_p)
+    for _ in range(3):
+        env.run_host("random", V, tid_p, off_p, seed=SEED, session_base=base, out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        env.run_host("random", V, tid_p, off_p, seed=SEED, session_base=base, out=host_out)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = chunk_steps / e2e_s
+    h2d = N * 4 + N * 8
+    d2h = 8 * N * 8 + 8 * 8
+
+    # ---- MPC decisions/s (configs[2] sharded: robust MPC, horizon 5, 7 776 sequences per decision) ----
+    mpc = None
+    if not args.no_mpc:
+        mpc = bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks)
+
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg_bytes = N * V * BYTES_PER_STEP + N * BYTES_PER_SESSION
+    achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("abr_rollout_kernel")
+    except Exception:
+        pass
+    line = dict(metric="chunk_steps_per_sec", value=value, unit="chunk-steps/s", n_gpus=world, steps=args.steps,
+                warmup=max(3, args.warmup), ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic", config=workload_config(args),
+                roofline=dict(kernel="abr_rollout_kernel<random>", bound="hbm", achieved=achieved, peak=hbm_peak,
+                              unit="GB/s", frac=achieved / hbm_peak, traffic=traffic, peak_source=peak_src,
+                              algorithmic_bytes_per_launch=alg_bytes, kernel_ms=kern_avg_ms,
+                              bytes_per_chunk_step=BYTES_PER_STEP, bytes_per_session=BYTES_PER_SESSION),
+                e2e=dict(value=e2e_value, unit="chunk-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         call="abr_env_run_host: reset + fused episode + statistics; per-session QoE sums [8][N] "
+                              "and the statistics vector copied back", ms_per_step=1e3 * e2e_s / args.steps),
+                gpu_launches=int(launches), clocks=clocks, wall_s_timed_region=wall,
+                qoe_stats=dict(zip(_lib.ACC_NAMES, [float(x) for x in tot_stats.cpu()])), flagged_sessions=errors)
+    if mpc:
+        line["mpc"] = mpc
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
+    import torch
+    from abrsimulator_b200 import synth, _lib
+    from abrsimulator_b200.env import BatchedABREnv
+    import ctypes as C
+    H, M = args.mpc_horizon, args.mpc_sessions
+    bitrates, sizes = synth.make_video(V)
+    bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
+    menv = BatchedABREnv(bw, sizes, bitrates, M, trace_len=tl, trace_interval=ti, track_history=1, track_acc=1)
+    tid, off = synth.make_sessions(M, N_TRACES, T_TRACE, session_base=rank * M)
+    menv.reset(tid, off, session_base=rank * M)
+    menv.rollout("bba", 8, want=())                              # fill the throughput-history ring
+    act = torch.empty(M, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    for _ in range(3):
+        menv.mpc_decide(H, "robust", out=act)
+    barrier()
+    reps = max(3, min(args.steps, 10))
+    ms = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        menv.mpc_decide(H, "robust", out=act)
+        e1.record(stream)
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    barrier()
+    tot = max_over_ranks(sum(ms), dev)
+    dec_per_s = world * M * reps / (tot * 1e-3)
+    # reference-exact mode for comparison
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    menv.mpc_decide(H, "reference", out=act)
+    e0.record(stream)
+    menv.mpc_decide(H, "reference", out=act)
+    e1.record(stream)
+    e1.synchronize()
+    ref_mode_rate = M / (e0.elapsed_time(e1) * 1e-3)
+    # whole MPC episode (decide + step per chunk) for one video, with final statistics
+    menv.reset(tid, off, session_base=rank * M)
+    barrier()
+    e0.record(stream)
+    menv.mpc_episode(V, H, "robust")
+    st = menv.stats()
+    e1.record(stream)
+    e1.synchronize()
+    ep_ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    res = dict(metric="mpc_decisions_per_sec", value=dec_per_s, unit="decisions/s", horizon=H, mode="robust",
+               sequences_per_decision=A ** H, sessions_per_gpu=M, ms_per_launch=sum(ms) / len(ms),
+               reference_exact_mode_decisions_per_s_per_gpu=ref_mode_rate,
+               episode=dict(chunks=V, ms=ep_ms, decisions_per_s=world * M * V / (ep_ms * 1e-3),
+                            mean_reward_per_chunk=float(st[0] / st[6])))
+    if rank == 0:
+        lib = _lib.load()
+        probe = {}
+        for kind, name in ((0, "dadd"), (1, "dfma"), (2, "dadd_dmul_dsetp_mix")):
+            g = C.c_double(0.0)
+            t = C.c_float(0.0)
+            _lib.check(lib.abr_fp64_probe(C.c_int(kind), C.c_int(4096), C.byref(g), C.byref(t), None))
+            probe[name + "_gops"] = g.value
+        # fp64-pipe instructions the search executes per decision: per prefix round
+        # (h-2) interior steps + A interior + A^2 leaves; 9 fp64-pipe instructions each (leaf: 8 arithmetic + compare)
+        rounds = -(-(A ** (H - 2)) // 32) * 32
+        executed = rounds * ((H - 2) * 9 + A * 9 + A * A * 9)
+        naive = A ** H * (14 * (H - 1) + 13) + 4 * A * H
+        peak = probe["dadd_gops"]
+        res["roofline"] = dict(bound="fp64-issue", unit="Gop/s", peak=peak, peak_source="abr_fp64_probe (DADD chains, same run)",
+                               probe=probe, executed_fp64_ops_per_decision=executed,
+                               achieved=dec_per_s / world * executed / 1e9, frac=dec_per_s / world * executed / 1e9 / peak,
+                               naive_equivalent_ops_per_decision=naive,
+                               naive_equivalent_gops=dec_per_s / world * naive / 1e9)
+    return res
+
+
+def cpu_baseline(args):
+    """The oracle port timed on this box's host cores, bounded sample (reported baseline, not the target)."""
+    rate, steps, busy, _ = cpu_python_steps(1, args.cpu_seconds)
+    c_rate, c_n, c_dt = cpu_c_oracle_steps()
+    out = dict(value=rate, unit="chunk-steps/s", cores=1, kind="port",
+               sample=f"pure-Python port (oracle/step_oracle.py) of the same random-policy workload: {steps} chunk-steps "
+                      f"in {busy:.1f} s on 1 core of {os.cpu_count()}",
+               c_oracle=dict(value=c_rate, unit="chunk-steps/s", cores=1,
+                             sample=f"oracle/abr_oracle.c (gcc -O2), {c_n} sessions x 48 chunks in {c_dt:.2f} s"))
+    if not args.no_mpc:
+        r, n, b = cpu_python_mpc(1, args.mpc_horizon, args.cpu_seconds)
+        out["mpc"] = dict(value=r, unit="decisions/s", cores=1,
+                          sample=f"pure-Python port of mpc.py's search (oracle/mpc_oracle.py), {n} horizon-"
+                                 f"{args.mpc_horizon} decisions in {b:.1f} s")
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,158 @@
+/* abr_b200.h — C-ABI of the B200-native batched ABR environment and MPC controller.
+ *
+ * This is the drop-in boundary for the hot path of Elliotshui/ABRSimulator:
+ * the per-session environment loop (Simulator.py:93-210) and the MPC bitrate
+ * decision (mpc.py:69-186).  The reference is pure Python and has no FFI; the
+ * entry points below are what a binding for that path would call (ctypes stub in
+ * INTEGRATION.md).  Semantics of every call are fixed by SPEC.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; "d_" = device pointer on the current CUDA
+ *    device, "h_" = host pointer.  The caller owns every buffer it passes; the
+ *    library owns only the opaque AbrEnv (device copies of the tables + SoA
+ *    session state).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls
+ *    taking device pointers are asynchronous on that stream and never synchronise;
+ *    calls with a "_host" suffix copy in/out and synchronise the stream before returning.
+ *  - return value: ABR_OK (0) or an error code; abr_last_error() returns a
+ *    thread-local message.  There is no CPU fallback: without a CUDA device every
+ *    compute entry point fails with ABR_ERR_CUDA.
+ *  - one AbrEnv per GPU/process; an AbrEnv is not thread-safe.
+ */
+#ifndef ABR_B200_H
+#define ABR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABR_VERSION 100
+
+enum { ABR_OK = 0, ABR_ERR_INVALID = 1, ABR_ERR_CUDA = 2, ABR_ERR_RANGE = 3, ABR_ERR_STATE = 4 };
+
+/* built-in policies of the fused episode (SPEC §4) */
+enum { ABR_POLICY_FIXED = 0, ABR_POLICY_RANDOM = 1, ABR_POLICY_BBA = 2 };
+/* MPC modes (SPEC §5): 0 = reference-exact mpc.py, 1 = robust MPC */
+enum { ABR_MPC_REF = 0, ABR_MPC_ROBUST = 1 };
+/* abr_mpc_decide flags */
+enum { ABR_MPC_TRUNCATE = 1,        /* mode 0: k+H > V truncates the horizon instead of flagging IndexError (mpc.py:125-128, D13) */
+       ABR_MPC_EMPTY_DEFAULT = 2 }; /* mode 0: empty history returns default_quality instead of flagging ZeroDivisionError (mpc.py:90, D14) */
+
+/* rows of the accumulator table / entries of the statistics vector (SPEC §6) */
+enum { ABR_ACC_REWARD = 0, ABR_ACC_REBUF = 1, ABR_ACC_UTILITY = 2, ABR_ACC_SMOOTH = 3, ABR_ACC_SLEEP = 4,
+       ABR_ACC_DELAY = 5, ABR_ACC_STEPS = 6, ABR_ACC_EPISODES = 7, ABR_NUM_ACC = 8, ABR_NUM_STATS = 8 };
+
+/* session-state fields exposed by abr_env_state_ptr (SPEC §1).  All arrays have max_sessions
+ * elements except BW_HIST / ERR_RING ([hist_k][max_sessions]) and ACC ([ABR_NUM_ACC][max_sessions]). */
+enum { ABR_F_SEG = 0, ABR_F_CHUNK = 1, ABR_F_LAST_Q = 2, ABR_F_TRACE_ID = 3, ABR_F_HIST_LEN = 4, ABR_F_DONE = 5,
+       ABR_F_ERR_LEN = 6, ABR_F_TAU = 10, ABR_F_BUFFER = 11, ABR_F_BW_HIST = 12, ABR_F_LAST_PRED = 13,
+       ABR_F_ERR_RING = 14, ABR_F_ACC = 15, ABR_F_SIZES = 20, ABR_F_UTILITY = 21, ABR_F_TRACE_BW = 22 };
+
+/* Replaces the attribute bags MPD / QOEMetric (Simulator.py:11-24, mpc_test.py:18-29) plus the
+ * north-star constants (SPEC §1). */
+typedef struct AbrParams {
+    double chunk_length;    /* MPD.chunk_length, Simulator.py:13 */
+    double max_buffer;      /* MPD.max_buffer, Simulator.py:14 */
+    double rtt;             /* added to every download delay */
+    double payload;         /* packet-payload fraction applied to the trace bandwidth */
+    double sleep_quantum;   /* sleep granularity while buffer > max_buffer */
+    double rebuf_penalty;   /* QOEMetric.rebuffer_weight, Simulator.py:21 */
+    double smooth_penalty;  /* QOEMetric.variance_weight, Simulator.py:22 */
+    double utility_scale;   /* utility_mode 0: U = bitrate * utility_scale (1.0 = mpc.py:95-97 identity) */
+    double bba_reservoir, bba_cushion;
+    int32_t utility_mode;   /* 0 linear, 1 log(bitrate / top bitrate) (mpc.py:99-102) */
+    int32_t default_quality;
+    int32_t auto_reset;     /* 1: a session restarts at chunk 0 after its last chunk */
+    int32_t hist_k;         /* capacity of the throughput-history ring (robust-MPC window) */
+    int32_t track_history;  /* 1: abr_env_step / rollout push size/delay into the ring */
+    int32_t track_acc;      /* 1: abr_env_step adds into the per-session accumulators */
+    int32_t reserved1, reserved2;
+} AbrParams;
+
+typedef struct AbrEnv AbrEnv;
+
+/* ---- library ---- */
+int abr_version(void);
+const char* abr_last_error(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+long long abr_launch_count(void);
+int abr_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* total_mem_bytes);
+void abr_params_default(AbrParams* p);
+
+/* ---- environment (replaces Simulator.set_network_info / set_mpd / set_qoe_metric + run,
+ *      Simulator.py:54-77,93-210).  Table pointers are HOST pointers; they are validated
+ *      (bandwidth finite and > 0, sizes finite and >= 0) and copied to the device. ---- */
+int abr_env_create(const double* h_trace_bw /*[n_traces][T_max]*/, const int32_t* h_trace_len /*[n_traces]*/,
+                   const double* h_trace_interval /*[n_traces]*/, int n_traces, int T_max,
+                   const double* h_sizes /*[V][A]*/, const double* h_bitrates /*[V][A]*/, int V, int A,
+                   const AbrParams* params, int max_sessions, AbrEnv** out);
+void abr_env_destroy(AbrEnv* env);
+int abr_env_num_sessions(const AbrEnv* env);
+/* SPEC §2.  session_base = global index of local session 0 (sharded runs; keys the random policy). */
+int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_offset /*nullable*/, int n_sessions,
+                  long long session_base, void* stream);
+int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_start_offset /*nullable*/,
+                       int n_sessions, long long session_base, void* stream);
+/* SPEC §3: one chunk step for every session.  Output pointers are nullable. */
+int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
+                 double* d_rebuf, double* d_reward, double* d_next_sizes /*[N][A]*/, uint8_t* d_end_of_video,
+                 double* d_throughput, void* stream);
+/* SPEC §3+§4: `steps` chunk steps in one launch, state in registers.  Trajectory outputs are
+ * [steps][N] and nullable; per-session sums are added into the env accumulators (ABR_F_ACC). */
+int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                          double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
+                          uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream);
+/* MPC decision for every session from the env's own state and history ring (SPEC §5);
+ * never flags errors (implies ABR_MPC_TRUNCATE | ABR_MPC_EMPTY_DEFAULT). */
+int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, double* d_best_j /*nullable*/,
+                       void* stream);
+/* SPEC §6: reduce the accumulators of the first n sessions into d_out[ABR_NUM_STATS]. */
+int abr_stats_partial(AbrEnv* env, double* d_out, void* stream);
+int abr_env_state_ptr(AbrEnv* env, int field, void** d_ptr);
+/* sessions flagged so far (walk guard hit, invalid action, MPC input error); synchronises the stream */
+int abr_env_error_count(AbrEnv* env, long long* out, void* stream);
+
+/* ---- host-buffer entry points: what Simulator.run() (Simulator.py:93-210) and
+ *      MPCBitrateController.next_bitrate() (mpc.py:181-186) callers use.  They copy inputs
+ *      host->device, run the kernels above and copy results device->host. ---- */
+int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* h_trace_id,
+                     const double* h_start_offset, int n_sessions, long long session_base,
+                     const int32_t* h_actions_in /*[steps][N], policy FIXED*/,
+                     double* h_acc /*[ABR_NUM_ACC][N], nullable*/, double* h_stats /*[ABR_NUM_STATS], nullable*/,
+                     double* h_reward_traj /*[steps][N], nullable*/, void* stream);
+
+/* ---- standalone MPC (replaces MPCBitrateController.next_bitrate over a batch of players,
+ *      mpc.py:164-186).  Tables are device pointers [V][A].  History is a per-session ring
+ *      [N][K]: slot (hist_len-1) mod K is the newest sample; hist_len <= K is a plain
+ *      oldest-first row.  d_last_pred/d_err_ring/d_err_len ([N],[N][K],[N]) hold the robust
+ *      error state (mode 1; nullable = no discount).  On an input error the action is -1
+ *      and *d_error_count is incremented.  Outputs other than d_action are nullable. ---- */
+int abr_mpc_decide(const double* d_sizes, const double* d_utility, int V, int A, const AbrParams* params, int N,
+                   const int32_t* d_chunk_idx, const int32_t* d_prev_q, const double* d_buffer,
+                   const double* d_bw_hist, const int32_t* d_hist_len, int K, double* d_last_pred,
+                   double* d_err_ring, int32_t* d_err_len, int horizon, int mode, int flags, int32_t* d_action,
+                   double* d_best_j, int32_t* d_best_seq /*[N][H]*/, double* d_preds /*[N][H]*/,
+                   int32_t* d_error_count, void* stream);
+int abr_mpc_decide_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params, int N,
+                        const int32_t* h_chunk_idx, const int32_t* h_prev_q, const double* h_buffer,
+                        const double* h_bw_hist, const int32_t* h_hist_len, int K, double* h_last_pred,
+                        double* h_err_ring, int32_t* h_err_len, int horizon, int mode, int flags, int32_t* h_action,
+                        double* h_best_j, int32_t* h_best_seq, double* h_preds, int32_t* h_error_count);
+
+/* objective() of caller-given sequences for ONE decision state (replaces MPCBitrateController.objective,
+ * mpc.py:120-162): scores[m] = J(sequences[m][0..H-1]).  h_history is oldest first.  mode 1 uses
+ * c = harmonic_mean / (1 + max_err).  Requires chunk_idx + horizon <= V and a non-empty, non-zero history. */
+int abr_mpc_score_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params,
+                       int chunk_idx, int prev_q, double buffer, const double* h_history, int n_history, int horizon,
+                       int mode, double max_err, const int32_t* h_sequences /*[M][H]*/, int M, double* h_scores /*[M]*/);
+
+/* ---- measurement helper: FP64 issue-rate probe used as the MPC kernel's roofline denominator.
+ *      kind 0 = dependent DADD chains, 1 = DFMA chains, 2 = DADD + DSETP/select mix.
+ *      Returns giga-ops/s (one op per thread-instruction; FMA counts 1). ---- */
+int abr_fp64_probe(int kind, int iters, double* gops_per_s, float* ms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

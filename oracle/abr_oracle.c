@@ -129,7 +129,7 @@ static void step_one(OrcEnv* e, int s, int q, StepOut* o) {
     const double size = e->sizes[chunk * e->A + q];
     /* 3.1 segment walk */
     double sent = 0.0, delay = 0.0;
-    int guard = 4 * T + 4;
+    int guard = 1 << 20;   /* safety net only: every bandwidth is > 0, so the walk terminates */
     for (;;) {
         double rate = bw[seg] * p->payload;
         double room = I - tau;
@@ -298,7 +298,7 @@ static int mpc_one(const double* sizes, const double* util, int V, int A, const 
     if (best_seq) for (int i = 0; i < H; ++i) best_seq[i] = -1;
     if (H < 1 || H > MAXH || A > 16 || k < 0) return 1;
     if (mode == 0) {
-        if (n <= 0 || k + H > V || prev_q < 0 || prev_q >= A) return 1; /* D14 / D13 */
+        if (n <= 0 || k + H > V || prev_q >= A) return 1; /* D14 / D13; prev_q < 0 = no previous chunk */
         double S = 0.0;
         for (int j = 0; j < n; ++j) {
             if (hist[j] == 0.0) return 1;                                  /* ZeroDivisionError, mpc.py:88 */
@@ -319,7 +319,7 @@ static int mpc_one(const double* sizes, const double* util, int V, int A, const 
         }
     } else {
         if (prev_q >= A) return 1;
-        if (n <= 0) { *action = p->default_quality; return 0; }
+        if (n <= 0) { *action = p->default_quality > 0 ? p->default_quality : 0; return 0; }
         double S = 0.0;
         for (int j = 0; j < n; ++j) {
             if (!(hist[j] > 0.0)) return 1;
@@ -396,7 +396,7 @@ void orc_env_mpc_decide(OrcEnv* e, int H, int mode, int32_t* action, double* bes
         if (e->done[s]) { action[s] = 0; if (best_j) best_j[s] = NAN; continue; }
         int n = gather_hist(e->bw_hist + (size_t)s * e->K, e->hist_len[s], e->K, tmp);
         if (mode == 0 && n == 0) {               /* env flow: no sample yet -> default quality (SPEC §5.2 rule reused) */
-            action[s] = e->p.default_quality; if (best_j) best_j[s] = NAN; continue;
+            action[s] = e->p.default_quality > 0 ? e->p.default_quality : 0; if (best_j) best_j[s] = NAN; continue;
         }
         if (mode == 0 && e->chunk[s] + H > e->V) { /* env flow never raises: truncate like mode 1 */
             int h = e->V - e->chunk[s];

@@ -1,0 +1,298 @@
+"""GPU parity of the chunk-step kernels (per-step and fused episode), through the C-ABI — run with -m gpu.
+
+Oracle: oracle/abr_oracle.c (SPEC.md restated; parity unpinned by the reference).
+Bar: 1e-9 relative (BASELINE.json) — and, because both sides execute the same IEEE operations in the
+same order without FMA contraction, bit-identical.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from abrsimulator_b200 import synth
+from abrsimulator_b200.env import BatchedABREnv
+from abrsimulator_b200.datamodel import Chunk, NetworkInfo, QOEMetric
+from abrsimulator_b200.simulator import Simulator, BufferBasedPolicy, RandomPolicy
+from abrsimulator_b200 import _lib
+from oracle import oracle as orc
+from helpers import small_world, assert_close, bits_equal
+
+STATE_I = ("seg", "chunk", "last_q", "trace_id")
+STATE_F = ("tau", "buffer")
+
+
+def make_pair(N, params=None, **world):
+    params = params or {}
+    bitrates, sizes, bw, tl, ti = small_world(**world)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, **params)
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **params)
+    n_traces, T = bw.shape
+    rng = np.random.default_rng(11)
+    tid = rng.integers(0, n_traces, size=N).astype(np.int32)
+    off = rng.uniform(0, T * float(np.max(ti)) * 1.5, size=N)
+    off[:4] = [0.0, float(ti[tid[1]]), 1e-9, 3.0 * float(ti[tid[3]])]   # segment boundaries
+    env.reset(tid, off)
+    ref.reset(tid, off)
+    return env, ref
+
+
+def check_state(env, ref):
+    for f in STATE_I:
+        assert np.array_equal(env.state(f).cpu().numpy(), ref.field(f)), f
+    for f in STATE_F:
+        assert bits_equal(env.state(f).cpu().numpy(), ref.field(f)) == 0, f
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_step_matches_oracle_over_two_episodes(ragged):
+    N, steps = 4096, 100                       # 48-chunk video: crosses two end-of-video resets
+    env, ref = make_pair(N, dict(track_history=1), ragged=ragged)
+    check_state(env, ref)
+    rng = np.random.default_rng(3)
+    for t in range(steps):
+        a = rng.integers(0, env.A, size=N).astype(np.int32)
+        got = env.step(a, want_throughput=True)
+        exp = ref.step(a)
+        assert_close(got.delay.cpu().numpy(), exp["delay"], f"delay@{t}")
+        assert_close(got.sleep.cpu().numpy(), exp["sleep"], f"sleep@{t}")
+        assert_close(got.buffer.cpu().numpy(), exp["buffer"], f"buffer@{t}")
+        assert_close(got.rebuffer.cpu().numpy(), exp["rebuf"], f"rebuf@{t}")
+        assert_close(got.reward.cpu().numpy(), exp["reward"], f"reward@{t}")
+        assert_close(got.throughput.cpu().numpy(), exp["throughput"], f"thr@{t}")
+        assert_close(got.next_sizes.cpu().numpy(), exp["next_sizes"], f"next_sizes@{t}")
+        assert np.array_equal(got.end_of_video.cpu().numpy(), exp["eov"])
+        if t in (47, 48, 95, 96):
+            assert got.end_of_video.sum().item() == (N if t in (47, 95) else 0)
+    check_state(env, ref)
+    assert np.array_equal(env.state("hist_len").cpu().numpy(), ref.field("hist_len"))
+    assert env.error_count() == 0 and ref.errors() == 0
+
+
+def test_sleep_cap_and_rebuffer_paths_are_exercised():
+    """Fast network + lowest bitrate fills the buffer past max_buffer (sleep); slow network rebuffers."""
+    N = 512
+    env, ref = make_pair(N, dict(max_buffer=12.0, sleep_quantum=0.5), n_traces=8, T=64)
+    slept = rebuffered = 0
+    for t in range(40):
+        a = np.full(N, 0 if t < 20 else env.A - 1, np.int32)
+        got = env.step(a)
+        exp = ref.step(a)
+        for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                         ("reward", "reward")):
+            assert_close(getattr(got, k_g).cpu().numpy(), exp[k_c], f"{k_g}@{t}")
+        slept += int((exp["sleep"] > 0).sum())
+        rebuffered += int((exp["rebuf"] > 0).sum())
+        assert float(got.buffer.max()) <= 12.0 + 1e-12
+    assert slept > 1000 and rebuffered > 100
+    check_state(env, ref)
+
+
+def test_no_auto_reset_sessions_become_inert():
+    N = 256
+    env, ref = make_pair(N, dict(auto_reset=0, track_acc=1), V=6)
+    for t in range(9):
+        a = np.full(N, t % env.A, np.int32)
+        got = env.step(a)
+        exp = ref.step(a)
+        assert_close(got.reward.cpu().numpy(), exp["reward"], f"reward@{t}")
+        assert_close(got.buffer.cpu().numpy(), exp["buffer"], f"buffer@{t}")
+        assert_close(got.next_sizes.cpu().numpy(), exp["next_sizes"], f"next@{t}")
+        assert np.array_equal(got.end_of_video.cpu().numpy(), exp["eov"])
+        if t >= 6:
+            assert float(got.delay.abs().sum()) == 0.0
+    assert np.array_equal(env.state("done").cpu().numpy(), np.ones(N, np.uint8))
+    acc = env.session_acc().cpu().numpy()
+    assert np.all(acc[6] == 6.0) and np.all(acc[7] == 1.0)
+
+
+@pytest.mark.parametrize("policy", ["random", "bba", "fixed"])
+def test_fused_rollout_matches_oracle(policy):
+    N, steps = 4096, 60
+    env, ref = make_pair(N, dict(track_history=1), ragged=(policy == "bba"))
+    acts = np.random.default_rng(9).integers(0, env.A, size=(steps, N)).astype(np.int32) if policy == "fixed" else None
+    got = env.rollout(policy, steps, seed=0xDEADBEEFCAFE, actions=acts)
+    pid = dict(random=orc.POLICY_RANDOM, bba=orc.POLICY_BBA, fixed=orc.POLICY_FIXED)[policy]
+    exp = ref.rollout(pid, steps, seed=0xDEADBEEFCAFE, actions=acts)
+    assert np.array_equal(got["actions"].cpu().numpy(), exp["actions"])
+    for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                     ("reward", "reward")):
+        assert_close(got[k_g].cpu().numpy(), exp[k_c], k_g)
+    assert np.array_equal(got["end_of_video"].cpu().numpy(), exp["eov"])
+    assert_close(env.session_acc().cpu().numpy(), exp["acc"], "acc")
+    check_state(env, ref)
+    stats = env.stats().cpu().numpy()
+    exp_stats = orc.stats_from_acc(exp["acc"])
+    np.testing.assert_allclose(stats, exp_stats, rtol=1e-9)
+    assert stats[6] == N * steps and stats[7] == N            # counts are exact
+    assert env.error_count() == 0
+
+
+def test_fused_rollout_equals_stepwise():
+    """Size-independent property: the fused episode is the per-step kernel applied `steps` times."""
+    N, steps = 2048, 48
+    env_a, _ = make_pair(N)
+    env_b, _ = make_pair(N)
+    got = env_a.rollout("random", steps, seed=5)
+    acts = got["actions"]
+    for t in range(steps):
+        r = env_b.step(acts[t], want_next_sizes=False)
+        assert torch.equal(r.reward, got["reward"][t]) and torch.equal(r.delay, got["delay"][t])
+        assert torch.equal(r.buffer, got["buffer"][t])
+    for f in STATE_I + STATE_F:
+        assert torch.equal(env_a.state(f), env_b.state(f)), f
+
+
+def test_sharded_random_rollout_equals_unsharded():
+    """Sharding invariance (SPEC §4): two half shards draw the same actions and produce the same
+    trajectories as one full run, and their statistics add up."""
+    N, steps = 4096, 48
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=32, T=256)
+    tid, off = synth.make_sessions(N, 32, 256)
+    full = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    full.reset(tid, off)
+    ref = full.rollout("random", steps, seed=42, want=("reward", "actions"))
+    parts = []
+    stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+    for lo, hi in ((0, N // 2), (N // 2, N)):
+        tid_s, off_s = synth.make_sessions(hi - lo, 32, 256, session_base=lo)
+        assert np.array_equal(tid_s, tid[lo:hi]) and np.array_equal(off_s, off[lo:hi])
+        e = BatchedABREnv(bw, sizes, bitrates, hi - lo, trace_len=tl, trace_interval=ti)
+        e.reset(tid_s, off_s, session_base=lo)
+        parts.append(e.rollout("random", steps, seed=42, want=("reward", "actions")))
+        stats += e.stats()
+    assert torch.equal(torch.cat([p["actions"] for p in parts], dim=1), ref["actions"])
+    assert torch.equal(torch.cat([p["reward"] for p in parts], dim=1), ref["reward"])
+    np.testing.assert_allclose(stats.cpu().numpy(), full.stats().cpu().numpy(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_mpc_episode_matches_oracle(mode):
+    """decide -> step loop over a whole video with the env-owned history ring and robust error state."""
+    N, H = 192, 4
+    params = dict(track_history=1, track_acc=1, hist_k=5)
+    env, ref = make_pair(N, params, V=20, n_traces=8, T=64)
+    for t in range(26):                         # crosses the end-of-video reset
+        act, bj = env.mpc_decide(H, mode, want_score=True)
+        act_ref, bj_ref = ref.mpc_decide(H, mode)
+        assert np.array_equal(act.cpu().numpy(), act_ref), f"actions differ at chunk {t}"
+        ok = ~np.isnan(bj_ref)
+        assert bits_equal(bj.cpu().numpy()[ok], bj_ref[ok]) == 0
+        got = env.step(act, want_next_sizes=False)
+        exp = ref.step(act_ref, want_next_sizes=False)
+        assert_close(got.reward.cpu().numpy(), exp["reward"], f"reward@{t}")
+    check_state(env, ref)
+    assert bits_equal(env.state("last_pred").cpu().numpy(), ref.field("last_pred")) == 0
+    assert np.array_equal(env.state("err_len").cpu().numpy(), ref.field("err_len"))
+    assert env.error_count() == 0 and ref.errors() == 0
+
+
+def test_run_host_path_matches_oracle():
+    N, steps = 3000, 48
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=32, T=256)
+    tid, off = synth.make_sessions(N, 32, 256)
+    env = BatchedABREnv(bw, sizes, bitrates, 4096, trace_len=tl, trace_interval=ti)
+    out = env.run_host("bba", steps, tid, off, want_reward_traj=True)
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
+    ref.reset(tid, off)
+    exp = ref.rollout(orc.POLICY_BBA, steps)
+    assert_close(out["acc"], exp["acc"], "acc")
+    assert_close(out["reward"], exp["reward"], "reward")
+    np.testing.assert_allclose(out["stats"], orc.stats_from_acc(exp["acc"]), rtol=1e-9)
+
+
+def test_invalid_inputs_are_flagged_or_rejected():
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=4, T=32)
+    env = BatchedABREnv(bw, sizes, bitrates, 64, trace_len=tl, trace_interval=ti)
+    env.reset(np.zeros(64, np.int32))
+    a = np.zeros(64, np.int32)
+    a[5], a[9] = -1, 99
+    env.step(a)
+    assert env.error_count() == 2
+    with pytest.raises(_lib.AbrError):
+        env.reset(np.zeros(65, np.int32))                       # over capacity
+    bad = bw.copy()
+    bad[1, 3] = 0.0
+    with pytest.raises(_lib.AbrError):
+        BatchedABREnv(bad, sizes, bitrates, 8, trace_len=tl, trace_interval=ti)   # zero bandwidth (D14 analogue)
+    with pytest.raises(_lib.AbrError):
+        BatchedABREnv(bw, -sizes, bitrates, 8, trace_len=tl, trace_interval=ti)
+    with pytest.raises(ValueError):
+        env.step(np.zeros(3, np.int32))
+
+
+def test_full_size_properties_65536x48():
+    """BASELINE config 2 at full size: properties that need no oracle."""
+    N, steps = 65536, 48
+    bitrates, sizes = synth.make_video(48)
+    bw, tl, ti = synth.make_traces(1024, 2048)
+    tid, off = synth.make_sessions(N, 1024, 2048)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    env.reset(tid, off)
+    out = env.rollout("random", steps, seed=7)
+    assert env.error_count() == 0
+    d, sl, b, rb, rw, q = (out[k] for k in ("delay", "sleep", "buffer", "rebuffer", "reward", "actions"))
+    assert bool((d > 0.08).all()) and bool((rb >= 0).all()) and bool((sl >= 0).all())
+    assert float(b.max()) <= 60.0 and float(b.min()) >= 4.0 - 1e-12        # buffer in [L, max_buffer]
+    assert bool((out["end_of_video"][-1] == 1).all()) and int(out["end_of_video"][:-1].sum()) == 0
+    # buffer recursion: b_t = max(b_{t-1} - delay, 0) + L - sleep
+    prev = torch.cat([torch.zeros(1, N, dtype=torch.float64, device="cuda"), b[:-1]])
+    assert torch.equal(torch.clamp(prev - d, min=0.0) + 4.0 - sl, b)
+    assert torch.equal(torch.clamp(d - prev, min=0.0), rb)
+    # reward identity from the outputs
+    U = torch.from_numpy(bitrates * 0.001).cuda()
+    u = U[torch.arange(steps, device="cuda")[:, None].expand(-1, N), q.long()]
+    last = torch.cat([torch.ones(1, N, dtype=torch.int64, device="cuda"), q[:-1].long()])
+    up = U[torch.arange(steps, device="cuda")[:, None].expand(-1, N), last]
+    assert torch.equal((u - 4.3 * rb) - 1.0 * (u - up).abs(), rw)
+    # determinism: a second run from the same reset is bit-identical
+    env.reset(tid, off)
+    out2 = env.rollout("random", steps, seed=7, want=("reward",))
+    assert torch.equal(out2["reward"], rw)
+    # random actions are uniform over the ladder
+    hist = torch.bincount(q.flatten().long(), minlength=6).double() / q.numel()
+    assert float((hist - 1 / 6).abs().max()) < 2e-3
+
+
+def test_simulator_facade_run():
+    """Simulator API (Simulator.py:45-93): setters + run() -> QoE cost rw*rebuffer + vw*sum|dbitrate|."""
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=1, T=200, V=30)
+    sim = Simulator(BufferBasedPolicy(), None)
+    sim.set_qoe_metric(QOEMetric(4.3, 0.001, 0, 0))
+    sim.set_network_info(1.0, list(bw[0]))
+    sim.set_mpd(4.0, 60.0, 0.0, [Chunk(list(b / 1000.0)) for b in bitrates])   # sizes = bitrate * chunk_length
+    cost = sim.run()
+    P = dict(chunk_length=4.0, max_buffer=60.0, rebuf_penalty=4.3, smooth_penalty=0.001, utility_scale=1.0,
+             default_quality=-1, auto_reset=0)
+    ref = orc.OracleEnv(bw, tl, ti, bitrates / 1000.0 * 4.0, bitrates / 1000.0, 1, **P)
+    ref.reset(np.zeros(1, np.int32))
+    exp = ref.rollout(orc.POLICY_BBA, 30)
+    want = 4.3 * exp["acc"][1, 0] + 0.001 * exp["acc"][3, 0]
+    assert cost == pytest.approx(want, rel=1e-12)
+
+    class Lowest:                                   # generic controller protocol (Simulator.py:155)
+        def __init__(self):
+            self.calls = []
+
+        def get_next_bitrate(self, chunk_id, previous_bitrates, previous_bandwidths, buffer_level):
+            self.calls.append((chunk_id, len(previous_bitrates), len(previous_bandwidths), buffer_level))
+            return 0
+
+    ctl = Lowest()
+    sim2 = Simulator(ctl, None)
+    sim2.set_qoe_metric(QOEMetric(4.3, 0.001, 0, 0))
+    sim2.set_network_info(NetworkInfo(1.0, list(bw[0])).interval, list(bw[0]))
+    sim2.set_mpd(4.0, 60.0, 0.0, [Chunk(list(b / 1000.0)) for b in bitrates])
+    cost2 = sim2.run()
+    assert len(ctl.calls) == 30 and ctl.calls[5][:3] == (5, 5, 5)
+    ref.reset(np.zeros(1, np.int32))
+    exp2 = ref.rollout(orc.POLICY_FIXED, 30, actions=np.zeros((30, 1), np.int32))
+    assert cost2 == pytest.approx(4.3 * exp2["acc"][1, 0] + 0.001 * exp2["acc"][3, 0], rel=1e-12)
+    # many sessions with the random policy
+    sim3 = Simulator(RandomPolicy(3), None)
+    sim3.set_qoe_metric(QOEMetric(4.3, 1.0, 0, 0))
+    sim3.set_network_info(1.0, [NetworkInfo(1.0, list(bw[0])), NetworkInfo(0.5, list(bw[0][:50]))])
+    sim3.set_mpd(4.0, 60.0, 0.0, [Chunk(list(b / 1000.0)) for b in bitrates])
+    costs = sim3.run_batch(100)
+    assert costs.shape == (100,) and np.all(np.isfinite(costs)) and np.all(costs >= 0)

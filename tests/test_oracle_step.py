@@ -1,0 +1,127 @@
+"""CPU-only: the C step oracle against the pure-Python restatement of SPEC.md, policies, Philox KAT,
+robust-MPC C vs Python, and a loose fixed-dt plausibility check in the spirit of Simulator.py:135-208."""
+import numpy as np
+import pytest
+
+from oracle import mpc_oracle as mo
+from oracle import oracle as orc
+from oracle import step_oracle as so
+from helpers import small_world, bits_equal
+
+
+def test_philox_known_answer():
+    # Random123 known-answer vectors for philox4x32-10
+    assert orc.philox(0, 0, 0, 0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert orc.philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff) == \
+        [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert orc.philox(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_c_step_equals_python_step(ragged):
+    N, steps = 24, 110
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=6, T=40, V=48, ragged=ragged)
+    P = dict(orc.DEFAULTS, track_history=1, max_buffer=20.0)
+    env = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **P)
+    rng = np.random.default_rng(1)
+    tid = rng.integers(0, 6, size=N).astype(np.int32)
+    off = rng.uniform(0, 100, size=N)
+    env.reset(tid, off)
+    util = orc.utility_table(bitrates, 0, P["utility_scale"])
+    py = [so.Session(bw[tid[s], :tl[tid[s]]], ti[tid[s]], sizes.tolist(), util.tolist(), P, off[s]) for s in range(N)]
+    for t in range(steps):
+        a = rng.integers(0, 6, size=N).astype(np.int32)
+        c = env.step(a)
+        for s in range(N):
+            r = py[s].step(int(a[s]))
+            for k in ("delay", "sleep", "buffer", "rebuf", "reward", "throughput"):
+                assert c[k][s] == r[k], (t, s, k)
+            assert c["eov"][s] == r["eov"]
+    assert np.array_equal(env.field("seg"), [p.seg for p in py])
+    assert bits_equal(env.field("tau"), np.array([p.tau for p in py])) == 0
+    assert np.array_equal(env.field("chunk"), [p.chunk for p in py])
+
+
+def test_rollout_policies_and_acc():
+    N, steps = 64, 48
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=4, T=64)
+    P = dict(orc.DEFAULTS)
+    tid = (np.arange(N) % 4).astype(np.int32)
+    for policy in (orc.POLICY_RANDOM, orc.POLICY_BBA):
+        env = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **P)
+        env.reset(tid)
+        tr = env.rollout(policy, steps, seed=123, session_base=1000)
+        util = orc.utility_table(bitrates, 0, P["utility_scale"])
+        for s in range(0, N, 7):
+            sess = so.Session(bw[tid[s]], ti[tid[s]], sizes.tolist(), util.tolist(), P)
+            tot = 0.0
+            for t in range(steps):
+                if policy == orc.POLICY_RANDOM:
+                    x0 = orc.philox((1000 + s) & 0xffffffff, 0, t, 0, 123, 0)[0]
+                    q = (x0 * 6) >> 32
+                else:
+                    q = so.bba_action(sess.buffer, 6, P["bba_reservoir"], P["bba_cushion"])
+                assert q == tr["actions"][t, s]
+                r = sess.step(q)
+                assert r["reward"] == tr["reward"][t, s]
+                tot = tot + r["reward"]
+            assert tot == tr["acc"][0, s]
+            assert tr["acc"][6, s] == steps and tr["acc"][7, s] == 1.0
+        st = orc.stats_from_acc(tr["acc"])
+        assert st[6] == N * steps and st[7] == N
+
+
+def test_robust_mpc_c_equals_python():
+    rng = np.random.default_rng(4)
+    V, A, H, K = 20, 4, 3, 5
+    bitrates, sizes, *_ = small_world(V=V, ladder=(300.0, 1200.0, 2850.0, 4300.0))
+    P = orc.make_params(max_buffer=30.0, hist_k=K)
+    util = orc.utility_table(bitrates, 0, 0.001)
+    for trial in range(40):
+        st = mo.RobustState(K)
+        lp, er, el = np.zeros(1), np.zeros((1, K)), np.zeros(1, np.int32)
+        hist = []
+        for k in range(0, V, 1 + trial % 3):
+            hist.append(float(rng.uniform(0.2, 6.0)))
+            prev_q, buf = int(rng.integers(-1, A)), float(rng.uniform(0, 30))
+            r = mo.decide_robust(k, prev_q, buf, hist, st, H, util.tolist(), sizes.tolist(), 4.0, 30.0, 1.0, 4.3)
+            ring = np.zeros((1, K))
+            for j, x in enumerate(hist):
+                ring[0, j % K] = x
+            c = orc.mpc_decide(sizes, util, [k], [prev_q], [buf], ring, [len(hist)], H, 1, P, lp, er, el)
+            assert c["action"][0] == r["action"], (trial, k)
+            assert c["best_J"][0] == r["best_J"]
+            assert list(c["best_seq"][0][:len(r["best_seq"])]) == r["best_seq"]
+            assert lp[0] == st.last_pred
+
+
+def test_env_mpc_flow_never_raises():
+    N = 8
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=2, T=32, V=10)
+    for mode in (0, 1):
+        env = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, track_history=1)
+        env.reset(np.zeros(N, np.int32))
+        for t in range(13):
+            act, _ = env.mpc_decide(4, mode)
+            assert np.all((act >= 0) & (act < 6))
+            if t == 0:
+                assert np.all(act == 1)          # no sample yet -> default quality
+            env.step(act)
+        assert env.errors() == 0
+
+
+def test_analytic_walk_agrees_with_fixed_dt_loop():
+    """Loose plausibility check: the closed-form walk and a 0.01 s Euler loop in the spirit of
+    Simulator.py:152-170 agree to within one tick per chunk."""
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=1, T=64, V=8)
+    P = dict(orc.DEFAULTS, rtt=0.0, payload=1.0)
+    util = orc.utility_table(bitrates, 0, 0.001)
+    sess = so.Session(bw[0], 1.0, sizes.tolist(), util.tolist(), P)
+    t_now = 0.0
+    for k in range(8):
+        q = k % 6
+        r = sess.step(q)
+        euler = so.euler_download_delay(bw[0], 1.0, t_now, sizes[k][q], 1.0)
+        assert abs(euler - r["delay"]) <= 0.0101 + 1e-9
+        t_now += r["delay"] + r["sleep"]
