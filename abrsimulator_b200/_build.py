@@ -6,6 +6,7 @@ GPU box with the repo snapshot.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -13,6 +14,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libabr_b200.so")
+STAMP = LIB + ".srchash"
 SOURCES = ["abr_step.cu", "abr_mpc.cu", "abr_capi.cu"]
 HEADERS = [os.path.join(CSRC, "abr_common.cuh"), os.path.join(HERE, "..", "include", "abr_b200.h")]
 
@@ -27,12 +29,24 @@ def _nvcc():
     return None
 
 
+def _source_hash() -> str:
+    h = hashlib.sha256()
+    for d in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB):
+    """True when the .so is missing or was built from different sources (content hash, not mtimes: the
+    snapshot that travels to the GPU box does not preserve a meaningful mtime order)."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
-    deps = [d for d in deps if os.path.exists(d)]
-    return os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps)
+    try:
+        return open(STAMP).read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -49,4 +63,6 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(_source_hash())
     return LIB

@@ -57,8 +57,9 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path):
-        _build.build_library()          # raises if there is no nvcc: loud failure, no fallback
+    if _build.is_stale():
+        # missing or built from other sources: rebuild (raises if there is no nvcc — loud failure, no fallback)
+        _build.build_library(force=True)
     lib = C.CDLL(path)
     lib.abr_last_error.restype = C.c_char_p
     lib.abr_launch_count.restype = C.c_longlong
