@@ -10,9 +10,9 @@
 //                        streamed out with st.global.cs (41 B/step) — the fused-episode form.
 //  * abr_reset_kernel, abr_stats_* helpers.
 //
-// Trace bandwidths are read through the read-only path (ld.global.nc): a session re-reads consecutive
-// segments of one trace, so one 128 B line (16 segments) serves ~16 walk iterations out of L1, and the
-// whole trace table (<= 16 MB at the benchmark shape) stays resident in the 126 MB L2.
+// Trace data is read through the read-only path (ld.global.nc.v2.f64) from a per-segment (rate, capacity) table:
+// a session visits consecutive segments of one trace, so one 128 B line (8 segments) serves 8 walk iterations
+// out of L1, and the whole table (32 MB at the benchmark shape) stays resident in the 126 MB L2.
 #include "abr_common.cuh"
 
 namespace abr {
@@ -20,12 +20,13 @@ namespace abr {
 namespace {
 
 constexpr int kStepBlock = 256;
-constexpr int kRolloutBlock = 128;
+constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per SM (balanced over 148 SMs)
 constexpr int kStatsBlock = 256;
 constexpr int kStatsSessionsPerBlock = 8192;
+constexpr int kWalkBlock = ABR_WALK_PAD;   // segments fetched per walk block = padding of every table row
 
 struct Sess {
-    const double* __restrict__ bw;
+    const double2* __restrict__ rc;   // per segment: x = bw*payload (rate), y = rate*I (bytes a whole segment carries)
     double I, tau, buffer;
     int T, seg, chunk, last_q, hist_len;
     bool done;
@@ -37,7 +38,7 @@ struct StepRes {
 };
 
 // SPEC §3 for one session held in registers.  `q` must already be a valid index.
-__device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, StepRes& r) {
+__device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, StepRes& r, const bool want_thr) {
     const AbrParams& p = v.p;
     r.walk_error = false;
     r.reset_mpc = false;
@@ -51,30 +52,49 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     r.inert = false;
     const int A = v.A;
     const double size = __ldg(v.sizes + s.chunk * A + q);
-    // 3.1 segment walk (Simulator.py:158-163 in closed form, with wrap-around)
+    // 3.1 segment walk (Simulator.py:158-163 in closed form, with wrap-around).  rate = bw*payload and the
+    // whole-segment capacity rate*(I - 0) come from the table built at create time (identical IEEE products);
+    // only the first, partially consumed segment multiplies explicitly.  Each table row is followed by a copy of
+    // its first kWalkBlock entries, so a block of kWalkBlock segments is fetched with independent 16-byte loads
+    // at constant offsets (no per-iteration address or wrap arithmetic, all loads in flight together) and only
+    // the compare chain is sequential.  The one division happens after the loop has reconverged.
     double sent = 0.0, delay = 0.0, tau = s.tau;
-    int seg = s.seg;
-    int guard = 1 << 20;  // safety net only: every bandwidth is > 0, so the walk terminates
-    double bwv = __ldg(s.bw + seg);
-    for (;;) {
-        const double rate = dmul(bwv, p.payload);
-        const double room = dsub(s.I, tau);
-        const double cap = dmul(rate, room);
-        if (dadd(sent, cap) >= size) {
-            const double dt = ddiv(dsub(size, sent), rate);
-            delay = dadd(delay, dt);
-            tau = dadd(tau, dt);
-            break;
+    int seg = s.seg;                       // < T; the padded row makes seg + kWalkBlock readable
+    int guard = (1 << 20) / kWalkBlock;    // safety net only: every bandwidth is > 0, so the walk terminates
+    const double2* __restrict__ row = s.rc;
+    double rate = __ldg(row + seg).x;
+    double room = dsub(s.I, tau);
+    double s2 = dadd(sent, dmul(rate, room));
+    bool done = s2 >= size;
+    while (!done) {
+        double2 nx[kWalkBlock];
+#pragma unroll
+        for (int u = 0; u < kWalkBlock; ++u) nx[u] = __ldg(row + seg + 1 + u);
+        int adv = 0;
+#pragma unroll
+        for (int u = 0; u < kWalkBlock; ++u) {
+            if (!done) {
+                sent = s2;
+                delay = dadd(delay, room);
+                room = s.I;
+                rate = nx[u].x;
+                s2 = dadd(sent, nx[u].y);
+                adv = u + 1;
+                done = s2 >= size;
+            }
         }
-        sent = dadd(sent, cap);
-        delay = dadd(delay, room);
-        seg = (seg + 1 == s.T) ? 0 : seg + 1;
         tau = 0.0;
-        bwv = __ldg(s.bw + seg);
+        seg += adv;
+        if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
         if (--guard <= 0) { r.walk_error = true; break; }
     }
+    {
+        const double dt = ddiv(dsub(size, sent), rate);
+        delay = dadd(delay, dt);
+        tau = dadd(tau, dt);
+    }
     delay = dadd(delay, p.rtt);
-    r.thr = ddiv(size, delay);
+    r.thr = want_thr ? ddiv(size, delay) : 0.0;
     // 3.2 buffer drain / rebuffer
     const double rebuf = max0(dsub(delay, s.buffer));
     double buffer = dadd(max0(dsub(s.buffer, delay)), p.chunk_length);
@@ -86,7 +106,12 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         const double x = dadd(tau, sleep);
         const double n = floor(ddiv(x, s.I));
         tau = dsub(x, dmul(n, s.I));
-        seg = (int)(((long long)seg + (long long)n) % (long long)s.T);
+        if (n < 2147480000.0) {   // 32-bit fast path; the modulo only runs when the position wraps
+            const unsigned tot = (unsigned)seg + (unsigned)(int)n;
+            seg = tot >= (unsigned)s.T ? (int)(tot % (unsigned)s.T) : (int)tot;
+        } else {
+            seg = (int)(((long long)seg + (long long)n) % (long long)s.T);
+        }
         if (tau < 0.0) tau = 0.0;
         if (tau >= s.I) { tau = 0.0; seg = (seg + 1 == s.T) ? 0 : seg + 1; }
     }
@@ -132,7 +157,7 @@ __device__ __forceinline__ int policy_action(const EnvView& v, const Sess& s, in
 
 __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     const int tr = v.trace_id[i];
-    s.bw = v.trace_bw + (size_t)tr * v.T_max;
+    s.rc = v.trace_rc + (size_t)tr * (v.T_max + ABR_WALK_PAD);
     s.T = __ldg(v.trace_len + tr);
     s.I = __ldg(v.trace_interval + tr);
     s.seg = v.seg[i];
@@ -142,6 +167,22 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     s.buffer = v.buffer[i];
     s.done = v.p.auto_reset ? false : (v.done[i] != 0);
     s.hist_len = v.p.track_history ? v.hist_len[i] : 0;
+}
+
+// Builds the (rate, whole-segment capacity) table from the raw trace: the same two IEEE products SPEC §3.1
+// performs per segment, done once per environment instead of once per visit.
+__global__ void __launch_bounds__(kStepBlock)
+abr_trace_table_kernel(const double* __restrict__ bw, const int32_t* __restrict__ trace_len,
+                       const double* __restrict__ interval, int n_traces, int T_max, double payload,
+                       double2* __restrict__ rc) {
+    const int stride = T_max + ABR_WALK_PAD;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_traces * stride) return;
+    const int t = (int)(i / stride), j = (int)(i % stride);
+    const int T = trace_len[t];
+    const int seg = j % T;                 // entries past the end repeat the trace from its start (wrap-around)
+    const double rate = dmul(bw[(size_t)t * T_max + seg], payload);
+    rc[i] = make_double2(rate, dmul(rate, dsub(interval[t], 0.0)));
 }
 
 __global__ void __launch_bounds__(kStepBlock)
@@ -177,7 +218,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restric
     int q = action[i];
     if (q < 0 || q >= v.A) { atomicAdd(v.errors, 1ull); q = q < 0 ? 0 : v.A - 1; }
     StepRes r;
-    step_core(v, s, q, r);
+    step_core(v, s, q, r, v.p.track_history || o_thr != nullptr);
     if (r.walk_error) atomicAdd(v.errors, 1ull);
     if (!r.inert) {
         v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
@@ -230,7 +271,7 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
         int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t, actions_in, i);
         if (q < 0 || q >= v.A) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
         StepRes r;
-        step_core(v, s, q, r);
+        step_core(v, s, q, r, v.p.track_history != 0);
         flagged |= r.walk_error;
         const size_t ix = (size_t)t * n + i;
         if (o_delay) __stcs(o_delay + ix, r.delay);
@@ -304,6 +345,14 @@ abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __
 }
 
 }  // namespace
+
+cudaError_t launch_trace_table(const EnvView& v, double2* d_rc, cudaStream_t st) {
+    const size_t n = (size_t)v.n_traces * (v.T_max + ABR_WALK_PAD);
+    abr_trace_table_kernel<<<(unsigned)((n + kStepBlock - 1) / kStepBlock), kStepBlock, 0, st>>>(
+        v.trace_bw, v.trace_len, v.trace_interval, v.n_traces, v.T_max, v.p.payload, d_rc);
+    count_launch();
+    return cudaGetLastError();
+}
 
 cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st) {
     if (v.n == 0) return cudaSuccess;
