@@ -6,7 +6,8 @@
 #include <stdint.h>
 #include "../../include/abr_b200.h"
 
-#define ABR_WALK_PAD 8   // every (rate, capacity) table row is followed by a copy of its first 8 entries
+#define ABR_WALK_BLOCK 8                     // segments consumed per walk block
+#define ABR_WALK_PAD (2 * ABR_WALK_BLOCK + 1)  // every (rate, capacity) row is followed by a wrapped copy of its start
 
 namespace abr {
 

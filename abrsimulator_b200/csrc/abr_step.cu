@@ -23,7 +23,7 @@ constexpr int kStepBlock = 256;
 constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per SM (balanced over 148 SMs)
 constexpr int kStatsBlock = 256;
 constexpr int kStatsSessionsPerBlock = 8192;
-constexpr int kWalkBlock = ABR_WALK_PAD;   // segments fetched per walk block = padding of every table row
+constexpr int kWalkBlock = ABR_WALK_BLOCK;   // segments fetched per walk block (rows are padded by 2 blocks + 1)
 
 struct Sess {
     const double2* __restrict__ rc;   // per segment: x = bw*payload (rate), y = rate*I (bytes a whole segment carries)
@@ -59,34 +59,64 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     // at constant offsets (no per-iteration address or wrap arithmetic, all loads in flight together) and only
     // the compare chain is sequential.  The one division happens after the loop has reconverged.
     double sent = 0.0, delay = 0.0, tau = s.tau;
-    int seg = s.seg;                       // < T; the padded row makes seg + kWalkBlock readable
+    int seg = s.seg;                       // < T; the padded row makes seg + 2*kWalkBlock readable
     int guard = (1 << 20) / kWalkBlock;    // safety net only: every bandwidth is > 0, so the walk terminates
     const double2* __restrict__ row = s.rc;
-    double rate = __ldg(row + seg).x;
+    // cur = entries of segments seg+1 .. seg+kWalkBlock, requested together with the current segment's entry so
+    // that a typical step pays one memory round trip; nxt is fetched while cur is being consumed
+    double2 cur[kWalkBlock], nxt[kWalkBlock];
+    const double2 first = __ldg(row + seg);
+#pragma unroll
+    for (int u = 0; u < kWalkBlock; ++u) cur[u] = __ldg(row + seg + 1 + u);
+    double rate = first.x;
     double room = dsub(s.I, tau);
     double s2 = dadd(sent, dmul(rate, room));
-    bool done = s2 >= size;
-    while (!done) {
-        double2 nx[kWalkBlock];
+    if (!(s2 >= size)) {
+        for (;;) {
+            // seg + kWalkBlock may already be past T: the row padding (2*kWalkBlock) keeps the prefetch in bounds
 #pragma unroll
-        for (int u = 0; u < kWalkBlock; ++u) nx[u] = __ldg(row + seg + 1 + u);
-        int adv = 0;
+            for (int u = 0; u < kWalkBlock; ++u) nxt[u] = __ldg(row + seg + 1 + kWalkBlock + u);
+            // running totals after each of the block's segments: the same left-to-right additions as the
+            // segment-by-segment walk, but as one uninterrupted DADD chain (compares are off the chain)
+            double c[kWalkBlock];
+            c[0] = dadd(s2, cur[0].y);
 #pragma unroll
-        for (int u = 0; u < kWalkBlock; ++u) {
-            if (!done) {
-                sent = s2;
+            for (int u = 1; u < kWalkBlock; ++u) c[u] = dadd(c[u - 1], cur[u].y);
+            if (!(c[kWalkBlock - 1] >= size)) {
+                // the whole block is consumed: capacities are > 0, so no earlier total reached `size` either
                 delay = dadd(delay, room);
+#pragma unroll
+                for (int u = 1; u < kWalkBlock; ++u) delay = dadd(delay, s.I);
                 room = s.I;
-                rate = nx[u].x;
-                s2 = dadd(sent, nx[u].y);
-                adv = u + 1;
-                done = s2 >= size;
+                sent = c[kWalkBlock - 2];
+                s2 = c[kWalkBlock - 1];
+                rate = cur[kWalkBlock - 1].x;
+                seg += kWalkBlock;
+                if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
+#pragma unroll
+                for (int u = 0; u < kWalkBlock; ++u) cur[u] = nxt[u];
+                if (--guard <= 0) { r.walk_error = true; break; }
+                continue;
             }
+            // the download ends inside this block: first u with c[u] >= size
+            int adv = kWalkBlock;
+            double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1].x;
+            double d = dadd(delay, room), delay_f = d;
+#pragma unroll
+            for (int u = kWalkBlock - 1; u >= 0; --u) {
+                if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u].x; }
+            }
+#pragma unroll
+            for (int u = 1; u < kWalkBlock; ++u) {
+                d = dadd(d, s.I);
+                if (u < adv) delay_f = d;
+            }
+            sent = sent_f; rate = rate_f; delay = delay_f;
+            seg += adv;
+            if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
+            break;
         }
         tau = 0.0;
-        seg += adv;
-        if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
-        if (--guard <= 0) { r.walk_error = true; break; }
     }
     {
         const double dt = ddiv(dsub(size, sent), rate);
