@@ -176,10 +176,10 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     CUDA_TRY(cudaMemcpy(d_sizes, h_sizes, sizeof(double) * V * A, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice));
     v.trace_bw = d_bw; v.trace_len = d_len; v.trace_interval = d_int; v.sizes = d_sizes; v.util = d_util;
-    double2* d_rc;
-    CUDA_TRY(e->alloc(&d_rc, (size_t)n_traces * (T_max + ABR_WALK_PAD)));
-    v.trace_rc = d_rc;
-    CUDA_TRY(launch_trace_table(v, d_rc, 0));
+    double* d_rate;
+    CUDA_TRY(e->alloc(&d_rate, (size_t)n_traces * (T_max + ABR_WALK_PAD)));
+    v.trace_rate = d_rate;
+    CUDA_TRY(launch_trace_table(v, d_rate, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
     CUDA_TRY(e->alloc(&v.seg, cap)); CUDA_TRY(e->alloc(&v.chunk, cap)); CUDA_TRY(e->alloc(&v.last_q, cap));
     CUDA_TRY(e->alloc(&v.trace_id, cap)); CUDA_TRY(e->alloc(&v.hist_len, cap)); CUDA_TRY(e->alloc(&v.err_len, cap));

@@ -7,7 +7,7 @@
 #include "../../include/abr_b200.h"
 
 #define ABR_WALK_BLOCK 8                     // segments consumed per walk block
-#define ABR_WALK_PAD (2 * ABR_WALK_BLOCK + 1)  // every (rate, capacity) row is followed by a wrapped copy of its start
+#define ABR_WALK_PAD (2 * ABR_WALK_BLOCK + 2)  // every rate-table row is followed by a wrapped copy of its start
 
 namespace abr {
 
@@ -52,7 +52,7 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
 struct EnvView {
     // read-only tables
     const double* __restrict__ trace_bw;        // [n_traces][T_max]
-    const double2* __restrict__ trace_rc;       // [n_traces][T_max + ABR_WALK_PAD] (bw*payload, bw*payload*interval), wrapped
+    const double* __restrict__ trace_rate;      // [n_traces][T_max + ABR_WALK_PAD] bw*payload, rows wrapped
     const int32_t* __restrict__ trace_len;      // [n_traces]
     const double* __restrict__ trace_interval;  // [n_traces]
     const double* __restrict__ sizes;           // [V][A]
@@ -68,7 +68,7 @@ struct EnvView {
 };
 
 // launchers implemented in abr_step.cu / abr_mpc.cu (C++ linkage, internal)
-cudaError_t launch_trace_table(const EnvView& v, double2* d_rc, cudaStream_t st);
+cudaError_t launch_trace_table(const EnvView& v, double* d_rate, cudaStream_t st);
 cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st);
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
                         double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_eov, double* d_thr,

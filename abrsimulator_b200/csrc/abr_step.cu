@@ -10,9 +10,15 @@
 //                        streamed out with st.global.cs (41 B/step) — the fused-episode form.
 //  * abr_reset_kernel, abr_stats_* helpers.
 //
-// Trace data is read through the read-only path (ld.global.nc.v2.f64) from a per-segment (rate, capacity) table:
-// a session visits consecutive segments of one trace, so one 128 B line (8 segments) serves 8 walk iterations
-// out of L1, and the whole table (32 MB at the benchmark shape) stays resident in the 126 MB L2.
+// Trace data comes from a per-segment rate table (rate = bw*payload, the product SPEC §3.1 forms per visit, built
+// once per environment; every row is followed by a wrapped copy of its first ABR_WALK_PAD entries so a walk block
+// never needs wrap arithmetic).  Two access paths:
+//   * shared-memory path (fused episode): when all sessions of a thread block follow the same trace and its row
+//     fits, the block stages the row in shared memory once (coalesced 16-byte loads) and every walk of the
+//     episode reads it with LDS — the "traces staged in shared memory" design of the north star.  Per-lane
+//     scattered global loads cost one L1 wavefront per lane (32 per instruction); LDS costs 2-5.
+//   * global path (any session order, per-step kernel): read-only loads (ld.global.nc) with the next block
+//     prefetched while the current one is consumed; the table (17 MB at the benchmark shape) is L2-resident.
 #include "abr_common.cuh"
 
 namespace abr {
@@ -26,7 +32,7 @@ constexpr int kStatsSessionsPerBlock = 8192;
 constexpr int kWalkBlock = ABR_WALK_BLOCK;   // segments fetched per walk block (rows are padded by 2 blocks + 1)
 
 struct Sess {
-    const double2* __restrict__ rc;   // per segment: x = bw*payload (rate), y = rate*I (bytes a whole segment carries)
+    const double* __restrict__ rate;  // per segment: bw*payload; global row or its shared-memory copy
     double I, tau, buffer;
     int T, seg, chunk, last_q, hist_len;
     bool done;
@@ -37,7 +43,14 @@ struct StepRes {
     bool eov, inert, walk_error, reset_mpc;
 };
 
+template <bool SMEM>
+__device__ __forceinline__ double rate_at(const double* __restrict__ row, int idx) {
+    return SMEM ? row[idx] : __ldg(row + idx);
+}
+
 // SPEC §3 for one session held in registers.  `q` must already be a valid index.
+// SMEM: s.rate points at the block's shared-memory copy of the trace row (else at the global table).
+template <bool SMEM>
 __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, StepRes& r, const bool want_thr) {
     const AbrParams& p = v.p;
     r.walk_error = false;
@@ -52,36 +65,31 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     r.inert = false;
     const int A = v.A;
     const double size = __ldg(v.sizes + s.chunk * A + q);
-    // 3.1 segment walk (Simulator.py:158-163 in closed form, with wrap-around).  rate = bw*payload and the
-    // whole-segment capacity rate*(I - 0) come from the table built at create time (identical IEEE products);
-    // only the first, partially consumed segment multiplies explicitly.  Each table row is followed by a copy of
-    // its first kWalkBlock entries, so a block of kWalkBlock segments is fetched with independent 16-byte loads
-    // at constant offsets (no per-iteration address or wrap arithmetic, all loads in flight together) and only
-    // the compare chain is sequential.  The one division happens after the loop has reconverged.
+    // 3.1 segment walk (Simulator.py:158-163 in closed form, with wrap-around).  A block of kWalkBlock segments
+    // is fetched with independent loads at constant offsets (no per-iteration address or wrap arithmetic); each
+    // whole-segment capacity rate*(I - 0) is an independent product, so only the running-total additions form a
+    // dependent chain — the same left-to-right additions as the segment-by-segment walk.  The one division
+    // happens after the loop has reconverged.
     double sent = 0.0, delay = 0.0, tau = s.tau;
-    int seg = s.seg;                       // < T; the padded row makes seg + 2*kWalkBlock readable
+    int seg = s.seg;                       // < T; the row padding makes seg + 2*kWalkBlock readable
     int guard = (1 << 20) / kWalkBlock;    // safety net only: every bandwidth is > 0, so the walk terminates
-    const double2* __restrict__ row = s.rc;
-    // cur = entries of segments seg+1 .. seg+kWalkBlock, requested together with the current segment's entry so
-    // that a typical step pays one memory round trip; nxt is fetched while cur is being consumed
-    double2 cur[kWalkBlock], nxt[kWalkBlock];
-    const double2 first = __ldg(row + seg);
+    const double* __restrict__ row = s.rate;
+    double cur[kWalkBlock], nxt[kWalkBlock];
+    double rate = rate_at<SMEM>(row, seg);
 #pragma unroll
-    for (int u = 0; u < kWalkBlock; ++u) cur[u] = __ldg(row + seg + 1 + u);
-    double rate = first.x;
+    for (int u = 0; u < kWalkBlock; ++u) cur[u] = rate_at<SMEM>(row, seg + 1 + u);
     double room = dsub(s.I, tau);
     double s2 = dadd(sent, dmul(rate, room));
     if (!(s2 >= size)) {
         for (;;) {
-            // seg + kWalkBlock may already be past T: the row padding (2*kWalkBlock) keeps the prefetch in bounds
+            if (!SMEM) {   // global path: fetch the following block while this one is consumed
 #pragma unroll
-            for (int u = 0; u < kWalkBlock; ++u) nxt[u] = __ldg(row + seg + 1 + kWalkBlock + u);
-            // running totals after each of the block's segments: the same left-to-right additions as the
-            // segment-by-segment walk, but as one uninterrupted DADD chain (compares are off the chain)
+                for (int u = 0; u < kWalkBlock; ++u) nxt[u] = __ldg(row + seg + 1 + kWalkBlock + u);
+            }
             double c[kWalkBlock];
-            c[0] = dadd(s2, cur[0].y);
+            c[0] = dadd(s2, dmul(cur[0], s.I));
 #pragma unroll
-            for (int u = 1; u < kWalkBlock; ++u) c[u] = dadd(c[u - 1], cur[u].y);
+            for (int u = 1; u < kWalkBlock; ++u) c[u] = dadd(c[u - 1], dmul(cur[u], s.I));
             if (!(c[kWalkBlock - 1] >= size)) {
                 // the whole block is consumed: capacities are > 0, so no earlier total reached `size` either
                 delay = dadd(delay, room);
@@ -90,21 +98,21 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
                 room = s.I;
                 sent = c[kWalkBlock - 2];
                 s2 = c[kWalkBlock - 1];
-                rate = cur[kWalkBlock - 1].x;
+                rate = cur[kWalkBlock - 1];
                 seg += kWalkBlock;
                 if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
 #pragma unroll
-                for (int u = 0; u < kWalkBlock; ++u) cur[u] = nxt[u];
+                for (int u = 0; u < kWalkBlock; ++u) cur[u] = SMEM ? row[seg + 1 + u] : nxt[u];
                 if (--guard <= 0) { r.walk_error = true; break; }
                 continue;
             }
             // the download ends inside this block: first u with c[u] >= size
             int adv = kWalkBlock;
-            double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1].x;
+            double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1];
             double d = dadd(delay, room), delay_f = d;
 #pragma unroll
             for (int u = kWalkBlock - 1; u >= 0; --u) {
-                if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u].x; }
+                if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u]; }
             }
 #pragma unroll
             for (int u = 1; u < kWalkBlock; ++u) {
@@ -187,7 +195,7 @@ __device__ __forceinline__ int policy_action(const EnvView& v, const Sess& s, in
 
 __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     const int tr = v.trace_id[i];
-    s.rc = v.trace_rc + (size_t)tr * (v.T_max + ABR_WALK_PAD);
+    s.rate = v.trace_rate + (size_t)tr * (v.T_max + ABR_WALK_PAD);
     s.T = __ldg(v.trace_len + tr);
     s.I = __ldg(v.trace_interval + tr);
     s.seg = v.seg[i];
@@ -199,20 +207,16 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     s.hist_len = v.p.track_history ? v.hist_len[i] : 0;
 }
 
-// Builds the (rate, whole-segment capacity) table from the raw trace: the same two IEEE products SPEC §3.1
-// performs per segment, done once per environment instead of once per visit.
+// Builds the rate table from the raw trace: the IEEE product bw*payload SPEC §3.1 forms per segment visit,
+// done once per environment.  Entries past a trace's end repeat it from its start (wrap-around).
 __global__ void __launch_bounds__(kStepBlock)
-abr_trace_table_kernel(const double* __restrict__ bw, const int32_t* __restrict__ trace_len,
-                       const double* __restrict__ interval, int n_traces, int T_max, double payload,
-                       double2* __restrict__ rc) {
+abr_trace_table_kernel(const double* __restrict__ bw, const int32_t* __restrict__ trace_len, int n_traces, int T_max,
+                       double payload, double* __restrict__ rate) {
     const int stride = T_max + ABR_WALK_PAD;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)n_traces * stride) return;
     const int t = (int)(i / stride), j = (int)(i % stride);
-    const int T = trace_len[t];
-    const int seg = j % T;                 // entries past the end repeat the trace from its start (wrap-around)
-    const double rate = dmul(bw[(size_t)t * T_max + seg], payload);
-    rc[i] = make_double2(rate, dmul(rate, dsub(interval[t], 0.0)));
+    rate[i] = dmul(bw[(size_t)t * T_max + j % trace_len[t]], payload);
 }
 
 __global__ void __launch_bounds__(kStepBlock)
@@ -248,7 +252,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restric
     int q = action[i];
     if (q < 0 || q >= v.A) { atomicAdd(v.errors, 1ull); q = q < 0 ? 0 : v.A - 1; }
     StepRes r;
-    step_core(v, s, q, r, v.p.track_history || o_thr != nullptr);
+    step_core<false>(v, s, q, r, v.p.track_history || o_thr != nullptr);
     if (r.walk_error) atomicAdd(v.errors, 1ull);
     if (!r.inert) {
         v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
@@ -283,16 +287,16 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restric
     }
 }
 
-template <int POLICY>
-__global__ void __launch_bounds__(kRolloutBlock)
-abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
-                   double* __restrict__ o_delay, double* __restrict__ o_sleep, double* __restrict__ o_buffer,
-                   double* __restrict__ o_rebuf, double* __restrict__ o_reward, uint8_t* __restrict__ o_eov,
-                   int32_t* __restrict__ o_actions) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.n) return;
-    Sess s;
-    load_sess(v, i, s);
+struct RolloutOut {
+    double* __restrict__ delay; double* __restrict__ sleep; double* __restrict__ buffer; double* __restrict__ rebuf;
+    double* __restrict__ reward; uint8_t* __restrict__ eov; int32_t* __restrict__ actions;
+};
+
+// `steps` chunk steps of one session with the state in registers (SPEC §3+§4).
+template <int POLICY, bool SMEM>
+__device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const int i, const uint32_t seed_lo,
+                                                const uint32_t seed_hi, const int steps,
+                                                const int32_t* __restrict__ actions_in, const RolloutOut& o) {
     const unsigned long long gsession = (unsigned long long)(v.session_base + i);
     double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_steps = 0.0, a_eps = 0.0;
     bool flagged = false, reset_mpc = false;
@@ -301,16 +305,16 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
         int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t, actions_in, i);
         if (q < 0 || q >= v.A) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
         StepRes r;
-        step_core(v, s, q, r, v.p.track_history != 0);
+        step_core<SMEM>(v, s, q, r, v.p.track_history != 0);
         flagged |= r.walk_error;
         const size_t ix = (size_t)t * n + i;
-        if (o_delay) __stcs(o_delay + ix, r.delay);
-        if (o_sleep) __stcs(o_sleep + ix, r.sleep);
-        if (o_buffer) __stcs(o_buffer + ix, r.buffer);
-        if (o_rebuf) __stcs(o_rebuf + ix, r.rebuf);
-        if (o_reward) __stcs(o_reward + ix, r.reward);
-        if (o_eov) o_eov[ix] = r.eov ? 1 : 0;
-        if (o_actions) __stcs(o_actions + ix, q);
+        if (o.delay) __stcs(o.delay + ix, r.delay);
+        if (o.sleep) __stcs(o.sleep + ix, r.sleep);
+        if (o.buffer) __stcs(o.buffer + ix, r.buffer);
+        if (o.rebuf) __stcs(o.rebuf + ix, r.rebuf);
+        if (o.reward) __stcs(o.reward + ix, r.reward);
+        if (o.eov) o.eov[ix] = r.eov ? 1 : 0;
+        if (o.actions) __stcs(o.actions + ix, q);
         if (!r.inert) {
             a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
             a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
@@ -332,6 +336,45 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
     a[0 * c] = dadd(a[0 * c], a_rew); a[1 * c] = dadd(a[1 * c], a_reb); a[2 * c] = dadd(a[2 * c], a_u);
     a[3 * c] = dadd(a[3 * c], a_sm); a[4 * c] = dadd(a[4 * c], a_sl); a[5 * c] = dadd(a[5 * c], a_dl);
     a[6 * c] = dadd(a[6 * c], a_steps); a[7 * c] = dadd(a[7 * c], a_eps);
+}
+
+// smem_doubles: capacity of the dynamic shared-memory row buffer (0 disables the shared-memory path).
+template <int POLICY>
+__global__ void __launch_bounds__(kRolloutBlock)
+abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
+                   RolloutOut o, int smem_doubles) {
+    extern __shared__ double2 s_row2[];
+    __shared__ int s_tr0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < v.n;
+    Sess s;
+    int tr = -1;
+    if (valid) { load_sess(v, i, s); tr = v.trace_id[i]; }
+    if (threadIdx.x == 0) s_tr0 = tr;            // thread 0 of a launched block is always a valid session
+    __syncthreads();
+    const int tr0 = s_tr0;
+    // block-uniform: every session of this block follows trace tr0 and its padded row fits
+    const int need = __ldg(v.trace_len + tr0) + ABR_WALK_PAD;
+    const bool use_smem = __syncthreads_and((!valid || tr == tr0) ? 1 : 0) && need <= smem_doubles;
+    if (use_smem) {
+        const size_t row_off = (size_t)tr0 * (v.T_max + ABR_WALK_PAD);   // rows start 16-byte aligned when the stride is even
+        const double* __restrict__ g = v.trace_rate + row_off;
+        double* s_row = reinterpret_cast<double*>(s_row2);
+        if (((row_off & 1) == 0)) {
+            const double2* __restrict__ g2 = reinterpret_cast<const double2*>(g);
+            for (int j = threadIdx.x; j < need / 2; j += blockDim.x) s_row2[j] = __ldg(g2 + j);
+            if ((need & 1) && threadIdx.x == 0) s_row[need - 1] = __ldg(g + need - 1);
+        } else {
+            for (int j = threadIdx.x; j < need; j += blockDim.x) s_row[j] = __ldg(g + j);
+        }
+        __syncthreads();
+        if (valid) {
+            s.rate = s_row;
+            rollout_session<POLICY, true>(v, s, i, seed_lo, seed_hi, steps, actions_in, o);
+        }
+    } else if (valid) {
+        rollout_session<POLICY, false>(v, s, i, seed_lo, seed_hi, steps, actions_in, o);
+    }
 }
 
 // ---- statistics: deterministic two-stage reduction of acc[ABR_NUM_ACC][n] (SPEC §6) ----
@@ -376,10 +419,10 @@ abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __
 
 }  // namespace
 
-cudaError_t launch_trace_table(const EnvView& v, double2* d_rc, cudaStream_t st) {
+cudaError_t launch_trace_table(const EnvView& v, double* d_rate, cudaStream_t st) {
     const size_t n = (size_t)v.n_traces * (v.T_max + ABR_WALK_PAD);
     abr_trace_table_kernel<<<(unsigned)((n + kStepBlock - 1) / kStepBlock), kStepBlock, 0, st>>>(
-        v.trace_bw, v.trace_len, v.trace_interval, v.n_traces, v.T_max, v.p.payload, d_rc);
+        v.trace_bw, v.trace_len, v.n_traces, v.T_max, v.p.payload, d_rate);
     count_launch();
     return cudaGetLastError();
 }
@@ -407,9 +450,14 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     if (v.n == 0 || steps <= 0) return cudaSuccess;
     const dim3 grid((v.n + kRolloutBlock - 1) / kRolloutBlock), block(kRolloutBlock);
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+    RolloutOut o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out};
+    // shared-memory row buffer: the longest padded row when it leaves room for >= 7 blocks per SM, else disabled
+    int smem_doubles = v.T_max + ABR_WALK_PAD;
+    smem_doubles += smem_doubles & 1;
+    size_t smem_bytes = (size_t)smem_doubles * sizeof(double);
+    if (smem_bytes > 32 * 1024) { smem_doubles = 0; smem_bytes = 0; }
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
-    abr_rollout_kernel<P><<<grid, block, 0, st>>>(v, lo, hi, steps, d_actions_in, d_delay, d_sleep, d_buffer,       \
-                                                  d_rebuf, d_reward, d_eov, d_actions_out)
+    abr_rollout_kernel<P><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o, smem_doubles)
     switch (policy) {
         case ABR_POLICY_FIXED: ABR_LAUNCH_ROLLOUT(ABR_POLICY_FIXED); break;
         case ABR_POLICY_RANDOM: ABR_LAUNCH_ROLLOUT(ABR_POLICY_RANDOM); break;

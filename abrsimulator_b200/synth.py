@@ -32,11 +32,13 @@ def make_traces(n_traces=1024, T=2048, interval=1.0, seed=1234):
     return (np.ascontiguousarray(bw), np.full(n_traces, T, np.int32), np.full(n_traces, float(interval)))
 
 
-def make_sessions(n_sessions, n_traces, T, interval=1.0, seed=42, session_base=0):
-    """trace_id = global session index mod n_traces; start offset ~ U(0, T·interval).  Sharding-invariant:
-    session g always gets the same draw regardless of which rank owns it."""
+def make_sessions(n_sessions, n_traces, T, interval=1.0, seed=42, session_base=0, group=1):
+    """trace_id = (global session index // group) mod n_traces; start offset ~ U(0, T·interval).
+    ``group`` consecutive sessions share a trace (group = 64 lets every 64-thread block of the fused episode
+    kernel stage its trace in shared memory).  Sharding-invariant: session g always gets the same draw
+    regardless of which rank owns it."""
     g = np.arange(session_base, session_base + n_sessions, dtype=np.int64)
-    trace_id = (g % n_traces).astype(np.int32)
+    trace_id = ((g // group) % n_traces).astype(np.int32)
     # counter-based draw so that shards agree with the unsharded run
     u = ((g * 2654435761 + seed * 40503) % 2**32).astype(np.float64) / 2**32
     return trace_id, np.ascontiguousarray(u * T * interval)

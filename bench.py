@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 V, A = 48, 6
 N_TRACES, T_TRACE = 1024, 2048
 SEED = 7
+GROUP = 64                          # consecutive sessions per trace (one 64-thread block = one trace)
 BYTES_PER_STEP = 5 * 8 + 1          # delay, sleep, buffer, rebuf, reward (f64) + end_of_video (u8)
 BYTES_PER_SESSION = 32 + 28 + 128   # state load + state store + accumulator read-modify-write, once per episode
 
@@ -56,7 +57,7 @@ def _py_step_worker(job):
     lo, hi, budget_s = job
     bitrates, sizes = synth.make_video(V)
     bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
-    tid, off = synth.make_sessions(hi - lo, N_TRACES, T_TRACE, session_base=lo)
+    tid, off = synth.make_sessions(hi - lo, N_TRACES, T_TRACE, session_base=lo, group=GROUP)
     P = dict(orc.DEFAULTS)
     util = (bitrates * P["utility_scale"]).tolist()
     sz = sizes.tolist()
@@ -96,7 +97,7 @@ def cpu_c_oracle_steps(n_sessions=8192):
     from oracle import oracle as orc
     bitrates, sizes = synth.make_video(V)
     bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
-    tid, off = synth.make_sessions(n_sessions, N_TRACES, T_TRACE)
+    tid, off = synth.make_sessions(n_sessions, N_TRACES, T_TRACE, group=GROUP)
     env = orc.OracleEnv(bw, tl, ti, sizes, bitrates, n_sessions)
     env.reset(tid, off)
     t0 = time.perf_counter()
@@ -174,7 +175,7 @@ def run_reference(args):
 def workload_config(args):
     return dict(workload="configs[1]: random-policy chunk-step sweep, fused 48-chunk episodes",
                 sessions_per_gpu=args.sessions, chunks=V, bitrates=A, n_traces=N_TRACES, trace_segments=T_TRACE,
-                policy="random(philox)", outputs="delay,sleep,buffer,rebuffer,reward,end_of_video",
+                policy="random(philox)", sessions_per_trace=GROUP, outputs="delay,sleep,buffer,rebuffer,reward,end_of_video",
                 l2="256 MiB buffer rewritten between timed steps (outside the timed region)")
 
 
@@ -252,7 +253,7 @@ def run_ours(args):
     base = rank * N
     bitrates, sizes = synth.make_video(V)
     bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
-    tid_h, off_h = synth.make_sessions(N, N_TRACES, T_TRACE, session_base=base)
+    tid_h, off_h = synth.make_sessions(N, N_TRACES, T_TRACE, session_base=base, group=GROUP)
     env = BatchedABREnv(bw, sizes, bitrates, max(N, args.mpc_sessions), trace_len=tl, trace_interval=ti)
     tid_d = torch.from_numpy(tid_h).to(dev)
     off_d = torch.from_numpy(off_h).to(dev)
@@ -375,7 +376,7 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
     bitrates, sizes = synth.make_video(V)
     bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
     menv = BatchedABREnv(bw, sizes, bitrates, M, trace_len=tl, trace_interval=ti, track_history=1, track_acc=1)
-    tid, off = synth.make_sessions(M, N_TRACES, T_TRACE, session_base=rank * M)
+    tid, off = synth.make_sessions(M, N_TRACES, T_TRACE, session_base=rank * M, group=GROUP)
     menv.reset(tid, off, session_base=rank * M)
     menv.rollout("bba", 8, want=())                              # fill the throughput-history ring
     act = torch.empty(M, dtype=torch.int32, device=dev)

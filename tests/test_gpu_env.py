@@ -129,6 +129,33 @@ def test_fused_rollout_matches_oracle(policy):
     assert env.error_count() == 0
 
 
+@pytest.mark.parametrize("ragged", [False, True])
+def test_fused_rollout_shared_memory_trace_path(ragged):
+    """Blocks of 64 consecutive sessions on one trace take the shared-memory staged path; blocks with mixed
+    traces (and the last, partial block) take the global path — both must match the oracle bit for bit."""
+    N, steps = 64 * 40 + 17, 60
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=12, T=300, ragged=ragged)
+    params = dict(track_history=1)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, **params)
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **params)
+    rng = np.random.default_rng(21)
+    tid = ((np.arange(N) // 64) % 12).astype(np.int32)
+    tid[64 * 30:64 * 36] = rng.integers(0, 12, size=64 * 6)        # six mixed blocks -> global path
+    off = rng.uniform(0, 900.0, size=N)
+    env.reset(tid, off)
+    ref.reset(tid, off)
+    got = env.rollout("random", steps, seed=99)
+    exp = ref.rollout(orc.POLICY_RANDOM, steps, seed=99)
+    assert np.array_equal(got["actions"].cpu().numpy(), exp["actions"])
+    for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                     ("reward", "reward")):
+        assert_close(got[k_g].cpu().numpy(), exp[k_c], k_g)
+    assert_close(env.session_acc().cpu().numpy(), exp["acc"], "acc")
+    check_state(env, ref)
+    assert bits_equal(env.state("bw_hist").cpu().numpy().T[:, :], ref.field("bw_hist")) == 0
+    assert env.error_count() == 0
+
+
 def test_fused_rollout_equals_stepwise():
     """Size-independent property: the fused episode is the per-step kernel applied `steps` times."""
     N, steps = 2048, 48
@@ -227,7 +254,7 @@ def test_full_size_properties_65536x48():
     N, steps = 65536, 48
     bitrates, sizes = synth.make_video(48)
     bw, tl, ti = synth.make_traces(1024, 2048)
-    tid, off = synth.make_sessions(N, 1024, 2048)
+    tid, off = synth.make_sessions(N, 1024, 2048, group=64)
     env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
     env.reset(tid, off)
     out = env.rollout("random", steps, seed=7)
