@@ -29,6 +29,15 @@ __device__ __forceinline__ double max0(double x) {
     return __hiloint2double(hi & keep, lo & keep);
 }
 
+// 1/d when d is a power of two in [2^-500, 2^500] (then x/d == x*(1/d) exactly for every finite x whose
+// quotient is a normal number; the callers' operands are seconds, far from the fp64 range limits), else 0.
+__device__ __forceinline__ double pow2_inverse(double d) {
+    const int hi = __double2hiint(d), lo = __double2loint(d);
+    const int e = (hi >> 20) & 0x7ff;
+    if (lo != 0 || (hi & 0x800fffff) != 0 || e < 523 || e > 1523) return 0.0;
+    return __hiloint2double((2046 - e) << 20, 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (SPEC §4); identical to oracle/abr_oracle.c:orc_philox4x32_10
 // ---------------------------------------------------------------------------------------------

@@ -80,50 +80,48 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     for (int u = 0; u < kWalkBlock; ++u) cur[u] = rate_at<SMEM>(row, seg + 1 + u);
     double room = dsub(s.I, tau);
     double s2 = dadd(sent, dmul(rate, room));
-    if (!(s2 >= size)) {
+    const bool multi = !(s2 >= size);      // the current segment does not finish the chunk
+    double c[kWalkBlock];
+    if (multi) {
         for (;;) {
             if (!SMEM) {   // global path: fetch the following block while this one is consumed
 #pragma unroll
                 for (int u = 0; u < kWalkBlock; ++u) nxt[u] = __ldg(row + seg + 1 + kWalkBlock + u);
             }
-            double c[kWalkBlock];
             c[0] = dadd(s2, dmul(cur[0], s.I));
 #pragma unroll
             for (int u = 1; u < kWalkBlock; ++u) c[u] = dadd(c[u - 1], dmul(cur[u], s.I));
-            if (!(c[kWalkBlock - 1] >= size)) {
-                // the whole block is consumed: capacities are > 0, so no earlier total reached `size` either
-                delay = dadd(delay, room);
+            if (c[kWalkBlock - 1] >= size) break;   // the download ends inside this block (c, cur stay live)
+            // the whole block is consumed: capacities are > 0, so no earlier total reached `size` either
+            delay = dadd(delay, room);
 #pragma unroll
-                for (int u = 1; u < kWalkBlock; ++u) delay = dadd(delay, s.I);
-                room = s.I;
-                sent = c[kWalkBlock - 2];
-                s2 = c[kWalkBlock - 1];
-                rate = cur[kWalkBlock - 1];
-                seg += kWalkBlock;
-                if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
-#pragma unroll
-                for (int u = 0; u < kWalkBlock; ++u) cur[u] = SMEM ? row[seg + 1 + u] : nxt[u];
-                if (--guard <= 0) { r.walk_error = true; break; }
-                continue;
-            }
-            // the download ends inside this block: first u with c[u] >= size
-            int adv = kWalkBlock;
-            double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1];
-            double d = dadd(delay, room), delay_f = d;
-#pragma unroll
-            for (int u = kWalkBlock - 1; u >= 0; --u) {
-                if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u]; }
-            }
-#pragma unroll
-            for (int u = 1; u < kWalkBlock; ++u) {
-                d = dadd(d, s.I);
-                if (u < adv) delay_f = d;
-            }
-            sent = sent_f; rate = rate_f; delay = delay_f;
-            seg += adv;
+            for (int u = 1; u < kWalkBlock; ++u) delay = dadd(delay, s.I);
+            room = s.I;
+            s2 = c[kWalkBlock - 1];
+            seg += kWalkBlock;
             if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
-            break;
+#pragma unroll
+            for (int u = 0; u < kWalkBlock; ++u) cur[u] = SMEM ? row[seg + 1 + u] : nxt[u];
+            if (--guard <= 0) { r.walk_error = true; break; }
         }
+    }
+    // every lane has reconverged here; lanes that walked pick the first u with c[u] >= size, once
+    if (multi) {
+        int adv = kWalkBlock;
+        double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1];
+        double d = dadd(delay, room), delay_f = d;
+#pragma unroll
+        for (int u = kWalkBlock - 1; u >= 0; --u) {
+            if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u]; }
+        }
+#pragma unroll
+        for (int u = 1; u < kWalkBlock; ++u) {
+            d = dadd(d, s.I);
+            if (u < adv) delay_f = d;
+        }
+        sent = sent_f; rate = rate_f; delay = delay_f;
+        seg += adv;
+        if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
         tau = 0.0;
     }
     {
@@ -139,10 +137,15 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     // 3.3 sleep cap
     double sleep = 0.0;
     if (buffer > p.max_buffer) {
-        sleep = dmul(ceil(ddiv(dsub(buffer, p.max_buffer), p.sleep_quantum)), p.sleep_quantum);
+        // x / d == x * (1/d) bit for bit when d is a power of two (barring over/underflow, excluded by the range
+        // check in pow2_inverse), which saves the two divisions of this path for the usual 0.5 s / 1 s settings
+        const double over = dsub(buffer, p.max_buffer);
+        const double inv_q = pow2_inverse(p.sleep_quantum);
+        sleep = dmul(ceil(inv_q != 0.0 ? dmul(over, inv_q) : ddiv(over, p.sleep_quantum)), p.sleep_quantum);
         buffer = dsub(buffer, sleep);
         const double x = dadd(tau, sleep);
-        const double n = floor(ddiv(x, s.I));
+        const double inv_i = pow2_inverse(s.I);
+        const double n = floor(inv_i != 0.0 ? dmul(x, inv_i) : ddiv(x, s.I));
         tau = dsub(x, dmul(n, s.I));
         if (n < 2147480000.0) {   // 32-bit fast path; the modulo only runs when the position wraps
             const unsigned tot = (unsigned)seg + (unsigned)(int)n;
