@@ -48,7 +48,8 @@ __device__ __forceinline__ void interior(double& vq, double& qv, double& rt, dou
 // Search all A^h sequences for one session; h >= 2.  sU/sRB/sDL are [h][A] tables in shared memory,
 // sAD is |U[h-1][a] - U[h-1][a']| as [a][a'] (the leaf-level smoothness term).
 // AT > 0: compile-time ladder size (loops fully unrolled); AT == 0: runtime A (generic path).
-template <int AT, bool CLAMP>
+// VW1: smooth_penalty == 1.0, so vw*qv == qv exactly and the multiply is dropped.
+template <int AT, bool CLAMP, bool VW1>
 __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const double* __restrict__ sRB,
                                             const double* __restrict__ sDL, const double* __restrict__ sAD,
                                             const int a_rt, const int h, const int prev_q, const double buf0,
@@ -61,14 +62,11 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
     int n_prefix = 1;
     for (int i = 0; i < P; ++i) n_prefix *= A;
     const int i4 = h - 2, i5 = h - 1;
-    // last two table rows are uniform across threads and prefixes: keep them in registers
-    double U4[AR], RB4[AR], DL4[AR], U5[AR], RB5[AR];
+    // the leaf-level rows are uniform across threads and prefixes and read A times per prefix: keep them in registers
+    double U5[AR], RB5[AR];
     if (REGTAB) {
 #pragma unroll
-        for (int a = 0; a < AR; ++a) {
-            U4[a] = sU[i4 * A + a]; RB4[a] = sRB[i4 * A + a]; DL4[a] = sDL[i4 * A + a];
-            U5[a] = sU[i5 * A + a]; RB5[a] = sRB[i5 * A + a];
-        }
+        for (int a = 0; a < AR; ++a) { U5[a] = sU[i5 * A + a]; RB5[a] = sRB[i5 * A + a]; }
     }
     double best_q = __longlong_as_double(0xfff0000000000000ll);  // -inf
     int best_idx = 0x7fffffff;
@@ -96,19 +94,21 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
         }
         const double up4 = ap >= 0 ? sU[i4 * A + ap] : 0.0;
         const int base = p * A * A;
-#pragma unroll
+        // a4 is a rolled loop on purpose: unrolling both levels makes ptxas keep all A*A leaves in flight
+        // (~240 registers, 2 warps per scheduler); A independent leaves already cover the fp64 latency
+#pragma unroll 1
         for (int a4 = 0; a4 < A; ++a4) {
-            const double u4 = REGTAB ? U4[a4] : sU[i4 * A + a4];
+            const double u4 = sU[i4 * A + a4];   // uniform address: one broadcast LDS per warp
             double vq4 = vq, qv4 = qv, rt4 = rt, b4 = b;
             interior<CLAMP>(vq4, qv4, rt4, b4, u4, ap >= 0 ? fabs(dsub(u4, up4)) : 0.0,
-                            REGTAB ? RB4[a4] : sRB[i4 * A + a4], REGTAB ? DL4[a4] : sDL[i4 * A + a4], L, B);
+                            sRB[i4 * A + a4], sDL[i4 * A + a4], L, B);
 #pragma unroll
             for (int a5 = 0; a5 < A; ++a5) {
                 const double vq5 = dadd(vq4, REGTAB ? U5[a5] : sU[i5 * A + a5]);
                 const double qv5 = dadd(qv4, sAD[a5 * A + a4]);
                 const double d = dsub(REGTAB ? RB5[a5] : sRB[i5 * A + a5], b4);
                 const double rt5 = dadd(rt4, CLAMP ? max0(d) : d);
-                const double q = dsub(dsub(vq5, dmul(vw, qv5)), dmul(rw, rt5));  // J = -q, mpc.py:158-162
+                const double q = dsub(dsub(vq5, VW1 ? qv5 : dmul(vw, qv5)), dmul(rw, rt5));  // J = -q, mpc.py:158-162
                 if (q > best_q) { best_q = q; best_idx = base + a4 * A + a5; }  // strict: first minimum of J
             }
         }
@@ -131,7 +131,7 @@ struct __align__(8) SessShared {
 // AT = compile-time ladder size (0 = runtime A), CLAMP = robust mode (SPEC §5.2) — one kernel per shape so
 // that each gets its own register allocation.
 template <int WPS, int AT, bool CLAMP>
-__global__ void __launch_bounds__(32 * kMpcWarpsPerBlock)
+__global__ void __launch_bounds__(32 * kMpcWarpsPerBlock, 4)
 abr_mpc_kernel(const MpcArgs a) {
     constexpr int SPB = kMpcWarpsPerBlock / WPS;
     __shared__ SessShared sh[SPB];
@@ -265,8 +265,12 @@ abr_mpc_kernel(const MpcArgs a) {
                 }
                 o.q = bq; o.idx = bi;
             } else {
-                o = search<AT, CLAMP>(S.U, S.RB, S.DL, S.AD, A, h, prev_q, buf0, p.smooth_penalty, p.rebuf_penalty, L, B,
-                                      tid, NT);
+                if (p.smooth_penalty == 1.0)
+                    o = search<AT, CLAMP, true>(S.U, S.RB, S.DL, S.AD, A, h, prev_q, buf0, 1.0, p.rebuf_penalty, L, B,
+                                                tid, NT);
+                else
+                    o = search<AT, CLAMP, false>(S.U, S.RB, S.DL, S.AD, A, h, prev_q, buf0, p.smooth_penalty,
+                                                 p.rebuf_penalty, L, B, tid, NT);
             }
             // ---- argmin over the session's threads: key (J, linear index) ----
 #pragma unroll

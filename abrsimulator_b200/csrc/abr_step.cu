@@ -28,7 +28,7 @@ namespace {
 constexpr int kStepBlock = 256;
 constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per SM (balanced over 148 SMs)
 constexpr int kStatsBlock = 256;
-constexpr int kStatsSessionsPerBlock = 8192;
+constexpr int kStatsSessionsPerBlock = 1024;   // 64 blocks at 65 536 sessions: enough loads in flight to hide HBM latency
 constexpr int kWalkBlock = ABR_WALK_BLOCK;   // segments fetched per walk block (rows are padded by 2 blocks + 1)
 
 struct Sess {
@@ -401,11 +401,17 @@ abr_stats_stage1(EnvView v, double* __restrict__ partials) {
     __shared__ double sm[32];
     const int lo = blockIdx.x * kStatsSessionsPerBlock;
     const int hi = min(v.n, lo + kStatsSessionsPerBlock);
+    // all rows' loads are issued before any reduction so that one block keeps 8 x 4 loads per thread in flight
+    double x[ABR_NUM_ACC];
+#pragma unroll
     for (int j = 0; j < ABR_NUM_ACC; ++j) {
-        double x = 0.0;
-        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) x = dadd(x, v.acc[(size_t)j * v.cap + i]);
-        x = block_sum(x, sm);
-        if (threadIdx.x == 0) partials[(size_t)blockIdx.x * ABR_NUM_ACC + j] = x;
+        x[j] = 0.0;
+        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) x[j] = dadd(x[j], v.acc[(size_t)j * v.cap + i]);
+    }
+#pragma unroll
+    for (int j = 0; j < ABR_NUM_ACC; ++j) {
+        const double t = block_sum(x[j], sm);
+        if (threadIdx.x == 0) partials[(size_t)blockIdx.x * ABR_NUM_ACC + j] = t;
     }
 }
 
