@@ -177,7 +177,7 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     CUDA_TRY(cudaMemcpy(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice));
     v.trace_bw = d_bw; v.trace_len = d_len; v.trace_interval = d_int; v.sizes = d_sizes; v.util = d_util;
     double* d_rate;
-    CUDA_TRY(e->alloc(&d_rate, (size_t)n_traces * (T_max + ABR_WALK_PAD)));
+    CUDA_TRY(e->alloc(&d_rate, (size_t)n_traces * rate_stride(T_max)));
     v.trace_rate = d_rate;
     CUDA_TRY(launch_trace_table(v, d_rate, 0));
     CUDA_TRY(cudaStreamSynchronize(0));

@@ -7,9 +7,12 @@
 #include "../../include/abr_b200.h"
 
 #define ABR_WALK_BLOCK 8                     // segments consumed per walk block
-#define ABR_WALK_PAD (2 * ABR_WALK_BLOCK + 2)  // every rate-table row is followed by a wrapped copy of its start
+#define ABR_WALK_PAD (2 * ABR_WALK_BLOCK + 4)  // every rate-table row is followed by a wrapped copy of its start
 
 namespace abr {
+
+// row stride of the rate table in doubles: padded and even, so every row starts 16-byte aligned
+__host__ __device__ __forceinline__ int rate_stride(int T_max) { return (T_max + ABR_WALK_PAD + 1) & ~1; }
 
 // ---------------------------------------------------------------------------------------------
 // exact fp64 helpers
@@ -41,8 +44,8 @@ __device__ __forceinline__ double pow2_inverse(double d) {
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (SPEC §4); identical to oracle/abr_oracle.c:orc_philox4x32_10
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                                 uint32_t k1) {
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -52,7 +55,7 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += W0; k1 += W1;
     }
-    return c0;
+    return make_uint4(c0, c1, c2, c3);
 }
 
 // ---------------------------------------------------------------------------------------------

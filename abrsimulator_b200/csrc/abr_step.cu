@@ -43,14 +43,40 @@ struct StepRes {
     bool eov, inert, walk_error, reset_mpc;
 };
 
+// Rate-table rows start 16-byte aligned (even stride), so N consecutive entries starting at any index are fetched
+// as ceil((N+1)/2) aligned 16-byte loads from the even index below and picked apart with selects: 5 scattered
+// global loads (one L1 wavefront per lane each) instead of 9 for the first block of a step.
 template <bool SMEM>
-__device__ __forceinline__ double rate_at(const double* __restrict__ row, int idx) {
-    return SMEM ? row[idx] : __ldg(row + idx);
+__device__ __forceinline__ double2 rate2_at(const double* __restrict__ row, int even_idx) {
+    const double2* p = reinterpret_cast<const double2*>(row + even_idx);
+    return SMEM ? *p : __ldg(p);
+}
+
+template <bool SMEM, int N>
+__device__ __forceinline__ void load_rates(const double* __restrict__ row, int idx, double (&out)[N]) {
+    if (SMEM) {   // shared memory: scalar 8-byte loads are cheaper than vector loads plus the selects below
+#pragma unroll
+        for (int u = 0; u < N; ++u) out[u] = row[idx + u];
+        return;
+    }
+    constexpr int NV = (N + 2) / 2;
+    const int odd = idx & 1;
+    double2 v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = rate2_at<SMEM>(row, idx - odd + 2 * k);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const double even_case = (u & 1) ? v[u / 2].y : v[u / 2].x;                    // flat[idx - 0 + u]
+        const double odd_case = ((u + 1) & 1) ? v[(u + 1) / 2].y : v[(u + 1) / 2].x;   // flat[idx - 1 + u + 1]
+        out[u] = odd ? odd_case : even_case;
+    }
 }
 
 // SPEC §3 for one session held in registers.  `q` must already be a valid index.
 // SMEM: s.rate points at the block's shared-memory copy of the trace row (else at the global table).
-template <bool SMEM>
+// PREFETCH: fetch the following block while the current one is consumed (pays off when few warps are resident,
+// i.e. the fused episode on the global path; the per-step kernel hides the latency with occupancy instead).
+template <bool SMEM, bool PREFETCH>
 __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, StepRes& r, const bool want_thr) {
     const AbrParams& p = v.p;
     r.walk_error = false;
@@ -74,20 +100,23 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     int seg = s.seg;                       // < T; the row padding makes seg + 2*kWalkBlock readable
     int guard = (1 << 20) / kWalkBlock;    // safety net only: every bandwidth is > 0, so the walk terminates
     const double* __restrict__ row = s.rate;
-    double cur[kWalkBlock], nxt[kWalkBlock];
-    double rate = rate_at<SMEM>(row, seg);
+    double cur[kWalkBlock];
+    double rate;
+    {
+        double head[kWalkBlock + 1];       // the current segment and the block after it, one round trip
+        load_rates<SMEM, kWalkBlock + 1>(row, seg, head);
+        rate = head[0];
 #pragma unroll
-    for (int u = 0; u < kWalkBlock; ++u) cur[u] = rate_at<SMEM>(row, seg + 1 + u);
+        for (int u = 0; u < kWalkBlock; ++u) cur[u] = head[u + 1];
+    }
     double room = dsub(s.I, tau);
     double s2 = dadd(sent, dmul(rate, room));
     const bool multi = !(s2 >= size);      // the current segment does not finish the chunk
     double c[kWalkBlock];
     if (multi) {
         for (;;) {
-            if (!SMEM) {   // global path: fetch the following block while this one is consumed
-#pragma unroll
-                for (int u = 0; u < kWalkBlock; ++u) nxt[u] = __ldg(row + seg + 1 + kWalkBlock + u);
-            }
+            double nxt[kWalkBlock];
+            if (PREFETCH) load_rates<SMEM, kWalkBlock>(row, seg + 1 + kWalkBlock, nxt);   // overlap with this block
             c[0] = dadd(s2, dmul(cur[0], s.I));
 #pragma unroll
             for (int u = 1; u < kWalkBlock; ++u) c[u] = dadd(c[u - 1], dmul(cur[u], s.I));
@@ -100,8 +129,12 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
             s2 = c[kWalkBlock - 1];
             seg += kWalkBlock;
             if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
+            if (PREFETCH) {
 #pragma unroll
-            for (int u = 0; u < kWalkBlock; ++u) cur[u] = SMEM ? row[seg + 1 + u] : nxt[u];
+                for (int u = 0; u < kWalkBlock; ++u) cur[u] = nxt[u];
+            } else {
+                load_rates<SMEM, kWalkBlock>(row, seg + 1, cur);
+            }
             if (--guard <= 0) { r.walk_error = true; break; }
         }
     }
@@ -179,14 +212,19 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     }
 }
 
+// SPEC §4.  The random policy draws one Philox4x32-10 block per four steps (counter = (session, step / 4)) and uses
+// word step % 4, so the generator costs a quarter of a call per step; `rnd` caches the block between steps.
 __device__ __forceinline__ int policy_action(const EnvView& v, const Sess& s, int policy, uint32_t seed_lo,
                                              uint32_t seed_hi, unsigned long long gsession, int step,
-                                             const int32_t* __restrict__ actions_in, int sidx) {
+                                             const int32_t* __restrict__ actions_in, int sidx, uint4& rnd) {
     const int A = v.A;
     if (policy == ABR_POLICY_FIXED) return __ldg(actions_in + (size_t)step * v.n + sidx);
     if (policy == ABR_POLICY_RANDOM) {
-        const uint32_t x = philox_first((uint32_t)gsession, (uint32_t)(gsession >> 32), (uint32_t)step, 0u, seed_lo,
-                                        seed_hi);
+        const int w = step & 3;
+        if (w == 0)
+            rnd = philox4x32_10((uint32_t)gsession, (uint32_t)(gsession >> 32), (uint32_t)(step >> 2), 0u, seed_lo,
+                                seed_hi);
+        const uint32_t x = w == 0 ? rnd.x : w == 1 ? rnd.y : w == 2 ? rnd.z : rnd.w;
         return (int)__umulhi(x, (uint32_t)A);
     }
     const double b = s.buffer;  // BBA
@@ -198,7 +236,7 @@ __device__ __forceinline__ int policy_action(const EnvView& v, const Sess& s, in
 
 __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     const int tr = v.trace_id[i];
-    s.rate = v.trace_rate + (size_t)tr * (v.T_max + ABR_WALK_PAD);
+    s.rate = v.trace_rate + (size_t)tr * rate_stride(v.T_max);
     s.T = __ldg(v.trace_len + tr);
     s.I = __ldg(v.trace_interval + tr);
     s.seg = v.seg[i];
@@ -215,7 +253,7 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
 __global__ void __launch_bounds__(kStepBlock)
 abr_trace_table_kernel(const double* __restrict__ bw, const int32_t* __restrict__ trace_len, int n_traces, int T_max,
                        double payload, double* __restrict__ rate) {
-    const int stride = T_max + ABR_WALK_PAD;
+    const int stride = rate_stride(T_max);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)n_traces * stride) return;
     const int t = (int)(i / stride), j = (int)(i % stride);
@@ -255,7 +293,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restric
     int q = action[i];
     if (q < 0 || q >= v.A) { atomicAdd(v.errors, 1ull); q = q < 0 ? 0 : v.A - 1; }
     StepRes r;
-    step_core<false>(v, s, q, r, v.p.track_history || o_thr != nullptr);
+    step_core<false, false>(v, s, q, r, v.p.track_history || o_thr != nullptr);
     if (r.walk_error) atomicAdd(v.errors, 1ull);
     if (!r.inert) {
         v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
@@ -304,11 +342,12 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_steps = 0.0, a_eps = 0.0;
     bool flagged = false, reset_mpc = false;
     const int n = v.n;
+    uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
     for (int t = 0; t < steps; ++t) {
-        int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t, actions_in, i);
+        int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t, actions_in, i, rnd);
         if (q < 0 || q >= v.A) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
         StepRes r;
-        step_core<SMEM>(v, s, q, r, v.p.track_history != 0);
+        step_core<SMEM, !SMEM>(v, s, q, r, v.p.track_history != 0);
         flagged |= r.walk_error;
         const size_t ix = (size_t)t * n + i;
         if (o.delay) __stcs(o.delay + ix, r.delay);
@@ -342,8 +381,10 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
 }
 
 // smem_doubles: capacity of the dynamic shared-memory row buffer (0 disables the shared-memory path).
+// 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
+// co-resident (6.9 per SM); at 140 registers only 3 warps fit per scheduler and a second wave appears.
 template <int POLICY>
-__global__ void __launch_bounds__(kRolloutBlock)
+__global__ void __launch_bounds__(kRolloutBlock, 8)
 abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
                    RolloutOut o, int smem_doubles) {
     extern __shared__ double2 s_row2[];
@@ -357,19 +398,14 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
     __syncthreads();
     const int tr0 = s_tr0;
     // block-uniform: every session of this block follows trace tr0 and its padded row fits
-    const int need = __ldg(v.trace_len + tr0) + ABR_WALK_PAD;
+    const int need = __ldg(v.trace_len + tr0) + ABR_WALK_PAD;   // <= rate_stride(T_max), so the copy stays in the row
     const bool use_smem = __syncthreads_and((!valid || tr == tr0) ? 1 : 0) && need <= smem_doubles;
     if (use_smem) {
-        const size_t row_off = (size_t)tr0 * (v.T_max + ABR_WALK_PAD);   // rows start 16-byte aligned when the stride is even
-        const double* __restrict__ g = v.trace_rate + row_off;
+        // rows start 16-byte aligned (rate_stride is even): stage with coalesced 16-byte loads
+        const double2* __restrict__ g2 =
+            reinterpret_cast<const double2*>(v.trace_rate + (size_t)tr0 * rate_stride(v.T_max));
         double* s_row = reinterpret_cast<double*>(s_row2);
-        if (((row_off & 1) == 0)) {
-            const double2* __restrict__ g2 = reinterpret_cast<const double2*>(g);
-            for (int j = threadIdx.x; j < need / 2; j += blockDim.x) s_row2[j] = __ldg(g2 + j);
-            if ((need & 1) && threadIdx.x == 0) s_row[need - 1] = __ldg(g + need - 1);
-        } else {
-            for (int j = threadIdx.x; j < need; j += blockDim.x) s_row[j] = __ldg(g + j);
-        }
+        for (int j = threadIdx.x; j < (need + 1) / 2; j += blockDim.x) s_row2[j] = __ldg(g2 + j);
         __syncthreads();
         if (valid) {
             s.rate = s_row;
@@ -429,7 +465,7 @@ abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __
 }  // namespace
 
 cudaError_t launch_trace_table(const EnvView& v, double* d_rate, cudaStream_t st) {
-    const size_t n = (size_t)v.n_traces * (v.T_max + ABR_WALK_PAD);
+    const size_t n = (size_t)v.n_traces * rate_stride(v.T_max);
     abr_trace_table_kernel<<<(unsigned)((n + kStepBlock - 1) / kStepBlock), kStepBlock, 0, st>>>(
         v.trace_bw, v.trace_len, v.n_traces, v.T_max, v.p.payload, d_rate);
     count_launch();
@@ -461,8 +497,7 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
     RolloutOut o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out};
     // shared-memory row buffer: the longest padded row when it leaves room for >= 7 blocks per SM, else disabled
-    int smem_doubles = v.T_max + ABR_WALK_PAD;
-    smem_doubles += smem_doubles & 1;
+    int smem_doubles = rate_stride(v.T_max);
     size_t smem_bytes = (size_t)smem_doubles * sizeof(double);
     if (smem_bytes > 32 * 1024) { smem_doubles = 0; smem_bytes = 0; }
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \

@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--mpc-sessions", type=int, default=131072, help="MPC sessions per GPU (configs[2] / 8)")
     ap.add_argument("--mpc-horizon", type=int, default=5)
     ap.add_argument("--no-mpc", action="store_true")
+    ap.add_argument("--no-step-form", action="store_true")
+    ap.add_argument("--step-sessions", type=int, default=1 << 22, help="sessions per GPU of the per-step-launch leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of each cpu_baseline sample")
     return ap.parse_args()
@@ -68,7 +70,7 @@ def _py_step_worker(job):
         sess = so.Session(bw[tid[s]].tolist(), float(ti[tid[s]]), sz, util, P, float(off[s]))
         g = lo + s
         for t in range(V):
-            x0 = orc.philox(g & 0xffffffff, g >> 32, t, 0, SEED, 0)[0]
+            x0 = orc.philox(g & 0xffffffff, g >> 32, t >> 2, 0, SEED, 0)[t & 3]
             tot += sess.step((x0 * A) >> 32)["reward"]
         done_steps += V
         if time.perf_counter() - t0 > budget_s:
@@ -326,6 +328,10 @@ def run_ours(args):
     if not args.no_mpc:
         mpc = bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks)
 
+    step_form = None
+    if not args.no_step_form:
+        step_form = bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak_gbs())
+
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
@@ -360,11 +366,57 @@ def run_ours(args):
                 qoe_stats=dict(zip(_lib.ACC_NAMES, [float(x) for x in tot_stats.cpu()])), flagged_sessions=errors)
     if mpc:
         line["mpc"] = mpc
+    if step_form:
+        line["step_form"] = step_form
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak):
+    """Per-step-launch form (RL-harness shape, configs[4] per GPU): one abr_step_kernel launch per chunk over
+    --step-sessions sessions with the SoA state in HBM; 105 algorithmic bytes per session-step."""
+    import torch
+    from abrsimulator_b200 import synth
+    from abrsimulator_b200.env import BatchedABREnv, StepResult
+    M = args.step_sessions
+    bitrates, sizes = synth.make_video(V)
+    bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
+    env = BatchedABREnv(bw, sizes, bitrates, M, trace_len=tl, trace_interval=ti)
+    tid, off = synth.make_sessions(M, N_TRACES, T_TRACE, session_base=rank * M, group=GROUP)
+    env.reset(tid, off, session_base=rank * M)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    acts = torch.randint(0, A, (8, M), dtype=torch.int32, device=dev, generator=g)
+    out = StepResult(*[torch.empty(M, dtype=torch.float64, device=dev) for _ in range(5)], None,
+                     torch.empty(M, dtype=torch.uint8, device=dev), None)
+    stream = torch.cuda.current_stream()
+    for t in range(8):
+        env.step(acts[t % 8], out=out)
+    barrier()
+    reps = 24
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(reps):
+        env.step(acts[t % 8], out=out)
+    e1.record(stream)
+    e1.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev) / reps
+    bytes_per = 32 + 4 + 28 + 41
+    achieved = M * bytes_per / (ms * 1e-3) / 1e9
+    return dict(kernel="abr_step_kernel", sessions_per_gpu=M, ms_per_launch=ms,
+                session_steps_per_s=world * M / (ms * 1e-3), bytes_per_session_step=bytes_per,
+                roofline=dict(bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak),
+                note="4 Mi sessions: 304 MB of SoA state + 172 MB of outputs per launch, larger than the 126 MB L2")
 
 
 def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):

@@ -214,9 +214,10 @@ static int policy_action(OrcEnv* e, int s, int policy, uint64_t seed, int64_t se
     if (policy == ORC_POLICY_RANDOM) {
         uint64_t g = (uint64_t)(session_base + s);
         uint32_t r[4];
-        orc_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32) ^ 0u, (uint32_t)step, 0u, (uint32_t)seed,
+        /* one Philox block per four steps: counter (session, step / 4), word step % 4 */
+        orc_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(step >> 2), 0u, (uint32_t)seed,
                           (uint32_t)(seed >> 32), r);
-        return (int)(((uint64_t)r[0] * (uint64_t)A) >> 32);
+        return (int)(((uint64_t)r[step & 3] * (uint64_t)A) >> 32);
     }
     /* BBA */
     double b = e->buffer[s];

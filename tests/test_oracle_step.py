@@ -58,7 +58,7 @@ def test_rollout_policies_and_acc():
             tot = 0.0
             for t in range(steps):
                 if policy == orc.POLICY_RANDOM:
-                    x0 = orc.philox((1000 + s) & 0xffffffff, 0, t, 0, 123, 0)[0]
+                    x0 = orc.philox((1000 + s) & 0xffffffff, 0, t >> 2, 0, 123, 0)[t & 3]
                     q = (x0 * 6) >> 32
                 else:
                     q = so.bba_action(sess.buffer, 6, P["bba_reservoir"], P["bba_cushion"])
