@@ -506,6 +506,21 @@ int abr_mpc_score_host(const double* h_sizes, const double* h_bitrates, int V, i
 int abr_fp64_probe(int kind, int iters, double* gops_per_s, float* ms, void* stream) {
     if (iters < 1) return fail(ABR_ERR_RANGE, "iters must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
+    if (kind >= 10) {   // latency probes: kind 10 DADD, 11 DMUL, 12 DADD+sign-mask; result = cycles per dependent op
+        double* d_s = nullptr;
+        long long* d_c = nullptr;
+        CUDA_TRY(cudaMalloc(&d_s, sizeof(double) * 32));
+        CUDA_TRY(cudaMalloc(&d_c, sizeof(long long)));
+        struct F { double* a; long long* b; ~F() { cudaFree(a); cudaFree(b); } } f{d_s, d_c};
+        CUDA_TRY(launch_fp64_latency(kind - 10, iters, d_s, d_c, st));
+        CUDA_TRY(launch_fp64_latency(kind - 10, iters, d_s, d_c, st));
+        long long cyc = 0;
+        CUDA_TRY(cudaMemcpyAsync(&cyc, d_c, sizeof(cyc), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (gops_per_s) *gops_per_s = (double)cyc / ((double)iters * 64.0);
+        if (ms) *ms = 0.f;
+        return ABR_OK;
+    }
     int dev = 0, sms = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -110,6 +110,8 @@ cudaError_t launch_mpc_score(const double* d_sizes, const double* d_util, int V,
 cudaError_t launch_fp64_probe(int kind, int iters, double* d_sink, int* threads_total, long long* ops_per_thread,
                               cudaStream_t st);
 
+cudaError_t launch_fp64_latency(int kind, int iters, double* d_sink, long long* d_cycles, cudaStream_t st);
+
 void count_launch(int n = 1);
 
 }  // namespace abr

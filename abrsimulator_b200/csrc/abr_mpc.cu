@@ -386,7 +386,36 @@ __global__ void __launch_bounds__(256) abr_fp64_probe_kernel(int iters, double* 
     sink[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// single dependent chain per thread, one warp per SM: cycles per instruction = pipeline latency
+template <int KIND>
+__global__ void __launch_bounds__(32) abr_fp64_latency_kernel(int iters, double* sink, long long* cycles) {
+    double x = 1.0 + threadIdx.x * 1e-9;
+    const double d = 1e-7, c = 1.0000001;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 64; ++r) {
+            if (KIND == 0) x = dadd(x, d);
+            else if (KIND == 1) x = dmul(x, c);
+            else x = max0(dsub(x, d));     // DADD + integer sign-mask
+        }
+    }
+    const long long t1 = clock64();
+    sink[blockIdx.x * 32 + threadIdx.x] = x;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 }  // namespace
+
+cudaError_t launch_fp64_latency(int kind, int iters, double* d_sink, long long* d_cycles, cudaStream_t st) {
+    switch (kind) {
+        case 0: abr_fp64_latency_kernel<0><<<1, 32, 0, st>>>(iters, d_sink, d_cycles); break;
+        case 1: abr_fp64_latency_kernel<1><<<1, 32, 0, st>>>(iters, d_sink, d_cycles); break;
+        default: abr_fp64_latency_kernel<2><<<1, 32, 0, st>>>(iters, d_sink, d_cycles); break;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
 
 cudaError_t launch_mpc(const MpcArgs& a, cudaStream_t st) {
     if (a.N <= 0) return cudaSuccess;

@@ -112,19 +112,21 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     double room = dsub(s.I, tau);
     double s2 = dadd(sent, dmul(rate, room));
     const bool multi = !(s2 >= size);      // the current segment does not finish the chunk
-    double c[kWalkBlock];
+    double c[kWalkBlock], dl[kWalkBlock];
     if (multi) {
         for (;;) {
             double nxt[kWalkBlock];
             if (PREFETCH) load_rates<SMEM, kWalkBlock>(row, seg + 1 + kWalkBlock, nxt);   // overlap with this block
             c[0] = dadd(s2, dmul(cur[0], s.I));
-#pragma unroll
-            for (int u = 1; u < kWalkBlock; ++u) c[u] = dadd(c[u - 1], dmul(cur[u], s.I));
-            if (c[kWalkBlock - 1] >= size) break;   // the download ends inside this block (c, cur stay live)
+            dl[0] = dadd(delay, room);               // elapsed time after leaving the current segment, then after
+#pragma unroll                                       // each further whole segment: independent of the c chain
+            for (int u = 1; u < kWalkBlock; ++u) {
+                c[u] = dadd(c[u - 1], dmul(cur[u], s.I));
+                dl[u] = dadd(dl[u - 1], s.I);
+            }
+            if (c[kWalkBlock - 1] >= size) break;   // the download ends inside this block (c, dl, cur stay live)
             // the whole block is consumed: capacities are > 0, so no earlier total reached `size` either
-            delay = dadd(delay, room);
-#pragma unroll
-            for (int u = 1; u < kWalkBlock; ++u) delay = dadd(delay, s.I);
+            delay = dl[kWalkBlock - 1];
             room = s.I;
             s2 = c[kWalkBlock - 1];
             seg += kWalkBlock;
@@ -141,16 +143,10 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     // every lane has reconverged here; lanes that walked pick the first u with c[u] >= size, once
     if (multi) {
         int adv = kWalkBlock;
-        double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1];
-        double d = dadd(delay, room), delay_f = d;
+        double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1], delay_f = dl[kWalkBlock - 1];
 #pragma unroll
         for (int u = kWalkBlock - 1; u >= 0; --u) {
-            if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u]; }
-        }
-#pragma unroll
-        for (int u = 1; u < kWalkBlock; ++u) {
-            d = dadd(d, s.I);
-            if (u < adv) delay_f = d;
+            if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u]; delay_f = dl[u]; }
         }
         sent = sent_f; rate = rate_f; delay = delay_f;
         seg += adv;
@@ -281,7 +277,8 @@ abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* 
     for (int j = 0; j < ABR_NUM_ACC; ++j) v.acc[(size_t)j * v.cap + i] = 0.0;
 }
 
-__global__ void __launch_bounds__(kStepBlock)
+// <= 64 registers: 4 blocks of 256 threads per SM; the kernel is latency/LSU-bound and lives on occupancy
+__global__ void __launch_bounds__(kStepBlock, 4)
 abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restrict__ o_delay,
                 double* __restrict__ o_sleep, double* __restrict__ o_buffer, double* __restrict__ o_rebuf,
                 double* __restrict__ o_reward, double* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov,
@@ -373,11 +370,15 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     if (v.p.track_history) v.hist_len[i] = s.hist_len;
     if (reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
     if (s.done) v.done[i] = 1;
+    // accumulator read-modify-write: all eight loads first (one memory round trip instead of eight dependent ones)
     double* a = v.acc + i;
     const size_t c = v.cap;
-    a[0 * c] = dadd(a[0 * c], a_rew); a[1 * c] = dadd(a[1 * c], a_reb); a[2 * c] = dadd(a[2 * c], a_u);
-    a[3 * c] = dadd(a[3 * c], a_sm); a[4 * c] = dadd(a[4 * c], a_sl); a[5 * c] = dadd(a[5 * c], a_dl);
-    a[6 * c] = dadd(a[6 * c], a_steps); a[7 * c] = dadd(a[7 * c], a_eps);
+    const double add[ABR_NUM_ACC] = {a_rew, a_reb, a_u, a_sm, a_sl, a_dl, a_steps, a_eps};
+    double old[ABR_NUM_ACC];
+#pragma unroll
+    for (int j = 0; j < ABR_NUM_ACC; ++j) old[j] = __ldcg(a + j * c);
+#pragma unroll
+    for (int j = 0; j < ABR_NUM_ACC; ++j) a[j * c] = dadd(old[j], add[j]);
 }
 
 // smem_doubles: capacity of the dynamic shared-memory row buffer (0 disables the shared-memory path).

@@ -149,7 +149,9 @@ int abr_mpc_score_host(const double* h_sizes, const double* h_bitrates, int V, i
 
 /* ---- measurement helper: FP64 issue-rate probe used as the MPC kernel's roofline denominator.
  *      kind 0 = dependent DADD chains, 1 = DFMA chains, 2 = DADD + DSETP/select mix.
- *      Returns giga-ops/s (one op per thread-instruction; FMA counts 1). ---- */
+ *      Returns giga-ops/s (one op per thread-instruction; FMA counts 1).
+ *      kind 10/11/12 = latency probes (one dependent DADD / DMUL / DADD+sign-mask chain in one warp): the value
+ *      returned in *gops_per_s is then SM cycles per dependent operation. ---- */
 int abr_fp64_probe(int kind, int iters, double* gops_per_s, float* ms, void* stream);
 
 #ifdef __cplusplus
