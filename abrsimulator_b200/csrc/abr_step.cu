@@ -33,6 +33,8 @@ constexpr int kWalkBlock = ABR_WALK_BLOCK;   // segments fetched per walk block 
 
 struct Sess {
     const double* __restrict__ rate;  // per segment: bw*payload; global row or its shared-memory copy
+    const double* __restrict__ sizes; // [V][A] chunk sizes and utilities: global tables or their shared-memory copies
+    const double* __restrict__ util;
     double I, tau, buffer;
     int T, seg, chunk, last_q, hist_len;
     bool done;
@@ -90,7 +92,11 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     }
     r.inert = false;
     const int A = v.A;
-    const double size = __ldg(v.sizes + s.chunk * A + q);
+    // all table reads of the step are issued up front so that their latency overlaps the walk
+    const double size = SMEM ? s.sizes[s.chunk * A + q] : __ldg(s.sizes + s.chunk * A + q);
+    const double u = SMEM ? s.util[s.chunk * A + q] : __ldg(s.util + s.chunk * A + q);
+    const double u_prev = s.last_q >= 0 ? (SMEM ? s.util[s.chunk * A + s.last_q] : __ldg(s.util + s.chunk * A + s.last_q))
+                                        : u;
     // 3.1 segment walk (Simulator.py:158-163 in closed form, with wrap-around).  A block of kWalkBlock segments
     // is fetched with independent loads at constant offsets (no per-iteration address or wrap arithmetic); each
     // whole-segment capacity rate*(I - 0) is an independent product, so only the running-total additions form a
@@ -186,8 +192,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         if (tau >= s.I) { tau = 0.0; seg = (seg + 1 == s.T) ? 0 : seg + 1; }
     }
     // 3.4 reward
-    const double u = __ldg(v.util + s.chunk * A + q);
-    const double smooth = (s.last_q >= 0) ? fabs(dsub(u, __ldg(v.util + s.chunk * A + s.last_q))) : 0.0;
+    const double smooth = (s.last_q >= 0) ? fabs(dsub(u, u_prev)) : 0.0;
     r.reward = dsub(dsub(u, dmul(p.rebuf_penalty, rebuf)), dmul(p.smooth_penalty, smooth));
     r.delay = delay; r.sleep = sleep; r.buffer = buffer; r.rebuf = rebuf; r.u = u; r.smooth = smooth;
     // 3.5 advance
@@ -233,6 +238,8 @@ __device__ __forceinline__ int policy_action(const EnvView& v, const Sess& s, in
 __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     const int tr = v.trace_id[i];
     s.rate = v.trace_rate + (size_t)tr * rate_stride(v.T_max);
+    s.sizes = v.sizes;
+    s.util = v.util;
     s.T = __ldg(v.trace_len + tr);
     s.I = __ldg(v.trace_interval + tr);
     s.seg = v.seg[i];
@@ -381,14 +388,36 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     for (int j = 0; j < ABR_NUM_ACC; ++j) a[j * c] = dadd(old[j], add[j]);
 }
 
-// smem_doubles: capacity of the dynamic shared-memory row buffer (0 disables the shared-memory path).
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (byte count multiple of 16, both addresses
+// 16-byte aligned).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint32_t mbar) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(gmem_src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// Wait for the given phase of an mbarrier (try_wait suspends the thread for a bounded, implementation-defined time
+// per call).  The retry count is bounded so that a programming error cannot hang the GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
+    for (int spins = 0; spins < (1 << 16); ++spins) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
+// smem_doubles: capacity of the dynamic shared-memory row buffer (0 disables the shared-memory path); the buffer
+// is followed by room for the sizes and utility tables.
 // 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
 // co-resident (6.9 per SM); at 140 registers only 3 warps fit per scheduler and a second wave appears.
 template <int POLICY>
 __global__ void __launch_bounds__(kRolloutBlock, 8)
 abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
                    RolloutOut o, int smem_doubles) {
-    extern __shared__ double2 s_row2[];
+    extern __shared__ __align__(16) double2 s_row2[];
+    __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_tr0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < v.n;
@@ -402,14 +431,44 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
     const int need = __ldg(v.trace_len + tr0) + ABR_WALK_PAD;   // <= rate_stride(T_max), so the copy stays in the row
     const bool use_smem = __syncthreads_and((!valid || tr == tr0) ? 1 : 0) && need <= smem_doubles;
     if (use_smem) {
-        // rows start 16-byte aligned (rate_stride is even): stage with coalesced 16-byte loads
-        const double2* __restrict__ g2 =
-            reinterpret_cast<const double2*>(v.trace_rate + (size_t)tr0 * rate_stride(v.T_max));
+        // Stage the trace row and the chunk-size / utility tables with TMA bulk copies (cp.async.bulk, SASS UBLKCP):
+        // one elected thread issues three asynchronous global->shared copies that complete on an mbarrier, so the
+        // 21 KB arrive without occupying the LSU or registers while the other threads finish loading their state.
+        // Rows start 16-byte aligned (rate_stride is even) and all byte counts are multiples of 16.
         double* s_row = reinterpret_cast<double*>(s_row2);
-        for (int j = threadIdx.x; j < (need + 1) / 2; j += blockDim.x) s_row2[j] = __ldg(g2 + j);
+        double* s_sizes = s_row + smem_doubles;
+        double* s_util = s_sizes + v.V * v.A;
+        const double* g_row = v.trace_rate + (size_t)tr0 * rate_stride(v.T_max);
+        const uint32_t row_bytes = (uint32_t)((need + 1) / 2) * 16u;
+        const uint32_t tab_bytes = (uint32_t)(v.V * v.A) * 8u;
+        const bool tab_bulk = (tab_bytes & 15u) == 0;
+        const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t total = row_bytes + (tab_bulk ? 2u * tab_bytes : 0u);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
+            bulk_g2s(s_row, g_row, row_bytes, mbar);
+            if (tab_bulk) {
+                bulk_g2s(s_sizes, v.sizes, tab_bytes, mbar);
+                bulk_g2s(s_util, v.util, tab_bytes, mbar);
+            }
+        }
+        if (!tab_bulk) {
+            for (int j = threadIdx.x; j < v.V * v.A; j += blockDim.x) {
+                s_sizes[j] = __ldg(v.sizes + j);
+                s_util[j] = __ldg(v.util + j);
+            }
+        }
+        if (!mbar_wait(mbar, 0u) && threadIdx.x == 0) atomicAdd(v.errors, 1ull);
         __syncthreads();
         if (valid) {
             s.rate = s_row;
+            s.sizes = s_sizes;
+            s.util = s_util;
             rollout_session<POLICY, true>(v, s, i, seed_lo, seed_hi, steps, actions_in, o);
         }
     } else if (valid) {
@@ -499,7 +558,7 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     RolloutOut o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out};
     // shared-memory row buffer: the longest padded row when it leaves room for >= 7 blocks per SM, else disabled
     int smem_doubles = rate_stride(v.T_max);
-    size_t smem_bytes = (size_t)smem_doubles * sizeof(double);
+    size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double);
     if (smem_bytes > 32 * 1024) { smem_doubles = 0; smem_bytes = 0; }
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
     abr_rollout_kernel<P><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o, smem_doubles)
