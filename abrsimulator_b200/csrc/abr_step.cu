@@ -102,9 +102,10 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     // whole-segment capacity rate*(I - 0) is an independent product, so only the running-total additions form a
     // dependent chain — the same left-to-right additions as the segment-by-segment walk.  The one division
     // happens after the loop has reconverged.
-    double sent = 0.0, delay = 0.0, tau = s.tau;
+    double sent = 0.0, tau = s.tau;
     int seg = s.seg;                       // < T; the row padding makes seg + 2*kWalkBlock readable
     int guard = (1 << 20) / kWalkBlock;    // safety net only: every bandwidth is > 0, so the walk terminates
+    int k = 0;                             // segments left behind
     const double* __restrict__ row = s.rate;
     double cur[kWalkBlock];
     double rate;
@@ -115,26 +116,21 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
 #pragma unroll
         for (int u = 0; u < kWalkBlock; ++u) cur[u] = head[u + 1];
     }
-    double room = dsub(s.I, tau);
-    double s2 = dadd(sent, dmul(rate, room));
+    const double room0 = dsub(s.I, tau);
+    double s2 = dadd(sent, dmul(rate, room0));
     const bool multi = !(s2 >= size);      // the current segment does not finish the chunk
-    double c[kWalkBlock], dl[kWalkBlock];
+    double c[kWalkBlock];
     if (multi) {
         for (;;) {
             double nxt[kWalkBlock];
             if (PREFETCH) load_rates<SMEM, kWalkBlock>(row, seg + 1 + kWalkBlock, nxt);   // overlap with this block
             c[0] = dadd(s2, dmul(cur[0], s.I));
-            dl[0] = dadd(delay, room);               // elapsed time after leaving the current segment, then after
-#pragma unroll                                       // each further whole segment: independent of the c chain
-            for (int u = 1; u < kWalkBlock; ++u) {
-                c[u] = dadd(c[u - 1], dmul(cur[u], s.I));
-                dl[u] = dadd(dl[u - 1], s.I);
-            }
-            if (c[kWalkBlock - 1] >= size) break;   // the download ends inside this block (c, dl, cur stay live)
+#pragma unroll
+            for (int u = 1; u < kWalkBlock; ++u) c[u] = dadd(c[u - 1], dmul(cur[u], s.I));
+            if (c[kWalkBlock - 1] >= size) break;   // the download ends inside this block (c, cur stay live)
             // the whole block is consumed: capacities are > 0, so no earlier total reached `size` either
-            delay = dl[kWalkBlock - 1];
-            room = s.I;
             s2 = c[kWalkBlock - 1];
+            k += kWalkBlock;
             seg += kWalkBlock;
             if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
             if (PREFETCH) {
@@ -147,21 +143,25 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         }
     }
     // every lane has reconverged here; lanes that walked pick the first u with c[u] >= size, once
+    double elapsed = 0.0;
     if (multi) {
         int adv = kWalkBlock;
-        double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1], delay_f = dl[kWalkBlock - 1];
+        double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1];
 #pragma unroll
         for (int u = kWalkBlock - 1; u >= 0; --u) {
-            if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u]; delay_f = dl[u]; }
+            if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u]; }
         }
-        sent = sent_f; rate = rate_f; delay = delay_f;
+        sent = sent_f; rate = rate_f;
+        k += adv;
         seg += adv;
         if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
         tau = 0.0;
+        elapsed = dadd(room0, dmul((double)(k - 1), s.I));   // time spent in the k segments left behind
     }
+    double delay;
     {
         const double dt = ddiv(dsub(size, sent), rate);
-        delay = dadd(delay, dt);
+        delay = dadd(elapsed, dt);
         tau = dadd(tau, dt);
     }
     delay = dadd(delay, p.rtt);

@@ -128,25 +128,28 @@ static void step_one(OrcEnv* e, int s, int q, StepOut* o) {
     double tau = e->tau[s], buffer = e->buffer[s];
     const double size = e->sizes[chunk * e->A + q];
     /* 3.1 segment walk */
-    double sent = 0.0, delay = 0.0;
+    double sent = 0.0, delay;
     int guard = 1 << 20;   /* safety net only: every bandwidth is > 0, so the walk terminates */
+    long long k = 0;       /* segments left behind */
+    const double room0 = I - tau;
+    double rate = bw[seg] * p->payload;
+    double cap = rate * room0;
     for (;;) {
-        double rate = bw[seg] * p->payload;
-        double room = I - tau;
-        double cap = rate * room;
-        if (sent + cap >= size) {
-            double dt = (size - sent) / rate;
-            delay = delay + dt;
-            tau = tau + dt;
-            break;
-        }
+        if (sent + cap >= size) break;
         sent = sent + cap;
-        delay = delay + room;
+        k += 1;
         seg = (seg + 1 == T) ? 0 : seg + 1;
         tau = 0.0;
+        rate = bw[seg] * p->payload;
+        cap = rate * I;
         if (--guard <= 0) { e->errors++; break; }
     }
-    delay = delay + p->rtt;
+    {
+        double dt = (size - sent) / rate;
+        tau = tau + dt;
+        double elapsed = (k == 0) ? 0.0 : room0 + (double)(k - 1) * I;
+        delay = (elapsed + dt) + p->rtt;
+    }
     double thr = size / delay;
     /* 3.2 */
     double rebuf = max0(delay - buffer);

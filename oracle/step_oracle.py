@@ -37,21 +37,23 @@ class Session:
             return dict(delay=0.0, sleep=0.0, buffer=self.buffer, rebuf=0.0, reward=0.0, eov=1, inert=True)
         size = self.sizes[self.chunk][q]
         sent = 0.0
-        delay = 0.0
+        k = 0
+        room0 = self.I - self.tau
+        rate = self.bw[self.seg] * P["payload"]
+        cap = rate * room0
         while True:                                  # SPEC 3.1 (Simulator.py:158-163)
-            rate = self.bw[self.seg] * P["payload"]
-            room = self.I - self.tau
-            cap = rate * room
             if sent + cap >= size:
-                dt = (size - sent) / rate
-                delay = delay + dt
-                self.tau = self.tau + dt
                 break
             sent = sent + cap
-            delay = delay + room
+            k += 1
             self.seg = 0 if self.seg + 1 == self.T else self.seg + 1
             self.tau = 0.0
-        delay = delay + P["rtt"]
+            rate = self.bw[self.seg] * P["payload"]
+            cap = rate * self.I
+        dt = (size - sent) / rate
+        self.tau = self.tau + dt
+        elapsed = 0.0 if k == 0 else room0 + float(k - 1) * self.I
+        delay = (elapsed + dt) + P["rtt"]
         thr = size / delay
         rebuf = delay - self.buffer if delay - self.buffer > 0 else 0.0     # SPEC 3.2
         self.buffer = (self.buffer - delay if self.buffer - delay > 0 else 0.0) + P["chunk_length"]

@@ -16,4 +16,8 @@ if [ -z "${SKIP_MPC:-}" ]; then
 ncu --set full --clock-control none --import-source on -k regex:abr_mpc_kernel -s 3 -c 1 -f -o gpurun_out/mpc_$TAG $CMD > gpurun_out/ncu_mpc_$TAG.log 2>&1
 echo "mpc capture rc=$?"
 fi
+if [ -n "${WITH_STEP:-}" ]; then
+ncu --set full --clock-control none --import-source on -k regex:abr_step_kernel -s 12 -c 1 -f -o gpurun_out/step_$TAG $CMD > gpurun_out/ncu_step_$TAG.log 2>&1
+echo "step capture rc=$?"
+fi
 ls -la gpurun_out/
