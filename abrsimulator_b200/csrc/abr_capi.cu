@@ -41,6 +41,7 @@ struct AbrEnv {
     std::vector<void*> allocs;
     double* d_stats_partials = nullptr;
     int n_partials_cap = 0;
+    int fresh_partials = 0;   // > 0: d_stats_partials holds that many block sums of the current accumulators
     double* d_stats_out = nullptr;
     // scratch for the *_host entry points
     int32_t* d_trace_id = nullptr;
@@ -190,7 +191,8 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     CUDA_TRY(cudaMemset(v.errors, 0, sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(v.bw_hist, 0, sizeof(double) * cap * v.K));
     CUDA_TRY(cudaMemset(v.err_ring, 0, sizeof(double) * cap * v.K));
-    e->n_partials_cap = stats_num_partials(max_sessions);
+    e->n_partials_cap = stats_num_partials(max_sessions) > rollout_num_blocks(max_sessions)
+                            ? stats_num_partials(max_sessions) : rollout_num_blocks(max_sessions);
     CUDA_TRY(e->alloc(&e->d_stats_partials, (size_t)e->n_partials_cap * ABR_NUM_ACC));
     CUDA_TRY(e->alloc(&e->d_stats_out, ABR_NUM_STATS));
     CUDA_TRY(e->alloc(&e->d_trace_id, cap));
@@ -210,6 +212,7 @@ int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_
     if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
     env->v.n = n_sessions;
     env->v.session_base = session_base;
+    env->fresh_partials = 0;
     CUDA_TRY(launch_reset(env->v, d_trace_id, d_start_offset, (cudaStream_t)stream));
     return ABR_OK;
 }
@@ -230,6 +233,7 @@ int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* 
                  void* stream) {
     if (!env || !d_action) return fail(ABR_ERR_INVALID, "env or action is NULL");
     if (env->v.n <= 0) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    env->fresh_partials = 0;
     CUDA_TRY(launch_step(env->v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_next_sizes, d_end_of_video,
                          d_throughput, (cudaStream_t)stream));
     return ABR_OK;
@@ -244,7 +248,8 @@ int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, con
     if (policy < ABR_POLICY_FIXED || policy > ABR_POLICY_BBA) return fail(ABR_ERR_INVALID, "unknown policy %d", policy);
     if (policy == ABR_POLICY_FIXED && !d_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs d_actions_in");
     CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_delay, d_sleep, d_buffer, d_rebuf, d_reward,
-                            d_end_of_video, d_actions_out, (cudaStream_t)stream));
+                            d_end_of_video, d_actions_out, env->d_stats_partials, (cudaStream_t)stream));
+    env->fresh_partials = steps > 0 ? rollout_num_blocks(env->v.n) : 0;
     return ABR_OK;
 }
 
@@ -279,8 +284,9 @@ int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, do
 
 int abr_stats_partial(AbrEnv* env, double* d_out, void* stream) {
     if (!env || !d_out) return fail(ABR_ERR_INVALID, "env or out is NULL");
-    const int np = stats_num_partials(env->v.n);
-    CUDA_TRY(launch_stats(env->v, env->d_stats_partials, np, d_out, (cudaStream_t)stream));
+    const bool fresh = env->fresh_partials > 0;
+    const int np = fresh ? env->fresh_partials : stats_num_partials(env->v.n);
+    CUDA_TRY(launch_stats(env->v, env->d_stats_partials, np, fresh, d_out, (cudaStream_t)stream));
     return ABR_OK;
 }
 

@@ -87,9 +87,11 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, double* d_del
                         cudaStream_t st);
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
-                           uint8_t* d_eov, int32_t* d_actions_out, cudaStream_t st);
-cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, double* d_out, cudaStream_t st);
+                           uint8_t* d_eov, int32_t* d_actions_out, double* d_block_partials, cudaStream_t st);
+cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, bool have_partials, double* d_out,
+                         cudaStream_t st);
 int stats_num_partials(int n);
+int rollout_num_blocks(int n);
 
 struct MpcArgs {
     const double* sizes; const double* util; int V, A;

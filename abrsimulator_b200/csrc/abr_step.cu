@@ -341,7 +341,8 @@ struct RolloutOut {
 template <int POLICY, bool SMEM>
 __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const int i, const uint32_t seed_lo,
                                                 const uint32_t seed_hi, const int steps,
-                                                const int32_t* __restrict__ actions_in, const RolloutOut& o) {
+                                                const int32_t* __restrict__ actions_in, const RolloutOut& o,
+                                                double (&acc_new)[ABR_NUM_ACC]) {
     const unsigned long long gsession = (unsigned long long)(v.session_base + i);
     double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_steps = 0.0, a_eps = 0.0;
     bool flagged = false, reset_mpc = false;
@@ -385,7 +386,10 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
 #pragma unroll
     for (int j = 0; j < ABR_NUM_ACC; ++j) old[j] = __ldcg(a + j * c);
 #pragma unroll
-    for (int j = 0; j < ABR_NUM_ACC; ++j) a[j * c] = dadd(old[j], add[j]);
+    for (int j = 0; j < ABR_NUM_ACC; ++j) {
+        acc_new[j] = dadd(old[j], add[j]);
+        a[j * c] = acc_new[j];
+    }
 }
 
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (byte count multiple of 16, both addresses
@@ -415,12 +419,16 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
 template <int POLICY>
 __global__ void __launch_bounds__(kRolloutBlock, 8)
 abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
-                   RolloutOut o, int smem_doubles) {
+                   RolloutOut o, int smem_doubles, double* __restrict__ block_partials) {
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_tr0;
+    __shared__ double s_part[kRolloutBlock / 32][ABR_NUM_ACC];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < v.n;
+    double acc_new[ABR_NUM_ACC];
+#pragma unroll
+    for (int j = 0; j < ABR_NUM_ACC; ++j) acc_new[j] = 0.0;
     Sess s;
     int tr = -1;
     if (valid) { load_sess(v, i, s); tr = v.trace_id[i]; }
@@ -469,10 +477,27 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
             s.rate = s_row;
             s.sizes = s_sizes;
             s.util = s_util;
-            rollout_session<POLICY, true>(v, s, i, seed_lo, seed_hi, steps, actions_in, o);
+            rollout_session<POLICY, true>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
         }
     } else if (valid) {
-        rollout_session<POLICY, false>(v, s, i, seed_lo, seed_hi, steps, actions_in, o);
+        rollout_session<POLICY, false>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+    }
+    // statistics stage 1 fused into the episode: per-block sums of the updated accumulators in a fixed order
+    // (warp tree, then warps in ascending order), so abr_stats_partial only has to add the block partials
+    if (block_partials) {
+#pragma unroll
+        for (int j = 0; j < ABR_NUM_ACC; ++j) {
+            double x = acc_new[j];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) x = dadd(x, __shfl_down_sync(0xffffffffu, x, d));
+            if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][j] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < ABR_NUM_ACC) {
+            double x = s_part[0][threadIdx.x];
+            for (int w = 1; w < kRolloutBlock / 32; ++w) x = dadd(x, s_part[w][threadIdx.x]);
+            block_partials[(size_t)blockIdx.x * ABR_NUM_ACC + threadIdx.x] = x;
+        }
     }
 }
 
@@ -551,7 +576,7 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, double* d_del
 
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
-                           uint8_t* d_eov, int32_t* d_actions_out, cudaStream_t st) {
+                           uint8_t* d_eov, int32_t* d_actions_out, double* d_block_partials, cudaStream_t st) {
     if (v.n == 0 || steps <= 0) return cudaSuccess;
     const dim3 grid((v.n + kRolloutBlock - 1) / kRolloutBlock), block(kRolloutBlock);
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
@@ -561,7 +586,8 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double);
     if (smem_bytes > 32 * 1024) { smem_doubles = 0; smem_bytes = 0; }
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
-    abr_rollout_kernel<P><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o, smem_doubles)
+    abr_rollout_kernel<P><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o, smem_doubles,            \
+                                                           d_block_partials)
     switch (policy) {
         case ABR_POLICY_FIXED: ABR_LAUNCH_ROLLOUT(ABR_POLICY_FIXED); break;
         case ABR_POLICY_RANDOM: ABR_LAUNCH_ROLLOUT(ABR_POLICY_RANDOM); break;
@@ -575,10 +601,17 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
 
 int stats_num_partials(int n) { return n <= 0 ? 1 : (n + kStatsSessionsPerBlock - 1) / kStatsSessionsPerBlock; }
 
-cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, double* d_out, cudaStream_t st) {
-    abr_stats_stage1<<<n_partials, kStatsBlock, 0, st>>>(v, d_partials);
+int rollout_num_blocks(int n) { return n <= 0 ? 1 : (n + kRolloutBlock - 1) / kRolloutBlock; }
+
+// have_partials: d_partials already holds n_partials block sums (written by the fused episode kernel)
+cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, bool have_partials, double* d_out,
+                         cudaStream_t st) {
+    if (!have_partials) {
+        abr_stats_stage1<<<n_partials, kStatsBlock, 0, st>>>(v, d_partials);
+        count_launch();
+    }
     abr_stats_stage2<<<1, kStatsBlock, 0, st>>>(d_partials, n_partials, d_out);
-    count_launch(2);
+    count_launch();
     return cudaGetLastError();
 }
 
