@@ -326,7 +326,7 @@ int abr_env_error_count(AbrEnv* env, long long* out, void* stream) {
 
 int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* h_trace_id,
                      const double* h_start_offset, int n_sessions, long long session_base, const int32_t* h_actions_in,
-                     double* h_acc, double* h_stats, double* h_reward_traj, void* stream) {
+                     double* h_acc, double* h_stats, double* h_reward_traj, double* h_qoe_cost, void* stream) {
     if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
     if (steps < 0) return fail(ABR_ERR_RANGE, "steps must be >= 0");
     cudaStream_t st = (cudaStream_t)stream;
@@ -365,6 +365,10 @@ int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const in
     }
     if (h_reward_traj)
         CUDA_TRY(cudaMemcpyAsync(h_reward_traj, env->d_reward_traj, sizeof(double) * traj, cudaMemcpyDeviceToHost, st));
+    if (h_qoe_cost) {   // d_offset is free again after the reset kernel has consumed it
+        CUDA_TRY(launch_qoe_cost(env->v, env->d_offset, st));
+        CUDA_TRY(cudaMemcpyAsync(h_qoe_cost, env->d_offset, sizeof(double) * n_sessions, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     return ABR_OK;
 }

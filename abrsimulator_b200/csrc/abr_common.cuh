@@ -91,6 +91,7 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
 cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, bool have_partials, double* d_out,
                          cudaStream_t st);
 int stats_num_partials(int n);
+cudaError_t launch_qoe_cost(const EnvView& v, double* d_out, cudaStream_t st);
 int rollout_num_blocks(int n);
 
 struct MpcArgs {

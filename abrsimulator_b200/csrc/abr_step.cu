@@ -547,6 +547,16 @@ abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __
     }
 }
 
+// Per-session QoE cost of Simulator.calculate_qoe (Simulator.py:83-86) from the accumulators:
+// rebuffer_weight * sum(rebuffer) + variance_weight * sum(|delta utility|)  (start-up and latency terms are 0).
+__global__ void __launch_bounds__(kStepBlock)
+abr_qoe_cost_kernel(EnvView v, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    out[i] = dadd(dmul(v.p.rebuf_penalty, v.acc[(size_t)ABR_ACC_REBUF * v.cap + i]),
+                  dmul(v.p.smooth_penalty, v.acc[(size_t)ABR_ACC_SMOOTH * v.cap + i]));
+}
+
 }  // namespace
 
 cudaError_t launch_trace_table(const EnvView& v, double* d_rate, cudaStream_t st) {
@@ -600,6 +610,13 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
 }
 
 int stats_num_partials(int n) { return n <= 0 ? 1 : (n + kStatsSessionsPerBlock - 1) / kStatsSessionsPerBlock; }
+
+cudaError_t launch_qoe_cost(const EnvView& v, double* d_out, cudaStream_t st) {
+    if (v.n == 0) return cudaSuccess;
+    abr_qoe_cost_kernel<<<(v.n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
 
 int rollout_num_blocks(int n) { return n <= 0 ? 1 : (n + kRolloutBlock - 1) / kRolloutBlock; }
 

@@ -254,9 +254,9 @@ class BatchedABREnv:
 
     # -- host-buffer path (what Simulator.run() uses; e2e benchmark leg) --
     def run_host(self, policy, steps, trace_id, start_offset=None, seed=0, session_base=0, actions=None,
-                 want_acc=True, want_stats=True, want_reward_traj=False, out=None):
+                 want_acc=True, want_stats=True, want_reward_traj=False, want_qoe_cost=False, out=None):
         """Reset + fused episode + statistics with HOST (numpy) inputs and outputs.
-        Returns dict(acc=[8,N], stats=[8], reward=[steps,N])."""
+        Returns dict(acc=[8,N], stats=[8], reward=[steps,N], qoe_cost=[N])."""
         pid = _policy_id(policy)
         tid = np.ascontiguousarray(trace_id, dtype=np.int32)
         n = tid.size
@@ -269,6 +269,8 @@ class BatchedABREnv:
             out["stats"] = np.empty(NUM_STATS)
         if want_reward_traj and "reward" not in out:
             out["reward"] = np.empty((steps, n))
+        if want_qoe_cost and "qoe_cost" not in out:
+            out["qoe_cost"] = np.empty(n)
 
         def hp(a):
             return None if a is None else a.ctypes.data_as(C.c_void_p)
@@ -277,7 +279,7 @@ class BatchedABREnv:
             _lib.check(self._lib.abr_env_run_host(
                 self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), hp(tid), hp(off), C.c_int(n),
                 C.c_longlong(session_base), hp(a_in), hp(out.get("acc")), hp(out.get("stats")), hp(out.get("reward")),
-                _stream()))
+                hp(out.get("qoe_cost")), _stream()))
         self.n = n
         self.session_base = int(session_base)
         return out

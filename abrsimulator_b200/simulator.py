@@ -117,8 +117,11 @@ class Simulator:
             env = self._make_env(n_sessions, **extra)
             policy = "random" if isinstance(ctrl, RandomPolicy) else "fixed" if isinstance(ctrl, FixedPolicy) else "bba"
             out = env.run_host(policy, V, tid, start_offset, seed=getattr(ctrl, "seed", 0), session_base=session_base,
-                               actions=getattr(ctrl, "actions", None))
+                               actions=getattr(ctrl, "actions", None), want_qoe_cost=True)
             acc = out["acc"]
+            self.last_run = dict(rebuffer=acc[1], smooth=acc[3], utility=acc[2], reward=acc[0], sleep=acc[4],
+                                 delay=acc[5])
+            return out["qoe_cost"]          # rw*rebuffer + vw*smooth, computed on the device
         elif isinstance(ctrl, MPCBitrateController):
             env = self._make_env(n_sessions, track_history=1, track_acc=1, **ctrl.extra_params)
             env.reset(tid, start_offset, session_base)

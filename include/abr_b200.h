@@ -120,7 +120,8 @@ int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const in
                      const double* h_start_offset, int n_sessions, long long session_base,
                      const int32_t* h_actions_in /*[steps][N], policy FIXED*/,
                      double* h_acc /*[ABR_NUM_ACC][N], nullable*/, double* h_stats /*[ABR_NUM_STATS], nullable*/,
-                     double* h_reward_traj /*[steps][N], nullable*/, void* stream);
+                     double* h_reward_traj /*[steps][N], nullable*/,
+                     double* h_qoe_cost /*[N], nullable: calculate_qoe per session, Simulator.py:83-86*/, void* stream);
 
 /* ---- standalone MPC (replaces MPCBitrateController.next_bitrate over a batch of players,
  *      mpc.py:164-186).  Tables are device pointers [V][A].  History is a per-session ring

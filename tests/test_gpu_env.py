@@ -220,13 +220,15 @@ def test_run_host_path_matches_oracle():
     bitrates, sizes, bw, tl, ti = small_world(n_traces=32, T=256)
     tid, off = synth.make_sessions(N, 32, 256)
     env = BatchedABREnv(bw, sizes, bitrates, 4096, trace_len=tl, trace_interval=ti)
-    out = env.run_host("bba", steps, tid, off, want_reward_traj=True)
+    out = env.run_host("bba", steps, tid, off, want_reward_traj=True, want_qoe_cost=True)
     ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
     ref.reset(tid, off)
     exp = ref.rollout(orc.POLICY_BBA, steps)
     assert_close(out["acc"], exp["acc"], "acc")
     assert_close(out["reward"], exp["reward"], "reward")
     np.testing.assert_allclose(out["stats"], orc.stats_from_acc(exp["acc"]), rtol=1e-9)
+    # per-session QoE cost of Simulator.calculate_qoe (Simulator.py:83-86), computed on the device
+    assert_close(out["qoe_cost"], 4.3 * exp["acc"][1] + 1.0 * exp["acc"][3], "qoe_cost")
 
 
 def test_invalid_inputs_are_flagged_or_rejected():
