@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--sessions", type=int, default=65536, help="sessions per GPU (configs[1])")
     ap.add_argument("--mpc-sessions", type=int, default=131072, help="MPC sessions per GPU (configs[2] / 8)")
     ap.add_argument("--mpc-horizon", type=int, default=5)
+    ap.add_argument("--mpc-h7-sessions", type=int, default=2048, help="sessions per GPU of the horizon-7 leg (0 = skip)")
     ap.add_argument("--no-mpc", action="store_true")
     ap.add_argument("--no-step-form", action="store_true")
     ap.add_argument("--step-sessions", type=int, default=1 << 22, help="sessions per GPU of the per-step-launch leg")
@@ -465,11 +466,31 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
     e1.record(stream)
     e1.synchronize()
     ep_ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    # configs[3]: horizon-7 stress (279 936 sequences per decision), 16 384 sessions over 8 GPUs = 2 048 per GPU;
+    # too few sessions for a warp each, so the kernel gives every session a whole 128-thread block
+    h7 = None
+    if args.mpc_h7_sessions > 0:
+        M7 = args.mpc_h7_sessions
+        env7 = BatchedABREnv(bw, sizes, bitrates, M7, trace_len=tl, trace_interval=ti, track_history=1)
+        tid7, off7 = synth.make_sessions(M7, N_TRACES, T_TRACE, session_base=rank * M7, group=GROUP)
+        env7.reset(tid7, off7, session_base=rank * M7)
+        env7.rollout("bba", 8, want=())
+        act7 = torch.empty(M7, dtype=torch.int32, device=dev)
+        env7.mpc_decide(7, "robust", out=act7)
+        barrier()
+        e0.record(stream)
+        for _ in range(3):
+            env7.mpc_decide(7, "robust", out=act7)
+        e1.record(stream)
+        e1.synchronize()
+        ms7 = max_over_ranks(e0.elapsed_time(e1), dev) / 3
+        h7 = dict(horizon=7, sequences_per_decision=A ** 7, sessions_per_gpu=M7, ms_per_launch=ms7,
+                  decisions_per_s=world * M7 / (ms7 * 1e-3), sequences_per_s=world * M7 * A ** 7 / (ms7 * 1e-3))
     res = dict(metric="mpc_decisions_per_sec", value=dec_per_s, unit="decisions/s", horizon=H, mode="robust",
                sequences_per_decision=A ** H, sessions_per_gpu=M, ms_per_launch=sum(ms) / len(ms),
                reference_exact_mode_decisions_per_s_per_gpu=ref_mode_rate,
                episode=dict(chunks=V, ms=ep_ms, decisions_per_s=world * M * V / (ep_ms * 1e-3),
-                            mean_reward_per_chunk=float(st[0] / st[6])))
+                            mean_reward_per_chunk=float(st[0] / st[6])), horizon7=h7)
     if rank == 0:
         lib = _lib.load()
         probe = {}

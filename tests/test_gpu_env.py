@@ -215,6 +215,25 @@ def test_mpc_episode_matches_oracle(mode):
     assert env.error_count() == 0 and ref.errors() == 0
 
 
+def test_log_utility_mode_matches_oracle():
+    """utility_mode = 1: U = ln(bitrate / top bitrate), the reference's log_bitrate_utility (mpc.py:99-102)."""
+    N, steps = 1024, 30
+    params = dict(utility_mode=1, track_history=1, rebuf_penalty=2.66, smooth_penalty=1.0)
+    env, ref = make_pair(N, params, V=24)
+    util_g = env.state("utility").cpu().numpy()
+    bitr = small_world(V=24)[0]
+    np.testing.assert_allclose(util_g, np.log(bitr / bitr[:, -1:]), rtol=1e-15, atol=0)
+    assert np.all(util_g[:, -1] == 0.0) and np.all(util_g[:, 0] < 0.0)
+    got = env.rollout("bba", steps)
+    exp = ref.rollout(orc.POLICY_BBA, steps)
+    assert np.array_equal(got["actions"].cpu().numpy(), exp["actions"])
+    assert_close(got["reward"].cpu().numpy(), exp["reward"], "reward")
+    for mode in (0, 1):
+        act = env.mpc_decide(4, mode).cpu().numpy()
+        act_ref, _ = ref.mpc_decide(4, mode)
+        assert np.array_equal(act, act_ref)
+
+
 def test_run_host_path_matches_oracle():
     N, steps = 3000, 48
     bitrates, sizes, bw, tl, ti = small_world(n_traces=32, T=256)
