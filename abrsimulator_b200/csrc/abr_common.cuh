@@ -7,6 +7,8 @@
 #include "../../include/abr_b200.h"
 
 #define ABR_WALK_BLOCK 8                     // segments consumed per walk block
+#define ABR_MIN_PERIOD 16                    // a trace is periodic: short ones are walked with a period of >= 16 segments,
+                                             // so that advancing by one block needs a single conditional subtraction
 #define ABR_WALK_PAD (2 * ABR_WALK_BLOCK + 4)  // every rate-table row is followed by a wrapped copy of its start
 
 namespace abr {
@@ -65,7 +67,9 @@ struct EnvView {
     // read-only tables
     const double* __restrict__ trace_bw;        // [n_traces][T_max]
     const double* __restrict__ trace_rate;      // [n_traces][T_max + ABR_WALK_PAD] bw*payload, rows wrapped
-    const int32_t* __restrict__ trace_len;      // [n_traces]
+    const int32_t* __restrict__ trace_len;      // [n_traces] walk period: the trace length, or for traces shorter than
+                                                // ABR_MIN_PERIOD the smallest multiple of it that reaches ABR_MIN_PERIOD
+    const int32_t* __restrict__ trace_len_raw;  // [n_traces] length as given by the caller
     const double* __restrict__ trace_interval;  // [n_traces]
     const double* __restrict__ sizes;           // [V][A]
     const double* __restrict__ util;            // [V][A]
@@ -74,7 +78,7 @@ struct EnvView {
     uint8_t* done;
     double* tau; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
     unsigned long long* errors;                 // device counter of flagged sessions
-    int n_traces, T_max, V, A, K, cap, n;       // n = active sessions
+    int n_traces, T_max, T_rate, V, A, K, cap, n;   // T_rate = max(T_max, longest period): row length of trace_rate; n = active sessions
     long long session_base;
     AbrParams p;
 };

@@ -132,7 +132,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
             s2 = c[kWalkBlock - 1];
             k += kWalkBlock;
             seg += kWalkBlock;
-            if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
+            if (seg >= s.T) seg -= s.T;   // the period is >= ABR_MIN_PERIOD > kWalkBlock
             if (PREFETCH) {
 #pragma unroll
                 for (int u = 0; u < kWalkBlock; ++u) cur[u] = nxt[u];
@@ -154,7 +154,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         sent = sent_f; rate = rate_f;
         k += adv;
         seg += adv;
-        if (seg >= s.T) seg = (seg - s.T < s.T) ? seg - s.T : seg % s.T;
+        if (seg >= s.T) seg -= s.T;
         tau = 0.0;
         elapsed = dadd(room0, dmul((double)(k - 1), s.I));   // time spent in the k segments left behind
     }
@@ -237,7 +237,7 @@ __device__ __forceinline__ int policy_action(const EnvView& v, const Sess& s, in
 
 __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     const int tr = v.trace_id[i];
-    s.rate = v.trace_rate + (size_t)tr * rate_stride(v.T_max);
+    s.rate = v.trace_rate + (size_t)tr * rate_stride(v.T_rate);
     s.sizes = v.sizes;
     s.util = v.util;
     s.T = __ldg(v.trace_len + tr);
@@ -254,13 +254,13 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
 // Builds the rate table from the raw trace: the IEEE product bw*payload SPEC §3.1 forms per segment visit,
 // done once per environment.  Entries past a trace's end repeat it from its start (wrap-around).
 __global__ void __launch_bounds__(kStepBlock)
-abr_trace_table_kernel(const double* __restrict__ bw, const int32_t* __restrict__ trace_len, int n_traces, int T_max,
-                       double payload, double* __restrict__ rate) {
-    const int stride = rate_stride(T_max);
+abr_trace_table_kernel(const double* __restrict__ bw, const int32_t* __restrict__ trace_len_raw, int n_traces, int T_max,
+                       int T_rate, double payload, double* __restrict__ rate) {
+    const int stride = rate_stride(T_rate);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)n_traces * stride) return;
     const int t = (int)(i / stride), j = (int)(i % stride);
-    rate[i] = dmul(bw[(size_t)t * T_max + j % trace_len[t]], payload);
+    rate[i] = dmul(bw[(size_t)t * T_max + j % trace_len_raw[t]], payload);
 }
 
 __global__ void __launch_bounds__(kStepBlock)
@@ -436,7 +436,7 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
     __syncthreads();
     const int tr0 = s_tr0;
     // block-uniform: every session of this block follows trace tr0 and its padded row fits
-    const int need = __ldg(v.trace_len + tr0) + ABR_WALK_PAD;   // <= rate_stride(T_max), so the copy stays in the row
+    const int need = __ldg(v.trace_len + tr0) + ABR_WALK_PAD;   // <= rate_stride(T_rate), so the copy stays in the row
     const bool use_smem = __syncthreads_and((!valid || tr == tr0) ? 1 : 0) && need <= smem_doubles;
     if (use_smem) {
         // Stage the trace row and the chunk-size / utility tables with TMA bulk copies (cp.async.bulk, SASS UBLKCP):
@@ -446,7 +446,7 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
         double* s_row = reinterpret_cast<double*>(s_row2);
         double* s_sizes = s_row + smem_doubles;
         double* s_util = s_sizes + v.V * v.A;
-        const double* g_row = v.trace_rate + (size_t)tr0 * rate_stride(v.T_max);
+        const double* g_row = v.trace_rate + (size_t)tr0 * rate_stride(v.T_rate);
         const uint32_t row_bytes = (uint32_t)((need + 1) / 2) * 16u;
         const uint32_t tab_bytes = (uint32_t)(v.V * v.A) * 8u;
         const bool tab_bulk = (tab_bytes & 15u) == 0;
@@ -560,9 +560,9 @@ abr_qoe_cost_kernel(EnvView v, double* __restrict__ out) {
 }  // namespace
 
 cudaError_t launch_trace_table(const EnvView& v, double* d_rate, cudaStream_t st) {
-    const size_t n = (size_t)v.n_traces * rate_stride(v.T_max);
+    const size_t n = (size_t)v.n_traces * rate_stride(v.T_rate);
     abr_trace_table_kernel<<<(unsigned)((n + kStepBlock - 1) / kStepBlock), kStepBlock, 0, st>>>(
-        v.trace_bw, v.trace_len, v.n_traces, v.T_max, v.p.payload, d_rate);
+        v.trace_bw, v.trace_len_raw, v.n_traces, v.T_max, v.T_rate, v.p.payload, d_rate);
     count_launch();
     return cudaGetLastError();
 }
@@ -592,7 +592,7 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
     RolloutOut o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out};
     // shared-memory row buffer: the longest padded row when it leaves room for >= 7 blocks per SM, else disabled
-    int smem_doubles = rate_stride(v.T_max);
+    int smem_doubles = rate_stride(v.T_rate);
     size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double);
     if (smem_bytes > 32 * 1024) { smem_doubles = 0; smem_bytes = 0; }
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
