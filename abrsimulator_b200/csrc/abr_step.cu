@@ -145,15 +145,28 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     // every lane has reconverged here; lanes that walked pick the first u with c[u] >= size, once
     double elapsed = 0.0;
     if (multi) {
-        int adv = kWalkBlock;
-        double sent_f = c[kWalkBlock - 2], rate_f = cur[kWalkBlock - 1];
-#pragma unroll
-        for (int u = kWalkBlock - 1; u >= 0; --u) {
-            if (c[u] >= size) { adv = u + 1; sent_f = u ? c[u - 1] : s2; rate_f = cur[u]; }
+        // c[] is non-decreasing and c[7] >= size: binary search for the first u with c[u] >= size (3 compares),
+        // then the total before that segment comes out of a 3-level select tree and its rate is re-read by index
+        static_assert(kWalkBlock == 8, "the selection tree below is written for blocks of 8 segments");
+        const bool h2 = !(c[3] >= size);
+        const double m1 = h2 ? c[5] : c[1];
+        const bool h1 = !(m1 >= size);
+        const double m0 = h2 ? (h1 ? c[6] : c[4]) : (h1 ? c[2] : c[0]);
+        const bool h0 = !(m0 >= size);
+        const int ustar = (h2 ? 4 : 0) + (h1 ? 2 : 0) + (h0 ? 1 : 0);
+        const double p01 = h0 ? c[0] : s2, p23 = h0 ? c[2] : c[1], p45 = h0 ? c[4] : c[3], p67 = h0 ? c[6] : c[5];
+        const double p03 = h1 ? p23 : p01, p47 = h1 ? p67 : p45;
+        sent = h2 ? p47 : p03;
+        if (SMEM) {
+            rate = row[seg + 1 + ustar];   // one LDS instead of a second select tree
+        } else {                           // a scattered global re-read would cost an L1 wavefront per lane
+            const double r01 = h0 ? cur[1] : cur[0], r23 = h0 ? cur[3] : cur[2];
+            const double r45 = h0 ? cur[5] : cur[4], r67 = h0 ? cur[7] : cur[6];
+            const double r03 = h1 ? r23 : r01, r47 = h1 ? r67 : r45;
+            rate = h2 ? r47 : r03;
         }
-        sent = sent_f; rate = rate_f;
-        k += adv;
-        seg += adv;
+        k += ustar + 1;
+        seg += ustar + 1;
         if (seg >= s.T) seg -= s.T;
         tau = 0.0;
         elapsed = dadd(room0, dmul((double)(k - 1), s.I));   // time spent in the k segments left behind
