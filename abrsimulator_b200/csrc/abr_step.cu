@@ -78,12 +78,13 @@ __device__ __forceinline__ void load_rates(const double* __restrict__ row, int i
 // SMEM: s.rate points at the block's shared-memory copy of the trace row (else at the global table).
 // PREFETCH: fetch the following block while the current one is consumed (pays off when few warps are resident,
 // i.e. the fused episode on the global path; the per-step kernel hides the latency with occupancy instead).
-template <bool SMEM, bool PREFETCH>
+// FAST: auto_reset is on (a session is never inert) — drops the done/inert bookkeeping.
+template <bool SMEM, bool PREFETCH, bool FAST = false>
 __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, StepRes& r, const bool want_thr) {
     const AbrParams& p = v.p;
     r.walk_error = false;
     r.reset_mpc = false;
-    if (s.done) {  // only reachable with auto_reset == 0
+    if (!FAST && s.done) {  // only reachable with auto_reset == 0
         r.delay = r.sleep = r.rebuf = r.reward = r.thr = r.u = r.smooth = 0.0;
         r.buffer = s.buffer;
         r.eov = true;
@@ -217,7 +218,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     s.buffer = buffer;
     r.eov = (s.chunk >= v.V);
     if (r.eov) {
-        if (p.auto_reset) {
+        if (FAST || p.auto_reset) {
             s.chunk = 0; s.buffer = 0.0; s.last_q = p.default_quality; s.hist_len = 0;
             r.reset_mpc = true;
         } else {
@@ -351,7 +352,9 @@ struct RolloutOut {
 };
 
 // `steps` chunk steps of one session with the state in registers (SPEC §3+§4).
-template <int POLICY, bool SMEM>
+// FAST: the common shape — all six trajectory outputs requested, no action trace, no throughput history,
+// auto_reset on — compiled without the per-output null checks and the inert/history bookkeeping.
+template <int POLICY, bool SMEM, bool FAST>
 __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const int i, const uint32_t seed_lo,
                                                 const uint32_t seed_hi, const int steps,
                                                 const int32_t* __restrict__ actions_in, const RolloutOut& o,
@@ -360,27 +363,34 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_steps = 0.0, a_eps = 0.0;
     bool flagged = false, reset_mpc = false;
     const int n = v.n;
+    const bool hist = !FAST && v.p.track_history != 0;
     uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
     for (int t = 0; t < steps; ++t) {
         int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t, actions_in, i, rnd);
-        if (q < 0 || q >= v.A) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
+        if (POLICY == ABR_POLICY_FIXED && (q < 0 || q >= v.A)) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
         StepRes r;
-        step_core<SMEM, !SMEM>(v, s, q, r, v.p.track_history != 0);
+        step_core<SMEM, !SMEM, FAST>(v, s, q, r, hist);
         flagged |= r.walk_error;
         const size_t ix = (size_t)t * n + i;
-        if (o.delay) __stcs(o.delay + ix, r.delay);
-        if (o.sleep) __stcs(o.sleep + ix, r.sleep);
-        if (o.buffer) __stcs(o.buffer + ix, r.buffer);
-        if (o.rebuf) __stcs(o.rebuf + ix, r.rebuf);
-        if (o.reward) __stcs(o.reward + ix, r.reward);
-        if (o.eov) o.eov[ix] = r.eov ? 1 : 0;
-        if (o.actions) __stcs(o.actions + ix, q);
-        if (!r.inert) {
+        if (FAST) {
+            __stcs(o.delay + ix, r.delay); __stcs(o.sleep + ix, r.sleep); __stcs(o.buffer + ix, r.buffer);
+            __stcs(o.rebuf + ix, r.rebuf); __stcs(o.reward + ix, r.reward);
+            o.eov[ix] = r.eov ? 1 : 0;
+        } else {
+            if (o.delay) __stcs(o.delay + ix, r.delay);
+            if (o.sleep) __stcs(o.sleep + ix, r.sleep);
+            if (o.buffer) __stcs(o.buffer + ix, r.buffer);
+            if (o.rebuf) __stcs(o.rebuf + ix, r.rebuf);
+            if (o.reward) __stcs(o.reward + ix, r.reward);
+            if (o.eov) o.eov[ix] = r.eov ? 1 : 0;
+            if (o.actions) __stcs(o.actions + ix, q);
+        }
+        if (FAST || !r.inert) {
             a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
             a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
             a_steps += 1.0;
             if (r.eov) a_eps += 1.0;
-            if (v.p.track_history) {
+            if (hist) {
                 if (r.reset_mpc) reset_mpc = true;
                 else v.bw_hist[(size_t)((s.hist_len - 1) % v.K) * v.cap + i] = r.thr;
             }
@@ -388,9 +398,9 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     }
     if (flagged) atomicAdd(v.errors, 1ull);
     v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
-    if (v.p.track_history) v.hist_len[i] = s.hist_len;
+    if (hist) v.hist_len[i] = s.hist_len;
     if (reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
-    if (s.done) v.done[i] = 1;
+    if (!FAST && s.done) v.done[i] = 1;
     // accumulator read-modify-write: all eight loads first (one memory round trip instead of eight dependent ones)
     double* a = v.acc + i;
     const size_t c = v.cap;
@@ -429,7 +439,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
 // is followed by room for the sizes and utility tables.
 // 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
 // co-resident (6.9 per SM); at 140 registers only 3 warps fit per scheduler and a second wave appears.
-template <int POLICY>
+template <int POLICY, bool FAST>
 __global__ void __launch_bounds__(kRolloutBlock, 8)
 abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
                    RolloutOut o, int smem_doubles, double* __restrict__ block_partials) {
@@ -490,10 +500,10 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
             s.rate = s_row;
             s.sizes = s_sizes;
             s.util = s_util;
-            rollout_session<POLICY, true>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+            rollout_session<POLICY, true, FAST>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
         }
     } else if (valid) {
-        rollout_session<POLICY, false>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+        rollout_session<POLICY, false, FAST>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
     }
     // statistics stage 1 fused into the episode: per-block sums of the updated accumulators in a fixed order
     // (warp tree, then warps in ascending order), so abr_stats_partial only has to add the block partials
@@ -608,9 +618,17 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     int smem_doubles = rate_stride(v.T_rate);
     size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double);
     if (smem_bytes > 32 * 1024) { smem_doubles = 0; smem_bytes = 0; }
+    const bool fast = d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && !d_actions_out &&
+                      v.p.track_history == 0 && v.p.auto_reset != 0;
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
-    abr_rollout_kernel<P><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o, smem_doubles,            \
-                                                           d_block_partials)
+    do {                                                                                                           \
+        if (fast)                                                                                                  \
+            abr_rollout_kernel<P, true><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,         \
+                                                                         smem_doubles, d_block_partials);          \
+        else                                                                                                       \
+            abr_rollout_kernel<P, false><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,        \
+                                                                          smem_doubles, d_block_partials);         \
+    } while (0)
     switch (policy) {
         case ABR_POLICY_FIXED: ABR_LAUNCH_ROLLOUT(ABR_POLICY_FIXED); break;
         case ABR_POLICY_RANDOM: ABR_LAUNCH_ROLLOUT(ABR_POLICY_RANDOM); break;

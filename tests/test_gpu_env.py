@@ -159,6 +159,42 @@ def test_fused_rollout_shared_memory_trace_path(ragged):
     assert env.error_count() == 0
 
 
+@pytest.mark.parametrize("policy", ["random", "bba", "fixed"])
+def test_fast_variant_of_the_fused_kernel(policy):
+    """All six trajectory outputs, no action trace, no history, auto_reset on selects the kernel variant compiled
+    without per-output null checks and inert bookkeeping (the bench shape): same results as the generic variant
+    and as the oracle, over two episodes (crosses the end-of-video reset), on both trace paths."""
+    N, steps = 64 * 20 + 9, 100
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=10, T=200)
+    tid = ((np.arange(N) // 64) % 10).astype(np.int32)
+    tid[64 * 12:64 * 15] = np.random.default_rng(2).integers(0, 10, size=64 * 3)     # mixed blocks: global path
+    off = np.random.default_rng(3).uniform(0, 400.0, size=N)
+    acts = np.random.default_rng(4).integers(0, 6, size=(steps, N)).astype(np.int32) if policy == "fixed" else None
+    six = ("delay", "sleep", "buffer", "rebuffer", "reward", "end_of_video")
+    outs = []
+    for want in (six, six + ("actions",)):
+        env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+        env.reset(tid, off)
+        outs.append((env.rollout(policy, steps, seed=11, actions=acts, want=want), env.session_acc().clone(),
+                     env.stats().clone(), {f: env.state(f).clone() for f in STATE_I + STATE_F}))
+        assert env.error_count() == 0
+    (fast, acc_f, st_f, state_f), (gen, acc_g, st_g, state_g) = outs
+    for k in six:
+        assert torch.equal(fast[k], gen[k]), k
+    assert torch.equal(acc_f, acc_g) and torch.equal(st_f, st_g)
+    for f in STATE_I + STATE_F:
+        assert torch.equal(state_f[f], state_g[f]), f
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
+    ref.reset(tid, off)
+    pid = dict(random=orc.POLICY_RANDOM, bba=orc.POLICY_BBA, fixed=orc.POLICY_FIXED)[policy]
+    exp = ref.rollout(pid, steps, seed=11, actions=acts)
+    for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                     ("reward", "reward")):
+        assert_close(fast[k_g].cpu().numpy(), exp[k_c], k_g)
+    assert np.array_equal(fast["end_of_video"].cpu().numpy(), exp["eov"])
+    assert_close(acc_f.cpu().numpy(), exp["acc"], "acc")
+
+
 def test_fused_rollout_equals_stepwise():
     """Size-independent property: the fused episode is the per-step kernel applied `steps` times."""
     N, steps = 2048, 48
