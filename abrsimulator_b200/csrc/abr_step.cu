@@ -298,7 +298,11 @@ abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* 
     for (int j = 0; j < ABR_NUM_ACC; ++j) v.acc[(size_t)j * v.cap + i] = 0.0;
 }
 
-// <= 64 registers: 4 blocks of 256 threads per SM; the kernel is latency/LSU-bound and lives on occupancy
+// <= 64 registers: 4 blocks of 256 threads per SM; the kernel is latency/LSU-bound and lives on occupancy.
+// FAST: the five f64 outputs and end_of_video requested, no throughput history / accumulators, auto_reset on —
+// compiled without the null checks and the inert/history/accumulator bookkeeping (next_sizes and throughput stay
+// optional in both variants).
+template <bool FAST>
 __global__ void __launch_bounds__(kStepBlock, 4)
 abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restrict__ o_delay,
                 double* __restrict__ o_sleep, double* __restrict__ o_buffer, double* __restrict__ o_rebuf,
@@ -311,38 +315,46 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restric
     int q = action[i];
     if (q < 0 || q >= v.A) { atomicAdd(v.errors, 1ull); q = q < 0 ? 0 : v.A - 1; }
     StepRes r;
-    step_core<false, false>(v, s, q, r, v.p.track_history || o_thr != nullptr);
+    step_core<false, false, FAST>(v, s, q, r, (!FAST && v.p.track_history) || o_thr != nullptr);
     if (r.walk_error) atomicAdd(v.errors, 1ull);
-    if (!r.inert) {
+    if (FAST) {
         v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
-        if (v.p.track_history) {
-            // ring slot of this sample = (hist_len before the step) mod K; after an auto-reset hist_len is 0
-            const int prev_len = r.reset_mpc ? 0 : s.hist_len - 1;
-            if (!r.reset_mpc) v.bw_hist[(size_t)(prev_len % v.K) * v.cap + i] = r.thr;
-            v.hist_len[i] = s.hist_len;
+        __stcs(o_delay + i, r.delay); __stcs(o_sleep + i, r.sleep); __stcs(o_buffer + i, r.buffer);
+        __stcs(o_rebuf + i, r.rebuf); __stcs(o_reward + i, r.reward);
+        o_eov[i] = r.eov ? 1 : 0;
+    } else {
+        if (!r.inert) {
+            v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
+            if (v.p.track_history) {
+                // ring slot of this sample = (hist_len before the step) mod K; after an auto-reset hist_len is 0
+                const int prev_len = r.reset_mpc ? 0 : s.hist_len - 1;
+                if (!r.reset_mpc) v.bw_hist[(size_t)(prev_len % v.K) * v.cap + i] = r.thr;
+                v.hist_len[i] = s.hist_len;
+            }
+            if (r.reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
+            if (s.done) v.done[i] = 1;
+            if (v.p.track_acc) {
+                double* a = v.acc + i;
+                const size_t c = v.cap;
+                a[0 * c] = dadd(a[0 * c], r.reward); a[1 * c] = dadd(a[1 * c], r.rebuf); a[2 * c] = dadd(a[2 * c], r.u);
+                a[3 * c] = dadd(a[3 * c], r.smooth); a[4 * c] = dadd(a[4 * c], r.sleep);
+                a[5 * c] = dadd(a[5 * c], r.delay);
+                a[6 * c] = dadd(a[6 * c], 1.0);
+                if (r.eov) a[7 * c] = dadd(a[7 * c], 1.0);
+            }
         }
-        if (r.reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
-        if (s.done) v.done[i] = 1;
-        if (v.p.track_acc) {
-            double* a = v.acc + i;
-            const size_t c = v.cap;
-            a[0 * c] = dadd(a[0 * c], r.reward); a[1 * c] = dadd(a[1 * c], r.rebuf); a[2 * c] = dadd(a[2 * c], r.u);
-            a[3 * c] = dadd(a[3 * c], r.smooth); a[4 * c] = dadd(a[4 * c], r.sleep); a[5 * c] = dadd(a[5 * c], r.delay);
-            a[6 * c] = dadd(a[6 * c], 1.0);
-            if (r.eov) a[7 * c] = dadd(a[7 * c], 1.0);
-        }
+        if (o_delay) __stcs(o_delay + i, r.delay);
+        if (o_sleep) __stcs(o_sleep + i, r.sleep);
+        if (o_buffer) __stcs(o_buffer + i, r.buffer);
+        if (o_rebuf) __stcs(o_rebuf + i, r.rebuf);
+        if (o_reward) __stcs(o_reward + i, r.reward);
+        if (o_eov) o_eov[i] = r.eov ? 1 : 0;
     }
-    if (o_delay) __stcs(o_delay + i, r.delay);
-    if (o_sleep) __stcs(o_sleep + i, r.sleep);
-    if (o_buffer) __stcs(o_buffer + i, r.buffer);
-    if (o_rebuf) __stcs(o_rebuf + i, r.rebuf);
-    if (o_reward) __stcs(o_reward + i, r.reward);
-    if (o_eov) o_eov[i] = r.eov ? 1 : 0;
     if (o_thr) __stcs(o_thr + i, r.thr);
     if (o_next_sizes) {
         const int A = v.A;
         for (int a = 0; a < A; ++a)
-            o_next_sizes[(size_t)i * A + a] = s.done ? 0.0 : __ldg(v.sizes + s.chunk * A + a);
+            o_next_sizes[(size_t)i * A + a] = (!FAST && s.done) ? 0.0 : __ldg(v.sizes + s.chunk * A + a);
     }
 }
 
@@ -601,8 +613,15 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, double* d_del
                         double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_eov, double* d_thr,
                         cudaStream_t st) {
     if (v.n == 0) return cudaSuccess;
-    abr_step_kernel<<<(v.n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(
-        v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_next_sizes, d_eov, d_thr);
+    const bool fast = d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && v.p.track_history == 0 &&
+                      v.p.track_acc == 0 && v.p.auto_reset != 0;
+    const unsigned grid = (v.n + kStepBlock - 1) / kStepBlock;
+    if (fast)
+        abr_step_kernel<true><<<grid, kStepBlock, 0, st>>>(v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward,
+                                                           d_next_sizes, d_eov, d_thr);
+    else
+        abr_step_kernel<false><<<grid, kStepBlock, 0, st>>>(v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward,
+                                                            d_next_sizes, d_eov, d_thr);
     count_launch();
     return cudaGetLastError();
 }

@@ -17,7 +17,7 @@ ncu --set full --clock-control none --import-source on -k regex:abr_mpc_kernel -
 echo "mpc capture rc=$?"
 fi
 if [ -n "${WITH_STEP:-}" ]; then
-ncu --set full --clock-control none --import-source on -k regex:abr_step_kernel -s 12 -c 1 -f -o gpurun_out/step_$TAG $CMD > gpurun_out/ncu_step_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:abr_step_kernel -s 60 -c 1 -f -o gpurun_out/step_$TAG $CMD > gpurun_out/ncu_step_$TAG.log 2>&1
 echo "step capture rc=$?"
 fi
 ls -la gpurun_out/

@@ -51,7 +51,7 @@ def to_bytes(s):
 
 summary = {}
 traffic = {}
-for name in ("rollout", "mpc"):
+for name in ("rollout", "mpc", "step"):
     rep = os.path.join(ROOT, "gpurun_out", f"{name}_{tag}.ncu-rep")
     if os.path.exists(rep):
         summary[name] = raw(rep)
