@@ -381,7 +381,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t, actions_in, i, rnd);
         if (POLICY == ABR_POLICY_FIXED && (q < 0 || q >= v.A)) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
         StepRes r;
-        step_core<SMEM, !SMEM, FAST>(v, s, q, r, hist);
+        step_core<SMEM, true, FAST>(v, s, q, r, hist);
         flagged |= r.walk_error;
         const size_t ix = (size_t)t * n + i;
         if (FAST) {
