@@ -27,6 +27,7 @@ namespace {
 constexpr int kMaxH = 8;
 constexpr int kMaxA = 16;
 constexpr int kMpcWarpsPerBlock = 4;
+constexpr int kPrefixCache = 64;   // parent states cached in shared memory per session (4 doubles each)
 
 struct SearchOut { double q; int idx; };
 
@@ -49,12 +50,13 @@ __device__ __forceinline__ void interior(double& vq, double& qv, double& rt, dou
 // sAD is |U[h-1][a] - U[h-1][a']| as [a][a'] (the leaf-level smoothness term).
 // AT > 0: compile-time ladder size (loops fully unrolled); AT == 0: runtime A (generic path).
 // VW1: smooth_penalty == 1.0, so vw*qv == qv exactly and the multiply is dropped.
-template <int AT, bool CLAMP, bool VW1>
+// WPS: warps per session (selects the barrier that separates filling and reading the parent-state cache).
+template <int AT, bool CLAMP, bool VW1, int WPS>
 __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const double* __restrict__ sRB,
                                             const double* __restrict__ sDL, const double* __restrict__ sAD,
-                                            const int a_rt, const int h, const int prev_q, const double buf0,
-                                            const double vw, const double rw, const double L, const double B,
-                                            const int tid, const int nthreads) {
+                                            double* __restrict__ sPC, const int a_rt, const int h, const int prev_q,
+                                            const double buf0, const double vw, const double rw, const double L,
+                                            const double B, const int tid, const int nthreads) {
     const int A = AT > 0 ? AT : a_rt;
     constexpr bool REGTAB = AT > 0 && AT <= 6;   // larger ladders keep the rows in shared memory
     constexpr int AR = REGTAB ? AT : 1;         // register-array extent
@@ -68,28 +70,65 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
 #pragma unroll
         for (int a = 0; a < AR; ++a) { U5[a] = sU[i5 * A + a]; RB5[a] = sRB[i5 * A + a]; }
     }
+    // Parent-state cache: the running sums after the first P-1 levels are shared by A prefixes each; when there are
+    // few enough (36 at A = 6, h = 5) they are computed once per decision into shared memory, so a prefix costs one
+    // interior step instead of P.  Same operations in the same order as the from-scratch path below.
+    const int n_par = P >= 2 ? n_prefix / A : 0;
+    const bool use_cache = P >= 2 && n_par <= kPrefixCache;
+    if (use_cache) {
+        for (int idx = tid; idx < n_par; idx += nthreads) {
+            int dig[kMaxH];
+            int rem = idx;
+#pragma unroll
+            for (int i = kMaxH - 4; i >= 0; --i) {
+                if (i < P - 1) { dig[i] = rem % A; rem /= A; }
+            }
+            double vq = 0.0, qv = 0.0, rt = 0.0, b = buf0;
+            int ap = prev_q;
+#pragma unroll
+            for (int i = 0; i < kMaxH - 3; ++i) {
+                if (i < P - 1) {
+                    const int a = dig[i];
+                    const double u = sU[i * A + a];
+                    const double up = ap >= 0 ? sU[i * A + ap] : u;
+                    interior<CLAMP>(vq, qv, rt, b, u, fabs(dsub(u, up)), sRB[i * A + a], sDL[i * A + a], L, B);
+                    ap = a;
+                }
+            }
+            sPC[idx * 4 + 0] = vq; sPC[idx * 4 + 1] = qv; sPC[idx * 4 + 2] = rt; sPC[idx * 4 + 3] = b;
+        }
+        if (WPS > 1) __syncthreads(); else __syncwarp();
+    }
     double best_q = __longlong_as_double(0xfff0000000000000ll);  // -inf
     int best_idx = 0x7fffffff;
     for (int p = tid; p < n_prefix; p += nthreads) {
-        // decode the prefix digits (most significant first) and roll the state through levels 0..P-1
-        int dig[kMaxH];
-        {
+        double vq = 0.0, qv = 0.0, rt = 0.0, b = buf0;
+        int ap = prev_q;
+        if (use_cache) {
+            const int par = p / A, a = p - par * A;
+            vq = sPC[par * 4 + 0]; qv = sPC[par * 4 + 1]; rt = sPC[par * 4 + 2]; b = sPC[par * 4 + 3];
+            ap = par % A;                                // last digit of the parent prefix (P >= 2)
+            const int i = P - 1;
+            const double u = sU[i * A + a];
+            interior<CLAMP>(vq, qv, rt, b, u, fabs(dsub(u, sU[i * A + ap])), sRB[i * A + a], sDL[i * A + a], L, B);
+            ap = a;
+        } else {
+            // decode the prefix digits (most significant first) and roll the state through levels 0..P-1
+            int dig[kMaxH];
             int rem = p;
 #pragma unroll
             for (int i = kMaxH - 3; i >= 0; --i) {
                 if (i < P) { dig[i] = rem % A; rem /= A; }
             }
-        }
-        double vq = 0.0, qv = 0.0, rt = 0.0, b = buf0;
-        int ap = prev_q;
 #pragma unroll
-        for (int i = 0; i < kMaxH - 2; ++i) {
-            if (i < P) {
-                const int a = dig[i];
-                const double u = sU[i * A + a];
-                const double up = ap >= 0 ? sU[i * A + ap] : u;
-                interior<CLAMP>(vq, qv, rt, b, u, fabs(dsub(u, up)), sRB[i * A + a], sDL[i * A + a], L, B);
-                ap = a;
+            for (int i = 0; i < kMaxH - 2; ++i) {
+                if (i < P) {
+                    const int a = dig[i];
+                    const double u = sU[i * A + a];
+                    const double up = ap >= 0 ? sU[i * A + ap] : u;
+                    interior<CLAMP>(vq, qv, rt, b, u, fabs(dsub(u, up)), sRB[i * A + a], sDL[i * A + a], L, B);
+                    ap = a;
+                }
             }
         }
         const double up4 = ap >= 0 ? sU[i4 * A + ap] : 0.0;
@@ -123,6 +162,7 @@ __device__ __forceinline__ void better(double& q, int& idx, const double oq, con
 
 struct __align__(8) SessShared {
     double U[kMaxH * kMaxA], RB[kMaxH * kMaxA], DL[kMaxH * kMaxA], AD[kMaxA * kMaxA];
+    double PC[kPrefixCache * 4];
     double redq[kMpcWarpsPerBlock];
     int redi[kMpcWarpsPerBlock];
 };
@@ -266,11 +306,11 @@ abr_mpc_kernel(const MpcArgs a) {
                 o.q = bq; o.idx = bi;
             } else {
                 if (p.smooth_penalty == 1.0)
-                    o = search<AT, CLAMP, true>(S.U, S.RB, S.DL, S.AD, A, h, prev_q, buf0, 1.0, p.rebuf_penalty, L, B,
-                                                tid, NT);
+                    o = search<AT, CLAMP, true, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, buf0, 1.0, p.rebuf_penalty,
+                                                     L, B, tid, NT);
                 else
-                    o = search<AT, CLAMP, false>(S.U, S.RB, S.DL, S.AD, A, h, prev_q, buf0, p.smooth_penalty,
-                                                 p.rebuf_penalty, L, B, tid, NT);
+                    o = search<AT, CLAMP, false, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, buf0, p.smooth_penalty,
+                                                      p.rebuf_penalty, L, B, tid, NT);
             }
             // ---- argmin over the session's threads: key (J, linear index) ----
 #pragma unroll
