@@ -41,6 +41,7 @@ struct AbrEnv {
     std::vector<void*> allocs;
     double* d_stats_partials = nullptr;
     int n_partials_cap = 0;
+    bool was_reset = false;   // abr_env_reset has run (an empty batch, n == 0, is legal and makes every call a no-op)
     int fresh_partials = 0;   // > 0: d_stats_partials holds that many block sums of the current accumulators
     double* d_stats_out = nullptr;
     // scratch for the *_host entry points
@@ -221,18 +222,19 @@ int abr_env_num_sessions(const AbrEnv* env) { return env ? env->v.n : 0; }
 
 int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_offset, int n_sessions,
                   long long session_base, void* stream) {
-    if (!env || !d_trace_id) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
+    if (!env || (!d_trace_id && n_sessions > 0)) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
     if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
     env->v.n = n_sessions;
     env->v.session_base = session_base;
     env->fresh_partials = 0;
+    env->was_reset = true;
     CUDA_TRY(launch_reset(env->v, d_trace_id, d_start_offset, (cudaStream_t)stream));
     return ABR_OK;
 }
 
 int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_start_offset, int n_sessions,
                        long long session_base, void* stream) {
-    if (!env || !h_trace_id) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
+    if (!env || (!h_trace_id && n_sessions > 0)) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
     if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(env->d_trace_id, h_trace_id, sizeof(int32_t) * n_sessions, cudaMemcpyHostToDevice, st));
@@ -244,8 +246,10 @@ int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_s
 int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
                  double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_end_of_video, double* d_throughput,
                  void* stream) {
-    if (!env || !d_action) return fail(ABR_ERR_INVALID, "env or action is NULL");
-    if (env->v.n <= 0) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
+    if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    if (env->v.n == 0) return ABR_OK;
+    if (!d_action) return fail(ABR_ERR_INVALID, "action is NULL");
     env->fresh_partials = 0;
     CUDA_TRY(launch_step(env->v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_next_sizes, d_end_of_video,
                          d_throughput, (cudaStream_t)stream));
@@ -256,7 +260,8 @@ int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, con
                           double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
                           uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream) {
     if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
-    if (env->v.n <= 0) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    if (env->v.n == 0) return ABR_OK;
     if (steps < 0) return fail(ABR_ERR_RANGE, "steps must be >= 0");
     if (policy < ABR_POLICY_FIXED || policy > ABR_POLICY_BBA) return fail(ABR_ERR_INVALID, "unknown policy %d", policy);
     if (policy == ABR_POLICY_FIXED && !d_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs d_actions_in");
@@ -276,8 +281,10 @@ static int check_mpc_shape(int A, int H) {
 }
 
 int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, double* d_best_j, void* stream) {
-    if (!env || !d_action) return fail(ABR_ERR_INVALID, "env or action is NULL");
-    if (env->v.n <= 0) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
+    if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    if (env->v.n == 0) return ABR_OK;
+    if (!d_action) return fail(ABR_ERR_INVALID, "action is NULL");
     if (mode != ABR_MPC_REF && mode != ABR_MPC_ROBUST) return fail(ABR_ERR_INVALID, "unknown MPC mode %d", mode);
     int rc = check_mpc_shape(env->v.A, horizon);
     if (rc) return rc;

@@ -673,6 +673,7 @@ int rollout_num_blocks(int n) { return n <= 0 ? 1 : (n + kRolloutBlock - 1) / kR
 // have_partials: d_partials already holds n_partials block sums (written by the fused episode kernel)
 cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, bool have_partials, double* d_out,
                          cudaStream_t st) {
+    if (v.n == 0) return cudaMemsetAsync(d_out, 0, sizeof(double) * ABR_NUM_STATS, st);   // empty batch
     if (!have_partials) {
         abr_stats_stage1<<<n_partials, kStatsBlock, 0, st>>>(v, d_partials);
         count_launch();

@@ -499,10 +499,11 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
             t = C.c_float(0.0)
             _lib.check(lib.abr_fp64_probe(C.c_int(kind), C.c_int(4096), C.byref(g), C.byref(t), None))
             probe[name + "_gops"] = g.value
-        # fp64-pipe instructions the search executes per decision: per prefix round
-        # (h-2) interior steps + A interior + A^2 leaves; 9 fp64-pipe instructions each (leaf: 8 arithmetic + compare)
+        # fp64-pipe thread-instructions the search executes per decision, counted from the SASS of the
+        # inner loops: per prefix slot (rounded up to whole warps) one interior step (9) + A interior steps (9 each) +
+        # A^2 leaves (7 arithmetic + 1 compare with smooth_penalty == 1), plus the parent-state cache fill
         rounds = -(-(A ** (H - 2)) // 32) * 32
-        executed = rounds * ((H - 2) * 9 + A * 9 + A * A * 9)
+        executed = rounds * (9 + A * 9 + A * A * 8) + 64 * (H - 3) * 9
         naive = A ** H * (14 * (H - 1) + 13) + 4 * A * H
         peak = probe["dadd_gops"]
         res["roofline"] = dict(bound="fp64-issue", unit="Gop/s", peak=peak, peak_source="abr_fp64_probe (DADD chains, same run)",

@@ -309,6 +309,44 @@ def test_invalid_inputs_are_flagged_or_rejected():
         env.step(np.zeros(3, np.int32))
 
 
+def test_edge_shapes_empty_batch_single_chunk_video_and_widest_ladder():
+    """Empty batch (legal no-op), a one-chunk video (end of video on every step), the widest supported ladder
+    (A = 16, runtime-A MPC path) and the longest history ring (K = 64)."""
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=4, T=64)
+    env = BatchedABREnv(bw, sizes, bitrates, 16, trace_len=tl, trace_interval=ti)
+    with pytest.raises(_lib.AbrError):
+        env.rollout("bba", 4)                                  # reset has not been called
+    env.reset(np.zeros(0, np.int32))
+    out = env.rollout("bba", 4)
+    assert out["reward"].shape == (4, 0)
+    assert env.step(np.zeros(0, np.int32)).reward.numel() == 0
+    assert float(env.stats().abs().sum()) == 0.0 and env.mpc_decide(3, "robust").numel() == 0
+    # one-chunk video
+    env1, ref1 = make_pair(128, dict(track_acc=1), V=1)
+    for t in range(3):
+        a = np.full(128, t % 6, np.int32)
+        got, exp = env1.step(a), ref1.step(a)
+        assert_close(got.reward.cpu().numpy(), exp["reward"], "reward")
+        assert bool((got.end_of_video == 1).all())
+    assert np.all(env1.session_acc().cpu().numpy()[7] == 3.0)
+    # A = 16, K = 64
+    lad = tuple(float(x) for x in np.linspace(200, 8000, 16))
+    params = dict(track_history=1, hist_k=64)
+    env16, ref16 = make_pair(256, params, V=20, ladder=lad)
+    for t in range(5):
+        act = env16.mpc_decide(2, t % 2)
+        act_ref, _ = ref16.mpc_decide(2, t % 2)
+        assert np.array_equal(act.cpu().numpy(), act_ref)
+        got, exp = env16.step(act, want_next_sizes=True), ref16.step(act_ref)
+        assert_close(got.next_sizes.cpu().numpy(), exp["next_sizes"], "next_sizes")
+    with pytest.raises(_lib.AbrError):
+        env16.mpc_decide(8, 0)                                 # 16^8 sequences exceed the 2^31-1 index range
+    with pytest.raises(_lib.AbrError):
+        BatchedABREnv(bw, np.ones((4, 17)), np.ones((4, 17)), 8)                      # A > 16
+    with pytest.raises(_lib.AbrError):
+        BatchedABREnv(bw, sizes, bitrates, 8, trace_len=tl, trace_interval=ti, hist_k=65)
+
+
 def test_full_size_properties_65536x48():
     """BASELINE config 2 at full size: properties that need no oracle."""
     N, steps = 65536, 48
