@@ -347,6 +347,44 @@ def test_edge_shapes_empty_batch_single_chunk_video_and_widest_ladder():
         BatchedABREnv(bw, sizes, bitrates, 8, trace_len=tl, trace_interval=ti, hist_k=65)
 
 
+def test_calls_are_cuda_graph_capturable():
+    """Device-pointer entry points never synchronise or allocate, so reset + fused episode + statistics can be
+    captured into a CUDA graph and replayed with identical results."""
+    import ctypes as C
+    N, steps = 4096, 24
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=16, T=128)
+    tid, off = synth.make_sessions(N, 16, 128, group=64)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    tid_d, off_d = torch.from_numpy(tid).cuda(), torch.from_numpy(off).cuda()
+    out = {k: torch.empty(steps, N, dtype=torch.float64, device="cuda") for k in
+           ("delay", "sleep", "buffer", "rebuffer", "reward")}
+    out["end_of_video"] = torch.empty(steps, N, dtype=torch.uint8, device="cuda")
+    stats = torch.empty(8, dtype=torch.float64, device="cuda")
+
+    def one():
+        env.reset(tid_d, off_d)
+        env.rollout("bba", steps, out=out)
+        _lib.check(env._lib.abr_stats_partial(env._h, C.c_void_p(stats.data_ptr()),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    one()
+    torch.cuda.synchronize()
+    ref_reward, ref_stats = out["reward"].clone(), stats.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        one()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        one()
+    out["reward"].zero_()
+    stats.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["reward"], ref_reward) and torch.equal(stats, ref_stats)
+
+
 def test_full_size_properties_65536x48():
     """BASELINE config 2 at full size: properties that need no oracle."""
     N, steps = 65536, 48
