@@ -10,16 +10,17 @@ import os
 
 from . import _build
 
-NUM_ACC = 8
-NUM_STATS = 8
+NUM_ACC = 10
+NUM_STATS = 10
 POLICY_FIXED, POLICY_RANDOM, POLICY_BBA = 0, 1, 2
 MPC_REF, MPC_ROBUST = 0, 1
 MPC_TRUNCATE, MPC_EMPTY_DEFAULT = 1, 2
-ACC_NAMES = ("reward", "rebuffer", "utility", "smooth", "sleep", "delay", "steps", "episodes")
+ACC_NAMES = ("reward", "rebuffer", "utility", "smooth", "sleep", "delay", "steps", "episodes", "startup", "latency")
 FIELDS = dict(seg=(0, "int32"), chunk=(1, "int32"), last_q=(2, "int32"), trace_id=(3, "int32"),
               hist_len=(4, "int32"), done=(5, "uint8"), err_len=(6, "int32"), tau=(10, "float64"),
               buffer=(11, "float64"), bw_hist=(12, "float64"), last_pred=(13, "float64"),
-              err_ring=(14, "float64"), acc=(15, "float64"), sizes=(20, "float64"), utility=(21, "float64"),
+              err_ring=(14, "float64"), acc=(15, "float64"), t_now=(16, "float64"), play_time=(17, "float64"),
+              started=(7, "uint8"), sizes=(20, "float64"), utility=(21, "float64"),
               trace_bw=(22, "float64"))
 
 
@@ -32,15 +33,16 @@ class AbrError(RuntimeError):
 class AbrParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "chunk_length", "max_buffer", "rtt", "payload", "sleep_quantum", "rebuf_penalty",
-        "smooth_penalty", "utility_scale", "bba_reservoir", "bba_cushion")] + [
+        "smooth_penalty", "utility_scale", "bba_reservoir", "bba_cushion", "start_up_length",
+        "startup_penalty", "latency_penalty")] + [
         (n, C.c_int32) for n in ("utility_mode", "default_quality", "auto_reset", "hist_k",
-                                 "track_history", "track_acc", "reserved1", "reserved2")]
+                                 "track_history", "track_acc", "live", "reserved2")]
 
 
 # every symbol include/abr_b200.h declares (tests check that the .so exports all of them)
 SYMBOLS = ("abr_version", "abr_last_error", "abr_launch_count", "abr_device_info", "abr_params_default",
            "abr_env_create", "abr_env_destroy", "abr_env_num_sessions", "abr_env_reset", "abr_env_reset_host",
-           "abr_env_step", "abr_env_rollout_fused", "abr_env_mpc_decide", "abr_stats_partial", "abr_env_state_ptr",
+           "abr_env_step", "abr_env_step_live", "abr_env_qoe_cost", "abr_env_rollout_fused", "abr_env_mpc_decide", "abr_stats_partial", "abr_env_state_ptr",
            "abr_env_error_count", "abr_env_run_host", "abr_mpc_decide", "abr_mpc_decide_host", "abr_mpc_score_host",
            "abr_fp64_probe")
 

@@ -90,8 +90,9 @@ void abr_params_default(AbrParams* p) {
     p->chunk_length = 4.0; p->max_buffer = 60.0; p->rtt = 0.08; p->payload = 0.95; p->sleep_quantum = 0.5;
     p->rebuf_penalty = 4.3; p->smooth_penalty = 1.0; p->utility_scale = 0.001;
     p->bba_reservoir = 5.0; p->bba_cushion = 10.0;
+    p->start_up_length = 0.0; p->startup_penalty = 0.0; p->latency_penalty = 0.0;
     p->utility_mode = 0; p->default_quality = 1; p->auto_reset = 1; p->hist_k = 5;
-    p->track_history = 0; p->track_acc = 0;
+    p->track_history = 0; p->track_acc = 0; p->live = 0;
 }
 
 static int check_params(const AbrParams* p, int A) {
@@ -105,6 +106,10 @@ static int check_params(const AbrParams* p, int A) {
     if (p->default_quality >= A) return fail(ABR_ERR_RANGE, "default_quality %d out of range for A=%d", p->default_quality, A);
     if (p->utility_mode != 0 && p->utility_mode != 1) return fail(ABR_ERR_INVALID, "utility_mode must be 0 or 1");
     if (!(p->bba_cushion > 0.0)) return fail(ABR_ERR_INVALID, "bba_cushion must be > 0");
+    if (p->live && !(p->start_up_length <= p->max_buffer))
+        return fail(ABR_ERR_INVALID, "live mode needs start_up_length <= max_buffer (the start-up phase could never end)");
+    if (!std::isfinite(p->start_up_length) || !std::isfinite(p->startup_penalty) || !std::isfinite(p->latency_penalty))
+        return fail(ABR_ERR_INVALID, "start_up_length / startup_penalty / latency_penalty must be finite");
     return ABR_OK;
 }
 
@@ -199,6 +204,7 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     CUDA_TRY(e->alloc(&v.seg, cap)); CUDA_TRY(e->alloc(&v.chunk, cap)); CUDA_TRY(e->alloc(&v.last_q, cap));
     CUDA_TRY(e->alloc(&v.trace_id, cap)); CUDA_TRY(e->alloc(&v.hist_len, cap)); CUDA_TRY(e->alloc(&v.err_len, cap));
     CUDA_TRY(e->alloc(&v.done, cap)); CUDA_TRY(e->alloc(&v.tau, cap)); CUDA_TRY(e->alloc(&v.buffer, cap));
+    CUDA_TRY(e->alloc(&v.started, cap)); CUDA_TRY(e->alloc(&v.t_now, cap)); CUDA_TRY(e->alloc(&v.play_time, cap));
     CUDA_TRY(e->alloc(&v.bw_hist, cap * v.K)); CUDA_TRY(e->alloc(&v.last_pred, cap));
     CUDA_TRY(e->alloc(&v.err_ring, cap * v.K)); CUDA_TRY(e->alloc(&v.acc, cap * ABR_NUM_ACC));
     CUDA_TRY(e->alloc(&v.errors, 1));
@@ -243,16 +249,29 @@ int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_s
     return abr_env_reset(env, env->d_trace_id, h_start_offset ? env->d_offset : nullptr, n_sessions, session_base, stream);
 }
 
-int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
-                 double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_end_of_video, double* d_throughput,
-                 void* stream) {
+int abr_env_step_live(AbrEnv* env, const int32_t* d_action, const double* d_speed, double* d_delay, double* d_sleep,
+                      double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency, double* d_next_sizes,
+                      uint8_t* d_end_of_video, double* d_throughput, void* stream) {
     if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
     if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
     if (env->v.n == 0) return ABR_OK;
     if (!d_action) return fail(ABR_ERR_INVALID, "action is NULL");
     env->fresh_partials = 0;
-    CUDA_TRY(launch_step(env->v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_next_sizes, d_end_of_video,
-                         d_throughput, (cudaStream_t)stream));
+    CUDA_TRY(launch_step(env->v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency,
+                         d_next_sizes, d_end_of_video, d_throughput, (cudaStream_t)stream));
+    return ABR_OK;
+}
+
+int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
+                 double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_end_of_video, double* d_throughput,
+                 void* stream) {
+    return abr_env_step_live(env, d_action, nullptr, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, nullptr,
+                             d_next_sizes, d_end_of_video, d_throughput, stream);
+}
+
+int abr_env_qoe_cost(AbrEnv* env, double* d_out, void* stream) {
+    if (!env || !d_out) return fail(ABR_ERR_INVALID, "env or out is NULL");
+    CUDA_TRY(launch_qoe_cost(env->v, d_out, (cudaStream_t)stream));
     return ABR_OK;
 }
 
@@ -265,6 +284,7 @@ int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, con
     if (steps < 0) return fail(ABR_ERR_RANGE, "steps must be >= 0");
     if (policy < ABR_POLICY_FIXED || policy > ABR_POLICY_BBA) return fail(ABR_ERR_INVALID, "unknown policy %d", policy);
     if (policy == ABR_POLICY_FIXED && !d_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs d_actions_in");
+    if (env->v.p.live) return fail(ABR_ERR_STATE, "the fused episode does not implement live mode (SPEC 7): use abr_env_step_live");
     CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_delay, d_sleep, d_buffer, d_rebuf, d_reward,
                             d_end_of_video, d_actions_out, env->d_stats_partials, (cudaStream_t)stream));
     env->fresh_partials = steps > 0 ? rollout_num_blocks(env->v.n) : 0;
@@ -327,6 +347,9 @@ int abr_env_state_ptr(AbrEnv* env, int field, void** d_ptr) {
         case ABR_F_LAST_PRED: *d_ptr = v.last_pred; break;
         case ABR_F_ERR_RING: *d_ptr = v.err_ring; break;
         case ABR_F_ACC: *d_ptr = v.acc; break;
+        case ABR_F_T_NOW: *d_ptr = v.t_now; break;
+        case ABR_F_PLAY_TIME: *d_ptr = v.play_time; break;
+        case ABR_F_STARTED: *d_ptr = v.started; break;
         case ABR_F_SIZES: *d_ptr = (void*)v.sizes; break;
         case ABR_F_UTILITY: *d_ptr = (void*)v.util; break;
         case ABR_F_TRACE_BW: *d_ptr = (void*)v.trace_bw; break;

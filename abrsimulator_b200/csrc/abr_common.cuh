@@ -75,7 +75,8 @@ struct EnvView {
     const double* __restrict__ util;            // [V][A]
     // SoA session state, capacity = cap
     int32_t* seg; int32_t* chunk; int32_t* last_q; int32_t* trace_id; int32_t* hist_len; int32_t* err_len;
-    uint8_t* done;
+    uint8_t* done; uint8_t* started;
+    double* t_now; double* play_time;            // live mode (SPEC §7)
     double* tau; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
     unsigned long long* errors;                 // device counter of flagged sessions
     int n_traces, T_max, T_rate, V, A, K, cap, n;   // T_rate = max(T_max, longest period): row length of trace_rate; n = active sessions
@@ -86,9 +87,9 @@ struct EnvView {
 // launchers implemented in abr_step.cu / abr_mpc.cu (C++ linkage, internal)
 cudaError_t launch_trace_table(const EnvView& v, double* d_rate, cudaStream_t st);
 cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st);
-cudaError_t launch_step(const EnvView& v, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
-                        double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_eov, double* d_thr,
-                        cudaStream_t st);
+cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
+                        double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,
+                        double* d_next_sizes, uint8_t* d_eov, double* d_thr, cudaStream_t st);
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
                            uint8_t* d_eov, int32_t* d_actions_out, double* d_block_partials, cudaStream_t st);

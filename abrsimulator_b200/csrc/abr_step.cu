@@ -38,10 +38,13 @@ struct Sess {
     double I, tau, buffer;
     int T, seg, chunk, last_q, hist_len;
     bool done;
+    // live mode (SPEC §7)
+    double t_now, play_time, speed;
+    bool started;
 };
 
 struct StepRes {
-    double delay, sleep, buffer, rebuf, reward, thr, u, smooth;
+    double delay, sleep, buffer, rebuf, reward, thr, u, smooth, latency, startup;
     bool eov, inert, walk_error, reset_mpc;
 };
 
@@ -74,12 +77,43 @@ __device__ __forceinline__ void load_rates(const double* __restrict__ row, int i
     }
 }
 
+// SPEC §3.3: move the trace position forward by dt seconds without downloading.
+__device__ __forceinline__ void advance_trace(int& seg, double& tau, const double dt, const double I, const int T) {
+    // x / d == x * (1/d) bit for bit when d is a power of two (barring over/underflow, excluded by the range check in
+    // pow2_inverse), which saves the division for the usual 0.5 s / 1 s intervals
+    const double x = dadd(tau, dt);
+    const double inv_i = pow2_inverse(I);
+    const double n = floor(inv_i != 0.0 ? dmul(x, inv_i) : ddiv(x, I));
+    tau = dsub(x, dmul(n, I));
+    if (n < 2147480000.0) {   // 32-bit fast path; the modulo only runs when the position wraps
+        const unsigned tot = (unsigned)seg + (unsigned)(int)n;
+        seg = tot >= (unsigned)T ? (int)(tot % (unsigned)T) : (int)tot;
+    } else {
+        seg = (int)(((long long)seg + (long long)n) % (long long)T);
+    }
+    if (tau < 0.0) tau = 0.0;
+    if (tau >= I) { tau = 0.0; seg = (seg + 1 == T) ? 0 : seg + 1; }
+}
+
+// SPEC §7 play(dt): playback during an interval; returns the stall time.
+__device__ __forceinline__ double live_play(Sess& s, double& buffer, double& startup, const double dt) {
+    if (!s.started) { startup = dadd(startup, dt); return 0.0; }
+    const double need = dmul(s.speed, dt);
+    double drained, stall;
+    if (buffer >= need) { drained = need; stall = 0.0; }
+    else { drained = buffer; stall = dsub(dt, s.speed == 1.0 ? buffer : ddiv(buffer, s.speed)); }
+    buffer = dsub(buffer, drained);
+    s.play_time = dadd(s.play_time, drained);
+    return stall;
+}
+
 // SPEC §3 for one session held in registers.  `q` must already be a valid index.
 // SMEM: s.rate points at the block's shared-memory copy of the trace row (else at the global table).
 // PREFETCH: fetch the following block while the current one is consumed (pays off when few warps are resident,
 // i.e. the fused episode on the global path; the per-step kernel hides the latency with occupancy instead).
 // FAST: auto_reset is on (a session is never inert) — drops the done/inert bookkeeping.
-template <bool SMEM, bool PREFETCH, bool FAST = false>
+// LIVE: live-streaming semantics of SPEC §7 (pause gate before the download, start-up latch, playback speed).
+template <bool SMEM, bool PREFETCH, bool FAST = false, bool LIVE = false>
 __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, StepRes& r, const bool want_thr) {
     const AbrParams& p = v.p;
     r.walk_error = false;
@@ -105,6 +139,18 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     // happens after the loop has reconverged.
     double sent = 0.0, tau = s.tau;
     int seg = s.seg;                       // < T; the row padding makes seg + 2*kWalkBlock readable
+    double live_buffer = s.buffer, live_rebuf = 0.0, live_idle = 0.0, live_startup = 0.0;
+    if (LIVE) {   // 7.1 pause gate (Simulator.py:143-145): live edge, then room in the buffer
+        const double w1 = max0(dsub(dmul((double)(s.chunk + 1), p.chunk_length), s.t_now));
+        live_rebuf = live_play(s, live_buffer, live_startup, w1);
+        const double w2 = (s.started && live_buffer > p.max_buffer)
+                              ? (s.speed == 1.0 ? dsub(live_buffer, p.max_buffer)
+                                                : ddiv(dsub(live_buffer, p.max_buffer), s.speed))
+                              : 0.0;
+        live_rebuf = dadd(live_rebuf, live_play(s, live_buffer, live_startup, w2));
+        live_idle = dadd(w1, w2);
+        if (live_idle > 0.0) advance_trace(seg, tau, live_idle, s.I, s.T);
+    }
     int guard = (1 << 20) / kWalkBlock;    // safety net only: every bandwidth is > 0, so the walk terminates
     int k = 0;                             // segments left behind
     const double* __restrict__ row = s.rate;
@@ -117,7 +163,8 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
 #pragma unroll
         for (int u = 0; u < kWalkBlock; ++u) cur[u] = head[u + 1];
     }
-    const double room0 = dsub(s.I, tau);
+    const double tau0 = tau;
+    const double room0 = dsub(s.I, tau0);
     double s2 = dadd(sent, dmul(rate, room0));
     const bool multi = !(s2 >= size);      // the current segment does not finish the chunk
     double c[kWalkBlock];
@@ -180,34 +227,34 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     }
     delay = dadd(delay, p.rtt);
     r.thr = want_thr ? ddiv(size, delay) : 0.0;
-    // 3.2 buffer drain / rebuffer
-    const double rebuf = max0(dsub(delay, s.buffer));
-    double buffer = dadd(max0(dsub(s.buffer, delay)), p.chunk_length);
-    // 3.3 sleep cap
-    double sleep = 0.0;
-    if (buffer > p.max_buffer) {
-        // x / d == x * (1/d) bit for bit when d is a power of two (barring over/underflow, excluded by the range
-        // check in pow2_inverse), which saves the two divisions of this path for the usual 0.5 s / 1 s settings
-        const double over = dsub(buffer, p.max_buffer);
-        const double inv_q = pow2_inverse(p.sleep_quantum);
-        sleep = dmul(ceil(inv_q != 0.0 ? dmul(over, inv_q) : ddiv(over, p.sleep_quantum)), p.sleep_quantum);
-        buffer = dsub(buffer, sleep);
-        const double x = dadd(tau, sleep);
-        const double inv_i = pow2_inverse(s.I);
-        const double n = floor(inv_i != 0.0 ? dmul(x, inv_i) : ddiv(x, s.I));
-        tau = dsub(x, dmul(n, s.I));
-        if (n < 2147480000.0) {   // 32-bit fast path; the modulo only runs when the position wraps
-            const unsigned tot = (unsigned)seg + (unsigned)(int)n;
-            seg = tot >= (unsigned)s.T ? (int)(tot % (unsigned)s.T) : (int)tot;
-        } else {
-            seg = (int)(((long long)seg + (long long)n) % (long long)s.T);
+    double rebuf, buffer, sleep = 0.0;
+    r.latency = 0.0;
+    r.startup = 0.0;
+    if (LIVE) {   // 7.2
+        rebuf = dadd(live_rebuf, live_play(s, live_buffer, live_startup, delay));
+        buffer = dadd(live_buffer, p.chunk_length);
+        s.t_now = dadd(dadd(s.t_now, live_idle), delay);
+        if (!s.started && buffer >= p.start_up_length) s.started = true;
+        r.latency = dsub(s.t_now, s.play_time);
+        r.startup = live_startup;
+        sleep = live_idle;
+    } else {
+        // 3.2 buffer drain / rebuffer
+        rebuf = max0(dsub(delay, s.buffer));
+        buffer = dadd(max0(dsub(s.buffer, delay)), p.chunk_length);
+        // 3.3 sleep cap
+        if (buffer > p.max_buffer) {
+            const double over = dsub(buffer, p.max_buffer);
+            const double inv_q = pow2_inverse(p.sleep_quantum);
+            sleep = dmul(ceil(inv_q != 0.0 ? dmul(over, inv_q) : ddiv(over, p.sleep_quantum)), p.sleep_quantum);
+            buffer = dsub(buffer, sleep);
+            advance_trace(seg, tau, sleep, s.I, s.T);
         }
-        if (tau < 0.0) tau = 0.0;
-        if (tau >= s.I) { tau = 0.0; seg = (seg + 1 == s.T) ? 0 : seg + 1; }
     }
     // 3.4 reward
     const double smooth = (s.last_q >= 0) ? fabs(dsub(u, u_prev)) : 0.0;
     r.reward = dsub(dsub(u, dmul(p.rebuf_penalty, rebuf)), dmul(p.smooth_penalty, smooth));
+    if (LIVE) r.reward = dsub(r.reward, dmul(p.latency_penalty, r.latency));
     r.delay = delay; r.sleep = sleep; r.buffer = buffer; r.rebuf = rebuf; r.u = u; r.smooth = smooth;
     // 3.5 advance
     s.hist_len += 1;
@@ -220,6 +267,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     if (r.eov) {
         if (FAST || p.auto_reset) {
             s.chunk = 0; s.buffer = 0.0; s.last_q = p.default_quality; s.hist_len = 0;
+            if (LIVE) { s.t_now = 0.0; s.play_time = 0.0; s.started = p.start_up_length <= 0.0; }
             r.reset_mpc = true;
         } else {
             s.done = true;
@@ -294,6 +342,7 @@ abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* 
     if (seg < 0 || seg >= T) { atomicAdd(v.errors, 1ull); seg = 0; }
     v.trace_id[i] = tr; v.seg[i] = seg; v.tau[i] = tau; v.buffer[i] = 0.0; v.chunk[i] = 0;
     v.last_q[i] = v.p.default_quality; v.done[i] = 0; v.hist_len[i] = 0; v.last_pred[i] = 0.0; v.err_len[i] = 0;
+    v.t_now[i] = 0.0; v.play_time[i] = 0.0; v.started[i] = v.p.start_up_length <= 0.0 ? 1 : 0;
 #pragma unroll
     for (int j = 0; j < ABR_NUM_ACC; ++j) v.acc[(size_t)j * v.cap + i] = 0.0;
 }
@@ -302,20 +351,27 @@ abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* 
 // FAST: the five f64 outputs and end_of_video requested, no throughput history / accumulators, auto_reset on —
 // compiled without the null checks and the inert/history/accumulator bookkeeping (next_sizes and throughput stay
 // optional in both variants).
-template <bool FAST>
+template <bool FAST, bool LIVE>
 __global__ void __launch_bounds__(kStepBlock, 4)
-abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restrict__ o_delay,
-                double* __restrict__ o_sleep, double* __restrict__ o_buffer, double* __restrict__ o_rebuf,
-                double* __restrict__ o_reward, double* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov,
-                double* __restrict__ o_thr) {
+abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __restrict__ speed,
+                double* __restrict__ o_delay, double* __restrict__ o_sleep, double* __restrict__ o_buffer,
+                double* __restrict__ o_rebuf, double* __restrict__ o_reward, double* __restrict__ o_latency,
+                double* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov, double* __restrict__ o_thr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.n) return;
     Sess s;
     load_sess(v, i, s);
+    if (LIVE) {
+        s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0;
+        s.speed = speed ? speed[i] : 1.0;
+    }
     int q = action[i];
-    if (q < 0 || q >= v.A) { atomicAdd(v.errors, 1ull); q = q < 0 ? 0 : v.A - 1; }
+    bool bad = q < 0 || q >= v.A;
+    if (bad) q = q < 0 ? 0 : v.A - 1;
+    if (LIVE && !(s.speed > 0.0)) { bad = true; s.speed = 1.0; }
+    if (bad) atomicAdd(v.errors, 1ull);
     StepRes r;
-    step_core<false, false, FAST>(v, s, q, r, (!FAST && v.p.track_history) || o_thr != nullptr);
+    step_core<false, false, FAST, LIVE>(v, s, q, r, (!FAST && v.p.track_history) || o_thr != nullptr);
     if (r.walk_error) atomicAdd(v.errors, 1ull);
     if (FAST) {
         v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
@@ -325,6 +381,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restric
     } else {
         if (!r.inert) {
             v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
+            if (LIVE) { v.t_now[i] = s.t_now; v.play_time[i] = s.play_time; v.started[i] = s.started ? 1 : 0; }
             if (v.p.track_history) {
                 // ring slot of this sample = (hist_len before the step) mod K; after an auto-reset hist_len is 0
                 const int prev_len = r.reset_mpc ? 0 : s.hist_len - 1;
@@ -341,6 +398,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restric
                 a[5 * c] = dadd(a[5 * c], r.delay);
                 a[6 * c] = dadd(a[6 * c], 1.0);
                 if (r.eov) a[7 * c] = dadd(a[7 * c], 1.0);
+                if (LIVE) { a[8 * c] = dadd(a[8 * c], r.startup); a[9 * c] = dadd(a[9 * c], r.latency); }
             }
         }
         if (o_delay) __stcs(o_delay + i, r.delay);
@@ -350,6 +408,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, double* __restric
         if (o_reward) __stcs(o_reward + i, r.reward);
         if (o_eov) o_eov[i] = r.eov ? 1 : 0;
     }
+    if (o_latency) __stcs(o_latency + i, r.latency);
     if (o_thr) __stcs(o_thr + i, r.thr);
     if (o_next_sizes) {
         const int A = v.A;
@@ -416,7 +475,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     // accumulator read-modify-write: all eight loads first (one memory round trip instead of eight dependent ones)
     double* a = v.acc + i;
     const size_t c = v.cap;
-    const double add[ABR_NUM_ACC] = {a_rew, a_reb, a_u, a_sm, a_sl, a_dl, a_steps, a_eps};
+    const double add[ABR_NUM_ACC] = {a_rew, a_reb, a_u, a_sm, a_sl, a_dl, a_steps, a_eps, 0.0, 0.0};   // not live
     double old[ABR_NUM_ACC];
 #pragma unroll
     for (int j = 0; j < ABR_NUM_ACC; ++j) old[j] = __ldcg(a + j * c);
@@ -583,13 +642,20 @@ abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __
 }
 
 // Per-session QoE cost of Simulator.calculate_qoe (Simulator.py:83-86) from the accumulators:
-// rebuffer_weight * sum(rebuffer) + variance_weight * sum(|delta utility|)  (start-up and latency terms are 0).
+// rebuffer_weight * sum(rebuffer) + variance_weight * sum(|delta utility|), plus in live mode
+// startup_weight * start-up time + latency_weight * mean latency.
 __global__ void __launch_bounds__(kStepBlock)
 abr_qoe_cost_kernel(EnvView v, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.n) return;
-    out[i] = dadd(dmul(v.p.rebuf_penalty, v.acc[(size_t)ABR_ACC_REBUF * v.cap + i]),
-                  dmul(v.p.smooth_penalty, v.acc[(size_t)ABR_ACC_SMOOTH * v.cap + i]));
+    double c = dadd(dmul(v.p.rebuf_penalty, v.acc[(size_t)ABR_ACC_REBUF * v.cap + i]),
+                    dmul(v.p.smooth_penalty, v.acc[(size_t)ABR_ACC_SMOOTH * v.cap + i]));
+    if (v.p.live) {   // + sw*start_up_time + lw*average_latency (Simulator.py:85-86)
+        const double steps = v.acc[(size_t)ABR_ACC_STEPS * v.cap + i];
+        c = dadd(c, dmul(v.p.startup_penalty, v.acc[(size_t)ABR_ACC_STARTUP * v.cap + i]));
+        c = dadd(c, dmul(v.p.latency_penalty, steps > 0.0 ? ddiv(v.acc[(size_t)ABR_ACC_LATENCY * v.cap + i], steps) : 0.0));
+    }
+    out[i] = c;
 }
 
 }  // namespace
@@ -609,19 +675,19 @@ cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const doub
     return cudaGetLastError();
 }
 
-cudaError_t launch_step(const EnvView& v, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
-                        double* d_rebuf, double* d_reward, double* d_next_sizes, uint8_t* d_eov, double* d_thr,
-                        cudaStream_t st) {
+cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
+                        double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,
+                        double* d_next_sizes, uint8_t* d_eov, double* d_thr, cudaStream_t st) {
     if (v.n == 0) return cudaSuccess;
-    const bool fast = d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && v.p.track_history == 0 &&
-                      v.p.track_acc == 0 && v.p.auto_reset != 0;
+    const bool live = v.p.live != 0;
+    const bool fast = !live && d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov &&
+                      v.p.track_history == 0 && v.p.track_acc == 0 && v.p.auto_reset != 0;
     const unsigned grid = (v.n + kStepBlock - 1) / kStepBlock;
-    if (fast)
-        abr_step_kernel<true><<<grid, kStepBlock, 0, st>>>(v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward,
-                                                           d_next_sizes, d_eov, d_thr);
-    else
-        abr_step_kernel<false><<<grid, kStepBlock, 0, st>>>(v, d_action, d_delay, d_sleep, d_buffer, d_rebuf, d_reward,
-                                                            d_next_sizes, d_eov, d_thr);
+#define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr
+    if (live) abr_step_kernel<false, true><<<grid, kStepBlock, 0, st>>>(ABR_STEP_ARGS);
+    else if (fast) abr_step_kernel<true, false><<<grid, kStepBlock, 0, st>>>(ABR_STEP_ARGS);
+    else abr_step_kernel<false, false><<<grid, kStepBlock, 0, st>>>(ABR_STEP_ARGS);
+#undef ABR_STEP_ARGS
     count_launch();
     return cudaGetLastError();
 }

@@ -19,7 +19,8 @@ from ._lib import (AbrError, MPC_REF, MPC_ROBUST, NUM_ACC, NUM_STATS, POLICY_BBA
                    POLICY_RANDOM)
 from .datamodel import MPD, NetworkInfo, QOEMetric, pack_traces
 
-StepResult = namedtuple("StepResult", "delay sleep buffer rebuffer reward next_sizes end_of_video throughput")
+StepResult = namedtuple("StepResult", "delay sleep buffer rebuffer reward next_sizes end_of_video throughput latency",
+                        defaults=(None,))
 
 _POLICIES = {"fixed": POLICY_FIXED, "random": POLICY_RANDOM, "bba": POLICY_BBA, "buffer": POLICY_BBA}
 _MODES = {"reference": MPC_REF, "ref": MPC_REF, "robust": MPC_ROBUST}
@@ -150,21 +151,36 @@ class BatchedABREnv:
         self.session_base = int(session_base)
 
     # -- SPEC §3 --
-    def step(self, action, want_next_sizes=True, want_throughput=False, out=None) -> StepResult:
-        """One chunk step for every session.  ``action``: int32 [N] on the device (or array-like)."""
+    def step(self, action, want_next_sizes=True, want_throughput=False, out=None, speed=None,
+             want_latency=None) -> StepResult:
+        """One chunk step for every session.  ``action``: int32 [N] on the device (or array-like).
+        Live mode (``live=1``, SPEC §7): ``speed`` is the playback speed per session (default 1.0), the result
+        carries ``latency`` and ``sleep`` is the idle time before the download."""
         a = self._dev(action, torch.int32)
         if a.numel() != self.n:
             raise ValueError(f"action has {a.numel()} entries for {self.n} sessions")
         n = self.n
+        live = bool(self.params.live)
+        v = None
+        if speed is not None:
+            if not live:
+                raise ValueError("speed is a live-mode action (create the environment with live=1)")
+            v = self._dev(speed, torch.float64)
+            if v.numel() != n:
+                raise ValueError("speed must have one entry per session")
+        if want_latency is None:
+            want_latency = live
         if out is None:
             out = StepResult(self._empty(n), self._empty(n), self._empty(n), self._empty(n), self._empty(n),
                              self._empty(n, self.A) if want_next_sizes else None,
                              self._empty(n, dtype=torch.uint8),
-                             self._empty(n) if want_throughput else None)
+                             self._empty(n) if want_throughput else None,
+                             self._empty(n) if want_latency else None)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.abr_env_step(self._h, _ptr(a), _ptr(out.delay), _ptr(out.sleep), _ptr(out.buffer),
-                                              _ptr(out.rebuffer), _ptr(out.reward), _ptr(out.next_sizes),
-                                              _ptr(out.end_of_video), _ptr(out.throughput), _stream()))
+            _lib.check(self._lib.abr_env_step_live(
+                self._h, _ptr(a), _ptr(v), _ptr(out.delay), _ptr(out.sleep), _ptr(out.buffer), _ptr(out.rebuffer),
+                _ptr(out.reward), _ptr(out.latency), _ptr(out.next_sizes), _ptr(out.end_of_video),
+                _ptr(out.throughput), _stream()))
         return out
 
     # -- SPEC §3+§4 --
@@ -208,12 +224,12 @@ class BatchedABREnv:
             self.mpc_decide(horizon, mode, out=act)
             with torch.cuda.device(self.device):
                 _lib.check(self._lib.abr_env_step(self._h, _ptr(act), None, None, None, None, None, None, None, None,
-                                                  _stream()))
+                                                  _stream()))   # live mode: speed 1.0
         return act
 
     # -- SPEC §6 --
     def stats(self) -> torch.Tensor:
-        """[Σreward, Σrebuffer, Σutility, Σsmooth, Σsleep, Σdelay, steps, episodes] over this env's sessions."""
+        """[Σreward, Σrebuffer, Σutility, Σsmooth, Σsleep, Σdelay, steps, episodes, Σstartup, Σlatency]."""
         out = torch.empty(NUM_STATS, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.abr_stats_partial(self._h, _ptr(out), _stream()))
@@ -243,8 +259,16 @@ class BatchedABREnv:
         return t[:self.n]
 
     def session_acc(self) -> torch.Tensor:
-        """[8, N] per-session sums (rows: reward, rebuffer, utility, smooth, sleep, delay, steps, episodes)."""
+        """[10, N] per-session sums (rows: reward, rebuffer, utility, smooth, sleep, delay, steps, episodes,
+        startup, latency)."""
         return self.state("acc")
+
+    def qoe_cost(self) -> torch.Tensor:
+        """Per-session cost of ``Simulator.calculate_qoe`` (Simulator.py:83-86) from the accumulators, on the device."""
+        out = self._empty(self.n)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.abr_env_qoe_cost(self._h, _ptr(out), _stream()))
+        return out
 
     def error_count(self) -> int:
         out = C.c_longlong(0)
@@ -256,7 +280,7 @@ class BatchedABREnv:
     def run_host(self, policy, steps, trace_id, start_offset=None, seed=0, session_base=0, actions=None,
                  want_acc=True, want_stats=True, want_reward_traj=False, want_qoe_cost=False, out=None):
         """Reset + fused episode + statistics with HOST (numpy) inputs and outputs.
-        Returns dict(acc=[8,N], stats=[8], reward=[steps,N], qoe_cost=[N])."""
+        Returns dict(acc=[NUM_ACC,N], stats=[NUM_STATS], reward=[steps,N], qoe_cost=[N])."""
         pid = _policy_id(policy)
         tid = np.ascontiguousarray(trace_id, dtype=np.int32)
         n = tid.size

@@ -3,8 +3,10 @@
 ``Simulator(AbrController, SpeedController)``, ``set_qoe_metric``, ``set_network_info``, ``set_mpd`` and ``run()``
 keep their reference signatures.  ``run()`` plays one session (or ``run_batch`` many) at chunk granularity
 (SPEC.md §3) and returns the QoE *cost* of ``calculate_qoe`` (``Simulator.py:79-86``):
-``rw·rebuffer_time + vw·Σ|Δbitrate| + sw·start_up_time + lw·average_latency`` — in this version start-up time and
-latency are not modelled and contribute 0.
+``rw·rebuffer_time + vw·Σ|Δbitrate| + sw·start_up_time + lw·average_latency``.  When the MPD carries a
+``start_up_length`` (the reference's 5-argument ``MPD`` / ``set_mpd``) the session runs in live mode (SPEC.md §7:
+live-edge availability gate, start-up latch, playback speed from the speed controller, latency); with
+``start_up_length=None`` it is the on-demand environment of SPEC.md §3 and the last two terms are 0.
 
 Controllers
 -----------
@@ -21,7 +23,7 @@ import torch
 from .datamodel import MPD, NetworkInfo, QOEMetric, load_mpd_file, load_network_trace
 from .env import BatchedABREnv
 from .mpc import MPCBitrateController
-from ._lib import MPC_ROBUST
+from ._lib import ACC_NAMES, MPC_ROBUST
 
 
 class RandomPolicy:
@@ -45,7 +47,7 @@ class Simulator:
         self.mpd = None
         self.network_info = None
         self.abr_controller = AbrController
-        self.speed_controller = SpeedController      # playback-speed hook: not modelled yet (always 1x)
+        self.speed_controller = SpeedController      # get_next_speed() -> playback speed (live mode, Simulator.py:177)
         self.params = dict(params)
         self._env = None
         self.last_run = None
@@ -103,6 +105,9 @@ class Simulator:
         """One session over trace 0 from offset 0; returns the scalar QoE cost."""
         return float(self.run_batch(1)[0])
 
+    def _live(self):
+        return self.mpd is not None and self.mpd.start_up_length is not None and not self.params.get("force_vod", False)
+
     def run_batch(self, n_sessions, trace_id=None, start_offset=None, session_base=0):
         """``n_sessions`` independent sessions; returns a numpy vector of QoE costs (one per session)."""
         V = len(self.mpd.chunks)
@@ -110,6 +115,8 @@ class Simulator:
         tid = np.arange(n_sessions, dtype=np.int32) % n_traces if trace_id is None else np.asarray(trace_id, np.int32)
         ctrl = self.abr_controller
         q = self.qoe_metric
+        if self._live():
+            return self._run_live(n_sessions, tid, start_offset, session_base)
         if isinstance(ctrl, (RandomPolicy, BufferBasedPolicy, FixedPolicy)) or ctrl is None:
             extra = {}
             if isinstance(ctrl, BufferBasedPolicy):
@@ -119,8 +126,7 @@ class Simulator:
             out = env.run_host(policy, V, tid, start_offset, seed=getattr(ctrl, "seed", 0), session_base=session_base,
                                actions=getattr(ctrl, "actions", None), want_qoe_cost=True)
             acc = out["acc"]
-            self.last_run = dict(rebuffer=acc[1], smooth=acc[3], utility=acc[2], reward=acc[0], sleep=acc[4],
-                                 delay=acc[5])
+            self.last_run = dict(zip(ACC_NAMES, acc))
             return out["qoe_cost"]          # rw*rebuffer + vw*smooth, computed on the device
         elif isinstance(ctrl, MPCBitrateController):
             env = self._make_env(n_sessions, track_history=1, track_acc=1, **ctrl.extra_params)
@@ -128,25 +134,73 @@ class Simulator:
             env.mpc_episode(V, horizon=ctrl.horizon, mode="robust" if ctrl.mode == MPC_ROBUST else "reference")
             acc = env.session_acc().cpu().numpy()
         else:
-            acc = self._run_callback(n_sessions, tid, start_offset)
-        self.last_run = dict(rebuffer=acc[1], smooth=acc[3], utility=acc[2], reward=acc[0], sleep=acc[4], delay=acc[5])
+            acc = self._run_callback(self._make_env(n_sessions, track_acc=1), n_sessions, tid, start_offset)
+        self.last_run = dict(zip(ACC_NAMES, acc))
         return q.rebuffer_weight * acc[1] + q.variance_weight * acc[3]
 
-    def _run_callback(self, n_sessions, tid, start_offset):
-        """Generic controller protocol: one ``get_next_bitrate`` call per session and chunk (Simulator.py:155)."""
+    def _run_live(self, n_sessions, tid, start_offset, session_base):
+        """Live mode (SPEC §7): per-step kernel, one bitrate and one playback-speed decision per chunk."""
+        q = self.qoe_metric
+        ctrl = self.abr_controller
+        extra = dict(live=1, start_up_length=float(self.mpd.start_up_length), startup_penalty=float(q.startup_weight),
+                     latency_penalty=float(getattr(q, "latency_weight", 0.0)), track_acc=1)
         V = len(self.mpd.chunks)
-        env = self._make_env(n_sessions, track_acc=1)
-        env.reset(tid, start_offset)
+        if isinstance(ctrl, MPCBitrateController):
+            env = self._make_env(n_sessions, track_history=1, **extra, **ctrl.extra_params)
+            env.reset(tid, start_offset, session_base)
+            mode = "robust" if ctrl.mode == MPC_ROBUST else "reference"
+            for _ in range(V):
+                act = env.mpc_decide(ctrl.horizon, mode)
+                env.step(act, want_next_sizes=False, speed=self._speeds(n_sessions))
+        else:
+            if isinstance(ctrl, BufferBasedPolicy):
+                extra.update(bba_reservoir=ctrl.reservoir, bba_cushion=ctrl.cushion)
+            env = self._make_env(n_sessions, **extra)
+            self._run_callback(env, n_sessions, tid, start_offset, session_base)
+        acc = env.session_acc().cpu().numpy()
+        self.last_run = dict(zip(ACC_NAMES, acc))
+        return env.qoe_cost().cpu().numpy()
+
+    def _speeds(self, n_sessions):
+        if self.speed_controller is None:
+            return None
+        return np.array([float(self.speed_controller.get_next_speed()) for _ in range(n_sessions)])
+
+    def _host_policy_actions(self, ctrl, k, n_sessions, buf, A, rng, session_base):
+        """Built-in policy markers evaluated on the host (used in live mode, where the fused episode does not apply)."""
+        if isinstance(ctrl, FixedPolicy):
+            return np.ascontiguousarray(ctrl.actions.reshape(len(self.mpd.chunks), -1)[k], dtype=np.int32)
+        if isinstance(ctrl, RandomPolicy):
+            return rng.integers(0, A, size=n_sessions).astype(np.int32)
+        r, c = ctrl.reservoir, ctrl.cushion          # BufferBasedPolicy / None
+        qv = np.floor((A - 1) * (buf - r) / c)
+        return np.clip(np.where(buf < r, 0, np.where(buf >= r + c, A - 1, qv)), 0, A - 1).astype(np.int32)
+
+    def _run_callback(self, env, n_sessions, tid, start_offset, session_base=0):
+        """One decision per session and chunk: the generic controller protocol ``get_next_bitrate(chunk_id,
+        previous_bitrates, previous_bandwidths, buffer_level)`` (Simulator.py:155), or a built-in policy marker."""
+        V = len(self.mpd.chunks)
+        A = env.A
+        ctrl = self.abr_controller if self.abr_controller is not None else BufferBasedPolicy()
+        marker = isinstance(ctrl, (RandomPolicy, BufferBasedPolicy, FixedPolicy))
+        live = bool(env.params.live)
+        env.reset(tid, start_offset, session_base)
         prev_q = [[] for _ in range(n_sessions)]
         prev_bw = [[] for _ in range(n_sessions)]
         buf = np.zeros(n_sessions)
+        rng = np.random.default_rng(getattr(ctrl, "seed", 0))
         for k in range(V):
-            acts = np.array([self.abr_controller.get_next_bitrate(k, prev_q[s], prev_bw[s], float(buf[s]))
-                             for s in range(n_sessions)], dtype=np.int32)
-            r = env.step(torch.from_numpy(acts), want_next_sizes=False, want_throughput=True)
+            if marker:
+                acts = self._host_policy_actions(ctrl, k, n_sessions, buf, A, rng, session_base)
+            else:
+                acts = np.array([ctrl.get_next_bitrate(k, prev_q[s], prev_bw[s], float(buf[s]))
+                                 for s in range(n_sessions)], dtype=np.int32)
+            r = env.step(torch.from_numpy(acts), want_next_sizes=False, want_throughput=True,
+                         speed=self._speeds(n_sessions) if live else None)
             buf = r.buffer.cpu().numpy()
-            thr = r.throughput.cpu().numpy()
-            for s in range(n_sessions):
-                prev_q[s].append(int(acts[s]))
-                prev_bw[s].append(float(thr[s]))
+            if not marker:
+                thr = r.throughput.cpu().numpy()
+                for s in range(n_sessions):
+                    prev_q[s].append(int(acts[s]))
+                    prev_bw[s].append(float(thr[s]))
         return env.session_acc().cpu().numpy()

@@ -310,7 +310,7 @@ def run_ours(args):
     tid_p = torch.from_numpy(tid_h).pin_memory().numpy()
     off_p = torch.from_numpy(off_h).pin_memory().numpy()
     qoe_p = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
-    st_p = torch.empty(8, dtype=torch.float64).pin_memory().numpy()
+    st_p = torch.empty(_lib.NUM_STATS, dtype=torch.float64).pin_memory().numpy()
     host_out = dict(qoe_cost=qoe_p, stats=st_p)
     for _ in range(3):
         env.run_host("random", V, tid_p, off_p, seed=SEED, session_base=base, want_acc=False, out=host_out)
@@ -322,7 +322,7 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = chunk_steps / e2e_s
     h2d = N * 4 + N * 8
-    d2h = N * 8 + 8 * 8
+    d2h = N * 8 + _lib.NUM_STATS * 8
 
     # ---- MPC decisions/s (configs[2] sharded: robust MPC, horizon 5, 7 776 sequences per decision) ----
     mpc = None

@@ -41,7 +41,8 @@ enum { ABR_MPC_TRUNCATE = 1,        /* mode 0: k+H > V truncates the horizon ins
 
 /* rows of the accumulator table / entries of the statistics vector (SPEC §6) */
 enum { ABR_ACC_REWARD = 0, ABR_ACC_REBUF = 1, ABR_ACC_UTILITY = 2, ABR_ACC_SMOOTH = 3, ABR_ACC_SLEEP = 4,
-       ABR_ACC_DELAY = 5, ABR_ACC_STEPS = 6, ABR_ACC_EPISODES = 7, ABR_NUM_ACC = 8, ABR_NUM_STATS = 8 };
+       ABR_ACC_DELAY = 5, ABR_ACC_STEPS = 6, ABR_ACC_EPISODES = 7, ABR_ACC_STARTUP = 8, ABR_ACC_LATENCY = 9,
+       ABR_NUM_ACC = 10, ABR_NUM_STATS = 10 };
 
 /* session-state fields exposed by abr_env_state_ptr (SPEC §1).  ABR_F_SEG is the segment index within the trace's
  * walk period: the trace length, or for traces shorter than 16 segments the smallest multiple of the length that
@@ -49,7 +50,7 @@ enum { ABR_ACC_REWARD = 0, ABR_ACC_REBUF = 1, ABR_ACC_UTILITY = 2, ABR_ACC_SMOOT
  * elements except BW_HIST / ERR_RING ([hist_k][max_sessions]) and ACC ([ABR_NUM_ACC][max_sessions]). */
 enum { ABR_F_SEG = 0, ABR_F_CHUNK = 1, ABR_F_LAST_Q = 2, ABR_F_TRACE_ID = 3, ABR_F_HIST_LEN = 4, ABR_F_DONE = 5,
        ABR_F_ERR_LEN = 6, ABR_F_TAU = 10, ABR_F_BUFFER = 11, ABR_F_BW_HIST = 12, ABR_F_LAST_PRED = 13,
-       ABR_F_ERR_RING = 14, ABR_F_ACC = 15, ABR_F_SIZES = 20, ABR_F_UTILITY = 21, ABR_F_TRACE_BW = 22 };
+       ABR_F_ERR_RING = 14, ABR_F_ACC = 15, ABR_F_T_NOW = 16, ABR_F_PLAY_TIME = 17, ABR_F_STARTED = 7, ABR_F_SIZES = 20, ABR_F_UTILITY = 21, ABR_F_TRACE_BW = 22 };
 
 /* Replaces the attribute bags MPD / QOEMetric (Simulator.py:11-24, mpc_test.py:18-29) plus the
  * north-star constants (SPEC §1). */
@@ -63,13 +64,17 @@ typedef struct AbrParams {
     double smooth_penalty;  /* QOEMetric.variance_weight, Simulator.py:22 */
     double utility_scale;   /* utility_mode 0: U = bitrate * utility_scale (1.0 = mpc.py:95-97 identity) */
     double bba_reservoir, bba_cushion;
+    double start_up_length; /* live mode: buffer that ends the start-up phase, MPD.start_up_length, Simulator.py:12,201-202 */
+    double startup_penalty; /* QOEMetric.startup_weight, Simulator.py:23 (session cost only) */
+    double latency_penalty; /* QOEMetric.latency_weight, Simulator.py:24 (per-step reward and session cost) */
     int32_t utility_mode;   /* 0 linear, 1 log(bitrate / top bitrate) (mpc.py:99-102) */
     int32_t default_quality;
     int32_t auto_reset;     /* 1: a session restarts at chunk 0 after its last chunk */
     int32_t hist_k;         /* capacity of the throughput-history ring (robust-MPC window) */
     int32_t track_history;  /* 1: abr_env_step / rollout push size/delay into the ring */
     int32_t track_acc;      /* 1: abr_env_step adds into the per-session accumulators */
-    int32_t reserved1, reserved2;
+    int32_t live;           /* 1: live-streaming semantics of SPEC §7 (per-step kernel only) */
+    int32_t reserved2;
 } AbrParams;
 
 typedef struct AbrEnv AbrEnv;
@@ -100,6 +105,12 @@ int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_s
 int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
                  double* d_rebuf, double* d_reward, double* d_next_sizes /*[N][A]*/, uint8_t* d_end_of_video,
                  double* d_throughput, void* stream);
+/* SPEC §7 (live = 1): like abr_env_step with the playback speed per session (d_speed, nullable = 1.0) as a second
+ * action (speed_controller.get_next_speed, Simulator.py:177) and the latency output; d_sleep receives the idle time
+ * before the download.  With live = 0 it behaves like abr_env_step and writes 0 latency. */
+int abr_env_step_live(AbrEnv* env, const int32_t* d_action, const double* d_speed, double* d_delay, double* d_sleep,
+                      double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,
+                      double* d_next_sizes /*[N][A]*/, uint8_t* d_end_of_video, double* d_throughput, void* stream);
 /* SPEC §3+§4: `steps` chunk steps in one launch, state in registers.  Trajectory outputs are
  * [steps][N] and nullable; per-session sums are added into the env accumulators (ABR_F_ACC). */
 int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
@@ -109,6 +120,9 @@ int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, con
  * never flags errors (implies ABR_MPC_TRUNCATE | ABR_MPC_EMPTY_DEFAULT). */
 int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, double* d_best_j /*nullable*/,
                        void* stream);
+/* Per-session QoE cost of Simulator.calculate_qoe (Simulator.py:83-86) from the accumulators into d_out[N]:
+ * rw*rebuffer + vw*smooth + sw*startup + lw*(latency/steps). */
+int abr_env_qoe_cost(AbrEnv* env, double* d_out, void* stream);
 /* SPEC §6: reduce the accumulators of the first n sessions into d_out[ABR_NUM_STATS]. */
 int abr_stats_partial(AbrEnv* env, double* d_out, void* stream);
 int abr_env_state_ptr(AbrEnv* env, int field, void** d_ptr);

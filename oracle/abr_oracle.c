@@ -20,7 +20,8 @@ struct OrcEnv {
     /* session state, SoA (SPEC §1) */
     int32_t *seg, *chunk, *last_q, *trace_id, *hist_len, *err_len;
     double *tau, *buffer, *bw_hist /* [N][K] ring */, *last_pred, *err_ring /* [N][K] */;
-    uint8_t* done;
+    double *t_now, *play_time;   /* live mode, SPEC §7 */
+    uint8_t *done, *started;
     int errors;
 };
 
@@ -73,6 +74,8 @@ OrcEnv* orc_env_create(const double* trace_bw, const int32_t* trace_len, const d
     e->tau = (double*)calloc(N, 8); e->buffer = (double*)calloc(N, 8); e->last_pred = (double*)calloc(N, 8);
     e->bw_hist = (double*)calloc((size_t)N * e->K, 8); e->err_ring = (double*)calloc((size_t)N * e->K, 8);
     e->done = (uint8_t*)calloc(N, 1);
+    e->started = (uint8_t*)calloc(N, 1);
+    e->t_now = (double*)calloc(N, 8); e->play_time = (double*)calloc(N, 8);
     return e;
 }
 
@@ -81,6 +84,7 @@ void orc_env_destroy(OrcEnv* e) {
     free(e->trace_bw); free(e->trace_len); free(e->trace_interval); free(e->sizes); free(e->bitrates); free(e->util);
     free(e->seg); free(e->chunk); free(e->last_q); free(e->trace_id); free(e->hist_len); free(e->err_len);
     free(e->tau); free(e->buffer); free(e->last_pred); free(e->bw_hist); free(e->err_ring); free(e->done);
+    free(e->started); free(e->t_now); free(e->play_time);
     free(e);
 }
 
@@ -89,7 +93,8 @@ const void* orc_env_field(OrcEnv* e, int f) {
         case 0: return e->seg; case 1: return e->chunk; case 2: return e->last_q; case 3: return e->trace_id;
         case 4: return e->hist_len; case 5: return e->done; case 6: return e->err_len;
         case 10: return e->tau; case 11: return e->buffer; case 12: return e->bw_hist; case 13: return e->last_pred;
-        case 14: return e->err_ring; case 15: return e->util;
+        case 14: return e->err_ring; case 15: return e->util; case 16: return e->t_now; case 17: return e->play_time;
+        case 7: return e->started;
     }
     return 0;
 }
@@ -110,13 +115,34 @@ void orc_env_reset(OrcEnv* e, const int32_t* trace_id, const double* start_offse
         e->trace_id[s] = tr; e->seg[s] = seg; e->tau[s] = tau;
         e->buffer[s] = 0.0; e->chunk[s] = 0; e->last_q[s] = e->p.default_quality; e->done[s] = 0;
         e->hist_len[s] = 0; e->last_pred[s] = 0.0; e->err_len[s] = 0;
+        e->t_now[s] = 0.0; e->play_time[s] = 0.0; e->started[s] = e->p.start_up_length <= 0.0;
     }
 }
 
-typedef struct StepOut { double delay, sleep, buffer, rebuf, reward, thr, u, smooth; uint8_t eov; int inert; } StepOut;
+typedef struct StepOut { double delay, sleep, buffer, rebuf, reward, thr, u, smooth, latency, startup; uint8_t eov; int inert; } StepOut;
 
 /* SPEC §3 for one session */
-static void step_one(OrcEnv* e, int s, int q, StepOut* o) {
+/* SPEC §7 play(dt): playback during an interval; returns the stall time */
+static double play(OrcEnv* e, int s, double dt, double v, double* buffer, double* startup) {
+    if (!e->started[s]) { *startup = *startup + dt; return 0.0; }
+    double need = v * dt, drained, stall;
+    if (*buffer >= need) { drained = need; stall = 0.0; }
+    else { drained = *buffer; stall = dt - *buffer / v; }
+    *buffer = *buffer - drained;
+    e->play_time[s] = e->play_time[s] + drained;
+    return stall;
+}
+
+static void advance_trace(int* seg, double* tau, double dt, double I, int T) {   /* SPEC §3.3 */
+    double x = *tau + dt;
+    double n = floor(x / I);
+    *tau = x - n * I;
+    *seg = (int)((*seg + (int64_t)n) % T);
+    if (*tau < 0.0) *tau = 0.0;
+    if (*tau >= I) { *tau = 0.0; *seg = (*seg + 1 == T) ? 0 : *seg + 1; }
+}
+
+static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     const OrcParams* p = &e->p;
     memset(o, 0, sizeof(*o));
     if (e->done[s]) { o->eov = 1; o->buffer = e->buffer[s]; o->inert = 1; return; }
@@ -127,6 +153,17 @@ static void step_one(OrcEnv* e, int s, int q, StepOut* o) {
     int chunk = e->chunk[s], seg = e->seg[s];
     double tau = e->tau[s], buffer = e->buffer[s];
     const double size = e->sizes[chunk * e->A + q];
+    const int live = p->live != 0;
+    double idle = 0.0, rebuf = 0.0, startup = 0.0, latency = 0.0;
+    if (live) {   /* 7.1 pause gate */
+        double w1 = (double)(chunk + 1) * p->chunk_length - e->t_now[s];
+        w1 = max0(w1);
+        rebuf = play(e, s, w1, v, &buffer, &startup);
+        double w2 = (e->started[s] && buffer > p->max_buffer) ? (buffer - p->max_buffer) / v : 0.0;
+        rebuf = rebuf + play(e, s, w2, v, &buffer, &startup);
+        idle = w1 + w2;
+        if (idle > 0.0) advance_trace(&seg, &tau, idle, I, T);
+    }
     /* 3.1 segment walk */
     double sent = 0.0, delay;
     int guard = 1 << 20;   /* safety net only: every bandwidth is > 0, so the walk terminates */
@@ -151,26 +188,31 @@ static void step_one(OrcEnv* e, int s, int q, StepOut* o) {
         delay = (elapsed + dt) + p->rtt;
     }
     double thr = size / delay;
-    /* 3.2 */
-    double rebuf = max0(delay - buffer);
-    buffer = max0(buffer - delay) + p->chunk_length;
-    /* 3.3 */
     double sleep = 0.0;
-    if (buffer > p->max_buffer) {
-        sleep = ceil((buffer - p->max_buffer) / p->sleep_quantum) * p->sleep_quantum;
-        buffer = buffer - sleep;
-        double x = tau + sleep;
-        double n = floor(x / I);
-        tau = x - n * I;
-        seg = (int)((seg + (int64_t)n) % T);
-        if (tau < 0.0) tau = 0.0;
-        if (tau >= I) { tau = 0.0; seg = (seg + 1 == T) ? 0 : seg + 1; }
+    if (live) {   /* 7.2 */
+        rebuf = rebuf + play(e, s, delay, v, &buffer, &startup);
+        buffer = buffer + p->chunk_length;
+        e->t_now[s] = (e->t_now[s] + idle) + delay;
+        if (!e->started[s] && buffer >= p->start_up_length) e->started[s] = 1;
+        latency = e->t_now[s] - e->play_time[s];
+        sleep = idle;
+    } else {
+        /* 3.2 */
+        rebuf = max0(delay - buffer);
+        buffer = max0(buffer - delay) + p->chunk_length;
+        /* 3.3 */
+        if (buffer > p->max_buffer) {
+            sleep = ceil((buffer - p->max_buffer) / p->sleep_quantum) * p->sleep_quantum;
+            buffer = buffer - sleep;
+            advance_trace(&seg, &tau, sleep, I, T);
+        }
     }
     /* 3.4 */
     const double u = e->util[chunk * e->A + q];
     const int lq = e->last_q[s];
     double smooth = (lq >= 0) ? fabs(u - e->util[chunk * e->A + lq]) : 0.0;
     double reward = (u - p->rebuf_penalty * rebuf) - p->smooth_penalty * smooth;
+    if (live) reward = reward - p->latency_penalty * latency;
     /* history ring */
     if (p->track_history) {
         e->bw_hist[(size_t)s * e->K + (e->hist_len[s] % e->K)] = thr;
@@ -179,34 +221,49 @@ static void step_one(OrcEnv* e, int s, int q, StepOut* o) {
     /* 3.5 */
     chunk += 1;
     o->delay = delay; o->sleep = sleep; o->buffer = buffer; o->rebuf = rebuf; o->reward = reward;
-    o->thr = thr; o->u = u; o->smooth = smooth;
+    o->thr = thr; o->u = u; o->smooth = smooth; o->latency = latency; o->startup = startup;
     o->eov = (chunk >= e->V);
     e->last_q[s] = q;
     if (o->eov && p->auto_reset) {
         chunk = 0; buffer = 0.0; e->last_q[s] = p->default_quality;
         e->hist_len[s] = 0; e->last_pred[s] = 0.0; e->err_len[s] = 0;
+        e->t_now[s] = 0.0; e->play_time[s] = 0.0; e->started[s] = p->start_up_length <= 0.0;
     } else if (o->eov) {
         e->done[s] = 1;
     }
     e->chunk[s] = chunk; e->seg[s] = seg; e->tau[s] = tau; e->buffer[s] = buffer;
 }
 
-void orc_env_step(OrcEnv* e, const int32_t* action, double* delay, double* sleep, double* buffer,
-                  double* rebuf, double* reward, double* next_sizes, uint8_t* eov, double* throughput) {
+void orc_env_step_live(OrcEnv* e, const int32_t* action, const double* speed, double* delay, double* sleep,
+                       double* buffer, double* rebuf, double* reward, double* latency, double* next_sizes,
+                       uint8_t* eov, double* throughput, double* acc) {
+    const size_t N = (size_t)e->N;
     for (int s = 0; s < e->N; ++s) {
         StepOut o;
-        step_one(e, s, action[s], &o);
+        step_one(e, s, action[s], speed ? speed[s] : 1.0, &o);
         if (delay) delay[s] = o.delay;
         if (sleep) sleep[s] = o.sleep;
         if (buffer) buffer[s] = o.buffer;
         if (rebuf) rebuf[s] = o.rebuf;
         if (reward) reward[s] = o.reward;
+        if (latency) latency[s] = o.latency;
         if (eov) eov[s] = o.eov;
         if (throughput) throughput[s] = o.thr;
         if (next_sizes)
             for (int a = 0; a < e->A; ++a)
                 next_sizes[(size_t)s * e->A + a] = e->done[s] ? 0.0 : e->sizes[e->chunk[s] * e->A + a];
+        if (acc && !o.inert) {
+            acc[0 * N + s] += o.reward; acc[1 * N + s] += o.rebuf; acc[2 * N + s] += o.u; acc[3 * N + s] += o.smooth;
+            acc[4 * N + s] += o.sleep; acc[5 * N + s] += o.delay; acc[6 * N + s] += 1.0;
+            if (o.eov) acc[7 * N + s] += 1.0;
+            acc[8 * N + s] += o.startup; acc[9 * N + s] += o.latency;
+        }
     }
+}
+
+void orc_env_step(OrcEnv* e, const int32_t* action, double* delay, double* sleep, double* buffer,
+                  double* rebuf, double* reward, double* next_sizes, uint8_t* eov, double* throughput) {
+    orc_env_step_live(e, action, 0, delay, sleep, buffer, rebuf, reward, 0, next_sizes, eov, throughput, 0);
 }
 
 /* SPEC §4 */
@@ -239,7 +296,7 @@ void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base,
         for (int t = 0; t < steps; ++t) {
             int q = policy_action(e, s, policy, seed, session_base, t, actions_in);
             StepOut o;
-            step_one(e, s, q, &o);
+            step_one(e, s, q, 1.0, &o);
             size_t ix = (size_t)t * N + s;
             if (delay) delay[ix] = o.delay;
             if (sleep) sleep[ix] = o.sleep;
@@ -258,6 +315,7 @@ void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base,
             acc[0 * (size_t)N + s] = a_rew; acc[1 * (size_t)N + s] = a_reb; acc[2 * (size_t)N + s] = a_u;
             acc[3 * (size_t)N + s] = a_sm; acc[4 * (size_t)N + s] = a_sl; acc[5 * (size_t)N + s] = a_dl;
             acc[6 * (size_t)N + s] = a_steps; acc[7 * (size_t)N + s] = a_eps;
+            acc[8 * (size_t)N + s] = 0.0; acc[9 * (size_t)N + s] = 0.0;   /* the fused episode is not live */
         }
     }
 }

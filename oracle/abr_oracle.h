@@ -23,12 +23,13 @@ typedef struct OrcParams {          /* same field order as AbrParams in include/
     double chunk_length, max_buffer, rtt, payload, sleep_quantum;
     double rebuf_penalty, smooth_penalty, utility_scale;
     double bba_reservoir, bba_cushion;
+    double start_up_length, startup_penalty, latency_penalty;      /* live mode, SPEC §7 */
     int32_t utility_mode, default_quality, auto_reset, hist_k;
-    int32_t track_history, reserved0, reserved1, reserved2;
+    int32_t track_history, reserved0, live, reserved2;
 } OrcParams;
 
 enum { ORC_POLICY_FIXED = 0, ORC_POLICY_RANDOM = 1, ORC_POLICY_BBA = 2 };
-enum { ORC_NUM_STATS = 8, ORC_NUM_ACC = 8 };  /* reward, rebuf, u, smooth, sleep, delay, steps, episodes */
+enum { ORC_NUM_STATS = 10, ORC_NUM_ACC = 10 };  /* reward, rebuf, u, smooth, sleep, delay, steps, episodes, startup, latency */
 
 typedef struct OrcEnv OrcEnv;
 
@@ -40,6 +41,10 @@ void orc_env_reset(OrcEnv* e, const int32_t* trace_id, const double* start_offse
 /* one chunk step for all N sessions (SPEC §3); any output pointer may be NULL */
 void orc_env_step(OrcEnv* e, const int32_t* action, double* delay, double* sleep, double* buffer,
                   double* rebuf, double* reward, double* next_sizes, uint8_t* eov, double* throughput);
+/* live mode (SPEC §7): playback speed per session (NULL = 1) and the latency output; also valid with live = 0 */
+void orc_env_step_live(OrcEnv* e, const int32_t* action, const double* speed, double* delay, double* sleep,
+                       double* buffer, double* rebuf, double* reward, double* latency, double* next_sizes,
+                       uint8_t* eov, double* throughput, double* acc /* [ORC_NUM_ACC][N] accumulated into, nullable */);
 /* fused episode (SPEC §3+§4): trajectories are [steps][N]; acc is [ORC_NUM_ACC][N] */
 void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,
                      const int32_t* actions_in, double* delay, double* sleep, double* buffer, double* rebuf,
@@ -48,7 +53,8 @@ void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base,
 void orc_env_mpc_decide(OrcEnv* e, int H, int mode, int32_t* action, double* best_j, int32_t* best_seq);
 /* statistics vector from an acc table (SPEC §6): plain ascending-session sums */
 void orc_stats_from_acc(const double* acc, int N, double* out);
-/* state access for tests: field 0 seg,1 chunk,2 last_q,3 trace_id,4 hist_len (int32) ; 10 tau,11 buffer (double) */
+/* state access for tests: field 0 seg,1 chunk,2 last_q,3 trace_id,4 hist_len (int32) ; 10 tau,11 buffer (double);
+ * live mode: 16 t_now, 17 play_time (double), 7 started (uint8) */
 const void* orc_env_field(OrcEnv* e, int field);
 int orc_env_error_count(OrcEnv* e);
 

@@ -14,23 +14,24 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libabr_oracle.so")
 
-NUM_STATS = 8
-NUM_ACC = 8
+NUM_STATS = 10
+NUM_ACC = 10
 POLICY_FIXED, POLICY_RANDOM, POLICY_BBA = 0, 1, 2
 
 
 class OrcParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "chunk_length", "max_buffer", "rtt", "payload", "sleep_quantum", "rebuf_penalty",
-        "smooth_penalty", "utility_scale", "bba_reservoir", "bba_cushion")] + [
+        "smooth_penalty", "utility_scale", "bba_reservoir", "bba_cushion", "start_up_length",
+        "startup_penalty", "latency_penalty")] + [
         (n, C.c_int32) for n in ("utility_mode", "default_quality", "auto_reset", "hist_k",
-                                 "track_history", "reserved0", "reserved1", "reserved2")]
+                                 "track_history", "reserved0", "live", "reserved2")]
 
 
 DEFAULTS = dict(chunk_length=4.0, max_buffer=60.0, rtt=0.08, payload=0.95, sleep_quantum=0.5,
                 rebuf_penalty=4.3, smooth_penalty=1.0, utility_scale=0.001, bba_reservoir=5.0,
-                bba_cushion=10.0, utility_mode=0, default_quality=1, auto_reset=1, hist_k=5,
-                track_history=0)
+                bba_cushion=10.0, start_up_length=0.0, startup_penalty=0.0, latency_penalty=0.0, utility_mode=0,
+                default_quality=1, auto_reset=1, hist_k=5, track_history=0, live=0)
 
 
 def make_params(**kw) -> OrcParams:
@@ -123,14 +124,18 @@ class OracleEnv:
         o = None if start_offset is None else _f64(start_offset)
         lib().orc_env_reset(self._h, _p(t), _p(o))
 
-    def step(self, action, want_next_sizes=True):
+    def step(self, action, want_next_sizes=True, speed=None, acc=None):
+        """One chunk step (SPEC §3, or §7 when live = 1).  ``speed``: playback speed per session (live mode);
+        ``acc``: [NUM_ACC, N] accumulator table to add this step into."""
         N, A = self.N, self.A
         a = _i32(action)
+        v = None if speed is None else _f64(speed)
         out = dict(delay=np.empty(N), sleep=np.empty(N), buffer=np.empty(N), rebuf=np.empty(N),
-                   reward=np.empty(N), eov=np.empty(N, np.uint8), throughput=np.empty(N),
+                   reward=np.empty(N), latency=np.empty(N), eov=np.empty(N, np.uint8), throughput=np.empty(N),
                    next_sizes=np.empty((N, A)) if want_next_sizes else None)
-        lib().orc_env_step(self._h, _p(a), _p(out["delay"]), _p(out["sleep"]), _p(out["buffer"]), _p(out["rebuf"]),
-                           _p(out["reward"]), _p(out["next_sizes"]), _p(out["eov"]), _p(out["throughput"]))
+        lib().orc_env_step_live(self._h, _p(a), _p(v), _p(out["delay"]), _p(out["sleep"]), _p(out["buffer"]),
+                                _p(out["rebuf"]), _p(out["reward"]), _p(out["latency"]), _p(out["next_sizes"]),
+                                _p(out["eov"]), _p(out["throughput"]), _p(acc))
         return out
 
     def rollout(self, policy, steps, seed=0, session_base=0, actions=None, want_traj=True):
@@ -160,7 +165,8 @@ class OracleEnv:
         ids = dict(seg=(0, np.int32, 1), chunk=(1, np.int32, 1), last_q=(2, np.int32, 1), trace_id=(3, np.int32, 1),
                    hist_len=(4, np.int32, 1), done=(5, np.uint8, 1), err_len=(6, np.int32, 1), tau=(10, np.float64, 1),
                    buffer=(11, np.float64, 1), bw_hist=(12, np.float64, self.K), last_pred=(13, np.float64, 1),
-                   err_ring=(14, np.float64, self.K))
+                   err_ring=(14, np.float64, self.K), t_now=(16, np.float64, 1), play_time=(17, np.float64, 1),
+                   started=(7, np.uint8, 1))
         fid, dt, w = ids[name]
         ptr = lib().orc_env_field(self._h, C.c_int(fid))
         n = self.N * w

@@ -30,12 +30,55 @@ class Session:
         self.last_q = P["default_quality"]
         self.done = False
         self.history = []          # all measured throughputs since reset
+        # live mode (SPEC §7)
+        self.t_now = 0.0
+        self.play_time = 0.0
+        self.started = P.get("start_up_length", 0.0) <= 0.0
 
-    def step(self, q):
+    def _play(self, dt, v, acc):
+        """SPEC §7 play(Δ): returns the stall time; acc['startup'] collects start-up time."""
+        if not self.started:
+            acc["startup"] = acc["startup"] + dt
+            return 0.0
+        need = v * dt
+        if self.buffer >= need:
+            drained, stall = need, 0.0
+        else:
+            drained, stall = self.buffer, dt - self.buffer / v
+        self.buffer = self.buffer - drained
+        self.play_time = self.play_time + drained
+        return stall
+
+    def _advance(self, dt):
+        x = self.tau + dt
+        n = math.floor(x / self.I)
+        self.tau = x - n * self.I
+        self.seg = (self.seg + n) % self.T
+        if self.tau < 0.0:
+            self.tau = 0.0
+        if self.tau >= self.I:
+            self.tau = 0.0
+            self.seg = (self.seg + 1) % self.T
+
+    def step(self, q, v=1.0):
         P = self.P
         if self.done:
-            return dict(delay=0.0, sleep=0.0, buffer=self.buffer, rebuf=0.0, reward=0.0, eov=1, inert=True)
+            return dict(delay=0.0, sleep=0.0, buffer=self.buffer, rebuf=0.0, reward=0.0, eov=1, inert=True,
+                        latency=0.0, startup=0.0)
         size = self.sizes[self.chunk][q]
+        live = bool(P.get("live", 0))
+        acc = dict(startup=0.0)
+        idle = 0.0
+        rebuf = 0.0
+        if live:                                                              # SPEC 7.1
+            w1 = (self.chunk + 1) * P["chunk_length"] - self.t_now
+            w1 = w1 if w1 > 0 else 0.0
+            rebuf = self._play(w1, v, acc)
+            w2 = (self.buffer - P["max_buffer"]) / v if (self.started and self.buffer > P["max_buffer"]) else 0.0
+            rebuf = rebuf + self._play(w2, v, acc)
+            idle = w1 + w2
+            if idle > 0:
+                self._advance(idle)
         sent = 0.0
         k = 0
         room0 = self.I - self.tau
@@ -55,10 +98,20 @@ class Session:
         elapsed = 0.0 if k == 0 else room0 + float(k - 1) * self.I
         delay = (elapsed + dt) + P["rtt"]
         thr = size / delay
-        rebuf = delay - self.buffer if delay - self.buffer > 0 else 0.0     # SPEC 3.2
-        self.buffer = (self.buffer - delay if self.buffer - delay > 0 else 0.0) + P["chunk_length"]
-        sleep = 0.0
-        if self.buffer > P["max_buffer"]:                                     # SPEC 3.3
+        latency = 0.0
+        if live:                                                              # SPEC 7.2
+            rebuf = rebuf + self._play(delay, v, acc)
+            self.buffer = self.buffer + P["chunk_length"]
+            self.t_now = (self.t_now + idle) + delay
+            if not self.started and self.buffer >= P.get("start_up_length", 0.0):
+                self.started = True
+            latency = self.t_now - self.play_time
+            sleep = idle
+        else:
+            rebuf = delay - self.buffer if delay - self.buffer > 0 else 0.0     # SPEC 3.2
+            self.buffer = (self.buffer - delay if self.buffer - delay > 0 else 0.0) + P["chunk_length"]
+            sleep = 0.0
+        if not live and self.buffer > P["max_buffer"]:                        # SPEC 3.3
             sleep = math.ceil((self.buffer - P["max_buffer"]) / P["sleep_quantum"]) * P["sleep_quantum"]
             self.buffer = self.buffer - sleep
             x = self.tau + sleep
@@ -73,17 +126,22 @@ class Session:
         u = self.util[self.chunk][q]                                          # SPEC 3.4
         smooth = abs(u - self.util[self.chunk][self.last_q]) if self.last_q >= 0 else 0.0
         reward = (u - P["rebuf_penalty"] * rebuf) - P["smooth_penalty"] * smooth
+        if live:
+            reward = reward - P.get("latency_penalty", 0.0) * latency
         self.history.append(thr)
         self.last_q = q                                                       # SPEC 3.5
         self.chunk += 1
         eov = self.chunk >= self.V
         out = dict(delay=delay, sleep=sleep, buffer=self.buffer, rebuf=rebuf, reward=reward, eov=int(eov),
-                   throughput=thr, u=u, smooth=smooth, inert=False)
+                   throughput=thr, u=u, smooth=smooth, inert=False, latency=latency, startup=acc["startup"])
         if eov and P["auto_reset"]:
             self.chunk = 0
             self.buffer = 0.0
             self.last_q = P["default_quality"]
             self.history = []
+            self.t_now = 0.0
+            self.play_time = 0.0
+            self.started = P.get("start_up_length", 0.0) <= 0.0
         elif eov:
             self.done = True
         return out
@@ -110,3 +168,41 @@ def euler_download_delay(bw, interval, start_time, size, payload, dt=0.01):
         elapsed += dt
         t += dt
     return elapsed
+
+
+def euler_live_session(bw, interval, sizes, L, B, start_up_length, payload, speed=1.0, dt=0.001):
+    """The intended live dynamics of Simulator.py:135-208 as a fixed-dt loop, written from the tick order in
+    SURVEY.md §3.2 with the two missing pause resets supplied (D2): timers, live-edge/buffer-full gate, download
+    against the square wave, playback drain at `speed`, start-up latch.  `sizes[k]` is the payload of chunk k.
+    Returns dict(rebuffer, startup, latency, delays).  Loose plausibility check for SPEC §7 only."""
+    T = len(bw)
+    t = 0.0
+    chunk = 0
+    buffer = 0.0
+    start_up = start_up_length > 0
+    rebuffer = startup = play_time = 0.0
+    got = dtime = 0.0
+    delays = []
+    while chunk < len(sizes):
+        if start_up:
+            startup += dt
+        elif buffer <= 0.0:
+            rebuffer += dt
+        available = int(t / L) - 1
+        if available >= chunk and (buffer < B or dtime > 0.0):
+            got += bw[int(t / interval) % T] * payload * dt
+            dtime += dt
+            if got >= sizes[chunk]:
+                delays.append(dtime)
+                chunk += 1
+                got = dtime = 0.0
+                buffer += L
+        if not start_up and buffer > 0.0:
+            play_time += speed * dt
+            buffer -= speed * dt
+        if buffer <= 0.0:
+            buffer = 0.0
+        if start_up and buffer >= start_up_length:
+            start_up = False
+        t += dt
+    return dict(rebuffer=rebuffer, startup=startup, latency=t - play_time, delays=delays, t=t, play_time=play_time)

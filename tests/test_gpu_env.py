@@ -15,6 +15,7 @@ from abrsimulator_b200 import synth
 from abrsimulator_b200.env import BatchedABREnv
 from abrsimulator_b200.datamodel import Chunk, NetworkInfo, QOEMetric
 from abrsimulator_b200.simulator import Simulator, BufferBasedPolicy, RandomPolicy
+from abrsimulator_b200.mpc import MPCBitrateController
 from abrsimulator_b200 import _lib
 from oracle import oracle as orc
 from helpers import small_world, assert_close, bits_equal
@@ -220,7 +221,7 @@ def test_sharded_random_rollout_equals_unsharded():
     full.reset(tid, off)
     ref = full.rollout("random", steps, seed=42, want=("reward", "actions"))
     parts = []
-    stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+    stats = torch.zeros(_lib.NUM_STATS, dtype=torch.float64, device="cuda")
     for lo, hi in ((0, N // 2), (N // 2, N)):
         tid_s, off_s = synth.make_sessions(hi - lo, 32, 256, session_base=lo)
         assert np.array_equal(tid_s, tid[lo:hi]) and np.array_equal(off_s, off[lo:hi])
@@ -271,6 +272,84 @@ def test_log_utility_mode_matches_oracle():
         act = env.mpc_decide(4, mode).cpu().numpy()
         act_ref, _ = ref.mpc_decide(4, mode)
         assert np.array_equal(act, act_ref)
+
+
+LIVE = dict(live=1, start_up_length=8.0, max_buffer=16.0, latency_penalty=0.05, startup_penalty=1.0, track_acc=1)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_live_mode_step_matches_oracle(ragged):
+    """SPEC §7: live-edge gate, start-up latch, playback speed as a second action, latency — over two videos."""
+    N, steps = 2048, 70
+    env, ref = make_pair(N, dict(LIVE, track_history=1), V=30, ragged=ragged)
+    rng = np.random.default_rng(17)
+    acc = np.zeros((orc.NUM_ACC, N))
+    for t in range(steps):
+        a = rng.integers(0, env.A, size=N).astype(np.int32)
+        v = rng.choice([0.75, 1.0, 1.0, 1.25, 1.5], size=N)
+        got = env.step(a, speed=v, want_throughput=True)
+        exp = ref.step(a, speed=v, acc=acc)
+        for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                         ("reward", "reward"), ("latency", "latency"), ("throughput", "throughput")):
+            assert_close(getattr(got, k_g).cpu().numpy(), exp[k_c], f"{k_g}@{t}")
+        assert np.array_equal(got.end_of_video.cpu().numpy(), exp["eov"])
+    check_state(env, ref)
+    for f in ("t_now", "play_time"):
+        assert bits_equal(env.state(f).cpu().numpy(), ref.field(f)) == 0, f
+    assert np.array_equal(env.state("started").cpu().numpy(), ref.field("started"))
+    assert_close(env.session_acc().cpu().numpy(), acc, "acc")
+    assert acc[8].min() > 0 and acc[9].min() > 0 and (acc[1] > 0).any()
+    # session cost: rw*rebuf + vw*smooth + sw*startup + lw*latency/steps (Simulator.py:83-86)
+    want = 4.3 * acc[1] + 1.0 * acc[3] + 1.0 * acc[8] + 0.05 * (acc[9] / acc[6])
+    np.testing.assert_allclose(env.qoe_cost().cpu().numpy(), want, rtol=1e-12)
+    assert env.error_count() == 0
+    with pytest.raises(_lib.AbrError):
+        env.rollout("bba", 4)                     # the fused episode refuses live mode
+    with pytest.raises(_lib.AbrError):
+        BatchedABREnv(np.ones((1, 8)), np.ones((2, 3)), np.ones((2, 3)), 4, live=1, start_up_length=100.0)
+
+
+def test_simulator_facade_live_mode():
+    """The reference's Simulator is a live simulator: MPD with start_up_length, speed controller, latency weight."""
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=1, T=200, V=20)
+
+    class Speed:
+        def __init__(self):
+            self.n = 0
+
+        def get_next_speed(self):
+            self.n += 1
+            return 1.25 if self.n > 10 else 1.0
+
+    class Second:
+        def get_next_bitrate(self, chunk_id, previous_bitrates, previous_bandwidths, buffer_level):
+            return 1
+
+    sp = Speed()
+    sim = Simulator(Second(), sp)
+    sim.set_qoe_metric(QOEMetric(4.3, 0.5, 2.0, 0.1))
+    sim.set_network_info(1.0, list(bw[0]))
+    sim.set_mpd(4.0, 16.0, 8.0, [Chunk(list(b / 1000.0)) for b in bitrates])
+    cost = sim.run()
+    assert sp.n == 20
+    P = dict(chunk_length=4.0, max_buffer=16.0, rebuf_penalty=4.3, smooth_penalty=0.5, utility_scale=1.0,
+             default_quality=-1, auto_reset=0, live=1, start_up_length=8.0, startup_penalty=2.0, latency_penalty=0.1)
+    ref = orc.OracleEnv(bw, tl, ti, bitrates / 1000.0 * 4.0, bitrates / 1000.0, 1, **P)
+    ref.reset(np.zeros(1, np.int32))
+    acc = np.zeros((orc.NUM_ACC, 1))
+    for k in range(20):
+        ref.step(np.ones(1, np.int32), speed=np.array([1.25 if k >= 10 else 1.0]), acc=acc)
+    want = 4.3 * acc[1, 0] + 0.5 * acc[3, 0] + 2.0 * acc[8, 0] + 0.1 * acc[9, 0] / 20
+    assert cost == pytest.approx(want, rel=1e-12) and acc[8, 0] > 0 and acc[9, 0] > 0
+    assert sim.last_run["startup"][0] == acc[8, 0]
+    # built-in policy markers and the MPC controller also run in live mode
+    for ctrl in (BufferBasedPolicy(), RandomPolicy(5), MPCBitrateController(horizon=3, mode="robust")):
+        sim2 = Simulator(ctrl, None)
+        sim2.set_qoe_metric(QOEMetric(4.3, 0.5, 2.0, 0.1))
+        sim2.set_network_info(1.0, [NetworkInfo(1.0, list(bw[0])), NetworkInfo(0.5, list(bw[0][:60]))])
+        sim2.set_mpd(4.0, 16.0, 8.0, [Chunk(list(b / 1000.0)) for b in bitrates])
+        costs = sim2.run_batch(64)
+        assert costs.shape == (64,) and np.all(np.isfinite(costs)) and np.all(costs > 0)
 
 
 def test_run_host_path_matches_oracle():
@@ -359,7 +438,7 @@ def test_calls_are_cuda_graph_capturable():
     out = {k: torch.empty(steps, N, dtype=torch.float64, device="cuda") for k in
            ("delay", "sleep", "buffer", "rebuffer", "reward")}
     out["end_of_video"] = torch.empty(steps, N, dtype=torch.uint8, device="cuda")
-    stats = torch.empty(8, dtype=torch.float64, device="cuda")
+    stats = torch.empty(_lib.NUM_STATS, dtype=torch.float64, device="cuda")
 
     def one():
         env.reset(tid_d, off_d)
@@ -424,7 +503,7 @@ def test_simulator_facade_run():
     sim = Simulator(BufferBasedPolicy(), None)
     sim.set_qoe_metric(QOEMetric(4.3, 0.001, 0, 0))
     sim.set_network_info(1.0, list(bw[0]))
-    sim.set_mpd(4.0, 60.0, 0.0, [Chunk(list(b / 1000.0)) for b in bitrates])   # sizes = bitrate * chunk_length
+    sim.set_mpd(4.0, 60.0, None, [Chunk(list(b / 1000.0)) for b in bitrates])   # sizes = bitrate * chunk_length; no start_up_length: on-demand
     cost = sim.run()
     P = dict(chunk_length=4.0, max_buffer=60.0, rebuf_penalty=4.3, smooth_penalty=0.001, utility_scale=1.0,
              default_quality=-1, auto_reset=0)
@@ -446,7 +525,7 @@ def test_simulator_facade_run():
     sim2 = Simulator(ctl, None)
     sim2.set_qoe_metric(QOEMetric(4.3, 0.001, 0, 0))
     sim2.set_network_info(NetworkInfo(1.0, list(bw[0])).interval, list(bw[0]))
-    sim2.set_mpd(4.0, 60.0, 0.0, [Chunk(list(b / 1000.0)) for b in bitrates])
+    sim2.set_mpd(4.0, 60.0, None, [Chunk(list(b / 1000.0)) for b in bitrates])
     cost2 = sim2.run()
     assert len(ctl.calls) == 30 and ctl.calls[5][:3] == (5, 5, 5)
     ref.reset(np.zeros(1, np.int32))
@@ -456,6 +535,6 @@ def test_simulator_facade_run():
     sim3 = Simulator(RandomPolicy(3), None)
     sim3.set_qoe_metric(QOEMetric(4.3, 1.0, 0, 0))
     sim3.set_network_info(1.0, [NetworkInfo(1.0, list(bw[0])), NetworkInfo(0.5, list(bw[0][:50]))])
-    sim3.set_mpd(4.0, 60.0, 0.0, [Chunk(list(b / 1000.0)) for b in bitrates])
+    sim3.set_mpd(4.0, 60.0, None, [Chunk(list(b / 1000.0)) for b in bitrates])
     costs = sim3.run_batch(100)
     assert costs.shape == (100,) and np.all(np.isfinite(costs)) and np.all(costs >= 0)

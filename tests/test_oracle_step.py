@@ -125,3 +125,66 @@ def test_analytic_walk_agrees_with_fixed_dt_loop():
         euler = so.euler_download_delay(bw[0], 1.0, t_now, sizes[k][q], 1.0)
         assert abs(euler - r["delay"]) <= 0.0101 + 1e-9
         t_now += r["delay"] + r["sleep"]
+
+
+def _live_params(**kw):
+    P = dict(orc.DEFAULTS, live=1, start_up_length=8.0, max_buffer=16.0, latency_penalty=0.05, startup_penalty=1.0)
+    P.update(kw)
+    return P
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_live_mode_c_equals_python(ragged):
+    """SPEC §7: live-edge gate, start-up latch, playback speed and latency — C oracle vs pure-Python restatement."""
+    N, steps = 20, 70
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=5, T=50, V=30, ragged=ragged)
+    P = _live_params()
+    env = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **P)
+    rng = np.random.default_rng(8)
+    tid = rng.integers(0, 5, size=N).astype(np.int32)
+    off = rng.uniform(0, 80, size=N)
+    env.reset(tid, off)
+    util = orc.utility_table(bitrates, 0, P["utility_scale"])
+    py = [so.Session(bw[tid[s], :tl[tid[s]]], ti[tid[s]], sizes.tolist(), util.tolist(), P, off[s]) for s in range(N)]
+    acc = np.zeros((orc.NUM_ACC, N))
+    tot_startup = np.zeros(N)
+    for t in range(steps):
+        a = rng.integers(0, 6, size=N).astype(np.int32)
+        v = rng.choice([0.75, 1.0, 1.0, 1.25, 1.5], size=N)
+        c = env.step(a, speed=v, acc=acc)
+        for s in range(N):
+            r = py[s].step(int(a[s]), float(v[s]))
+            for k in ("delay", "sleep", "buffer", "rebuf", "reward", "latency", "throughput"):
+                assert c[k][s] == r[k], (t, s, k)
+            assert c["eov"][s] == r["eov"]
+            tot_startup[s] += r["startup"]
+    assert bits_equal(env.field("t_now"), np.array([p.t_now for p in py])) == 0
+    assert bits_equal(env.field("play_time"), np.array([p.play_time for p in py])) == 0
+    assert np.array_equal(env.field("started"), np.array([p.started for p in py], np.uint8))
+    np.testing.assert_allclose(acc[8], tot_startup, rtol=1e-12)
+    assert acc[8].min() > 0 and acc[9].min() > 0 and (acc[1] > 0).any()      # start-up, latency, rebuffering all occur
+
+
+def test_live_mode_agrees_with_fixed_dt_loop():
+    """Plausibility of SPEC §7 against a 1 ms tick loop with the reference's intended order of operations
+    (Simulator.py:135-208): totals agree to within a few ticks per chunk."""
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=1, T=80, V=16)
+    for speed, sul in ((1.0, 8.0), (1.25, 4.0), (0.8, 12.0)):
+        P = _live_params(rtt=0.0, payload=1.0, start_up_length=sul, max_buffer=12.0, auto_reset=0)
+        util = orc.utility_table(bitrates, 0, 0.001)
+        sess = so.Session(bw[0], 1.0, sizes.tolist(), util.tolist(), P)
+        qs = [k % 6 for k in range(16)]
+        rebuf = startup = 0.0
+        delays = []
+        for k in range(16):
+            r = sess.step(qs[k], speed)
+            rebuf += r["rebuf"]
+            startup += r["startup"]
+            delays.append(r["delay"])
+        e = so.euler_live_session(bw[0], 1.0, [sizes[k][qs[k]] for k in range(16)], 4.0, 12.0, sul, 1.0, speed)
+        tol = 16 * 0.004 + 0.01
+        assert abs(e["t"] - sess.t_now) < tol, (speed, e["t"], sess.t_now)
+        assert abs(e["startup"] - startup) < tol
+        assert abs(e["rebuffer"] - rebuf) < tol * max(1.0, speed)
+        assert abs(e["latency"] - (sess.t_now - sess.play_time)) < tol * 2
+        assert max(abs(a - b) for a, b in zip(e["delays"], delays)) < 0.0031
