@@ -178,29 +178,26 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     std::vector<double> util;
     utility_table(h_bitrates, V, A, params, util);
     CUDA_TRY(cudaMemcpy(d_bw, h_trace_bw, sizeof(double) * n_traces * T_max, cudaMemcpyHostToDevice));
-    // walk period per trace: short traces are extended periodically (same square wave) to >= ABR_MIN_PERIOD
-    std::vector<int32_t> period(n_traces);
-    int T_rate = T_max;
-    for (int t = 0; t < n_traces; ++t) {
-        const int len = h_trace_len[t];
-        period[t] = len >= ABR_MIN_PERIOD ? len : len * ((ABR_MIN_PERIOD + len - 1) / len);
-        if (period[t] > T_rate) T_rate = period[t];
-    }
-    v.T_rate = T_rate;
-    int32_t* d_len_raw;
-    CUDA_TRY(e->alloc(&d_len_raw, n_traces));
-    CUDA_TRY(cudaMemcpy(d_len_raw, h_trace_len, sizeof(int32_t) * n_traces, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d_len, period.data(), sizeof(int32_t) * n_traces, cudaMemcpyHostToDevice));
-    v.trace_len_raw = d_len_raw;
+    CUDA_TRY(cudaMemcpy(d_len, h_trace_len, sizeof(int32_t) * n_traces, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_int, h_trace_interval, sizeof(double) * n_traces, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_sizes, h_sizes, sizeof(double) * V * A, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice));
     v.trace_bw = d_bw; v.trace_len = d_len; v.trace_interval = d_int; v.sizes = d_sizes; v.util = d_util;
-    double* d_rate;
-    CUDA_TRY(e->alloc(&d_rate, (size_t)n_traces * rate_stride(v.T_rate)));
-    v.trace_rate = d_rate;
-    CUDA_TRY(launch_trace_table(v, d_rate, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
+    // per-trace tables of SPEC §3.1 (cumulative capacity, search widths), built on the device
+    double* d_cum;
+    int32_t* d_bits;
+    CUDA_TRY(e->alloc(&d_cum, (size_t)n_traces * cum_stride(T_max)));
+    CUDA_TRY(e->alloc(&d_bits, n_traces));
+    v.trace_cum = d_cum; v.trace_bits = d_bits;
+    CUDA_TRY(launch_trace_table(v, d_cum, d_bits, 0));
+    {
+        std::vector<int32_t> bits(n_traces);
+        CUDA_TRY(cudaMemcpy(bits.data(), d_bits, sizeof(int32_t) * n_traces, cudaMemcpyDeviceToHost));
+        for (int t = 0; t < n_traces; ++t)
+            if (bits[t] < 0)
+                return fail(ABR_ERR_INVALID, "trace %d: every segment capacity bandwidth*payload*interval must be representable "
+                                             "next to the capacity of the whole trace period (positive, finite)", t);
+    }
     CUDA_TRY(e->alloc(&v.seg, cap)); CUDA_TRY(e->alloc(&v.chunk, cap)); CUDA_TRY(e->alloc(&v.last_q, cap));
     CUDA_TRY(e->alloc(&v.trace_id, cap)); CUDA_TRY(e->alloc(&v.hist_len, cap)); CUDA_TRY(e->alloc(&v.err_len, cap));
     CUDA_TRY(e->alloc(&v.done, cap)); CUDA_TRY(e->alloc(&v.tau, cap)); CUDA_TRY(e->alloc(&v.buffer, cap));

@@ -6,15 +6,11 @@
 #include <stdint.h>
 #include "../../include/abr_b200.h"
 
-#define ABR_WALK_BLOCK 8                     // segments consumed per walk block
-#define ABR_MIN_PERIOD 16                    // a trace is periodic: short ones are walked with a period of >= 16 segments,
-                                             // so that advancing by one block needs a single conditional subtraction
-#define ABR_WALK_PAD (2 * ABR_WALK_BLOCK + 4)  // every rate-table row is followed by a wrapped copy of its start
-
 namespace abr {
 
-// row stride of the rate table in doubles: padded and even, so every row starts 16-byte aligned
-__host__ __device__ __forceinline__ int rate_stride(int T_max) { return (T_max + ABR_WALK_PAD + 1) & ~1; }
+// Row stride (in doubles) of the cumulative-capacity table C[0..T] of SPEC §3.1, even so that every row starts
+// 16-byte aligned (TMA bulk copies).
+__host__ __device__ __forceinline__ int cum_stride(int T_max) { return (T_max + 2) & ~1; }
 
 // ---------------------------------------------------------------------------------------------
 // exact fp64 helpers
@@ -66,10 +62,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 struct EnvView {
     // read-only tables
     const double* __restrict__ trace_bw;        // [n_traces][T_max]
-    const double* __restrict__ trace_rate;      // [n_traces][T_max + ABR_WALK_PAD] bw*payload, rows wrapped
-    const int32_t* __restrict__ trace_len;      // [n_traces] walk period: the trace length, or for traces shorter than
-                                                // ABR_MIN_PERIOD the smallest multiple of it that reaches ABR_MIN_PERIOD
-    const int32_t* __restrict__ trace_len_raw;  // [n_traces] length as given by the caller
+    const double* __restrict__ trace_cum;       // [n_traces][cum_stride] C[0] = 0, C[j+1] = C[j] + (bw[j]*payload)*I (SPEC §3.1);
+                                                // entries past C[T] are +inf
+    const int32_t* __restrict__ trace_bits;     // [n_traces] search widths: bits 0-7 = b_near (2^b_near - 1 >= the most
+                                                // segments one download can cross), bits 8-15 = b_full (2^b_full >= T)
+    const int32_t* __restrict__ trace_len;      // [n_traces]
     const double* __restrict__ trace_interval;  // [n_traces]
     const double* __restrict__ sizes;           // [V][A]
     const double* __restrict__ util;            // [V][A]
@@ -79,13 +76,13 @@ struct EnvView {
     double* t_now; double* play_time;            // live mode (SPEC §7)
     double* tau; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
     unsigned long long* errors;                 // device counter of flagged sessions
-    int n_traces, T_max, T_rate, V, A, K, cap, n;   // T_rate = max(T_max, longest period): row length of trace_rate; n = active sessions
+    int n_traces, T_max, V, A, K, cap, n;       // n = active sessions
     long long session_base;
     AbrParams p;
 };
 
 // launchers implemented in abr_step.cu / abr_mpc.cu (C++ linkage, internal)
-cudaError_t launch_trace_table(const EnvView& v, double* d_rate, cudaStream_t st);
+cudaError_t launch_trace_table(const EnvView& v, double* d_cum, int32_t* d_bits, cudaStream_t st);
 cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st);
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
                         double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,

@@ -1,24 +1,29 @@
-// Chunk-step kernels (SPEC.md §2-§4, §6): one thread per session.
+// Chunk-step kernels (SPEC.md §2-§4, §6, §7): one thread per session.
 //
 // Replaces the per-session fixed-dt Python loop of the reference (Simulator.py:135-208: download block
-// :152-170, playback/buffer block :137-140,174-202, pause gate :143-145) with an analytic walk over the
-// square-wave trace segments (NetworkInfo, Simulator.py:37-42).
+// :152-170, playback/buffer block :137-140,174-202, pause gate :143-145) with a closed form over the
+// square-wave trace (NetworkInfo, Simulator.py:37-42).
 //
 //  * abr_step_kernel     one chunk step per launch, SoA state in HBM (RL harness form).  HBM-bound:
 //                        36 B read + 28 B state write + 41 B outputs per session-step.
 //  * abr_rollout_kernel  `steps` chunk steps per launch with the state in registers and the trajectory
 //                        streamed out with st.global.cs (41 B/step) — the fused-episode form.
-//  * abr_reset_kernel, abr_stats_* helpers.
+//  * abr_trace_table_kernel, abr_reset_kernel, abr_stats_* helpers.
 //
-// Trace data comes from a per-segment rate table (rate = bw*payload, the product SPEC §3.1 forms per visit, built
-// once per environment; every row is followed by a wrapped copy of its first ABR_WALK_PAD entries so a walk block
-// never needs wrap arithmetic).  Two access paths:
-//   * shared-memory path (fused episode): when all sessions of a thread block follow the same trace and its row
-//     fits, the block stages the row in shared memory once (coalesced 16-byte loads) and every walk of the
-//     episode reads it with LDS — the "traces staged in shared memory" design of the north star.  Per-lane
-//     scattered global loads cost one L1 wavefront per lane (32 per instruction); LDS costs 2-5.
-//   * global path (any session order, per-step kernel): read-only loads (ld.global.nc) with the next block
-//     prefetched while the current one is consumed; the table (17 MB at the benchmark shape) is L2-resident.
+// SPEC §3.1 integrates the download against the trace's cumulative capacity C[j] (data deliverable from the
+// start of the trace period up to the start of segment j, accumulated left to right once per environment).  A
+// download from position (seg, tau) ends in the segment j with C[j] <= pos + size < C[j+1], which a branch-free
+// descending-power-of-two search finds in b_near = log2(most segments a download can cross) probes that every
+// lane of a warp executes in lock step: no per-segment loop, no divergence between sessions on fast and slow
+// networks, and a dependency chain of one compare per probe instead of one add per segment.  C is the only trace
+// table the step reads (a segment's capacity is C[j+1] - C[j]).
+// Two access paths for C:
+//   * shared-memory path (fused episode): when all sessions of a thread block follow the same trace and its C row
+//     fits, the block stages the row in shared memory once (TMA bulk copy) and every probe is an LDS — the "traces
+//     staged in shared memory" design of the north star.  A per-lane scattered global load costs one L1 wavefront
+//     per lane (32 per instruction); an LDS costs 2-5.
+//   * global path (any session order, per-step kernel): read-only loads (ld.global.nc); the table (17 MB at the
+//     benchmark shape) is L2-resident.
 #include "abr_common.cuh"
 
 namespace abr {
@@ -29,14 +34,16 @@ constexpr int kStepBlock = 256;
 constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per SM (balanced over 148 SMs)
 constexpr int kStatsBlock = 256;
 constexpr int kStatsSessionsPerBlock = 1024;   // 64 blocks at 65 536 sessions: enough loads in flight to hide HBM latency
-constexpr int kWalkBlock = ABR_WALK_BLOCK;   // segments fetched per walk block (rows are padded by 2 blocks + 1)
+constexpr int kWrapGuard = 1 << 20;            // safety net of the whole-period loop (SPEC §3.1)
 
 struct Sess {
-    const double* __restrict__ rate;  // per segment: bw*payload; global row or its shared-memory copy
+    const double* __restrict__ cum;   // C[0..T] of the session's trace: global row or its shared-memory copy
     const double* __restrict__ sizes; // [V][A] chunk sizes and utilities: global tables or their shared-memory copies
     const double* __restrict__ util;
-    double I, tau, buffer;
-    int T, seg, chunk, last_q, hist_len;
+    double I, inv_i, tau, buffer;     // inv_i = 1/I when I is a power of two (then x/I == x*inv_i bit for bit), else 0
+    double P;                         // C[T]: capacity of one trace period
+    double c_seg, c_seg1, frac;       // C[seg], C[seg+1], tau/I carried between the steps of a fused episode (CARRY)
+    int T, seg, chunk, last_q, hist_len, bits;
     bool done;
     // live mode (SPEC §7)
     double t_now, play_time, speed;
@@ -48,33 +55,9 @@ struct StepRes {
     bool eov, inert, walk_error, reset_mpc;
 };
 
-// Rate-table rows start 16-byte aligned (even stride), so N consecutive entries starting at any index are fetched
-// as ceil((N+1)/2) aligned 16-byte loads from the even index below and picked apart with selects: 5 scattered
-// global loads (one L1 wavefront per lane each) instead of 9 for the first block of a step.
 template <bool SMEM>
-__device__ __forceinline__ double2 rate2_at(const double* __restrict__ row, int even_idx) {
-    const double2* p = reinterpret_cast<const double2*>(row + even_idx);
-    return SMEM ? *p : __ldg(p);
-}
-
-template <bool SMEM, int N>
-__device__ __forceinline__ void load_rates(const double* __restrict__ row, int idx, double (&out)[N]) {
-    if (SMEM) {   // shared memory: scalar 8-byte loads are cheaper than vector loads plus the selects below
-#pragma unroll
-        for (int u = 0; u < N; ++u) out[u] = row[idx + u];
-        return;
-    }
-    constexpr int NV = (N + 2) / 2;
-    const int odd = idx & 1;
-    double2 v[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = rate2_at<SMEM>(row, idx - odd + 2 * k);
-#pragma unroll
-    for (int u = 0; u < N; ++u) {
-        const double even_case = (u & 1) ? v[u / 2].y : v[u / 2].x;                    // flat[idx - 0 + u]
-        const double odd_case = ((u + 1) & 1) ? v[(u + 1) / 2].y : v[(u + 1) / 2].x;   // flat[idx - 1 + u + 1]
-        out[u] = odd ? odd_case : even_case;
-    }
+__device__ __forceinline__ double ld_cum(const double* __restrict__ cum, int idx) {
+    return SMEM ? cum[idx] : __ldg(cum + idx);
 }
 
 // SPEC §3.3: move the trace position forward by dt seconds without downloading.
@@ -108,12 +91,12 @@ __device__ __forceinline__ double live_play(Sess& s, double& buffer, double& sta
 }
 
 // SPEC §3 for one session held in registers.  `q` must already be a valid index.
-// SMEM: s.rate points at the block's shared-memory copy of the trace row (else at the global table).
-// PREFETCH: fetch the following block while the current one is consumed (pays off when few warps are resident,
-// i.e. the fused episode on the global path; the per-step kernel hides the latency with occupancy instead).
+// SMEM: s.cum points at the block's shared-memory copy of the trace's C row (else at the global table).
+// CARRY: s.c_seg / s.c_seg1 / s.frac hold C[seg] / C[seg+1] / tau/I on entry and on exit (fused episode: the segment
+// a download ends in is the one the next download starts in, so the values are already in registers).
 // FAST: auto_reset is on (a session is never inert) — drops the done/inert bookkeeping.
 // LIVE: live-streaming semantics of SPEC §7 (pause gate before the download, start-up latch, playback speed).
-template <bool SMEM, bool PREFETCH, bool FAST = false, bool LIVE = false>
+template <bool SMEM, bool CARRY, bool FAST = false, bool LIVE = false>
 __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, StepRes& r, const bool want_thr) {
     const AbrParams& p = v.p;
     r.walk_error = false;
@@ -127,18 +110,13 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     }
     r.inert = false;
     const int A = v.A;
-    // all table reads of the step are issued up front so that their latency overlaps the walk
+    // all table reads of the step are issued up front so that their latency overlaps the search
     const double size = SMEM ? s.sizes[s.chunk * A + q] : __ldg(s.sizes + s.chunk * A + q);
     const double u = SMEM ? s.util[s.chunk * A + q] : __ldg(s.util + s.chunk * A + q);
     const double u_prev = s.last_q >= 0 ? (SMEM ? s.util[s.chunk * A + s.last_q] : __ldg(s.util + s.chunk * A + s.last_q))
                                         : u;
-    // 3.1 segment walk (Simulator.py:158-163 in closed form, with wrap-around).  A block of kWalkBlock segments
-    // is fetched with independent loads at constant offsets (no per-iteration address or wrap arithmetic); each
-    // whole-segment capacity rate*(I - 0) is an independent product, so only the running-total additions form a
-    // dependent chain — the same left-to-right additions as the segment-by-segment walk.  The one division
-    // happens after the loop has reconverged.
-    double sent = 0.0, tau = s.tau;
-    int seg = s.seg;                       // < T; the row padding makes seg + 2*kWalkBlock readable
+    double tau = s.tau;
+    int seg = s.seg;
     double live_buffer = s.buffer, live_rebuf = 0.0, live_idle = 0.0, live_startup = 0.0;
     if (LIVE) {   // 7.1 pause gate (Simulator.py:143-145): live edge, then room in the buffer
         const double w1 = max0(dsub(dmul((double)(s.chunk + 1), p.chunk_length), s.t_now));
@@ -151,81 +129,43 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         live_idle = dadd(w1, w2);
         if (live_idle > 0.0) advance_trace(seg, tau, live_idle, s.I, s.T);
     }
-    int guard = (1 << 20) / kWalkBlock;    // safety net only: every bandwidth is > 0, so the walk terminates
-    int k = 0;                             // segments left behind
-    const double* __restrict__ row = s.rate;
-    double cur[kWalkBlock];
-    double rate;
-    {
-        double head[kWalkBlock + 1];       // the current segment and the block after it, one round trip
-        load_rates<SMEM, kWalkBlock + 1>(row, seg, head);
-        rate = head[0];
-#pragma unroll
-        for (int u = 0; u < kWalkBlock; ++u) cur[u] = head[u + 1];
+    // 3.1 download against the cumulative capacity (Simulator.py:158-163 in closed form, with wrap-around)
+    const int T = s.T;
+    double c_seg = s.c_seg, c_seg1 = s.c_seg1, frac = s.frac;
+    if (!CARRY) {
+        c_seg = ld_cum<SMEM>(s.cum, seg);
+        c_seg1 = ld_cum<SMEM>(s.cum, seg + 1);
+        frac = s.inv_i != 0.0 ? dmul(tau, s.inv_i) : ddiv(tau, s.I);
     }
-    const double tau0 = tau;
-    const double room0 = dsub(s.I, tau0);
-    double s2 = dadd(sent, dmul(rate, room0));
-    const bool multi = !(s2 >= size);      // the current segment does not finish the chunk
-    double c[kWalkBlock];
-    if (multi) {
-        for (;;) {
-            double nxt[kWalkBlock];
-            if (PREFETCH) load_rates<SMEM, kWalkBlock>(row, seg + 1 + kWalkBlock, nxt);   // overlap with this block
-            c[0] = dadd(s2, dmul(cur[0], s.I));
-#pragma unroll
-            for (int u = 1; u < kWalkBlock; ++u) c[u] = dadd(c[u - 1], dmul(cur[u], s.I));
-            if (c[kWalkBlock - 1] >= size) break;   // the download ends inside this block (c, cur stay live)
-            // the whole block is consumed: capacities are > 0, so no earlier total reached `size` either
-            s2 = c[kWalkBlock - 1];
-            k += kWalkBlock;
-            seg += kWalkBlock;
-            if (seg >= s.T) seg -= s.T;   // the period is >= ABR_MIN_PERIOD > kWalkBlock
-            if (PREFETCH) {
-#pragma unroll
-                for (int u = 0; u < kWalkBlock; ++u) cur[u] = nxt[u];
-            } else {
-                load_rates<SMEM, kWalkBlock>(row, seg + 1, cur);
-            }
-            if (--guard <= 0) { r.walk_error = true; break; }
-        }
+    double target = dadd(dadd(c_seg, dmul(dsub(c_seg1, c_seg), frac)), size);
+    int n = 0;                                    // whole trace periods
+    int lo = seg;                                 // C[lo] <= target throughout
+    int step = (1 << (s.bits & 0xff)) >> 1;       // b_near probes reach every segment one download can cross
+    if (target >= s.P) {                          // rare: the download runs past the end of the trace period
+        do { target = dsub(target, s.P); ++n; } while (target >= s.P && n < kWrapGuard);
+        if (n >= kWrapGuard) { r.walk_error = true; target = 0.0; }
+        lo = 0;
+        step = (1 << ((s.bits >> 8) & 0xff)) >> 1;
     }
-    // every lane has reconverged here; lanes that walked pick the first u with c[u] >= size, once
-    double elapsed = 0.0;
-    if (multi) {
-        // c[] is non-decreasing and c[7] >= size: binary search for the first u with c[u] >= size (3 compares),
-        // then the total before that segment comes out of a 3-level select tree and its rate is re-read by index
-        static_assert(kWalkBlock == 8, "the selection tree below is written for blocks of 8 segments");
-        const bool h2 = !(c[3] >= size);
-        const double m1 = h2 ? c[5] : c[1];
-        const bool h1 = !(m1 >= size);
-        const double m0 = h2 ? (h1 ? c[6] : c[4]) : (h1 ? c[2] : c[0]);
-        const bool h0 = !(m0 >= size);
-        const int ustar = (h2 ? 4 : 0) + (h1 ? 2 : 0) + (h0 ? 1 : 0);
-        const double p01 = h0 ? c[0] : s2, p23 = h0 ? c[2] : c[1], p45 = h0 ? c[4] : c[3], p67 = h0 ? c[6] : c[5];
-        const double p03 = h1 ? p23 : p01, p47 = h1 ? p67 : p45;
-        sent = h2 ? p47 : p03;
-        if (SMEM) {
-            rate = row[seg + 1 + ustar];   // one LDS instead of a second select tree
-        } else {                           // a scattered global re-read would cost an L1 wavefront per lane
-            const double r01 = h0 ? cur[1] : cur[0], r23 = h0 ? cur[3] : cur[2];
-            const double r45 = h0 ? cur[5] : cur[4], r67 = h0 ? cur[7] : cur[6];
-            const double r03 = h1 ? r23 : r01, r47 = h1 ? r67 : r45;
-            rate = h2 ? r47 : r03;
-        }
-        k += ustar + 1;
-        seg += ustar + 1;
-        if (seg >= s.T) seg -= s.T;
-        tau = 0.0;
-        elapsed = dadd(room0, dmul((double)(k - 1), s.I));   // time spent in the k segments left behind
+    // largest j in [lo, T) with C[j] <= target: descending powers of two, every lane of the warp in lock step;
+    // a probe past the row is clamped to C[T] = P > target and fails
+    while (step > 0) {
+        const int idx = min(lo + step, T);
+        if (ld_cum<SMEM>(s.cum, idx) <= target) lo = idx;
+        step >>= 1;
     }
-    double delay;
-    {
-        const double dt = ddiv(dsub(size, sent), rate);
-        delay = dadd(elapsed, dt);
-        tau = dadd(tau, dt);
-    }
-    delay = dadd(delay, p.rtt);
+    const int j = lo;
+    const double c_j = ld_cum<SMEM>(s.cum, j);
+    const double c_j1 = ld_cum<SMEM>(s.cum, j + 1);
+    if (!(target < c_j1)) r.walk_error = true;   // insurance: the search width covered the download
+    const double phi = ddiv(dsub(target, c_j), dsub(c_j1, c_j));   // fraction of segment j consumed
+    const double tau_new = dmul(phi, s.I);
+    // k = (j - seg) + n*T segment boundaries crossed (an exact integer in fp64)
+    const double kd = dadd((double)(j - seg), dmul((double)n, (double)T));
+    double delay = dadd(max0(dadd(dmul(kd, s.I), dsub(tau_new, tau))), p.rtt);
+    seg = j;
+    tau = tau_new;
+    if (CARRY) { c_seg = c_j; c_seg1 = c_j1; frac = s.inv_i != 0.0 ? phi : ddiv(tau_new, s.I); }
     r.thr = want_thr ? ddiv(size, delay) : 0.0;
     double rebuf, buffer, sleep = 0.0;
     r.latency = 0.0;
@@ -248,7 +188,12 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
             const double inv_q = pow2_inverse(p.sleep_quantum);
             sleep = dmul(ceil(inv_q != 0.0 ? dmul(over, inv_q) : ddiv(over, p.sleep_quantum)), p.sleep_quantum);
             buffer = dsub(buffer, sleep);
-            advance_trace(seg, tau, sleep, s.I, s.T);
+            advance_trace(seg, tau, sleep, s.I, T);
+            if (CARRY) {
+                c_seg = ld_cum<SMEM>(s.cum, seg);
+                c_seg1 = ld_cum<SMEM>(s.cum, seg + 1);
+                frac = s.inv_i != 0.0 ? dmul(tau, s.inv_i) : ddiv(tau, s.I);
+            }
         }
     }
     // 3.4 reward
@@ -263,6 +208,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     s.seg = seg;
     s.tau = tau;
     s.buffer = buffer;
+    if (CARRY) { s.c_seg = c_seg; s.c_seg1 = c_seg1; s.frac = frac; }
     r.eov = (s.chunk >= v.V);
     if (r.eov) {
         if (FAST || p.auto_reset) {
@@ -299,11 +245,14 @@ __device__ __forceinline__ int policy_action(const EnvView& v, const Sess& s, in
 
 __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     const int tr = v.trace_id[i];
-    s.rate = v.trace_rate + (size_t)tr * rate_stride(v.T_rate);
+    s.cum = v.trace_cum + (size_t)tr * cum_stride(v.T_max);
     s.sizes = v.sizes;
     s.util = v.util;
     s.T = __ldg(v.trace_len + tr);
     s.I = __ldg(v.trace_interval + tr);
+    s.inv_i = pow2_inverse(s.I);
+    s.bits = __ldg(v.trace_bits + tr);
+    s.P = __ldg(s.cum + s.T);
     s.seg = v.seg[i];
     s.chunk = v.chunk[i];
     s.last_q = v.last_q[i];
@@ -313,16 +262,44 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     s.hist_len = v.p.track_history ? v.hist_len[i] : 0;
 }
 
-// Builds the rate table from the raw trace: the IEEE product bw*payload SPEC §3.1 forms per segment visit,
-// done once per environment.  Entries past a trace's end repeat it from its start (wrap-around).
+// Builds the per-trace tables of SPEC §3.1, one thread per trace (the accumulation is sequential by definition;
+// runs once per environment): C[0] = 0, C[j+1] = C[j] + (bw[j]*payload)*I, and the search widths b_full
+// (2^b_full >= T) and b_near (2^b_near - 1 >= 3 + max chunk size / smallest segment capacity, the most segment
+// boundaries a download that stays inside the period can cross).  bits = -1 flags a trace whose period capacity is
+// not a positive finite number or that holds a segment without capacity.
 __global__ void __launch_bounds__(kStepBlock)
-abr_trace_table_kernel(const double* __restrict__ bw, const int32_t* __restrict__ trace_len_raw, int n_traces, int T_max,
-                       int T_rate, double payload, double* __restrict__ rate) {
-    const int stride = rate_stride(T_rate);
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)n_traces * stride) return;
-    const int t = (int)(i / stride), j = (int)(i % stride);
-    rate[i] = dmul(bw[(size_t)t * T_max + j % trace_len_raw[t]], payload);
+abr_trace_table_kernel(EnvView v, double* __restrict__ cum, int32_t* __restrict__ bits) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= v.n_traces) return;
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    const int T = v.trace_len[t];
+    const double I = v.trace_interval[t];
+    const double* bw = v.trace_bw + (size_t)t * v.T_max;
+    double* c_row = cum + (size_t)t * cum_stride(v.T_max);
+    double size_max = 0.0;
+    for (int i = 0; i < v.V * v.A; ++i) size_max = fmax(size_max, v.sizes[i]);
+    double c = 0.0, mincap = kInf;
+    c_row[0] = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < T; ++j) {
+        const double c_next = dadd(c, dmul(dmul(bw[j], v.p.payload), I));
+        c_row[j + 1] = c_next;
+        mincap = fmin(mincap, dsub(c_next, c));   // the capacity the step sees: C[j+1] - C[j]
+        c = c_next;
+    }
+    for (int j = T + 1; j < cum_stride(v.T_max); ++j) c_row[j] = kInf;
+    int b_full = 0;
+    while ((1 << b_full) < T) ++b_full;
+    int b_near = b_full;
+    const double R = dadd(3.0, dmul(ddiv(size_max, mincap), 1.000000001));
+    if (R < (double)T) {
+        const int Ri = (int)R + 1;
+        b_near = 0;
+        while ((1 << b_near) - 1 < Ri) ++b_near;
+        if (b_near > b_full) b_near = b_full;
+    }
+    const bool ok = c > 0.0 && c < kInf && mincap > 0.0;
+    bits[t] = ok ? (b_near | (b_full << 8)) : -1;
 }
 
 __global__ void __launch_bounds__(kStepBlock)
@@ -436,6 +413,9 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     const int n = v.n;
     const bool hist = !FAST && v.p.track_history != 0;
     uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+    s.c_seg = ld_cum<SMEM>(s.cum, s.seg);
+    s.c_seg1 = ld_cum<SMEM>(s.cum, s.seg + 1);
+    s.frac = s.inv_i != 0.0 ? dmul(s.tau, s.inv_i) : ddiv(s.tau, s.I);
     for (int t = 0; t < steps; ++t) {
         int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t, actions_in, i, rnd);
         if (POLICY == ABR_POLICY_FIXED && (q < 0 || q >= v.A)) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
@@ -529,18 +509,18 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
     if (threadIdx.x == 0) s_tr0 = tr;            // thread 0 of a launched block is always a valid session
     __syncthreads();
     const int tr0 = s_tr0;
-    // block-uniform: every session of this block follows trace tr0 and its padded row fits
-    const int need = __ldg(v.trace_len + tr0) + ABR_WALK_PAD;   // <= rate_stride(T_rate), so the copy stays in the row
+    // block-uniform: every session of this block follows trace tr0 and its C row (T + 1 entries) fits
+    const int need = __ldg(v.trace_len + tr0) + 1;   // <= cum_stride(T_max), so the copy stays in the row
     const bool use_smem = __syncthreads_and((!valid || tr == tr0) ? 1 : 0) && need <= smem_doubles;
     if (use_smem) {
-        // Stage the trace row and the chunk-size / utility tables with TMA bulk copies (cp.async.bulk, SASS UBLKCP):
+        // Stage the trace's C row and the chunk-size / utility tables with TMA bulk copies (cp.async.bulk, SASS UBLKCP):
         // one elected thread issues three asynchronous global->shared copies that complete on an mbarrier, so the
         // 21 KB arrive without occupying the LSU or registers while the other threads finish loading their state.
-        // Rows start 16-byte aligned (rate_stride is even) and all byte counts are multiples of 16.
+        // Rows start 16-byte aligned (cum_stride is even) and all byte counts are multiples of 16.
         double* s_row = reinterpret_cast<double*>(s_row2);
         double* s_sizes = s_row + smem_doubles;
         double* s_util = s_sizes + v.V * v.A;
-        const double* g_row = v.trace_rate + (size_t)tr0 * rate_stride(v.T_rate);
+        const double* g_row = v.trace_cum + (size_t)tr0 * cum_stride(v.T_max);
         const uint32_t row_bytes = (uint32_t)((need + 1) / 2) * 16u;
         const uint32_t tab_bytes = (uint32_t)(v.V * v.A) * 8u;
         const bool tab_bulk = (tab_bytes & 15u) == 0;
@@ -568,7 +548,7 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
         if (!mbar_wait(mbar, 0u) && threadIdx.x == 0) atomicAdd(v.errors, 1ull);
         __syncthreads();
         if (valid) {
-            s.rate = s_row;
+            s.cum = s_row;
             s.sizes = s_sizes;
             s.util = s_util;
             rollout_session<POLICY, true, FAST>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
@@ -660,10 +640,8 @@ abr_qoe_cost_kernel(EnvView v, double* __restrict__ out) {
 
 }  // namespace
 
-cudaError_t launch_trace_table(const EnvView& v, double* d_rate, cudaStream_t st) {
-    const size_t n = (size_t)v.n_traces * rate_stride(v.T_rate);
-    abr_trace_table_kernel<<<(unsigned)((n + kStepBlock - 1) / kStepBlock), kStepBlock, 0, st>>>(
-        v.trace_bw, v.trace_len_raw, v.n_traces, v.T_max, v.T_rate, v.p.payload, d_rate);
+cudaError_t launch_trace_table(const EnvView& v, double* d_cum, int32_t* d_bits, cudaStream_t st) {
+    abr_trace_table_kernel<<<(v.n_traces + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_cum, d_bits);
     count_launch();
     return cudaGetLastError();
 }
@@ -699,8 +677,8 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     const dim3 grid((v.n + kRolloutBlock - 1) / kRolloutBlock), block(kRolloutBlock);
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
     RolloutOut o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out};
-    // shared-memory row buffer: the longest padded row when it leaves room for >= 7 blocks per SM, else disabled
-    int smem_doubles = rate_stride(v.T_rate);
+    // shared-memory row buffer: the longest C row when it leaves room for >= 7 blocks per SM, else disabled
+    int smem_doubles = cum_stride(v.T_max);
     size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double);
     if (smem_bytes > 32 * 1024) { smem_doubles = 0; smem_bytes = 0; }
     const bool fast = d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && !d_actions_out &&

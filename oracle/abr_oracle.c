@@ -16,6 +16,7 @@ struct OrcEnv {
     int n_traces, T_max, V, A, N, K;
     OrcParams p;
     double *trace_bw, *trace_interval, *sizes, *bitrates, *util;
+    double *cum /* [n_traces][T_max + 1], SPEC 3.1 */;
     int32_t* trace_len;
     /* session state, SoA (SPEC §1) */
     int32_t *seg, *chunk, *last_q, *trace_id, *hist_len, *err_len;
@@ -69,6 +70,18 @@ OrcEnv* orc_env_create(const double* trace_bw, const int32_t* trace_len, const d
     e->bitrates = (double*)dup_mem(bitrates, sizeof(double) * V * A);
     e->util = (double*)malloc(sizeof(double) * V * A);
     orc_utility_table(bitrates, V, A, p->utility_mode, p->utility_scale, e->util);
+    /* SPEC 3.1 table: C[0] = 0 ; C[j+1] = C[j] + (bw[j]*payload)*I, left to right */
+    e->cum = (double*)calloc((size_t)n_traces * (T_max + 1), 8);
+    for (int t = 0; t < n_traces; ++t) {
+        const double I = trace_interval[t];
+        double c = 0.0;
+        e->cum[(size_t)t * (T_max + 1)] = 0.0;
+        for (int j = 0; j < trace_len[t]; ++j) {
+            double r = trace_bw[(size_t)t * T_max + j] * p->payload;
+            c = c + r * I;
+            e->cum[(size_t)t * (T_max + 1) + j + 1] = c;
+        }
+    }
     e->seg = (int32_t*)calloc(N, 4); e->chunk = (int32_t*)calloc(N, 4); e->last_q = (int32_t*)calloc(N, 4);
     e->trace_id = (int32_t*)calloc(N, 4); e->hist_len = (int32_t*)calloc(N, 4); e->err_len = (int32_t*)calloc(N, 4);
     e->tau = (double*)calloc(N, 8); e->buffer = (double*)calloc(N, 8); e->last_pred = (double*)calloc(N, 8);
@@ -81,6 +94,7 @@ OrcEnv* orc_env_create(const double* trace_bw, const int32_t* trace_len, const d
 
 void orc_env_destroy(OrcEnv* e) {
     if (!e) return;
+    free(e->cum);
     free(e->trace_bw); free(e->trace_len); free(e->trace_interval); free(e->sizes); free(e->bitrates); free(e->util);
     free(e->seg); free(e->chunk); free(e->last_q); free(e->trace_id); free(e->hist_len); free(e->err_len);
     free(e->tau); free(e->buffer); free(e->last_pred); free(e->bw_hist); free(e->err_ring); free(e->done);
@@ -149,7 +163,6 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     const int tr = e->trace_id[s];
     const int T = e->trace_len[tr];
     const double I = e->trace_interval[tr];
-    const double* bw = e->trace_bw + (size_t)tr * e->T_max;
     int chunk = e->chunk[s], seg = e->seg[s];
     double tau = e->tau[s], buffer = e->buffer[s];
     const double size = e->sizes[chunk * e->A + q];
@@ -164,28 +177,29 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
         idle = w1 + w2;
         if (idle > 0.0) advance_trace(&seg, &tau, idle, I, T);
     }
-    /* 3.1 segment walk */
-    double sent = 0.0, delay;
-    int guard = 1 << 20;   /* safety net only: every bandwidth is > 0, so the walk terminates */
-    long long k = 0;       /* segments left behind */
-    const double room0 = I - tau;
-    double rate = bw[seg] * p->payload;
-    double cap = rate * room0;
-    for (;;) {
-        if (sent + cap >= size) break;
-        sent = sent + cap;
-        k += 1;
-        seg = (seg + 1 == T) ? 0 : seg + 1;
-        tau = 0.0;
-        rate = bw[seg] * p->payload;
-        cap = rate * I;
-        if (--guard <= 0) { e->errors++; break; }
-    }
+    /* 3.1 download against the cumulative capacity of the trace */
+    const double* C = e->cum + (size_t)tr * (e->T_max + 1);
+    const double P = C[T];
+    double delay;
     {
-        double dt = (size - sent) / rate;
-        tau = tau + dt;
-        double elapsed = (k == 0) ? 0.0 : room0 + (double)(k - 1) * I;
-        delay = (elapsed + dt) + p->rtt;
+        double pos = C[seg] + (C[seg + 1] - C[seg]) * (tau / I);
+        double target = pos + size;
+        long long n = 0;               /* whole trace periods */
+        while (target >= P) {
+            target = target - P;
+            n += 1;
+            if (n >= (1 << 20)) { e->errors++; target = 0.0; break; }   /* safety net only: P > 0 */
+        }
+        /* the largest j in [0, T) with C[j] <= target; C is non-decreasing and, without a wrap,
+         * C[seg] <= pos <= target, so the scan may start at seg */
+        int j = (n == 0) ? seg : 0;
+        while (j + 1 < T && C[j + 1] <= target) ++j;
+        double phi = (target - C[j]) / (C[j + 1] - C[j]);   /* fraction of segment j consumed */
+        double tau_new = phi * I;
+        long long k = (long long)(j - seg) + n * (long long)T;   /* segment boundaries crossed */
+        delay = max0((double)k * I + (tau_new - tau)) + p->rtt;
+        seg = j;
+        tau = tau_new;
     }
     double thr = size / delay;
     double sleep = 0.0;

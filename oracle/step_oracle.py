@@ -3,7 +3,10 @@
 Small cases only; used to cross-check oracle/abr_oracle.c and as the timed
 "reference-style" CPU port of the chunk step (the reference's own step loop,
 Simulator.py:93-210, does not run: SURVEY.md D1-D6).  Parity unpinned by the
-reference; SPEC.md is the contract.  Also holds ``euler_session`` — the
+reference; SPEC.md is the contract.  ``Session(..., walk="segments")`` replaces the
+cumulative-capacity form of SPEC §3.1 by the segment-by-segment integration it is the
+closed form of (the running sum restarts at the session's position instead of the start
+of the trace), which tests use to bound the difference (≪ 1e-9 relative).  Also holds ``euler_session`` — the
 intended fixed-dt dynamics of Simulator.py:135-208 restated for a loose
 plausibility check (|Δdelay| ≲ dt per chunk) against the analytic walk.
 """
@@ -13,8 +16,14 @@ import math
 
 
 class Session:
-    def __init__(self, bw, interval, sizes, util, P, start_offset=0.0):
+    def __init__(self, bw, interval, sizes, util, P, start_offset=0.0, walk="table"):
         self.bw, self.I, self.T = list(bw), float(interval), len(bw)
+        self.walk = walk
+        # SPEC 3.1 table: C[0] = 0 ; C[j+1] = C[j] + (bw[j]*payload)*I (left to right)
+        self.rate = [b * P["payload"] for b in self.bw]      # walk="segments" only
+        self.C = [0.0]
+        for r in self.rate:
+            self.C.append(self.C[-1] + r * self.I)
         self.sizes, self.util, self.P = sizes, util, P
         self.V, self.A = len(sizes), len(sizes[0])
         n = math.floor(start_offset / self.I)
@@ -60,6 +69,26 @@ class Session:
             self.tau = 0.0
             self.seg = (self.seg + 1) % self.T
 
+    def _download_segments(self, size):
+        """Segment-by-segment integration from the current position (not the SPEC's arithmetic: cross-check only)."""
+        sent = 0.0
+        k = 0
+        room0 = self.I - self.tau
+        rate = self.rate[self.seg]
+        cap = rate * room0
+        while True:
+            if sent + cap >= size:
+                break
+            sent = sent + cap
+            k += 1
+            self.seg = 0 if self.seg + 1 == self.T else self.seg + 1
+            self.tau = 0.0
+            rate = self.rate[self.seg]
+            cap = rate * self.I
+        dt = (size - sent) / rate
+        self.tau = self.tau + dt
+        return (0.0 if k == 0 else room0 + float(k - 1) * self.I) + dt
+
     def step(self, q, v=1.0):
         P = self.P
         if self.done:
@@ -79,24 +108,23 @@ class Session:
             idle = w1 + w2
             if idle > 0:
                 self._advance(idle)
-        sent = 0.0
-        k = 0
-        room0 = self.I - self.tau
-        rate = self.bw[self.seg] * P["payload"]
-        cap = rate * room0
-        while True:                                  # SPEC 3.1 (Simulator.py:158-163)
-            if sent + cap >= size:
-                break
-            sent = sent + cap
-            k += 1
-            self.seg = 0 if self.seg + 1 == self.T else self.seg + 1
-            self.tau = 0.0
-            rate = self.bw[self.seg] * P["payload"]
-            cap = rate * self.I
-        dt = (size - sent) / rate
-        self.tau = self.tau + dt
-        elapsed = 0.0 if k == 0 else room0 + float(k - 1) * self.I
-        delay = (elapsed + dt) + P["rtt"]
+        if self.walk == "segments":
+            delay = self._download_segments(size) + P["rtt"]
+        else:                                        # SPEC 3.1 (Simulator.py:158-163 in closed form)
+            C, T = self.C, self.T
+            target = (C[self.seg] + (C[self.seg + 1] - C[self.seg]) * (self.tau / self.I)) + size
+            n = 0
+            while target >= C[T]:
+                target = target - C[T]
+                n += 1
+            j = self.seg if n == 0 else 0
+            while j + 1 < T and C[j + 1] <= target:
+                j += 1
+            tau_new = ((target - C[j]) / (C[j + 1] - C[j])) * self.I
+            k = (j - self.seg) + n * T
+            dl = float(k) * self.I + (tau_new - self.tau)
+            delay = (dl if dl > 0 else 0.0) + P["rtt"]
+            self.seg, self.tau = j, tau_new
         thr = size / delay
         latency = 0.0
         if live:                                                              # SPEC 7.2

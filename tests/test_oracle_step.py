@@ -43,6 +43,32 @@ def test_c_step_equals_python_step(ragged):
     assert np.array_equal(env.field("chunk"), [p.chunk for p in py])
 
 
+@pytest.mark.parametrize("ragged", [False, True])
+def test_cumulative_capacity_walk_equals_segment_walk_within_1e9(ragged):
+    """SPEC §3.1 integrates against the trace's cumulative capacity C[j]; the segment-by-segment integration it is
+    the closed form of restarts its running sum at the session's position, so the two differ by rounding only —
+    far inside the 1e-9 relative bar of BASELINE.json (bounded here at 1e-11 of max(|x|, 1 s); rebuffer is a
+    difference of two such values, so only its absolute error is meaningful)."""
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=8, T=300, V=48, ragged=ragged)
+    P = dict(orc.DEFAULTS, max_buffer=20.0)
+    util = orc.utility_table(bitrates, 0, P["utility_scale"])
+    rng = np.random.default_rng(6)
+    worst = 0.0
+    for s in range(16):
+        tr = s % 8
+        off = float(rng.uniform(0, 400))
+        a = so.Session(bw[tr, :tl[tr]], ti[tr], sizes.tolist(), util.tolist(), P, off)
+        b = so.Session(bw[tr, :tl[tr]], ti[tr], sizes.tolist(), util.tolist(), P, off, walk="segments")
+        for t in range(120):
+            q = int(rng.integers(0, 6))
+            ra, rb = a.step(q), b.step(q)
+            for k in ("delay", "buffer", "rebuf", "reward", "sleep"):
+                worst = max(worst, abs(ra[k] - rb[k]) / max(abs(rb[k]), 1.0))
+            assert abs(ra["delay"] - rb["delay"]) <= 1e-10 * rb["delay"]
+            assert ra["eov"] == rb["eov"]
+    assert worst < 1e-11, worst
+
+
 def test_rollout_policies_and_acc():
     N, steps = 64, 48
     bitrates, sizes, bw, tl, ti = small_world(n_traces=4, T=64)
