@@ -200,7 +200,7 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     }
     CUDA_TRY(e->alloc(&v.seg, cap)); CUDA_TRY(e->alloc(&v.chunk, cap)); CUDA_TRY(e->alloc(&v.last_q, cap));
     CUDA_TRY(e->alloc(&v.trace_id, cap)); CUDA_TRY(e->alloc(&v.hist_len, cap)); CUDA_TRY(e->alloc(&v.err_len, cap));
-    CUDA_TRY(e->alloc(&v.done, cap)); CUDA_TRY(e->alloc(&v.tau, cap)); CUDA_TRY(e->alloc(&v.buffer, cap));
+    CUDA_TRY(e->alloc(&v.done, cap)); CUDA_TRY(e->alloc(&v.phi, cap)); CUDA_TRY(e->alloc(&v.buffer, cap));
     CUDA_TRY(e->alloc(&v.started, cap)); CUDA_TRY(e->alloc(&v.t_now, cap)); CUDA_TRY(e->alloc(&v.play_time, cap));
     CUDA_TRY(e->alloc(&v.bw_hist, cap * v.K)); CUDA_TRY(e->alloc(&v.last_pred, cap));
     CUDA_TRY(e->alloc(&v.err_ring, cap * v.K)); CUDA_TRY(e->alloc(&v.acc, cap * ABR_NUM_ACC));
@@ -338,7 +338,7 @@ int abr_env_state_ptr(AbrEnv* env, int field, void** d_ptr) {
         case ABR_F_HIST_LEN: *d_ptr = v.hist_len; break;
         case ABR_F_DONE: *d_ptr = v.done; break;
         case ABR_F_ERR_LEN: *d_ptr = v.err_len; break;
-        case ABR_F_TAU: *d_ptr = v.tau; break;
+        case ABR_F_PHASE: *d_ptr = v.phi; break;
         case ABR_F_BUFFER: *d_ptr = v.buffer; break;
         case ABR_F_BW_HIST: *d_ptr = v.bw_hist; break;
         case ABR_F_LAST_PRED: *d_ptr = v.last_pred; break;

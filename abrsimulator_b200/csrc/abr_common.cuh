@@ -74,7 +74,7 @@ struct EnvView {
     int32_t* seg; int32_t* chunk; int32_t* last_q; int32_t* trace_id; int32_t* hist_len; int32_t* err_len;
     uint8_t* done; uint8_t* started;
     double* t_now; double* play_time;            // live mode (SPEC §7)
-    double* tau; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
+    double* phi; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
     unsigned long long* errors;                 // device counter of flagged sessions
     int n_traces, T_max, V, A, K, cap, n;       // n = active sessions
     long long session_base;

@@ -37,12 +37,14 @@ constexpr int kStatsSessionsPerBlock = 1024;   // 64 blocks at 65 536 sessions: 
 constexpr int kWrapGuard = 1 << 20;            // safety net of the whole-period loop (SPEC §3.1)
 
 struct Sess {
-    const double* __restrict__ cum;   // C[0..T] of the session's trace: global row or its shared-memory copy
-    const double* __restrict__ sizes; // [V][A] chunk sizes and utilities: global tables or their shared-memory copies
+    const double* __restrict__ cum;   // C[0..T] of the session's trace (global row)
+    uint32_t cum_s, sizes_s, util_s;  // shared-memory addresses of the block's copies of the C row and of the
+                                      // sizes / utility tables (SMEM path)
+    const double* __restrict__ sizes; // [V][A] chunk sizes and utilities (global tables)
     const double* __restrict__ util;
-    double I, inv_i, tau, buffer;     // inv_i = 1/I when I is a power of two (then x/I == x*inv_i bit for bit), else 0
+    double I, phi, buffer;            // phi = fraction of segment `seg` already consumed (SPEC §1)
     double P;                         // C[T]: capacity of one trace period
-    double c_seg, c_seg1, frac;       // C[seg], C[seg+1], tau/I carried between the steps of a fused episode (CARRY)
+    double c_seg, c_seg1;             // C[seg], C[seg+1] carried between the steps of a fused episode (CARRY)
     int T, seg, chunk, last_q, hist_len, bits;
     bool done;
     // live mode (SPEC §7)
@@ -55,27 +57,49 @@ struct StepRes {
     bool eov, inert, walk_error, reset_mpc;
 };
 
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double x;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr));
+    return x;
+}
+
+// C row access by byte position.  SMEM: `pos` is an absolute shared-memory address (the row base is folded into the
+// position, so a probe is one VIADDMNMX + one LDS); else a byte offset into the global row.
 template <bool SMEM>
-__device__ __forceinline__ double ld_cum(const double* __restrict__ cum, int idx) {
-    return SMEM ? cum[idx] : __ldg(cum + idx);
+__device__ __forceinline__ double ld_cum(const Sess& s, uint32_t pos) {
+    return SMEM ? lds_f64(pos) : __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(s.cum) + pos));
+}
+
+// The table reads of one step (SPEC §3.1 size, §3.4 utilities).  They depend only on (chunk, q, last_q), so the fused
+// episode issues them one step ahead for the policies whose action does not depend on the state.
+struct Lookup { double size, u, u_prev; };
+
+template <bool SMEM>
+__device__ __forceinline__ Lookup lookup_tables(const Sess& s, const int A, const int V, const int chunk, const int q,
+                                                const int last_q) {
+    const int row = (chunk < V ? chunk : 0) * A;   // an inert session (chunk == V) reads row 0 and ignores it
+    Lookup k;
+    k.size = SMEM ? lds_f64(s.sizes_s + 8u * (uint32_t)(row + q)) : __ldg(s.sizes + row + q);
+    k.u = SMEM ? lds_f64(s.util_s + 8u * (uint32_t)(row + q)) : __ldg(s.util + row + q);
+    k.u_prev = last_q >= 0 ? (SMEM ? lds_f64(s.util_s + 8u * (uint32_t)(row + last_q)) : __ldg(s.util + row + last_q))
+                           : k.u;
+    return k;
 }
 
 // SPEC §3.3: move the trace position forward by dt seconds without downloading.
-__device__ __forceinline__ void advance_trace(int& seg, double& tau, const double dt, const double I, const int T) {
+__device__ __forceinline__ void advance_trace(int& seg, double& phi, const double dt, const double I, const int T) {
     // x / d == x * (1/d) bit for bit when d is a power of two (barring over/underflow, excluded by the range check in
     // pow2_inverse), which saves the division for the usual 0.5 s / 1 s intervals
-    const double x = dadd(tau, dt);
     const double inv_i = pow2_inverse(I);
-    const double n = floor(inv_i != 0.0 ? dmul(x, inv_i) : ddiv(x, I));
-    tau = dsub(x, dmul(n, I));
-    if (n < 2147480000.0) {   // 32-bit fast path; the modulo only runs when the position wraps
+    const double x = dadd(phi, inv_i != 0.0 ? dmul(dt, inv_i) : ddiv(dt, I));
+    const double n = floor(x);
+    phi = dsub(x, n);          // exact, in [0, 1)
+    if (n < 2147480000.0) {    // 32-bit fast path; the modulo only runs when the position wraps
         const unsigned tot = (unsigned)seg + (unsigned)(int)n;
         seg = tot >= (unsigned)T ? (int)(tot % (unsigned)T) : (int)tot;
     } else {
-        seg = (int)(((long long)seg + (long long)n) % (long long)T);
+        seg = (int)(((long long)seg + (long long)fmod(n, (double)T)) % (long long)T);
     }
-    if (tau < 0.0) tau = 0.0;
-    if (tau >= I) { tau = 0.0; seg = (seg + 1 == T) ? 0 : seg + 1; }
 }
 
 // SPEC §7 play(dt): playback during an interval; returns the stall time.
@@ -90,14 +114,33 @@ __device__ __forceinline__ double live_play(Sess& s, double& buffer, double& sta
     return stall;
 }
 
-// SPEC §3 for one session held in registers.  `q` must already be a valid index.
-// SMEM: s.cum points at the block's shared-memory copy of the trace's C row (else at the global table).
-// CARRY: s.c_seg / s.c_seg1 / s.frac hold C[seg] / C[seg+1] / tau/I on entry and on exit (fused episode: the segment
-// a download ends in is the one the next download starts in, so the values are already in registers).
+// Largest j in [lo, lo + 4^rounds) and [0, T) with C[j] <= target, given C[lo] <= target: descending powers of four,
+// three independent probes per round (half the dependent round trips of a binary search); every lane of a warp
+// runs the same number of rounds.  Positions are byte positions (see ld_cum); a probe past the row is clamped to
+// C[T] = P > target and fails.
+template <bool SMEM>
+__device__ __forceinline__ uint32_t search_cum(const Sess& s, uint32_t p_lo, const uint32_t p_end, int rounds,
+                                               const double target) {
+    uint32_t st = 8u << (2 * (rounds - 1));
+    for (; rounds > 0; --rounds, st >>= 2) {
+        const uint32_t p1 = min(p_lo + st, p_end), p2 = min(p_lo + 2 * st, p_end), p3 = min(p_lo + 3 * st, p_end);
+        const double c1 = ld_cum<SMEM>(s, p1), c2 = ld_cum<SMEM>(s, p2), c3 = ld_cum<SMEM>(s, p3);
+        if (c1 <= target) p_lo = p1;
+        if (c2 <= target) p_lo = p2;
+        if (c3 <= target) p_lo = p3;
+    }
+    return p_lo;
+}
+
+// SPEC §3 for one session held in registers.  `q` must already be a valid index; `lk` holds the step's table reads.
+// SMEM: the block's shared-memory copy of the trace's C row is used (else the global table).
+// CARRY: s.c_seg / s.c_seg1 hold C[seg] / C[seg+1] on entry and on exit (fused episode: the segment a download ends
+// in is the one the next download starts in, so the values are already in registers).
 // FAST: auto_reset is on (a session is never inert) — drops the done/inert bookkeeping.
 // LIVE: live-streaming semantics of SPEC §7 (pause gate before the download, start-up latch, playback speed).
 template <bool SMEM, bool CARRY, bool FAST = false, bool LIVE = false>
-__device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, StepRes& r, const bool want_thr) {
+__device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, const Lookup& lk, StepRes& r,
+                                          const bool want_thr) {
     const AbrParams& p = v.p;
     r.walk_error = false;
     r.reset_mpc = false;
@@ -109,13 +152,8 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         return;
     }
     r.inert = false;
-    const int A = v.A;
-    // all table reads of the step are issued up front so that their latency overlaps the search
-    const double size = SMEM ? s.sizes[s.chunk * A + q] : __ldg(s.sizes + s.chunk * A + q);
-    const double u = SMEM ? s.util[s.chunk * A + q] : __ldg(s.util + s.chunk * A + q);
-    const double u_prev = s.last_q >= 0 ? (SMEM ? s.util[s.chunk * A + s.last_q] : __ldg(s.util + s.chunk * A + s.last_q))
-                                        : u;
-    double tau = s.tau;
+    const double size = lk.size, u = lk.u, u_prev = lk.u_prev;
+    double phi = s.phi;
     int seg = s.seg;
     double live_buffer = s.buffer, live_rebuf = 0.0, live_idle = 0.0, live_startup = 0.0;
     if (LIVE) {   // 7.1 pause gate (Simulator.py:143-145): live edge, then room in the buffer
@@ -127,45 +165,38 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
                               : 0.0;
         live_rebuf = dadd(live_rebuf, live_play(s, live_buffer, live_startup, w2));
         live_idle = dadd(w1, w2);
-        if (live_idle > 0.0) advance_trace(seg, tau, live_idle, s.I, s.T);
+        if (live_idle > 0.0) advance_trace(seg, phi, live_idle, s.I, s.T);
     }
     // 3.1 download against the cumulative capacity (Simulator.py:158-163 in closed form, with wrap-around)
     const int T = s.T;
-    double c_seg = s.c_seg, c_seg1 = s.c_seg1, frac = s.frac;
+    const uint32_t p_base = SMEM ? s.cum_s : 0u;          // byte position of C[0]
+    const uint32_t p_end = p_base + 8u * (uint32_t)T;     // ... of C[T]
+    double c_seg = s.c_seg, c_seg1 = s.c_seg1;
     if (!CARRY) {
-        c_seg = ld_cum<SMEM>(s.cum, seg);
-        c_seg1 = ld_cum<SMEM>(s.cum, seg + 1);
-        frac = s.inv_i != 0.0 ? dmul(tau, s.inv_i) : ddiv(tau, s.I);
+        c_seg = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg);
+        c_seg1 = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg + 8u);
     }
-    double target = dadd(dadd(c_seg, dmul(dsub(c_seg1, c_seg), frac)), size);
-    int n = 0;                                    // whole trace periods
-    int lo = seg;                                 // C[lo] <= target throughout
-    int step = (1 << (s.bits & 0xff)) >> 1;       // b_near probes reach every segment one download can cross
-    if (target >= s.P) {                          // rare: the download runs past the end of the trace period
+    double target = dadd(dadd(c_seg, dmul(dsub(c_seg1, c_seg), phi)), size);
+    double kd;                                            // segment boundaries crossed: (j - seg) + n*T
+    uint32_t p_j;
+    if (target >= s.P) {   // rare: the download runs past the end of the trace period; n = whole periods
+        int n = 0;
         do { target = dsub(target, s.P); ++n; } while (target >= s.P && n < kWrapGuard);
         if (n >= kWrapGuard) { r.walk_error = true; target = 0.0; }
-        lo = 0;
-        step = (1 << ((s.bits >> 8) & 0xff)) >> 1;
+        p_j = search_cum<SMEM>(s, p_base, p_end, (((s.bits >> 8) & 0xff) + 1) >> 1, target);
+        kd = dadd((double)((int)((p_j - p_base) >> 3) - seg), dmul((double)n, (double)T));   // exact in fp64
+    } else {               // C[seg] <= target: b_near bits reach every segment one download can cross
+        p_j = search_cum<SMEM>(s, p_base + 8u * (uint32_t)seg, p_end, ((s.bits & 0xff) + 1) >> 1, target);
+        kd = (double)((int)((p_j - p_base) >> 3) - seg);
     }
-    // largest j in [lo, T) with C[j] <= target: descending powers of two, every lane of the warp in lock step;
-    // a probe past the row is clamped to C[T] = P > target and fails
-    while (step > 0) {
-        const int idx = min(lo + step, T);
-        if (ld_cum<SMEM>(s.cum, idx) <= target) lo = idx;
-        step >>= 1;
-    }
-    const int j = lo;
-    const double c_j = ld_cum<SMEM>(s.cum, j);
-    const double c_j1 = ld_cum<SMEM>(s.cum, j + 1);
+    const double c_j = ld_cum<SMEM>(s, p_j);
+    const double c_j1 = ld_cum<SMEM>(s, p_j + 8u);
     if (!(target < c_j1)) r.walk_error = true;   // insurance: the search width covered the download
-    const double phi = ddiv(dsub(target, c_j), dsub(c_j1, c_j));   // fraction of segment j consumed
-    const double tau_new = dmul(phi, s.I);
-    // k = (j - seg) + n*T segment boundaries crossed (an exact integer in fp64)
-    const double kd = dadd((double)(j - seg), dmul((double)n, (double)T));
-    double delay = dadd(max0(dadd(dmul(kd, s.I), dsub(tau_new, tau))), p.rtt);
-    seg = j;
-    tau = tau_new;
-    if (CARRY) { c_seg = c_j; c_seg1 = c_j1; frac = s.inv_i != 0.0 ? phi : ddiv(tau_new, s.I); }
+    const double phi_new = ddiv(dsub(target, c_j), dsub(c_j1, c_j));   // fraction of segment j consumed
+    double delay = dadd(max0(dmul(dadd(kd, dsub(phi_new, phi)), s.I)), p.rtt);
+    seg = (int)((p_j - p_base) >> 3);
+    phi = phi_new;
+    if (CARRY) { c_seg = c_j; c_seg1 = c_j1; }
     r.thr = want_thr ? ddiv(size, delay) : 0.0;
     double rebuf, buffer, sleep = 0.0;
     r.latency = 0.0;
@@ -188,11 +219,10 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
             const double inv_q = pow2_inverse(p.sleep_quantum);
             sleep = dmul(ceil(inv_q != 0.0 ? dmul(over, inv_q) : ddiv(over, p.sleep_quantum)), p.sleep_quantum);
             buffer = dsub(buffer, sleep);
-            advance_trace(seg, tau, sleep, s.I, T);
+            advance_trace(seg, phi, sleep, s.I, T);
             if (CARRY) {
-                c_seg = ld_cum<SMEM>(s.cum, seg);
-                c_seg1 = ld_cum<SMEM>(s.cum, seg + 1);
-                frac = s.inv_i != 0.0 ? dmul(tau, s.inv_i) : ddiv(tau, s.I);
+                c_seg = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg);
+                c_seg1 = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg + 8u);
             }
         }
     }
@@ -206,9 +236,9 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     s.last_q = q;
     s.chunk += 1;
     s.seg = seg;
-    s.tau = tau;
+    s.phi = phi;
     s.buffer = buffer;
-    if (CARRY) { s.c_seg = c_seg; s.c_seg1 = c_seg1; s.frac = frac; }
+    if (CARRY) { s.c_seg = c_seg; s.c_seg1 = c_seg1; }
     r.eov = (s.chunk >= v.V);
     if (r.eov) {
         if (FAST || p.auto_reset) {
@@ -250,13 +280,13 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     s.util = v.util;
     s.T = __ldg(v.trace_len + tr);
     s.I = __ldg(v.trace_interval + tr);
-    s.inv_i = pow2_inverse(s.I);
+    s.cum_s = s.sizes_s = s.util_s = 0u;
     s.bits = __ldg(v.trace_bits + tr);
     s.P = __ldg(s.cum + s.T);
     s.seg = v.seg[i];
     s.chunk = v.chunk[i];
     s.last_q = v.last_q[i];
-    s.tau = v.tau[i];
+    s.phi = v.phi[i];
     s.buffer = v.buffer[i];
     s.done = v.p.auto_reset ? false : (v.done[i] != 0);
     s.hist_len = v.p.track_history ? v.hist_len[i] : 0;
@@ -311,13 +341,12 @@ abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* 
     const int T = v.trace_len[tr];
     const double I = v.trace_interval[tr];
     const double off = start_offset ? start_offset[i] : 0.0;
-    const double n = floor(ddiv(off, I));
+    const double x = ddiv(off, I);
+    const double n = floor(x);
     int seg = (int)fmod(n, (double)T);
-    double tau = dsub(off, dmul(n, I));
-    if (tau < 0.0) tau = 0.0;
-    if (tau >= I) { tau = 0.0; seg = (seg + 1 == T) ? 0 : seg + 1; }
+    const double phi = dsub(x, n);   // exact, in [0, 1)
     if (seg < 0 || seg >= T) { atomicAdd(v.errors, 1ull); seg = 0; }
-    v.trace_id[i] = tr; v.seg[i] = seg; v.tau[i] = tau; v.buffer[i] = 0.0; v.chunk[i] = 0;
+    v.trace_id[i] = tr; v.seg[i] = seg; v.phi[i] = phi; v.buffer[i] = 0.0; v.chunk[i] = 0;
     v.last_q[i] = v.p.default_quality; v.done[i] = 0; v.hist_len[i] = 0; v.last_pred[i] = 0.0; v.err_len[i] = 0;
     v.t_now[i] = 0.0; v.play_time[i] = 0.0; v.started[i] = v.p.start_up_length <= 0.0 ? 1 : 0;
 #pragma unroll
@@ -348,16 +377,17 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     if (LIVE && !(s.speed > 0.0)) { bad = true; s.speed = 1.0; }
     if (bad) atomicAdd(v.errors, 1ull);
     StepRes r;
-    step_core<false, false, FAST, LIVE>(v, s, q, r, (!FAST && v.p.track_history) || o_thr != nullptr);
+    const Lookup lk = lookup_tables<false>(s, v.A, v.V, s.chunk, q, s.last_q);
+    step_core<false, false, FAST, LIVE>(v, s, q, lk, r, (!FAST && v.p.track_history) || o_thr != nullptr);
     if (r.walk_error) atomicAdd(v.errors, 1ull);
     if (FAST) {
-        v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
+        v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
         __stcs(o_delay + i, r.delay); __stcs(o_sleep + i, r.sleep); __stcs(o_buffer + i, r.buffer);
         __stcs(o_rebuf + i, r.rebuf); __stcs(o_reward + i, r.reward);
         o_eov[i] = r.eov ? 1 : 0;
     } else {
         if (!r.inert) {
-            v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
+            v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
             if (LIVE) { v.t_now[i] = s.t_now; v.play_time[i] = s.play_time; v.started[i] = s.started ? 1 : 0; }
             if (v.p.track_history) {
                 // ring slot of this sample = (hist_len before the step) mod K; after an auto-reset hist_len is 0
@@ -413,14 +443,26 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     const int n = v.n;
     const bool hist = !FAST && v.p.track_history != 0;
     uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
-    s.c_seg = ld_cum<SMEM>(s.cum, s.seg);
-    s.c_seg1 = ld_cum<SMEM>(s.cum, s.seg + 1);
-    s.frac = s.inv_i != 0.0 ? dmul(s.tau, s.inv_i) : ddiv(s.tau, s.I);
+    s.c_seg = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg);
+    s.c_seg1 = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg + 8u);
+    // the action and the table reads of a step are issued one step ahead when the policy does not look at the state
+    constexpr bool kAhead = POLICY != ABR_POLICY_BBA;
+    int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, 0, actions_in, i, rnd);
+    if (POLICY == ABR_POLICY_FIXED && (q < 0 || q >= v.A)) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
+    Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);
     for (int t = 0; t < steps; ++t) {
-        int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t, actions_in, i, rnd);
-        if (POLICY == ABR_POLICY_FIXED && (q < 0 || q >= v.A)) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
+        int q_next = 0;
+        Lookup lk_next = lk;
+        if (kAhead && t + 1 < steps) {
+            q_next = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t + 1, actions_in, i, rnd);
+            if (POLICY == ABR_POLICY_FIXED && (q_next < 0 || q_next >= v.A)) { flagged = true; q_next = q_next < 0 ? 0 : v.A - 1; }
+            // state the next step will see (SPEC §3.5): an end of video restarts at chunk 0 with the default quality
+            const bool wraps = s.chunk + 1 >= v.V;
+            const bool resets = wraps && (FAST || v.p.auto_reset);
+            lk_next = lookup_tables<SMEM>(s, v.A, v.V, wraps ? 0 : s.chunk + 1, q_next, resets ? v.p.default_quality : q);
+        }
         StepRes r;
-        step_core<SMEM, true, FAST>(v, s, q, r, hist);
+        step_core<SMEM, true, FAST>(v, s, q, lk, r, hist);
         flagged |= r.walk_error;
         const size_t ix = (size_t)t * n + i;
         if (FAST) {
@@ -446,9 +488,15 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
                 else v.bw_hist[(size_t)((s.hist_len - 1) % v.K) * v.cap + i] = r.thr;
             }
         }
+        if (!kAhead && t + 1 < steps) {
+            q_next = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t + 1, actions_in, i, rnd);
+            lk_next = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q_next, s.last_q);
+        }
+        q = q_next;
+        lk = lk_next;
     }
     if (flagged) atomicAdd(v.errors, 1ull);
-    v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.tau[i] = s.tau; v.buffer[i] = s.buffer;
+    v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
     if (hist) v.hist_len[i] = s.hist_len;
     if (reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
     if (!FAST && s.done) v.done[i] = 1;
@@ -548,9 +596,9 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
         if (!mbar_wait(mbar, 0u) && threadIdx.x == 0) atomicAdd(v.errors, 1ull);
         __syncthreads();
         if (valid) {
-            s.cum = s_row;
-            s.sizes = s_sizes;
-            s.util = s_util;
+            s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row);
+            s.sizes_s = (uint32_t)__cvta_generic_to_shared(s_sizes);
+            s.util_s = (uint32_t)__cvta_generic_to_shared(s_util);
             rollout_session<POLICY, true, FAST>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
         }
     } else if (valid) {

@@ -20,7 +20,7 @@ struct OrcEnv {
     int32_t* trace_len;
     /* session state, SoA (SPEC §1) */
     int32_t *seg, *chunk, *last_q, *trace_id, *hist_len, *err_len;
-    double *tau, *buffer, *bw_hist /* [N][K] ring */, *last_pred, *err_ring /* [N][K] */;
+    double *phi /* fraction of segment seg consumed */, *buffer, *bw_hist /* [N][K] ring */, *last_pred, *err_ring /* [N][K] */;
     double *t_now, *play_time;   /* live mode, SPEC §7 */
     uint8_t *done, *started;
     int errors;
@@ -84,7 +84,7 @@ OrcEnv* orc_env_create(const double* trace_bw, const int32_t* trace_len, const d
     }
     e->seg = (int32_t*)calloc(N, 4); e->chunk = (int32_t*)calloc(N, 4); e->last_q = (int32_t*)calloc(N, 4);
     e->trace_id = (int32_t*)calloc(N, 4); e->hist_len = (int32_t*)calloc(N, 4); e->err_len = (int32_t*)calloc(N, 4);
-    e->tau = (double*)calloc(N, 8); e->buffer = (double*)calloc(N, 8); e->last_pred = (double*)calloc(N, 8);
+    e->phi = (double*)calloc(N, 8); e->buffer = (double*)calloc(N, 8); e->last_pred = (double*)calloc(N, 8);
     e->bw_hist = (double*)calloc((size_t)N * e->K, 8); e->err_ring = (double*)calloc((size_t)N * e->K, 8);
     e->done = (uint8_t*)calloc(N, 1);
     e->started = (uint8_t*)calloc(N, 1);
@@ -97,7 +97,7 @@ void orc_env_destroy(OrcEnv* e) {
     free(e->cum);
     free(e->trace_bw); free(e->trace_len); free(e->trace_interval); free(e->sizes); free(e->bitrates); free(e->util);
     free(e->seg); free(e->chunk); free(e->last_q); free(e->trace_id); free(e->hist_len); free(e->err_len);
-    free(e->tau); free(e->buffer); free(e->last_pred); free(e->bw_hist); free(e->err_ring); free(e->done);
+    free(e->phi); free(e->buffer); free(e->last_pred); free(e->bw_hist); free(e->err_ring); free(e->done);
     free(e->started); free(e->t_now); free(e->play_time);
     free(e);
 }
@@ -106,7 +106,7 @@ const void* orc_env_field(OrcEnv* e, int f) {
     switch (f) {
         case 0: return e->seg; case 1: return e->chunk; case 2: return e->last_q; case 3: return e->trace_id;
         case 4: return e->hist_len; case 5: return e->done; case 6: return e->err_len;
-        case 10: return e->tau; case 11: return e->buffer; case 12: return e->bw_hist; case 13: return e->last_pred;
+        case 10: return e->phi; case 11: return e->buffer; case 12: return e->bw_hist; case 13: return e->last_pred;
         case 14: return e->err_ring; case 15: return e->util; case 16: return e->t_now; case 17: return e->play_time;
         case 7: return e->started;
     }
@@ -121,12 +121,11 @@ void orc_env_reset(OrcEnv* e, const int32_t* trace_id, const double* start_offse
         int T = e->trace_len[tr];
         double I = e->trace_interval[tr];
         double off = start_offset ? start_offset[s] : 0.0;
-        double n = floor(off / I);
+        double x = off / I;
+        double n = floor(x);
         int seg = (int)fmod(n, (double)T);
-        double tau = off - n * I;
-        if (tau < 0.0) tau = 0.0;
-        if (tau >= I) { tau = 0.0; seg = (seg + 1 == T) ? 0 : seg + 1; }
-        e->trace_id[s] = tr; e->seg[s] = seg; e->tau[s] = tau;
+        double phi = x - n;
+        e->trace_id[s] = tr; e->seg[s] = seg; e->phi[s] = phi;
         e->buffer[s] = 0.0; e->chunk[s] = 0; e->last_q[s] = e->p.default_quality; e->done[s] = 0;
         e->hist_len[s] = 0; e->last_pred[s] = 0.0; e->err_len[s] = 0;
         e->t_now[s] = 0.0; e->play_time[s] = 0.0; e->started[s] = e->p.start_up_length <= 0.0;
@@ -147,13 +146,11 @@ static double play(OrcEnv* e, int s, double dt, double v, double* buffer, double
     return stall;
 }
 
-static void advance_trace(int* seg, double* tau, double dt, double I, int T) {   /* SPEC §3.3 */
-    double x = *tau + dt;
-    double n = floor(x / I);
-    *tau = x - n * I;
-    *seg = (int)((*seg + (int64_t)n) % T);
-    if (*tau < 0.0) *tau = 0.0;
-    if (*tau >= I) { *tau = 0.0; *seg = (*seg + 1 == T) ? 0 : *seg + 1; }
+static void advance_trace(int* seg, double* phi, double dt, double I, int T) {   /* SPEC §3.3 */
+    double x = *phi + dt / I;
+    double n = floor(x);
+    *phi = x - n;
+    *seg = (int)((*seg + (int64_t)fmod(n, (double)T)) % T);
 }
 
 static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
@@ -164,7 +161,7 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     const int T = e->trace_len[tr];
     const double I = e->trace_interval[tr];
     int chunk = e->chunk[s], seg = e->seg[s];
-    double tau = e->tau[s], buffer = e->buffer[s];
+    double phi = e->phi[s], buffer = e->buffer[s];
     const double size = e->sizes[chunk * e->A + q];
     const int live = p->live != 0;
     double idle = 0.0, rebuf = 0.0, startup = 0.0, latency = 0.0;
@@ -175,14 +172,14 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
         double w2 = (e->started[s] && buffer > p->max_buffer) ? (buffer - p->max_buffer) / v : 0.0;
         rebuf = rebuf + play(e, s, w2, v, &buffer, &startup);
         idle = w1 + w2;
-        if (idle > 0.0) advance_trace(&seg, &tau, idle, I, T);
+        if (idle > 0.0) advance_trace(&seg, &phi, idle, I, T);
     }
     /* 3.1 download against the cumulative capacity of the trace */
     const double* C = e->cum + (size_t)tr * (e->T_max + 1);
     const double P = C[T];
     double delay;
     {
-        double pos = C[seg] + (C[seg + 1] - C[seg]) * (tau / I);
+        double pos = C[seg] + (C[seg + 1] - C[seg]) * phi;
         double target = pos + size;
         long long n = 0;               /* whole trace periods */
         while (target >= P) {
@@ -194,12 +191,11 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
          * C[seg] <= pos <= target, so the scan may start at seg */
         int j = (n == 0) ? seg : 0;
         while (j + 1 < T && C[j + 1] <= target) ++j;
-        double phi = (target - C[j]) / (C[j + 1] - C[j]);   /* fraction of segment j consumed */
-        double tau_new = phi * I;
+        double phi_new = (target - C[j]) / (C[j + 1] - C[j]);   /* fraction of segment j consumed */
         long long k = (long long)(j - seg) + n * (long long)T;   /* segment boundaries crossed */
-        delay = max0((double)k * I + (tau_new - tau)) + p->rtt;
+        delay = max0(((double)k + (phi_new - phi)) * I) + p->rtt;
         seg = j;
-        tau = tau_new;
+        phi = phi_new;
     }
     double thr = size / delay;
     double sleep = 0.0;
@@ -218,7 +214,7 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
         if (buffer > p->max_buffer) {
             sleep = ceil((buffer - p->max_buffer) / p->sleep_quantum) * p->sleep_quantum;
             buffer = buffer - sleep;
-            advance_trace(&seg, &tau, sleep, I, T);
+            advance_trace(&seg, &phi, sleep, I, T);
         }
     }
     /* 3.4 */
@@ -245,7 +241,7 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     } else if (o->eov) {
         e->done[s] = 1;
     }
-    e->chunk[s] = chunk; e->seg[s] = seg; e->tau[s] = tau; e->buffer[s] = buffer;
+    e->chunk[s] = chunk; e->seg[s] = seg; e->phi[s] = phi; e->buffer[s] = buffer;
 }
 
 void orc_env_step_live(OrcEnv* e, const int32_t* action, const double* speed, double* delay, double* sleep,

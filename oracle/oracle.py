@@ -163,7 +163,7 @@ class OracleEnv:
 
     def field(self, name):
         ids = dict(seg=(0, np.int32, 1), chunk=(1, np.int32, 1), last_q=(2, np.int32, 1), trace_id=(3, np.int32, 1),
-                   hist_len=(4, np.int32, 1), done=(5, np.uint8, 1), err_len=(6, np.int32, 1), tau=(10, np.float64, 1),
+                   hist_len=(4, np.int32, 1), done=(5, np.uint8, 1), err_len=(6, np.int32, 1), phase=(10, np.float64, 1),
                    buffer=(11, np.float64, 1), bw_hist=(12, np.float64, self.K), last_pred=(13, np.float64, 1),
                    err_ring=(14, np.float64, self.K), t_now=(16, np.float64, 1), play_time=(17, np.float64, 1),
                    started=(7, np.uint8, 1))

@@ -26,14 +26,10 @@ class Session:
             self.C.append(self.C[-1] + r * self.I)
         self.sizes, self.util, self.P = sizes, util, P
         self.V, self.A = len(sizes), len(sizes[0])
-        n = math.floor(start_offset / self.I)
+        x = start_offset / self.I
+        n = math.floor(x)
         self.seg = int(math.fmod(n, self.T))
-        self.tau = start_offset - n * self.I
-        if self.tau < 0.0:
-            self.tau = 0.0
-        if self.tau >= self.I:
-            self.tau = 0.0
-            self.seg = (self.seg + 1) % self.T
+        self.phi = x - n                      # fraction of segment seg already consumed (SPEC §1)
         self.buffer = 0.0
         self.chunk = 0
         self.last_q = P["default_quality"]
@@ -59,21 +55,17 @@ class Session:
         return stall
 
     def _advance(self, dt):
-        x = self.tau + dt
-        n = math.floor(x / self.I)
-        self.tau = x - n * self.I
+        x = self.phi + dt / self.I
+        n = math.floor(x)
+        self.phi = x - n
         self.seg = (self.seg + n) % self.T
-        if self.tau < 0.0:
-            self.tau = 0.0
-        if self.tau >= self.I:
-            self.tau = 0.0
-            self.seg = (self.seg + 1) % self.T
 
     def _download_segments(self, size):
         """Segment-by-segment integration from the current position (not the SPEC's arithmetic: cross-check only)."""
         sent = 0.0
         k = 0
-        room0 = self.I - self.tau
+        tau = self.phi * self.I
+        room0 = self.I - tau
         rate = self.rate[self.seg]
         cap = rate * room0
         while True:
@@ -82,11 +74,11 @@ class Session:
             sent = sent + cap
             k += 1
             self.seg = 0 if self.seg + 1 == self.T else self.seg + 1
-            self.tau = 0.0
+            tau = 0.0
             rate = self.rate[self.seg]
             cap = rate * self.I
         dt = (size - sent) / rate
-        self.tau = self.tau + dt
+        self.phi = (tau + dt) / self.I
         return (0.0 if k == 0 else room0 + float(k - 1) * self.I) + dt
 
     def step(self, q, v=1.0):
@@ -112,7 +104,7 @@ class Session:
             delay = self._download_segments(size) + P["rtt"]
         else:                                        # SPEC 3.1 (Simulator.py:158-163 in closed form)
             C, T = self.C, self.T
-            target = (C[self.seg] + (C[self.seg + 1] - C[self.seg]) * (self.tau / self.I)) + size
+            target = (C[self.seg] + (C[self.seg + 1] - C[self.seg]) * self.phi) + size
             n = 0
             while target >= C[T]:
                 target = target - C[T]
@@ -120,11 +112,11 @@ class Session:
             j = self.seg if n == 0 else 0
             while j + 1 < T and C[j + 1] <= target:
                 j += 1
-            tau_new = ((target - C[j]) / (C[j + 1] - C[j])) * self.I
+            phi_new = (target - C[j]) / (C[j + 1] - C[j])
             k = (j - self.seg) + n * T
-            dl = float(k) * self.I + (tau_new - self.tau)
+            dl = (float(k) + (phi_new - self.phi)) * self.I
             delay = (dl if dl > 0 else 0.0) + P["rtt"]
-            self.seg, self.tau = j, tau_new
+            self.seg, self.phi = j, phi_new
         thr = size / delay
         latency = 0.0
         if live:                                                              # SPEC 7.2
@@ -142,15 +134,7 @@ class Session:
         if not live and self.buffer > P["max_buffer"]:                        # SPEC 3.3
             sleep = math.ceil((self.buffer - P["max_buffer"]) / P["sleep_quantum"]) * P["sleep_quantum"]
             self.buffer = self.buffer - sleep
-            x = self.tau + sleep
-            n = math.floor(x / self.I)
-            self.tau = x - n * self.I
-            self.seg = (self.seg + n) % self.T
-            if self.tau < 0.0:
-                self.tau = 0.0
-            if self.tau >= self.I:
-                self.tau = 0.0
-                self.seg = (self.seg + 1) % self.T
+            self._advance(sleep)
         u = self.util[self.chunk][q]                                          # SPEC 3.4
         smooth = abs(u - self.util[self.chunk][self.last_q]) if self.last_q >= 0 else 0.0
         reward = (u - P["rebuf_penalty"] * rebuf) - P["smooth_penalty"] * smooth

@@ -21,7 +21,7 @@ from oracle import oracle as orc
 from helpers import small_world, assert_close, bits_equal
 
 STATE_I = ("seg", "chunk", "last_q", "trace_id")
-STATE_F = ("tau", "buffer")
+STATE_F = ("phase", "buffer")
 
 
 def make_pair(N, params=None, **world):

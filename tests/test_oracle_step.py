@@ -39,7 +39,7 @@ def test_c_step_equals_python_step(ragged):
                 assert c[k][s] == r[k], (t, s, k)
             assert c["eov"][s] == r["eov"]
     assert np.array_equal(env.field("seg"), [p.seg for p in py])
-    assert bits_equal(env.field("tau"), np.array([p.tau for p in py])) == 0
+    assert bits_equal(env.field("phase"), np.array([p.phi for p in py])) == 0
     assert np.array_equal(env.field("chunk"), [p.chunk for p in py])
 
 
