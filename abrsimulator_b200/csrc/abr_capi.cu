@@ -188,8 +188,10 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     int32_t* d_bits;
     CUDA_TRY(e->alloc(&d_cum, (size_t)n_traces * cum_stride(T_max)));
     CUDA_TRY(e->alloc(&d_bits, n_traces));
-    v.trace_cum = d_cum; v.trace_bits = d_bits;
-    CUDA_TRY(launch_trace_table(v, d_cum, d_bits, 0));
+    TraceMeta* d_meta;
+    CUDA_TRY(e->alloc(&d_meta, n_traces));
+    v.trace_cum = d_cum; v.trace_bits = d_bits; v.trace_meta = d_meta;
+    CUDA_TRY(launch_trace_table(v, d_cum, d_bits, d_meta, 0));
     {
         std::vector<int32_t> bits(n_traces);
         CUDA_TRY(cudaMemcpy(bits.data(), d_bits, sizeof(int32_t) * n_traces, cudaMemcpyDeviceToHost));

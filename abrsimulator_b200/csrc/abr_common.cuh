@@ -59,6 +59,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 // ---------------------------------------------------------------------------------------------
 // device-side view of an environment (passed by value to kernels)
 // ---------------------------------------------------------------------------------------------
+// What a step reads about its trace, packed so that it is one dependent 32-byte read after trace_id instead of
+// four scattered ones (interval, period capacity C[T], length, search widths).
+struct __align__(16) TraceMeta {
+    double I, P;
+    int32_t T, bits, pad0, pad1;
+};
+
 struct EnvView {
     // read-only tables
     const double* __restrict__ trace_bw;        // [n_traces][T_max]
@@ -66,6 +73,7 @@ struct EnvView {
                                                 // entries past C[T] are +inf
     const int32_t* __restrict__ trace_bits;     // [n_traces] search widths: bits 0-7 = b_near (2^b_near - 1 >= the most
                                                 // segments one download can cross), bits 8-15 = b_full (2^b_full >= T)
+    const TraceMeta* __restrict__ trace_meta;   // [n_traces] the per-trace scalars a step needs, one 32-byte record
     const int32_t* __restrict__ trace_len;      // [n_traces]
     const double* __restrict__ trace_interval;  // [n_traces]
     const double* __restrict__ sizes;           // [V][A]
@@ -82,7 +90,7 @@ struct EnvView {
 };
 
 // launchers implemented in abr_step.cu / abr_mpc.cu (C++ linkage, internal)
-cudaError_t launch_trace_table(const EnvView& v, double* d_cum, int32_t* d_bits, cudaStream_t st);
+cudaError_t launch_trace_table(const EnvView& v, double* d_cum, int32_t* d_bits, TraceMeta* d_meta, cudaStream_t st);
 cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st);
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
                         double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,

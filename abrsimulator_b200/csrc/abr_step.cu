@@ -31,6 +31,7 @@ namespace abr {
 namespace {
 
 constexpr int kStepBlock = 256;
+constexpr int kStepTiles = 4;       // tiles of kStepBlock sessions per block of the per-step kernel
 constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per SM (balanced over 148 SMs)
 constexpr int kStatsBlock = 256;
 constexpr int kStatsSessionsPerBlock = 1024;   // 64 blocks at 65 536 sessions: enough loads in flight to hide HBM latency
@@ -114,15 +115,40 @@ __device__ __forceinline__ double live_play(Sess& s, double& buffer, double& sta
     return stall;
 }
 
-// Largest j in [lo, lo + 4^rounds) and [0, T) with C[j] <= target, given C[lo] <= target: descending powers of four,
-// three independent probes per round (half the dependent round trips of a binary search); every lane of a warp
-// runs the same number of rounds.  Positions are byte positions (see ld_cum); a probe past the row is clamped to
-// C[T] = P > target and fails.
+// Largest j in [lo, lo + 2^bits) and [0, T) with C[j] <= target, given C[lo] <= target.  Radix-4 rounds (three
+// independent probes each: half the dependent round trips of a binary search), preceded by one radix-8 round when
+// `bits` is odd; every lane of a warp runs the same rounds.  Positions are byte positions (see ld_cum); a probe
+// past the row is clamped to C[T] = P > target and fails, so successful probes are never clamped.
 template <bool SMEM>
-__device__ __forceinline__ uint32_t search_cum(const Sess& s, uint32_t p_lo, const uint32_t p_end, int rounds,
+__device__ __forceinline__ uint32_t search_cum(const Sess& s, uint32_t p_lo, const uint32_t p_end, int bits,
                                                const double target) {
-    uint32_t st = 8u << (2 * (rounds - 1));
-    for (; rounds > 0; --rounds, st >>= 2) {
+    if (!SMEM) {   // global path: bound by L1 wavefronts (one per lane per scattered load) -> fewest probes: radix 2
+        for (; bits > 0; --bits) {
+            const uint32_t p1 = min(p_lo + (8u << (bits - 1)), p_end);
+            if (ld_cum<SMEM>(s, p1) <= target) p_lo = p1;
+        }
+        return p_lo;
+    }
+    if (bits & 1) {
+        if (bits >= 3) {
+            bits -= 3;
+            const uint32_t st = 8u << bits;
+            double c[7];
+#pragma unroll
+            for (int m = 0; m < 7; ++m) c[m] = ld_cum<SMEM>(s, min(p_lo + (uint32_t)(m + 1) * st, p_end));
+            // C is non-decreasing: the successful probes are the first `cnt` (three-input adds, depth 3)
+            const int b0 = c[0] <= target, b1 = c[1] <= target, b2 = c[2] <= target, b3 = c[3] <= target;
+            const int b4 = c[4] <= target, b5 = c[5] <= target, b6 = c[6] <= target;
+            const int cnt = (b0 + b1 + b2) + (b3 + b4 + b5) + b6;
+            p_lo += (uint32_t)cnt * st;
+        } else {
+            bits -= 1;
+            const uint32_t p1 = min(p_lo + 8u, p_end);
+            if (ld_cum<SMEM>(s, p1) <= target) p_lo = p1;
+        }
+    }
+    for (; bits > 0; bits -= 2) {
+        const uint32_t st = 8u << (bits - 2);
         const uint32_t p1 = min(p_lo + st, p_end), p2 = min(p_lo + 2 * st, p_end), p3 = min(p_lo + 3 * st, p_end);
         const double c1 = ld_cum<SMEM>(s, p1), c2 = ld_cum<SMEM>(s, p2), c3 = ld_cum<SMEM>(s, p3);
         if (c1 <= target) p_lo = p1;
@@ -177,18 +203,22 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         c_seg1 = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg + 8u);
     }
     double target = dadd(dadd(c_seg, dmul(dsub(c_seg1, c_seg), phi)), size);
-    double kd;                                            // segment boundaries crossed: (j - seg) + n*T
-    uint32_t p_j;
-    if (target >= s.P) {   // rare: the download runs past the end of the trace period; n = whole periods
-        int n = 0;
+    // without a wrap C[seg] <= target and b_near bits reach every segment one download can cross; a download that
+    // runs past the end of the trace period (rare per session, but one lane in ten warp-steps) restarts at C[0]
+    // with the full width b_full — same code, so the warp stays converged and only runs the longer search
+    uint32_t p_lo = p_base + 8u * (uint32_t)seg;
+    int bits = s.bits & 0xff;
+    double kd = (double)(-seg);                           // segment boundaries crossed: (j - seg) + n*T, j added below
+    if (target >= s.P) {
+        int n = 0;                                        // whole trace periods
         do { target = dsub(target, s.P); ++n; } while (target >= s.P && n < kWrapGuard);
         if (n >= kWrapGuard) { r.walk_error = true; target = 0.0; }
-        p_j = search_cum<SMEM>(s, p_base, p_end, (((s.bits >> 8) & 0xff) + 1) >> 1, target);
-        kd = dadd((double)((int)((p_j - p_base) >> 3) - seg), dmul((double)n, (double)T));   // exact in fp64
-    } else {               // C[seg] <= target: b_near bits reach every segment one download can cross
-        p_j = search_cum<SMEM>(s, p_base + 8u * (uint32_t)seg, p_end, ((s.bits & 0xff) + 1) >> 1, target);
-        kd = (double)((int)((p_j - p_base) >> 3) - seg);
+        p_lo = p_base;
+        bits = (s.bits >> 8) & 0xff;
+        kd = dadd(kd, dmul((double)n, (double)T));        // exact in fp64
     }
+    const uint32_t p_j = search_cum<SMEM>(s, p_lo, p_end, bits, target);
+    kd = dadd(kd, (double)(int)((p_j - p_base) >> 3));    // exact
     const double c_j = ld_cum<SMEM>(s, p_j);
     const double c_j1 = ld_cum<SMEM>(s, p_j + 8u);
     if (!(target < c_j1)) r.walk_error = true;   // insurance: the search width covered the download
@@ -251,22 +281,9 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     }
 }
 
-// SPEC §4.  The random policy draws one Philox4x32-10 block per four steps (counter = (session, step / 4)) and uses
-// word step % 4, so the generator costs a quarter of a call per step; `rnd` caches the block between steps.
-__device__ __forceinline__ int policy_action(const EnvView& v, const Sess& s, int policy, uint32_t seed_lo,
-                                             uint32_t seed_hi, unsigned long long gsession, int step,
-                                             const int32_t* __restrict__ actions_in, int sidx, uint4& rnd) {
+// SPEC §4, buffer-based policy on the pre-step buffer level.
+__device__ __forceinline__ int policy_bba(const EnvView& v, const double b) {
     const int A = v.A;
-    if (policy == ABR_POLICY_FIXED) return __ldg(actions_in + (size_t)step * v.n + sidx);
-    if (policy == ABR_POLICY_RANDOM) {
-        const int w = step & 3;
-        if (w == 0)
-            rnd = philox4x32_10((uint32_t)gsession, (uint32_t)(gsession >> 32), (uint32_t)(step >> 2), 0u, seed_lo,
-                                seed_hi);
-        const uint32_t x = w == 0 ? rnd.x : w == 1 ? rnd.y : w == 2 ? rnd.z : rnd.w;
-        return (int)__umulhi(x, (uint32_t)A);
-    }
-    const double b = s.buffer;  // BBA
     if (b < v.p.bba_reservoir) return 0;
     if (b >= dadd(v.p.bba_reservoir, v.p.bba_cushion)) return A - 1;
     const int q = (int)floor(ddiv(dmul((double)(A - 1), dsub(b, v.p.bba_reservoir)), v.p.bba_cushion));
@@ -278,11 +295,12 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
     s.cum = v.trace_cum + (size_t)tr * cum_stride(v.T_max);
     s.sizes = v.sizes;
     s.util = v.util;
-    s.T = __ldg(v.trace_len + tr);
-    s.I = __ldg(v.trace_interval + tr);
+    {   // one 32-byte record: two 16-byte read-only loads from the same sector
+        const double2 ip = __ldg(reinterpret_cast<const double2*>(v.trace_meta + tr));
+        const int4 tb = __ldg(reinterpret_cast<const int4*>(v.trace_meta + tr) + 1);
+        s.I = ip.x; s.P = ip.y; s.T = tb.x; s.bits = tb.y;
+    }
     s.cum_s = s.sizes_s = s.util_s = 0u;
-    s.bits = __ldg(v.trace_bits + tr);
-    s.P = __ldg(s.cum + s.T);
     s.seg = v.seg[i];
     s.chunk = v.chunk[i];
     s.last_q = v.last_q[i];
@@ -298,7 +316,7 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
 // boundaries a download that stays inside the period can cross).  bits = -1 flags a trace whose period capacity is
 // not a positive finite number or that holds a segment without capacity.
 __global__ void __launch_bounds__(kStepBlock)
-abr_trace_table_kernel(EnvView v, double* __restrict__ cum, int32_t* __restrict__ bits) {
+abr_trace_table_kernel(EnvView v, double* __restrict__ cum, int32_t* __restrict__ bits, TraceMeta* __restrict__ meta) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= v.n_traces) return;
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
@@ -330,6 +348,9 @@ abr_trace_table_kernel(EnvView v, double* __restrict__ cum, int32_t* __restrict_
     }
     const bool ok = c > 0.0 && c < kInf && mincap > 0.0;
     bits[t] = ok ? (b_near | (b_full << 8)) : -1;
+    TraceMeta m;
+    m.I = I; m.P = c; m.T = T; m.bits = b_near | (b_full << 8); m.pad0 = m.pad1 = 0;
+    meta[t] = m;
 }
 
 __global__ void __launch_bounds__(kStepBlock)
@@ -353,20 +374,37 @@ abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* 
     for (int j = 0; j < ABR_NUM_ACC; ++j) v.acc[(size_t)j * v.cap + i] = 0.0;
 }
 
-// <= 64 registers: 4 blocks of 256 threads per SM; the kernel is latency/LSU-bound and lives on occupancy.
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (byte count multiple of 16, both addresses
+// 16-byte aligned).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint32_t mbar) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(gmem_src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// Wait for the given phase of an mbarrier (try_wait suspends the thread for a bounded, implementation-defined time
+// per call).  The retry count is bounded so that a programming error cannot hang the GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
+    for (int spins = 0; spins < (1 << 16); ++spins) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
+// One chunk step of one session with the state in HBM (SPEC §3, §7).
 // FAST: the five f64 outputs and end_of_video requested, no throughput history / accumulators, auto_reset on —
 // compiled without the null checks and the inert/history/accumulator bookkeeping (next_sizes and throughput stay
 // optional in both variants).
-template <bool FAST, bool LIVE>
-__global__ void __launch_bounds__(kStepBlock, 4)
-abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __restrict__ speed,
-                double* __restrict__ o_delay, double* __restrict__ o_sleep, double* __restrict__ o_buffer,
-                double* __restrict__ o_rebuf, double* __restrict__ o_reward, double* __restrict__ o_latency,
-                double* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov, double* __restrict__ o_thr) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.n) return;
-    Sess s;
-    load_sess(v, i, s);
+template <bool SMEM, bool FAST, bool LIVE>
+__device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const int i, const int32_t* __restrict__ action,
+                                             const double* __restrict__ speed, double* __restrict__ o_delay,
+                                             double* __restrict__ o_sleep, double* __restrict__ o_buffer,
+                                             double* __restrict__ o_rebuf, double* __restrict__ o_reward,
+                                             double* __restrict__ o_latency, double* __restrict__ o_next_sizes,
+                                             uint8_t* __restrict__ o_eov, double* __restrict__ o_thr) {
     if (LIVE) {
         s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0;
         s.speed = speed ? speed[i] : 1.0;
@@ -378,7 +416,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     if (bad) atomicAdd(v.errors, 1ull);
     StepRes r;
     const Lookup lk = lookup_tables<false>(s, v.A, v.V, s.chunk, q, s.last_q);
-    step_core<false, false, FAST, LIVE>(v, s, q, lk, r, (!FAST && v.p.track_history) || o_thr != nullptr);
+    step_core<SMEM, false, FAST, LIVE>(v, s, q, lk, r, (!FAST && v.p.track_history) || o_thr != nullptr);
     if (r.walk_error) atomicAdd(v.errors, 1ull);
     if (FAST) {
         v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
@@ -424,6 +462,75 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     }
 }
 
+// <= 64 registers: 4 blocks of 256 threads per SM.  A block walks kStepTiles consecutive tiles of 256 sessions.
+// When all sessions of a tile follow the same trace (callers that keep sessions sorted by trace) and its C row fits
+// in `smem_doubles`, the block stages the row with one TMA bulk copy — once, for as long as the following tiles stay
+// on that trace — and the search probes are LDS; a per-lane scattered global load costs one L1 wavefront per lane,
+// which is what bounds the global path (ncu: l1tex__data_pipe_lsu_wavefronts).
+template <bool FAST, bool LIVE>
+__global__ void __launch_bounds__(kStepBlock, LIVE ? 3 : 4)
+abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __restrict__ speed,
+                double* __restrict__ o_delay, double* __restrict__ o_sleep, double* __restrict__ o_buffer,
+                double* __restrict__ o_rebuf, double* __restrict__ o_reward, double* __restrict__ o_latency,
+                double* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov, double* __restrict__ o_thr,
+                int smem_doubles) {
+    extern __shared__ __align__(16) double2 s_row2[];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ int s_tr0;
+#define ABR_STEP_SESSION_ARGS v, s, i, action, speed, o_delay, o_sleep, o_buffer, o_rebuf, o_reward, o_latency, o_next_sizes, o_eov, o_thr
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (smem_doubles != 0) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    uint32_t parity = 0u;                        // phase of the next staging copy (block-uniform)
+    int staged = -1;                             // trace whose C row the buffer holds (block-uniform, kept per thread)
+    for (int k = 0; k < kStepTiles; ++k) {
+        const int tile0 = (blockIdx.x * kStepTiles + k) * kStepBlock;
+        if (tile0 >= v.n) break;                 // block-uniform
+        const int i = tile0 + threadIdx.x;
+        const bool valid = i < v.n;
+        Sess s;
+        int tr = -1;
+        if (valid) { load_sess(v, i, s); tr = v.trace_id[i]; }
+        if (smem_doubles == 0) {                 // launch-uniform: no shared-memory row buffer
+            if (valid) step_session<false, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
+            continue;
+        }
+        // also the barrier that ends the previous tile's reads of the row buffer
+        bool use_smem = __syncthreads_and((!valid || tr == staged) ? 1 : 0) != 0;
+        if (!use_smem) {                         // block-uniform: first tile, or the trace changed
+            if (threadIdx.x == 0) s_tr0 = tr;    // thread 0 of a tile is always a valid session
+            __syncthreads();
+            const int tr0 = s_tr0;
+            const int need = __ldg(&v.trace_meta[tr0].T) + 1;
+            use_smem = __syncthreads_and((!valid || tr == tr0) ? 1 : 0) != 0 && need <= smem_doubles;
+            if (use_smem) {
+                if (threadIdx.x == 0) {
+                    const uint32_t row_bytes = (uint32_t)((need + 1) / 2) * 16u;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(row_bytes) : "memory");
+                    bulk_g2s(s_row2, v.trace_cum + (size_t)tr0 * cum_stride(v.T_max), row_bytes, mbar);
+                }
+                if (!mbar_wait(mbar, parity) && threadIdx.x == 0) atomicAdd(v.errors, 1ull);
+                parity ^= 1u;
+            }
+            staged = use_smem ? tr0 : -1;
+        }
+        if (use_smem) {
+            if (valid) {
+                s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row2);
+                step_session<true, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
+            }
+        } else if (valid) {
+            step_session<false, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
+        }
+    }
+#undef ABR_STEP_SESSION_ARGS
+}
+
 struct RolloutOut {
     double* __restrict__ delay; double* __restrict__ sleep; double* __restrict__ buffer; double* __restrict__ rebuf;
     double* __restrict__ reward; uint8_t* __restrict__ eov; int32_t* __restrict__ actions;
@@ -438,24 +545,42 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
                                                 const int32_t* __restrict__ actions_in, const RolloutOut& o,
                                                 double (&acc_new)[ABR_NUM_ACC]) {
     const unsigned long long gsession = (unsigned long long)(v.session_base + i);
-    double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_steps = 0.0, a_eps = 0.0;
+    double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0;
+    int n_steps = 0, n_eps = 0;
     bool flagged = false, reset_mpc = false;
     const int n = v.n;
     const bool hist = !FAST && v.p.track_history != 0;
-    uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t packed = 0u;   // random policy: the four actions of one Philox block, one per byte
     s.c_seg = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg);
     s.c_seg1 = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg + 8u);
+    // SPEC §4 action of step t; must be called with increasing t.  FIXED clamps t to the last row so that the
+    // one-step-ahead call after the final step stays inside the caller's table.
+    auto action_at = [&](const int t) -> int {
+        if (POLICY == ABR_POLICY_FIXED) {
+            int a = __ldg(actions_in + (size_t)(t < steps ? t : steps - 1) * n + i);
+            if (a < 0 || a >= v.A) { flagged = true; a = a < 0 ? 0 : v.A - 1; }
+            return a;
+        }
+        if (POLICY == ABR_POLICY_RANDOM) {
+            if ((t & 3) == 0) {   // one Philox block per four steps (counter = (session, t / 4)), word t % 4
+                const uint4 r = philox4x32_10((uint32_t)gsession, (uint32_t)(gsession >> 32), (uint32_t)(t >> 2), 0u,
+                                              seed_lo, seed_hi);
+                const uint32_t A = (uint32_t)v.A;   // <= 16: an action fits a byte
+                packed = __umulhi(r.x, A) | (__umulhi(r.y, A) << 8) | (__umulhi(r.z, A) << 16) | (__umulhi(r.w, A) << 24);
+            }
+            return (int)((packed >> (8 * (t & 3))) & 0xffu);
+        }
+        return policy_bba(v, s.buffer);
+    };
     // the action and the table reads of a step are issued one step ahead when the policy does not look at the state
     constexpr bool kAhead = POLICY != ABR_POLICY_BBA;
-    int q = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, 0, actions_in, i, rnd);
-    if (POLICY == ABR_POLICY_FIXED && (q < 0 || q >= v.A)) { flagged = true; q = q < 0 ? 0 : v.A - 1; }
+    int q = action_at(0);
     Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);
     for (int t = 0; t < steps; ++t) {
         int q_next = 0;
-        Lookup lk_next = lk;
-        if (kAhead && t + 1 < steps) {
-            q_next = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t + 1, actions_in, i, rnd);
-            if (POLICY == ABR_POLICY_FIXED && (q_next < 0 || q_next >= v.A)) { flagged = true; q_next = q_next < 0 ? 0 : v.A - 1; }
+        Lookup lk_next;
+        if (kAhead) {   // also after the last step (its result is unused): no branch, no select on the loaded values
+            q_next = action_at(t + 1);
             // state the next step will see (SPEC §3.5): an end of video restarts at chunk 0 with the default quality
             const bool wraps = s.chunk + 1 >= v.V;
             const bool resets = wraps && (FAST || v.p.auto_reset);
@@ -481,20 +606,21 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         if (FAST || !r.inert) {
             a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
             a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
-            a_steps += 1.0;
-            if (r.eov) a_eps += 1.0;
+            n_steps += 1;
+            n_eps += r.eov ? 1 : 0;
             if (hist) {
                 if (r.reset_mpc) reset_mpc = true;
                 else v.bw_hist[(size_t)((s.hist_len - 1) % v.K) * v.cap + i] = r.thr;
             }
         }
-        if (!kAhead && t + 1 < steps) {
-            q_next = policy_action(v, s, POLICY, seed_lo, seed_hi, gsession, t + 1, actions_in, i, rnd);
+        if (!kAhead) {
+            q_next = action_at(t + 1);
             lk_next = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q_next, s.last_q);
         }
         q = q_next;
         lk = lk_next;
     }
+    const double a_steps = (double)n_steps, a_eps = (double)n_eps;   // exact: counts below 2^31
     if (flagged) atomicAdd(v.errors, 1ull);
     v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
     if (hist) v.hist_len[i] = s.hist_len;
@@ -512,26 +638,6 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         acc_new[j] = dadd(old[j], add[j]);
         a[j * c] = acc_new[j];
     }
-}
-
-// TMA bulk copy global -> shared, completion signalled on an mbarrier (byte count multiple of 16, both addresses
-// 16-byte aligned).
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint32_t mbar) {
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(gmem_src), "r"(bytes), "r"(mbar) : "memory");
-}
-
-// Wait for the given phase of an mbarrier (try_wait suspends the thread for a bounded, implementation-defined time
-// per call).  The retry count is bounded so that a programming error cannot hang the GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
-    for (int spins = 0; spins < (1 << 16); ++spins) {
-        uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-        if (done) return true;
-    }
-    return false;
 }
 
 // smem_doubles: capacity of the dynamic shared-memory row buffer (0 disables the shared-memory path); the buffer
@@ -599,6 +705,9 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
             s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row);
             s.sizes_s = (uint32_t)__cvta_generic_to_shared(s_sizes);
             s.util_s = (uint32_t)__cvta_generic_to_shared(s_util);
+            // keep the three addresses in registers: left alone, the compiler rematerialises them from
+            // SR_CgaCtaId (an S2R round trip) at every use inside the step loop
+            asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s));
             rollout_session<POLICY, true, FAST>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
         }
     } else if (valid) {
@@ -688,8 +797,8 @@ abr_qoe_cost_kernel(EnvView v, double* __restrict__ out) {
 
 }  // namespace
 
-cudaError_t launch_trace_table(const EnvView& v, double* d_cum, int32_t* d_bits, cudaStream_t st) {
-    abr_trace_table_kernel<<<(v.n_traces + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_cum, d_bits);
+cudaError_t launch_trace_table(const EnvView& v, double* d_cum, int32_t* d_bits, TraceMeta* d_meta, cudaStream_t st) {
+    abr_trace_table_kernel<<<(v.n_traces + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_cum, d_bits, d_meta);
     count_launch();
     return cudaGetLastError();
 }
@@ -708,11 +817,15 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
     const bool live = v.p.live != 0;
     const bool fast = !live && d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov &&
                       v.p.track_history == 0 && v.p.track_acc == 0 && v.p.auto_reset != 0;
-    const unsigned grid = (v.n + kStepBlock - 1) / kStepBlock;
-#define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr
-    if (live) abr_step_kernel<false, true><<<grid, kStepBlock, 0, st>>>(ABR_STEP_ARGS);
-    else if (fast) abr_step_kernel<true, false><<<grid, kStepBlock, 0, st>>>(ABR_STEP_ARGS);
-    else abr_step_kernel<false, false><<<grid, kStepBlock, 0, st>>>(ABR_STEP_ARGS);
+    const unsigned grid = (v.n + kStepBlock * kStepTiles - 1) / (kStepBlock * kStepTiles);
+    // shared-memory row buffer for blocks whose sessions share a trace (48 KB: no opt-in needed, 4 blocks per SM)
+    int smem_doubles = cum_stride(v.T_max);
+    size_t smem_bytes = (size_t)smem_doubles * sizeof(double);
+    if (smem_bytes > 48 * 1024) { smem_doubles = 0; smem_bytes = 0; }
+#define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr, smem_doubles
+    if (live) abr_step_kernel<false, true><<<grid, kStepBlock, smem_bytes, st>>>(ABR_STEP_ARGS);
+    else if (fast) abr_step_kernel<true, false><<<grid, kStepBlock, smem_bytes, st>>>(ABR_STEP_ARGS);
+    else abr_step_kernel<false, false><<<grid, kStepBlock, smem_bytes, st>>>(ABR_STEP_ARGS);
 #undef ABR_STEP_ARGS
     count_launch();
     return cudaGetLastError();

@@ -157,6 +157,38 @@ def test_fused_rollout_shared_memory_trace_path(ragged):
     assert env.error_count() == 0
 
 
+@pytest.mark.parametrize("ragged", [False, True])
+@pytest.mark.parametrize("fast", [False, True])
+def test_step_kernel_shared_memory_trace_path(ragged, fast):
+    """Per-step kernel: a block walks four consecutive tiles of 256 sessions; tiles on one trace use the staged
+    capacity row (restaged when the trace changes between tiles), mixed tiles and the partial last tile included."""
+    N, steps = 256 * 11 + 100, 30
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=9, T=400, ragged=ragged)
+    params = dict(track_history=0 if fast else 1, track_acc=0 if fast else 1)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, **params)
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **params)
+    rng = np.random.default_rng(5)
+    tid = ((np.arange(N) // 512) % 9).astype(np.int32)             # two tiles per trace: a restage inside a block
+    tid[256 * 5:256 * 6] = rng.integers(0, 9, size=256)            # one mixed tile -> global path, then staged again
+    tid[256 * 8:256 * 9 + 7] = 3                                   # a trace change in the middle of a tile
+    off = rng.uniform(0, 1200.0, size=N)
+    env.reset(tid, off)
+    ref.reset(tid, off)
+    acc = np.zeros((orc.NUM_ACC, N))
+    for t in range(steps):
+        a = rng.integers(0, env.A, size=N).astype(np.int32)
+        got = env.step(a)
+        exp = ref.step(a, acc=acc)
+        for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                         ("reward", "reward")):
+            assert_close(getattr(got, k_g).cpu().numpy(), exp[k_c], f"{k_g}@{t}")
+        assert np.array_equal(got.end_of_video.cpu().numpy(), exp["eov"])
+    check_state(env, ref)
+    if not fast:
+        assert_close(env.session_acc().cpu().numpy(), acc, "acc")
+    assert env.error_count() == 0
+
+
 @pytest.mark.parametrize("policy", ["random", "bba", "fixed"])
 def test_fast_variant_of_the_fused_kernel(policy):
     """All six trajectory outputs, no action trace, no history, auto_reset on selects the kernel variant compiled
