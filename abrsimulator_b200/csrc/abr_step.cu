@@ -31,7 +31,7 @@ namespace abr {
 namespace {
 
 constexpr int kStepBlock = 256;
-constexpr int kStepTiles = 4;       // tiles of kStepBlock sessions per block of the per-step kernel
+constexpr int kStepTiles = 8;       // tiles of kStepBlock sessions per block of the per-step kernel
 constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per SM (balanced over 148 SMs)
 constexpr int kStatsBlock = 256;
 constexpr int kStatsSessionsPerBlock = 1024;   // 64 blocks at 65 536 sessions: enough loads in flight to hide HBM latency
@@ -290,8 +290,18 @@ __device__ __forceinline__ int policy_bba(const EnvView& v, const double b) {
     return q > A - 1 ? A - 1 : q;
 }
 
-__device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
-    const int tr = v.trace_id[i];
+// The per-session words of a step that come straight from the SoA state (coalesced: thread i <-> session i).
+struct RawState { int tr, seg, chunk, last_q; double phi, buffer; };
+
+__device__ __forceinline__ RawState load_raw(const EnvView& v, int i) {
+    RawState w;
+    w.tr = v.trace_id[i]; w.seg = v.seg[i]; w.chunk = v.chunk[i]; w.last_q = v.last_q[i];
+    w.phi = v.phi[i]; w.buffer = v.buffer[i];
+    return w;
+}
+
+__device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawState& w, Sess& s) {
+    const int tr = w.tr;
     s.cum = v.trace_cum + (size_t)tr * cum_stride(v.T_max);
     s.sizes = v.sizes;
     s.util = v.util;
@@ -301,13 +311,18 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
         s.I = ip.x; s.P = ip.y; s.T = tb.x; s.bits = tb.y;
     }
     s.cum_s = s.sizes_s = s.util_s = 0u;
-    s.seg = v.seg[i];
-    s.chunk = v.chunk[i];
-    s.last_q = v.last_q[i];
-    s.phi = v.phi[i];
-    s.buffer = v.buffer[i];
+    s.seg = w.seg;
+    s.chunk = w.chunk;
+    s.last_q = w.last_q;
+    s.phi = w.phi;
+    s.buffer = w.buffer;
     s.done = v.p.auto_reset ? false : (v.done[i] != 0);
     s.hist_len = v.p.track_history ? v.hist_len[i] : 0;
+}
+
+__device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
+    const RawState w = load_raw(v, i);
+    make_sess(v, i, w, s);
 }
 
 // Builds the per-trace tables of SPEC §3.1, one thread per trace (the accumulation is sequential by definition;
@@ -399,7 +414,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
 // compiled without the null checks and the inert/history/accumulator bookkeeping (next_sizes and throughput stay
 // optional in both variants).
 template <bool SMEM, bool FAST, bool LIVE>
-__device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const int i, const int32_t* __restrict__ action,
+__device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const int i, const int q_in,
                                              const double* __restrict__ speed, double* __restrict__ o_delay,
                                              double* __restrict__ o_sleep, double* __restrict__ o_buffer,
                                              double* __restrict__ o_rebuf, double* __restrict__ o_reward,
@@ -409,7 +424,7 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
         s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0;
         s.speed = speed ? speed[i] : 1.0;
     }
-    int q = action[i];
+    int q = q_in;
     bool bad = q < 0 || q >= v.A;
     if (bad) q = q < 0 ? 0 : v.A - 1;
     if (LIVE && !(s.speed > 0.0)) { bad = true; s.speed = 1.0; }
@@ -468,7 +483,7 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
 // on that trace — and the search probes are LDS; a per-lane scattered global load costs one L1 wavefront per lane,
 // which is what bounds the global path (ncu: l1tex__data_pipe_lsu_wavefronts).
 template <bool FAST, bool LIVE>
-__global__ void __launch_bounds__(kStepBlock, LIVE ? 3 : 4)
+__global__ void __launch_bounds__(kStepBlock, LIVE ? 2 : 3)
 abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __restrict__ speed,
                 double* __restrict__ o_delay, double* __restrict__ o_sleep, double* __restrict__ o_buffer,
                 double* __restrict__ o_rebuf, double* __restrict__ o_reward, double* __restrict__ o_latency,
@@ -477,7 +492,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_tr0;
-#define ABR_STEP_SESSION_ARGS v, s, i, action, speed, o_delay, o_sleep, o_buffer, o_rebuf, o_reward, o_latency, o_next_sizes, o_eov, o_thr
+#define ABR_STEP_SESSION_ARGS v, s, i, q_cur, speed, o_delay, o_sleep, o_buffer, o_rebuf, o_reward, o_latency, o_next_sizes, o_eov, o_thr
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
     if (smem_doubles != 0) {
         if (threadIdx.x == 0) {
@@ -488,14 +503,25 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     }
     uint32_t parity = 0u;                        // phase of the next staging copy (block-uniform)
     int staged = -1;                             // trace whose C row the buffer holds (block-uniform, kept per thread)
+    // the state words and the action of the next tile are requested before the current tile is computed, so that
+    // two tiles of loads per warp are in flight (the kernel is bound by HBM latency x occupancy otherwise)
+    RawState w_next;
+    int q_next = 0;
+    {
+        const int i0 = blockIdx.x * kStepTiles * kStepBlock + threadIdx.x;
+        if (i0 < v.n) { w_next = load_raw(v, i0); q_next = action[i0]; }
+    }
     for (int k = 0; k < kStepTiles; ++k) {
         const int tile0 = (blockIdx.x * kStepTiles + k) * kStepBlock;
         if (tile0 >= v.n) break;                 // block-uniform
         const int i = tile0 + threadIdx.x;
         const bool valid = i < v.n;
+        const RawState w = w_next;
+        const int q_cur = q_next;
+        if (k + 1 < kStepTiles && i + kStepBlock < v.n) { w_next = load_raw(v, i + kStepBlock); q_next = action[i + kStepBlock]; }
         Sess s;
         int tr = -1;
-        if (valid) { load_sess(v, i, s); tr = v.trace_id[i]; }
+        if (valid) { make_sess(v, i, w, s); tr = w.tr; }
         if (smem_doubles == 0) {                 // launch-uniform: no shared-memory row buffer
             if (valid) step_session<false, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
             continue;
