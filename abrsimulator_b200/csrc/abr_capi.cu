@@ -190,8 +190,10 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     CUDA_TRY(e->alloc(&d_bits, n_traces));
     TraceMeta* d_meta;
     CUDA_TRY(e->alloc(&d_meta, n_traces));
-    v.trace_cum = d_cum; v.trace_bits = d_bits; v.trace_meta = d_meta;
-    CUDA_TRY(launch_trace_table(v, d_cum, d_bits, d_meta, 0));
+    uint32_t* d_key;
+    CUDA_TRY(e->alloc(&d_key, (size_t)n_traces * key_stride(T_max)));
+    v.trace_cum = d_cum; v.trace_bits = d_bits; v.trace_meta = d_meta; v.trace_key = d_key;
+    CUDA_TRY(launch_trace_table(v, d_cum, d_key, d_bits, d_meta, 0));
     {
         std::vector<int32_t> bits(n_traces);
         CUDA_TRY(cudaMemcpy(bits.data(), d_bits, sizeof(int32_t) * n_traces, cudaMemcpyDeviceToHost));

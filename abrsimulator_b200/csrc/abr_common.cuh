@@ -11,6 +11,8 @@ namespace abr {
 // Row stride (in doubles) of the cumulative-capacity table C[0..T] of SPEC §3.1, even so that every row starts
 // 16-byte aligned (TMA bulk copies).
 __host__ __device__ __forceinline__ int cum_stride(int T_max) { return (T_max + 2) & ~1; }
+// Row stride (in 32-bit words) of the search-key table K[j] = high word of C[j]; a multiple of 4 (16-byte rows).
+__host__ __device__ __forceinline__ int key_stride(int T_max) { return (T_max + 4) & ~3; }
 
 // ---------------------------------------------------------------------------------------------
 // exact fp64 helpers
@@ -73,6 +75,8 @@ struct EnvView {
                                                 // entries past C[T] are +inf
     const int32_t* __restrict__ trace_bits;     // [n_traces] search widths: bits 0-7 = b_near (2^b_near - 1 >= the most
                                                 // segments one download can cross), bits 8-15 = b_full (2^b_full >= T)
+    const uint32_t* __restrict__ trace_key;     // [n_traces][key_stride] K[j] = high 32 bits of C[j] (monotone, C >= 0);
+                                                // entries past K[T] are 0xffffffff
     const TraceMeta* __restrict__ trace_meta;   // [n_traces] the per-trace scalars a step needs, one 32-byte record
     const int32_t* __restrict__ trace_len;      // [n_traces]
     const double* __restrict__ trace_interval;  // [n_traces]
@@ -90,7 +94,8 @@ struct EnvView {
 };
 
 // launchers implemented in abr_step.cu / abr_mpc.cu (C++ linkage, internal)
-cudaError_t launch_trace_table(const EnvView& v, double* d_cum, int32_t* d_bits, TraceMeta* d_meta, cudaStream_t st);
+cudaError_t launch_trace_table(const EnvView& v, double* d_cum, uint32_t* d_key, int32_t* d_bits, TraceMeta* d_meta,
+                               cudaStream_t st);
 cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st);
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
                         double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,

@@ -41,6 +41,7 @@ struct Sess {
     const double* __restrict__ cum;   // C[0..T] of the session's trace (global row)
     uint32_t cum_s, sizes_s, util_s;  // shared-memory addresses of the block's copies of the C row and of the
                                       // sizes / utility tables (SMEM path)
+    uint32_t key_s;                   // ... and of the search-key row (KEYS path)
     const double* __restrict__ sizes; // [V][A] chunk sizes and utilities (global tables)
     const double* __restrict__ util;
     double I, phi, buffer;            // phi = fraction of segment `seg` already consumed (SPEC §1)
@@ -57,6 +58,12 @@ struct StepRes {
     double delay, sleep, buffer, rebuf, reward, thr, u, smooth, latency, startup;
     bool eov, inert, walk_error, reset_mpc;
 };
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t x;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(addr));
+    return x;
+}
 
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double x;
@@ -158,13 +165,47 @@ __device__ __forceinline__ uint32_t search_cum(const Sess& s, uint32_t p_lo, con
     return p_lo;
 }
 
+// The same search on the 32-bit keys K[j] = high word of C[j] (fused episode, shared memory): returns the byte
+// position in the key row of the largest j in [lo, lo + 2^bits) and [0, T) with K[j] < kt, or `kp_lo` itself.
+// K[j] < kt implies C[j] < target, so C[j] <= target holds at the result; the few j above it whose key equals kt
+// are settled by the caller with exact 64-bit compares.  A random 4-byte LDS costs ~3.5 shared-memory wavefronts
+// per warp against ~5.8 for an 8-byte one, and the compare runs on the integer pipe instead of the FP64 pipe —
+// at >= 1 Mi sessions the kernel is bound by exactly those wavefronts (ncu: l1tex__data_pipe_lsu_wavefronts 91 %).
+__device__ __forceinline__ uint32_t search_keys(uint32_t kp_lo, const uint32_t kp_end, int bits, const uint32_t kt) {
+    if (bits & 1) {
+        if (bits >= 3) {
+            bits -= 3;
+            const uint32_t st = 4u << bits;
+            uint32_t k[7];
+#pragma unroll
+            for (int m = 0; m < 7; ++m) k[m] = lds_u32(min(kp_lo + (uint32_t)(m + 1) * st, kp_end));
+            const int b0 = k[0] < kt, b1 = k[1] < kt, b2 = k[2] < kt, b3 = k[3] < kt;
+            const int b4 = k[4] < kt, b5 = k[5] < kt, b6 = k[6] < kt;
+            kp_lo += (uint32_t)((b0 + b1 + b2) + (b3 + b4 + b5) + b6) * st;
+        } else {
+            bits -= 1;
+            const uint32_t p1 = min(kp_lo + 4u, kp_end);
+            if (lds_u32(p1) < kt) kp_lo = p1;
+        }
+    }
+    for (; bits > 0; bits -= 2) {
+        const uint32_t st = 4u << (bits - 2);
+        const uint32_t p1 = min(kp_lo + st, kp_end), p2 = min(kp_lo + 2 * st, kp_end), p3 = min(kp_lo + 3 * st, kp_end);
+        const uint32_t k1 = lds_u32(p1), k2 = lds_u32(p2), k3 = lds_u32(p3);
+        if (k1 < kt) kp_lo = p1;
+        if (k2 < kt) kp_lo = p2;
+        if (k3 < kt) kp_lo = p3;
+    }
+    return kp_lo;
+}
+
 // SPEC §3 for one session held in registers.  `q` must already be a valid index; `lk` holds the step's table reads.
 // SMEM: the block's shared-memory copy of the trace's C row is used (else the global table).
 // CARRY: s.c_seg / s.c_seg1 hold C[seg] / C[seg+1] on entry and on exit (fused episode: the segment a download ends
 // in is the one the next download starts in, so the values are already in registers).
 // FAST: auto_reset is on (a session is never inert) — drops the done/inert bookkeeping.
 // LIVE: live-streaming semantics of SPEC §7 (pause gate before the download, start-up latch, playback speed).
-template <bool SMEM, bool CARRY, bool FAST = false, bool LIVE = false>
+template <bool SMEM, bool CARRY, bool FAST = false, bool LIVE = false, bool KEYS = false>
 __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, const Lookup& lk, StepRes& r,
                                           const bool want_thr) {
     const AbrParams& p = v.p;
@@ -217,10 +258,26 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         bits = (s.bits >> 8) & 0xff;
         kd = dadd(kd, dmul((double)n, (double)T));        // exact in fp64
     }
-    const uint32_t p_j = search_cum<SMEM>(s, p_lo, p_end, bits, target);
+    uint32_t p_j;
+    double c_j, c_j1;
+    if (KEYS) {
+        const uint32_t kp = search_keys(s.key_s + ((p_lo - p_base) >> 1), s.key_s + 4u * (uint32_t)T, bits,
+                                        (uint32_t)__double2hiint(target));
+        p_j = p_base + ((kp - s.key_s) << 1);
+        c_j = ld_cum<SMEM>(s, p_j);
+        c_j1 = ld_cum<SMEM>(s, p_j + 8u);
+        // segments whose key equals the target's: exact compares (rarely more than none; C[T] = P > target ends it)
+        for (int g = 0; c_j1 <= target && g < kWrapGuard; ++g) {
+            p_j += 8u;
+            c_j = c_j1;
+            c_j1 = ld_cum<SMEM>(s, p_j + 8u);
+        }
+    } else {
+        p_j = search_cum<SMEM>(s, p_lo, p_end, bits, target);
+        c_j = ld_cum<SMEM>(s, p_j);
+        c_j1 = ld_cum<SMEM>(s, p_j + 8u);
+    }
     kd = dadd(kd, (double)(int)((p_j - p_base) >> 3));    // exact
-    const double c_j = ld_cum<SMEM>(s, p_j);
-    const double c_j1 = ld_cum<SMEM>(s, p_j + 8u);
     if (!(target < c_j1)) r.walk_error = true;   // insurance: the search width covered the download
     const double phi_new = ddiv(dsub(target, c_j), dsub(c_j1, c_j));   // fraction of segment j consumed
     double delay = dadd(max0(dmul(dadd(kd, dsub(phi_new, phi)), s.I)), p.rtt);
@@ -310,7 +367,7 @@ __device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawStat
         const int4 tb = __ldg(reinterpret_cast<const int4*>(v.trace_meta + tr) + 1);
         s.I = ip.x; s.P = ip.y; s.T = tb.x; s.bits = tb.y;
     }
-    s.cum_s = s.sizes_s = s.util_s = 0u;
+    s.cum_s = s.sizes_s = s.util_s = s.key_s = 0u;
     s.seg = w.seg;
     s.chunk = w.chunk;
     s.last_q = w.last_q;
@@ -331,7 +388,8 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
 // boundaries a download that stays inside the period can cross).  bits = -1 flags a trace whose period capacity is
 // not a positive finite number or that holds a segment without capacity.
 __global__ void __launch_bounds__(kStepBlock)
-abr_trace_table_kernel(EnvView v, double* __restrict__ cum, int32_t* __restrict__ bits, TraceMeta* __restrict__ meta) {
+abr_trace_table_kernel(EnvView v, double* __restrict__ cum, uint32_t* __restrict__ key, int32_t* __restrict__ bits,
+                       TraceMeta* __restrict__ meta) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= v.n_traces) return;
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
@@ -339,18 +397,22 @@ abr_trace_table_kernel(EnvView v, double* __restrict__ cum, int32_t* __restrict_
     const double I = v.trace_interval[t];
     const double* bw = v.trace_bw + (size_t)t * v.T_max;
     double* c_row = cum + (size_t)t * cum_stride(v.T_max);
+    uint32_t* k_row = key + (size_t)t * key_stride(v.T_max);
     double size_max = 0.0;
     for (int i = 0; i < v.V * v.A; ++i) size_max = fmax(size_max, v.sizes[i]);
     double c = 0.0, mincap = kInf;
     c_row[0] = 0.0;
+    k_row[0] = 0u;
 #pragma unroll 8
     for (int j = 0; j < T; ++j) {
         const double c_next = dadd(c, dmul(dmul(bw[j], v.p.payload), I));
         c_row[j + 1] = c_next;
+        k_row[j + 1] = (uint32_t)__double2hiint(c_next);
         mincap = fmin(mincap, dsub(c_next, c));   // the capacity the step sees: C[j+1] - C[j]
         c = c_next;
     }
     for (int j = T + 1; j < cum_stride(v.T_max); ++j) c_row[j] = kInf;
+    for (int j = T + 1; j < key_stride(v.T_max); ++j) k_row[j] = 0xffffffffu;
     int b_full = 0;
     while ((1 << b_full) < T) ++b_full;
     int b_near = b_full;
@@ -598,22 +660,13 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         }
         return policy_bba(v, s.buffer);
     };
-    // the action and the table reads of a step are issued one step ahead when the policy does not look at the state
-    constexpr bool kAhead = POLICY != ABR_POLICY_BBA;
+    // the action and the table reads of the next step are issued at the end of a step (after its stores), so that
+    // they are in registers when the next step starts
     int q = action_at(0);
     Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);
     for (int t = 0; t < steps; ++t) {
-        int q_next = 0;
-        Lookup lk_next;
-        if (kAhead) {   // also after the last step (its result is unused): no branch, no select on the loaded values
-            q_next = action_at(t + 1);
-            // state the next step will see (SPEC §3.5): an end of video restarts at chunk 0 with the default quality
-            const bool wraps = s.chunk + 1 >= v.V;
-            const bool resets = wraps && (FAST || v.p.auto_reset);
-            lk_next = lookup_tables<SMEM>(s, v.A, v.V, wraps ? 0 : s.chunk + 1, q_next, resets ? v.p.default_quality : q);
-        }
         StepRes r;
-        step_core<SMEM, true, FAST>(v, s, q, lk, r, hist);
+        step_core<SMEM, true, FAST, false, SMEM>(v, s, q, lk, r, hist);   // shared-memory path searches on the keys
         flagged |= r.walk_error;
         const size_t ix = (size_t)t * n + i;
         if (FAST) {
@@ -627,7 +680,6 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             if (o.rebuf) __stcs(o.rebuf + ix, r.rebuf);
             if (o.reward) __stcs(o.reward + ix, r.reward);
             if (o.eov) o.eov[ix] = r.eov ? 1 : 0;
-            if (o.actions) __stcs(o.actions + ix, q);
         }
         if (FAST || !r.inert) {
             a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
@@ -639,12 +691,10 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
                 else v.bw_hist[(size_t)((s.hist_len - 1) % v.K) * v.cap + i] = r.thr;
             }
         }
-        if (!kAhead) {
-            q_next = action_at(t + 1);
-            lk_next = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q_next, s.last_q);
-        }
-        q = q_next;
-        lk = lk_next;
+        const int q_done = q;
+        q = action_at(t + 1);   // also after the last step (unused): no branch around the loads
+        lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);   // the state step t + 1 will see (SPEC §3.5)
+        if (!FAST && o.actions) __stcs(o.actions + ix, q_done);
     }
     const double a_steps = (double)n_steps, a_eps = (double)n_eps;   // exact: counts below 2^31
     if (flagged) atomicAdd(v.errors, 1ull);
@@ -667,7 +717,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
 }
 
 // smem_doubles: capacity of the dynamic shared-memory row buffer (0 disables the shared-memory path); the buffer
-// is followed by room for the sizes and utility tables.
+// is followed by the key row (key_stride(T_max) words, 16-byte aligned) and the sizes and utility tables.
 // 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
 // co-resident (6.9 per SM); at 140 registers only 3 warps fit per scheduler and a second wave appears.
 template <int POLICY, bool FAST>
@@ -694,12 +744,14 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
     const bool use_smem = __syncthreads_and((!valid || tr == tr0) ? 1 : 0) && need <= smem_doubles;
     if (use_smem) {
         // Stage the trace's C row and the chunk-size / utility tables with TMA bulk copies (cp.async.bulk, SASS UBLKCP):
-        // one elected thread issues three asynchronous global->shared copies that complete on an mbarrier, so the
-        // 21 KB arrive without occupying the LSU or registers while the other threads finish loading their state.
+        // one elected thread issues four asynchronous global->shared copies that complete on an mbarrier, so the
+        // 29 KB arrive without occupying the LSU or registers while the other threads finish loading their state.
         // Rows start 16-byte aligned (cum_stride is even) and all byte counts are multiples of 16.
         double* s_row = reinterpret_cast<double*>(s_row2);
-        double* s_sizes = s_row + smem_doubles;
+        uint32_t* s_key = reinterpret_cast<uint32_t*>(s_row + smem_doubles);
+        double* s_sizes = reinterpret_cast<double*>(s_key + key_stride(v.T_max));
         double* s_util = s_sizes + v.V * v.A;
+        const uint32_t key_bytes = (uint32_t)((need + 3) / 4) * 16u;
         const double* g_row = v.trace_cum + (size_t)tr0 * cum_stride(v.T_max);
         const uint32_t row_bytes = (uint32_t)((need + 1) / 2) * 16u;
         const uint32_t tab_bytes = (uint32_t)(v.V * v.A) * 8u;
@@ -711,9 +763,10 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t total = row_bytes + (tab_bulk ? 2u * tab_bytes : 0u);
+            const uint32_t total = row_bytes + key_bytes + (tab_bulk ? 2u * tab_bytes : 0u);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
             bulk_g2s(s_row, g_row, row_bytes, mbar);
+            bulk_g2s(s_key, v.trace_key + (size_t)tr0 * key_stride(v.T_max), key_bytes, mbar);
             if (tab_bulk) {
                 bulk_g2s(s_sizes, v.sizes, tab_bytes, mbar);
                 bulk_g2s(s_util, v.util, tab_bytes, mbar);
@@ -729,11 +782,12 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
         __syncthreads();
         if (valid) {
             s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row);
+            s.key_s = (uint32_t)__cvta_generic_to_shared(s_key);
             s.sizes_s = (uint32_t)__cvta_generic_to_shared(s_sizes);
             s.util_s = (uint32_t)__cvta_generic_to_shared(s_util);
             // keep the three addresses in registers: left alone, the compiler rematerialises them from
             // SR_CgaCtaId (an S2R round trip) at every use inside the step loop
-            asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s));
+            asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s), "+r"(s.key_s));
             rollout_session<POLICY, true, FAST>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
         }
     } else if (valid) {
@@ -823,8 +877,9 @@ abr_qoe_cost_kernel(EnvView v, double* __restrict__ out) {
 
 }  // namespace
 
-cudaError_t launch_trace_table(const EnvView& v, double* d_cum, int32_t* d_bits, TraceMeta* d_meta, cudaStream_t st) {
-    abr_trace_table_kernel<<<(v.n_traces + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_cum, d_bits, d_meta);
+cudaError_t launch_trace_table(const EnvView& v, double* d_cum, uint32_t* d_key, int32_t* d_bits, TraceMeta* d_meta,
+                               cudaStream_t st) {
+    abr_trace_table_kernel<<<(v.n_traces + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_cum, d_key, d_bits, d_meta);
     count_launch();
     return cudaGetLastError();
 }
@@ -866,8 +921,9 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     RolloutOut o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out};
     // shared-memory row buffer: the longest C row when it leaves room for >= 7 blocks per SM, else disabled
     int smem_doubles = cum_stride(v.T_max);
-    size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double);
-    if (smem_bytes > 32 * 1024) { smem_doubles = 0; smem_bytes = 0; }
+    size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double) +
+                        (size_t)key_stride(v.T_max) * sizeof(uint32_t);
+    if (smem_bytes > 31 * 1024) { smem_doubles = 0; smem_bytes = 0; }   // 7 blocks per SM must stay resident
     const bool fast = d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && !d_actions_out &&
                       v.p.track_history == 0 && v.p.auto_reset != 0;
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \

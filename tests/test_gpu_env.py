@@ -157,6 +157,31 @@ def test_fused_rollout_shared_memory_trace_path(ragged):
     assert env.error_count() == 0
 
 
+def test_fused_rollout_key_search_with_equal_keys():
+    """The shared-memory path searches on the high words of the capacity table; a trace whose capacities are tiny
+    next to its running total gives long runs of equal keys, which the exact 64-bit scan must settle."""
+    N, steps = 64 * 6, 40
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=3, T=50)
+    bw = bw.copy()
+    bw[0, :] = 1e-2
+    bw[0, 0] = 1e6                       # C[j] = 9.5e5 + j * 9.5e-3: one key for the whole trace
+    bw[1, :] = 0.3
+    bw[1, 7] = 4e4
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
+    tid = ((np.arange(N) // 64) % 3).astype(np.int32)
+    off = np.random.default_rng(8).uniform(0, 200.0, size=N)
+    env.reset(tid, off)
+    ref.reset(tid, off)
+    got = env.rollout("random", steps, seed=5)
+    exp = ref.rollout(orc.POLICY_RANDOM, steps, seed=5)
+    for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                     ("reward", "reward")):
+        assert_close(got[k_g].cpu().numpy(), exp[k_c], k_g)
+    check_state(env, ref)
+    assert env.error_count() == 0 and ref.errors() == 0
+
+
 @pytest.mark.parametrize("ragged", [False, True])
 @pytest.mark.parametrize("fast", [False, True])
 def test_step_kernel_shared_memory_trace_path(ragged, fast):
