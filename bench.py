@@ -67,8 +67,12 @@ def _py_step_worker(job):
     t0 = time.perf_counter()
     done_steps = 0
     tot = 0.0
+    tables = {}
     for s in range(hi - lo):
-        sess = so.Session(bw[tid[s]].tolist(), float(ti[tid[s]]), sz, util, P, float(off[s]))
+        tr = int(tid[s])
+        if tr not in tables:    # per-trace capacity table, built once like the device does
+            tables[tr] = (bw[tr].tolist(), so.capacity_table(bw[tr].tolist(), float(ti[tr]), P["payload"]))
+        sess = so.Session(tables[tr][0], float(ti[tr]), sz, util, P, float(off[s]), table=tables[tr][1])
         g = lo + s
         for t in range(V):
             x0 = orc.philox(g & 0xffffffff, g >> 32, t >> 2, 0, SEED, 0)[t & 3]

@@ -15,17 +15,24 @@ from __future__ import annotations
 import math
 
 
+def capacity_table(bw, interval, payload):
+    """SPEC §3.1: (rate, C) with C[0] = 0, C[j+1] = C[j] + (bw[j]*payload)*interval, left to right.
+    ``rate`` is used by walk="segments" only."""
+    rate = [b * payload for b in bw]
+    C = [0.0]
+    for r in rate:
+        C.append(C[-1] + r * interval)
+    return rate, C
+
+
 class Session:
-    def __init__(self, bw, interval, sizes, util, P, start_offset=0.0, walk="table"):
+    def __init__(self, bw, interval, sizes, util, P, start_offset=0.0, walk="table", table=None):
         self.bw, self.I, self.T = list(bw), float(interval), len(bw)
-        self.walk = walk
-        # SPEC 3.1 table: C[0] = 0 ; C[j+1] = C[j] + (bw[j]*payload)*I (left to right)
-        self.rate = [b * P["payload"] for b in self.bw]      # walk="segments" only
-        self.C = [0.0]
-        for r in self.rate:
-            self.C.append(self.C[-1] + r * self.I)
         self.sizes, self.util, self.P = sizes, util, P
         self.V, self.A = len(sizes), len(sizes[0])
+        self.walk = walk
+        # SPEC 3.1 table (per trace; pass ``table=capacity_table(...)`` to share it between sessions of a trace)
+        self.rate, self.C = table if table is not None else capacity_table(self.bw, self.I, P["payload"])
         x = start_offset / self.I
         n = math.floor(x)
         self.seg = int(math.fmod(n, self.T))
