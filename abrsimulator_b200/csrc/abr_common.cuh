@@ -76,7 +76,7 @@ struct EnvView {
     const int32_t* __restrict__ trace_bits;     // [n_traces] search widths: bits 0-7 = b_near (2^b_near - 1 >= the most
                                                 // segments one download can cross), bits 8-15 = b_full (2^b_full >= T)
     const uint32_t* __restrict__ trace_key;     // [n_traces][key_stride] K[j] = high 32 bits of C[j] (monotone, C >= 0);
-                                                // entries past K[T] are 0xffffffff
+                                                // entries past K[T] are 0x7fffffff
     const TraceMeta* __restrict__ trace_meta;   // [n_traces] the per-trace scalars a step needs, one 32-byte record
     const int32_t* __restrict__ trace_len;      // [n_traces]
     const double* __restrict__ trace_interval;  // [n_traces]

@@ -179,9 +179,16 @@ __device__ __forceinline__ uint32_t search_keys(uint32_t kp_lo, const uint32_t k
             uint32_t k[7];
 #pragma unroll
             for (int m = 0; m < 7; ++m) k[m] = lds_u32(min(kp_lo + (uint32_t)(m + 1) * st, kp_end));
-            const int b0 = k[0] < kt, b1 = k[1] < kt, b2 = k[2] < kt, b3 = k[3] < kt;
-            const int b4 = k[4] < kt, b5 = k[5] < kt, b6 = k[6] < kt;
-            kp_lo += (uint32_t)((b0 + b1 + b2) + (b3 + b4 + b5) + b6) * st;
+            // keys are below 2^31 (high words of non-negative doubles), so k - kt is negative exactly when k < kt:
+            // the sign bits are summed with three-input adds (depth 3) instead of a chain of seven selects
+            int neg = 0;
+            {
+                int d[7];
+#pragma unroll
+                for (int m = 0; m < 7; ++m) d[m] = (int)(k[m] - kt) >> 31;   // -1 or 0
+                neg = (d[0] + d[1] + d[2]) + (d[3] + d[4] + d[5]) + d[6];
+            }
+            kp_lo -= (uint32_t)neg * st;
         } else {
             bits -= 1;
             const uint32_t p1 = min(kp_lo + 4u, kp_end);
@@ -412,7 +419,7 @@ abr_trace_table_kernel(EnvView v, double* __restrict__ cum, uint32_t* __restrict
         c = c_next;
     }
     for (int j = T + 1; j < cum_stride(v.T_max); ++j) c_row[j] = kInf;
-    for (int j = T + 1; j < key_stride(v.T_max); ++j) k_row[j] = 0xffffffffu;
+    for (int j = T + 1; j < key_stride(v.T_max); ++j) k_row[j] = 0x7fffffffu;
     int b_full = 0;
     while ((1 << b_full) < T) ++b_full;
     int b_near = b_full;

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--mpc-h7-sessions", type=int, default=2048, help="sessions per GPU of the horizon-7 leg (0 = skip)")
     ap.add_argument("--no-mpc", action="store_true")
     ap.add_argument("--no-step-form", action="store_true")
+    ap.add_argument("--rl-sessions", type=int, default=1 << 19,
+                    help="sessions per GPU of the RL-harness leg (configs[4] / 8; 0 = skip)")
     ap.add_argument("--step-sessions", type=int, default=1 << 22, help="sessions per GPU of the per-step-launch leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of each cpu_baseline sample")
@@ -336,6 +338,9 @@ def run_ours(args):
     step_form = None
     if not args.no_step_form:
         step_form = bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak_gbs())
+    rl = None
+    if not args.no_step_form and args.rl_sessions > 0:
+        rl = bench_rl_harness(args, dev, rank, world, barrier, max_over_ranks)
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -373,6 +378,8 @@ def run_ours(args):
         line["mpc"] = mpc
     if step_form:
         line["step_form"] = step_form
+    if rl:
+        line["rl_harness"] = rl
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
@@ -432,6 +439,39 @@ def bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak):
                 roofline=best["roofline"], layouts=res,
                 note="4 Mi sessions: 304 MB of SoA state + 172 MB of outputs per launch, larger than the 126 MB L2; "
                      "headline = sessions sorted by trace (shared-memory staged capacity rows)")
+
+
+def bench_rl_harness(args, dev, rank, world, barrier, max_over_ranks):
+    """RL rollout harness (configs[4] per GPU): a batched torch policy (MLP, fp32) <-> abr_env_step with every state
+    tensor on the device, one 48-chunk episode of --rl-sessions sessions.  The policy kernels are torch's; the
+    environment step, the observation inputs (throughput, next-chunk sizes) and the state are this library's."""
+    import torch
+    from abrsimulator_b200 import synth
+    from abrsimulator_b200.env import BatchedABREnv
+    from examples.rl_harness import Policy, run_episode
+    M = args.rl_sessions
+    bitrates, sizes = synth.make_video(V)
+    bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
+    env = BatchedABREnv(bw, sizes, bitrates, M, trace_len=tl, trace_interval=ti)
+    tid, off = synth.make_sessions(M, N_TRACES, T_TRACE, session_base=rank * M, group=max(256, M // N_TRACES))
+    torch.manual_seed(0)
+    policy = Policy(4 + A, A).to(dev)
+    stream = torch.cuda.current_stream()
+    ms = []
+    for ep in range(3):
+        env.reset(tid, off, session_base=rank * M)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        total = run_episode(env, policy, V)
+        e1.record(stream)
+        e1.synchronize()
+        ms.append(max_over_ranks(e0.elapsed_time(e1), dev))
+    best = min(ms[1:])
+    return dict(sessions_per_gpu=M, chunks=V, ms_per_episode=best, env_steps_per_s=world * M * V / (best * 1e-3),
+                mean_episode_reward=float(total.mean().item()),
+                note="policy forward + categorical sampling (torch) + abr_env_step with throughput and next_sizes "
+                     "outputs + observation update, per chunk; state never leaves the device")
 
 
 def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):

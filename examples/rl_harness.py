@@ -71,7 +71,8 @@ def main():
     bitrates, sizes = synth.make_video(args.chunks)
     bw, tl, ti = synth.make_traces(1024, 2048)
     env = BatchedABREnv(bw, sizes, bitrates, args.sessions, trace_len=tl, trace_interval=ti)
-    tid, off = synth.make_sessions(args.sessions, 1024, 2048, group=64)
+    # sessions sorted by trace: every 256-session tile of the step kernel stages one capacity row in shared memory
+    tid, off = synth.make_sessions(args.sessions, 1024, 2048, group=max(256, args.sessions // 1024))
     policy = Policy(4 + env.A, env.A).to(dev)
     for ep in range(args.episodes):
         env.reset(tid, off)
