@@ -898,6 +898,16 @@ cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const doub
     return cudaGetLastError();
 }
 
+// Dynamic shared memory above 48 KB needs an opt-in per kernel; long traces (up to ~18 000 segments in the fused
+// kernel) then still run on the shared-memory path, with fewer blocks per SM.
+constexpr size_t kSmemOptInLimit = 200 * 1024;
+
+template <typename Kernel>
+static cudaError_t allow_smem(Kernel kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
                         double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,
                         double* d_next_sizes, uint8_t* d_eov, double* d_thr, cudaStream_t st) {
@@ -906,15 +916,23 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
     const bool fast = !live && d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov &&
                       v.p.track_history == 0 && v.p.track_acc == 0 && v.p.auto_reset != 0;
     const unsigned grid = (v.n + kStepBlock * kStepTiles - 1) / (kStepBlock * kStepTiles);
-    // shared-memory row buffer for blocks whose sessions share a trace (48 KB: no opt-in needed, 4 blocks per SM)
+    // shared-memory row buffer for blocks whose sessions share a trace (3 blocks per SM up to 74 KB per block)
     int smem_doubles = cum_stride(v.T_max);
     size_t smem_bytes = (size_t)smem_doubles * sizeof(double);
-    if (smem_bytes > 48 * 1024) { smem_doubles = 0; smem_bytes = 0; }
+    if (smem_bytes > kSmemOptInLimit) { smem_doubles = 0; smem_bytes = 0; }
+    cudaError_t e = cudaSuccess;
 #define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr, smem_doubles
-    if (live) abr_step_kernel<false, true><<<grid, kStepBlock, smem_bytes, st>>>(ABR_STEP_ARGS);
-    else if (fast) abr_step_kernel<true, false><<<grid, kStepBlock, smem_bytes, st>>>(ABR_STEP_ARGS);
-    else abr_step_kernel<false, false><<<grid, kStepBlock, smem_bytes, st>>>(ABR_STEP_ARGS);
+#define ABR_LAUNCH_STEP(F, L)                                                                  \
+    do {                                                                                       \
+        e = allow_smem(abr_step_kernel<F, L>, smem_bytes);                                     \
+        if (e == cudaSuccess) abr_step_kernel<F, L><<<grid, kStepBlock, smem_bytes, st>>>(ABR_STEP_ARGS); \
+    } while (0)
+    if (live) ABR_LAUNCH_STEP(false, true);
+    else if (fast) ABR_LAUNCH_STEP(true, false);
+    else ABR_LAUNCH_STEP(false, false);
+#undef ABR_LAUNCH_STEP
 #undef ABR_STEP_ARGS
+    if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
 }
@@ -930,17 +948,23 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     int smem_doubles = cum_stride(v.T_max);
     size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double) +
                         (size_t)key_stride(v.T_max) * sizeof(uint32_t);
-    if (smem_bytes > 31 * 1024) { smem_doubles = 0; smem_bytes = 0; }   // 7 blocks per SM must stay resident
+    // <= 31 KB keeps 7 blocks per SM resident (the 65 536-session shape is then one wave); longer traces opt in to
+    // more shared memory and run with fewer blocks per SM, which still beats scattered global probes
+    if (smem_bytes > kSmemOptInLimit) { smem_doubles = 0; smem_bytes = 0; }
     const bool fast = d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && !d_actions_out &&
                       v.p.track_history == 0 && v.p.auto_reset != 0;
+    cudaError_t e = cudaSuccess;
+#define ABR_LAUNCH_ROLLOUT_V(P, F)                                                                                 \
+    do {                                                                                                           \
+        e = allow_smem(abr_rollout_kernel<P, F>, smem_bytes);                                                      \
+        if (e == cudaSuccess)                                                                                      \
+            abr_rollout_kernel<P, F><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,            \
+                                                                      smem_doubles, d_block_partials);             \
+    } while (0)
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
     do {                                                                                                           \
-        if (fast)                                                                                                  \
-            abr_rollout_kernel<P, true><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,         \
-                                                                         smem_doubles, d_block_partials);          \
-        else                                                                                                       \
-            abr_rollout_kernel<P, false><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,        \
-                                                                          smem_doubles, d_block_partials);         \
+        if (fast) ABR_LAUNCH_ROLLOUT_V(P, true);                                                                   \
+        else ABR_LAUNCH_ROLLOUT_V(P, false);                                                                       \
     } while (0)
     switch (policy) {
         case ABR_POLICY_FIXED: ABR_LAUNCH_ROLLOUT(ABR_POLICY_FIXED); break;
@@ -949,6 +973,8 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
         default: return cudaErrorInvalidValue;
     }
 #undef ABR_LAUNCH_ROLLOUT
+#undef ABR_LAUNCH_ROLLOUT_V
+    if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
 }

@@ -157,6 +157,38 @@ def test_fused_rollout_shared_memory_trace_path(ragged):
     assert env.error_count() == 0
 
 
+@pytest.mark.parametrize("T", [6000, 30000])
+def test_long_traces_take_the_opt_in_shared_memory_path_or_fall_back(T):
+    """6 000 segments need 77 KB (fused) / 48 KB (per-step) of shared memory per block: the opt-in path;
+    30 000 segments do not fit and run on the global path.  Both must match the oracle bit for bit."""
+    N, steps = 256 * 3 + 40, 24
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=3, T=T, V=12)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
+    tid = ((np.arange(N) // 256) % 3).astype(np.int32)
+    off = np.random.default_rng(2).uniform(0, float(T), size=N)
+    off[:8] = T - 1e-3                                   # downloads that run past the end of the trace period
+    for fused in (True, False):
+        env.reset(tid, off)
+        ref.reset(tid, off)
+        if fused:
+            got = env.rollout("random", steps, seed=11)
+            exp = ref.rollout(orc.POLICY_RANDOM, steps, seed=11)
+            for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                             ("reward", "reward")):
+                assert_close(got[k_g].cpu().numpy(), exp[k_c], k_g)
+        else:
+            rng = np.random.default_rng(3)
+            for t in range(steps):
+                a = rng.integers(0, env.A, size=N).astype(np.int32)
+                g, e = env.step(a), ref.step(a)
+                assert_close(g.delay.cpu().numpy(), e["delay"], f"delay@{t}")
+                assert_close(g.buffer.cpu().numpy(), e["buffer"], f"buffer@{t}")
+                assert_close(g.reward.cpu().numpy(), e["reward"], f"reward@{t}")
+        check_state(env, ref)
+    assert env.error_count() == 0 and ref.errors() == 0
+
+
 def test_fused_rollout_key_search_with_equal_keys():
     """The shared-memory path searches on the high words of the capacity table; a trace whose capacities are tiny
     next to its running total gives long runs of equal keys, which the exact 64-bit scan must settle."""
