@@ -30,3 +30,26 @@ def assert_close(gpu, cpu, name, rtol=1e-9, atol=1e-12, exact=True):
     if exact:
         nd = bits_equal(gpu, cpu)
         assert nd == 0, f"{name}: {nd} of {gpu.size} values are within 1e-9 but not bit-identical"
+
+
+def load_step_golden():
+    """tests/golden/step_spec_golden.json (oracle/gen_step_golden.py): cases with inputs rebuilt and outputs as float64."""
+    import json
+    import os
+    from oracle.gen_step_golden import world, KEYS
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_spec_golden.json")
+    with open(path) as f:
+        doc = json.load(f)
+    cases = []
+    for c in doc["cases"]:
+        bitrates, sizes, bw, tl, ti = world(c["seed"])
+        unhex = lambda rows: np.array([[float.fromhex(x) for x in r] for r in rows])
+        cases.append(dict(name=c["name"], params=c["params"], bitrates=bitrates, sizes=sizes, bw=bw, tl=tl, ti=ti,
+                          trace_id=np.array(c["trace_id"], np.int32),
+                          start_offset=np.array([float.fromhex(x) for x in c["start_offset"]]),
+                          actions=np.array(c["actions"], np.int32), speeds=c["speeds"],
+                          outputs={k: unhex(c["outputs"][k]) for k in KEYS}, eov=np.array(c["outputs"]["eov"], np.uint8),
+                          final=dict(seg=np.array(c["final"]["seg"], np.int32), chunk=np.array(c["final"]["chunk"], np.int32),
+                                     phase=np.array([float.fromhex(x) for x in c["final"]["phase"]]),
+                                     buffer=np.array([float.fromhex(x) for x in c["final"]["buffer"]]))))
+    return cases

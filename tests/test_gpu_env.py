@@ -18,7 +18,7 @@ from abrsimulator_b200.simulator import Simulator, BufferBasedPolicy, RandomPoli
 from abrsimulator_b200.mpc import MPCBitrateController
 from abrsimulator_b200 import _lib
 from oracle import oracle as orc
-from helpers import small_world, assert_close, bits_equal
+from helpers import small_world, assert_close, bits_equal, load_step_golden
 
 STATE_I = ("seg", "chunk", "last_q", "trace_id")
 STATE_F = ("phase", "buffer")
@@ -624,3 +624,31 @@ def test_simulator_facade_run():
     sim3.set_mpd(4.0, 60.0, None, [Chunk(list(b / 1000.0)) for b in bitrates])
     costs = sim3.run_batch(100)
     assert costs.shape == (100,) and np.all(np.isfinite(costs)) and np.all(costs >= 0)
+
+
+@pytest.mark.parametrize("case", load_step_golden(), ids=lambda c: c["name"])
+def test_kernels_reproduce_the_step_spec_fixture(case):
+    """Committed fixture (tests/golden/step_spec_golden.json): per-step kernel bit for bit, then — for the on-demand
+    cases — the fused episode with the same action table."""
+    N = len(case["trace_id"])
+    P = dict(case["params"], track_acc=0)
+    env = BatchedABREnv(case["bw"], case["sizes"], case["bitrates"], N, trace_len=case["tl"], trace_interval=case["ti"], **P)
+    env.reset(case["trace_id"], case["start_offset"])
+    live = bool(P.get("live"))
+    for t, a in enumerate(case["actions"]):
+        v = None if case["speeds"] is None else np.full(N, case["speeds"][t % len(case["speeds"])])
+        got = env.step(a, speed=v, want_throughput=True) if live else env.step(a, want_throughput=True)
+        pairs = [("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"), ("reward", "reward"),
+                 ("throughput", "throughput")] + ([("latency", "latency")] if live else [])
+        for k_g, k_c in pairs:
+            assert bits_equal(getattr(got, k_g).cpu().numpy(), case["outputs"][k_c][t]) == 0, (case["name"], t, k_g)
+        assert np.array_equal(got.end_of_video.cpu().numpy(), case["eov"][t])
+    assert np.array_equal(env.state("seg").cpu().numpy(), case["final"]["seg"])
+    assert bits_equal(env.state("phase").cpu().numpy(), case["final"]["phase"]) == 0
+    if not live:
+        env.reset(case["trace_id"], case["start_offset"])
+        tr = env.rollout("fixed", len(case["actions"]), actions=case["actions"])
+        for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                         ("reward", "reward")):
+            assert bits_equal(tr[k_g].cpu().numpy(), case["outputs"][k_c]) == 0, (case["name"], k_g)
+    assert env.error_count() == 0

@@ -6,7 +6,7 @@ import pytest
 from oracle import mpc_oracle as mo
 from oracle import oracle as orc
 from oracle import step_oracle as so
-from helpers import small_world, bits_equal
+from helpers import small_world, bits_equal, load_step_golden
 
 
 def test_philox_known_answer():
@@ -214,3 +214,20 @@ def test_live_mode_agrees_with_fixed_dt_loop():
         assert abs(e["rebuffer"] - rebuf) < tol * max(1.0, speed)
         assert abs(e["latency"] - (sess.t_now - sess.play_time)) < tol * 2
         assert max(abs(a - b) for a, b in zip(e["delays"], delays)) < 0.0031
+
+
+@pytest.mark.parametrize("case", load_step_golden(), ids=lambda c: c["name"])
+def test_c_oracle_reproduces_the_step_spec_fixture(case):
+    """tests/golden/step_spec_golden.json pins SPEC.md §2-§4, §7 (generated by the pure-Python restatement)."""
+    N = len(case["trace_id"])
+    env = orc.OracleEnv(case["bw"], case["tl"], case["ti"], case["sizes"], case["bitrates"], N, **case["params"])
+    env.reset(case["trace_id"], case["start_offset"])
+    for t, a in enumerate(case["actions"]):
+        v = None if case["speeds"] is None else np.full(N, case["speeds"][t % len(case["speeds"])])
+        out = env.step(a, speed=v)
+        for k in ("delay", "sleep", "buffer", "rebuf", "reward", "throughput", "latency"):
+            assert bits_equal(out[k], case["outputs"][k][t]) == 0, (case["name"], t, k)
+        assert np.array_equal(out["eov"], case["eov"][t])
+    assert np.array_equal(env.field("seg"), case["final"]["seg"])
+    assert bits_equal(env.field("phase"), case["final"]["phase"]) == 0
+    assert bits_equal(env.field("buffer"), case["final"]["buffer"]) == 0
