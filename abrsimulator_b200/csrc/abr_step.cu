@@ -31,7 +31,7 @@ namespace abr {
 namespace {
 
 constexpr int kStepBlock = 256;
-constexpr int kStepTiles = 8;       // tiles of kStepBlock sessions per block of the per-step kernel
+constexpr int kStepTiles = 8;       // least number of tiles of kStepBlock sessions per block of the per-step kernel
 constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per SM (balanced over 148 SMs)
 constexpr int kStatsBlock = 256;
 constexpr int kStatsSessionsPerBlock = 1024;   // 64 blocks at 65 536 sessions: enough loads in flight to hide HBM latency
@@ -557,7 +557,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
                 double* __restrict__ o_delay, double* __restrict__ o_sleep, double* __restrict__ o_buffer,
                 double* __restrict__ o_rebuf, double* __restrict__ o_reward, double* __restrict__ o_latency,
                 double* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov, double* __restrict__ o_thr,
-                int smem_doubles) {
+                int smem_doubles, int tiles_per_block) {
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_tr0;
@@ -577,17 +577,17 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     RawState w_next;
     int q_next = 0;
     {
-        const int i0 = blockIdx.x * kStepTiles * kStepBlock + threadIdx.x;
+        const int i0 = blockIdx.x * tiles_per_block * kStepBlock + threadIdx.x;
         if (i0 < v.n) { w_next = load_raw(v, i0); q_next = action[i0]; }
     }
-    for (int k = 0; k < kStepTiles; ++k) {
-        const int tile0 = (blockIdx.x * kStepTiles + k) * kStepBlock;
+    for (int k = 0; k < tiles_per_block; ++k) {
+        const int tile0 = (blockIdx.x * tiles_per_block + k) * kStepBlock;
         if (tile0 >= v.n) break;                 // block-uniform
         const int i = tile0 + threadIdx.x;
         const bool valid = i < v.n;
         const RawState w = w_next;
         const int q_cur = q_next;
-        if (k + 1 < kStepTiles && i + kStepBlock < v.n) { w_next = load_raw(v, i + kStepBlock); q_next = action[i + kStepBlock]; }
+        if (k + 1 < tiles_per_block && i + kStepBlock < v.n) { w_next = load_raw(v, i + kStepBlock); q_next = action[i + kStepBlock]; }
         Sess s;
         int tr = -1;
         if (valid) { make_sess(v, i, w, s); tr = w.tr; }
@@ -915,13 +915,24 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
     const bool live = v.p.live != 0;
     const bool fast = !live && d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov &&
                       v.p.track_history == 0 && v.p.track_acc == 0 && v.p.auto_reset != 0;
-    const unsigned grid = (v.n + kStepBlock * kStepTiles - 1) / (kStepBlock * kStepTiles);
+    // persistent-style grid: one wave of 3 blocks per SM, each walking an equal run of consecutive tiles (at least
+    // kStepTiles, so that small batches still amortise the staging); no tail wave
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sm_count = 148;
+    }
+    const int total_tiles = (v.n + kStepBlock - 1) / kStepBlock;
+    int tiles_per_block = (total_tiles + sm_count * 3 - 1) / (sm_count * 3);
+    if (tiles_per_block < kStepTiles) tiles_per_block = kStepTiles;
+    const unsigned grid = (total_tiles + tiles_per_block - 1) / tiles_per_block;
     // shared-memory row buffer for blocks whose sessions share a trace (3 blocks per SM up to 74 KB per block)
     int smem_doubles = cum_stride(v.T_max);
     size_t smem_bytes = (size_t)smem_doubles * sizeof(double);
     if (smem_bytes > kSmemOptInLimit) { smem_doubles = 0; smem_bytes = 0; }
     cudaError_t e = cudaSuccess;
-#define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr, smem_doubles
+#define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr, smem_doubles, tiles_per_block
 #define ABR_LAUNCH_STEP(F, L)                                                                  \
     do {                                                                                       \
         e = allow_smem(abr_step_kernel<F, L>, smem_bytes);                                     \
