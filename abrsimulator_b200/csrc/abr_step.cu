@@ -171,7 +171,10 @@ __device__ __forceinline__ uint32_t search_cum(const Sess& s, uint32_t p_lo, con
 // are settled by the caller with exact 64-bit compares.  A random 4-byte LDS costs ~3.5 shared-memory wavefronts
 // per warp against ~5.8 for an 8-byte one, and the compare runs on the integer pipe instead of the FP64 pipe —
 // at >= 1 Mi sessions the kernel is bound by exactly those wavefronts (ncu: l1tex__data_pipe_lsu_wavefronts 91 %).
-__device__ __forceinline__ uint32_t search_keys(uint32_t kp_lo, const uint32_t kp_end, int bits, const uint32_t kt) {
+// BITS > 0: compile-time width (every round unrolled, no loop or parity branches); BITS == 0: `bits_rt`.
+template <int BITS>
+__device__ __forceinline__ uint32_t search_keys(uint32_t kp_lo, const uint32_t kp_end, const int bits_rt, const uint32_t kt) {
+    int bits = BITS > 0 ? BITS : bits_rt;
     if (bits & 1) {
         if (bits >= 3) {
             bits -= 3;
@@ -195,6 +198,7 @@ __device__ __forceinline__ uint32_t search_keys(uint32_t kp_lo, const uint32_t k
             if (lds_u32(p1) < kt) kp_lo = p1;
         }
     }
+#pragma unroll
     for (; bits > 0; bits -= 2) {
         const uint32_t st = 4u << (bits - 2);
         const uint32_t p1 = min(kp_lo + st, kp_end), p2 = min(kp_lo + 2 * st, kp_end), p3 = min(kp_lo + 3 * st, kp_end);
@@ -268,8 +272,16 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     uint32_t p_j;
     double c_j, c_j1;
     if (KEYS) {
-        const uint32_t kp = search_keys(s.key_s + ((p_lo - p_base) >> 1), s.key_s + 4u * (uint32_t)T, bits,
-                                        (uint32_t)__double2hiint(target));
+        const uint32_t kp0 = s.key_s + ((p_lo - p_base) >> 1), kp_end = s.key_s + 4u * (uint32_t)T;
+        const uint32_t kt = (uint32_t)__double2hiint(target);
+        uint32_t kp;
+        // the usual widths get fully unrolled searches; a lane whose download wrapped (bits = b_full) takes the
+        // generic one on its own — one lane in ~10 % of the warp-steps, cheaper than a warp vote in every step
+        if (bits == 7) kp = search_keys<7>(kp0, kp_end, 7, kt);
+        else if (bits == 6) kp = search_keys<6>(kp0, kp_end, 6, kt);
+        else if (bits == 8) kp = search_keys<8>(kp0, kp_end, 8, kt);
+        else if (bits == 5) kp = search_keys<5>(kp0, kp_end, 5, kt);
+        else kp = search_keys<0>(kp0, kp_end, bits, kt);
         p_j = p_base + ((kp - s.key_s) << 1);
         c_j = ld_cum<SMEM>(s, p_j);
         c_j1 = ld_cum<SMEM>(s, p_j + 8u);
