@@ -12,17 +12,18 @@
 //
 // SPEC §3.1 integrates the download against the trace's cumulative capacity C[j] (data deliverable from the
 // start of the trace period up to the start of segment j, accumulated left to right once per environment).  A
-// download from position (seg, tau) ends in the segment j with C[j] <= pos + size < C[j+1], which a branch-free
-// descending-power-of-two search finds in b_near = log2(most segments a download can cross) probes that every
-// lane of a warp executes in lock step: no per-segment loop, no divergence between sessions on fast and slow
-// networks, and a dependency chain of one compare per probe instead of one add per segment.  C is the only trace
-// table the step reads (a segment's capacity is C[j+1] - C[j]).
+// download from position (seg, phase) ends in the segment j with C[j] <= pos + size < C[j+1], which a search at
+// descending powers of four (2 for the global path) finds in b_near = log2(most segments a download can cross)
+// bits that every lane of a warp resolves in lock step: no per-segment loop, no divergence between sessions on
+// fast and slow networks, and a dependency chain of one compare per round instead of one add per segment.  C is
+// the only trace table the step reads (a segment's capacity is C[j+1] - C[j]).
 // Two access paths for C:
-//   * shared-memory path (fused episode): when all sessions of a thread block follow the same trace and its C row
-//     fits, the block stages the row in shared memory once (TMA bulk copy) and every probe is an LDS — the "traces
-//     staged in shared memory" design of the north star.  A per-lane scattered global load costs one L1 wavefront
-//     per lane (32 per instruction); an LDS costs 2-5.
-//   * global path (any session order, per-step kernel): read-only loads (ld.global.nc); the table (17 MB at the
+//   * shared-memory path (both kernels): when all sessions of a thread block (a 256-session tile in the per-step
+//     kernel) follow the same trace and its C row fits, the block stages the row in shared memory with a TMA bulk
+//     copy and every probe is an LDS — the "traces staged in shared memory" design of the north star; the fused
+//     episode searches on a staged row of 32-bit keys (the high words of C) and settles ties on C itself.
+//     A per-lane scattered global load costs one L1 wavefront per lane (32 per instruction); an LDS costs 2-6.
+//   * global path (any session order): read-only loads (ld.global.nc), binary search; the table (17 MB at the
 //     benchmark shape) is L2-resident.
 #include "abr_common.cuh"
 

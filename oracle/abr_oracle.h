@@ -53,7 +53,7 @@ void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base,
 void orc_env_mpc_decide(OrcEnv* e, int H, int mode, int32_t* action, double* best_j, int32_t* best_seq);
 /* statistics vector from an acc table (SPEC §6): plain ascending-session sums */
 void orc_stats_from_acc(const double* acc, int N, double* out);
-/* state access for tests: field 0 seg,1 chunk,2 last_q,3 trace_id,4 hist_len (int32) ; 10 tau,11 buffer (double);
+/* state access for tests: field 0 seg,1 chunk,2 last_q,3 trace_id,4 hist_len (int32) ; 10 phase,11 buffer (double);
  * live mode: 16 t_now, 17 play_time (double), 7 started (uint8) */
 const void* orc_env_field(OrcEnv* e, int field);
 int orc_env_error_count(OrcEnv* e);
