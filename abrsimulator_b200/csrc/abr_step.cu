@@ -31,8 +31,10 @@ namespace abr {
 
 namespace {
 
-constexpr int kStepBlock = 256;
-constexpr int kStepTiles = 8;       // least number of tiles of kStepBlock sessions per block of the per-step kernel
+constexpr int kStepBlock = 256;      // helper kernels (reset, tables, cost)
+constexpr int kTile = 128;           // threads per block = sessions per tile of the per-step kernel
+constexpr int kTileBlocksPerSM = 6;
+constexpr int kStepTiles = 8;         // least number of tiles per block of the per-step kernel
 constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per SM (balanced over 148 SMs)
 constexpr int kStatsBlock = 256;
 constexpr int kStatsSessionsPerBlock = 1024;   // 64 blocks at 65 536 sessions: enough loads in flight to hide HBM latency
@@ -559,13 +561,13 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
     }
 }
 
-// <= 64 registers: 4 blocks of 256 threads per SM.  A block walks kStepTiles consecutive tiles of 256 sessions.
+// <= 80 registers: 6 blocks of 128 threads per SM, one wave.  A block walks a run of consecutive tiles of 128 sessions.
 // When all sessions of a tile follow the same trace (callers that keep sessions sorted by trace) and its C row fits
 // in `smem_doubles`, the block stages the row with one TMA bulk copy — once, for as long as the following tiles stay
 // on that trace — and the search probes are LDS; a per-lane scattered global load costs one L1 wavefront per lane,
 // which is what bounds the global path (ncu: l1tex__data_pipe_lsu_wavefronts).
 template <bool FAST, bool LIVE>
-__global__ void __launch_bounds__(kStepBlock, LIVE ? 2 : 3)
+__global__ void __launch_bounds__(kTile, LIVE ? 4 : kTileBlocksPerSM)
 abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __restrict__ speed,
                 double* __restrict__ o_delay, double* __restrict__ o_sleep, double* __restrict__ o_buffer,
                 double* __restrict__ o_rebuf, double* __restrict__ o_reward, double* __restrict__ o_latency,
@@ -590,17 +592,17 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     RawState w_next;
     int q_next = 0;
     {
-        const int i0 = blockIdx.x * tiles_per_block * kStepBlock + threadIdx.x;
+        const int i0 = blockIdx.x * tiles_per_block * kTile + threadIdx.x;
         if (i0 < v.n) { w_next = load_raw(v, i0); q_next = action[i0]; }
     }
     for (int k = 0; k < tiles_per_block; ++k) {
-        const int tile0 = (blockIdx.x * tiles_per_block + k) * kStepBlock;
+        const int tile0 = (blockIdx.x * tiles_per_block + k) * kTile;
         if (tile0 >= v.n) break;                 // block-uniform
         const int i = tile0 + threadIdx.x;
         const bool valid = i < v.n;
         const RawState w = w_next;
         const int q_cur = q_next;
-        if (k + 1 < tiles_per_block && i + kStepBlock < v.n) { w_next = load_raw(v, i + kStepBlock); q_next = action[i + kStepBlock]; }
+        if (k + 1 < tiles_per_block && i + kTile < v.n) { w_next = load_raw(v, i + kTile); q_next = action[i + kTile]; }
         Sess s;
         int tr = -1;
         if (valid) { make_sess(v, i, w, s); tr = w.tr; }
@@ -936,8 +938,8 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
             sm_count = 148;
     }
-    const int total_tiles = (v.n + kStepBlock - 1) / kStepBlock;
-    int tiles_per_block = (total_tiles + sm_count * 3 - 1) / (sm_count * 3);
+    const int total_tiles = (v.n + kTile - 1) / kTile;
+    int tiles_per_block = (total_tiles + sm_count * kTileBlocksPerSM - 1) / (sm_count * kTileBlocksPerSM);
     if (tiles_per_block < kStepTiles) tiles_per_block = kStepTiles;
     const unsigned grid = (total_tiles + tiles_per_block - 1) / tiles_per_block;
     // shared-memory row buffer for blocks whose sessions share a trace (3 blocks per SM up to 74 KB per block)
@@ -949,7 +951,7 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
 #define ABR_LAUNCH_STEP(F, L)                                                                  \
     do {                                                                                       \
         e = allow_smem(abr_step_kernel<F, L>, smem_bytes);                                     \
-        if (e == cudaSuccess) abr_step_kernel<F, L><<<grid, kStepBlock, smem_bytes, st>>>(ABR_STEP_ARGS); \
+        if (e == cudaSuccess) abr_step_kernel<F, L><<<grid, kTile, smem_bytes, st>>>(ABR_STEP_ARGS); \
     } while (0)
     if (live) ABR_LAUNCH_STEP(false, true);
     else if (fast) ABR_LAUNCH_STEP(true, false);
