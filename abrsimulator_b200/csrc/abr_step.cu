@@ -869,15 +869,15 @@ abr_stats_stage1(EnvView v, double* __restrict__ partials) {
     }
 }
 
+// one block per statistic (same summation order per column as a single block walking the columns in turn)
 __global__ void __launch_bounds__(kStatsBlock)
 abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __restrict__ out) {
     __shared__ double sm[32];
-    for (int j = 0; j < ABR_NUM_ACC; ++j) {
-        double x = 0.0;
-        for (int i = threadIdx.x; i < n_partials; i += blockDim.x) x = dadd(x, partials[(size_t)i * ABR_NUM_ACC + j]);
-        x = block_sum(x, sm);
-        if (threadIdx.x == 0) out[j] = x;
-    }
+    const int j = blockIdx.x;
+    double x = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) x = dadd(x, partials[(size_t)i * ABR_NUM_ACC + j]);
+    x = block_sum(x, sm);
+    if (threadIdx.x == 0) out[j] = x;
 }
 
 // Per-session QoE cost of Simulator.calculate_qoe (Simulator.py:83-86) from the accumulators:
@@ -1024,7 +1024,7 @@ cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, b
         abr_stats_stage1<<<n_partials, kStatsBlock, 0, st>>>(v, d_partials);
         count_launch();
     }
-    abr_stats_stage2<<<1, kStatsBlock, 0, st>>>(d_partials, n_partials, d_out);
+    abr_stats_stage2<<<ABR_NUM_ACC, kStatsBlock, 0, st>>>(d_partials, n_partials, d_out);
     count_launch();
     return cudaGetLastError();
 }

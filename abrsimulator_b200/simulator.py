@@ -112,7 +112,10 @@ class Simulator:
         """``n_sessions`` independent sessions; returns a numpy vector of QoE costs (one per session)."""
         V = len(self.mpd.chunks)
         n_traces = len(self.network_info) if isinstance(self.network_info, list) else 1
-        tid = np.arange(n_sessions, dtype=np.int32) % n_traces if trace_id is None else np.asarray(trace_id, np.int32)
+        # default assignment: equal runs of consecutive sessions per trace (sessions sorted by trace take the
+        # shared-memory path of the kernels, DESIGN.md §4)
+        tid = ((np.arange(n_sessions, dtype=np.int64) * n_traces) // max(n_sessions, 1)).astype(np.int32) \
+            if trace_id is None else np.asarray(trace_id, np.int32)
         ctrl = self.abr_controller
         q = self.qoe_metric
         if self._live():
