@@ -649,7 +649,8 @@ struct RolloutOut {
 // `steps` chunk steps of one session with the state in registers (SPEC §3+§4).
 // FAST: the common shape — all six trajectory outputs requested, no action trace, no throughput history,
 // auto_reset on — compiled without the per-output null checks and the inert/history bookkeeping.
-template <int POLICY, bool SMEM, bool FAST>
+// NOOUT (with FAST): no trajectory output at all (statistics / per-session accumulators only, e.g. abr_env_run_host).
+template <int POLICY, bool SMEM, bool FAST, bool NOOUT>
 __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const int i, const uint32_t seed_lo,
                                                 const uint32_t seed_hi, const int steps,
                                                 const int32_t* __restrict__ actions_in, const RolloutOut& o,
@@ -691,7 +692,8 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         step_core<SMEM, true, FAST, false, SMEM>(v, s, q, lk, r, hist);   // shared-memory path searches on the keys
         flagged |= r.walk_error;
         const size_t ix = (size_t)t * n + i;
-        if (FAST) {
+        if (NOOUT) {
+        } else if (FAST) {
             __stcs(o.delay + ix, r.delay); __stcs(o.sleep + ix, r.sleep); __stcs(o.buffer + ix, r.buffer);
             __stcs(o.rebuf + ix, r.rebuf); __stcs(o.reward + ix, r.reward);
             o.eov[ix] = r.eov ? 1 : 0;
@@ -742,7 +744,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
 // is followed by the key row (key_stride(T_max) words, 16-byte aligned) and the sizes and utility tables.
 // 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
 // co-resident (6.9 per SM); at 140 registers only 3 warps fit per scheduler and a second wave appears.
-template <int POLICY, bool FAST>
+template <int POLICY, bool FAST, bool NOOUT>
 __global__ void __launch_bounds__(kRolloutBlock, 8)
 abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
                    RolloutOut o, int smem_doubles, double* __restrict__ block_partials) {
@@ -810,10 +812,10 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
             // keep the three addresses in registers: left alone, the compiler rematerialises them from
             // SR_CgaCtaId (an S2R round trip) at every use inside the step loop
             asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s), "+r"(s.key_s));
-            rollout_session<POLICY, true, FAST>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+            rollout_session<POLICY, true, FAST, NOOUT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
         }
     } else if (valid) {
-        rollout_session<POLICY, false, FAST>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+        rollout_session<POLICY, false, FAST, NOOUT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
     }
     // statistics stage 1 fused into the episode: per-block sums of the updated accumulators in a fixed order
     // (warp tree, then warps in ascending order), so abr_stats_partial only has to add the block partials
@@ -979,18 +981,21 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     if (smem_bytes > kSmemOptInLimit) { smem_doubles = 0; smem_bytes = 0; }
     const bool fast = d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && !d_actions_out &&
                       v.p.track_history == 0 && v.p.auto_reset != 0;
+    const bool none = !d_delay && !d_sleep && !d_buffer && !d_rebuf && !d_reward && !d_eov && !d_actions_out &&
+                      v.p.track_history == 0 && v.p.auto_reset != 0;
     cudaError_t e = cudaSuccess;
-#define ABR_LAUNCH_ROLLOUT_V(P, F)                                                                                 \
+#define ABR_LAUNCH_ROLLOUT_V(P, F, N)                                                                              \
     do {                                                                                                           \
-        e = allow_smem(abr_rollout_kernel<P, F>, smem_bytes);                                                      \
+        e = allow_smem(abr_rollout_kernel<P, F, N>, smem_bytes);                                                   \
         if (e == cudaSuccess)                                                                                      \
-            abr_rollout_kernel<P, F><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,            \
-                                                                      smem_doubles, d_block_partials);             \
+            abr_rollout_kernel<P, F, N><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,         \
+                                                                         smem_doubles, d_block_partials);          \
     } while (0)
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
     do {                                                                                                           \
-        if (fast) ABR_LAUNCH_ROLLOUT_V(P, true);                                                                   \
-        else ABR_LAUNCH_ROLLOUT_V(P, false);                                                                       \
+        if (fast) ABR_LAUNCH_ROLLOUT_V(P, true, false);                                                            \
+        else if (none) ABR_LAUNCH_ROLLOUT_V(P, true, true);                                                        \
+        else ABR_LAUNCH_ROLLOUT_V(P, false, false);                                                                \
     } while (0)
     switch (policy) {
         case ABR_POLICY_FIXED: ABR_LAUNCH_ROLLOUT(ABR_POLICY_FIXED); break;
