@@ -48,7 +48,12 @@ def parse():
     ap.add_argument("--step-sessions", type=int, default=1 << 22, help="sessions per GPU of the per-step-launch leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of each cpu_baseline sample")
-    return ap.parse_args()
+    ap.add_argument("--group", type=int, default=GROUP,
+                    help="consecutive sessions per trace (default 64: every 64-thread block of the fused kernel follows "
+                         "one trace and stages it in shared memory; 1 = trace = session mod n_traces, global path)")
+    args = ap.parse_args()
+    globals()["GROUP"] = args.group
+    return args
 
 
 # ------------------------------------------------------------------------------------------------
