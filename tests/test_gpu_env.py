@@ -652,3 +652,53 @@ def test_kernels_reproduce_the_step_spec_fixture(case):
                          ("reward", "reward")):
             assert bits_equal(tr[k_g].cpu().numpy(), case["outputs"][k_c]) == 0, (case["name"], k_g)
     assert env.error_count() == 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomized_worlds_match_oracle(seed):
+    """Differential fuzz: 25 random worlds per seed — trace lengths 1..400, arbitrary (non power-of-two) intervals,
+    bandwidths spanning six orders of magnitude, zero-size chunks, rtt 0, many-period downloads, ragged ladders —
+    through the fused episode (sorted and shuffled sessions) and the per-step kernel."""
+    rng = np.random.default_rng(1000 + seed)
+    for w in range(25):
+        n_traces = int(rng.integers(1, 6))
+        T = int(rng.choice([1, 2, 3, 17, 64, 255, 400]))
+        V = int(rng.integers(1, 14))
+        A = int(rng.integers(1, 9))
+        scale = 10.0 ** rng.uniform(-3, 3)
+        bw = scale * 10.0 ** rng.uniform(-1.5, 1.5, size=(n_traces, T))
+        tl = rng.integers(1, T + 1, size=n_traces).astype(np.int32)
+        ti = rng.choice([0.25, 0.3, 0.5, 1.0, 1.7, 2.0], size=n_traces)
+        bitrates = np.sort(rng.uniform(100.0, 5000.0, size=(V, A)), axis=1)
+        sizes = bitrates / 1000.0 * 4.0 * rng.uniform(0.5, 1.5, size=(V, A)) * 10.0 ** rng.uniform(-1, 1)
+        if rng.random() < 0.3:
+            sizes[rng.integers(0, V), rng.integers(0, A)] = 0.0
+        params = dict(rtt=float(rng.choice([0.0, 0.08])), payload=float(rng.choice([0.95, 1.0])),
+                      max_buffer=float(rng.choice([8.0, 20.0, 60.0])), sleep_quantum=float(rng.choice([0.3, 0.5])),
+                      default_quality=int(rng.integers(-1, A)), auto_reset=int(rng.integers(0, 2)))
+        N = 64 * int(rng.integers(1, 5)) + int(rng.integers(0, 64))
+        tid = np.sort(rng.integers(0, n_traces, size=N)).astype(np.int32)
+        if w % 3 == 0:
+            tid = rng.permutation(tid)
+        off = rng.uniform(0, 3.0 * float(np.max(tl * ti)), size=N)
+        steps = int(rng.integers(1, 2 * V + 3))
+        env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, **params)
+        ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **params)
+        tag = f"seed {seed} world {w}"
+        env.reset(tid, off)
+        ref.reset(tid, off)
+        got = env.rollout("random", steps, seed=w)
+        exp = ref.rollout(orc.POLICY_RANDOM, steps, seed=w)
+        for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                         ("reward", "reward")):
+            assert bits_equal(got[k_g].cpu().numpy(), exp[k_c]) == 0, (tag, "fused", k_g)
+        assert np.array_equal(got["end_of_video"].cpu().numpy(), exp["eov"]), tag
+        check_state(env, ref)
+        for t in range(min(steps, 6)):
+            a = rng.integers(0, A, size=N).astype(np.int32)
+            g, e = env.step(a), ref.step(a)
+            for k_g, k_c in (("delay", "delay"), ("buffer", "buffer"), ("rebuffer", "rebuf"), ("reward", "reward")):
+                assert bits_equal(getattr(g, k_g).cpu().numpy(), e[k_c]) == 0, (tag, "step", t, k_g)
+        check_state(env, ref)
+        # a download that needs more than 2^20 trace periods trips the same guard on both sides (SPEC §3.1)
+        assert (env.error_count() == 0) == (ref.errors() == 0), tag
