@@ -82,7 +82,7 @@ __device__ __forceinline__ double ld_cum(const Sess& s, uint32_t pos) {
 }
 
 // The table reads of one step (SPEC §3.1 size, §3.4 utilities).  They depend only on (chunk, q, last_q), so the fused
-// episode issues them one step ahead for the policies whose action does not depend on the state.
+// episode issues them at the end of the previous step.
 struct Lookup { double size, u, u_prev; };
 
 template <bool SMEM>
