@@ -276,20 +276,30 @@ int abr_env_qoe_cost(AbrEnv* env, double* d_out, void* stream) {
     return ABR_OK;
 }
 
-int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
-                          double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
-                          uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream) {
+int abr_env_rollout_fused_live(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                               const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer,
+                               double* d_rebuf, double* d_reward, double* d_latency, uint8_t* d_end_of_video,
+                               int32_t* d_actions_out, void* stream) {
     if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
     if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
     if (env->v.n == 0) return ABR_OK;
     if (steps < 0) return fail(ABR_ERR_RANGE, "steps must be >= 0");
     if (policy < ABR_POLICY_FIXED || policy > ABR_POLICY_BBA) return fail(ABR_ERR_INVALID, "unknown policy %d", policy);
     if (policy == ABR_POLICY_FIXED && !d_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs d_actions_in");
-    if (env->v.p.live) return fail(ABR_ERR_STATE, "the fused episode does not implement live mode (SPEC 7): use abr_env_step_live");
-    CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_delay, d_sleep, d_buffer, d_rebuf, d_reward,
-                            d_end_of_video, d_actions_out, env->d_stats_partials, (cudaStream_t)stream));
+    if (!env->v.p.live && (d_speed || d_latency))
+        return fail(ABR_ERR_STATE, "speed / latency belong to live mode (SPEC 7): create the environment with live = 1");
+    CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
+                            d_reward, d_latency, d_end_of_video, d_actions_out, env->d_stats_partials,
+                            (cudaStream_t)stream));
     env->fresh_partials = steps > 0 ? rollout_num_blocks(env->v.n) : 0;
     return ABR_OK;
+}
+
+int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                          double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
+                          uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream) {
+    return abr_env_rollout_fused_live(env, policy, seed, steps, d_actions_in, nullptr, d_delay, d_sleep, d_buffer,
+                                      d_rebuf, d_reward, nullptr, d_end_of_video, d_actions_out, stream);
 }
 
 static int check_mpc_shape(int A, int H) {

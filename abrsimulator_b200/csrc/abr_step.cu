@@ -237,6 +237,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     double phi = s.phi;
     int seg = s.seg;
     double live_buffer = s.buffer, live_rebuf = 0.0, live_idle = 0.0, live_startup = 0.0;
+    bool live_moved = false;   // the pause gate moved the trace position: the carried C[seg], C[seg+1] are stale
     if (LIVE) {   // 7.1 pause gate (Simulator.py:143-145): live edge, then room in the buffer
         const double w1 = max0(dsub(dmul((double)(s.chunk + 1), p.chunk_length), s.t_now));
         live_rebuf = live_play(s, live_buffer, live_startup, w1);
@@ -246,14 +247,14 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
                               : 0.0;
         live_rebuf = dadd(live_rebuf, live_play(s, live_buffer, live_startup, w2));
         live_idle = dadd(w1, w2);
-        if (live_idle > 0.0) advance_trace(seg, phi, live_idle, s.I, s.T);
+        if (live_idle > 0.0) { advance_trace(seg, phi, live_idle, s.I, s.T); live_moved = true; }
     }
     // 3.1 download against the cumulative capacity (Simulator.py:158-163 in closed form, with wrap-around)
     const int T = s.T;
     const uint32_t p_base = SMEM ? s.cum_s : 0u;          // byte position of C[0]
     const uint32_t p_end = p_base + 8u * (uint32_t)T;     // ... of C[T]
     double c_seg = s.c_seg, c_seg1 = s.c_seg1;
-    if (!CARRY) {
+    if (!CARRY || (LIVE && live_moved)) {
         c_seg = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg);
         c_seg1 = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg + 8u);
     }
@@ -644,19 +645,22 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
 struct RolloutOut {
     double* __restrict__ delay; double* __restrict__ sleep; double* __restrict__ buffer; double* __restrict__ rebuf;
     double* __restrict__ reward; uint8_t* __restrict__ eov; int32_t* __restrict__ actions;
+    double* __restrict__ latency;            // live mode only (SPEC §7), nullable
+    const double* __restrict__ speed;        // live mode only: playback speed [steps][N], nullable = 1.0
 };
 
 // `steps` chunk steps of one session with the state in registers (SPEC §3+§4).
 // FAST: the common shape — all six trajectory outputs requested, no action trace, no throughput history,
 // auto_reset on — compiled without the per-output null checks and the inert/history bookkeeping.
 // NOOUT (with FAST): no trajectory output at all (statistics / per-session accumulators only, e.g. abr_env_run_host).
-template <int POLICY, bool SMEM, bool FAST, bool NOOUT>
+// LIVE (never with FAST): live-streaming semantics of SPEC §7.
+template <int POLICY, bool SMEM, bool FAST, bool NOOUT, bool LIVE>
 __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const int i, const uint32_t seed_lo,
                                                 const uint32_t seed_hi, const int steps,
                                                 const int32_t* __restrict__ actions_in, const RolloutOut& o,
                                                 double (&acc_new)[ABR_NUM_ACC]) {
     const unsigned long long gsession = (unsigned long long)(v.session_base + i);
-    double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0;
+    double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_su = 0.0, a_lat = 0.0;
     int n_steps = 0, n_eps = 0;
     bool flagged = false, reset_mpc = false;
     const int n = v.n;
@@ -664,6 +668,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     uint32_t packed = 0u;   // random policy: the four actions of one Philox block, one per byte
     s.c_seg = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg);
     s.c_seg1 = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg + 8u);
+    if (LIVE) { s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0; s.speed = 1.0; }
     // SPEC §4 action of step t; must be called with increasing t.  FIXED clamps t to the last row so that the
     // one-step-ahead call after the final step stays inside the caller's table.
     auto action_at = [&](const int t) -> int {
@@ -689,9 +694,13 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);
     for (int t = 0; t < steps; ++t) {
         StepRes r;
-        step_core<SMEM, true, FAST, false, SMEM>(v, s, q, lk, r, hist);   // shared-memory path searches on the keys
-        flagged |= r.walk_error;
         const size_t ix = (size_t)t * n + i;
+        if (LIVE && o.speed) {
+            s.speed = __ldg(o.speed + ix);
+            if (!(s.speed > 0.0)) { flagged = true; s.speed = 1.0; }
+        }
+        step_core<SMEM, true, FAST, LIVE, SMEM>(v, s, q, lk, r, hist);   // shared-memory path searches on the keys
+        flagged |= r.walk_error;
         if (NOOUT) {
         } else if (FAST) {
             __stcs(o.delay + ix, r.delay); __stcs(o.sleep + ix, r.sleep); __stcs(o.buffer + ix, r.buffer);
@@ -704,10 +713,12 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             if (o.rebuf) __stcs(o.rebuf + ix, r.rebuf);
             if (o.reward) __stcs(o.reward + ix, r.reward);
             if (o.eov) o.eov[ix] = r.eov ? 1 : 0;
+            if (LIVE && o.latency) __stcs(o.latency + ix, r.latency);
         }
         if (FAST || !r.inert) {
             a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
             a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
+            if (LIVE) { a_su = dadd(a_su, r.startup); a_lat = dadd(a_lat, r.latency); }
             n_steps += 1;
             n_eps += r.eov ? 1 : 0;
             if (hist) {
@@ -723,13 +734,14 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     const double a_steps = (double)n_steps, a_eps = (double)n_eps;   // exact: counts below 2^31
     if (flagged) atomicAdd(v.errors, 1ull);
     v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
+    if (LIVE) { v.t_now[i] = s.t_now; v.play_time[i] = s.play_time; v.started[i] = s.started ? 1 : 0; }
     if (hist) v.hist_len[i] = s.hist_len;
     if (reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
     if (!FAST && s.done) v.done[i] = 1;
     // accumulator read-modify-write: all eight loads first (one memory round trip instead of eight dependent ones)
     double* a = v.acc + i;
     const size_t c = v.cap;
-    const double add[ABR_NUM_ACC] = {a_rew, a_reb, a_u, a_sm, a_sl, a_dl, a_steps, a_eps, 0.0, 0.0};   // not live
+    const double add[ABR_NUM_ACC] = {a_rew, a_reb, a_u, a_sm, a_sl, a_dl, a_steps, a_eps, a_su, a_lat};
     double old[ABR_NUM_ACC];
 #pragma unroll
     for (int j = 0; j < ABR_NUM_ACC; ++j) old[j] = __ldcg(a + j * c);
@@ -744,8 +756,8 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
 // is followed by the key row (key_stride(T_max) words, 16-byte aligned) and the sizes and utility tables.
 // 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
 // co-resident (6.9 per SM); at 140 registers only 3 warps fit per scheduler and a second wave appears.
-template <int POLICY, bool FAST, bool NOOUT>
-__global__ void __launch_bounds__(kRolloutBlock, 8)
+template <int POLICY, bool FAST, bool NOOUT, bool LIVE>
+__global__ void __launch_bounds__(kRolloutBlock, LIVE ? 6 : 8)
 abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
                    RolloutOut o, int smem_doubles, double* __restrict__ block_partials) {
     extern __shared__ __align__(16) double2 s_row2[];
@@ -812,10 +824,10 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
             // keep the three addresses in registers: left alone, the compiler rematerialises them from
             // SR_CgaCtaId (an S2R round trip) at every use inside the step loop
             asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s), "+r"(s.key_s));
-            rollout_session<POLICY, true, FAST, NOOUT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+            rollout_session<POLICY, true, FAST, NOOUT, LIVE>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
         }
     } else if (valid) {
-        rollout_session<POLICY, false, FAST, NOOUT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+        rollout_session<POLICY, false, FAST, NOOUT, LIVE>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
     }
     // statistics stage 1 fused into the episode: per-block sums of the updated accumulators in a fixed order
     // (warp tree, then warps in ascending order), so abr_stats_partial only has to add the block partials
@@ -966,12 +978,14 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
 }
 
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
-                           double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
-                           uint8_t* d_eov, int32_t* d_actions_out, double* d_block_partials, cudaStream_t st) {
+                           const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf,
+                           double* d_reward, double* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
+                           double* d_block_partials, cudaStream_t st) {
     if (v.n == 0 || steps <= 0) return cudaSuccess;
     const dim3 grid((v.n + kRolloutBlock - 1) / kRolloutBlock), block(kRolloutBlock);
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
-    RolloutOut o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out};
+    RolloutOut o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out, d_latency, d_speed};
+    const bool live = v.p.live != 0;
     // shared-memory row buffer: the longest C row when it leaves room for >= 7 blocks per SM, else disabled
     int smem_doubles = cum_stride(v.T_max);
     size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double) +
@@ -979,23 +993,24 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     // <= 31 KB keeps 7 blocks per SM resident (the 65 536-session shape is then one wave); longer traces opt in to
     // more shared memory and run with fewer blocks per SM, which still beats scattered global probes
     if (smem_bytes > kSmemOptInLimit) { smem_doubles = 0; smem_bytes = 0; }
-    const bool fast = d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && !d_actions_out &&
+    const bool fast = !live && d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && !d_actions_out &&
                       v.p.track_history == 0 && v.p.auto_reset != 0;
-    const bool none = !d_delay && !d_sleep && !d_buffer && !d_rebuf && !d_reward && !d_eov && !d_actions_out &&
+    const bool none = !live && !d_delay && !d_sleep && !d_buffer && !d_rebuf && !d_reward && !d_eov && !d_actions_out &&
                       v.p.track_history == 0 && v.p.auto_reset != 0;
     cudaError_t e = cudaSuccess;
-#define ABR_LAUNCH_ROLLOUT_V(P, F, N)                                                                              \
+#define ABR_LAUNCH_ROLLOUT_V(P, F, N, L)                                                                           \
     do {                                                                                                           \
-        e = allow_smem(abr_rollout_kernel<P, F, N>, smem_bytes);                                                   \
+        e = allow_smem(abr_rollout_kernel<P, F, N, L>, smem_bytes);                                                \
         if (e == cudaSuccess)                                                                                      \
-            abr_rollout_kernel<P, F, N><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,         \
-                                                                         smem_doubles, d_block_partials);          \
+            abr_rollout_kernel<P, F, N, L><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,      \
+                                                                            smem_doubles, d_block_partials);       \
     } while (0)
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
     do {                                                                                                           \
-        if (fast) ABR_LAUNCH_ROLLOUT_V(P, true, false);                                                            \
-        else if (none) ABR_LAUNCH_ROLLOUT_V(P, true, true);                                                        \
-        else ABR_LAUNCH_ROLLOUT_V(P, false, false);                                                                \
+        if (live) ABR_LAUNCH_ROLLOUT_V(P, false, false, true);                                                     \
+        else if (fast) ABR_LAUNCH_ROLLOUT_V(P, true, false, false);                                                \
+        else if (none) ABR_LAUNCH_ROLLOUT_V(P, true, true, false);                                                 \
+        else ABR_LAUNCH_ROLLOUT_V(P, false, false, false);                                                         \
     } while (0)
     switch (policy) {
         case ABR_POLICY_FIXED: ABR_LAUNCH_ROLLOUT(ABR_POLICY_FIXED); break;

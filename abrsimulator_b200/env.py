@@ -185,8 +185,9 @@ class BatchedABREnv:
 
     # -- SPEC §3+§4 --
     def rollout(self, policy, steps, seed=0, actions=None, want=("delay", "sleep", "buffer", "rebuffer", "reward",
-                                                                "end_of_video", "actions"), out=None):
-        """`steps` chunk steps in one fused launch.  Returns a dict of [steps, N] device tensors."""
+                                                                "end_of_video", "actions"), out=None, speed=None):
+        """`steps` chunk steps in one fused launch.  Returns a dict of [steps, N] device tensors.  In live mode
+        (SPEC §7) ``speed`` is the playback-speed table [steps, N] (default 1.0) and "latency" may be wanted."""
         pid = _policy_id(policy)
         n = self.n
         a_in = None
@@ -196,16 +197,21 @@ class BatchedABREnv:
             a_in = self._dev(actions, torch.int32)
             if a_in.numel() != steps * n:
                 raise ValueError("actions must be [steps, N]")
+        v = None
+        if speed is not None:
+            v = self._dev(speed, torch.float64)
+            if v.numel() != steps * n:
+                raise ValueError("speed must be [steps, N]")
         if out is None:
             out = {}
             for k in want:
                 dt = torch.uint8 if k == "end_of_video" else torch.int32 if k == "actions" else torch.float64
                 out[k] = self._empty(steps, n, dtype=dt)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.abr_env_rollout_fused(
-                self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), _ptr(a_in), _ptr(out.get("delay")),
+            _lib.check(self._lib.abr_env_rollout_fused_live(
+                self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), _ptr(a_in), _ptr(v), _ptr(out.get("delay")),
                 _ptr(out.get("sleep")), _ptr(out.get("buffer")), _ptr(out.get("rebuffer")), _ptr(out.get("reward")),
-                _ptr(out.get("end_of_video")), _ptr(out.get("actions")), _stream()))
+                _ptr(out.get("latency")), _ptr(out.get("end_of_video")), _ptr(out.get("actions")), _stream()))
         return out
 
     # -- SPEC §5 --

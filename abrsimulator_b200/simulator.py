@@ -155,9 +155,19 @@ class Simulator:
             for _ in range(V):
                 act = env.mpc_decide(ctrl.horizon, mode)
                 env.step(act, want_next_sizes=False, speed=self._speeds(n_sessions))
-        else:
+        elif isinstance(ctrl, (RandomPolicy, BufferBasedPolicy, FixedPolicy)) or ctrl is None:
+            # built-in policies: one fused live episode (abr_env_rollout_fused_live), speed table from the controller
             if isinstance(ctrl, BufferBasedPolicy):
                 extra.update(bba_reservoir=ctrl.reservoir, bba_cushion=ctrl.cushion)
+            env = self._make_env(n_sessions, **extra)
+            env.reset(tid, start_offset, session_base)
+            speed = None
+            if self.speed_controller is not None:
+                speed = np.stack([self._speeds(n_sessions) for _ in range(V)])
+            policy = "random" if isinstance(ctrl, RandomPolicy) else "fixed" if isinstance(ctrl, FixedPolicy) else "bba"
+            env.rollout(policy, V, seed=getattr(ctrl, "seed", 0), actions=getattr(ctrl, "actions", None), speed=speed,
+                        want=())
+        else:
             env = self._make_env(n_sessions, **extra)
             self._run_callback(env, n_sessions, tid, start_offset, session_base)
         acc = env.session_acc().cpu().numpy()

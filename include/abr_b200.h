@@ -114,6 +114,15 @@ int abr_env_step_live(AbrEnv* env, const int32_t* d_action, const double* d_spee
 int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                           double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
                           uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream);
+/* The same episode with the live-streaming outputs (SPEC §7, live = 1): d_speed is the playback speed of every
+ * session at every step ([steps][N], nullable = 1.0; speed_controller.get_next_speed, Simulator.py:177), d_latency
+ * the per-step latency ([steps][N], nullable), d_sleep the idle time before each download.  With live = 0 it is
+ * abr_env_rollout_fused and both extra pointers must be NULL; abr_env_rollout_fused on a live environment plays
+ * every session at speed 1. */
+int abr_env_rollout_fused_live(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                               const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer,
+                               double* d_rebuf, double* d_reward, double* d_latency, uint8_t* d_end_of_video,
+                               int32_t* d_actions_out, void* stream);
 /* MPC decision for every session from the env's own state and history ring (SPEC §5);
  * never flags errors (implies ABR_MPC_TRUNCATE | ABR_MPC_EMPTY_DEFAULT). */
 int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, double* d_best_j /*nullable*/,

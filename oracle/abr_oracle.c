@@ -297,27 +297,30 @@ static int policy_action(OrcEnv* e, int s, int policy, uint64_t seed, int64_t se
     return q > A - 1 ? A - 1 : q;
 }
 
-void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,
-                     const int32_t* actions_in, double* delay, double* sleep, double* buffer, double* rebuf,
-                     double* reward, uint8_t* eov, int32_t* actions_out, double* acc) {
+void orc_env_rollout_live(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,
+                          const int32_t* actions_in, const double* speed /*[steps][N] or NULL*/, double* delay,
+                          double* sleep, double* buffer, double* rebuf, double* reward, double* latency, uint8_t* eov,
+                          int32_t* actions_out, double* acc) {
     const int N = e->N;
     for (int s = 0; s < N; ++s) {
-        double a_rew = 0, a_reb = 0, a_u = 0, a_sm = 0, a_sl = 0, a_dl = 0, a_steps = 0, a_eps = 0;
+        double a_rew = 0, a_reb = 0, a_u = 0, a_sm = 0, a_sl = 0, a_dl = 0, a_steps = 0, a_eps = 0, a_su = 0, a_lat = 0;
         for (int t = 0; t < steps; ++t) {
             int q = policy_action(e, s, policy, seed, session_base, t, actions_in);
             StepOut o;
-            step_one(e, s, q, 1.0, &o);
             size_t ix = (size_t)t * N + s;
+            step_one(e, s, q, speed ? speed[ix] : 1.0, &o);
             if (delay) delay[ix] = o.delay;
             if (sleep) sleep[ix] = o.sleep;
             if (buffer) buffer[ix] = o.buffer;
             if (rebuf) rebuf[ix] = o.rebuf;
             if (reward) reward[ix] = o.reward;
+            if (latency) latency[ix] = o.latency;
             if (eov) eov[ix] = o.eov;
             if (actions_out) actions_out[ix] = q;
             if (!o.inert) {
                 a_rew = a_rew + o.reward; a_reb = a_reb + o.rebuf; a_u = a_u + o.u;
                 a_sm = a_sm + o.smooth; a_sl = a_sl + o.sleep; a_dl = a_dl + o.delay;
+                a_su = a_su + o.startup; a_lat = a_lat + o.latency;
                 a_steps += 1.0; if (o.eov) a_eps += 1.0;
             }
         }
@@ -325,9 +328,16 @@ void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base,
             acc[0 * (size_t)N + s] = a_rew; acc[1 * (size_t)N + s] = a_reb; acc[2 * (size_t)N + s] = a_u;
             acc[3 * (size_t)N + s] = a_sm; acc[4 * (size_t)N + s] = a_sl; acc[5 * (size_t)N + s] = a_dl;
             acc[6 * (size_t)N + s] = a_steps; acc[7 * (size_t)N + s] = a_eps;
-            acc[8 * (size_t)N + s] = 0.0; acc[9 * (size_t)N + s] = 0.0;   /* the fused episode is not live */
+            acc[8 * (size_t)N + s] = a_su; acc[9 * (size_t)N + s] = a_lat;   /* 0 outside live mode */
         }
     }
+}
+
+void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,
+                     const int32_t* actions_in, double* delay, double* sleep, double* buffer, double* rebuf,
+                     double* reward, uint8_t* eov, int32_t* actions_out, double* acc) {
+    orc_env_rollout_live(e, policy, seed, session_base, steps, actions_in, 0, delay, sleep, buffer, rebuf, reward, 0,
+                         eov, actions_out, acc);
 }
 
 void orc_stats_from_acc(const double* acc, int N, double* out) {

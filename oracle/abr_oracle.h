@@ -46,6 +46,10 @@ void orc_env_step_live(OrcEnv* e, const int32_t* action, const double* speed, do
                        double* buffer, double* rebuf, double* reward, double* latency, double* next_sizes,
                        uint8_t* eov, double* throughput, double* acc /* [ORC_NUM_ACC][N] accumulated into, nullable */);
 /* fused episode (SPEC §3+§4): trajectories are [steps][N]; acc is [ORC_NUM_ACC][N] */
+void orc_env_rollout_live(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,
+                          const int32_t* actions_in, const double* speed /*[steps][N] or NULL*/, double* delay,
+                          double* sleep, double* buffer, double* rebuf, double* reward, double* latency, uint8_t* eov,
+                          int32_t* actions_out, double* acc);
 void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,
                      const int32_t* actions_in, double* delay, double* sleep, double* buffer, double* rebuf,
                      double* reward, uint8_t* eov, int32_t* actions_out, double* acc);

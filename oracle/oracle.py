@@ -138,19 +138,21 @@ class OracleEnv:
                                 _p(out["eov"]), _p(out["throughput"]), _p(acc))
         return out
 
-    def rollout(self, policy, steps, seed=0, session_base=0, actions=None, want_traj=True):
+    def rollout(self, policy, steps, seed=0, session_base=0, actions=None, want_traj=True, speed=None):
+        """Fused-episode semantics (SPEC §3+§4; §7 with ``speed`` [steps, N] when live = 1)."""
         N = self.N
         a_in = None if actions is None else _i32(actions)
+        v = None if speed is None else _f64(speed)
         tr = dict(acc=np.empty((NUM_ACC, N)))
         if want_traj:
-            for k in ("delay", "sleep", "buffer", "rebuf", "reward"):
+            for k in ("delay", "sleep", "buffer", "rebuf", "reward", "latency"):
                 tr[k] = np.empty((steps, N))
             tr["eov"] = np.empty((steps, N), np.uint8)
             tr["actions"] = np.empty((steps, N), np.int32)
-        lib().orc_env_rollout(self._h, C.c_int(policy), C.c_uint64(seed), C.c_int64(session_base), C.c_int(steps),
-                              _p(a_in), _p(tr.get("delay")), _p(tr.get("sleep")), _p(tr.get("buffer")),
-                              _p(tr.get("rebuf")), _p(tr.get("reward")), _p(tr.get("eov")), _p(tr.get("actions")),
-                              _p(tr["acc"]))
+        lib().orc_env_rollout_live(self._h, C.c_int(policy), C.c_uint64(seed), C.c_int64(session_base), C.c_int(steps),
+                                   _p(a_in), _p(v), _p(tr.get("delay")), _p(tr.get("sleep")), _p(tr.get("buffer")),
+                                   _p(tr.get("rebuf")), _p(tr.get("reward")), _p(tr.get("latency")), _p(tr.get("eov")),
+                                   _p(tr.get("actions")), _p(tr["acc"]))
         return tr
 
     def mpc_decide(self, H, mode, want_seq=False):

@@ -390,9 +390,58 @@ def test_live_mode_step_matches_oracle(ragged):
     np.testing.assert_allclose(env.qoe_cost().cpu().numpy(), want, rtol=1e-12)
     assert env.error_count() == 0
     with pytest.raises(_lib.AbrError):
-        env.rollout("bba", 4)                     # the fused episode refuses live mode
-    with pytest.raises(_lib.AbrError):
         BatchedABREnv(np.ones((1, 8)), np.ones((2, 3)), np.ones((2, 3)), 4, live=1, start_up_length=100.0)
+
+
+@pytest.mark.parametrize("policy", ["random", "bba", "fixed"])
+def test_fused_live_episode_matches_oracle(policy):
+    """SPEC §7 in the fused episode: speed table [steps][N], latency output, start-up / latency accumulators,
+    sorted (shared-memory path) and mixed blocks; and the same episode step by step."""
+    N, steps = 64 * 9 + 21, 75
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=5, T=300, V=30, ragged=(policy == "bba"))
+    P = dict(LIVE, track_history=1)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, **P)
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **P)
+    rng = np.random.default_rng(31)
+    tid = ((np.arange(N) // 64) % 5).astype(np.int32)
+    tid[64 * 4:64 * 6] = rng.integers(0, 5, size=128)            # two mixed blocks -> global path
+    off = rng.uniform(0, 500.0, size=N)
+    speed = rng.choice([0.75, 1.0, 1.0, 1.25, 1.5], size=(steps, N))
+    acts = rng.integers(0, env.A, size=(steps, N)).astype(np.int32) if policy == "fixed" else None
+    pid = dict(random=orc.POLICY_RANDOM, bba=orc.POLICY_BBA, fixed=orc.POLICY_FIXED)[policy]
+    env.reset(tid, off)
+    ref.reset(tid, off)
+    want = ("delay", "sleep", "buffer", "rebuffer", "reward", "latency", "end_of_video", "actions")
+    got = env.rollout(policy, steps, seed=77, actions=acts, speed=speed, want=want)
+    exp = ref.rollout(pid, steps, seed=77, actions=acts, speed=speed)
+    assert np.array_equal(got["actions"].cpu().numpy(), exp["actions"])
+    for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                     ("reward", "reward"), ("latency", "latency")):
+        assert_close(got[k_g].cpu().numpy(), exp[k_c], k_g)
+    assert np.array_equal(got["end_of_video"].cpu().numpy(), exp["eov"])
+    assert_close(env.session_acc().cpu().numpy(), exp["acc"], "acc")
+    assert exp["acc"][8].min() > 0 and exp["acc"][9].min() > 0
+    check_state(env, ref)
+    for f in ("t_now", "play_time"):
+        assert bits_equal(env.state(f).cpu().numpy(), ref.field(f)) == 0, f
+    assert np.array_equal(env.state("started").cpu().numpy(), ref.field("started"))
+    # the same actions and speeds through the per-step kernel
+    env.reset(tid, off)
+    a_all = got["actions"]
+    for t in range(steps):
+        r = env.step(a_all[t], speed=speed[t])
+        assert bits_equal(r.reward.cpu().numpy(), exp["reward"][t]) == 0, t
+        assert bits_equal(r.latency.cpu().numpy(), exp["latency"][t]) == 0, t
+    # statistics vector carries the two live sums
+    st = env.stats().cpu().numpy()
+    np.testing.assert_allclose(st[8:], [exp["acc"][8].sum(), exp["acc"][9].sum()], rtol=1e-9)
+    assert env.error_count() == 0
+    # without a speed table every session plays at speed 1
+    env.reset(tid, off)
+    ref.reset(tid, off)
+    g1 = env.rollout(policy, 12, seed=5, actions=None if acts is None else acts[:12], want=("reward", "latency"))
+    e1 = ref.rollout(pid, 12, seed=5, actions=None if acts is None else acts[:12])
+    assert_close(g1["latency"].cpu().numpy(), e1["latency"], "latency(speed 1)")
 
 
 def test_simulator_facade_live_mode():
@@ -436,6 +485,14 @@ def test_simulator_facade_live_mode():
         sim2.set_mpd(4.0, 16.0, 8.0, [Chunk(list(b / 1000.0)) for b in bitrates])
         costs = sim2.run_batch(64)
         assert costs.shape == (64,) and np.all(np.isfinite(costs)) and np.all(costs > 0)
+        if isinstance(ctrl, BufferBasedPolicy):     # one fused live episode: compare with the oracle's
+            bw2 = np.ones((2, 200)); bw2[0] = bw[0]; bw2[1, :60] = bw[0][:60]
+            ref2 = orc.OracleEnv(bw2, np.array([200, 60], np.int32), np.array([1.0, 0.5]), bitrates / 1000.0 * 4.0,
+                                 bitrates / 1000.0, 64, **dict(P, smooth_penalty=0.5, bba_reservoir=ctrl.reservoir,
+                                                               bba_cushion=ctrl.cushion))
+            ref2.reset(((np.arange(64) * 2) // 64).astype(np.int32))
+            a2 = ref2.rollout(orc.POLICY_BBA, 20)["acc"]
+            np.testing.assert_allclose(costs, 4.3 * a2[1] + 0.5 * a2[3] + 2.0 * a2[8] + 0.1 * a2[9] / 20, rtol=1e-12)
 
 
 def test_run_host_path_matches_oracle():

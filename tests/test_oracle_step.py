@@ -231,3 +231,28 @@ def test_c_oracle_reproduces_the_step_spec_fixture(case):
     assert np.array_equal(env.field("seg"), case["final"]["seg"])
     assert bits_equal(env.field("phase"), case["final"]["phase"]) == 0
     assert bits_equal(env.field("buffer"), case["final"]["buffer"]) == 0
+
+
+def test_c_rollout_live_equals_python_steps():
+    """orc_env_rollout_live (fused-episode semantics in live mode, speed table) against the pure-Python session."""
+    N, steps = 10, 40
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=3, T=50, V=16)
+    P = _live_params()
+    env = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **P)
+    rng = np.random.default_rng(12)
+    tid = rng.integers(0, 3, size=N).astype(np.int32)
+    off = rng.uniform(0, 60, size=N)
+    speed = rng.choice([0.75, 1.0, 1.5], size=(steps, N))
+    acts = rng.integers(0, 6, size=(steps, N)).astype(np.int32)
+    env.reset(tid, off)
+    tr = env.rollout(orc.POLICY_FIXED, steps, actions=acts, speed=speed)
+    util = orc.utility_table(bitrates, 0, P["utility_scale"])
+    for s in range(N):
+        sess = so.Session(bw[tid[s]], ti[tid[s]], sizes.tolist(), util.tolist(), P, off[s])
+        su = lat = 0.0
+        for t in range(steps):
+            r = sess.step(int(acts[t, s]), float(speed[t, s]))
+            for k in ("delay", "sleep", "buffer", "rebuf", "reward", "latency"):
+                assert tr[k][t, s] == r[k], (s, t, k)
+            su, lat = su + r["startup"], lat + r["latency"]
+        assert tr["acc"][8, s] == su and tr["acc"][9, s] == lat
