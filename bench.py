@@ -317,6 +317,23 @@ def run_ours(args):
     value = chunk_steps / (total_ms * 1e-3)
     errors = env.error_count()
 
+    # ---- the other policy of configs[1]: buffer-based (the action depends on the state, so nothing is hoisted) ----
+    bba_ms = []
+    for it in range(3 + 8):
+        flush.fill_(1)
+        env.reset(tid_d, off_d, session_base=base)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        env.rollout("bba", V, out=out)
+        k1.record(stream)
+        k1.synchronize()
+        if it >= 3:
+            bba_ms.append(k0.elapsed_time(k1))
+    bba_kernel_ms = max_over_ranks(sum(bba_ms), dev) / len(bba_ms)
+    bba = dict(kernel="abr_rollout_kernel<bba>", kernel_ms=bba_kernel_ms,
+               chunk_steps_per_s=world * N * V / (bba_kernel_ms * 1e-3),
+               frac=(N * (V * BYTES_PER_STEP + BYTES_PER_SESSION)) / (bba_kernel_ms * 1e-3) / 1e9 / hbm_peak_gbs())
+
     # ---- e2e: the host-buffer call (Simulator.run semantics: per-session QoE sums + statistics to the host) ----
     tid_p = torch.from_numpy(tid_h).pin_memory().numpy()
     off_p = torch.from_numpy(off_h).pin_memory().numpy()
@@ -381,6 +398,7 @@ def run_ours(args):
                 qoe_stats=dict(zip(_lib.ACC_NAMES, [float(x) for x in tot_stats.cpu()])), flagged_sessions=errors)
     if mpc:
         line["mpc"] = mpc
+    line["bba_policy"] = bba
     if step_form:
         line["step_form"] = step_form
     if rl:
