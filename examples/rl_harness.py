@@ -34,29 +34,91 @@ class Policy(torch.nn.Module):
         return self.net(obs)
 
 
-def run_episode(env, policy, chunks, sample=True, out=None):
-    """One episode of `chunks` steps for all sessions; returns (sum of rewards [N], steps)."""
+def _step_outputs(env):
     n, A, dev = env.n, env.A, env.device
-    out = out or StepResult(*[torch.empty(n, dtype=torch.float64, device=dev) for _ in range(5)],
-                            torch.empty(n, A, dtype=torch.float64, device=dev),
-                            torch.empty(n, dtype=torch.uint8, device=dev),
-                            torch.empty(n, dtype=torch.float64, device=dev))
-    obs = torch.zeros(n, 4 + A, dtype=torch.float32, device=dev)
-    obs[:, 4:] = env.state("sizes")[0].float()          # sizes of the first chunk
+    return StepResult(*[torch.empty(n, dtype=torch.float64, device=dev) for _ in range(5)],
+                      torch.empty(n, A, dtype=torch.float64, device=dev),
+                      torch.empty(n, dtype=torch.uint8, device=dev),
+                      torch.empty(n, dtype=torch.float64, device=dev), None)
+
+
+def _one_chunk(env, policy, obs, action, total, out, sample):
+    """policy(obs) -> action -> env.step -> next observation, all on the device and all in place (so that the
+    sequence can be captured into a CUDA graph once and replayed for every chunk).  ``obs`` is feature-major
+    [4 + A, N]: every feature row is written with one coalesced kernel and the first Linear reads it transposed."""
+    A = env.A
+    logits = policy(obs.t())
+    if sample:      # Gumbel-max: argmax(logits + G) is a draw from softmax(logits); three elementwise kernels
+        u = torch.rand_like(logits).clamp_(1e-12, 1.0)
+        logits = logits - torch.log(-torch.log(u))
+    action.copy_(logits.argmax(dim=1))
+    r = env.step(action, out=out, want_throughput=True)
+    total += r.reward
+    obs[0] = r.buffer / 10.0
+    obs[1] = r.throughput
+    obs[2] = r.delay / 10.0
+    obs[3] = action / float(A)
+    obs[4:] = r.next_sizes.t()
+
+
+def _first_observation(env):
+    obs = torch.zeros(4 + env.A, env.n, dtype=torch.float32, device=env.device)
+    obs[4:] = env.state("sizes")[0].float()[:, None]     # sizes of the first chunk
+    return obs
+
+
+class GraphedEpisode:
+    """One chunk (policy kernels + abr_env_step + observation update) captured into a CUDA graph once; an episode is
+    `chunks` replays.  Buffers are persistent, so the capture is reused across episodes (call after ``env.reset``)."""
+
+    def __init__(self, env, policy, sample=True):
+        self.env, self.policy, self.sample = env, policy, sample
+        n, dev = env.n, env.device
+        self.out = _step_outputs(env)
+        self.obs = _first_observation(env)
+        self.total = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.action = torch.full((n,), 1, dtype=torch.int32, device=dev)
+        self.graph = None
+
+    def _capture(self):
+        env = self.env
+        # warm up the allocator and cuBLAS on a side stream, restore the state, then capture (capture runs nothing)
+        snap = {f: env.state(f).clone() for f in ("seg", "chunk", "last_q", "phase", "buffer")}
+        side = torch.cuda.Stream(device=env.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            _one_chunk(env, self.policy, self.obs, self.action, self.total, self.out, self.sample)
+        torch.cuda.current_stream().wait_stream(side)
+        for f, t in snap.items():
+            env.state(f).copy_(t)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            _one_chunk(env, self.policy, self.obs, self.action, self.total, self.out, self.sample)
+
+    def run(self, chunks):
+        with torch.no_grad():
+            if self.graph is None:
+                self._capture()
+            self.obs.copy_(_first_observation(self.env))
+            self.total.zero_()
+            for _ in range(chunks):
+                self.graph.replay()
+        return self.total
+
+
+def run_episode(env, policy, chunks, sample=True, out=None, use_graph=False):
+    """One episode of `chunks` steps for all sessions; returns the sum of rewards [N] (``use_graph``: through a
+    freshly captured ``GraphedEpisode``; keep one around to reuse the capture across episodes)."""
+    if use_graph:
+        return GraphedEpisode(env, policy, sample).run(chunks)
+    n, dev = env.n, env.device
+    out = out or _step_outputs(env)
+    obs = _first_observation(env)
     total = torch.zeros(n, dtype=torch.float64, device=dev)
     action = torch.full((n,), 1, dtype=torch.int32, device=dev)
     with torch.no_grad():
         for _ in range(chunks):
-            logits = policy(obs)
-            action = (torch.distributions.Categorical(logits=logits).sample() if sample
-                      else logits.argmax(dim=1)).to(torch.int32)
-            r = env.step(action, out=out, want_throughput=True)
-            total += r.reward
-            obs[:, 0] = (r.buffer / 10.0).float()
-            obs[:, 1] = r.throughput.float()
-            obs[:, 2] = (r.delay / 10.0).float()
-            obs[:, 3] = action.float() / A
-            obs[:, 4:] = r.next_sizes.float()
+            _one_chunk(env, policy, obs, action, total, out, sample)
     return total
 
 
@@ -65,20 +127,27 @@ def main():
     ap.add_argument("--sessions", type=int, default=524288)
     ap.add_argument("--chunks", type=int, default=48)
     ap.add_argument("--episodes", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of every chunk separately")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = True        # the stand-in policy may use the tensor cores
     bitrates, sizes = synth.make_video(args.chunks)
     bw, tl, ti = synth.make_traces(1024, 2048)
     env = BatchedABREnv(bw, sizes, bitrates, args.sessions, trace_len=tl, trace_interval=ti)
     # sessions sorted by trace: every 256-session tile of the step kernel stages one capacity row in shared memory
     tid, off = synth.make_sessions(args.sessions, 1024, 2048, group=max(256, args.sessions // 1024))
     policy = Policy(4 + env.A, env.A).to(dev)
+    runner = None
     for ep in range(args.episodes):
         env.reset(tid, off)
+        if runner is None and not args.no_graph:
+            runner = GraphedEpisode(env, policy)      # buffers are sized by the reset; captured on first use
+            runner.run(1)
+            env.reset(tid, off)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        total = run_episode(env, policy, args.chunks)
+        total = runner.run(args.chunks) if runner else run_episode(env, policy, args.chunks)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         print(f"episode {ep}: {args.sessions * args.chunks / dt:.3e} env steps/s "
