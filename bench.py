@@ -28,7 +28,7 @@ N_TRACES, T_TRACE = 1024, 2048
 SEED = 7
 GROUP = 64                          # consecutive sessions per trace (one 64-thread block = one trace)
 BYTES_PER_STEP = 5 * 8 + 1          # delay, sleep, buffer, rebuf, reward (f64) + end_of_video (u8)
-BYTES_PER_SESSION = 32 + 28 + 128   # state load + state store + accumulator read-modify-write, once per episode
+BYTES_PER_SESSION = 32 + 28 + 160   # state load + state store + read-modify-write of the 10 accumulators, once per episode
 
 
 def parse():
