@@ -563,10 +563,11 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
 }
 
 // <= 80 registers: 6 blocks of 128 threads per SM, one wave.  A block walks a run of consecutive tiles of 128 sessions.
-// When all sessions of a tile follow the same trace (callers that keep sessions sorted by trace) and its C row fits
-// in `smem_doubles`, the block stages the row with one TMA bulk copy — once, for as long as the following tiles stay
-// on that trace — and the search probes are LDS; a per-lane scattered global load costs one L1 wavefront per lane,
-// which is what bounds the global path (ncu: l1tex__data_pipe_lsu_wavefronts).
+// When a tile starts and ends on the same trace (callers that keep sessions sorted by trace) and its C row fits in
+// `smem_doubles`, the block stages the row with one TMA bulk copy — once, for as long as the following tiles stay on
+// that trace; no barrier is needed while the row stays — and the search probes of the lanes on that trace are LDS.
+// A per-lane scattered global load costs one L1 wavefront per lane, which is what bounds the global path (ncu:
+// l1tex__data_pipe_lsu_wavefronts).
 template <bool FAST, bool LIVE>
 __global__ void __launch_bounds__(kTile, LIVE ? 4 : kTileBlocksPerSM)
 abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __restrict__ speed,
@@ -576,7 +577,6 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
                 int smem_doubles, int tiles_per_block) {
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
-    __shared__ int s_tr0;
 #define ABR_STEP_SESSION_ARGS v, s, i, q_cur, speed, o_delay, o_sleep, o_buffer, o_rebuf, o_reward, o_latency, o_next_sizes, o_eov, o_thr
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
     if (smem_doubles != 0) {
@@ -588,13 +588,16 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     }
     uint32_t parity = 0u;                        // phase of the next staging copy (block-uniform)
     int staged = -1;                             // trace whose C row the buffer holds (block-uniform, kept per thread)
+    int nofit = -1;                              // last trace whose row did not fit (not retried tile after tile)
     // the state words and the action of the next tile are requested before the current tile is computed, so that
     // two tiles of loads per warp are in flight (the kernel is bound by HBM latency x occupancy otherwise)
     RawState w_next;
-    int q_next = 0;
+    int q_next = 0, first_next = -1, last_next = -1;
     {
-        const int i0 = blockIdx.x * tiles_per_block * kTile + threadIdx.x;
+        const int t0 = blockIdx.x * tiles_per_block * kTile;
+        const int i0 = t0 + threadIdx.x;
         if (i0 < v.n) { w_next = load_raw(v, i0); q_next = action[i0]; }
+        if (t0 < v.n) { first_next = __ldg(v.trace_id + t0); last_next = __ldg(v.trace_id + min(t0 + kTile, v.n) - 1); }
     }
     for (int k = 0; k < tiles_per_block; ++k) {
         const int tile0 = (blockIdx.x * tiles_per_block + k) * kTile;
@@ -603,7 +606,15 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
         const bool valid = i < v.n;
         const RawState w = w_next;
         const int q_cur = q_next;
-        if (k + 1 < tiles_per_block && i + kTile < v.n) { w_next = load_raw(v, i + kTile); q_next = action[i + kTile]; }
+        // traces of the first and the last session of the tile: the same words in every thread, so decisions taken
+        // on them are block-uniform without a barrier.  Equal ends mean one trace for callers that keep sessions
+        // sorted by trace; a lane that disagrees anyway simply takes the global path.
+        const int tr_first = first_next, tr_last = last_next;
+        if (k + 1 < tiles_per_block && tile0 + kTile < v.n) {
+            if (i + kTile < v.n) { w_next = load_raw(v, i + kTile); q_next = action[i + kTile]; }
+            first_next = __ldg(v.trace_id + tile0 + kTile);
+            last_next = __ldg(v.trace_id + min(tile0 + 2 * kTile, v.n) - 1);
+        }
         Sess s;
         int tr = -1;
         if (valid) { make_sess(v, i, w, s); tr = w.tr; }
@@ -611,32 +622,29 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
             if (valid) step_session<false, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
             continue;
         }
-        // also the barrier that ends the previous tile's reads of the row buffer
-        bool use_smem = __syncthreads_and((!valid || tr == staged) ? 1 : 0) != 0;
-        if (!use_smem) {                         // block-uniform: first tile, or the trace changed
-            if (threadIdx.x == 0) s_tr0 = tr;    // thread 0 of a tile is always a valid session
-            __syncthreads();
-            const int tr0 = s_tr0;
-            const int need = __ldg(&v.trace_meta[tr0].T) + 1;
-            use_smem = __syncthreads_and((!valid || tr == tr0) ? 1 : 0) != 0 && need <= smem_doubles;
-            if (use_smem) {
+        if (tr_first == tr_last && tr_first != staged && tr_first != nofit) {   // block-uniform: stage another row
+            __syncthreads();                     // every warp is done with the row the buffer holds
+            const int need = __ldg(&v.trace_meta[tr_first].T) + 1;
+            if (need <= smem_doubles) {
                 if (threadIdx.x == 0) {
                     const uint32_t row_bytes = (uint32_t)((need + 1) / 2) * 16u;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(row_bytes) : "memory");
-                    bulk_g2s(s_row2, v.trace_cum + (size_t)tr0 * cum_stride(v.T_max), row_bytes, mbar);
+                    bulk_g2s(s_row2, v.trace_cum + (size_t)tr_first * cum_stride(v.T_max), row_bytes, mbar);
                 }
                 if (!mbar_wait(mbar, parity) && threadIdx.x == 0) atomicAdd(v.errors, 1ull);
                 parity ^= 1u;
+                staged = tr_first;
+            } else {
+                nofit = tr_first;
             }
-            staged = use_smem ? tr0 : -1;
         }
-        if (use_smem) {
-            if (valid) {
+        if (valid) {
+            if (tr == staged) {
                 s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row2);
                 step_session<true, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
+            } else {
+                step_session<false, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
             }
-        } else if (valid) {
-            step_session<false, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
         }
     }
 #undef ABR_STEP_SESSION_ARGS
