@@ -33,7 +33,7 @@ namespace {
 
 constexpr int kStepBlock = 256;      // helper kernels (reset, tables, cost)
 constexpr int kTile = 128;           // threads per block = sessions per tile of the per-step kernel
-constexpr int kTileBlocksPerSM = 6;
+constexpr int kTileBlocksPerSM = 7;
 constexpr int kStepTiles = 8;         // least number of tiles per block of the per-step kernel
 constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per SM (balanced over 148 SMs)
 constexpr int kStatsBlock = 256;
@@ -562,7 +562,7 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
     }
 }
 
-// <= 80 registers: 6 blocks of 128 threads per SM, one wave.  A block walks a run of consecutive tiles of 128 sessions.
+// <= 72 registers: 7 blocks of 128 threads per SM, one wave.  A block walks a run of consecutive tiles of 128 sessions.
 // When a tile starts and ends on the same trace (callers that keep sessions sorted by trace) and its C row fits in
 // `smem_doubles`, the block stages the row with one TMA bulk copy — once, for as long as the following tiles stay on
 // that trace; no barrier is needed while the row stays — and the search probes of the lanes on that trace are LDS.
