@@ -60,6 +60,29 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _OnDevice:
+    """``with torch.cuda.device(dev)`` that costs nothing when `dev` is already current (the usual one-process-per-GPU
+    case): the per-call overhead of env.step matters when the kernel itself takes 25 us."""
+    __slots__ = ("index", "prev")
+
+    def __init__(self, device):
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.index:
+            self.prev = cur
+            torch.cuda.set_device(self.index)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+            self.prev = -1
+        return False
+
+
 class BatchedABREnv:
     """N sessions over shared trace / video tables.
 
@@ -78,6 +101,7 @@ class BatchedABREnv:
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedABREnv needs a CUDA device (B200); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._on = _OnDevice(self.device)
         self._lib = _lib.load()
         bw = np.ascontiguousarray(trace_bw, dtype=np.float64)
         if bw.ndim == 1:
@@ -96,7 +120,7 @@ class BatchedABREnv:
         self.capacity = int(max_sessions)
         self.n = 0
         self._h = C.c_void_p()
-        with torch.cuda.device(self.device):
+        with self._on:
             _lib.check(self._lib.abr_env_create(
                 bw.ctypes.data_as(C.c_void_p), tl.ctypes.data_as(C.c_void_p), ti.ctypes.data_as(C.c_void_p),
                 C.c_int(self.n_traces), C.c_int(self.T_max), sz.ctypes.data_as(C.c_void_p),
@@ -144,7 +168,7 @@ class BatchedABREnv:
         n = tid.numel()
         if off is not None and off.numel() != n:
             raise ValueError("start_offset must have one entry per session")
-        with torch.cuda.device(self.device):
+        with self._on:
             _lib.check(self._lib.abr_env_reset(self._h, _ptr(tid), _ptr(off), C.c_int(n), C.c_longlong(session_base),
                                                _stream()))
         self.n = n
@@ -176,7 +200,7 @@ class BatchedABREnv:
                              self._empty(n, dtype=torch.uint8),
                              self._empty(n) if want_throughput else None,
                              self._empty(n) if want_latency else None)
-        with torch.cuda.device(self.device):
+        with self._on:
             _lib.check(self._lib.abr_env_step_live(
                 self._h, _ptr(a), _ptr(v), _ptr(out.delay), _ptr(out.sleep), _ptr(out.buffer), _ptr(out.rebuffer),
                 _ptr(out.reward), _ptr(out.latency), _ptr(out.next_sizes), _ptr(out.end_of_video),
@@ -207,7 +231,7 @@ class BatchedABREnv:
             for k in want:
                 dt = torch.uint8 if k == "end_of_video" else torch.int32 if k == "actions" else torch.float64
                 out[k] = self._empty(steps, n, dtype=dt)
-        with torch.cuda.device(self.device):
+        with self._on:
             _lib.check(self._lib.abr_env_rollout_fused_live(
                 self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), _ptr(a_in), _ptr(v), _ptr(out.get("delay")),
                 _ptr(out.get("sleep")), _ptr(out.get("buffer")), _ptr(out.get("rebuffer")), _ptr(out.get("reward")),
@@ -218,7 +242,7 @@ class BatchedABREnv:
     def mpc_decide(self, horizon=5, mode="robust", want_score=False, out=None):
         act = self._empty(self.n, dtype=torch.int32) if out is None else out
         bj = self._empty(self.n) if want_score else None
-        with torch.cuda.device(self.device):
+        with self._on:
             _lib.check(self._lib.abr_env_mpc_decide(self._h, C.c_int(horizon), C.c_int(_mode_id(mode)), _ptr(act),
                                                     _ptr(bj), _stream()))
         return (act, bj) if want_score else act
@@ -228,7 +252,7 @@ class BatchedABREnv:
         act = self._empty(self.n, dtype=torch.int32)
         for _ in range(steps):
             self.mpc_decide(horizon, mode, out=act)
-            with torch.cuda.device(self.device):
+            with self._on:
                 _lib.check(self._lib.abr_env_step(self._h, _ptr(act), None, None, None, None, None, None, None, None,
                                                   _stream()))   # live mode: speed 1.0
         return act
@@ -237,7 +261,7 @@ class BatchedABREnv:
     def stats(self) -> torch.Tensor:
         """[Σreward, Σrebuffer, Σutility, Σsmooth, Σsleep, Σdelay, steps, episodes, Σstartup, Σlatency]."""
         out = torch.empty(NUM_STATS, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._on:
             _lib.check(self._lib.abr_stats_partial(self._h, _ptr(out), _stream()))
         return out
 
@@ -272,13 +296,13 @@ class BatchedABREnv:
     def qoe_cost(self) -> torch.Tensor:
         """Per-session cost of ``Simulator.calculate_qoe`` (Simulator.py:83-86) from the accumulators, on the device."""
         out = self._empty(self.n)
-        with torch.cuda.device(self.device):
+        with self._on:
             _lib.check(self._lib.abr_env_qoe_cost(self._h, _ptr(out), _stream()))
         return out
 
     def error_count(self) -> int:
         out = C.c_longlong(0)
-        with torch.cuda.device(self.device):
+        with self._on:
             _lib.check(self._lib.abr_env_error_count(self._h, C.byref(out), _stream()))
         return int(out.value)
 
@@ -305,7 +329,7 @@ class BatchedABREnv:
         def hp(a):
             return None if a is None else a.ctypes.data_as(C.c_void_p)
 
-        with torch.cuda.device(self.device):
+        with self._on:
             _lib.check(self._lib.abr_env_run_host(
                 self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), hp(tid), hp(off), C.c_int(n),
                 C.c_longlong(session_base), hp(a_in), hp(out.get("acc")), hp(out.get("stats")), hp(out.get("reward")),
