@@ -631,6 +631,30 @@ def test_full_size_properties_65536x48():
     last = torch.cat([torch.ones(1, N, dtype=torch.int64, device="cuda"), q[:-1].long()])
     up = U[torch.arange(steps, device="cuda")[:, None].expand(-1, N), last]
     assert torch.equal((u - 4.3 * rb) - 1.0 * (u - up).abs(), rw)
+    # physics, independent of the capacity table: the bandwidth integral over every download interval is the chunk
+    # size.  The trace clock of a session advances by (delay - rtt) + sleep per step; integrate the raw square wave
+    # in extended precision for a sample of sessions.
+    sample = np.arange(0, N, 97)
+    dn, sn, qn = (x[:, sample].cpu().numpy() for x in (d, sl, q))
+    ld = np.longdouble
+    worst = 0.0
+    for c, s_idx in enumerate(sample):
+        rate = bw[tid[s_idx]].astype(ld) * ld(0.95)
+        Ccum = np.concatenate([[ld(0)], np.cumsum(rate)])            # interval = 1 s
+        P = Ccum[-1]
+
+        def F(t):                                                    # data deliverable in [0, t)
+            n, r = divmod(t, ld(2048))
+            j = int(r)
+            return n * P + Ccum[j] + rate[j] * (r - j)
+        t0 = ld(off[s_idx])
+        for t in range(steps):
+            dl = ld(dn[t, c]) - ld(0.08)
+            got = F(t0 + dl) - F(t0)
+            want = ld(sizes[t, qn[t, c]])
+            worst = max(worst, float(abs(got - want) / want))
+            t0 = t0 + dl + ld(sn[t, c])
+    assert worst < 1e-9, worst
     # determinism: a second run from the same reset is bit-identical
     env.reset(tid, off)
     out2 = env.rollout("random", steps, seed=7, want=("reward",))
