@@ -250,9 +250,11 @@ int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_s
     return abr_env_reset(env, env->d_trace_id, h_start_offset ? env->d_offset : nullptr, n_sessions, session_base, stream);
 }
 
-int abr_env_step_live(AbrEnv* env, const int32_t* d_action, const double* d_speed, double* d_delay, double* d_sleep,
-                      double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency, double* d_next_sizes,
-                      uint8_t* d_end_of_video, double* d_throughput, void* stream) {
+extern "C++" {
+template <typename OT>
+static int env_step_any(AbrEnv* env, const int32_t* d_action, const double* d_speed, OT* d_delay, OT* d_sleep,
+                        OT* d_buffer, OT* d_rebuf, OT* d_reward, OT* d_latency, OT* d_next_sizes,
+                        uint8_t* d_end_of_video, OT* d_throughput, void* stream) {
     if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
     if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
     if (env->v.n == 0) return ABR_OK;
@@ -261,6 +263,21 @@ int abr_env_step_live(AbrEnv* env, const int32_t* d_action, const double* d_spee
     CUDA_TRY(launch_step(env->v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency,
                          d_next_sizes, d_end_of_video, d_throughput, (cudaStream_t)stream));
     return ABR_OK;
+}
+}  // extern "C++"
+
+int abr_env_step_live(AbrEnv* env, const int32_t* d_action, const double* d_speed, double* d_delay, double* d_sleep,
+                      double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency, double* d_next_sizes,
+                      uint8_t* d_end_of_video, double* d_throughput, void* stream) {
+    return env_step_any<double>(env, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency,
+                                d_next_sizes, d_end_of_video, d_throughput, stream);
+}
+
+int abr_env_step_f32(AbrEnv* env, const int32_t* d_action, const double* d_speed, float* d_delay, float* d_sleep,
+                     float* d_buffer, float* d_rebuf, float* d_reward, float* d_latency, float* d_next_sizes,
+                     uint8_t* d_end_of_video, float* d_throughput, void* stream) {
+    return env_step_any<float>(env, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency,
+                               d_next_sizes, d_end_of_video, d_throughput, stream);
 }
 
 int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
@@ -276,10 +293,11 @@ int abr_env_qoe_cost(AbrEnv* env, double* d_out, void* stream) {
     return ABR_OK;
 }
 
-int abr_env_rollout_fused_live(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
-                               const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer,
-                               double* d_rebuf, double* d_reward, double* d_latency, uint8_t* d_end_of_video,
-                               int32_t* d_actions_out, void* stream) {
+extern "C++" {
+template <typename OT>
+static int env_rollout_any(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                           const double* d_speed, OT* d_delay, OT* d_sleep, OT* d_buffer, OT* d_rebuf, OT* d_reward,
+                           OT* d_latency, uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream) {
     if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
     if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
     if (env->v.n == 0) return ABR_OK;
@@ -293,6 +311,23 @@ int abr_env_rollout_fused_live(AbrEnv* env, int policy, uint64_t seed, int steps
                             (cudaStream_t)stream));
     env->fresh_partials = steps > 0 ? rollout_num_blocks(env->v.n) : 0;
     return ABR_OK;
+}
+}  // extern "C++"
+
+int abr_env_rollout_fused_live(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                               const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer,
+                               double* d_rebuf, double* d_reward, double* d_latency, uint8_t* d_end_of_video,
+                               int32_t* d_actions_out, void* stream) {
+    return env_rollout_any<double>(env, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer,
+                                   d_rebuf, d_reward, d_latency, d_end_of_video, d_actions_out, stream);
+}
+
+int abr_env_rollout_fused_f32(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                              const double* d_speed, float* d_delay, float* d_sleep, float* d_buffer, float* d_rebuf,
+                              float* d_reward, float* d_latency, uint8_t* d_end_of_video, int32_t* d_actions_out,
+                              void* stream) {
+    return env_rollout_any<float>(env, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer,
+                                  d_rebuf, d_reward, d_latency, d_end_of_video, d_actions_out, stream);
 }
 
 int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,

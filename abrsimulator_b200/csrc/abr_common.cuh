@@ -104,6 +104,14 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
                            const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf,
                            double* d_reward, double* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
                            double* d_block_partials, cudaStream_t st);
+// fp32-output overloads (arithmetic stays fp64; outputs are rounded once on the store)
+cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, float* d_delay,
+                        float* d_sleep, float* d_buffer, float* d_rebuf, float* d_reward, float* d_latency,
+                        float* d_next_sizes, uint8_t* d_eov, float* d_thr, cudaStream_t st);
+cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                           const double* d_speed, float* d_delay, float* d_sleep, float* d_buffer, float* d_rebuf,
+                           float* d_reward, float* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
+                           double* d_block_partials, cudaStream_t st);
 cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, bool have_partials, double* d_out,
                          cudaStream_t st);
 int stats_num_partials(int n);

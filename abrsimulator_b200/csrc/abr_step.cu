@@ -498,13 +498,14 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
 // FAST: the five f64 outputs and end_of_video requested, no throughput history / accumulators, auto_reset on —
 // compiled without the null checks and the inert/history/accumulator bookkeeping (next_sizes and throughput stay
 // optional in both variants).
-template <bool SMEM, bool FAST, bool LIVE>
+// OT: element type of the outputs (double, or float for the optional fp32-output mode: arithmetic stays fp64).
+template <bool SMEM, bool FAST, bool LIVE, typename OT>
 __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const int i, const int q_in,
-                                             const double* __restrict__ speed, double* __restrict__ o_delay,
-                                             double* __restrict__ o_sleep, double* __restrict__ o_buffer,
-                                             double* __restrict__ o_rebuf, double* __restrict__ o_reward,
-                                             double* __restrict__ o_latency, double* __restrict__ o_next_sizes,
-                                             uint8_t* __restrict__ o_eov, double* __restrict__ o_thr) {
+                                             const double* __restrict__ speed, OT* __restrict__ o_delay,
+                                             OT* __restrict__ o_sleep, OT* __restrict__ o_buffer,
+                                             OT* __restrict__ o_rebuf, OT* __restrict__ o_reward,
+                                             OT* __restrict__ o_latency, OT* __restrict__ o_next_sizes,
+                                             uint8_t* __restrict__ o_eov, OT* __restrict__ o_thr) {
     if (LIVE) {
         s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0;
         s.speed = speed ? speed[i] : 1.0;
@@ -520,8 +521,8 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
     if (r.walk_error) atomicAdd(v.errors, 1ull);
     if (FAST) {
         v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
-        __stcs(o_delay + i, r.delay); __stcs(o_sleep + i, r.sleep); __stcs(o_buffer + i, r.buffer);
-        __stcs(o_rebuf + i, r.rebuf); __stcs(o_reward + i, r.reward);
+        __stcs(o_delay + i, (OT)r.delay); __stcs(o_sleep + i, (OT)r.sleep); __stcs(o_buffer + i, (OT)r.buffer);
+        __stcs(o_rebuf + i, (OT)r.rebuf); __stcs(o_reward + i, (OT)r.reward);
         o_eov[i] = r.eov ? 1 : 0;
     } else {
         if (!r.inert) {
@@ -546,19 +547,19 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
                 if (LIVE) { a[8 * c] = dadd(a[8 * c], r.startup); a[9 * c] = dadd(a[9 * c], r.latency); }
             }
         }
-        if (o_delay) __stcs(o_delay + i, r.delay);
-        if (o_sleep) __stcs(o_sleep + i, r.sleep);
-        if (o_buffer) __stcs(o_buffer + i, r.buffer);
-        if (o_rebuf) __stcs(o_rebuf + i, r.rebuf);
-        if (o_reward) __stcs(o_reward + i, r.reward);
+        if (o_delay) __stcs(o_delay + i, (OT)r.delay);
+        if (o_sleep) __stcs(o_sleep + i, (OT)r.sleep);
+        if (o_buffer) __stcs(o_buffer + i, (OT)r.buffer);
+        if (o_rebuf) __stcs(o_rebuf + i, (OT)r.rebuf);
+        if (o_reward) __stcs(o_reward + i, (OT)r.reward);
         if (o_eov) o_eov[i] = r.eov ? 1 : 0;
     }
-    if (o_latency) __stcs(o_latency + i, r.latency);
-    if (o_thr) __stcs(o_thr + i, r.thr);
+    if (o_latency) __stcs(o_latency + i, (OT)r.latency);
+    if (o_thr) __stcs(o_thr + i, (OT)r.thr);
     if (o_next_sizes) {
         const int A = v.A;
         for (int a = 0; a < A; ++a)
-            o_next_sizes[(size_t)i * A + a] = (!FAST && s.done) ? 0.0 : __ldg(v.sizes + s.chunk * A + a);
+            o_next_sizes[(size_t)i * A + a] = (OT)((!FAST && s.done) ? 0.0 : __ldg(v.sizes + s.chunk * A + a));
     }
 }
 
@@ -568,12 +569,12 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
 // that trace; no barrier is needed while the row stays — and the search probes of the lanes on that trace are LDS.
 // A per-lane scattered global load costs one L1 wavefront per lane, which is what bounds the global path (ncu:
 // l1tex__data_pipe_lsu_wavefronts).
-template <bool FAST, bool LIVE>
+template <bool FAST, bool LIVE, typename OT>
 __global__ void __launch_bounds__(kTile, LIVE ? 4 : kTileBlocksPerSM)
 abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __restrict__ speed,
-                double* __restrict__ o_delay, double* __restrict__ o_sleep, double* __restrict__ o_buffer,
-                double* __restrict__ o_rebuf, double* __restrict__ o_reward, double* __restrict__ o_latency,
-                double* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov, double* __restrict__ o_thr,
+                OT* __restrict__ o_delay, OT* __restrict__ o_sleep, OT* __restrict__ o_buffer,
+                OT* __restrict__ o_rebuf, OT* __restrict__ o_reward, OT* __restrict__ o_latency,
+                OT* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov, OT* __restrict__ o_thr,
                 int smem_doubles, int tiles_per_block) {
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
@@ -619,7 +620,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
         int tr = -1;
         if (valid) { make_sess(v, i, w, s); tr = w.tr; }
         if (smem_doubles == 0) {                 // launch-uniform: no shared-memory row buffer
-            if (valid) step_session<false, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
+            if (valid) step_session<false, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
             continue;
         }
         if (tr_first == tr_last && tr_first != staged && tr_first != nofit) {   // block-uniform: stage another row
@@ -641,19 +642,20 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
         if (valid) {
             if (tr == staged) {
                 s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row2);
-                step_session<true, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
+                step_session<true, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
             } else {
-                step_session<false, FAST, LIVE>(ABR_STEP_SESSION_ARGS);
+                step_session<false, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
             }
         }
     }
 #undef ABR_STEP_SESSION_ARGS
 }
 
+template <typename OT>
 struct RolloutOut {
-    double* __restrict__ delay; double* __restrict__ sleep; double* __restrict__ buffer; double* __restrict__ rebuf;
-    double* __restrict__ reward; uint8_t* __restrict__ eov; int32_t* __restrict__ actions;
-    double* __restrict__ latency;            // live mode only (SPEC §7), nullable
+    OT* __restrict__ delay; OT* __restrict__ sleep; OT* __restrict__ buffer; OT* __restrict__ rebuf;
+    OT* __restrict__ reward; uint8_t* __restrict__ eov; int32_t* __restrict__ actions;
+    OT* __restrict__ latency;                // live mode only (SPEC §7), nullable
     const double* __restrict__ speed;        // live mode only: playback speed [steps][N], nullable = 1.0
 };
 
@@ -662,10 +664,10 @@ struct RolloutOut {
 // auto_reset on — compiled without the per-output null checks and the inert/history bookkeeping.
 // NOOUT (with FAST): no trajectory output at all (statistics / per-session accumulators only, e.g. abr_env_run_host).
 // LIVE (never with FAST): live-streaming semantics of SPEC §7.
-template <int POLICY, bool SMEM, bool FAST, bool NOOUT, bool LIVE>
+template <int POLICY, bool SMEM, bool FAST, bool NOOUT, bool LIVE, typename OT>
 __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const int i, const uint32_t seed_lo,
                                                 const uint32_t seed_hi, const int steps,
-                                                const int32_t* __restrict__ actions_in, const RolloutOut& o,
+                                                const int32_t* __restrict__ actions_in, const RolloutOut<OT>& o,
                                                 double (&acc_new)[ABR_NUM_ACC]) {
     const unsigned long long gsession = (unsigned long long)(v.session_base + i);
     double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_su = 0.0, a_lat = 0.0;
@@ -711,17 +713,17 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         flagged |= r.walk_error;
         if (NOOUT) {
         } else if (FAST) {
-            __stcs(o.delay + ix, r.delay); __stcs(o.sleep + ix, r.sleep); __stcs(o.buffer + ix, r.buffer);
-            __stcs(o.rebuf + ix, r.rebuf); __stcs(o.reward + ix, r.reward);
+            __stcs(o.delay + ix, (OT)r.delay); __stcs(o.sleep + ix, (OT)r.sleep); __stcs(o.buffer + ix, (OT)r.buffer);
+            __stcs(o.rebuf + ix, (OT)r.rebuf); __stcs(o.reward + ix, (OT)r.reward);
             o.eov[ix] = r.eov ? 1 : 0;
         } else {
-            if (o.delay) __stcs(o.delay + ix, r.delay);
-            if (o.sleep) __stcs(o.sleep + ix, r.sleep);
-            if (o.buffer) __stcs(o.buffer + ix, r.buffer);
-            if (o.rebuf) __stcs(o.rebuf + ix, r.rebuf);
-            if (o.reward) __stcs(o.reward + ix, r.reward);
+            if (o.delay) __stcs(o.delay + ix, (OT)r.delay);
+            if (o.sleep) __stcs(o.sleep + ix, (OT)r.sleep);
+            if (o.buffer) __stcs(o.buffer + ix, (OT)r.buffer);
+            if (o.rebuf) __stcs(o.rebuf + ix, (OT)r.rebuf);
+            if (o.reward) __stcs(o.reward + ix, (OT)r.reward);
             if (o.eov) o.eov[ix] = r.eov ? 1 : 0;
-            if (LIVE && o.latency) __stcs(o.latency + ix, r.latency);
+            if (LIVE && o.latency) __stcs(o.latency + ix, (OT)r.latency);
         }
         if (FAST || !r.inert) {
             a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
@@ -764,10 +766,10 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
 // is followed by the key row (key_stride(T_max) words, 16-byte aligned) and the sizes and utility tables.
 // 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
 // co-resident (6.9 per SM); at 140 registers only 3 warps fit per scheduler and a second wave appears.
-template <int POLICY, bool FAST, bool NOOUT, bool LIVE>
+template <int POLICY, bool FAST, bool NOOUT, bool LIVE, typename OT>
 __global__ void __launch_bounds__(kRolloutBlock, LIVE ? 6 : 8)
 abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
-                   RolloutOut o, int smem_doubles, double* __restrict__ block_partials) {
+                   RolloutOut<OT> o, int smem_doubles, double* __restrict__ block_partials) {
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_tr0;
@@ -832,10 +834,10 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
             // keep the three addresses in registers: left alone, the compiler rematerialises them from
             // SR_CgaCtaId (an S2R round trip) at every use inside the step loop
             asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s), "+r"(s.key_s));
-            rollout_session<POLICY, true, FAST, NOOUT, LIVE>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+            rollout_session<POLICY, true, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
         }
     } else if (valid) {
-        rollout_session<POLICY, false, FAST, NOOUT, LIVE>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+        rollout_session<POLICY, false, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
     }
     // statistics stage 1 fused into the episode: per-block sums of the updated accumulators in a fixed order
     // (warp tree, then warps in ascending order), so abr_stats_partial only has to add the block partials
@@ -945,9 +947,10 @@ static cudaError_t allow_smem(Kernel kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
-                        double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,
-                        double* d_next_sizes, uint8_t* d_eov, double* d_thr, cudaStream_t st) {
+template <typename OT>
+static cudaError_t launch_step_t(const EnvView& v, const int32_t* d_action, const double* d_speed, OT* d_delay,
+                                 OT* d_sleep, OT* d_buffer, OT* d_rebuf, OT* d_reward, OT* d_latency,
+                                 OT* d_next_sizes, uint8_t* d_eov, OT* d_thr, cudaStream_t st) {
     if (v.n == 0) return cudaSuccess;
     const bool live = v.p.live != 0;
     const bool fast = !live && d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov &&
@@ -972,8 +975,8 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
 #define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr, smem_doubles, tiles_per_block
 #define ABR_LAUNCH_STEP(F, L)                                                                  \
     do {                                                                                       \
-        e = allow_smem(abr_step_kernel<F, L>, smem_bytes);                                     \
-        if (e == cudaSuccess) abr_step_kernel<F, L><<<grid, kTile, smem_bytes, st>>>(ABR_STEP_ARGS); \
+        e = allow_smem(abr_step_kernel<F, L, OT>, smem_bytes);                                 \
+        if (e == cudaSuccess) abr_step_kernel<F, L, OT><<<grid, kTile, smem_bytes, st>>>(ABR_STEP_ARGS); \
     } while (0)
     if (live) ABR_LAUNCH_STEP(false, true);
     else if (fast) ABR_LAUNCH_STEP(true, false);
@@ -985,14 +988,30 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
     return cudaGetLastError();
 }
 
-cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
-                           const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf,
-                           double* d_reward, double* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
-                           double* d_block_partials, cudaStream_t st) {
+cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
+                        double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,
+                        double* d_next_sizes, uint8_t* d_eov, double* d_thr, cudaStream_t st) {
+    return launch_step_t<double>(v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency,
+                                 d_next_sizes, d_eov, d_thr, st);
+}
+
+// fp32-output mode: same fp64 arithmetic, every floating-point output rounded once to float on the store
+cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, float* d_delay,
+                        float* d_sleep, float* d_buffer, float* d_rebuf, float* d_reward, float* d_latency,
+                        float* d_next_sizes, uint8_t* d_eov, float* d_thr, cudaStream_t st) {
+    return launch_step_t<float>(v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency,
+                                d_next_sizes, d_eov, d_thr, st);
+}
+
+template <typename OT>
+static cudaError_t launch_rollout_t(const EnvView& v, int policy, uint64_t seed, int steps,
+                                    const int32_t* d_actions_in, const double* d_speed, OT* d_delay, OT* d_sleep,
+                                    OT* d_buffer, OT* d_rebuf, OT* d_reward, OT* d_latency, uint8_t* d_eov,
+                                    int32_t* d_actions_out, double* d_block_partials, cudaStream_t st) {
     if (v.n == 0 || steps <= 0) return cudaSuccess;
     const dim3 grid((v.n + kRolloutBlock - 1) / kRolloutBlock), block(kRolloutBlock);
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
-    RolloutOut o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out, d_latency, d_speed};
+    RolloutOut<OT> o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out, d_latency, d_speed};
     const bool live = v.p.live != 0;
     // shared-memory row buffer: the longest C row when it leaves room for >= 7 blocks per SM, else disabled
     int smem_doubles = cum_stride(v.T_max);
@@ -1008,10 +1027,10 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     cudaError_t e = cudaSuccess;
 #define ABR_LAUNCH_ROLLOUT_V(P, F, N, L)                                                                           \
     do {                                                                                                           \
-        e = allow_smem(abr_rollout_kernel<P, F, N, L>, smem_bytes);                                                \
+        e = allow_smem(abr_rollout_kernel<P, F, N, L, OT>, smem_bytes);                                            \
         if (e == cudaSuccess)                                                                                      \
-            abr_rollout_kernel<P, F, N, L><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,      \
-                                                                            smem_doubles, d_block_partials);       \
+            abr_rollout_kernel<P, F, N, L, OT><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,  \
+                                                                                smem_doubles, d_block_partials);   \
     } while (0)
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
     do {                                                                                                           \
@@ -1031,6 +1050,22 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
     if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
+}
+
+cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                           const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf,
+                           double* d_reward, double* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
+                           double* d_block_partials, cudaStream_t st) {
+    return launch_rollout_t<double>(v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
+                                    d_reward, d_latency, d_eov, d_actions_out, d_block_partials, st);
+}
+
+cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                           const double* d_speed, float* d_delay, float* d_sleep, float* d_buffer, float* d_rebuf,
+                           float* d_reward, float* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
+                           double* d_block_partials, cudaStream_t st) {
+    return launch_rollout_t<float>(v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
+                                   d_reward, d_latency, d_eov, d_actions_out, d_block_partials, st);
 }
 
 int stats_num_partials(int n) { return n <= 0 ? 1 : (n + kStatsSessionsPerBlock - 1) / kStatsSessionsPerBlock; }

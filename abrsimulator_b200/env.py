@@ -83,6 +83,14 @@ class _OnDevice:
         return False
 
 
+def _out_dtype(t, dtype):
+    """float64 or float32: the dtype of a caller-given output tensor, else the requested one."""
+    d = dtype if t is None else t.dtype
+    if d not in (torch.float64, torch.float32):
+        raise TypeError(f"outputs are float64 or float32 (got {d})")
+    return d
+
+
 class BatchedABREnv:
     """N sessions over shared trace / video tables.
 
@@ -176,10 +184,12 @@ class BatchedABREnv:
 
     # -- SPEC §3 --
     def step(self, action, want_next_sizes=True, want_throughput=False, out=None, speed=None,
-             want_latency=None) -> StepResult:
+             want_latency=None, dtype=torch.float64) -> StepResult:
         """One chunk step for every session.  ``action``: int32 [N] on the device (or array-like).
         Live mode (``live=1``, SPEC §7): ``speed`` is the playback speed per session (default 1.0), the result
-        carries ``latency`` and ``sleep`` is the idle time before the download."""
+        carries ``latency`` and ``sleep`` is the idle time before the download.
+        ``dtype=torch.float32`` selects the optional fp32-output mode: the arithmetic and the state stay fp64, the
+        outputs are rounded once to float (``abr_env_step_f32``)."""
         a = self._dev(action, torch.int32)
         if a.numel() != self.n:
             raise ValueError(f"action has {a.numel()} entries for {self.n} sessions")
@@ -195,13 +205,13 @@ class BatchedABREnv:
         if want_latency is None:
             want_latency = live
         if out is None:
-            out = StepResult(self._empty(n), self._empty(n), self._empty(n), self._empty(n), self._empty(n),
-                             self._empty(n, self.A) if want_next_sizes else None,
-                             self._empty(n, dtype=torch.uint8),
-                             self._empty(n) if want_throughput else None,
-                             self._empty(n) if want_latency else None)
+            e = lambda *shape: self._empty(*shape, dtype=dtype)
+            out = StepResult(e(n), e(n), e(n), e(n), e(n), e(n, self.A) if want_next_sizes else None,
+                             self._empty(n, dtype=torch.uint8), e(n) if want_throughput else None,
+                             e(n) if want_latency else None)
+        fn = self._lib.abr_env_step_live if _out_dtype(out.delay, dtype) == torch.float64 else self._lib.abr_env_step_f32
         with self._on:
-            _lib.check(self._lib.abr_env_step_live(
+            _lib.check(fn(
                 self._h, _ptr(a), _ptr(v), _ptr(out.delay), _ptr(out.sleep), _ptr(out.buffer), _ptr(out.rebuffer),
                 _ptr(out.reward), _ptr(out.latency), _ptr(out.next_sizes), _ptr(out.end_of_video),
                 _ptr(out.throughput), _stream()))
@@ -209,9 +219,12 @@ class BatchedABREnv:
 
     # -- SPEC §3+§4 --
     def rollout(self, policy, steps, seed=0, actions=None, want=("delay", "sleep", "buffer", "rebuffer", "reward",
-                                                                "end_of_video", "actions"), out=None, speed=None):
+                                                                "end_of_video", "actions"), out=None, speed=None,
+                dtype=torch.float64):
         """`steps` chunk steps in one fused launch.  Returns a dict of [steps, N] device tensors.  In live mode
-        (SPEC §7) ``speed`` is the playback-speed table [steps, N] (default 1.0) and "latency" may be wanted."""
+        (SPEC §7) ``speed`` is the playback-speed table [steps, N] (default 1.0) and "latency" may be wanted.
+        ``dtype=torch.float32``: fp32-output mode (fp64 arithmetic, outputs rounded once; 21 B instead of 41 B of
+        trajectory per chunk-step)."""
         pid = _policy_id(policy)
         n = self.n
         a_in = None
@@ -229,10 +242,15 @@ class BatchedABREnv:
         if out is None:
             out = {}
             for k in want:
-                dt = torch.uint8 if k == "end_of_video" else torch.int32 if k == "actions" else torch.float64
+                dt = torch.uint8 if k == "end_of_video" else torch.int32 if k == "actions" else dtype
                 out[k] = self._empty(steps, n, dtype=dt)
+        fp = [t for k, t in out.items() if k not in ("end_of_video", "actions") and t is not None]
+        f32 = _out_dtype(fp[0] if fp else None, dtype) == torch.float32
+        if any(t.dtype != (torch.float32 if f32 else torch.float64) for t in fp):
+            raise TypeError("all floating-point outputs must share one dtype (float64, or float32 for the fp32-output mode)")
+        fn = self._lib.abr_env_rollout_fused_f32 if f32 else self._lib.abr_env_rollout_fused_live
         with self._on:
-            _lib.check(self._lib.abr_env_rollout_fused_live(
+            _lib.check(fn(
                 self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), _ptr(a_in), _ptr(v), _ptr(out.get("delay")),
                 _ptr(out.get("sleep")), _ptr(out.get("buffer")), _ptr(out.get("rebuffer")), _ptr(out.get("reward")),
                 _ptr(out.get("latency")), _ptr(out.get("end_of_video")), _ptr(out.get("actions")), _stream()))

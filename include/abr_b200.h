@@ -123,6 +123,18 @@ int abr_env_rollout_fused_live(AbrEnv* env, int policy, uint64_t seed, int steps
                                const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer,
                                double* d_rebuf, double* d_reward, double* d_latency, uint8_t* d_end_of_video,
                                int32_t* d_actions_out, void* stream);
+/* Optional fp32-output mode (BASELINE.json north star: "1e-5 for an optional fp32 mode").  State, tables and every
+ * arithmetic operation stay fp64 (SPEC §3), so trajectories do not drift; each floating-point output is rounded once
+ * to float on the store (relative error <= 2^-24 = 6e-8 of the fp64 value).  The trajectory of a fused episode
+ * shrinks from 41 to 21 B per chunk-step.  Signatures otherwise as abr_env_step_live / abr_env_rollout_fused_live
+ * (d_speed / d_latency NULL unless live = 1). */
+int abr_env_step_f32(AbrEnv* env, const int32_t* d_action, const double* d_speed, float* d_delay, float* d_sleep,
+                     float* d_buffer, float* d_rebuf, float* d_reward, float* d_latency,
+                     float* d_next_sizes /*[N][A]*/, uint8_t* d_end_of_video, float* d_throughput, void* stream);
+int abr_env_rollout_fused_f32(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
+                              const double* d_speed, float* d_delay, float* d_sleep, float* d_buffer, float* d_rebuf,
+                              float* d_reward, float* d_latency, uint8_t* d_end_of_video, int32_t* d_actions_out,
+                              void* stream);
 /* MPC decision for every session from the env's own state and history ring (SPEC §5);
  * never flags errors (implies ABR_MPC_TRUNCATE | ABR_MPC_EMPTY_DEFAULT). */
 int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, double* d_best_j /*nullable*/,

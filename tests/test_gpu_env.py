@@ -783,3 +783,80 @@ def test_randomized_worlds_match_oracle(seed):
         check_state(env, ref)
         # a download that needs more than 2^20 trace periods trips the same guard on both sides (SPEC §3.1)
         assert (env.error_count() == 0) == (ref.errors() == 0), tag
+
+
+# ---- optional fp32-output mode (BASELINE.json: "1e-5 for an optional fp32 mode") ----
+# The arithmetic and the state stay fp64, so the bar is tighter than 1e-5: every output equals the oracle's fp64 value
+# rounded once to float (bit-identical to numpy's float64 -> float32 conversion), and the state matches bit for bit.
+F32_RTOL = 1e-5
+
+
+def _check_f32(got, exp, name):
+    got = got.cpu().numpy()
+    assert got.dtype == np.float32, name
+    np.testing.assert_allclose(got.astype(np.float64), exp, rtol=F32_RTOL, atol=1e-30, err_msg=name)
+    assert np.array_equal(got.view(np.uint32), exp.astype(np.float32).view(np.uint32)), f"{name}: not the rounded fp64 value"
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_step_f32_outputs_are_rounded_fp64(ragged):
+    N, steps = 2048, 60
+    env, ref = make_pair(N, dict(track_history=1, track_acc=1), ragged=ragged)
+    rng = np.random.default_rng(5)
+    acc = np.zeros((orc.NUM_ACC, N))
+    for t in range(steps):
+        a = rng.integers(0, env.A, size=N).astype(np.int32)
+        got = env.step(a, want_throughput=True, dtype=torch.float32)
+        exp = ref.step(a, acc=acc)
+        for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                         ("reward", "reward"), ("throughput", "throughput"), ("next_sizes", "next_sizes")):
+            _check_f32(getattr(got, k_g), exp[k_c], f"{k_g}@{t}")
+        assert np.array_equal(got.end_of_video.cpu().numpy(), exp["eov"])
+    check_state(env, ref)                                  # fp64 state: no drift
+    assert_close(env.session_acc().cpu().numpy(), acc, "acc")
+
+
+def test_step_f32_fast_path():
+    """Default parameters (no history, no accumulators): the specialised per-step kernel."""
+    N = 4096
+    env, ref = make_pair(N)
+    rng = np.random.default_rng(6)
+    for t in range(50):
+        a = rng.integers(0, env.A, size=N).astype(np.int32)
+        got = env.step(a, want_next_sizes=False, dtype=torch.float32)
+        exp = ref.step(a)
+        for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                         ("reward", "reward")):
+            _check_f32(getattr(got, k_g), exp[k_c], f"{k_g}@{t}")
+        assert np.array_equal(got.end_of_video.cpu().numpy(), exp["eov"])
+    check_state(env, ref)
+
+
+@pytest.mark.parametrize("policy", ["random", "bba", "fixed"])
+def test_fused_rollout_f32(policy):
+    N, steps = 4096, 60
+    env, ref = make_pair(N, ragged=(policy == "bba"))
+    acts = np.random.default_rng(9).integers(0, env.A, size=(steps, N)).astype(np.int32) if policy == "fixed" else None
+    want = ("delay", "sleep", "buffer", "rebuffer", "reward", "end_of_video") + (("actions",) if policy == "bba" else ())
+    got = env.rollout(policy, steps, seed=77, actions=acts, want=want, dtype=torch.float32)
+    pid = dict(random=orc.POLICY_RANDOM, bba=orc.POLICY_BBA, fixed=orc.POLICY_FIXED)[policy]
+    exp = ref.rollout(pid, steps, seed=77, actions=acts)
+    for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                     ("reward", "reward")):
+        _check_f32(got[k_g], exp[k_c], k_g)
+    assert np.array_equal(got["end_of_video"].cpu().numpy(), exp["eov"])
+    if "actions" in got:
+        assert np.array_equal(got["actions"].cpu().numpy(), exp["actions"])
+    check_state(env, ref)
+    assert_close(env.session_acc().cpu().numpy(), exp["acc"], "acc")      # accumulators stay fp64
+    np.testing.assert_allclose(env.stats().cpu().numpy(), orc.stats_from_acc(exp["acc"]), rtol=1e-12)
+
+
+def test_f32_rejects_mixed_output_dtypes():
+    env, _ = make_pair(64)
+    out = dict(delay=torch.empty(4, 64, dtype=torch.float32, device=env.device),
+               reward=torch.empty(4, 64, dtype=torch.float64, device=env.device))
+    with pytest.raises(TypeError):
+        env.rollout("random", 4, out=out)
+    with pytest.raises(TypeError):
+        env.step(np.zeros(64, np.int32), dtype=torch.float16)
