@@ -5,8 +5,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "abr_common.cuh"
@@ -297,7 +299,8 @@ extern "C++" {
 template <typename OT>
 static int env_rollout_any(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            const double* d_speed, OT* d_delay, OT* d_sleep, OT* d_buffer, OT* d_rebuf, OT* d_reward,
-                           OT* d_latency, uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream) {
+                           OT* d_latency, uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream,
+                           const RolloutFused& fused = RolloutFused{}) {
     if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
     if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
     if (env->v.n == 0) return ABR_OK;
@@ -306,9 +309,15 @@ static int env_rollout_any(AbrEnv* env, int policy, uint64_t seed, int steps, co
     if (policy == ABR_POLICY_FIXED && !d_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs d_actions_in");
     if (!env->v.p.live && (d_speed || d_latency))
         return fail(ABR_ERR_STATE, "speed / latency belong to live mode (SPEC 7): create the environment with live = 1");
-    CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
-                            d_reward, d_latency, d_end_of_video, d_actions_out, env->d_stats_partials,
-                            (cudaStream_t)stream));
+    if constexpr (std::is_same<OT, double>::value) {
+        CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
+                                d_reward, d_latency, d_end_of_video, d_actions_out, env->d_stats_partials,
+                                (cudaStream_t)stream, fused));
+    } else {
+        CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
+                                d_reward, d_latency, d_end_of_video, d_actions_out, env->d_stats_partials,
+                                (cudaStream_t)stream));
+    }
     env->fresh_partials = steps > 0 ? rollout_num_blocks(env->v.n) : 0;
     return ABR_OK;
 }
@@ -413,17 +422,62 @@ int abr_env_error_count(AbrEnv* env, long long* out, void* stream) {
     return ABR_OK;
 }
 
+// Zero-copy: a host pointer inside page-locked memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor)
+// has a device alias under unified addressing; the kernels then read the inputs and write the results over PCIe
+// themselves, which removes the copy launches and overlaps the transfers with the kernels' other work.  Returns
+// nullptr for pageable memory (the staged cudaMemcpyAsync path is used).  ABR_ZERO_COPY=0 disables it (A/B timing).
+static void* device_alias(const void* h) {
+    static const bool enabled = [] {
+        const char* e = getenv("ABR_ZERO_COPY");
+        return !(e && e[0] == '0');
+    }();
+    if (!h || !enabled) return nullptr;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* h_trace_id,
                      const double* h_start_offset, int n_sessions, long long session_base, const int32_t* h_actions_in,
                      double* h_acc, double* h_stats, double* h_reward_traj, double* h_qoe_cost, void* stream) {
     if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
     if (steps < 0) return fail(ABR_ERR_RANGE, "steps must be >= 0");
+    if (!h_trace_id && n_sessions > 0) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
+    if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
+    if (policy < ABR_POLICY_FIXED || policy > ABR_POLICY_BBA) return fail(ABR_ERR_INVALID, "unknown policy %d", policy);
+    if (policy == ABR_POLICY_FIXED && !h_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs h_actions_in");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = abr_env_reset_host(env, h_trace_id, h_start_offset, n_sessions, session_base, stream);
-    if (rc) return rc;
+    // inputs: device aliases of page-locked buffers (read over PCIe by the kernel), else staged copies
+    const int32_t* tid = (const int32_t*)device_alias(h_trace_id);
+    if (!tid && n_sessions > 0) {
+        CUDA_TRY(cudaMemcpyAsync(env->d_trace_id, h_trace_id, sizeof(int32_t) * n_sessions, cudaMemcpyHostToDevice, st));
+        tid = env->d_trace_id;
+    }
+    if (!tid) tid = env->d_trace_id;   // empty batch
+    const double* off = nullptr;
+    if (h_start_offset) {
+        off = (const double*)device_alias(h_start_offset);
+        if (!off) {
+            CUDA_TRY(cudaMemcpyAsync(env->d_offset, h_start_offset, sizeof(double) * n_sessions, cudaMemcpyHostToDevice, st));
+            off = env->d_offset;
+        }
+    }
+    // The episode kernel resets the sessions itself (one launch, no state round trip through HBM) unless there is
+    // no episode to run; the per-session cost goes straight to a page-locked h_qoe_cost from the same kernel.
+    const bool fuse = n_sessions > 0 && steps > 0;
+    double* z_cost = fuse ? (double*)device_alias(h_qoe_cost) : nullptr;
+    int rc;
+    if (fuse) {
+        env->v.n = n_sessions;
+        env->v.session_base = session_base;
+        env->fresh_partials = 0;
+        env->was_reset = true;
+    } else {
+        rc = abr_env_reset(env, tid, off, n_sessions, session_base, stream);
+        if (rc) return rc;
+    }
     const size_t traj = (size_t)steps * n_sessions;
     if (policy == ABR_POLICY_FIXED) {
-        if (!h_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs h_actions_in");
         if (traj > env->d_actions_cap) {
             if (env->d_actions) cudaFree(env->d_actions);
             env->d_actions = nullptr; env->d_actions_cap = 0;
@@ -438,14 +492,18 @@ int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const in
         CUDA_TRY(cudaMalloc(&env->d_reward_traj, sizeof(double) * (traj ? traj : 1)));
         env->d_reward_cap = traj;
     }
-    rc = abr_env_rollout_fused(env, policy, seed, steps, policy == ABR_POLICY_FIXED ? env->d_actions : nullptr, nullptr,
-                               nullptr, nullptr, nullptr, h_reward_traj ? env->d_reward_traj : nullptr, nullptr, nullptr,
-                               stream);
+    RolloutFused fused;
+    if (fuse) { fused.in_trace_id = tid; fused.in_offset = off; fused.out_cost = z_cost; }
+    rc = env_rollout_any<double>(env, policy, seed, steps, policy == ABR_POLICY_FIXED ? env->d_actions : nullptr, nullptr,
+                                 nullptr, nullptr, nullptr, nullptr, h_reward_traj ? env->d_reward_traj : nullptr,
+                                 nullptr, nullptr, nullptr, stream, fused);
     if (rc) return rc;
     if (h_stats) {
-        rc = abr_stats_partial(env, env->d_stats_out, stream);
+        double* z_stats = (double*)device_alias(h_stats);
+        rc = abr_stats_partial(env, z_stats ? z_stats : env->d_stats_out, stream);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h_stats, env->d_stats_out, sizeof(double) * ABR_NUM_STATS, cudaMemcpyDeviceToHost, st));
+        if (!z_stats)
+            CUDA_TRY(cudaMemcpyAsync(h_stats, env->d_stats_out, sizeof(double) * ABR_NUM_STATS, cudaMemcpyDeviceToHost, st));
     }
     if (h_acc) {
         // acc rows are strided by the capacity on the device; the host table is dense [ABR_NUM_ACC][N]
@@ -454,9 +512,15 @@ int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const in
     }
     if (h_reward_traj)
         CUDA_TRY(cudaMemcpyAsync(h_reward_traj, env->d_reward_traj, sizeof(double) * traj, cudaMemcpyDeviceToHost, st));
-    if (h_qoe_cost) {   // d_offset is free again after the reset kernel has consumed it
-        CUDA_TRY(launch_qoe_cost(env->v, env->d_offset, st));
-        CUDA_TRY(cudaMemcpyAsync(h_qoe_cost, env->d_offset, sizeof(double) * n_sessions, cudaMemcpyDeviceToHost, st));
+    if (h_qoe_cost) {
+        double* z_alias = z_cost ? nullptr : (double*)device_alias(h_qoe_cost);
+        if (z_cost) {                                                // already written by the episode kernel
+        } else if (z_alias) {
+            CUDA_TRY(launch_qoe_cost(env->v, z_alias, st));          // written to host memory by the kernel
+        } else {                                                     // d_offset is free again after the reset
+            CUDA_TRY(launch_qoe_cost(env->v, env->d_offset, st));
+            CUDA_TRY(cudaMemcpyAsync(h_qoe_cost, env->d_offset, sizeof(double) * n_sessions, cudaMemcpyDeviceToHost, st));
+        }
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     return ABR_OK;

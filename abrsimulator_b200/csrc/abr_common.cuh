@@ -100,10 +100,13 @@ cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const doub
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
                         double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,
                         double* d_next_sizes, uint8_t* d_eov, double* d_thr, cudaStream_t st);
+// Fused reset + episode + session cost (abr_env_run_host): with in_trace_id the episode kernel resets every session
+// itself (SPEC §2) and out_cost receives Simulator.calculate_qoe per session; the pointers may alias pinned host memory.
+struct RolloutFused { const int32_t* in_trace_id = nullptr; const double* in_offset = nullptr; double* out_cost = nullptr; };
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf,
                            double* d_reward, double* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
-                           double* d_block_partials, cudaStream_t st);
+                           double* d_block_partials, cudaStream_t st, const RolloutFused& f = RolloutFused{});
 // fp32-output overloads (arithmetic stays fp64; outputs are rounded once on the store)
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, float* d_delay,
                         float* d_sleep, float* d_buffer, float* d_rebuf, float* d_reward, float* d_latency,

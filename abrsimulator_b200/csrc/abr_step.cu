@@ -453,21 +453,30 @@ abr_trace_table_kernel(EnvView v, double* __restrict__ cum, uint32_t* __restrict
     meta[t] = m;
 }
 
+// SPEC §2 for one session: the validated trace and the position (seg, phase) of the start offset.  Shared by the
+// reset kernel and the episode kernel's fused reset, so that both perform the same operations.
+__device__ __forceinline__ RawState reset_position(const EnvView& v, int tr, const double off, int& n_bad) {
+    RawState w;
+    if (tr < 0 || tr >= v.n_traces) { ++n_bad; tr = 0; }
+    const int T = v.trace_len[tr];
+    const double I = v.trace_interval[tr];
+    const double x = ddiv(off, I);
+    const double n = floor(x);
+    int seg = (int)fmod(n, (double)T);
+    w.phi = dsub(x, n);   // exact, in [0, 1)
+    if (seg < 0 || seg >= T) { ++n_bad; seg = 0; }
+    w.tr = tr; w.seg = seg; w.chunk = 0; w.last_q = v.p.default_quality; w.buffer = 0.0;
+    return w;
+}
+
 __global__ void __launch_bounds__(kStepBlock)
 abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* __restrict__ start_offset) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.n) return;
-    int tr = trace_id[i];
-    if (tr < 0 || tr >= v.n_traces) { atomicAdd(v.errors, 1ull); tr = 0; }
-    const int T = v.trace_len[tr];
-    const double I = v.trace_interval[tr];
-    const double off = start_offset ? start_offset[i] : 0.0;
-    const double x = ddiv(off, I);
-    const double n = floor(x);
-    int seg = (int)fmod(n, (double)T);
-    const double phi = dsub(x, n);   // exact, in [0, 1)
-    if (seg < 0 || seg >= T) { atomicAdd(v.errors, 1ull); seg = 0; }
-    v.trace_id[i] = tr; v.seg[i] = seg; v.phi[i] = phi; v.buffer[i] = 0.0; v.chunk[i] = 0;
+    int n_bad = 0;
+    const RawState w = reset_position(v, trace_id[i], start_offset ? start_offset[i] : 0.0, n_bad);
+    if (n_bad) atomicAdd(v.errors, (unsigned long long)n_bad);
+    v.trace_id[i] = w.tr; v.seg[i] = w.seg; v.phi[i] = w.phi; v.buffer[i] = 0.0; v.chunk[i] = 0;
     v.last_q[i] = v.p.default_quality; v.done[i] = 0; v.hist_len[i] = 0; v.last_pred[i] = 0.0; v.err_len[i] = 0;
     v.t_now[i] = 0.0; v.play_time[i] = 0.0; v.started[i] = v.p.start_up_length <= 0.0 ? 1 : 0;
 #pragma unroll
@@ -651,12 +660,32 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
 #undef ABR_STEP_SESSION_ARGS
 }
 
+// Per-session QoE cost of Simulator.calculate_qoe (Simulator.py:83-86) from the accumulators:
+// rebuffer_weight * sum(rebuffer) + variance_weight * sum(|delta utility|), plus in live mode
+// startup_weight * start-up time + latency_weight * mean latency.
+__device__ __forceinline__ double session_cost(const EnvView& v, const double rebuf, const double smooth,
+                                               const double steps, const double startup, const double latency) {
+    double c = dadd(dmul(v.p.rebuf_penalty, rebuf), dmul(v.p.smooth_penalty, smooth));
+    if (v.p.live) {   // + sw*start_up_time + lw*average_latency (Simulator.py:85-86)
+        c = dadd(c, dmul(v.p.startup_penalty, startup));
+        c = dadd(c, dmul(v.p.latency_penalty, steps > 0.0 ? ddiv(latency, steps) : 0.0));
+    }
+    return c;
+}
+
 template <typename OT>
 struct RolloutOut {
     OT* __restrict__ delay; OT* __restrict__ sleep; OT* __restrict__ buffer; OT* __restrict__ rebuf;
     OT* __restrict__ reward; uint8_t* __restrict__ eov; int32_t* __restrict__ actions;
     OT* __restrict__ latency;                // live mode only (SPEC §7), nullable
     const double* __restrict__ speed;        // live mode only: playback speed [steps][N], nullable = 1.0
+    // fused reset + episode + session cost (abr_env_run_host): with in_trace_id the kernel resets every session itself
+    // (SPEC §2) instead of loading its state, and out_cost receives Simulator.calculate_qoe per session.  Both may
+    // be device aliases of page-locked HOST memory: the inputs are then pulled and the result pushed over PCIe by
+    // the kernel, overlapped with the other blocks' episodes.
+    const int32_t* __restrict__ in_trace_id; // nullable
+    const double* __restrict__ in_offset;    // nullable = 0.0
+    double* __restrict__ out_cost;           // nullable
 };
 
 // `steps` chunk steps of one session with the state in registers (SPEC §3+§4).
@@ -668,7 +697,7 @@ template <int POLICY, bool SMEM, bool FAST, bool NOOUT, bool LIVE, typename OT>
 __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const int i, const uint32_t seed_lo,
                                                 const uint32_t seed_hi, const int steps,
                                                 const int32_t* __restrict__ actions_in, const RolloutOut<OT>& o,
-                                                double (&acc_new)[ABR_NUM_ACC]) {
+                                                double (&acc_new)[ABR_NUM_ACC], const bool fresh) {
     const unsigned long long gsession = (unsigned long long)(v.session_base + i);
     double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_su = 0.0, a_lat = 0.0;
     int n_steps = 0, n_eps = 0;
@@ -678,7 +707,11 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     uint32_t packed = 0u;   // random policy: the four actions of one Philox block, one per byte
     s.c_seg = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg);
     s.c_seg1 = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg + 8u);
-    if (LIVE) { s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0; s.speed = 1.0; }
+    if (LIVE) {
+        if (fresh) { s.t_now = 0.0; s.play_time = 0.0; s.started = v.p.start_up_length <= 0.0; }
+        else { s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0; }
+        s.speed = 1.0;
+    }
     // SPEC §4 action of step t; must be called with increasing t.  FIXED clamps t to the last row so that the
     // one-step-ahead call after the final step stays inside the caller's table.
     auto action_at = [&](const int t) -> int {
@@ -748,18 +781,26 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     if (hist) v.hist_len[i] = s.hist_len;
     if (reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
     if (!FAST && s.done) v.done[i] = 1;
+    if (fresh) {   // the rest of what abr_reset_kernel writes
+        if (!hist) v.hist_len[i] = 0;
+        if (!reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
+        if (FAST || !s.done) v.done[i] = 0;
+        if (!LIVE) { v.t_now[i] = 0.0; v.play_time[i] = 0.0; v.started[i] = v.p.start_up_length <= 0.0 ? 1 : 0; }
+    }
     // accumulator read-modify-write: all eight loads first (one memory round trip instead of eight dependent ones)
     double* a = v.acc + i;
     const size_t c = v.cap;
     const double add[ABR_NUM_ACC] = {a_rew, a_reb, a_u, a_sm, a_sl, a_dl, a_steps, a_eps, a_su, a_lat};
     double old[ABR_NUM_ACC];
 #pragma unroll
-    for (int j = 0; j < ABR_NUM_ACC; ++j) old[j] = __ldcg(a + j * c);
+    for (int j = 0; j < ABR_NUM_ACC; ++j) old[j] = fresh ? 0.0 : __ldcg(a + j * c);
 #pragma unroll
     for (int j = 0; j < ABR_NUM_ACC; ++j) {
         acc_new[j] = dadd(old[j], add[j]);
         a[j * c] = acc_new[j];
     }
+    if (o.out_cost) o.out_cost[i] = session_cost(v, acc_new[ABR_ACC_REBUF], acc_new[ABR_ACC_SMOOTH], acc_new[ABR_ACC_STEPS],
+                                                 acc_new[ABR_ACC_STARTUP], acc_new[ABR_ACC_LATENCY]);
 }
 
 // smem_doubles: capacity of the dynamic shared-memory row buffer (0 disables the shared-memory path); the buffer
@@ -781,7 +822,21 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
     for (int j = 0; j < ABR_NUM_ACC; ++j) acc_new[j] = 0.0;
     Sess s;
     int tr = -1;
-    if (valid) { load_sess(v, i, s); tr = v.trace_id[i]; }
+    const bool fresh = o.in_trace_id != nullptr;   // fused reset (launch-uniform)
+    int n_bad = 0;
+    if (valid) {
+        if (fresh) {
+            const RawState w = reset_position(v, o.in_trace_id[i], o.in_offset ? o.in_offset[i] : 0.0, n_bad);
+            make_sess(v, i, w, s);
+            s.done = false; s.hist_len = 0;
+            tr = w.tr;
+            v.trace_id[i] = tr;
+            if (n_bad) atomicAdd(v.errors, (unsigned long long)n_bad);
+        } else {
+            load_sess(v, i, s);
+            tr = v.trace_id[i];
+        }
+    }
     if (threadIdx.x == 0) s_tr0 = tr;            // thread 0 of a launched block is always a valid session
     __syncthreads();
     const int tr0 = s_tr0;
@@ -834,10 +889,10 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
             // keep the three addresses in registers: left alone, the compiler rematerialises them from
             // SR_CgaCtaId (an S2R round trip) at every use inside the step loop
             asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s), "+r"(s.key_s));
-            rollout_session<POLICY, true, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+            rollout_session<POLICY, true, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new, fresh);
         }
     } else if (valid) {
-        rollout_session<POLICY, false, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new);
+        rollout_session<POLICY, false, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new, fresh);
     }
     // statistics stage 1 fused into the episode: per-block sums of the updated accumulators in a fixed order
     // (warp tree, then warps in ascending order), so abr_stats_partial only has to add the block partials
@@ -904,21 +959,13 @@ abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __
     if (threadIdx.x == 0) out[j] = x;
 }
 
-// Per-session QoE cost of Simulator.calculate_qoe (Simulator.py:83-86) from the accumulators:
-// rebuffer_weight * sum(rebuffer) + variance_weight * sum(|delta utility|), plus in live mode
-// startup_weight * start-up time + latency_weight * mean latency.
 __global__ void __launch_bounds__(kStepBlock)
 abr_qoe_cost_kernel(EnvView v, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.n) return;
-    double c = dadd(dmul(v.p.rebuf_penalty, v.acc[(size_t)ABR_ACC_REBUF * v.cap + i]),
-                    dmul(v.p.smooth_penalty, v.acc[(size_t)ABR_ACC_SMOOTH * v.cap + i]));
-    if (v.p.live) {   // + sw*start_up_time + lw*average_latency (Simulator.py:85-86)
-        const double steps = v.acc[(size_t)ABR_ACC_STEPS * v.cap + i];
-        c = dadd(c, dmul(v.p.startup_penalty, v.acc[(size_t)ABR_ACC_STARTUP * v.cap + i]));
-        c = dadd(c, dmul(v.p.latency_penalty, steps > 0.0 ? ddiv(v.acc[(size_t)ABR_ACC_LATENCY * v.cap + i], steps) : 0.0));
-    }
-    out[i] = c;
+    const size_t c = v.cap;
+    out[i] = session_cost(v, v.acc[ABR_ACC_REBUF * c + i], v.acc[ABR_ACC_SMOOTH * c + i], v.acc[ABR_ACC_STEPS * c + i],
+                          v.acc[ABR_ACC_STARTUP * c + i], v.acc[ABR_ACC_LATENCY * c + i]);
 }
 
 }  // namespace
@@ -1007,11 +1054,13 @@ template <typename OT>
 static cudaError_t launch_rollout_t(const EnvView& v, int policy, uint64_t seed, int steps,
                                     const int32_t* d_actions_in, const double* d_speed, OT* d_delay, OT* d_sleep,
                                     OT* d_buffer, OT* d_rebuf, OT* d_reward, OT* d_latency, uint8_t* d_eov,
-                                    int32_t* d_actions_out, double* d_block_partials, cudaStream_t st) {
+                                    int32_t* d_actions_out, double* d_block_partials, const RolloutFused& f,
+                                    cudaStream_t st) {
     if (v.n == 0 || steps <= 0) return cudaSuccess;
     const dim3 grid((v.n + kRolloutBlock - 1) / kRolloutBlock), block(kRolloutBlock);
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
-    RolloutOut<OT> o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out, d_latency, d_speed};
+    RolloutOut<OT> o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out, d_latency, d_speed,
+                     f.in_trace_id, f.in_offset, f.out_cost};
     const bool live = v.p.live != 0;
     // shared-memory row buffer: the longest C row when it leaves room for >= 7 blocks per SM, else disabled
     int smem_doubles = cum_stride(v.T_max);
@@ -1055,9 +1104,9 @@ static cudaError_t launch_rollout_t(const EnvView& v, int policy, uint64_t seed,
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf,
                            double* d_reward, double* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
-                           double* d_block_partials, cudaStream_t st) {
+                           double* d_block_partials, cudaStream_t st, const RolloutFused& f) {
     return launch_rollout_t<double>(v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
-                                    d_reward, d_latency, d_eov, d_actions_out, d_block_partials, st);
+                                    d_reward, d_latency, d_eov, d_actions_out, d_block_partials, f, st);
 }
 
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
@@ -1065,7 +1114,7 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
                            float* d_reward, float* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
                            double* d_block_partials, cudaStream_t st) {
     return launch_rollout_t<float>(v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
-                                   d_reward, d_latency, d_eov, d_actions_out, d_block_partials, st);
+                                   d_reward, d_latency, d_eov, d_actions_out, d_block_partials, RolloutFused{}, st);
 }
 
 int stats_num_partials(int n) { return n <= 0 ? 1 : (n + kStatsSessionsPerBlock - 1) / kStatsSessionsPerBlock; }

@@ -860,3 +860,72 @@ def test_f32_rejects_mixed_output_dtypes():
         env.rollout("random", 4, out=out)
     with pytest.raises(TypeError):
         env.step(np.zeros(64, np.int32), dtype=torch.float16)
+
+
+def test_run_host_zero_copy_equals_staged_copies():
+    """Page-locked host buffers are read and written by the kernels directly (device alias under unified addressing);
+    pageable ones go through staged copies.  Both give the same bytes, mixed combinations included."""
+    N, steps = 5000, 48
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=32, T=256)
+    tid, off = synth.make_sessions(N, 32, 256)
+    env = BatchedABREnv(bw, sizes, bitrates, 8192, trace_len=tl, trace_interval=ti)
+    pageable = env.run_host("random", steps, tid, off, seed=5, want_qoe_cost=True)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    tid_p, off_p = pin(tid.astype(np.int32)), pin(off.astype(np.float64))
+    assert tid_p.dtype == np.int32 and off_p.dtype == np.float64
+    out = dict(qoe_cost=pin(np.full(N, np.nan)), stats=pin(np.full(_lib.NUM_STATS, np.nan)))
+    pinned = env.run_host("random", steps, tid_p, off_p, seed=5, out=out)
+    assert out["qoe_cost"] is pinned["qoe_cost"]
+    for k in ("acc", "stats", "qoe_cost"):
+        assert bits_equal(pinned[k], pageable[k]) == 0, k
+    mixed = env.run_host("random", steps, tid_p, off, seed=5, out=dict(qoe_cost=pin(np.full(N, np.nan))))   # pinned ids, pageable offsets
+    for k in ("acc", "stats", "qoe_cost"):
+        assert bits_equal(mixed[k], pageable[k]) == 0, k
+    none_off = env.run_host("random", steps, tid_p, None, seed=5, out=dict(stats=pin(np.full(_lib.NUM_STATS, np.nan))))
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
+    ref.reset(tid, None)
+    exp = ref.rollout(orc.POLICY_RANDOM, steps, seed=5)
+    assert_close(none_off["acc"], exp["acc"], "acc")
+    np.testing.assert_allclose(none_off["stats"], orc.stats_from_acc(exp["acc"]), rtol=1e-9)
+
+
+ALL_FIELDS = ("seg", "chunk", "last_q", "trace_id", "hist_len", "done", "err_len", "phase", "buffer", "last_pred",
+              "t_now", "play_time", "started")
+
+
+@pytest.mark.parametrize("params", [dict(), dict(track_history=1), dict(auto_reset=0), dict(live=1, start_up_length=8.0),
+                                    dict(live=1, track_history=1, auto_reset=0)])
+@pytest.mark.parametrize("policy", ["random", "bba"])
+def test_run_host_fused_reset_equals_reset_then_rollout(params, policy):
+    """abr_env_run_host resets the sessions inside the episode kernel; every state array, the accumulators, the
+    statistics, the session cost and the error count must equal abr_env_reset followed by abr_env_rollout_fused —
+    also when the environment held another, longer run before (stale state must not leak through)."""
+    N, steps = 3000, 57                      # V = 48: crosses an end of video
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=32, T=256, ragged=True)
+    tid, off = synth.make_sessions(N, 32, 256)
+    tid = tid.astype(np.int32)
+    tid[7], tid[100] = -3, 32                # invalid traces: flagged and replaced by trace 0 (SPEC §2)
+    env_a = BatchedABREnv(bw, sizes, bitrates, 4096, trace_len=tl, trace_interval=ti, **params)
+    env_b = BatchedABREnv(bw, sizes, bitrates, 4096, trace_len=tl, trace_interval=ti, **params)
+    for env in (env_a, env_b):               # dirty both environments with an unrelated run
+        env.reset((np.arange(4096) % 32).astype(np.int32), np.linspace(0.0, 300.0, 4096))
+        env.rollout("random", 31, seed=99, want=())
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    for host in (lambda a: a, pin):          # staged copies, then zero-copy
+        e0 = env_a.error_count()
+        out = env_a.run_host(policy, steps, host(tid), host(off), seed=3, want_qoe_cost=True,
+                             out=dict(qoe_cost=host(np.full(N, np.nan))))
+        err_a = env_a.error_count() - e0
+        e0 = env_b.error_count()
+        env_b.reset(tid, off)
+        env_b.rollout(policy, steps, seed=3, want=())
+        err_b = env_b.error_count() - e0
+        assert err_a == err_b == 2
+        for f in ALL_FIELDS:
+            a, b = env_a.state(f).cpu().numpy()[:N], env_b.state(f).cpu().numpy()[:N]
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f
+        assert bits_equal(out["acc"], env_b.session_acc().cpu().numpy()) == 0
+        assert bits_equal(out["stats"], env_b.stats().cpu().numpy()) == 0
+        assert bits_equal(out["qoe_cost"], env_b.qoe_cost().cpu().numpy()) == 0
+    if params.get("track_history"):
+        assert bits_equal(env_a.state("bw_hist").cpu().numpy(), env_b.state("bw_hist").cpu().numpy()) == 0
