@@ -43,7 +43,7 @@ class AbrParams(C.Structure):
 SYMBOLS = ("abr_version", "abr_last_error", "abr_launch_count", "abr_device_info", "abr_params_default",
            "abr_env_create", "abr_env_destroy", "abr_env_num_sessions", "abr_env_reset", "abr_env_reset_host",
            "abr_env_step", "abr_env_step_live", "abr_env_step_f32", "abr_env_qoe_cost", "abr_env_rollout_fused",
-           "abr_env_rollout_fused_live", "abr_env_rollout_fused_f32", "abr_env_mpc_decide", "abr_stats_partial",
+           "abr_env_rollout_fused_live", "abr_env_rollout_fused_f32", "abr_env_run", "abr_env_mpc_decide", "abr_stats_partial",
            "abr_env_state_ptr",
            "abr_env_error_count", "abr_env_run_host", "abr_mpc_decide", "abr_mpc_decide_host", "abr_mpc_score_host",
            "abr_fp64_probe")
@@ -68,6 +68,10 @@ def load():
     lib.abr_last_error.restype = C.c_char_p
     lib.abr_launch_count.restype = C.c_longlong
     lib.abr_version.restype = C.c_int
+    # argtypes for the host-buffer entry point: plain Python ints / None convert without per-call ctypes objects
+    vp = C.c_void_p
+    lib.abr_env_run_host.argtypes = [vp, C.c_int, C.c_uint64, C.c_int, vp, vp, C.c_int, C.c_longlong, vp, vp, vp, vp, vp, vp]
+    lib.abr_env_run_host.restype = C.c_int
     _lib = lib
     return lib
 

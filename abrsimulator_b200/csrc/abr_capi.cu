@@ -422,6 +422,35 @@ int abr_env_error_count(AbrEnv* env, long long* out, void* stream) {
     return ABR_OK;
 }
 
+int abr_env_run(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_trace_id,
+                const double* d_start_offset, int n_sessions, long long session_base, const int32_t* d_actions_in,
+                double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
+                uint8_t* d_end_of_video, int32_t* d_actions_out, double* d_qoe_cost, double* d_stats, void* stream) {
+    if (!env || (!d_trace_id && n_sessions > 0)) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
+    if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
+    if (steps < 0) return fail(ABR_ERR_RANGE, "steps must be >= 0");
+    if (policy < ABR_POLICY_FIXED || policy > ABR_POLICY_BBA) return fail(ABR_ERR_INVALID, "unknown policy %d", policy);
+    if (policy == ABR_POLICY_FIXED && !d_actions_in && n_sessions > 0 && steps > 0)
+        return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs d_actions_in");
+    int rc;
+    if (n_sessions > 0 && steps > 0) {   // the episode kernel resets the sessions itself and writes the session cost
+        env->v.n = n_sessions;
+        env->v.session_base = session_base;
+        env->fresh_partials = 0;
+        env->was_reset = true;
+        RolloutFused fused;
+        fused.in_trace_id = d_trace_id; fused.in_offset = d_start_offset; fused.out_cost = d_qoe_cost;
+        rc = env_rollout_any<double>(env, policy, seed, steps, d_actions_in, nullptr, d_delay, d_sleep, d_buffer, d_rebuf,
+                                     d_reward, nullptr, d_end_of_video, d_actions_out, stream, fused);
+        if (rc) return rc;
+    } else {
+        rc = abr_env_reset(env, d_trace_id, d_start_offset, n_sessions, session_base, stream);
+        if (rc) return rc;
+        if (d_qoe_cost) CUDA_TRY(launch_qoe_cost(env->v, d_qoe_cost, (cudaStream_t)stream));
+    }
+    return d_stats ? abr_stats_partial(env, d_stats, stream) : ABR_OK;
+}
+
 // Zero-copy: a host pointer inside page-locked memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor)
 // has a device alias under unified addressing; the kernels then read the inputs and write the results over PCIe
 // themselves, which removes the copy launches and overlaps the transfers with the kernels' other work.  Returns

@@ -83,6 +83,32 @@ class _OnDevice:
         return False
 
 
+def _host(x, np_dtype, torch_dtype):
+    """A contiguous host buffer of the given element type: CPU torch tensors and matching numpy arrays pass through."""
+    if isinstance(x, torch.Tensor):
+        if x.device.type != "cpu" or x.dtype != torch_dtype or not x.is_contiguous():
+            raise TypeError(f"host tensors must be contiguous CPU {torch_dtype} (got {x.dtype} on {x.device})")
+        return x
+    return np.ascontiguousarray(x, dtype=np_dtype)
+
+
+def _check_host_out(a, size, name):
+    if a is None:
+        return
+    if isinstance(a, torch.Tensor):
+        ok = a.device.type == "cpu" and a.dtype == torch.float64 and a.is_contiguous() and a.numel() == size
+    else:
+        ok = a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable and a.size == size
+    if not ok:
+        raise TypeError(f"output {name!r} must be a contiguous host float64 buffer of {size} elements")
+
+
+def _hptr(a):
+    if a is None:
+        return None
+    return a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data
+
+
 def _out_dtype(t, dtype):
     """float64 or float32: the dtype of a caller-given output tensor, else the requested one."""
     d = dtype if t is None else t.dtype
@@ -111,6 +137,7 @@ class BatchedABREnv:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._on = _OnDevice(self.device)
         self._lib = _lib.load()
+        self._run_host = self._lib.abr_env_run_host
         bw = np.ascontiguousarray(trace_bw, dtype=np.float64)
         if bw.ndim == 1:
             bw = bw[None, :]
@@ -256,6 +283,48 @@ class BatchedABREnv:
                 _ptr(out.get("latency")), _ptr(out.get("end_of_video")), _ptr(out.get("actions")), _stream()))
         return out
 
+    # -- SPEC §2+§3+§4+§6 in two launches --
+    def run(self, policy, steps, trace_id, start_offset=None, seed=0, session_base=0, actions=None,
+            want=("delay", "sleep", "buffer", "rebuffer", "reward", "end_of_video"), out=None, qoe_cost=None,
+            stats=None):
+        """One whole run, device-resident (``abr_env_run``): reset + `steps` chunk steps + per-session QoE cost +
+        statistics; the episode kernel resets the sessions itself.  ``trace_id`` / ``start_offset``: device tensors
+        (or array-likes).  ``out``: dict of [steps, N] float64 device tensors as for ``rollout``; ``qoe_cost`` [N] and
+        ``stats`` [NUM_STATS] are allocated when None (pass False to skip).  Returns (out, qoe_cost, stats)."""
+        pid = _policy_id(policy)
+        tid = self._dev(trace_id, torch.int32)
+        n = tid.numel()
+        off = None if start_offset is None else self._dev(start_offset, torch.float64)
+        if off is not None and off.numel() != n:
+            raise ValueError("start_offset must have one entry per session")
+        a_in = None
+        if pid == POLICY_FIXED:
+            if actions is None:
+                raise ValueError("policy 'fixed' needs an actions table [steps, N]")
+            a_in = self._dev(actions, torch.int32)
+            if a_in.numel() != steps * n:
+                raise ValueError("actions must be [steps, N]")
+        if out is None:
+            out = {}
+            for k in want:
+                dt = torch.uint8 if k == "end_of_video" else torch.int32 if k == "actions" else torch.float64
+                out[k] = self._empty(steps, n, dtype=dt)
+        for k, t in out.items():
+            if t is not None and k not in ("end_of_video", "actions") and t.dtype != torch.float64:
+                raise TypeError("run() outputs are float64")
+        qoe_cost = self._empty(n) if qoe_cost is None else (None if qoe_cost is False else qoe_cost)
+        stats = self._empty(NUM_STATS) if stats is None else (None if stats is False else stats)
+        g = out.get
+        with self._on:
+            _lib.check(self._lib.abr_env_run(
+                self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), _ptr(tid), _ptr(off), C.c_int(n),
+                C.c_longlong(session_base), _ptr(a_in), _ptr(g("delay")), _ptr(g("sleep")), _ptr(g("buffer")),
+                _ptr(g("rebuffer")), _ptr(g("reward")), _ptr(g("end_of_video")), _ptr(g("actions")), _ptr(qoe_cost),
+                _ptr(stats), _stream()))
+        self.n = n
+        self.session_base = int(session_base)
+        return out, qoe_cost, stats
+
     # -- SPEC §5 --
     def mpc_decide(self, horizon=5, mode="robust", want_score=False, out=None):
         act = self._empty(self.n, dtype=torch.int32) if out is None else out
@@ -327,13 +396,15 @@ class BatchedABREnv:
     # -- host-buffer path (what Simulator.run() uses; e2e benchmark leg) --
     def run_host(self, policy, steps, trace_id, start_offset=None, seed=0, session_base=0, actions=None,
                  want_acc=True, want_stats=True, want_reward_traj=False, want_qoe_cost=False, out=None):
-        """Reset + fused episode + statistics with HOST (numpy) inputs and outputs.
+        """Reset + fused episode + statistics with HOST inputs and outputs: numpy arrays or CPU torch tensors
+        (int32 / float64, contiguous).  Page-locked buffers (``tensor.pin_memory()``) are read and written by the
+        kernels directly, pageable ones through staged copies.
         Returns dict(acc=[NUM_ACC,N], stats=[NUM_STATS], reward=[steps,N], qoe_cost=[N])."""
         pid = _policy_id(policy)
-        tid = np.ascontiguousarray(trace_id, dtype=np.int32)
-        n = tid.size
-        off = None if start_offset is None else np.ascontiguousarray(start_offset, dtype=np.float64)
-        a_in = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
+        tid = _host(trace_id, np.int32, torch.int32)
+        n = tid.numel() if isinstance(tid, torch.Tensor) else tid.size
+        off = None if start_offset is None else _host(start_offset, np.float64, torch.float64)
+        a_in = None if actions is None else _host(actions, np.int32, torch.int32)
         out = {} if out is None else out
         if want_acc and "acc" not in out:
             out["acc"] = np.empty((NUM_ACC, n))
@@ -343,15 +414,15 @@ class BatchedABREnv:
             out["reward"] = np.empty((steps, n))
         if want_qoe_cost and "qoe_cost" not in out:
             out["qoe_cost"] = np.empty(n)
-
-        def hp(a):
-            return None if a is None else a.ctypes.data_as(C.c_void_p)
-
+        g = out.get
+        for k, size in (("acc", NUM_ACC * n), ("stats", NUM_STATS), ("reward", steps * n), ("qoe_cost", n)):
+            _check_host_out(g(k), size, k)
         with self._on:
-            _lib.check(self._lib.abr_env_run_host(
-                self._h, C.c_int(pid), C.c_uint64(seed), C.c_int(steps), hp(tid), hp(off), C.c_int(n),
-                C.c_longlong(session_base), hp(a_in), hp(out.get("acc")), hp(out.get("stats")), hp(out.get("reward")),
-                hp(out.get("qoe_cost")), _stream()))
+            rc = self._run_host(self._h, pid, seed, steps, _hptr(tid), _hptr(off), n, session_base, _hptr(a_in),
+                                _hptr(g("acc")), _hptr(g("stats")), _hptr(g("reward")), _hptr(g("qoe_cost")),
+                                torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _lib.check(rc)
         self.n = n
         self.session_base = int(session_base)
         return out

@@ -29,6 +29,10 @@ SEED = 7
 GROUP = 64                          # consecutive sessions per trace (one 64-thread block = one trace)
 BYTES_PER_STEP = 5 * 8 + 1          # delay, sleep, buffer, rebuf, reward (f64) + end_of_video (u8)
 BYTES_PER_SESSION = 32 + 28 + 160   # state load + state store + read-modify-write of the 10 accumulators, once per episode
+# abr_env_run (reset fused into the episode kernel): 12 B of trace id + start offset in, the whole reset state out
+# (28 B of position + 38 B that only a reset writes: trace_id, hist_len, last_pred, err_len, done, t_now, play_time,
+# started) and the 10 accumulators written without being read
+BYTES_PER_SESSION_RUN = 12 + 28 + 38 + 80
 
 
 def parse():
@@ -46,6 +50,8 @@ def parse():
     ap.add_argument("--rl-sessions", type=int, default=1 << 19,
                     help="sessions per GPU of the RL-harness leg (configs[4] / 8; 0 = skip)")
     ap.add_argument("--step-sessions", type=int, default=1 << 22, help="sessions per GPU of the per-step-launch leg")
+    ap.add_argument("--separate-reset", action="store_true",
+                    help="timed step = abr_env_reset + abr_env_rollout_fused + statistics (three launches) instead of abr_env_run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of each cpu_baseline sample")
     ap.add_argument("--group", type=int, default=GROUP,
@@ -277,10 +283,15 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
 
     def one_step(ev=None):
-        env.reset(tid_d, off_d, session_base=base)
-        if ev:
-            ev[0].record(stream)
-        env.rollout("random", V, seed=SEED, out=out)
+        if args.separate_reset:                                # three launches: reset, episode, statistics
+            env.reset(tid_d, off_d, session_base=base)
+            if ev:
+                ev[0].record(stream)
+            env.rollout("random", V, seed=SEED, out=out)
+        else:                                                  # two launches: the episode kernel resets the sessions
+            if ev:
+                ev[0].record(stream)
+            env.run("random", V, tid_d, off_d, seed=SEED, session_base=base, out=out, qoe_cost=False, stats=False)
         if ev:
             ev[1].record(stream)
         return env.stats()
@@ -335,10 +346,11 @@ def run_ours(args):
                frac=(N * (V * BYTES_PER_STEP + BYTES_PER_SESSION)) / (bba_kernel_ms * 1e-3) / 1e9 / hbm_peak_gbs())
 
     # ---- e2e: the host-buffer call (Simulator.run semantics: per-session QoE sums + statistics to the host) ----
-    tid_p = torch.from_numpy(tid_h).pin_memory().numpy()
-    off_p = torch.from_numpy(off_h).pin_memory().numpy()
-    qoe_p = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
-    st_p = torch.empty(_lib.NUM_STATS, dtype=torch.float64).pin_memory().numpy()
+    # page-locked host tensors: the kernels pull the inputs and push the results over PCIe themselves (zero-copy)
+    tid_p = torch.from_numpy(tid_h).pin_memory()
+    off_p = torch.from_numpy(off_h).pin_memory()
+    qoe_p = torch.empty(N, dtype=torch.float64).pin_memory()
+    st_p = torch.empty(_lib.NUM_STATS, dtype=torch.float64).pin_memory()
     host_out = dict(qoe_cost=qoe_p, stats=st_p)
     for _ in range(3):
         env.run_host("random", V, tid_p, off_p, seed=SEED, session_base=base, want_acc=False, out=host_out)
@@ -377,7 +389,8 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    alg_bytes = N * V * BYTES_PER_STEP + N * BYTES_PER_SESSION
+    per_session = BYTES_PER_SESSION if args.separate_reset else BYTES_PER_SESSION_RUN
+    alg_bytes = N * V * BYTES_PER_STEP + N * per_session
     achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
     traffic = None
     try:
@@ -390,7 +403,9 @@ def run_ours(args):
                 roofline=dict(kernel="abr_rollout_kernel<random>", bound="hbm", achieved=achieved, peak=hbm_peak,
                               unit="GB/s", frac=achieved / hbm_peak, traffic=traffic, peak_source=peak_src,
                               algorithmic_bytes_per_launch=alg_bytes, kernel_ms=kern_avg_ms,
-                              bytes_per_chunk_step=BYTES_PER_STEP, bytes_per_session=BYTES_PER_SESSION),
+                              bytes_per_chunk_step=BYTES_PER_STEP, bytes_per_session=per_session,
+                              launch="abr_env_rollout_fused after abr_env_reset" if args.separate_reset else
+                                     "abr_env_run: reset fused into the episode kernel"),
                 e2e=dict(value=e2e_value, unit="chunk-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          call="abr_env_run_host: reset + fused episode + statistics; the per-session QoE cost that "
                               "Simulator.run() returns ([N] doubles) and the statistics vector copied back", ms_per_step=1e3 * e2e_s / args.steps),

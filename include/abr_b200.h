@@ -123,6 +123,16 @@ int abr_env_rollout_fused_live(AbrEnv* env, int policy, uint64_t seed, int steps
                                const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer,
                                double* d_rebuf, double* d_reward, double* d_latency, uint8_t* d_end_of_video,
                                int32_t* d_actions_out, void* stream);
+/* One whole run per call, device-resident: abr_env_reset + abr_env_rollout_fused + abr_env_qoe_cost +
+ * abr_stats_partial in two launches — the episode kernel resets every session itself (SPEC §2, same operations as
+ * abr_env_reset) and writes the per-session cost, so the state makes no round trip through HBM between the two.
+ * This is Simulator.run() (Simulator.py:93-210) for a batch: d_qoe_cost[N] is what run() returns per session
+ * (calculate_qoe, Simulator.py:83-86).  Trajectory outputs [steps][N], d_qoe_cost and d_stats are nullable. */
+int abr_env_run(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_trace_id,
+                const double* d_start_offset /*nullable*/, int n_sessions, long long session_base,
+                const int32_t* d_actions_in /*[steps][N], policy FIXED*/, double* d_delay, double* d_sleep,
+                double* d_buffer, double* d_rebuf, double* d_reward, uint8_t* d_end_of_video, int32_t* d_actions_out,
+                double* d_qoe_cost /*[N]*/, double* d_stats /*[ABR_NUM_STATS]*/, void* stream);
 /* Optional fp32-output mode (BASELINE.json north star: "1e-5 for an optional fp32 mode").  State, tables and every
  * arithmetic operation stay fp64 (SPEC §3), so trajectories do not drift; each floating-point output is rounded once
  * to float on the store (relative error <= 2^-24 = 6e-8 of the fp64 value).  The trajectory of a fused episode
@@ -150,7 +160,11 @@ int abr_env_error_count(AbrEnv* env, long long* out, void* stream);
 
 /* ---- host-buffer entry points: what Simulator.run() (Simulator.py:93-210) and
  *      MPCBitrateController.next_bitrate() (mpc.py:181-186) callers use.  They copy inputs
- *      host->device, run the kernels above and copy results device->host. ---- */
+ *      host->device, run the kernels above and copy results device->host.
+ *      abr_env_run_host is abr_env_run with host buffers.  Buffers in page-locked memory (cudaHostAlloc /
+ *      cudaHostRegister, e.g. torch's pin_memory()) are not copied: the episode kernel reads h_trace_id /
+ *      h_start_offset and writes h_qoe_cost / h_stats through their device aliases, over PCIe, while other
+ *      thread blocks compute.  Pageable buffers go through staged cudaMemcpyAsync.  Synchronises the stream. ---- */
 int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* h_trace_id,
                      const double* h_start_offset, int n_sessions, long long session_base,
                      const int32_t* h_actions_in /*[steps][N], policy FIXED*/,

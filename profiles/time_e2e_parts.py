@@ -53,3 +53,21 @@ def copies():
 
 print("copies only (2 H2D + 1 D2H + sync) %.1f us" % loop(copies))
 print("empty sync                         %.1f us" % loop(lambda: torch.cuda.current_stream().synchronize()))
+
+# GPU-side span of one run_host call (events on the launching stream around the call)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+spans = []
+for _ in range(50):
+    e0.record()
+    env.run_host("random", V, tid_p, off_p, seed=7, want_acc=False, out=out)
+    e1.record()
+    e1.synchronize()
+    spans.append(e0.elapsed_time(e1) * 1e3)
+print("run_host GPU span (events)        %.1f us (median)" % sorted(spans)[len(spans) // 2])
+import ctypes as C
+from abrsimulator_b200 import _lib
+lib = _lib.load()
+hp = lambda a: a.ctypes.data_as(C.c_void_p)
+args = (env._h, C.c_int(1), C.c_uint64(7), C.c_int(V), hp(tid_p), hp(off_p), C.c_int(N), C.c_longlong(0), None, None,
+        hp(out["stats"]), None, hp(out["qoe_cost"]), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+print("raw C call (no façade)            %.1f us" % loop(lambda: lib.abr_env_run_host(*args)))

@@ -929,3 +929,36 @@ def test_run_host_fused_reset_equals_reset_then_rollout(params, policy):
         assert bits_equal(out["qoe_cost"], env_b.qoe_cost().cpu().numpy()) == 0
     if params.get("track_history"):
         assert bits_equal(env_a.state("bw_hist").cpu().numpy(), env_b.state("bw_hist").cpu().numpy()) == 0
+
+
+@pytest.mark.parametrize("policy", ["random", "bba", "fixed"])
+def test_env_run_equals_reset_rollout_cost_stats(policy):
+    """abr_env_run (two launches) against the four separate calls and against the oracle."""
+    N, steps = 4000, 50
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=32, T=256)
+    tid, off = synth.make_sessions(N, 32, 256, group=64)
+    acts = np.random.default_rng(4).integers(0, 6, size=(steps, N)).astype(np.int32) if policy == "fixed" else None
+    env_a = BatchedABREnv(bw, sizes, bitrates, 4096, trace_len=tl, trace_interval=ti)
+    env_b = BatchedABREnv(bw, sizes, bitrates, 4096, trace_len=tl, trace_interval=ti)
+    env_a.reset((np.arange(4096) % 32).astype(np.int32))
+    env_a.rollout("bba", 20, want=())                       # stale state and accumulators
+    out, cost, stats = env_a.run(policy, steps, tid, off, seed=21, session_base=1000, actions=acts)
+    env_b.reset(tid, off, session_base=1000)
+    exp = env_b.rollout(policy, steps, seed=21, actions=acts)
+    for k in out:
+        assert torch.equal(out[k], exp[k]), k
+    assert torch.equal(cost, env_b.qoe_cost()) and torch.equal(stats, env_b.stats())
+    for f in ALL_FIELDS:
+        assert torch.equal(env_a.state(f)[:N], env_b.state(f)[:N]), f
+    assert torch.equal(env_a.session_acc(), env_b.session_acc())
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
+    ref.reset(tid, off)
+    pid = dict(random=orc.POLICY_RANDOM, bba=orc.POLICY_BBA, fixed=orc.POLICY_FIXED)[policy]
+    o = ref.rollout(pid, steps, seed=21, session_base=1000, actions=acts)
+    assert_close(out["reward"].cpu().numpy(), o["reward"], "reward")
+    assert_close(out["delay"].cpu().numpy(), o["delay"], "delay")
+    assert_close(cost.cpu().numpy(), 4.3 * o["acc"][1] + 1.0 * o["acc"][3], "qoe_cost")
+    # empty run: a plain reset
+    out0, cost0, stats0 = env_a.run(policy, 0, tid, off, actions=None if acts is None else acts[:0])
+    assert float(cost0.abs().sum()) == 0.0 and float(stats0.abs().sum()) == 0.0
+    assert np.array_equal(env_a.state("chunk").cpu().numpy()[:N], np.zeros(N, np.int32))
