@@ -328,6 +328,29 @@ def run_ours(args):
     value = chunk_steps / (total_ms * 1e-3)
     errors = env.error_count()
 
+    # ---- optional fp32-output mode (fp64 arithmetic and state; 5 x 4 + 1 B of trajectory per chunk-step) ----
+    out32 = {k: torch.empty(V, N, dtype=torch.float32, device=dev) for k in ("delay", "sleep", "buffer", "rebuffer", "reward")}
+    out32["end_of_video"] = out["end_of_video"]
+    f32_ms = []
+    for it in range(3 + 8):
+        flush.fill_(1)
+        env.reset(tid_d, off_d, session_base=base)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        env.rollout("random", V, seed=SEED, out=out32)
+        k1.record(stream)
+        k1.synchronize()
+        if it >= 3:
+            f32_ms.append(k0.elapsed_time(k1))
+    f32_kernel_ms = max_over_ranks(sum(f32_ms), dev) / len(f32_ms)
+    f32_bytes = N * (V * (5 * 4 + 1) + BYTES_PER_SESSION)
+    fp32_outputs = dict(kernel="abr_rollout_kernel<random, float>", kernel_ms=f32_kernel_ms,
+                        chunk_steps_per_s=world * N * V / (f32_kernel_ms * 1e-3), bytes_per_chunk_step=21,
+                        frac=f32_bytes / (f32_kernel_ms * 1e-3) / 1e9 / hbm_peak_gbs(),
+                        max_rel_err_vs_f64=float(((out32["reward"].double() - out["reward"]).abs() /
+                                                  out["reward"].abs().clamp_min(1e-300)).max()))
+    del out32
+
     # ---- the other policy of configs[1]: buffer-based (the action depends on the state, so nothing is hoisted) ----
     bba_ms = []
     for it in range(3 + 8):
@@ -414,6 +437,7 @@ def run_ours(args):
     if mpc:
         line["mpc"] = mpc
     line["bba_policy"] = bba
+    line["fp32_outputs"] = fp32_outputs
     if step_form:
         line["step_form"] = step_form
     if rl:
