@@ -261,16 +261,17 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     double target = dadd(dadd(c_seg, dmul(dsub(c_seg1, c_seg), phi)), size);
     // without a wrap C[seg] <= target and b_near bits reach every segment one download can cross; a download that
     // runs past the end of the trace period (rare per session, but one lane in ten warp-steps) restarts at C[0]
-    // with the full width b_full — same code, so the warp stays converged and only runs the longer search
+    // with the same width: what is left of it after the wrap is less than one chunk (target - n*P < size because
+    // the start position is below P), so it ends within size_max / min capacity < 2^b_near - 1 segments of C[0].
+    // Every lane of a block on the shared-memory path therefore runs the same search (bits is a per-trace constant).
     uint32_t p_lo = p_base + 8u * (uint32_t)seg;
-    int bits = s.bits & 0xff;
+    const int bits = s.bits & 0xff;
     double kd = (double)(-seg);                           // segment boundaries crossed: (j - seg) + n*T, j added below
     if (target >= s.P) {
         int n = 0;                                        // whole trace periods
         do { target = dsub(target, s.P); ++n; } while (target >= s.P && n < kWrapGuard);
         if (n >= kWrapGuard) { r.walk_error = true; target = 0.0; }
         p_lo = p_base;
-        bits = (s.bits >> 8) & 0xff;
         kd = dadd(kd, dmul((double)n, (double)T));        // exact in fp64
     }
     uint32_t p_j;
@@ -279,8 +280,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         const uint32_t kp0 = s.key_s + ((p_lo - p_base) >> 1), kp_end = s.key_s + 4u * (uint32_t)T;
         const uint32_t kt = (uint32_t)__double2hiint(target);
         uint32_t kp;
-        // the usual widths get fully unrolled searches; a lane whose download wrapped (bits = b_full) takes the
-        // generic one on its own — one lane in ~10 % of the warp-steps, cheaper than a warp vote in every step
+        // the usual widths get fully unrolled searches
         if (bits == 7) kp = search_keys<7>(kp0, kp_end, 7, kt);
         else if (bits == 6) kp = search_keys<6>(kp0, kp_end, 6, kt);
         else if (bits == 8) kp = search_keys<8>(kp0, kp_end, 8, kt);

@@ -881,6 +881,14 @@ def test_run_host_zero_copy_equals_staged_copies():
     mixed = env.run_host("random", steps, tid_p, off, seed=5, out=dict(qoe_cost=pin(np.full(N, np.nan))))   # pinned ids, pageable offsets
     for k in ("acc", "stats", "qoe_cost"):
         assert bits_equal(mixed[k], pageable[k]) == 0, k
+    # interior pointers of page-locked allocations (slices) alias correctly too
+    big_t, big_o, big_c = pin(np.zeros(N + 11, np.int32)), pin(np.zeros(N + 5)), pin(np.full(N + 3, np.nan))
+    big_t[11:] = tid
+    big_o[5:] = off
+    inner = env.run_host("random", steps, big_t[11:], big_o[5:], seed=5, out=dict(qoe_cost=big_c[3:]))
+    for k in ("acc", "stats", "qoe_cost"):
+        assert bits_equal(inner[k], pageable[k]) == 0, k
+    assert np.isnan(big_c[:3]).all()
     none_off = env.run_host("random", steps, tid_p, None, seed=5, out=dict(stats=pin(np.full(_lib.NUM_STATS, np.nan))))
     ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
     ref.reset(tid, None)
