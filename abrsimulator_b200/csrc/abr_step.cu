@@ -735,6 +735,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     // they are in registers when the next step starts
     int q = action_at(0);
     Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);
+#pragma unroll 2   // two steps per trip: fewer loop-carried register moves (54.9 vs 55.8 us; unroll 4 spills and is slower)
     for (int t = 0; t < steps; ++t) {
         StepRes r;
         const size_t ix = (size_t)t * n + i;
