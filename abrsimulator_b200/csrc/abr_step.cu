@@ -816,6 +816,9 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_tr0;
     __shared__ double s_part[kRolloutBlock / 32][ABR_NUM_ACC];
+    // let a dependent grid launched with programmatic stream serialization (the statistics stage 2) become resident
+    // now; it waits for this grid's completion itself (griddepcontrol.wait), so only its launch latency is hidden
+    asm volatile("griddepcontrol.launch_dependents;");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < v.n;
     double acc_new[ABR_NUM_ACC];
@@ -954,6 +957,9 @@ __global__ void __launch_bounds__(kStatsBlock)
 abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __restrict__ out) {
     __shared__ double sm[32];
     const int j = blockIdx.x;
+    // launched with programmatic stream serialization: the grid may be resident before the kernel in front of it
+    // in the stream (the episode) has finished; wait here for its completion and its writes
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     double x = 0.0;
     for (int i = threadIdx.x; i < n_partials; i += blockDim.x) x = dadd(x, partials[(size_t)i * ABR_NUM_ACC + j]);
     x = block_sum(x, sm);
@@ -1137,7 +1143,21 @@ cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, b
         abr_stats_stage1<<<n_partials, kStatsBlock, 0, st>>>(v, d_partials);
         count_launch();
     }
-    abr_stats_stage2<<<ABR_NUM_ACC, kStatsBlock, 0, st>>>(d_partials, n_partials, d_out);
+    {   // programmatic dependent launch: scheduled while the episode kernel still runs, starts working when it is done
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ABR_NUM_ACC);
+        cfg.blockDim = dim3(kStatsBlock);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const double* partials_c = d_partials;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, abr_stats_stage2, partials_c, n_partials, d_out);
+        if (e != cudaSuccess) return e;
+    }
     count_launch();
     return cudaGetLastError();
 }

@@ -16,6 +16,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import signal
 import subprocess
 import sys
 import time
@@ -203,13 +204,20 @@ def workload_config(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.proc = None
         self.index = index
+        self.t_load = None
+
+    def mark_load(self):
+        """Samples older than this moment (the poller is started early so that nvidia-smi's start-up, which holds
+        driver locks for most of a second, is over before the timed region) are not counted."""
+        import datetime
+        self.t_load = datetime.datetime.now()
 
     def start(self):
         try:
@@ -219,7 +227,18 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def pause(self, on=True):
+        """SIGSTOP / SIGCONT the poller: nvidia-smi queries take driver locks that the launch- and sync-latency
+        bound host-buffer leg (90 us per call) would otherwise pay for."""
+        if self.proc is not None:
+            try:
+                self.proc.send_signal(signal.SIGSTOP if on else signal.SIGCONT)
+            except Exception:
+                pass
+
     def stop(self):
+        if self.proc is not None:
+            self.pause(False)
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -230,10 +249,18 @@ class ClockSampler:
             out = ""
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        import datetime
         for ln in out.strip().splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                if self.t_load is not None and ts < self.t_load:
+                    continue
+            except ValueError:
+                pass
+            f = f[1:]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
@@ -269,6 +296,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                        # early: see ClockSampler.mark_load
+
     N = args.sessions
     base = rank * N
     bitrates, sizes = synth.make_video(V)
@@ -300,9 +331,8 @@ def run_ours(args):
         flush.fill_(1)
         stats = one_step()
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark_load()
     launches0 = _lib.launch_count()
     step_ms, kern_ms = [], []
     barrier()
@@ -375,6 +405,8 @@ def run_ours(args):
     qoe_p = torch.empty(N, dtype=torch.float64).pin_memory()
     st_p = torch.empty(_lib.NUM_STATS, dtype=torch.float64).pin_memory()
     host_out = dict(qoe_cost=qoe_p, stats=st_p)
+    if rank == 0:
+        sampler.pause(True)
     for _ in range(10):
         env.run_host("random", V, tid_p, off_p, seed=SEED, session_base=base, want_acc=False, out=host_out)
     # K calls per block, wall clock (the call synchronises), max over ranks; the median of five blocks is reported —
@@ -388,6 +420,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         blocks.append(max_over_ranks(time.perf_counter() - t0, dev))
     e2e_s = sorted(blocks)[len(blocks) // 2]
+    if rank == 0:
+        sampler.pause(False)
     e2e_value = chunk_steps / e2e_s
     h2d = N * 4 + N * 8
     d2h = N * 8 + _lib.NUM_STATS * 8
