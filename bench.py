@@ -536,6 +536,26 @@ def bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak):
                          session_steps_per_s=world * M / (ms * 1e-3),
                          roofline=dict(bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s",
                                        frac=achieved / hbm_peak))
+    # optional fp32-output mode on the trace-sorted layout: 5 x 4 + 1 B of outputs, state and arithmetic unchanged
+    out32 = StepResult(*[torch.empty(M, dtype=torch.float32, device=dev) for _ in range(5)], None, out.end_of_video, None)
+    tid, off = synth.make_sessions(M, N_TRACES, T_TRACE, session_base=rank * M, group=max(256, M // N_TRACES))
+    env.reset(tid, off, session_base=rank * M)
+    for t in range(8):
+        env.step(acts[t % 8], out=out32)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(24):
+        env.step(acts[t % 8], out=out32)
+    e1.record(stream)
+    e1.synchronize()
+    ms32 = max_over_ranks(e0.elapsed_time(e1), dev) / 24
+    bytes32 = 32 + 4 + 28 + 21
+    res["sorted_by_trace_fp32_outputs"] = dict(ms_per_launch=ms32, session_steps_per_s=world * M / (ms32 * 1e-3),
+                                               bytes_per_session_step=bytes32,
+                                               roofline=dict(bound="hbm", achieved=M * bytes32 / (ms32 * 1e-3) / 1e9,
+                                                             peak=hbm_peak, unit="GB/s",
+                                                             frac=M * bytes32 / (ms32 * 1e-3) / 1e9 / hbm_peak))
     best = res["sorted_by_trace"]
     return dict(kernel="abr_step_kernel", sessions_per_gpu=M, ms_per_launch=best["ms_per_launch"],
                 session_steps_per_s=best["session_steps_per_s"], bytes_per_session_step=bytes_per,
