@@ -39,3 +39,31 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def bind_to_gpu_cpus(device_index: int) -> list | None:
+    """Restrict this process to the CPU cores next to GPU ``device_index`` (NVML's ideal CPU affinity: the cores of
+    the NUMA node its PCIe root hangs off).  One process per GPU: host buffers allocated afterwards are first-touched
+    on that node, so the kernels' zero-copy PCIe reads of pinned buffers and the launch path stay local.  Returns the
+    core list, or None when NVML or the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = device_index
+        if visible:                                    # NVML ignores CUDA_VISIBLE_DEVICES
+            ids = [x.strip() for x in visible.split(",") if x.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                index = int(ids[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--step-sessions", type=int, default=1 << 22, help="sessions per GPU of the per-step-launch leg")
     ap.add_argument("--separate-reset", action="store_true",
                     help="timed step = abr_env_reset + abr_env_rollout_fused + statistics (three launches) instead of abr_env_run")
+    ap.add_argument("--no-cpu-bind", action="store_true", help="do not restrict the rank to the CPU cores next to its GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of each cpu_baseline sample")
     ap.add_argument("--group", type=int, default=GROUP,
@@ -288,6 +289,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from abrsimulator_b200.distributed import bind_to_gpu_cpus
+    all_cpus = os.sched_getaffinity(0)
+    cpus = None if args.no_cpu_bind else bind_to_gpu_cpus(local)   # cores of the NUMA node next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -472,7 +476,8 @@ def run_ours(args):
                          call="abr_env_run_host: reset + fused episode + statistics; the per-session QoE cost that "
                               "Simulator.run() returns ([N] doubles) and the statistics vector, written to pinned host buffers",
                          ms_per_step=1e3 * e2e_s / args.steps, timing="median of 5 blocks of K calls, wall clock, max over ranks",
-                         blocks_ms_per_step=[1e3 * b / args.steps for b in blocks]),
+                         blocks_ms_per_step=[1e3 * b / args.steps for b in blocks],
+                         host_cores=(f"{len(cpus)} cores next to the GPU (NVML affinity)" if cpus else "unbound")),
                 gpu_launches=int(launches), clocks=clocks, wall_s_timed_region=wall,
                 qoe_stats=dict(zip(_lib.ACC_NAMES, [float(x) for x in tot_stats.cpu()])), flagged_sessions=errors)
     if mpc:
@@ -484,6 +489,7 @@ def run_ours(args):
     if rl:
         line["rl_harness"] = rl
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
     if world > 1:
