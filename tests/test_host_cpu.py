@@ -130,3 +130,17 @@ def test_gloo_world_size_2_stats_reduction(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out
+
+
+def test_bind_to_gpu_cpus_is_a_no_op_without_a_gpu():
+    """No NVML device in the CPU container: the helper reports None and leaves the affinity alone."""
+    import os
+    from abrsimulator_b200.distributed import bind_to_gpu_cpus
+    before = os.sched_getaffinity(0)
+    got = bind_to_gpu_cpus(0)
+    after = os.sched_getaffinity(0)
+    if got is None:
+        assert after == before
+    else:                                   # a GPU box: the process now sits on a non-empty subset of what it had
+        assert set(got) == after and after <= before and after
+        os.sched_setaffinity(0, before)
