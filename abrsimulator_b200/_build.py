@@ -56,13 +56,29 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libabr_b200.so (set NVCC or add nvcc to PATH)")
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    # one nvcc per source, in parallel (abr_step.cu alone holds ~50 kernel instantiations), then one link
+    from concurrent.futures import ThreadPoolExecutor
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    obj_dir = os.path.join(os.path.dirname(LIB), "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    log = ""
+    for obj, res in results:
+        log += res.stdout + res.stderr
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", LIB] + [obj for obj, _ in results], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stdout + res.stderr)
+        print(log + res.stdout + res.stderr)
     with open(STAMP, "w") as f:
         f.write(_source_hash())
     return LIB
