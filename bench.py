@@ -460,9 +460,10 @@ def run_ours(args):
     per_session = BYTES_PER_SESSION if args.separate_reset else BYTES_PER_SESSION_RUN
     alg_bytes = N * V * BYTES_PER_STEP + N * per_session
     achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_all = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("abr_rollout_kernel")
+        traffic_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = traffic_all.get("abr_rollout_kernel")
     except Exception:
         pass
     line = dict(metric="chunk_steps_per_sec", value=value, unit="chunk-steps/s", n_gpus=world, steps=args.steps,
@@ -479,6 +480,7 @@ def run_ours(args):
                               "Simulator.run() returns ([N] doubles) and the statistics vector, written to pinned host buffers",
                          ms_per_step=1e3 * e2e_s / args.steps, timing="median of 5 blocks of K calls, wall clock, max over ranks",
                          blocks_ms_per_step=[1e3 * b / args.steps for b in blocks],
+                         best_block_ms_per_step=1e3 * min(blocks) / args.steps,
                          host_cores=(f"{len(cpus)} cores next to the GPU (NVML affinity)" if cpus else "unbound")),
                 gpu_launches=int(launches), clocks=clocks, wall_s_timed_region=wall,
                 qoe_stats=dict(zip(_lib.ACC_NAMES, [float(x) for x in tot_stats.cpu()])), flagged_sessions=errors)
@@ -488,6 +490,11 @@ def run_ours(args):
     line["fp32_outputs"] = fp32_outputs
     if step_form:
         line["step_form"] = step_form
+        # the per-step-launch kernel is the HBM-bound one (north star: >= 0.6 of peak); repeated at the top level
+        line["roofline_step_kernel"] = dict(kernel="abr_step_kernel (one launch per chunk, 4 Mi sessions, state in HBM)",
+                                            **step_form["roofline"], traffic=(traffic_all or {}).get("abr_step_kernel"),
+                                            algorithmic_bytes_per_launch=step_form["sessions_per_gpu"] * step_form["bytes_per_session_step"],
+                                            kernel_ms=step_form["ms_per_launch"])
     if rl:
         line["rl_harness"] = rl
     if world == 1 and not args.no_cpu_baseline:
