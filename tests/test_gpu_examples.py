@@ -72,3 +72,10 @@ def test_rl_harness_cuda_graph_replay_equals_eager():
     env.reset(tid, off)
     sampled = run_episode(env, policy, V, sample=True, use_graph=True)
     assert bool(torch.isfinite(sampled).all()) and env.error_count() == 0
+
+
+def test_mpc_dropin_example_prints_the_reference_answer(capsys):
+    """examples/mpc_dropin.py: the reference's mpc_test.py scenario -> 'Test next bitrate: 2'."""
+    from examples.mpc_dropin import main
+    assert main() == 2
+    assert capsys.readouterr().out.strip() == "Test next bitrate: 2"
