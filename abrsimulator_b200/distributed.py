@@ -45,7 +45,8 @@ def bind_to_gpu_cpus(device_index: int) -> list | None:
     """Restrict this process to the CPU cores next to GPU ``device_index`` (NVML's ideal CPU affinity: the cores of
     the NUMA node its PCIe root hangs off).  One process per GPU: host buffers allocated afterwards are first-touched
     on that node, so the kernels' zero-copy PCIe reads of pinned buffers and the launch path stay local.  Returns the
-    core list, or None when NVML or the affinity call is unavailable (nothing is changed then)."""
+    core list, or None when NVML or the affinity call is unavailable or fewer than four of those cores are usable by
+    this process (nothing is changed then)."""
     import os
     try:
         import pynvml
@@ -61,7 +62,7 @@ def bind_to_gpu_cpus(device_index: int) -> list | None:
         words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
         cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
         allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
-        if not allowed:
+        if len(allowed) < 4:                           # leave room for the driver's and NCCL's helper threads
             return None
         os.sched_setaffinity(0, allowed)
         return allowed
