@@ -17,7 +17,7 @@ MPC_REF, MPC_ROBUST = 0, 1
 MPC_TRUNCATE, MPC_EMPTY_DEFAULT = 1, 2
 ACC_NAMES = ("reward", "rebuffer", "utility", "smooth", "sleep", "delay", "steps", "episodes", "startup", "latency")
 FIELDS = dict(seg=(0, "int32"), chunk=(1, "int32"), last_q=(2, "int32"), trace_id=(3, "int32"),
-              hist_len=(4, "int32"), done=(5, "uint8"), err_len=(6, "int32"), phase=(10, "float64"),
+              hist_len=(4, "int32"), done=(5, "uint8"), err_len=(6, "int32"), phase=(10, "float64"), pos=(18, "float64"),
               buffer=(11, "float64"), bw_hist=(12, "float64"), last_pred=(13, "float64"),
               err_ring=(14, "float64"), acc=(15, "float64"), t_now=(16, "float64"), play_time=(17, "float64"),
               started=(7, "uint8"), sizes=(20, "float64"), utility=(21, "float64"),

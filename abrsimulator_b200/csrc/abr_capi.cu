@@ -44,6 +44,7 @@ struct AbrEnv {
     double* d_stats_partials = nullptr;
     int n_partials_cap = 0;
     bool was_reset = false;   // abr_env_reset has run (an empty batch, n == 0, is legal and makes every call a no-op)
+    uint32_t step_base = 0;   // fused-episode steps since the last reset: offsets the random policy's counter (SPEC §4)
     int fresh_partials = 0;   // > 0: d_stats_partials holds that many block sums of the current accumulators
     double* d_stats_out = nullptr;
     // scratch for the *_host entry points
@@ -186,27 +187,30 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     CUDA_TRY(cudaMemcpy(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice));
     v.trace_bw = d_bw; v.trace_len = d_len; v.trace_interval = d_int; v.sizes = d_sizes; v.util = d_util;
     // per-trace tables of SPEC §3.1 (cumulative capacity, search widths), built on the device
+    // (+4 doubles of slack: the step reads C[j .. j+3] and discards what lies past its candidates)
     double* d_cum;
-    int32_t* d_bits;
-    CUDA_TRY(e->alloc(&d_cum, (size_t)n_traces * cum_stride(T_max)));
-    CUDA_TRY(e->alloc(&d_bits, n_traces));
+    int32_t* d_ok;
+    CUDA_TRY(e->alloc(&d_cum, (size_t)n_traces * cum_stride(T_max) + 4));
+    CUDA_TRY(cudaMemset(d_cum + (size_t)n_traces * cum_stride(T_max), 0, 4 * sizeof(double)));
+    CUDA_TRY(e->alloc(&d_ok, n_traces));
     TraceMeta* d_meta;
     CUDA_TRY(e->alloc(&d_meta, n_traces));
-    uint32_t* d_key;
-    CUDA_TRY(e->alloc(&d_key, (size_t)n_traces * key_stride(T_max)));
-    v.trace_cum = d_cum; v.trace_bits = d_bits; v.trace_meta = d_meta; v.trace_key = d_key;
-    CUDA_TRY(launch_trace_table(v, d_cum, d_key, d_bits, d_meta, 0));
+    uint16_t* d_idx;
+    CUDA_TRY(e->alloc(&d_idx, (size_t)n_traces * idx_stride(T_max) + 8));
+    v.trace_cum = d_cum; v.trace_meta = d_meta; v.trace_idx = d_idx;
+    CUDA_TRY(launch_trace_table(v, d_cum, d_idx, d_ok, d_meta, 0));
     {
         std::vector<int32_t> bits(n_traces);
-        CUDA_TRY(cudaMemcpy(bits.data(), d_bits, sizeof(int32_t) * n_traces, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(bits.data(), d_ok, sizeof(int32_t) * n_traces, cudaMemcpyDeviceToHost));
         for (int t = 0; t < n_traces; ++t)
-            if (bits[t] < 0)
+            if (bits[t] <= 0)
                 return fail(ABR_ERR_INVALID, "trace %d: every segment capacity bandwidth*payload*interval must be representable "
                                              "next to the capacity of the whole trace period (positive, finite)", t);
     }
     CUDA_TRY(e->alloc(&v.seg, cap)); CUDA_TRY(e->alloc(&v.chunk, cap)); CUDA_TRY(e->alloc(&v.last_q, cap));
     CUDA_TRY(e->alloc(&v.trace_id, cap)); CUDA_TRY(e->alloc(&v.hist_len, cap)); CUDA_TRY(e->alloc(&v.err_len, cap));
     CUDA_TRY(e->alloc(&v.done, cap)); CUDA_TRY(e->alloc(&v.phi, cap)); CUDA_TRY(e->alloc(&v.buffer, cap));
+    CUDA_TRY(e->alloc(&v.pos, cap));
     CUDA_TRY(e->alloc(&v.started, cap)); CUDA_TRY(e->alloc(&v.t_now, cap)); CUDA_TRY(e->alloc(&v.play_time, cap));
     CUDA_TRY(e->alloc(&v.bw_hist, cap * v.K)); CUDA_TRY(e->alloc(&v.last_pred, cap));
     CUDA_TRY(e->alloc(&v.err_ring, cap * v.K)); CUDA_TRY(e->alloc(&v.acc, cap * ABR_NUM_ACC));
@@ -237,6 +241,7 @@ int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_
     env->v.session_base = session_base;
     env->fresh_partials = 0;
     env->was_reset = true;
+    env->step_base = 0;
     CUDA_TRY(launch_reset(env->v, d_trace_id, d_start_offset, (cudaStream_t)stream));
     return ABR_OK;
 }
@@ -309,15 +314,20 @@ static int env_rollout_any(AbrEnv* env, int policy, uint64_t seed, int steps, co
     if (policy == ABR_POLICY_FIXED && !d_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs d_actions_in");
     if (!env->v.p.live && (d_speed || d_latency))
         return fail(ABR_ERR_STATE, "speed / latency belong to live mode (SPEC 7): create the environment with live = 1");
+    // the kernel indexes the [steps][N] outputs with 32 bits (4 Gi elements of one array are 32 GB)
+    if ((unsigned long long)steps * (unsigned long long)env->v.n > 0xffffffffull)
+        return fail(ABR_ERR_RANGE, "steps * sessions = %llu exceeds 2^32 - 1: split the episode into several calls",
+                    (unsigned long long)steps * (unsigned long long)env->v.n);
     if constexpr (std::is_same<OT, double>::value) {
         CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
                                 d_reward, d_latency, d_end_of_video, d_actions_out, env->d_stats_partials,
-                                (cudaStream_t)stream, fused));
+                                (cudaStream_t)stream, fused, env->step_base));
     } else {
         CUDA_TRY(launch_rollout(env->v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
                                 d_reward, d_latency, d_end_of_video, d_actions_out, env->d_stats_partials,
-                                (cudaStream_t)stream));
+                                (cudaStream_t)stream, env->step_base));
     }
+    env->step_base += (uint32_t)steps;
     env->fresh_partials = steps > 0 ? rollout_num_blocks(env->v.n) : 0;
     return ABR_OK;
 }
@@ -361,6 +371,8 @@ int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, do
     if (env->v.n == 0) return ABR_OK;
     if (!d_action) return fail(ABR_ERR_INVALID, "action is NULL");
     if (mode != ABR_MPC_REF && mode != ABR_MPC_ROBUST) return fail(ABR_ERR_INVALID, "unknown MPC mode %d", mode);
+    if (!env->v.p.track_history)
+        return fail(ABR_ERR_STATE, "abr_env_mpc_decide needs the throughput history: create the environment with track_history = 1");
     int rc = check_mpc_shape(env->v.A, horizon);
     if (rc) return rc;
     const EnvView& v = env->v;
@@ -397,6 +409,7 @@ int abr_env_state_ptr(AbrEnv* env, int field, void** d_ptr) {
         case ABR_F_DONE: *d_ptr = v.done; break;
         case ABR_F_ERR_LEN: *d_ptr = v.err_len; break;
         case ABR_F_PHASE: *d_ptr = v.phi; break;
+        case ABR_F_POS: *d_ptr = v.pos; break;
         case ABR_F_BUFFER: *d_ptr = v.buffer; break;
         case ABR_F_BW_HIST: *d_ptr = v.bw_hist; break;
         case ABR_F_LAST_PRED: *d_ptr = v.last_pred; break;
@@ -438,6 +451,7 @@ int abr_env_run(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t
         env->v.session_base = session_base;
         env->fresh_partials = 0;
         env->was_reset = true;
+        env->step_base = 0;
         RolloutFused fused;
         fused.in_trace_id = d_trace_id; fused.in_offset = d_start_offset; fused.out_cost = d_qoe_cost;
         rc = env_rollout_any<double>(env, policy, seed, steps, d_actions_in, nullptr, d_delay, d_sleep, d_buffer, d_rebuf,
@@ -501,6 +515,7 @@ int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const in
         env->v.session_base = session_base;
         env->fresh_partials = 0;
         env->was_reset = true;
+        env->step_base = 0;
     } else {
         rc = abr_env_reset(env, tid, off, n_sessions, session_base, stream);
         if (rc) return rc;

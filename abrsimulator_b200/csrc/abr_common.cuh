@@ -11,8 +11,18 @@ namespace abr {
 // Row stride (in doubles) of the cumulative-capacity table C[0..T] of SPEC §3.1, even so that every row starts
 // 16-byte aligned (TMA bulk copies).
 __host__ __device__ __forceinline__ int cum_stride(int T_max) { return (T_max + 2) & ~1; }
-// Row stride (in 32-bit words) of the search-key table K[j] = high word of C[j]; a multiple of 4 (16-byte rows).
-__host__ __device__ __forceinline__ int key_stride(int T_max) { return (T_max + 4) & ~3; }
+// Bucket index of SPEC §3.1 (how the step finds the segment a download ends in; not part of the arithmetic contract):
+// the trace period's data range [0, P) is cut into M = 2T equal cells, idx[b] = number of interior segment
+// boundaries C[1..T-1] that lie in cells below b.  A position x in cell b then ends in a segment j with
+// idx[b] <= j <= idx[b+1] — usually zero or one candidate boundary instead of a log2(T)-step search.
+// 16-bit entries: traces longer than 65 535 segments get no index (M = 0) and are searched by bisection.
+constexpr int kIdxMaxT = 65535;
+__host__ __device__ __forceinline__ int idx_cells(int T) { return T <= kIdxMaxT ? 2 * T : 0; }
+// Row stride (in 16-bit words) of the index table, M + 1 entries per row; a multiple of 8 (16-byte rows for TMA).
+__host__ __device__ __forceinline__ int idx_stride(int T_max) { return T_max <= kIdxMaxT ? (2 * T_max + 2 + 7) & ~7 : 0; }
+// Doubles a staged copy of a C row occupies in shared memory: the row plus two entries of slack (the step reads
+// C[j0 .. j0+3] unconditionally and discards what lies past the candidates).
+__host__ __device__ __forceinline__ int cum_smem_doubles(int T_max) { return cum_stride(T_max) + 2; }
 
 // ---------------------------------------------------------------------------------------------
 // exact fp64 helpers
@@ -64,8 +74,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 // What a step reads about its trace, packed so that it is one dependent 32-byte read after trace_id instead of
 // four scattered ones (interval, period capacity C[T], length, search widths).
 struct __align__(16) TraceMeta {
-    double I, P;
-    int32_t T, bits, pad0, pad1;
+    double I, P;      // segment duration, capacity of one trace period C[T]
+    double scale;     // M / P: cell of a data position x is (int)(x * scale), clamped to M - 1
+    int32_t T, M;     // segments, index cells (0 = no index)
 };
 
 struct EnvView {
@@ -73,10 +84,7 @@ struct EnvView {
     const double* __restrict__ trace_bw;        // [n_traces][T_max]
     const double* __restrict__ trace_cum;       // [n_traces][cum_stride] C[0] = 0, C[j+1] = C[j] + (bw[j]*payload)*I (SPEC §3.1);
                                                 // entries past C[T] are +inf
-    const int32_t* __restrict__ trace_bits;     // [n_traces] search widths: bits 0-7 = b_near (2^b_near - 1 >= the most
-                                                // segments one download can cross), bits 8-15 = b_full (2^b_full >= T)
-    const uint32_t* __restrict__ trace_key;     // [n_traces][key_stride] K[j] = high 32 bits of C[j] (monotone, C >= 0);
-                                                // entries past K[T] are 0x7fffffff
+    const uint16_t* __restrict__ trace_idx;     // [n_traces][idx_stride] bucket index over C (see idx_cells)
     const TraceMeta* __restrict__ trace_meta;   // [n_traces] the per-trace scalars a step needs, one 32-byte record
     const int32_t* __restrict__ trace_len;      // [n_traces]
     const double* __restrict__ trace_interval;  // [n_traces]
@@ -86,7 +94,7 @@ struct EnvView {
     int32_t* seg; int32_t* chunk; int32_t* last_q; int32_t* trace_id; int32_t* hist_len; int32_t* err_len;
     uint8_t* done; uint8_t* started;
     double* t_now; double* play_time;            // live mode (SPEC §7)
-    double* phi; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
+    double* phi; double* pos; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
     unsigned long long* errors;                 // device counter of flagged sessions
     int n_traces, T_max, V, A, K, cap, n;       // n = active sessions
     long long session_base;
@@ -94,7 +102,7 @@ struct EnvView {
 };
 
 // launchers implemented in abr_step.cu / abr_mpc.cu (C++ linkage, internal)
-cudaError_t launch_trace_table(const EnvView& v, double* d_cum, uint32_t* d_key, int32_t* d_bits, TraceMeta* d_meta,
+cudaError_t launch_trace_table(const EnvView& v, double* d_cum, uint16_t* d_idx, int32_t* d_ok, TraceMeta* d_meta,
                                cudaStream_t st);
 cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st);
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
@@ -106,7 +114,8 @@ struct RolloutFused { const int32_t* in_trace_id = nullptr; const double* in_off
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf,
                            double* d_reward, double* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
-                           double* d_block_partials, cudaStream_t st, const RolloutFused& f = RolloutFused{});
+                           double* d_block_partials, cudaStream_t st, const RolloutFused& f = RolloutFused{},
+                           uint32_t step_base = 0);
 // fp32-output overloads (arithmetic stays fp64; outputs are rounded once on the store)
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, float* d_delay,
                         float* d_sleep, float* d_buffer, float* d_rebuf, float* d_reward, float* d_latency,
@@ -114,7 +123,7 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            const double* d_speed, float* d_delay, float* d_sleep, float* d_buffer, float* d_rebuf,
                            float* d_reward, float* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
-                           double* d_block_partials, cudaStream_t st);
+                           double* d_block_partials, cudaStream_t st, uint32_t step_base = 0);
 cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, bool have_partials, double* d_out,
                          cudaStream_t st);
 int stats_num_partials(int n);

@@ -5,26 +5,30 @@
 // square-wave trace (NetworkInfo, Simulator.py:37-42).
 //
 //  * abr_step_kernel     one chunk step per launch, SoA state in HBM (RL harness form).  HBM-bound:
-//                        36 B read + 28 B state write + 41 B outputs per session-step.
+//                        44 B read + 36 B state write + 41 B outputs per session-step.
 //  * abr_rollout_kernel  `steps` chunk steps per launch with the state in registers and the trajectory
 //                        streamed out with st.global.cs (41 B/step) — the fused-episode form.
 //  * abr_trace_table_kernel, abr_reset_kernel, abr_stats_* helpers.
 //
 // SPEC §3.1 integrates the download against the trace's cumulative capacity C[j] (data deliverable from the
 // start of the trace period up to the start of segment j, accumulated left to right once per environment).  A
-// download from position (seg, phase) ends in the segment j with C[j] <= pos + size < C[j+1], which a search at
-// descending powers of four (2 for the global path) finds in b_near = log2(most segments a download can cross)
-// bits that every lane of a warp resolves in lock step: no per-segment loop, no divergence between sessions on
-// fast and slow networks, and a dependency chain of one compare per round instead of one add per segment.  C is
-// the only trace table the step reads (a segment's capacity is C[j+1] - C[j]).
-// Two access paths for C:
-//   * shared-memory path (both kernels): when all sessions of a thread block (a 256-session tile in the per-step
-//     kernel) follow the same trace and its C row fits, the block stages the row in shared memory with a TMA bulk
-//     copy and every probe is an LDS — the "traces staged in shared memory" design of the north star; the fused
-//     episode searches on a staged row of 32-bit keys (the high words of C) and settles ties on C itself.
-//     A per-lane scattered global load costs one L1 wavefront per lane (32 per instruction); an LDS costs 2-6.
-//   * global path (any session order): read-only loads (ld.global.nc), binary search; the table (17 MB at the
-//     benchmark shape) is L2-resident.
+// session carries its position in those data coordinates (`pos`), so a download is `target = pos + size`
+// followed by "which segment holds `target`" — and, as long as the session does not sleep, the next download's
+// target does not depend on anything this step computes after that one addition.  The step is therefore split in
+// two halves:
+//   head  target -> segment j with C[j] <= target < C[j+1], through the per-trace bucket index (abr_common.cuh:
+//         one 16-bit pair lookup bounds j to a handful of candidates — none or one on typical traces — that are
+//         settled with exact compares on C); a fixed, branch-free sequence in the common case.
+//   tail  the division that turns the position inside segment j into time, delay, buffer drain / rebuffer,
+//         sleep cap, reward, stores.
+// The fused episode issues the head of step t+1 *before* the tail of step t (software pipelining: two independent
+// instruction streams per thread instead of one serial chain) and redoes it in the rare case that step t slept.
+// Two access paths for C and the index:
+//   * shared-memory path (both kernels): when all sessions of a thread block (a 128-session tile in the per-step
+//     kernel) follow the same trace and its rows fit, the block stages them in shared memory with TMA bulk
+//     copies and every probe is an LDS — the "traces staged in shared memory" design of the north star.
+//   * global path (any session order): read-only loads (ld.global.nc): one 32-byte record, one index pair and
+//     one or two sectors of C per step; the tables (25 MB at the benchmark shape) are L2-resident.
 #include "abr_common.cuh"
 
 namespace abr {
@@ -41,16 +45,15 @@ constexpr int kStatsSessionsPerBlock = 1024;   // 64 blocks at 65 536 sessions: 
 constexpr int kWrapGuard = 1 << 20;            // safety net of the whole-period loop (SPEC §3.1)
 
 struct Sess {
-    const double* __restrict__ cum;   // C[0..T] of the session's trace (global row)
-    uint32_t cum_s, sizes_s, util_s;  // shared-memory addresses of the block's copies of the C row and of the
-                                      // sizes / utility tables (SMEM path)
-    uint32_t key_s;                   // ... and of the search-key row (KEYS path)
-    const double* __restrict__ sizes; // [V][A] chunk sizes and utilities (global tables)
+    const double* __restrict__ cum;    // C[0..T] of the session's trace (global row)
+    const uint16_t* __restrict__ idx;  // bucket index of the session's trace (global row)
+    uint32_t cum_s, idx_s, sizes_s, util_s;  // shared-memory addresses of the block's copies (SMEM path)
+    const double* __restrict__ sizes;  // [V][A] chunk sizes and utilities (global tables)
     const double* __restrict__ util;
-    double I, phi, buffer;            // phi = fraction of segment `seg` already consumed (SPEC §1)
-    double P;                         // C[T]: capacity of one trace period
-    double c_seg, c_seg1;             // C[seg], C[seg+1] carried between the steps of a fused episode (CARRY)
-    int T, seg, chunk, last_q, hist_len, bits;
+    double I, phi, buffer;             // phi = fraction of segment `seg` already consumed (SPEC §1)
+    double pos;                        // the same position in data coordinates: C[seg] + (C[seg+1] - C[seg]) * phi
+    double P, scale;                   // C[T]: capacity of one trace period; cells per unit of data
+    int T, M, seg, chunk, last_q, hist_len;
     bool done;
     // live mode (SPEC §7)
     double t_now, play_time, speed;
@@ -62,9 +65,9 @@ struct StepRes {
     bool eov, inert, walk_error, reset_mpc;
 };
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint32_t x;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(addr));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(x) : "r"(addr));
     return x;
 }
 
@@ -74,15 +77,19 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return x;
 }
 
-// C row access by byte position.  SMEM: `pos` is an absolute shared-memory address (the row base is folded into the
-// position, so a probe is one VIADDMNMX + one LDS); else a byte offset into the global row.
+// C[j] / idx[b] of the session's trace: an LDS on the shared-memory path, else a read-only global load.
 template <bool SMEM>
-__device__ __forceinline__ double ld_cum(const Sess& s, uint32_t pos) {
-    return SMEM ? lds_f64(pos) : __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(s.cum) + pos));
+__device__ __forceinline__ double ld_c(const Sess& s, const int j) {
+    return SMEM ? lds_f64(s.cum_s + 8u * (uint32_t)j) : __ldg(s.cum + j);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ int ld_idx(const Sess& s, const int b) {
+    return SMEM ? (int)lds_u16(s.idx_s + 2u * (uint32_t)b) : (int)__ldg(s.idx + b);
 }
 
 // The table reads of one step (SPEC §3.1 size, §3.4 utilities).  They depend only on (chunk, q, last_q), so the fused
-// episode issues them at the end of the previous step.
+// episode issues them ahead of the step.
 struct Lookup { double size, u, u_prev; };
 
 template <bool SMEM>
@@ -113,6 +120,13 @@ __device__ __forceinline__ void advance_trace(int& seg, double& phi, const doubl
     }
 }
 
+// SPEC §3.1 / §3.3: data-space position of (seg, phi).
+template <bool SMEM>
+__device__ __forceinline__ double position_of(const Sess& s, const int seg, const double phi) {
+    const double c0 = ld_c<SMEM>(s, seg), c1 = ld_c<SMEM>(s, seg + 1);
+    return dadd(c0, dmul(dsub(c1, c0), phi));
+}
+
 // SPEC §7 play(dt): playback during an interval; returns the stall time.
 __device__ __forceinline__ double live_play(Sess& s, double& buffer, double& startup, const double dt) {
     if (!s.started) { startup = dadd(startup, dt); return 0.0; }
@@ -125,200 +139,129 @@ __device__ __forceinline__ double live_play(Sess& s, double& buffer, double& sta
     return stall;
 }
 
-// Largest j in [lo, lo + 2^bits) and [0, T) with C[j] <= target, given C[lo] <= target.  Radix-4 rounds (three
-// independent probes each: half the dependent round trips of a binary search), preceded by one radix-8 round when
-// `bits` is odd; every lane of a warp runs the same rounds.  Positions are byte positions (see ld_cum); a probe
-// past the row is clamped to C[T] = P > target and fails, so successful probes are never clamped.
+// ---- head of a step (SPEC §3.1): where does the download end? ----
+// target is the wrapped data position in [0, P), n the whole trace periods it went through, j the segment with
+// C[j] <= target < C[j+1], c_j / c_j1 those two entries.
+struct Head { double target, c_j, c_j1; int j, n; };
+
+// Common case as one branch-free sequence: no wrap (raw < P), an index exists and the target's cell holds at most
+// two segment boundaries.  Returns false otherwise (the caller then runs head_any); the loads are in range either way.
 template <bool SMEM>
-__device__ __forceinline__ uint32_t search_cum(const Sess& s, uint32_t p_lo, const uint32_t p_end, int bits,
-                                               const double target) {
-    if (!SMEM) {   // global path: bound by L1 wavefronts (one per lane per scattered load) -> fewest probes: radix 2
-        for (; bits > 0; --bits) {
-            const uint32_t p1 = min(p_lo + (8u << (bits - 1)), p_end);
-            if (ld_cum<SMEM>(s, p1) <= target) p_lo = p1;
-        }
-        return p_lo;
-    }
-    if (bits & 1) {
-        if (bits >= 3) {
-            bits -= 3;
-            const uint32_t st = 8u << bits;
-            double c[7];
-#pragma unroll
-            for (int m = 0; m < 7; ++m) c[m] = ld_cum<SMEM>(s, min(p_lo + (uint32_t)(m + 1) * st, p_end));
-            // C is non-decreasing: the successful probes are the first `cnt` (three-input adds, depth 3)
-            const int b0 = c[0] <= target, b1 = c[1] <= target, b2 = c[2] <= target, b3 = c[3] <= target;
-            const int b4 = c[4] <= target, b5 = c[5] <= target, b6 = c[6] <= target;
-            const int cnt = (b0 + b1 + b2) + (b3 + b4 + b5) + b6;
-            p_lo += (uint32_t)cnt * st;
-        } else {
-            bits -= 1;
-            const uint32_t p1 = min(p_lo + 8u, p_end);
-            if (ld_cum<SMEM>(s, p1) <= target) p_lo = p1;
-        }
-    }
-    for (; bits > 0; bits -= 2) {
-        const uint32_t st = 8u << (bits - 2);
-        const uint32_t p1 = min(p_lo + st, p_end), p2 = min(p_lo + 2 * st, p_end), p3 = min(p_lo + 3 * st, p_end);
-        const double c1 = ld_cum<SMEM>(s, p1), c2 = ld_cum<SMEM>(s, p2), c3 = ld_cum<SMEM>(s, p3);
-        if (c1 <= target) p_lo = p1;
-        if (c2 <= target) p_lo = p2;
-        if (c3 <= target) p_lo = p3;
-    }
-    return p_lo;
+__device__ __forceinline__ bool head_fast(const Sess& s, const double raw, Head& h) {
+    const int Mc = s.M > 0 ? s.M - 1 : 0;
+    int b = __double2int_rz(dmul(raw, s.scale));
+    b = min(max(b, 0), Mc);
+    const int j0 = s.M > 0 ? ld_idx<SMEM>(s, b) : 0;
+    const int cnt = s.M > 0 ? ld_idx<SMEM>(s, b + 1) - j0 : 3;
+    const double c0 = ld_c<SMEM>(s, j0), c1 = ld_c<SMEM>(s, j0 + 1), c2 = ld_c<SMEM>(s, j0 + 2), c3 = ld_c<SMEM>(s, j0 + 3);
+    const bool m1 = cnt >= 1 && c1 <= raw;     // the boundaries are increasing: m2 implies m1
+    const bool m2 = cnt >= 2 && c2 <= raw;
+    h.target = raw;
+    h.n = 0;
+    h.j = j0 + (m1 ? 1 : 0) + (m2 ? 1 : 0);
+    h.c_j = m2 ? c2 : (m1 ? c1 : c0);
+    h.c_j1 = m2 ? c3 : (m1 ? c2 : c1);
+    return raw < s.P && cnt <= 2;
 }
 
-// The same search on the 32-bit keys K[j] = high word of C[j] (fused episode, shared memory): returns the byte
-// position in the key row of the largest j in [lo, lo + 2^bits) and [0, T) with K[j] < kt, or `kp_lo` itself.
-// K[j] < kt implies C[j] < target, so C[j] <= target holds at the result; the few j above it whose key equals kt
-// are settled by the caller with exact 64-bit compares.  A random 4-byte LDS costs ~3.5 shared-memory wavefronts
-// per warp against ~5.8 for an 8-byte one, and the compare runs on the integer pipe instead of the FP64 pipe —
-// at >= 1 Mi sessions the kernel is bound by exactly those wavefronts (ncu: l1tex__data_pipe_lsu_wavefronts 91 %).
-// BITS > 0: compile-time width (every round unrolled, no loop or parity branches); BITS == 0: `bits_rt`.
-template <int BITS>
-__device__ __forceinline__ uint32_t search_keys(uint32_t kp_lo, const uint32_t kp_end, const int bits_rt, const uint32_t kt) {
-    int bits = BITS > 0 ? BITS : bits_rt;
-    if (bits & 1) {
-        if (bits >= 3) {
-            bits -= 3;
-            const uint32_t st = 4u << bits;
-            uint32_t k[7];
-#pragma unroll
-            for (int m = 0; m < 7; ++m) k[m] = lds_u32(min(kp_lo + (uint32_t)(m + 1) * st, kp_end));
-            // keys are below 2^31 (high words of non-negative doubles), so k - kt is negative exactly when k < kt:
-            // the sign bits are summed with three-input adds (depth 3) instead of a chain of seven selects
-            int neg = 0;
-            {
-                int d[7];
-#pragma unroll
-                for (int m = 0; m < 7; ++m) d[m] = (int)(k[m] - kt) >> 31;   // -1 or 0
-                neg = (d[0] + d[1] + d[2]) + (d[3] + d[4] + d[5]) + d[6];
-            }
-            kp_lo -= (uint32_t)neg * st;
-        } else {
-            bits -= 1;
-            const uint32_t p1 = min(kp_lo + 4u, kp_end);
-            if (lds_u32(p1) < kt) kp_lo = p1;
+// Any case: whole-period wrap, any number of boundaries in the cell, traces without an index (bisection).
+template <bool SMEM>
+__device__ __forceinline__ void head_any(const Sess& s, double target, Head& h, bool& walk_error) {
+    int n = 0;
+    if (target >= s.P) {
+        do { target = dsub(target, s.P); ++n; } while (target >= s.P && n < kWrapGuard);
+        if (n >= kWrapGuard) { walk_error = true; target = 0.0; }
+    }
+    int j, j_hi;
+    if (s.M > 0) {
+        const int b = min(max(__double2int_rz(dmul(target, s.scale)), 0), s.M - 1);
+        j = ld_idx<SMEM>(s, b);
+        j_hi = ld_idx<SMEM>(s, b + 1);
+    } else {
+        j = 0;
+        j_hi = s.T - 1;
+    }
+    if (j_hi - j > 8) {   // long run of candidates (a stretch of near-zero bandwidth, or no index): bisection
+        while (j < j_hi) {
+            const int mid = (j + j_hi + 1) >> 1;
+            if (ld_c<SMEM>(s, mid) <= target) j = mid; else j_hi = mid - 1;
         }
     }
-#pragma unroll
-    for (; bits > 0; bits -= 2) {
-        const uint32_t st = 4u << (bits - 2);
-        const uint32_t p1 = min(kp_lo + st, kp_end), p2 = min(kp_lo + 2 * st, kp_end), p3 = min(kp_lo + 3 * st, kp_end);
-        const uint32_t k1 = lds_u32(p1), k2 = lds_u32(p2), k3 = lds_u32(p3);
-        if (k1 < kt) kp_lo = p1;
-        if (k2 < kt) kp_lo = p2;
-        if (k3 < kt) kp_lo = p3;
-    }
-    return kp_lo;
+    double c_j = ld_c<SMEM>(s, j), c_j1 = ld_c<SMEM>(s, j + 1);
+    while (j < j_hi && c_j1 <= target) { ++j; c_j = c_j1; c_j1 = ld_c<SMEM>(s, j + 1); }
+    h.target = target; h.n = n; h.j = j; h.c_j = c_j; h.c_j1 = c_j1;
 }
 
-// SPEC §3 for one session held in registers.  `q` must already be a valid index; `lk` holds the step's table reads.
-// SMEM: the block's shared-memory copy of the trace's C row is used (else the global table).
-// CARRY: s.c_seg / s.c_seg1 hold C[seg] / C[seg+1] on entry and on exit (fused episode: the segment a download ends
-// in is the one the next download starts in, so the values are already in registers).
-// FAST: auto_reset is on (a session is never inert) — drops the done/inert bookkeeping.
-// LIVE: live-streaming semantics of SPEC §7 (pause gate before the download, start-up latch, playback speed).
-template <bool SMEM, bool CARRY, bool FAST = false, bool LIVE = false, bool KEYS = false>
-__device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, const Lookup& lk, StepRes& r,
-                                          const bool want_thr) {
+template <bool SMEM>
+__device__ __forceinline__ void head(const Sess& s, const double raw, Head& h, bool& walk_error) {
+    if (!head_fast<SMEM>(s, raw, h)) head_any<SMEM>(s, raw, h, walk_error);
+}
+
+// SPEC §7.1 pause gate (Simulator.py:143-145): wait for the live edge, then for room in the buffer; moves the trace
+// position by the idle time.  Runs before the head of a live step.
+struct LiveGate { double buffer, rebuf, idle, startup; };
+
+template <bool SMEM>
+__device__ __forceinline__ void live_gate(const EnvView& v, Sess& s, LiveGate& g) {
     const AbrParams& p = v.p;
-    r.walk_error = false;
+    g.buffer = s.buffer; g.startup = 0.0;
+    const double w1 = max0(dsub(dmul((double)(s.chunk + 1), p.chunk_length), s.t_now));
+    g.rebuf = live_play(s, g.buffer, g.startup, w1);
+    const double w2 = (s.started && g.buffer > p.max_buffer)
+                          ? (s.speed == 1.0 ? dsub(g.buffer, p.max_buffer) : ddiv(dsub(g.buffer, p.max_buffer), s.speed))
+                          : 0.0;
+    g.rebuf = dadd(g.rebuf, live_play(s, g.buffer, g.startup, w2));
+    g.idle = dadd(w1, w2);
+    if (g.idle > 0.0) {
+        advance_trace(s.seg, s.phi, g.idle, s.I, s.T);
+        s.pos = position_of<SMEM>(s, s.seg, s.phi);
+    }
+}
+
+// ---- tail of a step (SPEC §3.1 from the division on, §3.2-§3.5) for one session held in registers ----
+// `q` must already be a valid index; `lk` holds the step's table reads, `h` its head.
+// FAST: auto_reset is on (a session is never inert) — drops the done/inert bookkeeping.
+// LIVE: live-streaming semantics of SPEC §7 (`g` = the step's pause gate).
+// Returns true when the step moved the trace position in time (sleep): s.pos was then recomputed from (seg, phi)
+// and a head issued ahead for the next step is stale.
+template <bool SMEM, bool FAST, bool LIVE>
+__device__ __forceinline__ bool step_tail(const EnvView& v, Sess& s, const Head& h, const int q, const Lookup& lk,
+                                          const LiveGate& g, StepRes& r, const bool want_thr) {
+    const AbrParams& p = v.p;
     r.reset_mpc = false;
     if (!FAST && s.done) {  // only reachable with auto_reset == 0
-        r.delay = r.sleep = r.rebuf = r.reward = r.thr = r.u = r.smooth = 0.0;
+        r.delay = r.sleep = r.rebuf = r.reward = r.thr = r.u = r.smooth = r.latency = r.startup = 0.0;
         r.buffer = s.buffer;
         r.eov = true;
         r.inert = true;
-        return;
+        return false;
     }
     r.inert = false;
     const double size = lk.size, u = lk.u, u_prev = lk.u_prev;
-    double phi = s.phi;
-    int seg = s.seg;
-    double live_buffer = s.buffer, live_rebuf = 0.0, live_idle = 0.0, live_startup = 0.0;
-    bool live_moved = false;   // the pause gate moved the trace position: the carried C[seg], C[seg+1] are stale
-    if (LIVE) {   // 7.1 pause gate (Simulator.py:143-145): live edge, then room in the buffer
-        const double w1 = max0(dsub(dmul((double)(s.chunk + 1), p.chunk_length), s.t_now));
-        live_rebuf = live_play(s, live_buffer, live_startup, w1);
-        const double w2 = (s.started && live_buffer > p.max_buffer)
-                              ? (s.speed == 1.0 ? dsub(live_buffer, p.max_buffer)
-                                                : ddiv(dsub(live_buffer, p.max_buffer), s.speed))
-                              : 0.0;
-        live_rebuf = dadd(live_rebuf, live_play(s, live_buffer, live_startup, w2));
-        live_idle = dadd(w1, w2);
-        if (live_idle > 0.0) { advance_trace(seg, phi, live_idle, s.I, s.T); live_moved = true; }
-    }
-    // 3.1 download against the cumulative capacity (Simulator.py:158-163 in closed form, with wrap-around)
     const int T = s.T;
-    const uint32_t p_base = SMEM ? s.cum_s : 0u;          // byte position of C[0]
-    const uint32_t p_end = p_base + 8u * (uint32_t)T;     // ... of C[T]
-    double c_seg = s.c_seg, c_seg1 = s.c_seg1;
-    if (!CARRY || (LIVE && live_moved)) {
-        c_seg = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg);
-        c_seg1 = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg + 8u);
-    }
-    double target = dadd(dadd(c_seg, dmul(dsub(c_seg1, c_seg), phi)), size);
-    // without a wrap C[seg] <= target and b_near bits reach every segment one download can cross; a download that
-    // runs past the end of the trace period (rare per session, but one lane in ten warp-steps) restarts at C[0]
-    // with the same width: what is left of it after the wrap is less than one chunk (target - n*P < size because
-    // the start position is below P), so it ends within size_max / min capacity < 2^b_near - 1 segments of C[0].
-    // Every lane of a block on the shared-memory path therefore runs the same search (bits is a per-trace constant).
-    uint32_t p_lo = p_base + 8u * (uint32_t)seg;
-    const int bits = s.bits & 0xff;
-    double kd = (double)(-seg);                           // segment boundaries crossed: (j - seg) + n*T, j added below
-    if (target >= s.P) {
-        int n = 0;                                        // whole trace periods
-        do { target = dsub(target, s.P); ++n; } while (target >= s.P && n < kWrapGuard);
-        if (n >= kWrapGuard) { r.walk_error = true; target = 0.0; }
-        p_lo = p_base;
-        kd = dadd(kd, dmul((double)n, (double)T));        // exact in fp64
-    }
-    uint32_t p_j;
-    double c_j, c_j1;
-    if (KEYS) {
-        const uint32_t kp0 = s.key_s + ((p_lo - p_base) >> 1), kp_end = s.key_s + 4u * (uint32_t)T;
-        const uint32_t kt = (uint32_t)__double2hiint(target);
-        uint32_t kp;
-        // the usual widths get fully unrolled searches
-        if (bits == 7) kp = search_keys<7>(kp0, kp_end, 7, kt);
-        else if (bits == 6) kp = search_keys<6>(kp0, kp_end, 6, kt);
-        else if (bits == 8) kp = search_keys<8>(kp0, kp_end, 8, kt);
-        else if (bits == 5) kp = search_keys<5>(kp0, kp_end, 5, kt);
-        else kp = search_keys<0>(kp0, kp_end, bits, kt);
-        p_j = p_base + ((kp - s.key_s) << 1);
-        c_j = ld_cum<SMEM>(s, p_j);
-        c_j1 = ld_cum<SMEM>(s, p_j + 8u);
-        // segments whose key equals the target's: exact compares (rarely more than none; C[T] = P > target ends it)
-        for (int g = 0; c_j1 <= target && g < kWrapGuard; ++g) {
-            p_j += 8u;
-            c_j = c_j1;
-            c_j1 = ld_cum<SMEM>(s, p_j + 8u);
-        }
-    } else {
-        p_j = search_cum<SMEM>(s, p_lo, p_end, bits, target);
-        c_j = ld_cum<SMEM>(s, p_j);
-        c_j1 = ld_cum<SMEM>(s, p_j + 8u);
-    }
-    kd = dadd(kd, (double)(int)((p_j - p_base) >> 3));    // exact
-    if (!(target < c_j1)) r.walk_error = true;   // insurance: the search width covered the download
-    const double phi_new = ddiv(dsub(target, c_j), dsub(c_j1, c_j));   // fraction of segment j consumed
-    double delay = dadd(max0(dmul(dadd(kd, dsub(phi_new, phi)), s.I)), p.rtt);
-    seg = (int)((p_j - p_base) >> 3);
-    phi = phi_new;
-    if (CARRY) { c_seg = c_j; c_seg1 = c_j1; }
+    if (!(h.target < h.c_j1)) r.walk_error = true;   // insurance: the index covered the download
+    // segment boundaries crossed: (j - seg) + n*T
+    double kd = (double)(h.j - s.seg);
+    if (h.n != 0) kd = dadd(kd, dmul((double)h.n, (double)T));   // exact in fp64
+    const double phi_new = ddiv(dsub(h.target, h.c_j), dsub(h.c_j1, h.c_j));   // fraction of segment j consumed
+    const double delay = dadd(max0(dmul(dadd(kd, dsub(phi_new, s.phi)), s.I)), p.rtt);
+    int seg = h.j;
+    double phi = phi_new;
+    bool moved = false;
     r.thr = want_thr ? ddiv(size, delay) : 0.0;
     double rebuf, buffer, sleep = 0.0;
     r.latency = 0.0;
     r.startup = 0.0;
+    s.pos = h.target;
     if (LIVE) {   // 7.2
-        rebuf = dadd(live_rebuf, live_play(s, live_buffer, live_startup, delay));
+        double live_buffer = g.buffer, live_startup = g.startup;
+        rebuf = dadd(g.rebuf, live_play(s, live_buffer, live_startup, delay));
         buffer = dadd(live_buffer, p.chunk_length);
-        s.t_now = dadd(dadd(s.t_now, live_idle), delay);
+        s.t_now = dadd(dadd(s.t_now, g.idle), delay);
         if (!s.started && buffer >= p.start_up_length) s.started = true;
         r.latency = dsub(s.t_now, s.play_time);
         r.startup = live_startup;
-        sleep = live_idle;
+        sleep = g.idle;
     } else {
         // 3.2 buffer drain / rebuffer
         rebuf = max0(dsub(delay, s.buffer));
@@ -330,10 +273,8 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
             sleep = dmul(ceil(inv_q != 0.0 ? dmul(over, inv_q) : ddiv(over, p.sleep_quantum)), p.sleep_quantum);
             buffer = dsub(buffer, sleep);
             advance_trace(seg, phi, sleep, s.I, T);
-            if (CARRY) {
-                c_seg = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg);
-                c_seg1 = ld_cum<SMEM>(s, p_base + 8u * (uint32_t)seg + 8u);
-            }
+            s.pos = position_of<SMEM>(s, seg, phi);
+            moved = true;
         }
     }
     // 3.4 reward
@@ -348,7 +289,6 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     s.seg = seg;
     s.phi = phi;
     s.buffer = buffer;
-    if (CARRY) { s.c_seg = c_seg; s.c_seg1 = c_seg1; }
     r.eov = (s.chunk >= v.V);
     if (r.eov) {
         if (FAST || p.auto_reset) {
@@ -359,6 +299,24 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
             s.done = true;
         }
     }
+    return moved;
+}
+
+// One whole step (gate, head, tail) — the per-step kernel's form.
+template <bool SMEM, bool FAST, bool LIVE>
+__device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q, const Lookup& lk, StepRes& r,
+                                          const bool want_thr) {
+    r.walk_error = false;
+    LiveGate g;
+    g.buffer = s.buffer; g.rebuf = g.idle = g.startup = 0.0;
+    Head h;
+    if (!FAST && s.done) {
+        h.target = h.c_j = 0.0; h.c_j1 = 1.0; h.j = 0; h.n = 0;
+    } else {
+        if (LIVE) live_gate<SMEM>(v, s, g);
+        head<SMEM>(s, dadd(s.pos, lk.size), h, r.walk_error);
+    }
+    step_tail<SMEM, FAST, LIVE>(v, s, h, q, lk, g, r, want_thr);
 }
 
 // SPEC §4, buffer-based policy on the pre-step buffer level.
@@ -371,30 +329,32 @@ __device__ __forceinline__ int policy_bba(const EnvView& v, const double b) {
 }
 
 // The per-session words of a step that come straight from the SoA state (coalesced: thread i <-> session i).
-struct RawState { int tr, seg, chunk, last_q; double phi, buffer; };
+struct RawState { int tr, seg, chunk, last_q; double phi, pos, buffer; };
 
 __device__ __forceinline__ RawState load_raw(const EnvView& v, int i) {
     RawState w;
     w.tr = v.trace_id[i]; w.seg = v.seg[i]; w.chunk = v.chunk[i]; w.last_q = v.last_q[i];
-    w.phi = v.phi[i]; w.buffer = v.buffer[i];
+    w.phi = v.phi[i]; w.pos = v.pos[i]; w.buffer = v.buffer[i];
     return w;
 }
 
 __device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawState& w, Sess& s) {
     const int tr = w.tr;
     s.cum = v.trace_cum + (size_t)tr * cum_stride(v.T_max);
+    s.idx = v.trace_idx + (size_t)tr * idx_stride(v.T_max);
     s.sizes = v.sizes;
     s.util = v.util;
     {   // one 32-byte record: two 16-byte read-only loads from the same sector
         const double2 ip = __ldg(reinterpret_cast<const double2*>(v.trace_meta + tr));
         const int4 tb = __ldg(reinterpret_cast<const int4*>(v.trace_meta + tr) + 1);
-        s.I = ip.x; s.P = ip.y; s.T = tb.x; s.bits = tb.y;
+        s.I = ip.x; s.P = ip.y; s.scale = __hiloint2double(tb.y, tb.x); s.T = tb.z; s.M = tb.w;
     }
-    s.cum_s = s.sizes_s = s.util_s = s.key_s = 0u;
+    s.cum_s = s.idx_s = s.sizes_s = s.util_s = 0u;
     s.seg = w.seg;
     s.chunk = w.chunk;
     s.last_q = w.last_q;
     s.phi = w.phi;
+    s.pos = w.pos;
     s.buffer = w.buffer;
     s.done = v.p.auto_reset ? false : (v.done[i] != 0);
     s.hist_len = v.p.track_history ? v.hist_len[i] : 0;
@@ -406,12 +366,12 @@ __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
 }
 
 // Builds the per-trace tables of SPEC §3.1, one thread per trace (the accumulation is sequential by definition;
-// runs once per environment): C[0] = 0, C[j+1] = C[j] + (bw[j]*payload)*I, and the search widths b_full
-// (2^b_full >= T) and b_near (2^b_near - 1 >= 3 + max chunk size / smallest segment capacity, the most segment
-// boundaries a download that stays inside the period can cross).  bits = -1 flags a trace whose period capacity is
-// not a positive finite number or that holds a segment without capacity.
+// runs once per environment): C[0] = 0, C[j+1] = C[j] + (bw[j]*payload)*I, and the bucket index over C (abr_common.cuh):
+// cell(x) = min((int)(x * scale), M - 1) is non-decreasing in x, so with idx[b] = #{interior boundaries j in 1..T-1 :
+// cell(C[j]) < b} every x of cell b satisfies C[idx[b]] <= x, and the boundaries above idx[b+1] lie beyond x.
+// ok = 0 flags a trace whose period capacity is not a positive finite number or that holds a segment without capacity.
 __global__ void __launch_bounds__(kStepBlock)
-abr_trace_table_kernel(EnvView v, double* __restrict__ cum, uint32_t* __restrict__ key, int32_t* __restrict__ bits,
+abr_trace_table_kernel(EnvView v, double* __restrict__ cum, uint16_t* __restrict__ idx, int32_t* __restrict__ ok_out,
                        TraceMeta* __restrict__ meta) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= v.n_traces) return;
@@ -420,41 +380,42 @@ abr_trace_table_kernel(EnvView v, double* __restrict__ cum, uint32_t* __restrict
     const double I = v.trace_interval[t];
     const double* bw = v.trace_bw + (size_t)t * v.T_max;
     double* c_row = cum + (size_t)t * cum_stride(v.T_max);
-    uint32_t* k_row = key + (size_t)t * key_stride(v.T_max);
-    double size_max = 0.0;
-    for (int i = 0; i < v.V * v.A; ++i) size_max = fmax(size_max, v.sizes[i]);
     double c = 0.0, mincap = kInf;
     c_row[0] = 0.0;
-    k_row[0] = 0u;
 #pragma unroll 8
     for (int j = 0; j < T; ++j) {
         const double c_next = dadd(c, dmul(dmul(bw[j], v.p.payload), I));
         c_row[j + 1] = c_next;
-        k_row[j + 1] = (uint32_t)__double2hiint(c_next);
         mincap = fmin(mincap, dsub(c_next, c));   // the capacity the step sees: C[j+1] - C[j]
         c = c_next;
     }
     for (int j = T + 1; j < cum_stride(v.T_max); ++j) c_row[j] = kInf;
-    for (int j = T + 1; j < key_stride(v.T_max); ++j) k_row[j] = 0x7fffffffu;
-    int b_full = 0;
-    while ((1 << b_full) < T) ++b_full;
-    int b_near = b_full;
-    const double R = dadd(3.0, dmul(ddiv(size_max, mincap), 1.000000001));
-    if (R < (double)T) {
-        const int Ri = (int)R + 1;
-        b_near = 0;
-        while ((1 << b_near) - 1 < Ri) ++b_near;
-        if (b_near > b_full) b_near = b_full;
-    }
     const bool ok = c > 0.0 && c < kInf && mincap > 0.0;
-    bits[t] = ok ? (b_near | (b_full << 8)) : -1;
+    int M = idx_cells(T);
+    double scale = 0.0;
+    if (M > 0 && ok) {
+        scale = ddiv((double)M, c);
+        if (!(scale > 0.0) || !(scale < kInf)) M = 0;   // period capacity too small to scale: bisection instead
+    } else {
+        M = 0;
+    }
+    if (idx_stride(v.T_max) > 0) {
+        uint16_t* i_row = idx + (size_t)t * idx_stride(v.T_max);
+        int j = 1;   // next interior boundary not yet known to lie in a cell below b
+        for (int b = 0; b <= M; ++b) {
+            while (j <= T - 1 && min(max(__double2int_rz(dmul(c_row[j], scale)), 0), M - 1) < b) ++j;
+            i_row[b] = (uint16_t)(j - 1);
+        }
+        for (int b = M + 1; b < idx_stride(v.T_max); ++b) i_row[b] = (uint16_t)(T > 0 ? T - 1 : 0);
+    }
+    ok_out[t] = ok ? 1 : 0;
     TraceMeta m;
-    m.I = I; m.P = c; m.T = T; m.bits = b_near | (b_full << 8); m.pad0 = m.pad1 = 0;
+    m.I = I; m.P = c; m.scale = scale; m.T = T; m.M = M;
     meta[t] = m;
 }
 
-// SPEC §2 for one session: the validated trace and the position (seg, phase) of the start offset.  Shared by the
-// reset kernel and the episode kernel's fused reset, so that both perform the same operations.
+// SPEC §2 for one session: the validated trace and the position (seg, phase, data position) of the start offset.
+// Shared by the reset kernel and the episode kernel's fused reset, so that both perform the same operations.
 __device__ __forceinline__ RawState reset_position(const EnvView& v, int tr, const double off, int& n_bad) {
     RawState w;
     if (tr < 0 || tr >= v.n_traces) { ++n_bad; tr = 0; }
@@ -465,6 +426,10 @@ __device__ __forceinline__ RawState reset_position(const EnvView& v, int tr, con
     int seg = (int)fmod(n, (double)T);
     w.phi = dsub(x, n);   // exact, in [0, 1)
     if (seg < 0 || seg >= T) { ++n_bad; seg = 0; }
+    if (!(w.phi >= 0.0 && w.phi < 1.0)) { ++n_bad; w.phi = 0.0; }   // NaN / infinite start offset
+    const double* c_row = v.trace_cum + (size_t)tr * cum_stride(v.T_max);
+    const double c0 = __ldg(c_row + seg), c1 = __ldg(c_row + seg + 1);
+    w.pos = dadd(c0, dmul(dsub(c1, c0), w.phi));
     w.tr = tr; w.seg = seg; w.chunk = 0; w.last_q = v.p.default_quality; w.buffer = 0.0;
     return w;
 }
@@ -476,7 +441,7 @@ abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* 
     int n_bad = 0;
     const RawState w = reset_position(v, trace_id[i], start_offset ? start_offset[i] : 0.0, n_bad);
     if (n_bad) atomicAdd(v.errors, (unsigned long long)n_bad);
-    v.trace_id[i] = w.tr; v.seg[i] = w.seg; v.phi[i] = w.phi; v.buffer[i] = 0.0; v.chunk[i] = 0;
+    v.trace_id[i] = w.tr; v.seg[i] = w.seg; v.phi[i] = w.phi; v.pos[i] = w.pos; v.buffer[i] = 0.0; v.chunk[i] = 0;
     v.last_q[i] = v.p.default_quality; v.done[i] = 0; v.hist_len[i] = 0; v.last_pred[i] = 0.0; v.err_len[i] = 0;
     v.t_now[i] = 0.0; v.play_time[i] = 0.0; v.started[i] = v.p.start_up_length <= 0.0 ? 1 : 0;
 #pragma unroll
@@ -492,16 +457,21 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 
 // Wait for the given phase of an mbarrier (try_wait suspends the thread for a bounded, implementation-defined time
-// per call).  The retry count is bounded so that a programming error cannot hang the GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
-    for (int spins = 0; spins < (1 << 16); ++spins) {
+// per call).  The retry count is bounded so that a programming error cannot hang the GPU: a wait that gives up traps
+// (the launch fails with an error the caller sees) instead of computing on whatever the buffer holds.
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    for (int spins = 0; spins < (1 << 20); ++spins) {
         uint32_t done;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-        if (done) return true;
+        if (done) return;
     }
-    return false;
+    __trap();
 }
+
+// Bytes of the staged copies of one trace's rows (multiples of 16): C[0..T] and idx[0..M].
+__device__ __forceinline__ uint32_t row_bytes_of(int T) { return (uint32_t)((T + 2) / 2) * 16u; }
+__device__ __forceinline__ uint32_t idx_bytes_of(int M) { return (uint32_t)((M + 1 + 7) / 8) * 16u; }
 
 // One chunk step of one session with the state in HBM (SPEC §3, §7).
 // FAST: the five f64 outputs and end_of_video requested, no throughput history / accumulators, auto_reset on —
@@ -526,16 +496,18 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
     if (bad) atomicAdd(v.errors, 1ull);
     StepRes r;
     const Lookup lk = lookup_tables<false>(s, v.A, v.V, s.chunk, q, s.last_q);
-    step_core<SMEM, false, FAST, LIVE>(v, s, q, lk, r, (!FAST && v.p.track_history) || o_thr != nullptr);
+    step_core<SMEM, FAST, LIVE>(v, s, q, lk, r, (!FAST && v.p.track_history) || o_thr != nullptr);
     if (r.walk_error) atomicAdd(v.errors, 1ull);
     if (FAST) {
-        v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
+        v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.pos[i] = s.pos;
+        v.buffer[i] = s.buffer;
         __stcs(o_delay + i, (OT)r.delay); __stcs(o_sleep + i, (OT)r.sleep); __stcs(o_buffer + i, (OT)r.buffer);
         __stcs(o_rebuf + i, (OT)r.rebuf); __stcs(o_reward + i, (OT)r.reward);
         o_eov[i] = r.eov ? 1 : 0;
     } else {
         if (!r.inert) {
-            v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
+            v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.pos[i] = s.pos;
+            v.buffer[i] = s.buffer;
             if (LIVE) { v.t_now[i] = s.t_now; v.play_time[i] = s.play_time; v.started[i] = s.started ? 1 : 0; }
             if (v.p.track_history) {
                 // ring slot of this sample = (hist_len before the step) mod K; after an auto-reset hist_len is 0
@@ -573,11 +545,10 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
 }
 
 // <= 72 registers: 7 blocks of 128 threads per SM, one wave.  A block walks a run of consecutive tiles of 128 sessions.
-// When a tile starts and ends on the same trace (callers that keep sessions sorted by trace) and its C row fits in
-// `smem_doubles`, the block stages the row with one TMA bulk copy — once, for as long as the following tiles stay on
-// that trace; no barrier is needed while the row stays — and the search probes of the lanes on that trace are LDS.
-// A per-lane scattered global load costs one L1 wavefront per lane, which is what bounds the global path (ncu:
-// l1tex__data_pipe_lsu_wavefronts).
+// When a tile starts and ends on the same trace (callers that keep sessions sorted by trace) and the trace's C and
+// index rows fit in the shared-memory buffer, the block stages them with two TMA bulk copies — once, for as long as
+// the following tiles stay on that trace; no barrier is needed while the rows stay — and the probes of the lanes on
+// that trace are LDS.  Every other lane reads the L2-resident tables directly (one index pair + one or two sectors of C).
 template <bool FAST, bool LIVE, typename OT>
 __global__ void __launch_bounds__(kTile, LIVE ? 4 : kTileBlocksPerSM)
 abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __restrict__ speed,
@@ -596,9 +567,10 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
         }
         __syncthreads();
     }
+    double* s_row = reinterpret_cast<double*>(s_row2);
+    uint16_t* s_idx = reinterpret_cast<uint16_t*>(s_row + smem_doubles);
     uint32_t parity = 0u;                        // phase of the next staging copy (block-uniform)
-    int staged = -1;                             // trace whose C row the buffer holds (block-uniform, kept per thread)
-    int nofit = -1;                              // last trace whose row did not fit (not retried tile after tile)
+    int staged = -1;                             // trace whose rows the buffer holds (block-uniform, kept per thread)
     // the state words and the action of the next tile are requested before the current tile is computed, so that
     // two tiles of loads per warp are in flight (the kernel is bound by HBM latency x occupancy otherwise)
     RawState w_next;
@@ -632,25 +604,23 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
             if (valid) step_session<false, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
             continue;
         }
-        if (tr_first == tr_last && tr_first != staged && tr_first != nofit) {   // block-uniform: stage another row
-            __syncthreads();                     // every warp is done with the row the buffer holds
-            const int need = __ldg(&v.trace_meta[tr_first].T) + 1;
-            if (need <= smem_doubles) {
-                if (threadIdx.x == 0) {
-                    const uint32_t row_bytes = (uint32_t)((need + 1) / 2) * 16u;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(row_bytes) : "memory");
-                    bulk_g2s(s_row2, v.trace_cum + (size_t)tr_first * cum_stride(v.T_max), row_bytes, mbar);
-                }
-                if (!mbar_wait(mbar, parity) && threadIdx.x == 0) atomicAdd(v.errors, 1ull);
-                parity ^= 1u;
-                staged = tr_first;
-            } else {
-                nofit = tr_first;
+        if (tr_first == tr_last && tr_first != staged) {   // block-uniform: stage another trace's rows
+            __syncthreads();                     // every warp is done with the rows the buffer holds
+            if (threadIdx.x == 0) {
+                const int T0 = __ldg(&v.trace_meta[tr_first].T), M0 = __ldg(&v.trace_meta[tr_first].M);
+                const uint32_t rb = row_bytes_of(T0), ib = idx_bytes_of(M0);   // T0 <= T_max: both fit the buffer
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(rb + ib) : "memory");
+                bulk_g2s(s_row, v.trace_cum + (size_t)tr_first * cum_stride(v.T_max), rb, mbar);
+                bulk_g2s(s_idx, v.trace_idx + (size_t)tr_first * idx_stride(v.T_max), ib, mbar);
             }
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+            staged = tr_first;
         }
         if (valid) {
             if (tr == staged) {
-                s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row2);
+                s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row);
+                s.idx_s = (uint32_t)__cvta_generic_to_shared(s_idx);
                 step_session<true, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
             } else {
                 step_session<false, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
@@ -693,27 +663,33 @@ struct RolloutOut {
 // auto_reset on — compiled without the per-output null checks and the inert/history bookkeeping.
 // NOOUT (with FAST): no trajectory output at all (statistics / per-session accumulators only, e.g. abr_env_run_host).
 // LIVE (never with FAST): live-streaming semantics of SPEC §7.
+//
+// Software pipeline (policies whose action does not depend on the state: FIXED, RANDOM; not LIVE, whose pause gate
+// moves the position before every download): iteration t holds the finished head of step t and issues the head of
+// step t+1 from `head(t).target + size(t+1)` before running the tail of step t, so the index / C loads of the next
+// step overlap the division and the buffer / reward arithmetic of this one.  The assumption is that step t does not
+// sleep; when it does (its position moved in time) the head of step t+1 is redone from the moved position.
+// The action and table reads run two steps ahead for the same reason.
 template <int POLICY, bool SMEM, bool FAST, bool NOOUT, bool LIVE, typename OT>
 __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const int i, const uint32_t seed_lo,
-                                                const uint32_t seed_hi, const int steps,
+                                                const uint32_t seed_hi, const int steps, const uint32_t step_base,
                                                 const int32_t* __restrict__ actions_in, const RolloutOut<OT>& o,
                                                 double (&acc_new)[ABR_NUM_ACC], const bool fresh) {
+    constexpr bool AHEAD = POLICY != ABR_POLICY_BBA && !LIVE;
     const unsigned long long gsession = (unsigned long long)(v.session_base + i);
     double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_su = 0.0, a_lat = 0.0;
     int n_steps = 0, n_eps = 0;
     bool flagged = false, reset_mpc = false;
-    const int n = v.n;
+    const uint32_t n = (uint32_t)v.n;
     const bool hist = !FAST && v.p.track_history != 0;
     uint32_t packed = 0u;   // random policy: the four actions of one Philox block, one per byte
-    s.c_seg = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg);
-    s.c_seg1 = ld_cum<SMEM>(s, (SMEM ? s.cum_s : 0u) + 8u * (uint32_t)s.seg + 8u);
     if (LIVE) {
         if (fresh) { s.t_now = 0.0; s.play_time = 0.0; s.started = v.p.start_up_length <= 0.0; }
         else { s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0; }
         s.speed = 1.0;
     }
     // SPEC §4 action of step t; must be called with increasing t.  FIXED clamps t to the last row so that the
-    // one-step-ahead call after the final step stays inside the caller's table.
+    // calls that run ahead of the final step stay inside the caller's table.
     auto action_at = [&](const int t) -> int {
         if (POLICY == ABR_POLICY_FIXED) {
             int a = __ldg(actions_in + (size_t)(t < steps ? t : steps - 1) * n + i);
@@ -721,63 +697,120 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             return a;
         }
         if (POLICY == ABR_POLICY_RANDOM) {
-            if ((t & 3) == 0) {   // one Philox block per four steps (counter = (session, t / 4)), word t % 4
-                const uint4 r = philox4x32_10((uint32_t)gsession, (uint32_t)(gsession >> 32), (uint32_t)(t >> 2), 0u,
+            const uint32_t tg = step_base + (uint32_t)t;   // step index since the last reset (SPEC §4)
+            if ((tg & 3u) == 0u || t == 0) {   // one Philox block per four steps (counter = (session, step / 4)), word step % 4
+                const uint4 r = philox4x32_10((uint32_t)gsession, (uint32_t)(gsession >> 32), tg >> 2, 0u,
                                               seed_lo, seed_hi);
                 const uint32_t A = (uint32_t)v.A;   // <= 16: an action fits a byte
                 packed = __umulhi(r.x, A) | (__umulhi(r.y, A) << 8) | (__umulhi(r.z, A) << 16) | (__umulhi(r.w, A) << 24);
             }
-            return (int)((packed >> (8 * (t & 3))) & 0xffu);
+            return (int)((packed >> (8 * (tg & 3u))) & 0xffu);
         }
         return policy_bba(v, s.buffer);
     };
-    // the action and the table reads of the next step are issued at the end of a step (after its stores), so that
-    // they are in registers when the next step starts
-    int q = action_at(0);
-    Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);
-#pragma unroll 2   // two steps per trip: fewer loop-carried register moves (54.9 vs 55.8 us; unroll 4 spills and is slower)
-    for (int t = 0; t < steps; ++t) {
-        StepRes r;
-        const size_t ix = (size_t)t * n + i;
-        if (LIVE && o.speed) {
-            s.speed = __ldg(o.speed + ix);
-            if (!(s.speed > 0.0)) { flagged = true; s.speed = 1.0; }
-        }
-        step_core<SMEM, true, FAST, LIVE, SMEM>(v, s, q, lk, r, hist);   // shared-memory path searches on the keys
-        flagged |= r.walk_error;
-        if (NOOUT) {
-        } else if (FAST) {
-            __stcs(o.delay + ix, (OT)r.delay); __stcs(o.sleep + ix, (OT)r.sleep); __stcs(o.buffer + ix, (OT)r.buffer);
-            __stcs(o.rebuf + ix, (OT)r.rebuf); __stcs(o.reward + ix, (OT)r.reward);
-            o.eov[ix] = r.eov ? 1 : 0;
-        } else {
-            if (o.delay) __stcs(o.delay + ix, (OT)r.delay);
-            if (o.sleep) __stcs(o.sleep + ix, (OT)r.sleep);
-            if (o.buffer) __stcs(o.buffer + ix, (OT)r.buffer);
-            if (o.rebuf) __stcs(o.rebuf + ix, (OT)r.rebuf);
-            if (o.reward) __stcs(o.reward + ix, (OT)r.reward);
-            if (o.eov) o.eov[ix] = r.eov ? 1 : 0;
-            if (LIVE && o.latency) __stcs(o.latency + ix, (OT)r.latency);
-        }
-        if (FAST || !r.inert) {
-            a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
-            a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
-            if (LIVE) { a_su = dadd(a_su, r.startup); a_lat = dadd(a_lat, r.latency); }
-            n_steps += 1;
-            n_eps += r.eov ? 1 : 0;
-            if (hist) {
-                if (r.reset_mpc) reset_mpc = true;
-                else v.bw_hist[(size_t)((s.hist_len - 1) % v.K) * v.cap + i] = r.thr;
+    // chunk index / previous quality the step after (chunk, q) will see (SPEC §3.5), without running the step
+    auto next_chunk = [&](const int chunk) -> int {
+        const int c = chunk + 1;
+        return (c >= v.V && (FAST || v.p.auto_reset)) ? 0 : c;
+    };
+    auto next_last_q = [&](const int chunk, const int q) -> int {
+        return (chunk + 1 >= v.V && (FAST || v.p.auto_reset)) ? v.p.default_quality : q;
+    };
+    uint32_t ix = (uint32_t)i;   // element index of (step t, session i) in the [steps][N] outputs (< 2^32, checked by the host)
+    StepRes r;
+    LiveGate g;
+    g.buffer = 0.0; g.rebuf = g.idle = g.startup = 0.0;
+    if (AHEAD) {
+        int q0 = action_at(0);
+        Lookup lk0 = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q0, s.last_q);
+        int c1 = next_chunk(s.chunk);
+        int q1 = action_at(1);
+        Lookup lk1 = lookup_tables<SMEM>(s, v.A, v.V, c1, q1, next_last_q(s.chunk, q0));
+        Head h;
+        r.walk_error = false;
+        head<SMEM>(s, dadd(s.pos, lk0.size), h, r.walk_error);
+        for (int t = 0; t < steps; ++t) {
+            // head of step t+1, assuming that step t does not sleep
+            Head h1;
+            const bool ok1 = head_fast<SMEM>(s, dadd(h.target, lk1.size), h1);
+            // tail of step t
+            const bool moved = step_tail<SMEM, FAST, false>(v, s, h, q0, lk0, g, r, hist);
+            // action and table reads of step t+2
+            const int c2 = next_chunk(c1);
+            const int q2 = action_at(t + 2);
+            const Lookup lk2 = lookup_tables<SMEM>(s, v.A, v.V, c2, q2, next_last_q(c1, q1));
+            if (NOOUT) {
+            } else if (FAST) {
+                __stcs(o.delay + ix, (OT)r.delay); __stcs(o.sleep + ix, (OT)r.sleep); __stcs(o.buffer + ix, (OT)r.buffer);
+                __stcs(o.rebuf + ix, (OT)r.rebuf); __stcs(o.reward + ix, (OT)r.reward);
+                o.eov[ix] = r.eov ? 1 : 0;
+            } else {
+                if (o.delay) __stcs(o.delay + ix, (OT)r.delay);
+                if (o.sleep) __stcs(o.sleep + ix, (OT)r.sleep);
+                if (o.buffer) __stcs(o.buffer + ix, (OT)r.buffer);
+                if (o.rebuf) __stcs(o.rebuf + ix, (OT)r.rebuf);
+                if (o.reward) __stcs(o.reward + ix, (OT)r.reward);
+                if (o.eov) o.eov[ix] = r.eov ? 1 : 0;
+                if (o.actions) __stcs(o.actions + ix, q0);
             }
+            if (FAST || !r.inert) {
+                a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
+                a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
+                n_steps += 1;
+                n_eps += r.eov ? 1 : 0;
+                if (r.reset_mpc) reset_mpc = true;   // an auto-reset also clears the robust-MPC predictor state
+                else if (hist) v.bw_hist[(size_t)((s.hist_len - 1) % v.K) * v.cap + i] = r.thr;
+            }
+            flagged |= r.walk_error;
+            r.walk_error = false;
+            if (moved || !ok1) head_any<SMEM>(s, dadd(s.pos, lk1.size), h1, r.walk_error);   // s.pos: where step t left the session
+            h = h1;
+            q0 = q1; q1 = q2; lk0 = lk1; lk1 = lk2; c1 = c2;
+            ix += n;
         }
-        const int q_done = q;
-        q = action_at(t + 1);   // also after the last step (unused): no branch around the loads
-        lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);   // the state step t + 1 will see (SPEC §3.5)
-        if (!FAST && o.actions) __stcs(o.actions + ix, q_done);
+        flagged |= r.walk_error;
+    } else {
+        for (int t = 0; t < steps; ++t) {
+            const size_t ixw = (size_t)t * n + i;
+            if (LIVE && o.speed) {
+                s.speed = __ldg(o.speed + ixw);
+                if (!(s.speed > 0.0)) { flagged = true; s.speed = 1.0; }
+            }
+            const int q = action_at(t);
+            const Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);
+            step_core<SMEM, FAST, LIVE>(v, s, q, lk, r, hist);
+            flagged |= r.walk_error;
+            if (NOOUT) {
+            } else if (FAST) {
+                __stcs(o.delay + ix, (OT)r.delay); __stcs(o.sleep + ix, (OT)r.sleep); __stcs(o.buffer + ix, (OT)r.buffer);
+                __stcs(o.rebuf + ix, (OT)r.rebuf); __stcs(o.reward + ix, (OT)r.reward);
+                o.eov[ix] = r.eov ? 1 : 0;
+            } else {
+                if (o.delay) __stcs(o.delay + ix, (OT)r.delay);
+                if (o.sleep) __stcs(o.sleep + ix, (OT)r.sleep);
+                if (o.buffer) __stcs(o.buffer + ix, (OT)r.buffer);
+                if (o.rebuf) __stcs(o.rebuf + ix, (OT)r.rebuf);
+                if (o.reward) __stcs(o.reward + ix, (OT)r.reward);
+                if (o.eov) o.eov[ix] = r.eov ? 1 : 0;
+                if (LIVE && o.latency) __stcs(o.latency + ix, (OT)r.latency);
+                if (o.actions) __stcs(o.actions + ix, q);
+            }
+            if (FAST || !r.inert) {
+                a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
+                a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
+                if (LIVE) { a_su = dadd(a_su, r.startup); a_lat = dadd(a_lat, r.latency); }
+                n_steps += 1;
+                n_eps += r.eov ? 1 : 0;
+                if (r.reset_mpc) reset_mpc = true;   // an auto-reset also clears the robust-MPC predictor state
+                else if (hist) v.bw_hist[(size_t)((s.hist_len - 1) % v.K) * v.cap + i] = r.thr;
+            }
+            ix += n;
+        }
     }
     const double a_steps = (double)n_steps, a_eps = (double)n_eps;   // exact: counts below 2^31
     if (flagged) atomicAdd(v.errors, 1ull);
-    v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.buffer[i] = s.buffer;
+    v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.pos[i] = s.pos;
+    v.buffer[i] = s.buffer;
     if (LIVE) { v.t_now[i] = s.t_now; v.play_time[i] = s.play_time; v.started[i] = s.started ? 1 : 0; }
     if (hist) v.hist_len[i] = s.hist_len;
     if (reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
@@ -788,7 +821,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         if (FAST || !s.done) v.done[i] = 0;
         if (!LIVE) { v.t_now[i] = 0.0; v.play_time[i] = 0.0; v.started[i] = v.p.start_up_length <= 0.0 ? 1 : 0; }
     }
-    // accumulator read-modify-write: all eight loads first (one memory round trip instead of eight dependent ones)
+    // accumulator read-modify-write: all loads first (one memory round trip instead of ten dependent ones)
     double* a = v.acc + i;
     const size_t c = v.cap;
     const double add[ABR_NUM_ACC] = {a_rew, a_reb, a_u, a_sm, a_sl, a_dl, a_steps, a_eps, a_su, a_lat};
@@ -804,14 +837,15 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
                                                  acc_new[ABR_ACC_STARTUP], acc_new[ABR_ACC_LATENCY]);
 }
 
-// smem_doubles: capacity of the dynamic shared-memory row buffer (0 disables the shared-memory path); the buffer
-// is followed by the key row (key_stride(T_max) words, 16-byte aligned) and the sizes and utility tables.
+// smem_doubles: capacity of the dynamic shared-memory C-row buffer (0 disables the shared-memory path); the buffer
+// is followed by the index row (idx_stride(T_max) 16-bit words, 16-byte aligned) and the sizes and utility tables.
 // 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
-// co-resident (6.9 per SM); at 140 registers only 3 warps fit per scheduler and a second wave appears.
+// co-resident (6.9 per SM).
 template <int POLICY, bool FAST, bool NOOUT, bool LIVE, typename OT>
 __global__ void __launch_bounds__(kRolloutBlock, LIVE ? 6 : 8)
-abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, const int32_t* __restrict__ actions_in,
-                   RolloutOut<OT> o, int smem_doubles, double* __restrict__ block_partials) {
+abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uint32_t step_base,
+                   const int32_t* __restrict__ actions_in, RolloutOut<OT> o, int smem_doubles,
+                   double* __restrict__ block_partials) {
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_tr0;
@@ -844,21 +878,17 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
     if (threadIdx.x == 0) s_tr0 = tr;            // thread 0 of a launched block is always a valid session
     __syncthreads();
     const int tr0 = s_tr0;
-    // block-uniform: every session of this block follows trace tr0 and its C row (T + 1 entries) fits
-    const int need = __ldg(v.trace_len + tr0) + 1;   // <= cum_stride(T_max), so the copy stays in the row
-    const bool use_smem = __syncthreads_and((!valid || tr == tr0) ? 1 : 0) && need <= smem_doubles;
+    // block-uniform: every session of this block follows trace tr0 (whose rows fit: T <= T_max)
+    const bool use_smem = smem_doubles != 0 && __syncthreads_and((!valid || tr == tr0) ? 1 : 0);
     if (use_smem) {
-        // Stage the trace's C row and the chunk-size / utility tables with TMA bulk copies (cp.async.bulk, SASS UBLKCP):
-        // one elected thread issues four asynchronous global->shared copies that complete on an mbarrier, so the
-        // 29 KB arrive without occupying the LSU or registers while the other threads finish loading their state.
-        // Rows start 16-byte aligned (cum_stride is even) and all byte counts are multiples of 16.
+        // Stage the trace's C and index rows and the chunk-size / utility tables with TMA bulk copies (cp.async.bulk,
+        // SASS UBLKCP): one elected thread issues four asynchronous global->shared copies that complete on an
+        // mbarrier, so the 29 KB arrive without occupying the LSU or registers while the other threads finish loading
+        // their state.  Rows start 16-byte aligned and all byte counts are multiples of 16.
         double* s_row = reinterpret_cast<double*>(s_row2);
-        uint32_t* s_key = reinterpret_cast<uint32_t*>(s_row + smem_doubles);
-        double* s_sizes = reinterpret_cast<double*>(s_key + key_stride(v.T_max));
+        uint16_t* s_idx = reinterpret_cast<uint16_t*>(s_row + smem_doubles);
+        double* s_sizes = reinterpret_cast<double*>(s_idx + idx_stride(v.T_max));
         double* s_util = s_sizes + v.V * v.A;
-        const uint32_t key_bytes = (uint32_t)((need + 3) / 4) * 16u;
-        const double* g_row = v.trace_cum + (size_t)tr0 * cum_stride(v.T_max);
-        const uint32_t row_bytes = (uint32_t)((need + 1) / 2) * 16u;
         const uint32_t tab_bytes = (uint32_t)(v.V * v.A) * 8u;
         const bool tab_bulk = (tab_bytes & 15u) == 0;
         const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
@@ -868,10 +898,11 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t total = row_bytes + key_bytes + (tab_bulk ? 2u * tab_bytes : 0u);
+            const uint32_t rb = row_bytes_of(__ldg(&v.trace_meta[tr0].T)), ib = idx_bytes_of(__ldg(&v.trace_meta[tr0].M));
+            const uint32_t total = rb + ib + (tab_bulk ? 2u * tab_bytes : 0u);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
-            bulk_g2s(s_row, g_row, row_bytes, mbar);
-            bulk_g2s(s_key, v.trace_key + (size_t)tr0 * key_stride(v.T_max), key_bytes, mbar);
+            bulk_g2s(s_row, v.trace_cum + (size_t)tr0 * cum_stride(v.T_max), rb, mbar);
+            bulk_g2s(s_idx, v.trace_idx + (size_t)tr0 * idx_stride(v.T_max), ib, mbar);
             if (tab_bulk) {
                 bulk_g2s(s_sizes, v.sizes, tab_bytes, mbar);
                 bulk_g2s(s_util, v.util, tab_bytes, mbar);
@@ -883,20 +914,20 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, con
                 s_util[j] = __ldg(v.util + j);
             }
         }
-        if (!mbar_wait(mbar, 0u) && threadIdx.x == 0) atomicAdd(v.errors, 1ull);
+        mbar_wait(mbar, 0u);
         __syncthreads();
         if (valid) {
             s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row);
-            s.key_s = (uint32_t)__cvta_generic_to_shared(s_key);
+            s.idx_s = (uint32_t)__cvta_generic_to_shared(s_idx);
             s.sizes_s = (uint32_t)__cvta_generic_to_shared(s_sizes);
             s.util_s = (uint32_t)__cvta_generic_to_shared(s_util);
-            // keep the three addresses in registers: left alone, the compiler rematerialises them from
+            // keep the addresses in registers: left alone, the compiler rematerialises them from
             // SR_CgaCtaId (an S2R round trip) at every use inside the step loop
-            asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s), "+r"(s.key_s));
-            rollout_session<POLICY, true, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new, fresh);
+            asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s), "+r"(s.idx_s));
+            rollout_session<POLICY, true, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);
         }
     } else if (valid) {
-        rollout_session<POLICY, false, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, actions_in, o, acc_new, fresh);
+        rollout_session<POLICY, false, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);
     }
     // statistics stage 1 fused into the episode: per-block sums of the updated accumulators in a fixed order
     // (warp tree, then warps in ascending order), so abr_stats_partial only has to add the block partials
@@ -977,9 +1008,9 @@ abr_qoe_cost_kernel(EnvView v, double* __restrict__ out) {
 
 }  // namespace
 
-cudaError_t launch_trace_table(const EnvView& v, double* d_cum, uint32_t* d_key, int32_t* d_bits, TraceMeta* d_meta,
+cudaError_t launch_trace_table(const EnvView& v, double* d_cum, uint16_t* d_idx, int32_t* d_ok, TraceMeta* d_meta,
                                cudaStream_t st) {
-    abr_trace_table_kernel<<<(v.n_traces + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_cum, d_key, d_bits, d_meta);
+    abr_trace_table_kernel<<<(v.n_traces + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_cum, d_idx, d_ok, d_meta);
     count_launch();
     return cudaGetLastError();
 }
@@ -1021,10 +1052,10 @@ static cudaError_t launch_step_t(const EnvView& v, const int32_t* d_action, cons
     int tiles_per_block = (total_tiles + sm_count * kTileBlocksPerSM - 1) / (sm_count * kTileBlocksPerSM);
     if (tiles_per_block < kStepTiles) tiles_per_block = kStepTiles;
     const unsigned grid = (total_tiles + tiles_per_block - 1) / tiles_per_block;
-    // shared-memory row buffer for blocks whose sessions share a trace (3 blocks per SM up to 74 KB per block)
-    int smem_doubles = cum_stride(v.T_max);
-    size_t smem_bytes = (size_t)smem_doubles * sizeof(double);
-    if (smem_bytes > kSmemOptInLimit) { smem_doubles = 0; smem_bytes = 0; }
+    // shared-memory buffer (C row + index row) for blocks whose sessions share a trace
+    int smem_doubles = cum_smem_doubles(v.T_max);
+    size_t smem_bytes = (size_t)smem_doubles * sizeof(double) + (size_t)idx_stride(v.T_max) * sizeof(uint16_t);
+    if (smem_bytes > kSmemOptInLimit || idx_stride(v.T_max) == 0) { smem_doubles = 0; smem_bytes = 0; }
     cudaError_t e = cudaSuccess;
 #define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr, smem_doubles, tiles_per_block
 #define ABR_LAUNCH_STEP(F, L)                                                                  \
@@ -1062,20 +1093,20 @@ static cudaError_t launch_rollout_t(const EnvView& v, int policy, uint64_t seed,
                                     const int32_t* d_actions_in, const double* d_speed, OT* d_delay, OT* d_sleep,
                                     OT* d_buffer, OT* d_rebuf, OT* d_reward, OT* d_latency, uint8_t* d_eov,
                                     int32_t* d_actions_out, double* d_block_partials, const RolloutFused& f,
-                                    cudaStream_t st) {
+                                    uint32_t step_base, cudaStream_t st) {
     if (v.n == 0 || steps <= 0) return cudaSuccess;
     const dim3 grid((v.n + kRolloutBlock - 1) / kRolloutBlock), block(kRolloutBlock);
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
     RolloutOut<OT> o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out, d_latency, d_speed,
                      f.in_trace_id, f.in_offset, f.out_cost};
     const bool live = v.p.live != 0;
-    // shared-memory row buffer: the longest C row when it leaves room for >= 7 blocks per SM, else disabled
-    int smem_doubles = cum_stride(v.T_max);
+    // shared-memory buffer: the longest C row, the longest index row and the two tables
+    int smem_doubles = cum_smem_doubles(v.T_max);
     size_t smem_bytes = ((size_t)smem_doubles + 2 * (size_t)v.V * v.A) * sizeof(double) +
-                        (size_t)key_stride(v.T_max) * sizeof(uint32_t);
+                        (size_t)idx_stride(v.T_max) * sizeof(uint16_t);
     // <= 31 KB keeps 7 blocks per SM resident (the 65 536-session shape is then one wave); longer traces opt in to
     // more shared memory and run with fewer blocks per SM, which still beats scattered global probes
-    if (smem_bytes > kSmemOptInLimit) { smem_doubles = 0; smem_bytes = 0; }
+    if (smem_bytes > kSmemOptInLimit || idx_stride(v.T_max) == 0) { smem_doubles = 0; smem_bytes = 0; }
     const bool fast = !live && d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov && !d_actions_out &&
                       v.p.track_history == 0 && v.p.auto_reset != 0;
     const bool none = !live && !d_delay && !d_sleep && !d_buffer && !d_rebuf && !d_reward && !d_eov && !d_actions_out &&
@@ -1085,8 +1116,9 @@ static cudaError_t launch_rollout_t(const EnvView& v, int policy, uint64_t seed,
     do {                                                                                                           \
         e = allow_smem(abr_rollout_kernel<P, F, N, L, OT>, smem_bytes);                                            \
         if (e == cudaSuccess)                                                                                      \
-            abr_rollout_kernel<P, F, N, L, OT><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, d_actions_in, o,  \
-                                                                                smem_doubles, d_block_partials);   \
+            abr_rollout_kernel<P, F, N, L, OT><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, step_base,        \
+                                                                                d_actions_in, o, smem_doubles,     \
+                                                                                d_block_partials);                 \
     } while (0)
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
     do {                                                                                                           \
@@ -1111,17 +1143,17 @@ static cudaError_t launch_rollout_t(const EnvView& v, int policy, uint64_t seed,
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf,
                            double* d_reward, double* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
-                           double* d_block_partials, cudaStream_t st, const RolloutFused& f) {
+                           double* d_block_partials, cudaStream_t st, const RolloutFused& f, uint32_t step_base) {
     return launch_rollout_t<double>(v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
-                                    d_reward, d_latency, d_eov, d_actions_out, d_block_partials, f, st);
+                                    d_reward, d_latency, d_eov, d_actions_out, d_block_partials, f, step_base, st);
 }
 
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            const double* d_speed, float* d_delay, float* d_sleep, float* d_buffer, float* d_rebuf,
                            float* d_reward, float* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
-                           double* d_block_partials, cudaStream_t st) {
+                           double* d_block_partials, cudaStream_t st, uint32_t step_base) {
     return launch_rollout_t<float>(v, policy, seed, steps, d_actions_in, d_speed, d_delay, d_sleep, d_buffer, d_rebuf,
-                                   d_reward, d_latency, d_eov, d_actions_out, d_block_partials, RolloutFused{}, st);
+                                   d_reward, d_latency, d_eov, d_actions_out, d_block_partials, RolloutFused{}, step_base, st);
 }
 
 int stats_num_partials(int n) { return n <= 0 ? 1 : (n + kStatsSessionsPerBlock - 1) / kStatsSessionsPerBlock; }

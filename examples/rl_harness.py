@@ -83,7 +83,7 @@ class GraphedEpisode:
     def _capture(self):
         env = self.env
         # warm up the allocator and cuBLAS on a side stream, restore the state, then capture (capture runs nothing)
-        snap = {f: env.state(f).clone() for f in ("seg", "chunk", "last_q", "phase", "buffer")}
+        snap = {f: env.state(f).clone() for f in ("seg", "chunk", "last_q", "phase", "pos", "buffer")}
         side = torch.cuda.Stream(device=env.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ABR_VERSION 100
+#define ABR_VERSION 200
 
 enum { ABR_OK = 0, ABR_ERR_INVALID = 1, ABR_ERR_CUDA = 2, ABR_ERR_RANGE = 3, ABR_ERR_STATE = 4 };
 
@@ -47,7 +47,7 @@ enum { ABR_ACC_REWARD = 0, ABR_ACC_REBUF = 1, ABR_ACC_UTILITY = 2, ABR_ACC_SMOOT
 /* session-state fields exposed by abr_env_state_ptr (SPEC §1).  All arrays have max_sessions elements except
  * BW_HIST / ERR_RING ([hist_k][max_sessions]) and ACC ([ABR_NUM_ACC][max_sessions]). */
 enum { ABR_F_SEG = 0, ABR_F_CHUNK = 1, ABR_F_LAST_Q = 2, ABR_F_TRACE_ID = 3, ABR_F_HIST_LEN = 4, ABR_F_DONE = 5,
-       ABR_F_ERR_LEN = 6, ABR_F_PHASE = 10, ABR_F_BUFFER = 11, ABR_F_BW_HIST = 12, ABR_F_LAST_PRED = 13,
+       ABR_F_ERR_LEN = 6, ABR_F_PHASE = 10, ABR_F_POS = 18, ABR_F_BUFFER = 11, ABR_F_BW_HIST = 12, ABR_F_LAST_PRED = 13,
        ABR_F_ERR_RING = 14, ABR_F_ACC = 15, ABR_F_T_NOW = 16, ABR_F_PLAY_TIME = 17, ABR_F_STARTED = 7, ABR_F_SIZES = 20, ABR_F_UTILITY = 21, ABR_F_TRACE_BW = 22 };
 
 /* Replaces the attribute bags MPD / QOEMetric (Simulator.py:11-24, mpc_test.py:18-29) plus the

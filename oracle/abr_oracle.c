@@ -20,10 +20,11 @@ struct OrcEnv {
     int32_t* trace_len;
     /* session state, SoA (SPEC §1) */
     int32_t *seg, *chunk, *last_q, *trace_id, *hist_len, *err_len;
-    double *phi /* fraction of segment seg consumed */, *buffer, *bw_hist /* [N][K] ring */, *last_pred, *err_ring /* [N][K] */;
+    double *phi /* fraction of segment seg consumed */, *pos /* the same position in data coordinates, SPEC 3.1 */, *buffer, *bw_hist /* [N][K] ring */, *last_pred, *err_ring /* [N][K] */;
     double *t_now, *play_time;   /* live mode, SPEC §7 */
     uint8_t *done, *started;
     int errors;
+    uint32_t step_base;   /* fused-episode steps since the last reset (SPEC §4: step_index of the random policy) */
 };
 
 static inline double max0(double x) { return x > 0.0 ? x : 0.0; } /* Python max(0, x), mpc.py:107 */
@@ -84,7 +85,7 @@ OrcEnv* orc_env_create(const double* trace_bw, const int32_t* trace_len, const d
     }
     e->seg = (int32_t*)calloc(N, 4); e->chunk = (int32_t*)calloc(N, 4); e->last_q = (int32_t*)calloc(N, 4);
     e->trace_id = (int32_t*)calloc(N, 4); e->hist_len = (int32_t*)calloc(N, 4); e->err_len = (int32_t*)calloc(N, 4);
-    e->phi = (double*)calloc(N, 8); e->buffer = (double*)calloc(N, 8); e->last_pred = (double*)calloc(N, 8);
+    e->phi = (double*)calloc(N, 8); e->pos = (double*)calloc(N, 8); e->buffer = (double*)calloc(N, 8); e->last_pred = (double*)calloc(N, 8);
     e->bw_hist = (double*)calloc((size_t)N * e->K, 8); e->err_ring = (double*)calloc((size_t)N * e->K, 8);
     e->done = (uint8_t*)calloc(N, 1);
     e->started = (uint8_t*)calloc(N, 1);
@@ -97,7 +98,7 @@ void orc_env_destroy(OrcEnv* e) {
     free(e->cum);
     free(e->trace_bw); free(e->trace_len); free(e->trace_interval); free(e->sizes); free(e->bitrates); free(e->util);
     free(e->seg); free(e->chunk); free(e->last_q); free(e->trace_id); free(e->hist_len); free(e->err_len);
-    free(e->phi); free(e->buffer); free(e->last_pred); free(e->bw_hist); free(e->err_ring); free(e->done);
+    free(e->phi); free(e->pos); free(e->buffer); free(e->last_pred); free(e->bw_hist); free(e->err_ring); free(e->done);
     free(e->started); free(e->t_now); free(e->play_time);
     free(e);
 }
@@ -108,7 +109,7 @@ const void* orc_env_field(OrcEnv* e, int f) {
         case 4: return e->hist_len; case 5: return e->done; case 6: return e->err_len;
         case 10: return e->phi; case 11: return e->buffer; case 12: return e->bw_hist; case 13: return e->last_pred;
         case 14: return e->err_ring; case 15: return e->util; case 16: return e->t_now; case 17: return e->play_time;
-        case 7: return e->started;
+        case 7: return e->started; case 18: return e->pos;
     }
     return 0;
 }
@@ -116,6 +117,7 @@ int orc_env_error_count(OrcEnv* e) { return e->errors; }
 
 /* SPEC §2 */
 void orc_env_reset(OrcEnv* e, const int32_t* trace_id, const double* start_offset) {
+    e->step_base = 0;
     for (int s = 0; s < e->N; ++s) {
         int tr = trace_id[s];
         int T = e->trace_len[tr];
@@ -125,7 +127,9 @@ void orc_env_reset(OrcEnv* e, const int32_t* trace_id, const double* start_offse
         double n = floor(x);
         int seg = (int)fmod(n, (double)T);
         double phi = x - n;
+        const double* C = e->cum + (size_t)tr * (e->T_max + 1);
         e->trace_id[s] = tr; e->seg[s] = seg; e->phi[s] = phi;
+        e->pos[s] = C[seg] + (C[seg + 1] - C[seg]) * phi;
         e->buffer[s] = 0.0; e->chunk[s] = 0; e->last_q[s] = e->p.default_quality; e->done[s] = 0;
         e->hist_len[s] = 0; e->last_pred[s] = 0.0; e->err_len[s] = 0;
         e->t_now[s] = 0.0; e->play_time[s] = 0.0; e->started[s] = e->p.start_up_length <= 0.0;
@@ -161,8 +165,9 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     const int T = e->trace_len[tr];
     const double I = e->trace_interval[tr];
     int chunk = e->chunk[s], seg = e->seg[s];
-    double phi = e->phi[s], buffer = e->buffer[s];
+    double phi = e->phi[s], pos = e->pos[s], buffer = e->buffer[s];
     const double size = e->sizes[chunk * e->A + q];
+    const double* C = e->cum + (size_t)tr * (e->T_max + 1);
     const int live = p->live != 0;
     double idle = 0.0, rebuf = 0.0, startup = 0.0, latency = 0.0;
     if (live) {   /* 7.1 pause gate */
@@ -172,14 +177,12 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
         double w2 = (e->started[s] && buffer > p->max_buffer) ? (buffer - p->max_buffer) / v : 0.0;
         rebuf = rebuf + play(e, s, w2, v, &buffer, &startup);
         idle = w1 + w2;
-        if (idle > 0.0) advance_trace(&seg, &phi, idle, I, T);
+        if (idle > 0.0) { advance_trace(&seg, &phi, idle, I, T); pos = C[seg] + (C[seg + 1] - C[seg]) * phi; }
     }
     /* 3.1 download against the cumulative capacity of the trace */
-    const double* C = e->cum + (size_t)tr * (e->T_max + 1);
     const double P = C[T];
     double delay;
     {
-        double pos = C[seg] + (C[seg + 1] - C[seg]) * phi;
         double target = pos + size;
         long long n = 0;               /* whole trace periods */
         while (target >= P) {
@@ -187,7 +190,7 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
             n += 1;
             if (n >= (1 << 20)) { e->errors++; target = 0.0; break; }   /* safety net only: P > 0 */
         }
-        /* the largest j in [0, T) with C[j] <= target; C is non-decreasing and, without a wrap,
+        /* the largest j in [0, T) with C[j] <= target; C is increasing and, without a wrap,
          * C[seg] <= pos <= target, so the scan may start at seg */
         int j = (n == 0) ? seg : 0;
         while (j + 1 < T && C[j + 1] <= target) ++j;
@@ -196,6 +199,7 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
         delay = max0(((double)k + (phi_new - phi)) * I) + p->rtt;
         seg = j;
         phi = phi_new;
+        pos = target;
     }
     double thr = size / delay;
     double sleep = 0.0;
@@ -215,6 +219,7 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
             sleep = ceil((buffer - p->max_buffer) / p->sleep_quantum) * p->sleep_quantum;
             buffer = buffer - sleep;
             advance_trace(&seg, &phi, sleep, I, T);
+            pos = C[seg] + (C[seg + 1] - C[seg]) * phi;
         }
     }
     /* 3.4 */
@@ -241,7 +246,7 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     } else if (o->eov) {
         e->done[s] = 1;
     }
-    e->chunk[s] = chunk; e->seg[s] = seg; e->phi[s] = phi; e->buffer[s] = buffer;
+    e->chunk[s] = chunk; e->seg[s] = seg; e->phi[s] = phi; e->pos[s] = pos; e->buffer[s] = buffer;
 }
 
 void orc_env_step_live(OrcEnv* e, const int32_t* action, const double* speed, double* delay, double* sleep,
@@ -285,9 +290,10 @@ static int policy_action(OrcEnv* e, int s, int policy, uint64_t seed, int64_t se
         uint64_t g = (uint64_t)(session_base + s);
         uint32_t r[4];
         /* one Philox block per four steps: counter (session, step / 4), word step % 4 */
-        orc_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(step >> 2), 0u, (uint32_t)seed,
+        const uint32_t tg = e->step_base + (uint32_t)step;   /* step index since the last reset */
+        orc_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), tg >> 2, 0u, (uint32_t)seed,
                           (uint32_t)(seed >> 32), r);
-        return (int)(((uint64_t)r[step & 3] * (uint64_t)A) >> 32);
+        return (int)(((uint64_t)r[tg & 3] * (uint64_t)A) >> 32);
     }
     /* BBA */
     double b = e->buffer[s];
@@ -331,6 +337,7 @@ void orc_env_rollout_live(OrcEnv* e, int policy, uint64_t seed, int64_t session_
             acc[8 * (size_t)N + s] = a_su; acc[9 * (size_t)N + s] = a_lat;   /* 0 outside live mode */
         }
     }
+    e->step_base += (uint32_t)(steps > 0 ? steps : 0);
 }
 
 void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,

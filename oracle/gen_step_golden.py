@@ -65,7 +65,7 @@ def run_case(name, params, seed, n_sessions=20, steps=25, speeds=None):
             out[k].append(row[k])
         out["eov"].append(eov)
     final = dict(seg=[s.seg for s in sessions], phase=[float(s.phi).hex() for s in sessions],
-                 buffer=[float(s.buffer).hex() for s in sessions], chunk=[s.chunk for s in sessions])
+                 pos=[float(s.pos).hex() for s in sessions], buffer=[float(s.buffer).hex() for s in sessions], chunk=[s.chunk for s in sessions])
     return dict(name=name, params=params, seed=seed, trace_id=tid.tolist(), start_offset=[float(x).hex() for x in off],
                 actions=actions.tolist(), speeds=speeds, outputs=out, final=final)
 

@@ -168,7 +168,7 @@ class OracleEnv:
                    hist_len=(4, np.int32, 1), done=(5, np.uint8, 1), err_len=(6, np.int32, 1), phase=(10, np.float64, 1),
                    buffer=(11, np.float64, 1), bw_hist=(12, np.float64, self.K), last_pred=(13, np.float64, 1),
                    err_ring=(14, np.float64, self.K), t_now=(16, np.float64, 1), play_time=(17, np.float64, 1),
-                   started=(7, np.uint8, 1))
+                   started=(7, np.uint8, 1), pos=(18, np.float64, 1))
         fid, dt, w = ids[name]
         ptr = lib().orc_env_field(self._h, C.c_int(fid))
         n = self.N * w

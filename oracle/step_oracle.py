@@ -37,6 +37,7 @@ class Session:
         n = math.floor(x)
         self.seg = int(math.fmod(n, self.T))
         self.phi = x - n                      # fraction of segment seg already consumed (SPEC §1)
+        self.pos = self._position()           # the same position in data coordinates (SPEC §3.1)
         self.buffer = 0.0
         self.chunk = 0
         self.last_q = P["default_quality"]
@@ -61,11 +62,16 @@ class Session:
         self.play_time = self.play_time + drained
         return stall
 
+    def _position(self):
+        C = self.C
+        return C[self.seg] + (C[self.seg + 1] - C[self.seg]) * self.phi
+
     def _advance(self, dt):
         x = self.phi + dt / self.I
         n = math.floor(x)
         self.phi = x - n
         self.seg = (self.seg + n) % self.T
+        self.pos = self._position()
 
     def _download_segments(self, size):
         """Segment-by-segment integration from the current position (not the SPEC's arithmetic: cross-check only)."""
@@ -111,19 +117,19 @@ class Session:
             delay = self._download_segments(size) + P["rtt"]
         else:                                        # SPEC 3.1 (Simulator.py:158-163 in closed form)
             C, T = self.C, self.T
-            target = (C[self.seg] + (C[self.seg + 1] - C[self.seg]) * self.phi) + size
+            target = self.pos + size
             n = 0
             while target >= C[T]:
                 target = target - C[T]
                 n += 1
-            j = self.seg if n == 0 else 0
+            j = self.seg if n == 0 else 0          # C[seg] <= pos <= target without a wrap
             while j + 1 < T and C[j + 1] <= target:
                 j += 1
             phi_new = (target - C[j]) / (C[j + 1] - C[j])
             k = (j - self.seg) + n * T
             dl = (float(k) + (phi_new - self.phi)) * self.I
             delay = (dl if dl > 0 else 0.0) + P["rtt"]
-            self.seg, self.phi = j, phi_new
+            self.seg, self.phi, self.pos = j, phi_new, target
         thr = size / delay
         latency = 0.0
         if live:                                                              # SPEC 7.2

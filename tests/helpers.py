@@ -51,5 +51,6 @@ def load_step_golden():
                           outputs={k: unhex(c["outputs"][k]) for k in KEYS}, eov=np.array(c["outputs"]["eov"], np.uint8),
                           final=dict(seg=np.array(c["final"]["seg"], np.int32), chunk=np.array(c["final"]["chunk"], np.int32),
                                      phase=np.array([float.fromhex(x) for x in c["final"]["phase"]]),
+                                     pos=np.array([float.fromhex(x) for x in c["final"]["pos"]]),
                                      buffer=np.array([float.fromhex(x) for x in c["final"]["buffer"]]))))
     return cases

@@ -21,7 +21,7 @@ from oracle import oracle as orc
 from helpers import small_world, assert_close, bits_equal, load_step_golden
 
 STATE_I = ("seg", "chunk", "last_q", "trace_id")
-STATE_F = ("phase", "buffer")
+STATE_F = ("phase", "pos", "buffer")
 
 
 def make_pair(N, params=None, **world):
@@ -726,6 +726,7 @@ def test_kernels_reproduce_the_step_spec_fixture(case):
         assert np.array_equal(got.end_of_video.cpu().numpy(), case["eov"][t])
     assert np.array_equal(env.state("seg").cpu().numpy(), case["final"]["seg"])
     assert bits_equal(env.state("phase").cpu().numpy(), case["final"]["phase"]) == 0
+    assert bits_equal(env.state("pos").cpu().numpy(), case["final"]["pos"]) == 0
     if not live:
         env.reset(case["trace_id"], case["start_offset"])
         tr = env.rollout("fixed", len(case["actions"]), actions=case["actions"])
@@ -897,7 +898,7 @@ def test_run_host_zero_copy_equals_staged_copies():
     np.testing.assert_allclose(none_off["stats"], orc.stats_from_acc(exp["acc"]), rtol=1e-9)
 
 
-ALL_FIELDS = ("seg", "chunk", "last_q", "trace_id", "hist_len", "done", "err_len", "phase", "buffer", "last_pred",
+ALL_FIELDS = ("seg", "chunk", "last_q", "trace_id", "hist_len", "done", "err_len", "phase", "pos", "buffer", "last_pred",
               "t_now", "play_time", "started")
 
 

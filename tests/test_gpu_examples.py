@@ -62,7 +62,7 @@ def test_rl_harness_cuda_graph_replay_equals_eager():
     policy = Policy(4 + env.A, env.A).cuda()
     env.reset(tid, off)
     eager = run_episode(env, policy, V, sample=False).cpu().numpy()
-    state_eager = {f: env.state(f).cpu().numpy().copy() for f in ("seg", "chunk", "phase", "buffer")}
+    state_eager = {f: env.state(f).cpu().numpy().copy() for f in ("seg", "chunk", "phase", "pos", "buffer")}
     env.reset(tid, off)
     graphed = run_episode(env, policy, V, sample=False, use_graph=True).cpu().numpy()
     assert np.array_equal(eager, graphed)

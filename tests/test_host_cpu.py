@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.abr_version() == 100
+    assert lib.abr_version() == 200
     p = _lib.default_params(chunk_length=2.0)
     assert p.chunk_length == 2.0 and p.max_buffer == 60.0 and p.hist_k == 5 and p.rebuf_penalty == 4.3
     assert ctypes.sizeof(_lib.AbrParams) == 13 * 8 + 8 * 4

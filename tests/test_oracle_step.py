@@ -40,6 +40,7 @@ def test_c_step_equals_python_step(ragged):
             assert c["eov"][s] == r["eov"]
     assert np.array_equal(env.field("seg"), [p.seg for p in py])
     assert bits_equal(env.field("phase"), np.array([p.phi for p in py])) == 0
+    assert bits_equal(env.field("pos"), np.array([p.pos for p in py])) == 0
     assert np.array_equal(env.field("chunk"), [p.chunk for p in py])
 
 
@@ -230,6 +231,7 @@ def test_c_oracle_reproduces_the_step_spec_fixture(case):
         assert np.array_equal(out["eov"], case["eov"][t])
     assert np.array_equal(env.field("seg"), case["final"]["seg"])
     assert bits_equal(env.field("phase"), case["final"]["phase"]) == 0
+    assert bits_equal(env.field("pos"), case["final"]["pos"]) == 0
     assert bits_equal(env.field("buffer"), case["final"]["buffer"]) == 0
 
 
