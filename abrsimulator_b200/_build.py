@@ -13,13 +13,15 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "lib", "libabr_b200.so")
+# development only: ABR_LIB_SUFFIX=_x builds/loads lib/libabr_b200_x.so with ABR_EXTRA_NVCC_FLAGS (A/B kernel variants)
+_SUFFIX = os.environ.get("ABR_LIB_SUFFIX", "")
+LIB = os.path.join(HERE, "lib", f"libabr_b200{_SUFFIX}.so")
 STAMP = LIB + ".srchash"
 SOURCES = ["abr_step.cu", "abr_mpc.cu", "abr_capi.cu"]
 HEADERS = [os.path.join(CSRC, "abr_common.cuh"), os.path.join(HERE, "..", "include", "abr_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"] + os.environ.get("ABR_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc():
@@ -59,7 +61,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     # one nvcc per source, in parallel (abr_step.cu alone holds ~50 kernel instantiations), then one link
     from concurrent.futures import ThreadPoolExecutor
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
-    obj_dir = os.path.join(os.path.dirname(LIB), "obj")
+    obj_dir = os.path.join(os.path.dirname(LIB), "obj" + _SUFFIX)
     os.makedirs(obj_dir, exist_ok=True)
 
     def compile_one(src):

@@ -186,8 +186,16 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     CUDA_TRY(cudaMemcpy(d_sizes, h_sizes, sizeof(double) * V * A, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice));
     v.trace_bw = d_bw; v.trace_len = d_len; v.trace_interval = d_int; v.sizes = d_sizes; v.util = d_util;
+    {   // packed {size, utility} table for the step kernels
+        std::vector<double> tab(2 * (size_t)V * A);
+        for (size_t i = 0; i < (size_t)V * A; ++i) { tab[2 * i] = h_sizes[i]; tab[2 * i + 1] = util[i]; }
+        double* d_tab;
+        CUDA_TRY(e->alloc(&d_tab, tab.size()));
+        CUDA_TRY(cudaMemcpy(d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+        v.tab = reinterpret_cast<const double2*>(d_tab);
+    }
     // per-trace tables of SPEC §3.1 (cumulative capacity, search widths), built on the device
-    // (+4 doubles of slack: the step reads C[j .. j+3] and discards what lies past its candidates)
+    // (+4 doubles of slack: the step reads C[j .. j+4] and discards what lies past its candidates)
     double* d_cum;
     int32_t* d_ok;
     CUDA_TRY(e->alloc(&d_cum, (size_t)n_traces * cum_stride(T_max) + 4));

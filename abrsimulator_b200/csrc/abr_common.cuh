@@ -90,6 +90,7 @@ struct EnvView {
     const double* __restrict__ trace_interval;  // [n_traces]
     const double* __restrict__ sizes;           // [V][A]
     const double* __restrict__ util;            // [V][A]
+    const double2* __restrict__ tab;            // [V][A] {size, utility}: one 16-byte read per step instead of two
     // SoA session state, capacity = cap
     int32_t* seg; int32_t* chunk; int32_t* last_q; int32_t* trace_id; int32_t* hist_len; int32_t* err_len;
     uint8_t* done; uint8_t* started;

@@ -43,16 +43,20 @@ constexpr int kRolloutBlock = 64;   // 65 536 sessions -> 1 024 blocks = 6.9 per
 constexpr int kStatsBlock = 256;
 constexpr int kStatsSessionsPerBlock = 1024;   // 64 blocks at 65 536 sessions: enough loads in flight to hide HBM latency
 constexpr int kWrapGuard = 1 << 20;            // safety net of the whole-period loop (SPEC §3.1)
+#ifndef ABR_ROLLOUT_UNROLL
+#define ABR_ROLLOUT_UNROLL 1   // A/B-tested on B200: 1 and 2 are within 0.3 % of each other; 1 is half the code and spills nothing
+#endif
+constexpr int kRolloutUnroll = ABR_ROLLOUT_UNROLL;   // steps per trip of the fused episode's loop
 
 struct Sess {
     const double* __restrict__ cum;    // C[0..T] of the session's trace (global row)
     const uint16_t* __restrict__ idx;  // bucket index of the session's trace (global row)
-    uint32_t cum_s, idx_s, sizes_s, util_s;  // shared-memory addresses of the block's copies (SMEM path)
-    const double* __restrict__ sizes;  // [V][A] chunk sizes and utilities (global tables)
-    const double* __restrict__ util;
+    uint32_t cum_s, idx_s, tab_s;      // shared-memory addresses of the block's copies (SMEM path)
+    const double2* __restrict__ tab;   // [V][A] {chunk size, utility} (global table)
     double I, phi, buffer;             // phi = fraction of segment `seg` already consumed (SPEC §1)
     double pos;                        // the same position in data coordinates: C[seg] + (C[seg+1] - C[seg]) * phi
     double P, scale;                   // C[T]: capacity of one trace period; cells per unit of data
+    double Td;                         // (double)T
     int T, M, seg, chunk, last_q, hist_len;
     bool done;
     // live mode (SPEC §7)
@@ -77,6 +81,30 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return x;
 }
 
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 x;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x.x), "=d"(x.y) : "r"(addr));
+    return x;
+}
+
+// Cell of a data position in the bucket index: x * scale rounded to the nearest integer, clamped to M - 1.  The
+// rounding goes through the 2^52 trick (the low word of x*scale + 1.5*2^52 is the integer for 0 <= x*scale < 2^31):
+// one FP64 add (8 cycles) instead of a conversion instruction on the slow XU pipe.  Non-decreasing in x, which is all
+// the index needs (abr_common.cuh); the table is built with this same function.
+__device__ __forceinline__ uint32_t cell_of(const double x, const double scale, const int M) {
+    const double y = dadd(dmul(x, scale), 6755399441055744.0);
+    return min((uint32_t)__double2loint(y), (uint32_t)(M - 1));
+}
+
+// (double)i for |i| < 2^31, exact, without the XU conversion: 2^52 + 2^31 + i has i + 2^31 in its low word.
+__device__ __forceinline__ double int2double(const int i) {
+    return dsub(__hiloint2double(0x43300000, (int)((uint32_t)i ^ 0x80000000u)), 4503601774854144.0);
+}
+
+// max(x, 0) = (x + |x|) / 2 on the FP64 pipe: exact (x + x and the halving never round; x - x = +0), two dependent
+// FP64 operations (16 cycles) where the sign-mask form of abr_common.cuh takes three on the busier integer pipe.
+__device__ __forceinline__ double max0d(double x) { return dmul(dadd(x, fabs(x)), 0.5); }
+
 // C[j] / idx[b] of the session's trace: an LDS on the shared-memory path, else a read-only global load.
 template <bool SMEM>
 __device__ __forceinline__ double ld_c(const Sess& s, const int j) {
@@ -97,10 +125,12 @@ __device__ __forceinline__ Lookup lookup_tables(const Sess& s, const int A, cons
                                                 const int last_q) {
     const int row = (chunk < V ? chunk : 0) * A;   // an inert session (chunk == V) reads row 0 and ignores it
     Lookup k;
-    k.size = SMEM ? lds_f64(s.sizes_s + 8u * (uint32_t)(row + q)) : __ldg(s.sizes + row + q);
-    k.u = SMEM ? lds_f64(s.util_s + 8u * (uint32_t)(row + q)) : __ldg(s.util + row + q);
-    k.u_prev = last_q >= 0 ? (SMEM ? lds_f64(s.util_s + 8u * (uint32_t)(row + last_q)) : __ldg(s.util + row + last_q))
-                           : k.u;
+    const double2 su = SMEM ? lds_f64x2(s.tab_s + 16u * (uint32_t)(row + q)) : __ldg(s.tab + row + q);
+    k.size = su.x;
+    k.u = su.y;
+    // no previous chunk (last_q < 0): the smoothness term |u - u_prev| is 0
+    const int lq = last_q >= 0 ? last_q : q;
+    k.u_prev = SMEM ? lds_f64(s.tab_s + 16u * (uint32_t)(row + lq) + 8u) : __ldg(&s.tab[row + lq].y);
     return k;
 }
 
@@ -140,31 +170,46 @@ __device__ __forceinline__ double live_play(Sess& s, double& buffer, double& sta
 }
 
 // ---- head of a step (SPEC §3.1): where does the download end? ----
-// target is the wrapped data position in [0, P), n the whole trace periods it went through, j the segment with
-// C[j] <= target < C[j+1], c_j / c_j1 those two entries.
-struct Head { double target, c_j, c_j1; int j, n; };
+// target is the wrapped data position in [0, P), kx = n*T as a double (n = whole trace periods the download went
+// through), j the segment with C[j] <= target < C[j+1], c_j / c_j1 those two entries.
+struct Head { double target, c_j, c_j1, kx; int j; };
 
-// Common case as one branch-free sequence: no wrap (raw < P), an index exists and the target's cell holds at most
-// two segment boundaries.  Returns false otherwise (the caller then runs head_any); the loads are in range either way.
+// Common case as one branch-free sequence: at most one wrap, and the target's cell holds at most three segment
+// boundaries.  Returns false otherwise (the caller then runs head_any); the loads are in range either way.
+// Needs an index (s.M > 0).  Three dependent rounds of loads: the index pair, the candidate boundaries, C[j] / C[j+1].
 template <bool SMEM>
 __device__ __forceinline__ bool head_fast(const Sess& s, const double raw, Head& h) {
-    const int Mc = s.M > 0 ? s.M - 1 : 0;
-    int b = __double2int_rz(dmul(raw, s.scale));
-    b = min(max(b, 0), Mc);
-    const int j0 = s.M > 0 ? ld_idx<SMEM>(s, b) : 0;
-    const int cnt = s.M > 0 ? ld_idx<SMEM>(s, b + 1) - j0 : 3;
-    const double c0 = ld_c<SMEM>(s, j0), c1 = ld_c<SMEM>(s, j0 + 1), c2 = ld_c<SMEM>(s, j0 + 2), c3 = ld_c<SMEM>(s, j0 + 3);
-    const bool m1 = cnt >= 1 && c1 <= raw;     // the boundaries are increasing: m2 implies m1
-    const bool m2 = cnt >= 2 && c2 <= raw;
-    h.target = raw;
-    h.n = 0;
-    h.j = j0 + (m1 ? 1 : 0) + (m2 ? 1 : 0);
-    h.c_j = m2 ? c2 : (m1 ? c1 : c0);
-    h.c_j1 = m2 ? c3 : (m1 ? c2 : c1);
-    return raw < s.P && cnt <= 2;
+    const bool w = raw >= s.P;
+    const double t = w ? dsub(raw, s.P) : raw;
+    const uint32_t b = cell_of(t, s.scale, s.M);
+    const int j0 = ld_idx<SMEM>(s, (int)b);
+    const int cnt = ld_idx<SMEM>(s, (int)b + 1) - j0;
+    const double c1 = ld_c<SMEM>(s, j0 + 1), c2 = ld_c<SMEM>(s, j0 + 2), c3 = ld_c<SMEM>(s, j0 + 3);
+    int j = j0;                                  // the boundaries are increasing: each test implies the one before
+    if (SMEM) {
+        if (cnt >= 1 && c1 <= t) j = j0 + 1;
+        if (cnt >= 2 && c2 <= t) j = j0 + 2;
+        if (cnt >= 3 && c3 <= t) j = j0 + 3;
+        h.c_j = ld_c<SMEM>(s, j);                // a third round of (cheap) shared-memory loads instead of selects
+        h.c_j1 = ld_c<SMEM>(s, j + 1);
+    } else {
+        // global path: every dependent round is an L2 round trip, so C[j0] and C[j0+4] come with the candidates
+        // (five consecutive doubles: one or two sectors) and the pair is selected
+        const double c0 = ld_c<SMEM>(s, j0), c4 = ld_c<SMEM>(s, j0 + 4);
+        double a = c0, b1 = c1;
+        if (cnt >= 1 && c1 <= t) { j = j0 + 1; a = c1; b1 = c2; }
+        if (cnt >= 2 && c2 <= t) { j = j0 + 2; a = c2; b1 = c3; }
+        if (cnt >= 3 && c3 <= t) { j = j0 + 3; a = c3; b1 = c4; }
+        h.c_j = a;
+        h.c_j1 = b1;
+    }
+    h.target = t;
+    h.j = j;
+    h.kx = w ? s.Td : 0.0;
+    return cnt <= 3 && t < s.P;
 }
 
-// Any case: whole-period wrap, any number of boundaries in the cell, traces without an index (bisection).
+// Any case: several whole-period wraps, any number of boundaries in the cell, traces without an index (bisection).
 template <bool SMEM>
 __device__ __forceinline__ void head_any(const Sess& s, double target, Head& h, bool& walk_error) {
     int n = 0;
@@ -174,9 +219,9 @@ __device__ __forceinline__ void head_any(const Sess& s, double target, Head& h, 
     }
     int j, j_hi;
     if (s.M > 0) {
-        const int b = min(max(__double2int_rz(dmul(target, s.scale)), 0), s.M - 1);
-        j = ld_idx<SMEM>(s, b);
-        j_hi = ld_idx<SMEM>(s, b + 1);
+        const uint32_t b = cell_of(target, s.scale, s.M);
+        j = ld_idx<SMEM>(s, (int)b);
+        j_hi = ld_idx<SMEM>(s, (int)b + 1);
     } else {
         j = 0;
         j_hi = s.T - 1;
@@ -189,12 +234,13 @@ __device__ __forceinline__ void head_any(const Sess& s, double target, Head& h, 
     }
     double c_j = ld_c<SMEM>(s, j), c_j1 = ld_c<SMEM>(s, j + 1);
     while (j < j_hi && c_j1 <= target) { ++j; c_j = c_j1; c_j1 = ld_c<SMEM>(s, j + 1); }
-    h.target = target; h.n = n; h.j = j; h.c_j = c_j; h.c_j1 = c_j1;
+    h.target = target; h.j = j; h.c_j = c_j; h.c_j1 = c_j1;
+    h.kx = n == 0 ? 0.0 : dmul((double)n, s.Td);   // exact in fp64
 }
 
 template <bool SMEM>
 __device__ __forceinline__ void head(const Sess& s, const double raw, Head& h, bool& walk_error) {
-    if (!head_fast<SMEM>(s, raw, h)) head_any<SMEM>(s, raw, h, walk_error);
+    if (s.M == 0 || !head_fast<SMEM>(s, raw, h)) head_any<SMEM>(s, raw, h, walk_error);
 }
 
 // SPEC §7.1 pause gate (Simulator.py:143-145): wait for the live edge, then for room in the buffer; moves the trace
@@ -240,11 +286,10 @@ __device__ __forceinline__ bool step_tail(const EnvView& v, Sess& s, const Head&
     const double size = lk.size, u = lk.u, u_prev = lk.u_prev;
     const int T = s.T;
     if (!(h.target < h.c_j1)) r.walk_error = true;   // insurance: the index covered the download
-    // segment boundaries crossed: (j - seg) + n*T
-    double kd = (double)(h.j - s.seg);
-    if (h.n != 0) kd = dadd(kd, dmul((double)h.n, (double)T));   // exact in fp64
+    // segment boundaries crossed: (j - seg) + n*T (both terms and the sum are exact)
+    const double kd = dadd(int2double(h.j - s.seg), h.kx);
     const double phi_new = ddiv(dsub(h.target, h.c_j), dsub(h.c_j1, h.c_j));   // fraction of segment j consumed
-    const double delay = dadd(max0(dmul(dadd(kd, dsub(phi_new, s.phi)), s.I)), p.rtt);
+    const double delay = dadd(max0d(dmul(dadd(kd, dsub(phi_new, s.phi)), s.I)), p.rtt);
     int seg = h.j;
     double phi = phi_new;
     bool moved = false;
@@ -264,8 +309,8 @@ __device__ __forceinline__ bool step_tail(const EnvView& v, Sess& s, const Head&
         sleep = g.idle;
     } else {
         // 3.2 buffer drain / rebuffer
-        rebuf = max0(dsub(delay, s.buffer));
-        buffer = dadd(max0(dsub(s.buffer, delay)), p.chunk_length);
+        rebuf = max0d(dsub(delay, s.buffer));
+        buffer = dadd(max0d(dsub(s.buffer, delay)), p.chunk_length);
         // 3.3 sleep cap
         if (buffer > p.max_buffer) {
             const double over = dsub(buffer, p.max_buffer);
@@ -278,7 +323,7 @@ __device__ __forceinline__ bool step_tail(const EnvView& v, Sess& s, const Head&
         }
     }
     // 3.4 reward
-    const double smooth = (s.last_q >= 0) ? fabs(dsub(u, u_prev)) : 0.0;
+    const double smooth = fabs(dsub(u, u_prev));   // u_prev == u when there is no previous chunk (lookup_tables)
     r.reward = dsub(dsub(u, dmul(p.rebuf_penalty, rebuf)), dmul(p.smooth_penalty, smooth));
     if (LIVE) r.reward = dsub(r.reward, dmul(p.latency_penalty, r.latency));
     r.delay = delay; r.sleep = sleep; r.buffer = buffer; r.rebuf = rebuf; r.u = u; r.smooth = smooth;
@@ -311,7 +356,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
     g.buffer = s.buffer; g.rebuf = g.idle = g.startup = 0.0;
     Head h;
     if (!FAST && s.done) {
-        h.target = h.c_j = 0.0; h.c_j1 = 1.0; h.j = 0; h.n = 0;
+        h.target = h.c_j = h.kx = 0.0; h.c_j1 = 1.0; h.j = 0;
     } else {
         if (LIVE) live_gate<SMEM>(v, s, g);
         head<SMEM>(s, dadd(s.pos, lk.size), h, r.walk_error);
@@ -342,14 +387,14 @@ __device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawStat
     const int tr = w.tr;
     s.cum = v.trace_cum + (size_t)tr * cum_stride(v.T_max);
     s.idx = v.trace_idx + (size_t)tr * idx_stride(v.T_max);
-    s.sizes = v.sizes;
-    s.util = v.util;
+    s.tab = v.tab;
     {   // one 32-byte record: two 16-byte read-only loads from the same sector
         const double2 ip = __ldg(reinterpret_cast<const double2*>(v.trace_meta + tr));
         const int4 tb = __ldg(reinterpret_cast<const int4*>(v.trace_meta + tr) + 1);
         s.I = ip.x; s.P = ip.y; s.scale = __hiloint2double(tb.y, tb.x); s.T = tb.z; s.M = tb.w;
+        s.Td = (double)tb.z;
     }
-    s.cum_s = s.idx_s = s.sizes_s = s.util_s = 0u;
+    s.cum_s = s.idx_s = s.tab_s = 0u;
     s.seg = w.seg;
     s.chunk = w.chunk;
     s.last_q = w.last_q;
@@ -403,7 +448,7 @@ abr_trace_table_kernel(EnvView v, double* __restrict__ cum, uint16_t* __restrict
         uint16_t* i_row = idx + (size_t)t * idx_stride(v.T_max);
         int j = 1;   // next interior boundary not yet known to lie in a cell below b
         for (int b = 0; b <= M; ++b) {
-            while (j <= T - 1 && min(max(__double2int_rz(dmul(c_row[j], scale)), 0), M - 1) < b) ++j;
+            while (j <= T - 1 && (int)cell_of(c_row[j], scale, M) < b) ++j;
             i_row[b] = (uint16_t)(j - 1);
         }
         for (int b = M + 1; b < idx_stride(v.T_max); ++b) i_row[b] = (uint16_t)(T > 0 ? T - 1 : 0);
@@ -416,17 +461,25 @@ abr_trace_table_kernel(EnvView v, double* __restrict__ cum, uint16_t* __restrict
 
 // SPEC §2 for one session: the validated trace and the position (seg, phase, data position) of the start offset.
 // Shared by the reset kernel and the episode kernel's fused reset, so that both perform the same operations.
+__device__ __forceinline__ void reset_seg_phase(const double I, const int T, const double off, int& seg_out,
+                                                double& phi_out, int& n_bad) {
+    const double x = ddiv(off, I);
+    const double n = floor(x);
+    // n mod T: the 32-bit remainder when n fits (every realistic offset), fmod otherwise — the same value
+    int seg = (n >= 0.0 && n < 2147483648.0) ? (int)((uint32_t)n % (uint32_t)T) : (int)fmod(n, (double)T);
+    double phi = dsub(x, n);   // exact, in [0, 1)
+    if (seg < 0 || seg >= T) { ++n_bad; seg = 0; }
+    if (!(phi >= 0.0 && phi < 1.0)) { ++n_bad; phi = 0.0; }   // NaN / infinite start offset
+    seg_out = seg; phi_out = phi;
+}
+
 __device__ __forceinline__ RawState reset_position(const EnvView& v, int tr, const double off, int& n_bad) {
     RawState w;
     if (tr < 0 || tr >= v.n_traces) { ++n_bad; tr = 0; }
     const int T = v.trace_len[tr];
     const double I = v.trace_interval[tr];
-    const double x = ddiv(off, I);
-    const double n = floor(x);
-    int seg = (int)fmod(n, (double)T);
-    w.phi = dsub(x, n);   // exact, in [0, 1)
-    if (seg < 0 || seg >= T) { ++n_bad; seg = 0; }
-    if (!(w.phi >= 0.0 && w.phi < 1.0)) { ++n_bad; w.phi = 0.0; }   // NaN / infinite start offset
+    int seg;
+    reset_seg_phase(I, T, off, seg, w.phi, n_bad);
     const double* c_row = v.trace_cum + (size_t)tr * cum_stride(v.T_max);
     const double c0 = __ldg(c_row + seg), c1 = __ldg(c_row + seg + 1);
     w.pos = dadd(c0, dmul(dsub(c1, c0), w.phi));
@@ -682,7 +735,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     bool flagged = false, reset_mpc = false;
     const uint32_t n = (uint32_t)v.n;
     const bool hist = !FAST && v.p.track_history != 0;
-    uint32_t packed = 0u;   // random policy: the four actions of one Philox block, one per byte
+    uint32_t packed = 0u;   // random policy: the eight actions of one Philox block, one per nibble
     if (LIVE) {
         if (fresh) { s.t_now = 0.0; s.play_time = 0.0; s.started = v.p.start_up_length <= 0.0; }
         else { s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0; }
@@ -698,13 +751,15 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         }
         if (POLICY == ABR_POLICY_RANDOM) {
             const uint32_t tg = step_base + (uint32_t)t;   // step index since the last reset (SPEC §4)
-            if ((tg & 3u) == 0u || t == 0) {   // one Philox block per four steps (counter = (session, step / 4)), word step % 4
-                const uint4 r = philox4x32_10((uint32_t)gsession, (uint32_t)(gsession >> 32), tg >> 2, 0u,
+            if ((tg & 7u) == 0u || t == 0) {   // one Philox block per eight steps: counter = (session, step / 8),
+                                               // 16-bit slice step % 8 (low half of word 0 first)
+                const uint4 r = philox4x32_10((uint32_t)gsession, (uint32_t)(gsession >> 32), tg >> 3, 0u,
                                               seed_lo, seed_hi);
-                const uint32_t A = (uint32_t)v.A;   // <= 16: an action fits a byte
-                packed = __umulhi(r.x, A) | (__umulhi(r.y, A) << 8) | (__umulhi(r.z, A) << 16) | (__umulhi(r.w, A) << 24);
+                const uint32_t A = (uint32_t)v.A;   // <= 16: an action fits a nibble, (x16 * A) >> 16 < A
+                auto two = [A](uint32_t x) { return (((x & 0xffffu) * A) >> 16) | ((((x >> 16) * A) >> 16) << 4); };
+                packed = two(r.x) | (two(r.y) << 8) | (two(r.z) << 16) | (two(r.w) << 24);
             }
-            return (int)((packed >> (8 * (tg & 3u))) & 0xffu);
+            return (int)((packed >> (4 * (tg & 7u))) & 0xfu);
         }
         return policy_bba(v, s.buffer);
     };
@@ -723,22 +778,25 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     if (AHEAD) {
         int q0 = action_at(0);
         Lookup lk0 = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q0, s.last_q);
-        int c1 = next_chunk(s.chunk);
-        int q1 = action_at(1);
-        Lookup lk1 = lookup_tables<SMEM>(s, v.A, v.V, c1, q1, next_last_q(s.chunk, q0));
+        int c1 = next_chunk(s.chunk);            // chunk index / previous quality step t+1 will see
+        int lq1 = next_last_q(s.chunk, q0);
         Head h;
         r.walk_error = false;
         head<SMEM>(s, dadd(s.pos, lk0.size), h, r.walk_error);
+        bool spec = true;   // warp-uniform: no lane of the warp slept in the previous step
+        const unsigned lanes = __activemask();   // the warp's sessions (converged here; all run `steps` iterations)
+#pragma unroll kRolloutUnroll
         for (int t = 0; t < steps; ++t) {
-            // head of step t+1, assuming that step t does not sleep
+            // action, table reads and head of step t+1, assuming that step t does not sleep.  Sessions whose buffer
+            // sits at the cap sleep after every chunk, and the lanes of a warp tend to do so together (same trace):
+            // a warp that slept in the last step does not speculate (its head would be redone anyway).
+            const int q1 = action_at(t + 1);
+            const Lookup lk1 = lookup_tables<SMEM>(s, v.A, v.V, c1, q1, lq1);
             Head h1;
-            const bool ok1 = head_fast<SMEM>(s, dadd(h.target, lk1.size), h1);
+            bool ok1 = false;
+            if (spec && (SMEM || s.M > 0)) ok1 = head_fast<SMEM>(s, dadd(h.target, lk1.size), h1);
             // tail of step t
             const bool moved = step_tail<SMEM, FAST, false>(v, s, h, q0, lk0, g, r, hist);
-            // action and table reads of step t+2
-            const int c2 = next_chunk(c1);
-            const int q2 = action_at(t + 2);
-            const Lookup lk2 = lookup_tables<SMEM>(s, v.A, v.V, c2, q2, next_last_q(c1, q1));
             if (NOOUT) {
             } else if (FAST) {
                 __stcs(o.delay + ix, (OT)r.delay); __stcs(o.sleep + ix, (OT)r.sleep); __stcs(o.buffer + ix, (OT)r.buffer);
@@ -763,9 +821,16 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             }
             flagged |= r.walk_error;
             r.walk_error = false;
-            if (moved || !ok1) head_any<SMEM>(s, dadd(s.pos, lk1.size), h1, r.walk_error);   // s.pos: where step t left the session
+            spec = !__any_sync(lanes, moved);
+            if (moved || !ok1) {   // s.pos: where step t left the session
+                const double raw = dadd(s.pos, lk1.size);
+                if (!(SMEM || s.M > 0) || !head_fast<SMEM>(s, raw, h1)) head_any<SMEM>(s, raw, h1, r.walk_error);
+            }
             h = h1;
-            q0 = q1; q1 = q2; lk0 = lk1; lk1 = lk2; c1 = c2;
+            lk0 = lk1;
+            q0 = q1;
+            lq1 = next_last_q(c1, q1);
+            c1 = next_chunk(c1);
             ix += n;
         }
         flagged |= r.walk_error;
@@ -842,7 +907,10 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
 // 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
 // co-resident (6.9 per SM).
 template <int POLICY, bool FAST, bool NOOUT, bool LIVE, typename OT>
-__global__ void __launch_bounds__(kRolloutBlock, LIVE ? 6 : 8)
+#ifndef ABR_ROLLOUT_MINBLOCKS
+#define ABR_ROLLOUT_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(kRolloutBlock, LIVE ? 6 : ABR_ROLLOUT_MINBLOCKS)
 abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uint32_t step_base,
                    const int32_t* __restrict__ actions_in, RolloutOut<OT> o, int smem_doubles,
                    double* __restrict__ block_partials) {
@@ -864,8 +932,15 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
     int n_bad = 0;
     if (valid) {
         if (fresh) {
-            const RawState w = reset_position(v, o.in_trace_id[i], o.in_offset ? o.in_offset[i] : 0.0, n_bad);
+            // SPEC §2 from the per-trace record (one dependent read after the trace id); the data position is taken
+            // from the C row once it is known where that row is read from (shared memory or global)
+            RawState w;
+            w.tr = o.in_trace_id[i];
+            const double off = o.in_offset ? o.in_offset[i] : 0.0;
+            if (w.tr < 0 || w.tr >= v.n_traces) { ++n_bad; w.tr = 0; }
+            w.seg = 0; w.chunk = 0; w.last_q = v.p.default_quality; w.phi = 0.0; w.pos = 0.0; w.buffer = 0.0;
             make_sess(v, i, w, s);
+            reset_seg_phase(s.I, s.T, off, s.seg, s.phi, n_bad);
             s.done = false; s.hist_len = 0;
             tr = w.tr;
             v.trace_id[i] = tr;
@@ -879,7 +954,8 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
     __syncthreads();
     const int tr0 = s_tr0;
     // block-uniform: every session of this block follows trace tr0 (whose rows fit: T <= T_max)
-    const bool use_smem = smem_doubles != 0 && __syncthreads_and((!valid || tr == tr0) ? 1 : 0);
+    const bool use_smem = smem_doubles != 0 && __syncthreads_and((!valid || tr == tr0) ? 1 : 0) &&
+                          __ldg(&v.trace_meta[tr0].M) > 0;
     if (use_smem) {
         // Stage the trace's C and index rows and the chunk-size / utility tables with TMA bulk copies (cp.async.bulk,
         // SASS UBLKCP): one elected thread issues four asynchronous global->shared copies that complete on an
@@ -887,10 +963,8 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
         // their state.  Rows start 16-byte aligned and all byte counts are multiples of 16.
         double* s_row = reinterpret_cast<double*>(s_row2);
         uint16_t* s_idx = reinterpret_cast<uint16_t*>(s_row + smem_doubles);
-        double* s_sizes = reinterpret_cast<double*>(s_idx + idx_stride(v.T_max));
-        double* s_util = s_sizes + v.V * v.A;
-        const uint32_t tab_bytes = (uint32_t)(v.V * v.A) * 8u;
-        const bool tab_bulk = (tab_bytes & 15u) == 0;
+        double2* s_tab = reinterpret_cast<double2*>(s_idx + idx_stride(v.T_max));
+        const uint32_t tab_bytes = (uint32_t)(v.V * v.A) * 16u;
         const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
@@ -899,34 +973,26 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint32_t rb = row_bytes_of(__ldg(&v.trace_meta[tr0].T)), ib = idx_bytes_of(__ldg(&v.trace_meta[tr0].M));
-            const uint32_t total = rb + ib + (tab_bulk ? 2u * tab_bytes : 0u);
+            const uint32_t total = rb + ib + tab_bytes;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
             bulk_g2s(s_row, v.trace_cum + (size_t)tr0 * cum_stride(v.T_max), rb, mbar);
             bulk_g2s(s_idx, v.trace_idx + (size_t)tr0 * idx_stride(v.T_max), ib, mbar);
-            if (tab_bulk) {
-                bulk_g2s(s_sizes, v.sizes, tab_bytes, mbar);
-                bulk_g2s(s_util, v.util, tab_bytes, mbar);
-            }
-        }
-        if (!tab_bulk) {
-            for (int j = threadIdx.x; j < v.V * v.A; j += blockDim.x) {
-                s_sizes[j] = __ldg(v.sizes + j);
-                s_util[j] = __ldg(v.util + j);
-            }
+            bulk_g2s(s_tab, v.tab, tab_bytes, mbar);
         }
         mbar_wait(mbar, 0u);
         __syncthreads();
         if (valid) {
             s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row);
             s.idx_s = (uint32_t)__cvta_generic_to_shared(s_idx);
-            s.sizes_s = (uint32_t)__cvta_generic_to_shared(s_sizes);
-            s.util_s = (uint32_t)__cvta_generic_to_shared(s_util);
+            s.tab_s = (uint32_t)__cvta_generic_to_shared(s_tab);
             // keep the addresses in registers: left alone, the compiler rematerialises them from
             // SR_CgaCtaId (an S2R round trip) at every use inside the step loop
-            asm volatile("" : "+r"(s.cum_s), "+r"(s.sizes_s), "+r"(s.util_s), "+r"(s.idx_s));
+            asm volatile("" : "+r"(s.cum_s), "+r"(s.tab_s), "+r"(s.idx_s));
+            if (fresh) s.pos = position_of<true>(s, s.seg, s.phi);
             rollout_session<POLICY, true, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);
         }
     } else if (valid) {
+        if (fresh) s.pos = position_of<false>(s, s.seg, s.phi);
         rollout_session<POLICY, false, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);
     }
     // statistics stage 1 fused into the episode: per-block sums of the updated accumulators in a fixed order

@@ -29,11 +29,11 @@ N_TRACES, T_TRACE = 1024, 2048
 SEED = 7
 GROUP = 64                          # consecutive sessions per trace (one 64-thread block = one trace)
 BYTES_PER_STEP = 5 * 8 + 1          # delay, sleep, buffer, rebuf, reward (f64) + end_of_video (u8)
-BYTES_PER_SESSION = 32 + 28 + 160   # state load + state store + read-modify-write of the 10 accumulators, once per episode
+BYTES_PER_SESSION = 40 + 36 + 160   # state load + state store + read-modify-write of the 10 accumulators, once per episode
 # abr_env_run (reset fused into the episode kernel): 12 B of trace id + start offset in, the whole reset state out
-# (28 B of position + 38 B that only a reset writes: trace_id, hist_len, last_pred, err_len, done, t_now, play_time,
+# (36 B of position + 38 B that only a reset writes: trace_id, hist_len, last_pred, err_len, done, t_now, play_time,
 # started) and the 10 accumulators written without being read
-BYTES_PER_SESSION_RUN = 12 + 28 + 38 + 80
+BYTES_PER_SESSION_RUN = 12 + 36 + 38 + 80
 
 
 def parse():
@@ -90,8 +90,8 @@ def _py_step_worker(job):
         sess = so.Session(tables[tr][0], float(ti[tr]), sz, util, P, float(off[s]), table=tables[tr][1])
         g = lo + s
         for t in range(V):
-            x0 = orc.philox(g & 0xffffffff, g >> 32, t >> 2, 0, SEED, 0)[t & 3]
-            tot += sess.step((x0 * A) >> 32)["reward"]
+            x16 = (orc.philox(g & 0xffffffff, g >> 32, t >> 3, 0, SEED, 0)[(t & 7) >> 1] >> (16 * (t & 1))) & 0xffff
+            tot += sess.step((x16 * A) >> 16)["reward"]
         done_steps += V
         if time.perf_counter() - t0 > budget_s:
             break
@@ -514,7 +514,7 @@ def hbm_peak_gbs():
 
 def bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak):
     """Per-step-launch form (RL-harness shape, configs[4] per GPU): one abr_step_kernel launch per chunk over
-    --step-sessions sessions with the SoA state in HBM; 105 algorithmic bytes per session-step.  Measured for two
+    --step-sessions sessions with the SoA state in HBM; 121 algorithmic bytes per session-step.  Measured for two
     session layouts: sorted by trace (every 256-thread block follows one trace and stages its capacity row in shared
     memory) and interleaved (trace = session mod n_traces: every probe is a scattered global load)."""
     import torch
@@ -530,7 +530,7 @@ def bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak):
     out = StepResult(*[torch.empty(M, dtype=torch.float64, device=dev) for _ in range(5)], None,
                      torch.empty(M, dtype=torch.uint8, device=dev), None)
     stream = torch.cuda.current_stream()
-    bytes_per = 32 + 4 + 28 + 41
+    bytes_per = 40 + 4 + 36 + 41      # state read (seg, chunk, last_q, trace_id, phase, pos, buffer) + action, state write, outputs
     res = {}
     for name, group in (("sorted_by_trace", max(256, M // N_TRACES)), ("interleaved", 1)):
         tid, off = synth.make_sessions(M, N_TRACES, T_TRACE, session_base=rank * M, group=group)
@@ -565,7 +565,7 @@ def bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak):
     e1.record(stream)
     e1.synchronize()
     ms32 = max_over_ranks(e0.elapsed_time(e1), dev) / 24
-    bytes32 = 32 + 4 + 28 + 21
+    bytes32 = 40 + 4 + 36 + 21
     res["sorted_by_trace_fp32_outputs"] = dict(ms_per_launch=ms32, session_steps_per_s=world * M / (ms32 * 1e-3),
                                                bytes_per_session_step=bytes32,
                                                roofline=dict(bound="hbm", achieved=M * bytes32 / (ms32 * 1e-3) / 1e9,

@@ -289,11 +289,12 @@ static int policy_action(OrcEnv* e, int s, int policy, uint64_t seed, int64_t se
     if (policy == ORC_POLICY_RANDOM) {
         uint64_t g = (uint64_t)(session_base + s);
         uint32_t r[4];
-        /* one Philox block per four steps: counter (session, step / 4), word step % 4 */
+        /* one Philox block per eight steps: counter (session, step / 8), 16-bit slice step % 8 (low half of word 0 first) */
         const uint32_t tg = e->step_base + (uint32_t)step;   /* step index since the last reset */
-        orc_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), tg >> 2, 0u, (uint32_t)seed,
+        orc_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), tg >> 3, 0u, (uint32_t)seed,
                           (uint32_t)(seed >> 32), r);
-        return (int)(((uint64_t)r[tg & 3] * (uint64_t)A) >> 32);
+        const uint32_t x16 = (r[(tg & 7) >> 1] >> (16 * (tg & 1))) & 0xffffu;
+        return (int)((x16 * (uint32_t)A) >> 16);
     }
     /* BBA */
     double b = e->buffer[s];

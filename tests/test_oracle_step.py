@@ -85,8 +85,8 @@ def test_rollout_policies_and_acc():
             tot = 0.0
             for t in range(steps):
                 if policy == orc.POLICY_RANDOM:
-                    x0 = orc.philox((1000 + s) & 0xffffffff, 0, t >> 2, 0, 123, 0)[t & 3]
-                    q = (x0 * 6) >> 32
+                    x16 = (orc.philox((1000 + s) & 0xffffffff, 0, t >> 3, 0, 123, 0)[(t & 7) >> 1] >> (16 * (t & 1))) & 0xffff
+                    q = (x16 * 6) >> 16
                 else:
                     q = so.bba_action(sess.buffer, 6, P["bba_reservoir"], P["bba_cushion"])
                 assert q == tr["actions"][t, s]
