@@ -8,9 +8,10 @@
 
 namespace abr {
 
-// Row stride (in doubles) of the cumulative-capacity table C[0..T] of SPEC §3.1, even so that every row starts
-// 16-byte aligned (TMA bulk copies).
-__host__ __device__ __forceinline__ int cum_stride(int T_max) { return (T_max + 2) & ~1; }
+// Row stride (in doubles) of the cumulative-capacity table C[0..T] of SPEC §3.1: a multiple of four, so that every
+// row starts 32-byte aligned (TMA bulk copies need 16; the global path reads aligned 256-bit quads), with at least
+// seven entries of +inf padding behind C[T] (the global path's eight-entry window may start at C[T-1]).
+__host__ __device__ __forceinline__ int cum_stride(int T_max) { return (T_max + 8 + 3) & ~3; }
 // Bucket index of SPEC §3.1 (how the step finds the segment a download ends in; not part of the arithmetic contract):
 // the trace period's data range [0, P) is cut into M = 2T equal cells, idx[b] = number of interior segment
 // boundaries C[1..T-1] that lie in cells below b.  A position x in cell b then ends in a segment j with
@@ -73,7 +74,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 // ---------------------------------------------------------------------------------------------
 // What a step reads about its trace, packed so that it is one dependent 32-byte read after trace_id instead of
 // four scattered ones (interval, period capacity C[T], length, search widths).
-struct __align__(16) TraceMeta {
+struct __align__(32) TraceMeta {
     double I, P;      // segment duration, capacity of one trace period C[T]
     double scale;     // M / P: cell of a data position x is (int)(x * scale), clamped to M - 1
     int32_t T, M;     // segments, index cells (0 = no index)

@@ -105,6 +105,23 @@ __device__ __forceinline__ double int2double(const int i) {
 // FP64 operations (16 cycles) where the sign-mask form of abr_common.cuh takes three on the busier integer pipe.
 __device__ __forceinline__ double max0d(double x) { return dmul(dadd(x, fabs(x)), 0.5); }
 
+// One aligned 256-bit read-only load (SASS LDG.E.256): a scattered load costs the L1 one tag cycle per distinct line
+// whatever its width, so the global path fetches four doubles per instruction.
+struct Quad { double a, b, c, d; };
+__device__ __forceinline__ Quad ldg256(const void* p) {
+    Quad q;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(q.a), "=d"(q.b), "=d"(q.c), "=d"(q.d) : "l"(p));
+    return q;
+}
+
+// x[k] of eight doubles held in registers, k in [0, 8): a three-level select tree.
+__device__ __forceinline__ double sel8(const Quad& A, const Quad& B, const int k) {
+    const bool b0 = (k & 1) != 0, b1 = (k & 2) != 0, b2 = (k & 4) != 0;
+    const double y0 = b0 ? A.b : A.a, y1 = b0 ? A.d : A.c, y2 = b0 ? B.b : B.a, y3 = b0 ? B.d : B.c;
+    const double z0 = b1 ? y1 : y0, z1 = b1 ? y3 : y2;
+    return b2 ? z1 : z0;
+}
+
 // C[j] / idx[b] of the session's trace: an LDS on the shared-memory path, else a read-only global load.
 template <bool SMEM>
 __device__ __forceinline__ double ld_c(const Sess& s, const int j) {
@@ -183,30 +200,38 @@ __device__ __forceinline__ bool head_fast(const Sess& s, const double raw, Head&
     const double t = w ? dsub(raw, s.P) : raw;
     const uint32_t b = cell_of(t, s.scale, s.M);
     const int j0 = ld_idx<SMEM>(s, (int)b);
-    const int cnt = ld_idx<SMEM>(s, (int)b + 1) - j0;
-    const double c1 = ld_c<SMEM>(s, j0 + 1), c2 = ld_c<SMEM>(s, j0 + 2), c3 = ld_c<SMEM>(s, j0 + 3);
-    int j = j0;                                  // the boundaries are increasing: each test implies the one before
+    int j;
+    bool ok;
     if (SMEM) {
+        const int cnt = ld_idx<SMEM>(s, (int)b + 1) - j0;
+        const double c1 = ld_c<SMEM>(s, j0 + 1), c2 = ld_c<SMEM>(s, j0 + 2), c3 = ld_c<SMEM>(s, j0 + 3);
+        j = j0;                                  // the boundaries are increasing: each test implies the one before
         if (cnt >= 1 && c1 <= t) j = j0 + 1;
         if (cnt >= 2 && c2 <= t) j = j0 + 2;
         if (cnt >= 3 && c3 <= t) j = j0 + 3;
         h.c_j = ld_c<SMEM>(s, j);                // a third round of (cheap) shared-memory loads instead of selects
         h.c_j1 = ld_c<SMEM>(s, j + 1);
+        ok = cnt <= 3;
     } else {
-        // global path: every dependent round is an L2 round trip, so C[j0] and C[j0+4] come with the candidates
-        // (five consecutive doubles: one or two sectors) and the pair is selected
-        const double c0 = ld_c<SMEM>(s, j0), c4 = ld_c<SMEM>(s, j0 + 4);
-        double a = c0, b1 = c1;
-        if (cnt >= 1 && c1 <= t) { j = j0 + 1; a = c1; b1 = c2; }
-        if (cnt >= 2 && c2 <= t) { j = j0 + 2; a = c2; b1 = c3; }
-        if (cnt >= 3 && c3 <= t) { j = j0 + 3; a = c3; b1 = c4; }
-        h.c_j = a;
-        h.c_j1 = b1;
+        // Global path: bound by the L1's tag stage (one cycle per lane and scattered load instruction), and every
+        // dependent round is an L2 round trip.  So: one index entry, then the aligned eight-entry window of C that
+        // holds C[j0] as two 256-bit loads.  C[q0 .. j0] <= t by the index, entries past the row's C[T] are +inf,
+        // and C is increasing, so the entries <= t are a prefix of the window and their count places j — provided
+        // C[j+1] is still inside the window (count <= 7).
+        const int q0 = j0 & ~3;
+        const Quad A = ldg256(s.cum + q0), B = ldg256(s.cum + q0 + 4);
+        const int n_le = (A.a <= t ? 1 : 0) + (A.b <= t ? 1 : 0) + (A.c <= t ? 1 : 0) + (A.d <= t ? 1 : 0) +
+                         (B.a <= t ? 1 : 0) + (B.b <= t ? 1 : 0) + (B.c <= t ? 1 : 0) + (B.d <= t ? 1 : 0);
+        ok = n_le >= 1 && n_le <= 7;
+        const int i = ok ? n_le - 1 : 0;
+        j = q0 + i;
+        h.c_j = sel8(A, B, i);
+        h.c_j1 = sel8(A, B, i + 1);
     }
     h.target = t;
     h.j = j;
     h.kx = w ? s.Td : 0.0;
-    return cnt <= 3 && t < s.P;
+    return ok && t < s.P;
 }
 
 // Any case: several whole-period wraps, any number of boundaries in the cell, traces without an index (bisection).
@@ -388,11 +413,10 @@ __device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawStat
     s.cum = v.trace_cum + (size_t)tr * cum_stride(v.T_max);
     s.idx = v.trace_idx + (size_t)tr * idx_stride(v.T_max);
     s.tab = v.tab;
-    {   // one 32-byte record: two 16-byte read-only loads from the same sector
-        const double2 ip = __ldg(reinterpret_cast<const double2*>(v.trace_meta + tr));
-        const int4 tb = __ldg(reinterpret_cast<const int4*>(v.trace_meta + tr) + 1);
-        s.I = ip.x; s.P = ip.y; s.scale = __hiloint2double(tb.y, tb.x); s.T = tb.z; s.M = tb.w;
-        s.Td = (double)tb.z;
+    {   // one 32-byte record, one 256-bit read-only load
+        const Quad m = ldg256(v.trace_meta + tr);
+        s.I = m.a; s.P = m.b; s.scale = m.c; s.T = __double2loint(m.d); s.M = __double2hiint(m.d);
+        s.Td = (double)s.T;
     }
     s.cum_s = s.idx_s = s.tab_s = 0u;
     s.seg = w.seg;
