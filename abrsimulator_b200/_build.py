@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 _SUFFIX = os.environ.get("ABR_LIB_SUFFIX", "")
 LIB = os.path.join(HERE, "lib", f"libabr_b200{_SUFFIX}.so")
 STAMP = LIB + ".srchash"
-SOURCES = ["abr_step.cu", "abr_mpc.cu", "abr_capi.cu"]
+SOURCES = ["abr_step.cu", "abr_mpc.cu", "abr_capi.cu", "abr_sort.cu"]
 HEADERS = [os.path.join(CSRC, "abr_common.cuh"), os.path.join(HERE, "..", "include", "abr_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

@@ -41,7 +41,7 @@ class AbrParams(C.Structure):
 
 # every symbol include/abr_b200.h declares (tests check that the .so exports all of them)
 SYMBOLS = ("abr_version", "abr_last_error", "abr_launch_count", "abr_device_info", "abr_params_default",
-           "abr_env_create", "abr_env_destroy", "abr_env_num_sessions", "abr_env_reset", "abr_env_reset_host",
+           "abr_env_create", "abr_env_destroy", "abr_env_num_sessions", "abr_sort_by_trace", "abr_env_set_order", "abr_env_reset", "abr_env_reset_host",
            "abr_env_step", "abr_env_step_live", "abr_env_step_f32", "abr_env_qoe_cost", "abr_env_rollout_fused",
            "abr_env_rollout_fused_live", "abr_env_rollout_fused_f32", "abr_env_run", "abr_env_mpc_decide", "abr_stats_partial",
            "abr_env_state_ptr",

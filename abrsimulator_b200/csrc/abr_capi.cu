@@ -45,6 +45,8 @@ struct AbrEnv {
     int n_partials_cap = 0;
     bool was_reset = false;   // abr_env_reset has run (an empty batch, n == 0, is legal and makes every call a no-op)
     uint32_t step_base = 0;   // fused-episode steps since the last reset: offsets the random policy's counter (SPEC §4)
+    int32_t* d_perm = nullptr;   // session order installed by abr_env_set_order (capacity entries), v.perm points here when set
+    int n_order = 0;
     int fresh_partials = 0;   // > 0: d_stats_partials holds that many block sums of the current accumulators
     double* d_stats_out = nullptr;
     // scratch for the *_host entry points
@@ -241,10 +243,38 @@ void abr_env_destroy(AbrEnv* env) { delete env; }
 
 int abr_env_num_sessions(const AbrEnv* env) { return env ? env->v.n : 0; }
 
+int abr_sort_by_trace(const int32_t* d_trace_id, int n_sessions, int n_traces, int32_t* d_perm, void* stream) {
+    if (n_sessions < 0 || n_traces < 1) return fail(ABR_ERR_RANGE, "n_sessions must be >= 0 and n_traces >= 1");
+    if (n_sessions == 0) return ABR_OK;
+    if (!d_trace_id || !d_perm) return fail(ABR_ERR_INVALID, "trace_id or perm is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t bytes = 0;
+    CUDA_TRY(launch_sort_by_trace(d_trace_id, n_sessions, n_traces, d_perm, nullptr, &bytes, st));
+    void* tmp = nullptr;
+    CUDA_TRY(cudaMallocAsync(&tmp, bytes, st));
+    cudaError_t e = launch_sort_by_trace(d_trace_id, n_sessions, n_traces, d_perm, tmp, &bytes, st);
+    cudaFreeAsync(tmp, st);
+    CUDA_TRY(e);
+    return ABR_OK;
+}
+
+int abr_env_set_order(AbrEnv* env, const int32_t* d_perm, int n_sessions, void* stream) {
+    if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
+    if (!d_perm) { env->v.perm = nullptr; env->n_order = 0; return ABR_OK; }
+    if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
+    if (!env->d_perm) CUDA_TRY(env->alloc(&env->d_perm, (size_t)env->v.cap));
+    CUDA_TRY(cudaMemcpyAsync(env->d_perm, d_perm, sizeof(int32_t) * n_sessions, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    env->v.perm = env->d_perm;
+    env->n_order = n_sessions;
+    return ABR_OK;
+}
+
 int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_offset, int n_sessions,
                   long long session_base, void* stream) {
     if (!env || (!d_trace_id && n_sessions > 0)) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
     if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
+    if (env->v.perm && env->n_order != n_sessions)
+        return fail(ABR_ERR_STATE, "the installed session order has %d entries, the batch %d (abr_env_set_order)", env->n_order, n_sessions);
     env->v.n = n_sessions;
     env->v.session_base = session_base;
     env->fresh_partials = 0;
@@ -454,6 +484,8 @@ int abr_env_run(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t
     if (policy == ABR_POLICY_FIXED && !d_actions_in && n_sessions > 0 && steps > 0)
         return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs d_actions_in");
     int rc;
+    if (env->v.perm && env->n_order != n_sessions)
+        return fail(ABR_ERR_STATE, "the installed session order has %d entries, the batch %d (abr_env_set_order)", env->n_order, n_sessions);
     if (n_sessions > 0 && steps > 0) {   // the episode kernel resets the sessions itself and writes the session cost
         env->v.n = n_sessions;
         env->v.session_base = session_base;
@@ -497,6 +529,8 @@ int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const in
     if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
     if (policy < ABR_POLICY_FIXED || policy > ABR_POLICY_BBA) return fail(ABR_ERR_INVALID, "unknown policy %d", policy);
     if (policy == ABR_POLICY_FIXED && !h_actions_in) return fail(ABR_ERR_INVALID, "ABR_POLICY_FIXED needs h_actions_in");
+    if (env->v.perm && env->n_order != n_sessions)
+        return fail(ABR_ERR_STATE, "the installed session order has %d entries, the batch %d (abr_env_set_order)", env->n_order, n_sessions);
     cudaStream_t st = (cudaStream_t)stream;
     // inputs: device aliases of page-locked buffers (read over PCIe by the kernel), else staged copies
     const int32_t* tid = (const int32_t*)device_alias(h_trace_id);

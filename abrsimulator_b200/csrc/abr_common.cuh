@@ -97,6 +97,7 @@ struct EnvView {
     uint8_t* done; uint8_t* started;
     double* t_now; double* play_time;            // live mode (SPEC §7)
     double* phi; double* pos; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
+    const int32_t* perm;                        // session order (abr_env_set_order): caller's index of position i, or null
     unsigned long long* errors;                 // device counter of flagged sessions
     int n_traces, T_max, V, A, K, cap, n;       // n = active sessions
     long long session_base;
@@ -129,6 +130,8 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
 cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, bool have_partials, double* d_out,
                          cudaStream_t st);
 int stats_num_partials(int n);
+cudaError_t launch_sort_by_trace(const int32_t* d_trace_id, int n, int n_traces, int32_t* d_perm, void* d_tmp,
+                                 size_t* tmp_bytes, cudaStream_t st);
 cudaError_t launch_qoe_cost(const EnvView& v, double* d_out, cudaStream_t st);
 int rollout_num_blocks(int n);
 

@@ -753,7 +753,8 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
                                                 const int32_t* __restrict__ actions_in, const RolloutOut<OT>& o,
                                                 double (&acc_new)[ABR_NUM_ACC], const bool fresh) {
     constexpr bool AHEAD = POLICY != ABR_POLICY_BBA && !LIVE;
-    const unsigned long long gsession = (unsigned long long)(v.session_base + i);
+    // the random policy is keyed by the caller's session index, whatever order the environment keeps the sessions in
+    const unsigned long long gsession = (unsigned long long)(v.session_base + (v.perm ? __ldg(v.perm + i) : i));
     double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_su = 0.0, a_lat = 0.0;
     int n_steps = 0, n_eps = 0;
     bool flagged = false, reset_mpc = false;

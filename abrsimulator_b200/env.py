@@ -181,6 +181,8 @@ class BatchedABREnv:
         self.K = int(self.params.hist_k)
         self.capacity = int(max_sessions)
         self.n = 0
+        self.perm = None          # installed session order (set_order), environment position -> caller's index
+        self._inv_perm = None
         self._h = C.c_void_p()
         with self._on:
             _lib.check(self._lib.abr_env_create(
@@ -224,12 +226,54 @@ class BatchedABREnv:
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
     # -- SPEC §2 --
-    def reset(self, trace_id, start_offset=None, session_base=0):
+    # -- session order (sessions are independent, so the environment may keep them sorted by trace) --
+    def sort_by_trace(self, trace_id) -> torch.Tensor:
+        """``perm`` (int32 [N], device): ``perm[p]`` = caller's index of the session that a trace-sorted environment
+        keeps at position ``p`` (stable, deterministic; ``abr_sort_by_trace``)."""
+        tid = self._dev(trace_id, torch.int32)
+        perm = self._empty(tid.numel(), dtype=torch.int32)
+        with self._on:
+            _lib.check(self._lib.abr_sort_by_trace(_ptr(tid), C.c_int(tid.numel()), C.c_int(self.n_traces), _ptr(perm),
+                                                   _stream()))
+        return perm
+
+    def set_order(self, perm):
+        """Install (``perm`` int32 [N]) or remove (None) the session order.  Afterwards every per-session array passed
+        to or returned by this environment is in environment order: element ``p`` is the caller's session ``perm[p]``
+        (``to_caller_order`` maps results back); the random policy stays keyed by the caller's index."""
+        self.perm = None if perm is None else self._dev(perm, torch.int32)
+        self._inv_perm = None
+        with self._on:
+            _lib.check(self._lib.abr_env_set_order(self._h, _ptr(self.perm),
+                                                   C.c_int(0 if self.perm is None else self.perm.numel()), _stream()))
+
+    def to_env_order(self, x):
+        """Caller-order array(s) [..., N] -> environment order (identity without an installed order)."""
+        if self.perm is None:
+            return x
+        return torch.as_tensor(x).to(self.device).index_select(-1, self.perm.long())
+
+    def to_caller_order(self, x):
+        """Environment-order result [..., N] -> the caller's session order."""
+        if self.perm is None:
+            return x
+        if self._inv_perm is None:
+            self._inv_perm = torch.empty_like(self.perm, dtype=torch.int64)
+            self._inv_perm[self.perm.long()] = torch.arange(self.perm.numel(), device=self.device)
+        return x.index_select(-1, self._inv_perm)
+
+    def reset(self, trace_id, start_offset=None, session_base=0, sort_by_trace=False):
+        """SPEC §2.  ``sort_by_trace=True``: the sessions are given in the caller's order; the environment sorts them
+        by trace (``sort_by_trace`` + ``set_order``) and keeps them in that order — see ``set_order``."""
         tid = self._dev(trace_id, torch.int32)
         off = None if start_offset is None else self._dev(start_offset, torch.float64)
         n = tid.numel()
         if off is not None and off.numel() != n:
             raise ValueError("start_offset must have one entry per session")
+        if sort_by_trace:
+            self.set_order(self.sort_by_trace(tid))
+            tid = self.to_env_order(tid).contiguous()
+            off = None if off is None else self.to_env_order(off).contiguous()
         with self._on:
             _lib.check(self._lib.abr_env_reset(self._h, _ptr(tid), _ptr(off), C.c_int(n), C.c_longlong(session_base),
                                                _stream()))

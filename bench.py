@@ -532,9 +532,15 @@ def bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak):
     stream = torch.cuda.current_stream()
     bytes_per = 40 + 4 + 36 + 41      # state read (seg, chunk, last_q, trace_id, phase, pos, buffer) + action, state write, outputs
     res = {}
-    for name, group in (("sorted_by_trace", max(256, M // N_TRACES)), ("interleaved", 1)):
+    for name, group, sort in (("sorted_by_trace", max(256, M // N_TRACES), False), ("interleaved", 1, False),
+                              ("interleaved_env_sorted", 1, True)):
+        # interleaved: trace = session mod n_traces, every probe of a lane a scattered L2 access;
+        # interleaved_env_sorted: the same sessions, the environment keeps them sorted by trace (reset(sort_by_trace=True):
+        # abr_sort_by_trace + abr_env_set_order, outside the timed region — the session->trace map is static) and all
+        # per-session arrays are in environment order
         tid, off = synth.make_sessions(M, N_TRACES, T_TRACE, session_base=rank * M, group=group)
-        env.reset(tid, off, session_base=rank * M)
+        env.set_order(None)
+        env.reset(tid, off, session_base=rank * M, sort_by_trace=sort)
         for t in range(8):
             env.step(acts[t % 8], out=out)
         barrier()
@@ -554,6 +560,7 @@ def bench_step_form(args, dev, rank, world, barrier, max_over_ranks, hbm_peak):
     # optional fp32-output mode on the trace-sorted layout: 5 x 4 + 1 B of outputs, state and arithmetic unchanged
     out32 = StepResult(*[torch.empty(M, dtype=torch.float32, device=dev) for _ in range(5)], None, out.end_of_video, None)
     tid, off = synth.make_sessions(M, N_TRACES, T_TRACE, session_base=rank * M, group=max(256, M // N_TRACES))
+    env.set_order(None)
     env.reset(tid, off, session_base=rank * M)
     for t in range(8):
         env.step(acts[t % 8], out=out32)

@@ -94,6 +94,17 @@ int abr_env_create(const double* h_trace_bw /*[n_traces][T_max]*/, const int32_t
                    const AbrParams* params, int max_sessions, AbrEnv** out);
 void abr_env_destroy(AbrEnv* env);
 int abr_env_num_sessions(const AbrEnv* env);
+/* Session order.  Sessions are independent (the reference's Simulator holds exactly one, Simulator.py:93-131), so the
+ * order in which an environment keeps them is free; kept sorted by trace, every thread block of the step kernels follows
+ * one trace and stages it in shared memory whatever order the caller's sessions come in.
+ * abr_sort_by_trace: d_perm[p] = caller's index of the session at environment position p (stable sort by trace id,
+ * deterministic; run once per session->trace assignment).
+ * abr_env_set_order: installs (copies) such an order; NULL removes it.  Every per-session array the caller passes or
+ * receives afterwards (trace ids, start offsets, actions, speeds, outputs, state views) is in ENVIRONMENT order, i.e.
+ * element p belongs to the caller's session d_perm[p]; the only thing the library does with the order is key the
+ * random policy by session_base + d_perm[p], so that a reordered run draws exactly the actions of the original one. */
+int abr_sort_by_trace(const int32_t* d_trace_id, int n_sessions, int n_traces, int32_t* d_perm, void* stream);
+int abr_env_set_order(AbrEnv* env, const int32_t* d_perm /*nullable*/, int n_sessions, void* stream);
 /* SPEC §2.  session_base = global index of local session 0 (sharded runs; keys the random policy). */
 int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_offset /*nullable*/, int n_sessions,
                   long long session_base, void* stream);

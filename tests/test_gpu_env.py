@@ -993,3 +993,47 @@ def test_prepared_host_run_equals_run_host():
     exp = env.run_host("random", steps, tid, off + 3.0, seed=1, want_qoe_cost=True)
     assert bits_equal(got["qoe_cost"].numpy(), exp["qoe_cost"]) == 0
     assert env.n == N
+
+
+def test_trace_sorted_order_is_bit_identical_to_the_callers_order():
+    """Sessions given interleaved over the traces (trace = session mod n_traces): an environment that keeps them sorted
+    by trace (abr_sort_by_trace + abr_env_set_order) returns, mapped back through the order, exactly what the
+    unsorted environment returns — fused random episode (the policy is keyed by the caller's index), per-step kernel,
+    state and statistics."""
+    N, steps = 3000, 30
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=37, T=96, ragged=True)
+    tid = (np.arange(N) % 37).astype(np.int32)
+    off = np.random.default_rng(3).uniform(0, 150.0, size=N)
+    env_a = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, max_buffer=20.0)
+    env_b = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, max_buffer=20.0)
+    env_a.reset(tid, off, session_base=500)
+    env_b.reset(tid, off, session_base=500, sort_by_trace=True)
+    perm = env_b.perm.cpu().numpy()
+    assert sorted(perm.tolist()) == list(range(N))
+    assert np.all(np.diff(tid[perm]) >= 0)                              # sorted by trace ...
+    same = np.diff(tid[perm]) == 0
+    assert np.all(np.diff(perm)[same] > 0)                              # ... and stable within a trace
+    out_a = env_a.rollout("random", steps, seed=11)
+    out_b = env_b.rollout("random", steps, seed=11)
+    for k in out_a:
+        assert torch.equal(out_a[k], env_b.to_caller_order(out_b[k])), k
+    acts = torch.from_numpy(np.random.default_rng(4).integers(0, bitrates.shape[1], size=(5, N)).astype(np.int32)).cuda()
+    for t in range(5):
+        ra = env_a.step(acts[t])
+        rb = env_b.step(env_b.to_env_order(acts[t]).contiguous())
+        for f in ("delay", "sleep", "buffer", "rebuffer", "reward", "end_of_video", "next_sizes"):
+            xa, xb = getattr(ra, f), getattr(rb, f)
+            if xb.dim() == 2:
+                xb = env_b.to_caller_order(xb.t().contiguous()).t()
+            else:
+                xb = env_b.to_caller_order(xb)
+            assert torch.equal(xa, xb), (t, f)
+    for f in ("seg", "chunk", "last_q", "phase", "pos", "buffer"):
+        assert torch.equal(env_a.state(f), env_b.to_caller_order(env_b.state(f))), f
+    np.testing.assert_allclose(env_a.stats().cpu().numpy(), env_b.stats().cpu().numpy(), rtol=1e-12)
+    assert env_a.error_count() == 0 and env_b.error_count() == 0
+    # a batch of another size needs a new order
+    with pytest.raises(_lib.AbrError):
+        env_b.reset(tid[:100], off[:100])
+    env_b.set_order(None)
+    env_b.reset(tid[:100], off[:100])
