@@ -10,17 +10,18 @@ import os
 
 from . import _build
 
-NUM_ACC = 10
-NUM_STATS = 10
+NUM_ACC = 11
+NUM_STATS = 11
 POLICY_FIXED, POLICY_RANDOM, POLICY_BBA = 0, 1, 2
 MPC_REF, MPC_ROBUST = 0, 1
 MPC_TRUNCATE, MPC_EMPTY_DEFAULT = 1, 2
-ACC_NAMES = ("reward", "rebuffer", "utility", "smooth", "sleep", "delay", "steps", "episodes", "startup", "latency")
+ACC_NAMES = ("reward", "rebuffer", "utility", "smooth", "sleep", "delay", "steps", "episodes", "startup", "latency",
+             "played")
 FIELDS = dict(seg=(0, "int32"), chunk=(1, "int32"), last_q=(2, "int32"), trace_id=(3, "int32"),
               hist_len=(4, "int32"), done=(5, "uint8"), err_len=(6, "int32"), phase=(10, "float64"), pos=(18, "float64"),
               buffer=(11, "float64"), bw_hist=(12, "float64"), last_pred=(13, "float64"),
               err_ring=(14, "float64"), acc=(15, "float64"), t_now=(16, "float64"), play_time=(17, "float64"),
-              started=(7, "uint8"), sizes=(20, "float64"), utility=(21, "float64"),
+              started=(7, "uint8"), play_id=(8, "int32"), play_len=(19, "float64"), sizes=(20, "float64"), utility=(21, "float64"),
               trace_bw=(22, "float64"))
 
 
@@ -34,9 +35,9 @@ class AbrParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "chunk_length", "max_buffer", "rtt", "payload", "sleep_quantum", "rebuf_penalty",
         "smooth_penalty", "utility_scale", "bba_reservoir", "bba_cushion", "start_up_length",
-        "startup_penalty", "latency_penalty")] + [
+        "startup_penalty", "latency_penalty", "latency_tick")] + [
         (n, C.c_int32) for n in ("utility_mode", "default_quality", "auto_reset", "hist_k",
-                                 "track_history", "track_acc", "live", "reserved2")]
+                                 "track_history", "track_acc", "live", "smooth_prev_ladder")]
 
 
 # every symbol include/abr_b200.h declares (tests check that the .so exports all of them)

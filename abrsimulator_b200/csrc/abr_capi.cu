@@ -95,9 +95,9 @@ void abr_params_default(AbrParams* p) {
     p->chunk_length = 4.0; p->max_buffer = 60.0; p->rtt = 0.08; p->payload = 0.95; p->sleep_quantum = 0.5;
     p->rebuf_penalty = 4.3; p->smooth_penalty = 1.0; p->utility_scale = 0.001;
     p->bba_reservoir = 5.0; p->bba_cushion = 10.0;
-    p->start_up_length = 0.0; p->startup_penalty = 0.0; p->latency_penalty = 0.0;
+    p->start_up_length = 0.0; p->startup_penalty = 0.0; p->latency_penalty = 0.0; p->latency_tick = 0.01;
     p->utility_mode = 0; p->default_quality = 1; p->auto_reset = 1; p->hist_k = 5;
-    p->track_history = 0; p->track_acc = 0; p->live = 0;
+    p->track_history = 0; p->track_acc = 0; p->live = 0; p->smooth_prev_ladder = 0;
 }
 
 static int check_params(const AbrParams* p, int A) {
@@ -115,6 +115,7 @@ static int check_params(const AbrParams* p, int A) {
         return fail(ABR_ERR_INVALID, "live mode needs start_up_length <= max_buffer (the start-up phase could never end)");
     if (!std::isfinite(p->start_up_length) || !std::isfinite(p->startup_penalty) || !std::isfinite(p->latency_penalty))
         return fail(ABR_ERR_INVALID, "start_up_length / startup_penalty / latency_penalty must be finite");
+    if (!(p->latency_tick > 0.0) || !std::isfinite(p->latency_tick)) return fail(ABR_ERR_INVALID, "latency_tick must be finite and > 0");
     return ABR_OK;
 }
 
@@ -222,6 +223,7 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     CUDA_TRY(e->alloc(&v.done, cap)); CUDA_TRY(e->alloc(&v.phi, cap)); CUDA_TRY(e->alloc(&v.buffer, cap));
     CUDA_TRY(e->alloc(&v.pos, cap));
     CUDA_TRY(e->alloc(&v.started, cap)); CUDA_TRY(e->alloc(&v.t_now, cap)); CUDA_TRY(e->alloc(&v.play_time, cap));
+    CUDA_TRY(e->alloc(&v.play_id, cap)); CUDA_TRY(e->alloc(&v.play_len, cap));
     CUDA_TRY(e->alloc(&v.bw_hist, cap * v.K)); CUDA_TRY(e->alloc(&v.last_pred, cap));
     CUDA_TRY(e->alloc(&v.err_ring, cap * v.K)); CUDA_TRY(e->alloc(&v.acc, cap * ABR_NUM_ACC));
     CUDA_TRY(e->alloc(&v.errors, 1));
@@ -456,6 +458,8 @@ int abr_env_state_ptr(AbrEnv* env, int field, void** d_ptr) {
         case ABR_F_T_NOW: *d_ptr = v.t_now; break;
         case ABR_F_PLAY_TIME: *d_ptr = v.play_time; break;
         case ABR_F_STARTED: *d_ptr = v.started; break;
+        case ABR_F_PLAY_ID: *d_ptr = v.play_id; break;
+        case ABR_F_PLAY_LEN: *d_ptr = v.play_len; break;
         case ABR_F_SIZES: *d_ptr = (void*)v.sizes; break;
         case ABR_F_UTILITY: *d_ptr = (void*)v.util; break;
         case ABR_F_TRACE_BW: *d_ptr = (void*)v.trace_bw; break;

@@ -96,6 +96,7 @@ struct EnvView {
     int32_t* seg; int32_t* chunk; int32_t* last_q; int32_t* trace_id; int32_t* hist_len; int32_t* err_len;
     uint8_t* done; uint8_t* started;
     double* t_now; double* play_time;            // live mode (SPEC §7)
+    int32_t* play_id; double* play_len;          // content chunk being played and how much of it has been played
     double* phi; double* pos; double* buffer; double* bw_hist; double* last_pred; double* err_ring; double* acc;
     const int32_t* perm;                        // session order (abr_env_set_order): caller's index of position i, or null
     unsigned long long* errors;                 // device counter of flagged sessions

@@ -60,12 +60,15 @@ struct Sess {
     int T, M, seg, chunk, last_q, hist_len;
     bool done;
     // live mode (SPEC §7)
-    double t_now, play_time, speed;
-    bool started;
+    double t_now, play_time, play_len;   // wall clock, content played, content played of the chunk being played
+    const double* __restrict__ speed;    // playback speed of content chunk k at speed[k * speed_stride] (null = 1.0)
+    size_t speed_stride;
+    int play_id, V;                      // content chunk being played
+    bool started, bad_speed;
 };
 
 struct StepRes {
-    double delay, sleep, buffer, rebuf, reward, thr, u, smooth, latency, startup;
+    double delay, sleep, buffer, rebuf, reward, thr, u, smooth, latency, startup, area, played;
     bool eov, inert, walk_error, reset_mpc;
 };
 
@@ -137,18 +140,22 @@ __device__ __forceinline__ int ld_idx(const Sess& s, const int b) {
 // episode issues them ahead of the step.
 struct Lookup { double size, u, u_prev; };
 
+// prev_ladder (AbrParams.smooth_prev_ladder): the previous quality is looked up in the previous chunk's own ladder
+// (Simulator.calculate_qoe, Simulator.py:81-82) instead of the current chunk's (mpc.py:148-149).
 template <bool SMEM>
 __device__ __forceinline__ Lookup lookup_tables(const Sess& s, const int A, const int V, const int chunk, const int q,
-                                                const int last_q) {
+                                                const int last_q, const bool prev_ladder) {
     const int row = (chunk < V ? chunk : 0) * A;   // an inert session (chunk == V) reads row 0 and ignores it
+    const int prow = (prev_ladder && last_q >= 0 && chunk > 0 && chunk < V) ? row - A : row;
     Lookup k;
     const double2 su = SMEM ? lds_f64x2(s.tab_s + 16u * (uint32_t)(row + q)) : __ldg(s.tab + row + q);
     k.size = su.x;
     k.u = su.y;
     // no previous chunk (last_q < 0): the smoothness term |u - u_prev| is 0
     const int lq = last_q >= 0 ? last_q : q;
-    k.u_prev = SMEM ? lds_f64(s.tab_s + 16u * (uint32_t)(row + lq) + 8u) : __ldg(&s.tab[row + lq].y);
+    k.u_prev = SMEM ? lds_f64(s.tab_s + 16u * (uint32_t)(prow + lq) + 8u) : __ldg(&s.tab[prow + lq].y);
     return k;
+
 }
 
 // SPEC §3.3: move the trace position forward by dt seconds without downloading.
@@ -174,16 +181,73 @@ __device__ __forceinline__ double position_of(const Sess& s, const int seg, cons
     return dadd(c0, dmul(dsub(c1, c0), phi));
 }
 
-// SPEC §7 play(dt): playback during an interval; returns the stall time.
-__device__ __forceinline__ double live_play(Sess& s, double& buffer, double& startup, const double dt) {
-    if (!s.started) { startup = dadd(startup, dt); return 0.0; }
-    const double need = dmul(s.speed, dt);
-    double drained, stall;
-    if (buffer >= need) { drained = need; stall = 0.0; }
-    else { drained = buffer; stall = dsub(dt, s.speed == 1.0 ? buffer : ddiv(buffer, s.speed)); }
-    buffer = dsub(buffer, drained);
-    s.play_time = dadd(s.play_time, drained);
-    return stall;
+// ---- SPEC §7 playback model (live mode): the closed form of the reference's playback block, Simulator.py:174-187 ----
+// The playback speed belongs to the content chunk being played (speed_controller.get_next_speed() is called when a
+// chunk starts to play, Simulator.py:176-177), so playback over a wall-clock interval is piecewise: one stretch per
+// content chunk.  `area` integrates the latency (wall clock - content played) over the stretches: the reference's
+// average_latency is that integral per tick (Simulator.py:179-180, see SPEC §7).
+struct LiveAcc { double startup, area, played, tc; };   // tc: wall clock inside the step
+
+__device__ __forceinline__ double live_speed(Sess& s) {
+    if (!s.speed) return 1.0;
+    const int k = s.play_id < s.V ? s.play_id : s.V - 1;
+    double v = __ldg(s.speed + (size_t)k * s.speed_stride);
+    if (!(v > 0.0)) { s.bad_speed = true; v = 1.0; }
+    return v;
+}
+
+// one stretch: d seconds of content in dw seconds of wall time at speed v
+__device__ __forceinline__ void live_piece(Sess& s, double& buffer, LiveAcc& a, const double d, const double dw,
+                                           const double v) {
+    a.area = dadd(a.area, dadd(dmul(dsub(a.tc, s.play_time), dw), dmul(dmul(dsub(1.0, v), dw), dmul(dw, 0.5))));
+    s.play_time = dadd(s.play_time, d);
+    buffer = dsub(buffer, d);
+    a.tc = dadd(a.tc, dw);
+    a.played = dadd(a.played, d);
+}
+
+// playback during dt seconds of wall time; returns the stall time
+__device__ __forceinline__ double live_play_wall(Sess& s, double& buffer, LiveAcc& a, const double dt, const double L) {
+    if (!s.started) { a.startup = dadd(a.startup, dt); a.tc = dadd(a.tc, dt); return 0.0; }
+    double rem = dt;
+    while (rem > 0.0 && buffer > 0.0) {
+        const double v = live_speed(s);
+        const double room = dsub(L, s.play_len);
+        const double can = room < buffer ? room : buffer;
+        const double need = dmul(v, rem);
+        if (need < can) {
+            live_piece(s, buffer, a, need, rem, v);
+            s.play_len = dadd(s.play_len, need);
+            rem = 0.0;
+        } else {
+            const double dw = ddiv(can, v);
+            const bool finished = room <= buffer;          // the chunk ends before the buffer does
+            live_piece(s, buffer, a, can, dw, v);
+            rem = dsub(rem, dw);
+            if (finished) { s.play_id += 1; s.play_len = 0.0; }
+            else s.play_len = dadd(s.play_len, can);
+        }
+    }
+    if (rem < 0.0) rem = 0.0;
+    a.tc = dadd(a.tc, rem);
+    return rem;
+}
+
+// playback until x seconds of content have drained (x <= buffer); returns the wall time it takes
+__device__ __forceinline__ double live_play_content(Sess& s, double& buffer, LiveAcc& a, double x, const double L) {
+    double w = 0.0;
+    while (x > 0.0) {
+        const double v = live_speed(s);
+        const double room = dsub(L, s.play_len);
+        const bool finished = room <= x;
+        const double d = finished ? room : x;
+        const double dw = ddiv(d, v);
+        live_piece(s, buffer, a, d, dw, v);
+        w = dadd(w, dw);
+        if (finished) { s.play_id += 1; s.play_len = 0.0; x = dsub(x, d); }
+        else { s.play_len = dadd(s.play_len, d); x = 0.0; }
+    }
+    return w;
 }
 
 // ---- head of a step (SPEC §3.1): where does the download end? ----
@@ -270,18 +334,18 @@ __device__ __forceinline__ void head(const Sess& s, const double raw, Head& h, b
 
 // SPEC §7.1 pause gate (Simulator.py:143-145): wait for the live edge, then for room in the buffer; moves the trace
 // position by the idle time.  Runs before the head of a live step.
-struct LiveGate { double buffer, rebuf, idle, startup; };
+struct LiveGate { double buffer, rebuf, idle; LiveAcc a; };
 
 template <bool SMEM>
 __device__ __forceinline__ void live_gate(const EnvView& v, Sess& s, LiveGate& g) {
     const AbrParams& p = v.p;
-    g.buffer = s.buffer; g.startup = 0.0;
+    g.buffer = s.buffer;
+    g.a.startup = g.a.area = g.a.played = 0.0;
+    g.a.tc = s.t_now;
     const double w1 = max0(dsub(dmul((double)(s.chunk + 1), p.chunk_length), s.t_now));
-    g.rebuf = live_play(s, g.buffer, g.startup, w1);
+    g.rebuf = live_play_wall(s, g.buffer, g.a, w1, p.chunk_length);
     const double w2 = (s.started && g.buffer > p.max_buffer)
-                          ? (s.speed == 1.0 ? dsub(g.buffer, p.max_buffer) : ddiv(dsub(g.buffer, p.max_buffer), s.speed))
-                          : 0.0;
-    g.rebuf = dadd(g.rebuf, live_play(s, g.buffer, g.startup, w2));
+                          ? live_play_content(s, g.buffer, g.a, dsub(g.buffer, p.max_buffer), p.chunk_length) : 0.0;
     g.idle = dadd(w1, w2);
     if (g.idle > 0.0) {
         advance_trace(s.seg, s.phi, g.idle, s.I, s.T);
@@ -301,7 +365,7 @@ __device__ __forceinline__ bool step_tail(const EnvView& v, Sess& s, const Head&
     const AbrParams& p = v.p;
     r.reset_mpc = false;
     if (!FAST && s.done) {  // only reachable with auto_reset == 0
-        r.delay = r.sleep = r.rebuf = r.reward = r.thr = r.u = r.smooth = r.latency = r.startup = 0.0;
+        r.delay = r.sleep = r.rebuf = r.reward = r.thr = r.u = r.smooth = r.latency = r.startup = r.area = r.played = 0.0;
         r.buffer = s.buffer;
         r.eov = true;
         r.inert = true;
@@ -321,16 +385,17 @@ __device__ __forceinline__ bool step_tail(const EnvView& v, Sess& s, const Head&
     r.thr = want_thr ? ddiv(size, delay) : 0.0;
     double rebuf, buffer, sleep = 0.0;
     r.latency = 0.0;
-    r.startup = 0.0;
+    r.startup = r.area = r.played = 0.0;
     s.pos = h.target;
     if (LIVE) {   // 7.2
-        double live_buffer = g.buffer, live_startup = g.startup;
-        rebuf = dadd(g.rebuf, live_play(s, live_buffer, live_startup, delay));
+        double live_buffer = g.buffer;
+        LiveAcc a = g.a;
+        rebuf = dadd(g.rebuf, live_play_wall(s, live_buffer, a, delay, p.chunk_length));
         buffer = dadd(live_buffer, p.chunk_length);
         s.t_now = dadd(dadd(s.t_now, g.idle), delay);
         if (!s.started && buffer >= p.start_up_length) s.started = true;
         r.latency = dsub(s.t_now, s.play_time);
-        r.startup = live_startup;
+        r.startup = a.startup; r.area = a.area; r.played = a.played;
         sleep = g.idle;
     } else {
         // 3.2 buffer drain / rebuffer
@@ -363,7 +428,7 @@ __device__ __forceinline__ bool step_tail(const EnvView& v, Sess& s, const Head&
     if (r.eov) {
         if (FAST || p.auto_reset) {
             s.chunk = 0; s.buffer = 0.0; s.last_q = p.default_quality; s.hist_len = 0;
-            if (LIVE) { s.t_now = 0.0; s.play_time = 0.0; s.started = p.start_up_length <= 0.0; }
+            if (LIVE) { s.t_now = 0.0; s.play_time = 0.0; s.play_len = 0.0; s.play_id = 0; s.started = p.start_up_length <= 0.0; }
             r.reset_mpc = true;
         } else {
             s.done = true;
@@ -378,7 +443,8 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
                                           const bool want_thr) {
     r.walk_error = false;
     LiveGate g;
-    g.buffer = s.buffer; g.rebuf = g.idle = g.startup = 0.0;
+    g.buffer = s.buffer; g.rebuf = g.idle = 0.0;
+    g.a.startup = g.a.area = g.a.played = g.a.tc = 0.0;
     Head h;
     if (!FAST && s.done) {
         h.target = h.c_j = h.kx = 0.0; h.c_j1 = 1.0; h.j = 0;
@@ -521,6 +587,7 @@ abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* 
     v.trace_id[i] = w.tr; v.seg[i] = w.seg; v.phi[i] = w.phi; v.pos[i] = w.pos; v.buffer[i] = 0.0; v.chunk[i] = 0;
     v.last_q[i] = v.p.default_quality; v.done[i] = 0; v.hist_len[i] = 0; v.last_pred[i] = 0.0; v.err_len[i] = 0;
     v.t_now[i] = 0.0; v.play_time[i] = 0.0; v.started[i] = v.p.start_up_length <= 0.0 ? 1 : 0;
+    v.play_id[i] = 0; v.play_len[i] = 0.0;
 #pragma unroll
     for (int j = 0; j < ABR_NUM_ACC; ++j) v.acc[(size_t)j * v.cap + i] = 0.0;
 }
@@ -564,17 +631,18 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
                                              uint8_t* __restrict__ o_eov, OT* __restrict__ o_thr) {
     if (LIVE) {
         s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0;
-        s.speed = speed ? speed[i] : 1.0;
+        s.play_id = v.play_id[i]; s.play_len = v.play_len[i];
+        s.speed = speed ? speed + i : nullptr;   // [V][N] table: the speed of content chunk k is speed[k][i]
+        s.speed_stride = (size_t)v.n; s.V = v.V; s.bad_speed = false;
     }
     int q = q_in;
     bool bad = q < 0 || q >= v.A;
     if (bad) q = q < 0 ? 0 : v.A - 1;
-    if (LIVE && !(s.speed > 0.0)) { bad = true; s.speed = 1.0; }
     if (bad) atomicAdd(v.errors, 1ull);
     StepRes r;
-    const Lookup lk = lookup_tables<false>(s, v.A, v.V, s.chunk, q, s.last_q);
+    const Lookup lk = lookup_tables<false>(s, v.A, v.V, s.chunk, q, s.last_q, v.p.smooth_prev_ladder != 0);
     step_core<SMEM, FAST, LIVE>(v, s, q, lk, r, (!FAST && v.p.track_history) || o_thr != nullptr);
-    if (r.walk_error) atomicAdd(v.errors, 1ull);
+    if (r.walk_error || (LIVE && s.bad_speed)) atomicAdd(v.errors, 1ull);
     if (FAST) {
         v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.pos[i] = s.pos;
         v.buffer[i] = s.buffer;
@@ -585,7 +653,10 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
         if (!r.inert) {
             v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.pos[i] = s.pos;
             v.buffer[i] = s.buffer;
-            if (LIVE) { v.t_now[i] = s.t_now; v.play_time[i] = s.play_time; v.started[i] = s.started ? 1 : 0; }
+            if (LIVE) {
+                v.t_now[i] = s.t_now; v.play_time[i] = s.play_time; v.started[i] = s.started ? 1 : 0;
+                v.play_id[i] = s.play_id; v.play_len[i] = s.play_len;
+            }
             if (v.p.track_history) {
                 // ring slot of this sample = (hist_len before the step) mod K; after an auto-reset hist_len is 0
                 const int prev_len = r.reset_mpc ? 0 : s.hist_len - 1;
@@ -602,7 +673,10 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
                 a[5 * c] = dadd(a[5 * c], r.delay);
                 a[6 * c] = dadd(a[6 * c], 1.0);
                 if (r.eov) a[7 * c] = dadd(a[7 * c], 1.0);
-                if (LIVE) { a[8 * c] = dadd(a[8 * c], r.startup); a[9 * c] = dadd(a[9 * c], r.latency); }
+                if (LIVE) {
+                    a[8 * c] = dadd(a[8 * c], r.startup); a[9 * c] = dadd(a[9 * c], r.area);
+                    a[10 * c] = dadd(a[10 * c], r.played);
+                }
             }
         }
         if (o_delay) __stcs(o_delay + i, (OT)r.delay);
@@ -709,13 +783,15 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
 
 // Per-session QoE cost of Simulator.calculate_qoe (Simulator.py:83-86) from the accumulators:
 // rebuffer_weight * sum(rebuffer) + variance_weight * sum(|delta utility|), plus in live mode
-// startup_weight * start-up time + latency_weight * mean latency.
+// startup_weight * start-up time + latency_weight * average_latency, where the reference's average_latency is the
+// sum over the playing ticks of the instantaneous latency divided by the content played (Simulator.py:179-180: the
+// running mean is weighted by play_time), i.e. the latency integral per tick: area / (latency_tick * played).
 __device__ __forceinline__ double session_cost(const EnvView& v, const double rebuf, const double smooth,
-                                               const double steps, const double startup, const double latency) {
+                                               const double played, const double startup, const double area) {
     double c = dadd(dmul(v.p.rebuf_penalty, rebuf), dmul(v.p.smooth_penalty, smooth));
     if (v.p.live) {   // + sw*start_up_time + lw*average_latency (Simulator.py:85-86)
         c = dadd(c, dmul(v.p.startup_penalty, startup));
-        c = dadd(c, dmul(v.p.latency_penalty, steps > 0.0 ? ddiv(latency, steps) : 0.0));
+        c = dadd(c, dmul(v.p.latency_penalty, played > 0.0 ? ddiv(area, dmul(v.p.latency_tick, played)) : 0.0));
     }
     return c;
 }
@@ -755,16 +831,21 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     constexpr bool AHEAD = POLICY != ABR_POLICY_BBA && !LIVE;
     // the random policy is keyed by the caller's session index, whatever order the environment keeps the sessions in
     const unsigned long long gsession = (unsigned long long)(v.session_base + (v.perm ? __ldg(v.perm + i) : i));
-    double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_su = 0.0, a_lat = 0.0;
+    double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_su = 0.0, a_lat = 0.0, a_pl = 0.0;
     int n_steps = 0, n_eps = 0;
     bool flagged = false, reset_mpc = false;
     const uint32_t n = (uint32_t)v.n;
     const bool hist = !FAST && v.p.track_history != 0;
+    const bool prev_ladder = v.p.smooth_prev_ladder != 0;
     uint32_t packed = 0u;   // random policy: the eight actions of one Philox block, one per nibble
     if (LIVE) {
-        if (fresh) { s.t_now = 0.0; s.play_time = 0.0; s.started = v.p.start_up_length <= 0.0; }
-        else { s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0; }
-        s.speed = 1.0;
+        if (fresh) { s.t_now = 0.0; s.play_time = 0.0; s.play_len = 0.0; s.play_id = 0; s.started = v.p.start_up_length <= 0.0; }
+        else {
+            s.t_now = v.t_now[i]; s.play_time = v.play_time[i]; s.started = v.started[i] != 0;
+            s.play_id = v.play_id[i]; s.play_len = v.play_len[i];
+        }
+        s.speed = o.speed ? o.speed + i : nullptr;   // [V][N] table: the speed of content chunk k is speed[k][i]
+        s.speed_stride = (size_t)n; s.V = v.V; s.bad_speed = false;
     }
     // SPEC §4 action of step t; must be called with increasing t.  FIXED clamps t to the last row so that the
     // calls that run ahead of the final step stay inside the caller's table.
@@ -799,10 +880,11 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     uint32_t ix = (uint32_t)i;   // element index of (step t, session i) in the [steps][N] outputs (< 2^32, checked by the host)
     StepRes r;
     LiveGate g;
-    g.buffer = 0.0; g.rebuf = g.idle = g.startup = 0.0;
+    g.buffer = 0.0; g.rebuf = g.idle = 0.0;
+    g.a.startup = g.a.area = g.a.played = g.a.tc = 0.0;
     if (AHEAD) {
         int q0 = action_at(0);
-        Lookup lk0 = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q0, s.last_q);
+        Lookup lk0 = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q0, s.last_q, prev_ladder);
         int c1 = next_chunk(s.chunk);            // chunk index / previous quality step t+1 will see
         int lq1 = next_last_q(s.chunk, q0);
         Head h;
@@ -816,7 +898,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             // sits at the cap sleep after every chunk, and the lanes of a warp tend to do so together (same trace):
             // a warp that slept in the last step does not speculate (its head would be redone anyway).
             const int q1 = action_at(t + 1);
-            const Lookup lk1 = lookup_tables<SMEM>(s, v.A, v.V, c1, q1, lq1);
+            const Lookup lk1 = lookup_tables<SMEM>(s, v.A, v.V, c1, q1, lq1, prev_ladder);
             Head h1;
             bool ok1 = false;
             if (spec && (SMEM || s.M > 0)) ok1 = head_fast<SMEM>(s, dadd(h.target, lk1.size), h1);
@@ -861,13 +943,8 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         flagged |= r.walk_error;
     } else {
         for (int t = 0; t < steps; ++t) {
-            const size_t ixw = (size_t)t * n + i;
-            if (LIVE && o.speed) {
-                s.speed = __ldg(o.speed + ixw);
-                if (!(s.speed > 0.0)) { flagged = true; s.speed = 1.0; }
-            }
             const int q = action_at(t);
-            const Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q);
+            const Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q, prev_ladder);
             step_core<SMEM, FAST, LIVE>(v, s, q, lk, r, hist);
             flagged |= r.walk_error;
             if (NOOUT) {
@@ -888,7 +965,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             if (FAST || !r.inert) {
                 a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
                 a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
-                if (LIVE) { a_su = dadd(a_su, r.startup); a_lat = dadd(a_lat, r.latency); }
+                if (LIVE) { a_su = dadd(a_su, r.startup); a_lat = dadd(a_lat, r.area); a_pl = dadd(a_pl, r.played); }
                 n_steps += 1;
                 n_eps += r.eov ? 1 : 0;
                 if (r.reset_mpc) reset_mpc = true;   // an auto-reset also clears the robust-MPC predictor state
@@ -898,10 +975,13 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         }
     }
     const double a_steps = (double)n_steps, a_eps = (double)n_eps;   // exact: counts below 2^31
-    if (flagged) atomicAdd(v.errors, 1ull);
+    if (flagged || (LIVE && s.bad_speed)) atomicAdd(v.errors, 1ull);
     v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.pos[i] = s.pos;
     v.buffer[i] = s.buffer;
-    if (LIVE) { v.t_now[i] = s.t_now; v.play_time[i] = s.play_time; v.started[i] = s.started ? 1 : 0; }
+    if (LIVE) {
+        v.t_now[i] = s.t_now; v.play_time[i] = s.play_time; v.started[i] = s.started ? 1 : 0;
+        v.play_id[i] = s.play_id; v.play_len[i] = s.play_len;
+    }
     if (hist) v.hist_len[i] = s.hist_len;
     if (reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
     if (!FAST && s.done) v.done[i] = 1;
@@ -909,12 +989,15 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         if (!hist) v.hist_len[i] = 0;
         if (!reset_mpc) { v.last_pred[i] = 0.0; v.err_len[i] = 0; }
         if (FAST || !s.done) v.done[i] = 0;
-        if (!LIVE) { v.t_now[i] = 0.0; v.play_time[i] = 0.0; v.started[i] = v.p.start_up_length <= 0.0 ? 1 : 0; }
+        if (!LIVE) {
+            v.t_now[i] = 0.0; v.play_time[i] = 0.0; v.started[i] = v.p.start_up_length <= 0.0 ? 1 : 0;
+            v.play_id[i] = 0; v.play_len[i] = 0.0;
+        }
     }
     // accumulator read-modify-write: all loads first (one memory round trip instead of ten dependent ones)
     double* a = v.acc + i;
     const size_t c = v.cap;
-    const double add[ABR_NUM_ACC] = {a_rew, a_reb, a_u, a_sm, a_sl, a_dl, a_steps, a_eps, a_su, a_lat};
+    const double add[ABR_NUM_ACC] = {a_rew, a_reb, a_u, a_sm, a_sl, a_dl, a_steps, a_eps, a_su, a_lat, a_pl};
     double old[ABR_NUM_ACC];
 #pragma unroll
     for (int j = 0; j < ABR_NUM_ACC; ++j) old[j] = fresh ? 0.0 : __ldcg(a + j * c);
@@ -923,7 +1006,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         acc_new[j] = dadd(old[j], add[j]);
         a[j * c] = acc_new[j];
     }
-    if (o.out_cost) o.out_cost[i] = session_cost(v, acc_new[ABR_ACC_REBUF], acc_new[ABR_ACC_SMOOTH], acc_new[ABR_ACC_STEPS],
+    if (o.out_cost) o.out_cost[i] = session_cost(v, acc_new[ABR_ACC_REBUF], acc_new[ABR_ACC_SMOOTH], acc_new[ABR_ACC_PLAY],
                                                  acc_new[ABR_ACC_STARTUP], acc_new[ABR_ACC_LATENCY]);
 }
 
@@ -1093,7 +1176,7 @@ abr_qoe_cost_kernel(EnvView v, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.n) return;
     const size_t c = v.cap;
-    out[i] = session_cost(v, v.acc[ABR_ACC_REBUF * c + i], v.acc[ABR_ACC_SMOOTH * c + i], v.acc[ABR_ACC_STEPS * c + i],
+    out[i] = session_cost(v, v.acc[ABR_ACC_REBUF * c + i], v.acc[ABR_ACC_SMOOTH * c + i], v.acc[ABR_ACC_PLAY * c + i],
                           v.acc[ABR_ACC_STARTUP * c + i], v.acc[ABR_ACC_LATENCY * c + i]);
 }
 

@@ -225,6 +225,15 @@ class BatchedABREnv:
     def _empty(self, *shape, dtype=torch.float64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
+    def _speed_table(self, speed, n):
+        """[V, N] float64 device table from a [V, N] table or a per-session vector [N]."""
+        v = self._dev(speed, torch.float64)
+        if v.dim() == 1 and v.numel() == n:
+            v = v.unsqueeze(0).expand(self.V, n).contiguous()
+        if v.numel() != self.V * n:
+            raise ValueError(f"speed must be [V, N] = [{self.V}, {n}] (or [N]): the playback speed of each content chunk")
+        return v
+
     # -- SPEC §2 --
     # -- session order (sessions are independent, so the environment may keep them sorted by trace) --
     def sort_by_trace(self, trace_id) -> torch.Tensor:
@@ -284,8 +293,10 @@ class BatchedABREnv:
     def step(self, action, want_next_sizes=True, want_throughput=False, out=None, speed=None,
              want_latency=None, dtype=torch.float64) -> StepResult:
         """One chunk step for every session.  ``action``: int32 [N] on the device (or array-like).
-        Live mode (``live=1``, SPEC §7): ``speed`` is the playback speed per session (default 1.0), the result
-        carries ``latency`` and ``sleep`` is the idle time before the download.
+        Live mode (``live=1``, SPEC §7): ``speed`` is the playback-speed table [V, N] — ``speed[k, s]`` is the speed
+        at which session ``s`` plays content chunk ``k`` (the reference asks its speed controller once per played
+        chunk, ``Simulator.py:176-177``); a vector [N] means one speed per session for every chunk; default 1.0.
+        The result carries ``latency`` and ``sleep`` is the idle time before the download.
         ``dtype=torch.float32`` selects the optional fp32-output mode: the arithmetic and the state stay fp64, the
         outputs are rounded once to float (``abr_env_step_f32``)."""
         a = self._dev(action, torch.int32)
@@ -297,9 +308,7 @@ class BatchedABREnv:
         if speed is not None:
             if not live:
                 raise ValueError("speed is a live-mode action (create the environment with live=1)")
-            v = self._dev(speed, torch.float64)
-            if v.numel() != n:
-                raise ValueError("speed must have one entry per session")
+            v = self._speed_table(speed, n)
         if want_latency is None:
             want_latency = live
         if out is None:
@@ -320,7 +329,7 @@ class BatchedABREnv:
                                                                 "end_of_video", "actions"), out=None, speed=None,
                 dtype=torch.float64):
         """`steps` chunk steps in one fused launch.  Returns a dict of [steps, N] device tensors.  In live mode
-        (SPEC §7) ``speed`` is the playback-speed table [steps, N] (default 1.0) and "latency" may be wanted.
+        (SPEC §7) ``speed`` is the playback-speed table [V, N] of ``step`` (default 1.0) and "latency" may be wanted.
         ``dtype=torch.float32``: fp32-output mode (fp64 arithmetic, outputs rounded once; 21 B instead of 41 B of
         trajectory per chunk-step)."""
         pid = _policy_id(policy)
@@ -334,9 +343,9 @@ class BatchedABREnv:
                 raise ValueError("actions must be [steps, N]")
         v = None
         if speed is not None:
-            v = self._dev(speed, torch.float64)
-            if v.numel() != steps * n:
-                raise ValueError("speed must be [steps, N]")
+            if not self.params.live:
+                raise ValueError("speed is a live-mode action (create the environment with live=1)")
+            v = self._speed_table(speed, n)
         if out is None:
             out = {}
             for k in want:
@@ -417,7 +426,8 @@ class BatchedABREnv:
 
     # -- SPEC §6 --
     def stats(self) -> torch.Tensor:
-        """[Σreward, Σrebuffer, Σutility, Σsmooth, Σsleep, Σdelay, steps, episodes, Σstartup, Σlatency]."""
+        """[Σreward, Σrebuffer, Σutility, Σsmooth, Σsleep, Σdelay, steps, episodes, Σstartup, Σlatency integral,
+        Σcontent played] (the last three are live-mode sums, SPEC §7)."""
         out = torch.empty(NUM_STATS, dtype=torch.float64, device=self.device)
         with self._on:
             _lib.check(self._lib.abr_stats_partial(self._h, _ptr(out), _stream()))
@@ -447,8 +457,8 @@ class BatchedABREnv:
         return t[:self.n]
 
     def session_acc(self) -> torch.Tensor:
-        """[10, N] per-session sums (rows: reward, rebuffer, utility, smooth, sleep, delay, steps, episodes,
-        startup, latency)."""
+        """[NUM_ACC, N] per-session sums (rows: reward, rebuffer, utility, smooth, sleep, delay, steps, episodes,
+        startup, latency integral over the playing time, content played)."""
         return self.state("acc")
 
     def qoe_cost(self) -> torch.Tensor:
@@ -477,6 +487,14 @@ class BatchedABREnv:
         n = tid.numel() if isinstance(tid, torch.Tensor) else tid.size
         off = None if start_offset is None else _host(start_offset, np.float64, torch.float64)
         a_in = None if actions is None else _host(actions, np.int32, torch.int32)
+        size = lambda x: x.numel() if isinstance(x, torch.Tensor) else x.size
+        if off is not None and size(off) != n:
+            raise ValueError("start_offset must have one entry per session")
+        if pid == POLICY_FIXED:
+            if a_in is None:
+                raise ValueError("policy 'fixed' needs an actions table [steps, N]")
+            if size(a_in) != steps * n:
+                raise ValueError("actions must be [steps, N]")
         out = {} if out is None else out
         if want_acc and "acc" not in out:
             out["acc"] = np.empty((NUM_ACC, n))

@@ -5,8 +5,16 @@ keep their reference signatures.  ``run()`` plays one session (or ``run_batch`` 
 (SPEC.md §3) and returns the QoE *cost* of ``calculate_qoe`` (``Simulator.py:79-86``):
 ``rw·rebuffer_time + vw·Σ|Δbitrate| + sw·start_up_time + lw·average_latency``.  When the MPD carries a
 ``start_up_length`` (the reference's 5-argument ``MPD`` / ``set_mpd``) the session runs in live mode (SPEC.md §7:
-live-edge availability gate, start-up latch, playback speed from the speed controller, latency); with
-``start_up_length=None`` it is the on-demand environment of SPEC.md §3 and the last two terms are 0.
+live-edge availability gate, start-up latch, playback speed from the speed controller — asked once per *played*
+chunk, ``Simulator.py:176-177`` — and the reference's ``average_latency``); with ``start_up_length=None`` it is the
+on-demand environment of SPEC.md §3 and the last two terms are 0.
+
+Defaults follow the reference, not the north-star constants of ``BatchedABREnv``: no RTT, no packet-payload factor
+(``downloaded_size += bandwidth*dt``, ``Simulator.py:160``), a tick-sized (0.01 s, ``Simulator.py:133``) sleep
+quantum, cost in bitrate units with each chunk's own ladder in the variance term (``Simulator.py:81-82``).  In live
+mode the façade is the closed form of the reference's loop — ``tests/`` check it against that loop's own output
+(``tests/golden/sim_ref_tick_golden.json``); keyword arguments of ``Simulator(...)`` override any of this
+(e.g. ``Simulator(ctrl, None, rtt=0.08, payload=0.95, sleep_quantum=0.5)`` for the north-star environment).
 
 Controllers
 -----------
@@ -96,7 +104,10 @@ class Simulator:
     def _make_env(self, n_sessions, **extra):
         if self.mpd is None or self.network_info is None or self.qoe_metric is None:
             raise RuntimeError("set_qoe_metric, set_network_info and set_mpd must be called before run()")
-        kw = dict(utility_scale=1.0, default_quality=-1, auto_reset=0)   # cost is in bitrate units, first chunk free
+        # the reference's environment (see the module docstring): cost in bitrate units, first chunk free, no RTT, no
+        # payload factor, continuous pause (one tick), variance over each chunk's own ladder
+        kw = dict(utility_scale=1.0, default_quality=-1, auto_reset=0, rtt=0.0, payload=1.0, sleep_quantum=0.01,
+                  latency_tick=0.01, smooth_prev_ladder=1)
         kw.update(self.params)
         kw.update(extra)
         return BatchedABREnv.from_objects(self.network_info, self.mpd, self.qoe_metric, max_sessions=n_sessions, **kw)
@@ -152,18 +163,17 @@ class Simulator:
             env = self._make_env(n_sessions, track_history=1, **extra, **ctrl.extra_params)
             env.reset(tid, start_offset, session_base)
             mode = "robust" if ctrl.mode == MPC_ROBUST else "reference"
+            speed = self._speed_table(n_sessions, V)
             for _ in range(V):
                 act = env.mpc_decide(ctrl.horizon, mode)
-                env.step(act, want_next_sizes=False, speed=self._speeds(n_sessions))
+                env.step(act, want_next_sizes=False, speed=speed)
         elif isinstance(ctrl, (RandomPolicy, BufferBasedPolicy, FixedPolicy)) or ctrl is None:
             # built-in policies: one fused live episode (abr_env_rollout_fused_live), speed table from the controller
             if isinstance(ctrl, BufferBasedPolicy):
                 extra.update(bba_reservoir=ctrl.reservoir, bba_cushion=ctrl.cushion)
             env = self._make_env(n_sessions, **extra)
             env.reset(tid, start_offset, session_base)
-            speed = None
-            if self.speed_controller is not None:
-                speed = np.stack([self._speeds(n_sessions) for _ in range(V)])
+            speed = self._speed_table(n_sessions, V)
             policy = "random" if isinstance(ctrl, RandomPolicy) else "fixed" if isinstance(ctrl, FixedPolicy) else "bba"
             env.rollout(policy, V, seed=getattr(ctrl, "seed", 0), actions=getattr(ctrl, "actions", None), speed=speed,
                         want=())
@@ -174,10 +184,22 @@ class Simulator:
         self.last_run = dict(zip(ACC_NAMES, acc))
         return env.qoe_cost().cpu().numpy()
 
-    def _speeds(self, n_sessions):
+    def _speed_table(self, n_sessions, V):
+        """[V, N] playback speeds: ``get_next_speed()`` is called once per content chunk of every session, in playing
+        order (the k-th call of a session's run is the speed of its k-th played chunk, Simulator.py:176-177).  The
+        controller protocol takes no arguments, so its answers cannot depend on the session's state and may be
+        drawn before the run."""
         if self.speed_controller is None:
             return None
-        return np.array([float(self.speed_controller.get_next_speed()) for _ in range(n_sessions)])
+        table = np.empty((V, n_sessions))
+        for s in range(n_sessions):
+            for k in range(V):
+                table[k, s] = float(self.speed_controller.get_next_speed())
+        return torch.from_numpy(table).to(self._device())
+
+    @staticmethod
+    def _device():
+        return torch.device("cuda", torch.cuda.current_device())
 
     def _host_policy_actions(self, ctrl, k, n_sessions, buf, A, rng, session_base):
         """Built-in policy markers evaluated on the host (used in live mode, where the fused episode does not apply)."""
@@ -198,6 +220,7 @@ class Simulator:
         marker = isinstance(ctrl, (RandomPolicy, BufferBasedPolicy, FixedPolicy))
         live = bool(env.params.live)
         env.reset(tid, start_offset, session_base)
+        speed = self._speed_table(n_sessions, V) if live else None
         prev_q = [[] for _ in range(n_sessions)]
         prev_bw = [[] for _ in range(n_sessions)]
         buf = np.zeros(n_sessions)
@@ -209,7 +232,7 @@ class Simulator:
                 acts = np.array([ctrl.get_next_bitrate(k, prev_q[s], prev_bw[s], float(buf[s]))
                                  for s in range(n_sessions)], dtype=np.int32)
             r = env.step(torch.from_numpy(acts), want_next_sizes=False, want_throughput=True,
-                         speed=self._speeds(n_sessions) if live else None)
+                         speed=speed)
             buf = r.buffer.cpu().numpy()
             if not marker:
                 thr = r.throughput.cpu().numpy()

@@ -29,11 +29,11 @@ N_TRACES, T_TRACE = 1024, 2048
 SEED = 7
 GROUP = 64                          # consecutive sessions per trace (one 64-thread block = one trace)
 BYTES_PER_STEP = 5 * 8 + 1          # delay, sleep, buffer, rebuf, reward (f64) + end_of_video (u8)
-BYTES_PER_SESSION = 40 + 36 + 160   # state load + state store + read-modify-write of the 10 accumulators, once per episode
+BYTES_PER_SESSION = 40 + 36 + 176   # state load + state store + read-modify-write of the 11 accumulators, once per episode
 # abr_env_run (reset fused into the episode kernel): 12 B of trace id + start offset in, the whole reset state out
-# (36 B of position + 38 B that only a reset writes: trace_id, hist_len, last_pred, err_len, done, t_now, play_time,
-# started) and the 10 accumulators written without being read
-BYTES_PER_SESSION_RUN = 12 + 36 + 38 + 80
+# (36 B of position + 50 B that only a reset writes: trace_id, hist_len, last_pred, err_len, done, t_now, play_time,
+# started, play_id, play_len) and the 11 accumulators written without being read
+BYTES_PER_SESSION_RUN = 12 + 36 + 50 + 88
 
 
 def parse():

@@ -41,14 +41,17 @@ enum { ABR_MPC_TRUNCATE = 1,        /* mode 0: k+H > V truncates the horizon ins
 
 /* rows of the accumulator table / entries of the statistics vector (SPEC §6) */
 enum { ABR_ACC_REWARD = 0, ABR_ACC_REBUF = 1, ABR_ACC_UTILITY = 2, ABR_ACC_SMOOTH = 3, ABR_ACC_SLEEP = 4,
-       ABR_ACC_DELAY = 5, ABR_ACC_STEPS = 6, ABR_ACC_EPISODES = 7, ABR_ACC_STARTUP = 8, ABR_ACC_LATENCY = 9,
-       ABR_NUM_ACC = 10, ABR_NUM_STATS = 10 };
+       ABR_ACC_DELAY = 5, ABR_ACC_STEPS = 6, ABR_ACC_EPISODES = 7, ABR_ACC_STARTUP = 8,
+       ABR_ACC_LATENCY = 9, /* live mode: integral of the latency over the time spent playing (SPEC §7) */
+       ABR_ACC_PLAY = 10,   /* live mode: content played */
+       ABR_NUM_ACC = 11, ABR_NUM_STATS = 11 };
 
 /* session-state fields exposed by abr_env_state_ptr (SPEC §1).  All arrays have max_sessions elements except
  * BW_HIST / ERR_RING ([hist_k][max_sessions]) and ACC ([ABR_NUM_ACC][max_sessions]). */
 enum { ABR_F_SEG = 0, ABR_F_CHUNK = 1, ABR_F_LAST_Q = 2, ABR_F_TRACE_ID = 3, ABR_F_HIST_LEN = 4, ABR_F_DONE = 5,
        ABR_F_ERR_LEN = 6, ABR_F_PHASE = 10, ABR_F_POS = 18, ABR_F_BUFFER = 11, ABR_F_BW_HIST = 12, ABR_F_LAST_PRED = 13,
-       ABR_F_ERR_RING = 14, ABR_F_ACC = 15, ABR_F_T_NOW = 16, ABR_F_PLAY_TIME = 17, ABR_F_STARTED = 7, ABR_F_SIZES = 20, ABR_F_UTILITY = 21, ABR_F_TRACE_BW = 22 };
+       ABR_F_ERR_RING = 14, ABR_F_ACC = 15, ABR_F_T_NOW = 16, ABR_F_PLAY_TIME = 17, ABR_F_STARTED = 7,
+       ABR_F_PLAY_ID = 8, ABR_F_PLAY_LEN = 19, ABR_F_SIZES = 20, ABR_F_UTILITY = 21, ABR_F_TRACE_BW = 22 };
 
 /* Replaces the attribute bags MPD / QOEMetric (Simulator.py:11-24, mpc_test.py:18-29) plus the
  * north-star constants (SPEC §1). */
@@ -65,14 +68,17 @@ typedef struct AbrParams {
     double start_up_length; /* live mode: buffer that ends the start-up phase, MPD.start_up_length, Simulator.py:12,201-202 */
     double startup_penalty; /* QOEMetric.startup_weight, Simulator.py:23 (session cost only) */
     double latency_penalty; /* QOEMetric.latency_weight, Simulator.py:24 (per-step reward and session cost) */
+    double latency_tick;    /* live mode: the reference's tick (Simulator.py:133): its average_latency is the latency integral
+                               over the playing time divided by (tick * content played), Simulator.py:179-180 */
     int32_t utility_mode;   /* 0 linear, 1 log(bitrate / top bitrate) (mpc.py:99-102) */
     int32_t default_quality;
     int32_t auto_reset;     /* 1: a session restarts at chunk 0 after its last chunk */
     int32_t hist_k;         /* capacity of the throughput-history ring (robust-MPC window) */
     int32_t track_history;  /* 1: abr_env_step / rollout push size/delay into the ring */
     int32_t track_acc;      /* 1: abr_env_step adds into the per-session accumulators */
-    int32_t live;           /* 1: live-streaming semantics of SPEC §7 (per-step kernel only) */
-    int32_t reserved2;
+    int32_t live;           /* 1: live-streaming semantics of SPEC §7 */
+    int32_t smooth_prev_ladder; /* smoothness term |U[k][q_k] - U[k'][q_{k-1}]|: 0: k' = k (the current chunk's ladder,
+                               mpc.py:148-149); 1: k' = k-1 (each chunk's own ladder, Simulator.calculate_qoe, Simulator.py:81-82) */
 } AbrParams;
 
 typedef struct AbrEnv AbrEnv;
@@ -114,9 +120,12 @@ int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_s
 int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
                  double* d_rebuf, double* d_reward, double* d_next_sizes /*[N][A]*/, uint8_t* d_end_of_video,
                  double* d_throughput, void* stream);
-/* SPEC §7 (live = 1): like abr_env_step with the playback speed per session (d_speed, nullable = 1.0) as a second
- * action (speed_controller.get_next_speed, Simulator.py:177) and the latency output; d_sleep receives the idle time
- * before the download.  With live = 0 it behaves like abr_env_step and writes 0 latency. */
+/* SPEC §7 (live = 1): like abr_env_step with the playback speeds as a second action and the latency output; d_sleep
+ * receives the idle time before the download.  d_speed is a [V][N] table (nullable = 1.0): d_speed[k][s] is the speed
+ * at which session s plays content chunk k — the reference asks its speed controller once per PLAYED chunk
+ * (speed_controller.get_next_speed(), Simulator.py:176-177), so playback during one download may run at several
+ * speeds; a caller that decides step by step rewrites the rows of the chunks not yet played between two calls.
+ * With live = 0 it behaves like abr_env_step and writes 0 latency. */
 int abr_env_step_live(AbrEnv* env, const int32_t* d_action, const double* d_speed, double* d_delay, double* d_sleep,
                       double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,
                       double* d_next_sizes /*[N][A]*/, uint8_t* d_end_of_video, double* d_throughput, void* stream);
@@ -125,11 +134,10 @@ int abr_env_step_live(AbrEnv* env, const int32_t* d_action, const double* d_spee
 int abr_env_rollout_fused(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                           double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward,
                           uint8_t* d_end_of_video, int32_t* d_actions_out, void* stream);
-/* The same episode with the live-streaming outputs (SPEC §7, live = 1): d_speed is the playback speed of every
- * session at every step ([steps][N], nullable = 1.0; speed_controller.get_next_speed, Simulator.py:177), d_latency
- * the per-step latency ([steps][N], nullable), d_sleep the idle time before each download.  With live = 0 it is
- * abr_env_rollout_fused and both extra pointers must be NULL; abr_env_rollout_fused on a live environment plays
- * every session at speed 1. */
+/* The same episode with the live-streaming outputs (SPEC §7, live = 1): d_speed is the [V][N] playback-speed table
+ * of abr_env_step_live (nullable = 1.0), d_latency the per-step latency ([steps][N], nullable), d_sleep the idle time
+ * before each download.  With live = 0 it is abr_env_rollout_fused and both extra pointers must be NULL;
+ * abr_env_rollout_fused on a live environment plays every session at speed 1. */
 int abr_env_rollout_fused_live(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                                const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer,
                                double* d_rebuf, double* d_reward, double* d_latency, uint8_t* d_end_of_video,

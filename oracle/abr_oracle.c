@@ -21,9 +21,10 @@ struct OrcEnv {
     /* session state, SoA (SPEC §1) */
     int32_t *seg, *chunk, *last_q, *trace_id, *hist_len, *err_len;
     double *phi /* fraction of segment seg consumed */, *pos /* the same position in data coordinates, SPEC 3.1 */, *buffer, *bw_hist /* [N][K] ring */, *last_pred, *err_ring /* [N][K] */;
-    double *t_now, *play_time;   /* live mode, SPEC §7 */
+    double *t_now, *play_time, *play_len;   /* live mode, SPEC §7 */
+    int32_t* play_id;
     uint8_t *done, *started;
-    int errors;
+    int errors, bad_speed;
     uint32_t step_base;   /* fused-episode steps since the last reset (SPEC §4: step_index of the random policy) */
 };
 
@@ -90,6 +91,7 @@ OrcEnv* orc_env_create(const double* trace_bw, const int32_t* trace_len, const d
     e->done = (uint8_t*)calloc(N, 1);
     e->started = (uint8_t*)calloc(N, 1);
     e->t_now = (double*)calloc(N, 8); e->play_time = (double*)calloc(N, 8);
+    e->play_len = (double*)calloc(N, 8); e->play_id = (int32_t*)calloc(N, 4);
     return e;
 }
 
@@ -99,7 +101,7 @@ void orc_env_destroy(OrcEnv* e) {
     free(e->trace_bw); free(e->trace_len); free(e->trace_interval); free(e->sizes); free(e->bitrates); free(e->util);
     free(e->seg); free(e->chunk); free(e->last_q); free(e->trace_id); free(e->hist_len); free(e->err_len);
     free(e->phi); free(e->pos); free(e->buffer); free(e->last_pred); free(e->bw_hist); free(e->err_ring); free(e->done);
-    free(e->started); free(e->t_now); free(e->play_time);
+    free(e->started); free(e->t_now); free(e->play_time); free(e->play_len); free(e->play_id);
     free(e);
 }
 
@@ -109,7 +111,7 @@ const void* orc_env_field(OrcEnv* e, int f) {
         case 4: return e->hist_len; case 5: return e->done; case 6: return e->err_len;
         case 10: return e->phi; case 11: return e->buffer; case 12: return e->bw_hist; case 13: return e->last_pred;
         case 14: return e->err_ring; case 15: return e->util; case 16: return e->t_now; case 17: return e->play_time;
-        case 7: return e->started; case 18: return e->pos;
+        case 7: return e->started; case 18: return e->pos; case 8: return e->play_id; case 19: return e->play_len;
     }
     return 0;
 }
@@ -133,21 +135,79 @@ void orc_env_reset(OrcEnv* e, const int32_t* trace_id, const double* start_offse
         e->buffer[s] = 0.0; e->chunk[s] = 0; e->last_q[s] = e->p.default_quality; e->done[s] = 0;
         e->hist_len[s] = 0; e->last_pred[s] = 0.0; e->err_len[s] = 0;
         e->t_now[s] = 0.0; e->play_time[s] = 0.0; e->started[s] = e->p.start_up_length <= 0.0;
+        e->play_id[s] = 0; e->play_len[s] = 0.0;
     }
 }
 
-typedef struct StepOut { double delay, sleep, buffer, rebuf, reward, thr, u, smooth, latency, startup; uint8_t eov; int inert; } StepOut;
+typedef struct StepOut { double delay, sleep, buffer, rebuf, reward, thr, u, smooth, latency, startup, area, played; uint8_t eov; int inert; } StepOut;
 
-/* SPEC §3 for one session */
-/* SPEC §7 play(dt): playback during an interval; returns the stall time */
-static double play(OrcEnv* e, int s, double dt, double v, double* buffer, double* startup) {
-    if (!e->started[s]) { *startup = *startup + dt; return 0.0; }
-    double need = v * dt, drained, stall;
-    if (*buffer >= need) { drained = need; stall = 0.0; }
-    else { drained = *buffer; stall = dt - *buffer / v; }
-    *buffer = *buffer - drained;
-    e->play_time[s] = e->play_time[s] + drained;
-    return stall;
+/* ---- SPEC §7 playback model: closed form of the reference's playback block, Simulator.py:174-187 ---- */
+typedef struct LiveAcc { double startup, area, played, tc; } LiveAcc;   /* tc: wall clock inside the step */
+
+/* speed of the content chunk session s is playing: speed[k][s] of the [V][N] table (Simulator.py:176-177: the speed
+ * controller is asked when a chunk starts to play); a non-positive or NaN entry counts as an error and plays at 1 */
+static double live_speed(OrcEnv* e, int s, const double* speed) {
+    if (!speed) return 1.0;
+    int k = e->play_id[s] < e->V ? e->play_id[s] : e->V - 1;
+    double v = speed[(size_t)k * e->N + s];
+    if (!(v > 0.0)) { e->bad_speed = 1; v = 1.0; }
+    return v;
+}
+
+/* one stretch: d seconds of content in dw seconds of wall time at speed v; the latency (wall clock - content
+ * played) changes at the rate 1 - v inside the stretch, area integrates it (Simulator.py:179-180) */
+static void live_piece(OrcEnv* e, int s, double* buffer, LiveAcc* a, double d, double dw, double v) {
+    a->area = a->area + ((a->tc - e->play_time[s]) * dw + ((1.0 - v) * dw) * (dw * 0.5));
+    e->play_time[s] = e->play_time[s] + d;
+    *buffer = *buffer - d;
+    a->tc = a->tc + dw;
+    a->played = a->played + d;
+}
+
+/* SPEC §7 play_wall(dt): playback during dt seconds of wall time; returns the stall time */
+static double play_wall(OrcEnv* e, int s, const double* speed, double* buffer, LiveAcc* a, double dt) {
+    const double L = e->p.chunk_length;
+    if (!e->started[s]) { a->startup = a->startup + dt; a->tc = a->tc + dt; return 0.0; }
+    double rem = dt;
+    while (rem > 0.0 && *buffer > 0.0) {
+        double v = live_speed(e, s, speed);
+        double room = L - e->play_len[s];
+        double can = room < *buffer ? room : *buffer;
+        double need = v * rem;
+        if (need < can) {
+            live_piece(e, s, buffer, a, need, rem, v);
+            e->play_len[s] = e->play_len[s] + need;
+            rem = 0.0;
+        } else {
+            double dw = can / v;
+            int finished = room <= *buffer;          /* the chunk ends before the buffer does */
+            live_piece(e, s, buffer, a, can, dw, v);
+            rem = rem - dw;
+            if (finished) { e->play_id[s] += 1; e->play_len[s] = 0.0; }
+            else e->play_len[s] = e->play_len[s] + can;
+        }
+    }
+    if (rem < 0.0) rem = 0.0;
+    a->tc = a->tc + rem;
+    return rem;
+}
+
+/* SPEC §7 play_content(x): playback until x seconds of content have drained (x <= buffer); returns the wall time */
+static double play_content(OrcEnv* e, int s, const double* speed, double* buffer, LiveAcc* a, double x) {
+    const double L = e->p.chunk_length;
+    double w = 0.0;
+    while (x > 0.0) {
+        double v = live_speed(e, s, speed);
+        double room = L - e->play_len[s];
+        int finished = room <= x;
+        double d = finished ? room : x;
+        double dw = d / v;
+        live_piece(e, s, buffer, a, d, dw, v);
+        w = w + dw;
+        if (finished) { e->play_id[s] += 1; e->play_len[s] = 0.0; x = x - d; }
+        else { e->play_len[s] = e->play_len[s] + d; x = 0.0; }
+    }
+    return w;
 }
 
 static void advance_trace(int* seg, double* phi, double dt, double I, int T) {   /* SPEC §3.3 */
@@ -157,7 +217,8 @@ static void advance_trace(int* seg, double* phi, double dt, double I, int T) {  
     *seg = (int)((*seg + (int64_t)fmod(n, (double)T)) % T);
 }
 
-static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
+/* SPEC §3 (and §7 when live = 1) for one session; speed: [V][N] playback-speed table or NULL */
+static void step_one(OrcEnv* e, int s, int q, const double* speed, StepOut* o) {
     const OrcParams* p = &e->p;
     memset(o, 0, sizeof(*o));
     if (e->done[s]) { o->eov = 1; o->buffer = e->buffer[s]; o->inert = 1; return; }
@@ -169,13 +230,14 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     const double size = e->sizes[chunk * e->A + q];
     const double* C = e->cum + (size_t)tr * (e->T_max + 1);
     const int live = p->live != 0;
-    double idle = 0.0, rebuf = 0.0, startup = 0.0, latency = 0.0;
+    double idle = 0.0, rebuf = 0.0, latency = 0.0;
+    LiveAcc a = {0.0, 0.0, 0.0, e->t_now[s]};
+    e->bad_speed = 0;
     if (live) {   /* 7.1 pause gate */
         double w1 = (double)(chunk + 1) * p->chunk_length - e->t_now[s];
         w1 = max0(w1);
-        rebuf = play(e, s, w1, v, &buffer, &startup);
-        double w2 = (e->started[s] && buffer > p->max_buffer) ? (buffer - p->max_buffer) / v : 0.0;
-        rebuf = rebuf + play(e, s, w2, v, &buffer, &startup);
+        rebuf = play_wall(e, s, speed, &buffer, &a, w1);
+        double w2 = (e->started[s] && buffer > p->max_buffer) ? play_content(e, s, speed, &buffer, &a, buffer - p->max_buffer) : 0.0;
         idle = w1 + w2;
         if (idle > 0.0) { advance_trace(&seg, &phi, idle, I, T); pos = C[seg] + (C[seg + 1] - C[seg]) * phi; }
     }
@@ -204,7 +266,7 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     double thr = size / delay;
     double sleep = 0.0;
     if (live) {   /* 7.2 */
-        rebuf = rebuf + play(e, s, delay, v, &buffer, &startup);
+        rebuf = rebuf + play_wall(e, s, speed, &buffer, &a, delay);
         buffer = buffer + p->chunk_length;
         e->t_now[s] = (e->t_now[s] + idle) + delay;
         if (!e->started[s] && buffer >= p->start_up_length) e->started[s] = 1;
@@ -225,7 +287,10 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     /* 3.4 */
     const double u = e->util[chunk * e->A + q];
     const int lq = e->last_q[s];
-    double smooth = (lq >= 0) ? fabs(u - e->util[chunk * e->A + lq]) : 0.0;
+    /* previous index in the current chunk's ladder (mpc.py:148-149) or, smooth_prev_ladder = 1, in the previous chunk's
+     * own ladder (Simulator.calculate_qoe, Simulator.py:81-82) */
+    const int prow = (p->smooth_prev_ladder && chunk > 0) ? chunk - 1 : chunk;
+    double smooth = (lq >= 0) ? fabs(u - e->util[prow * e->A + lq]) : 0.0;
     double reward = (u - p->rebuf_penalty * rebuf) - p->smooth_penalty * smooth;
     if (live) reward = reward - p->latency_penalty * latency;
     /* history ring */
@@ -236,13 +301,15 @@ static void step_one(OrcEnv* e, int s, int q, double v, StepOut* o) {
     /* 3.5 */
     chunk += 1;
     o->delay = delay; o->sleep = sleep; o->buffer = buffer; o->rebuf = rebuf; o->reward = reward;
-    o->thr = thr; o->u = u; o->smooth = smooth; o->latency = latency; o->startup = startup;
+    o->thr = thr; o->u = u; o->smooth = smooth; o->latency = latency; o->startup = a.startup; o->area = a.area; o->played = a.played;
+    if (live && e->bad_speed) e->errors++;
     o->eov = (chunk >= e->V);
     e->last_q[s] = q;
     if (o->eov && p->auto_reset) {
         chunk = 0; buffer = 0.0; e->last_q[s] = p->default_quality;
         e->hist_len[s] = 0; e->last_pred[s] = 0.0; e->err_len[s] = 0;
         e->t_now[s] = 0.0; e->play_time[s] = 0.0; e->started[s] = p->start_up_length <= 0.0;
+        e->play_id[s] = 0; e->play_len[s] = 0.0;
     } else if (o->eov) {
         e->done[s] = 1;
     }
@@ -255,7 +322,7 @@ void orc_env_step_live(OrcEnv* e, const int32_t* action, const double* speed, do
     const size_t N = (size_t)e->N;
     for (int s = 0; s < e->N; ++s) {
         StepOut o;
-        step_one(e, s, action[s], speed ? speed[s] : 1.0, &o);
+        step_one(e, s, action[s], speed, &o);
         if (delay) delay[s] = o.delay;
         if (sleep) sleep[s] = o.sleep;
         if (buffer) buffer[s] = o.buffer;
@@ -271,7 +338,7 @@ void orc_env_step_live(OrcEnv* e, const int32_t* action, const double* speed, do
             acc[0 * N + s] += o.reward; acc[1 * N + s] += o.rebuf; acc[2 * N + s] += o.u; acc[3 * N + s] += o.smooth;
             acc[4 * N + s] += o.sleep; acc[5 * N + s] += o.delay; acc[6 * N + s] += 1.0;
             if (o.eov) acc[7 * N + s] += 1.0;
-            acc[8 * N + s] += o.startup; acc[9 * N + s] += o.latency;
+            acc[8 * N + s] += o.startup; acc[9 * N + s] += o.area; acc[10 * N + s] += o.played;
         }
     }
 }
@@ -305,17 +372,17 @@ static int policy_action(OrcEnv* e, int s, int policy, uint64_t seed, int64_t se
 }
 
 void orc_env_rollout_live(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,
-                          const int32_t* actions_in, const double* speed /*[steps][N] or NULL*/, double* delay,
+                          const int32_t* actions_in, const double* speed /*[V][N] or NULL*/, double* delay,
                           double* sleep, double* buffer, double* rebuf, double* reward, double* latency, uint8_t* eov,
                           int32_t* actions_out, double* acc) {
     const int N = e->N;
     for (int s = 0; s < N; ++s) {
-        double a_rew = 0, a_reb = 0, a_u = 0, a_sm = 0, a_sl = 0, a_dl = 0, a_steps = 0, a_eps = 0, a_su = 0, a_lat = 0;
+        double a_rew = 0, a_reb = 0, a_u = 0, a_sm = 0, a_sl = 0, a_dl = 0, a_steps = 0, a_eps = 0, a_su = 0, a_lat = 0, a_pl = 0;
         for (int t = 0; t < steps; ++t) {
             int q = policy_action(e, s, policy, seed, session_base, t, actions_in);
             StepOut o;
             size_t ix = (size_t)t * N + s;
-            step_one(e, s, q, speed ? speed[ix] : 1.0, &o);
+            step_one(e, s, q, speed, &o);
             if (delay) delay[ix] = o.delay;
             if (sleep) sleep[ix] = o.sleep;
             if (buffer) buffer[ix] = o.buffer;
@@ -327,7 +394,7 @@ void orc_env_rollout_live(OrcEnv* e, int policy, uint64_t seed, int64_t session_
             if (!o.inert) {
                 a_rew = a_rew + o.reward; a_reb = a_reb + o.rebuf; a_u = a_u + o.u;
                 a_sm = a_sm + o.smooth; a_sl = a_sl + o.sleep; a_dl = a_dl + o.delay;
-                a_su = a_su + o.startup; a_lat = a_lat + o.latency;
+                a_su = a_su + o.startup; a_lat = a_lat + o.area; a_pl = a_pl + o.played;
                 a_steps += 1.0; if (o.eov) a_eps += 1.0;
             }
         }
@@ -335,7 +402,7 @@ void orc_env_rollout_live(OrcEnv* e, int policy, uint64_t seed, int64_t session_
             acc[0 * (size_t)N + s] = a_rew; acc[1 * (size_t)N + s] = a_reb; acc[2 * (size_t)N + s] = a_u;
             acc[3 * (size_t)N + s] = a_sm; acc[4 * (size_t)N + s] = a_sl; acc[5 * (size_t)N + s] = a_dl;
             acc[6 * (size_t)N + s] = a_steps; acc[7 * (size_t)N + s] = a_eps;
-            acc[8 * (size_t)N + s] = a_su; acc[9 * (size_t)N + s] = a_lat;   /* 0 outside live mode */
+            acc[8 * (size_t)N + s] = a_su; acc[9 * (size_t)N + s] = a_lat; acc[10 * (size_t)N + s] = a_pl;   /* 0 outside live mode */
         }
     }
     e->step_base += (uint32_t)(steps > 0 ? steps : 0);

@@ -23,13 +23,13 @@ typedef struct OrcParams {          /* same field order as AbrParams in include/
     double chunk_length, max_buffer, rtt, payload, sleep_quantum;
     double rebuf_penalty, smooth_penalty, utility_scale;
     double bba_reservoir, bba_cushion;
-    double start_up_length, startup_penalty, latency_penalty;      /* live mode, SPEC §7 */
+    double start_up_length, startup_penalty, latency_penalty, latency_tick;      /* live mode, SPEC §7 */
     int32_t utility_mode, default_quality, auto_reset, hist_k;
-    int32_t track_history, reserved0, live, reserved2;
+    int32_t track_history, reserved0, live, smooth_prev_ladder;
 } OrcParams;
 
 enum { ORC_POLICY_FIXED = 0, ORC_POLICY_RANDOM = 1, ORC_POLICY_BBA = 2 };
-enum { ORC_NUM_STATS = 10, ORC_NUM_ACC = 10 };  /* reward, rebuf, u, smooth, sleep, delay, steps, episodes, startup, latency */
+enum { ORC_NUM_STATS = 11, ORC_NUM_ACC = 11 };  /* reward, rebuf, u, smooth, sleep, delay, steps, episodes, startup, latency integral, content played */
 
 typedef struct OrcEnv OrcEnv;
 
@@ -41,13 +41,14 @@ void orc_env_reset(OrcEnv* e, const int32_t* trace_id, const double* start_offse
 /* one chunk step for all N sessions (SPEC §3); any output pointer may be NULL */
 void orc_env_step(OrcEnv* e, const int32_t* action, double* delay, double* sleep, double* buffer,
                   double* rebuf, double* reward, double* next_sizes, uint8_t* eov, double* throughput);
-/* live mode (SPEC §7): playback speed per session (NULL = 1) and the latency output; also valid with live = 0 */
+/* live mode (SPEC §7): speed is the [V][N] playback-speed table (speed[k][s]: session s plays content chunk k at that
+ * speed; NULL = 1) and latency the extra output; also valid with live = 0 */
 void orc_env_step_live(OrcEnv* e, const int32_t* action, const double* speed, double* delay, double* sleep,
                        double* buffer, double* rebuf, double* reward, double* latency, double* next_sizes,
                        uint8_t* eov, double* throughput, double* acc /* [ORC_NUM_ACC][N] accumulated into, nullable */);
 /* fused episode (SPEC §3+§4): trajectories are [steps][N]; acc is [ORC_NUM_ACC][N] */
 void orc_env_rollout_live(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,
-                          const int32_t* actions_in, const double* speed /*[steps][N] or NULL*/, double* delay,
+                          const int32_t* actions_in, const double* speed /*[V][N] or NULL*/, double* delay,
                           double* sleep, double* buffer, double* rebuf, double* reward, double* latency, uint8_t* eov,
                           int32_t* actions_out, double* acc);
 void orc_env_rollout(OrcEnv* e, int policy, uint64_t seed, int64_t session_base, int steps,
@@ -58,7 +59,7 @@ void orc_env_mpc_decide(OrcEnv* e, int H, int mode, int32_t* action, double* bes
 /* statistics vector from an acc table (SPEC §6): plain ascending-session sums */
 void orc_stats_from_acc(const double* acc, int N, double* out);
 /* state access for tests: field 0 seg,1 chunk,2 last_q,3 trace_id,4 hist_len (int32) ; 10 phase,11 buffer (double);
- * live mode: 16 t_now, 17 play_time (double), 7 started (uint8) */
+ * live mode: 16 t_now, 17 play_time, 19 play_len (double), 7 started (uint8), 8 play_id (int32) */
 const void* orc_env_field(OrcEnv* e, int field);
 int orc_env_error_count(OrcEnv* e);
 

@@ -1,14 +1,15 @@
 """Run the reference's OWN tick loop — TEST INFRASTRUCTURE.
 
-    python oracle/make_ref_simulator.py            ->  oracle/_ref/Simulator_repaired.py   (git-ignored)
-                                                    ->  tests/golden/sim_ref_tick_golden.json
+    python oracle/make_ref_simulator.py            ->  tests/golden/sim_ref_tick_golden.json
 
 ``/root/reference/Simulator.py`` does not run as shipped.  This script reads that file where
 it lies, applies the textual repairs of SURVEY.md §3.2 *programmatically* (nothing is copied into the repository: the
-repaired module is written to the git-ignored ``oracle/_ref/``), executes ``Simulator.run()`` — the reference's own
-per-0.01 s loop, Simulator.py:135-210 — over scripted ABR / speed controllers, and commits what it produced as a
-fixture.  The chunk-step kernels are closed forms of that loop; the fixture lets ``tests/`` check them against the
-reference's code itself, within the loop's own discretisation (one tick per event).
+repaired text exists only in this process's memory), executes ``Simulator.run()`` — the reference's own per-tick
+loop, Simulator.py:135-210 — over scripted ABR / speed controllers, and commits what it produced as a fixture.  The
+chunk-step kernels are closed forms of that loop; the fixture lets ``tests/`` check them against the reference's code
+itself, within the loop's own discretisation.  Every scenario is run twice: with the reference's tick (0.01 s,
+``reference``) and with a tick of 0.001 s (``reference_fine``, one more textual edit: the literal on Simulator.py:133),
+so that the tests can also check that the loop *converges* to the closed form as the tick shrinks.
 
 Repairs (each is an edit of the reference text, located by its content, so a changed reference fails loudly):
   D1  the ``return self.calculate_qoe(...)`` at :210 is dedented out of the ``while`` body;
@@ -16,11 +17,10 @@ Repairs (each is an edit of the reference text, located by its content, so a cha
   D3  ``self.mpd.chunks.bitrates[...]`` (:82, :156) index the chunk list first;
   D6  the bandwidth index (:158-159) wraps around at the end of the trace.
 One probe line is added after ``chunk_id += 1`` (:166): it appends the loop's local timers to ``self.ref_log`` and
-changes nothing the loop computes.
+changes nothing the loop computes.  ``tick`` replaces the literal of ``dt = 0.01`` (:133) for the convergence runs.
 """
 from __future__ import annotations
 
-import importlib.util
 import json
 import os
 import sys
@@ -29,8 +29,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("ABR_REFERENCE_DIR", "/root/reference")
-OUT_DIR = os.path.join(ROOT, "oracle", "_ref")
-OUT_PY = os.path.join(OUT_DIR, "Simulator_repaired.py")
 GOLDEN = os.path.join(ROOT, "tests", "golden", "sim_ref_tick_golden.json")
 
 
@@ -40,8 +38,10 @@ def _replace_once(text, old, new, what):
     return text.replace(old, new)
 
 
-def repaired_source(wrap_trace=True) -> str:
+def repaired_source(wrap_trace=True, tick=None) -> str:
     src = open(os.path.join(REF, "Simulator.py")).read()
+    if tick is not None:
+        src = _replace_once(src, "        dt = 0.01\n", f"        dt = {tick!r}\n", "tick")
     # D1: the return statement sits inside the while body (12 spaces) -> function level (8 spaces)
     src = _replace_once(src, "\n            return self.calculate_qoe(rebuffer_time, previous_bitrates, start_up_time, average_latency)",
                         "\n        return self.calculate_qoe(rebuffer_time, previous_bitrates, start_up_time, average_latency)", "D1")
@@ -68,14 +68,12 @@ def repaired_source(wrap_trace=True) -> str:
     return src
 
 
-def load_repaired(wrap_trace=True):
-    os.makedirs(OUT_DIR, exist_ok=True)
-    with open(OUT_PY, "w") as f:
-        f.write("# GENERATED by oracle/make_ref_simulator.py from the reference's Simulator.py — do not commit\n")
-        f.write(repaired_source(wrap_trace))
-    spec = importlib.util.spec_from_file_location("Simulator_repaired", OUT_PY)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+def load_repaired(wrap_trace=True, tick=None):
+    """The repaired reference module, compiled from memory (no copy of the reference's text is written anywhere)."""
+    import types
+    mod = types.ModuleType("Simulator_repaired")
+    exec(compile(repaired_source(wrap_trace, tick), os.path.join(REF, "Simulator.py") + " (repaired in memory)", "exec"),
+         mod.__dict__)
     return mod
 
 
@@ -151,16 +149,20 @@ def run_reference(mod, sc):
 
 def main(n=60):
     mod = load_repaired(wrap_trace=True)
+    fine = load_repaired(wrap_trace=True, tick=0.001)
     cases = []
     for i in range(n):
         sc = scenario(i)
         sc["reference"] = run_reference(mod, sc)
+        f = run_reference(fine, sc)
+        sc["reference_fine"] = dict(qoe=f["qoe"], final=f["final"], speed_calls=f["speed_calls"],
+                                    per_chunk={k: f["per_chunk"][k] for k in ("t", "rebuffer_time", "start_up_time", "play_time")})
         cases.append(sc)
     with open(GOLDEN, "w") as f:
         json.dump(dict(generator="oracle/make_ref_simulator.py: /root/reference/Simulator.py with repairs D1, D2, D3, D6 applied "
-                                 "programmatically, executed here (tick dt = 0.01 s)",
-                       dt=0.01, cases=cases), f)
-    print(f"wrote {GOLDEN}: {len(cases)} scenarios from the reference's own tick loop ({OUT_PY})")
+                                 "programmatically, executed here (tick dt = 0.01 s; reference_fine: dt = 0.001 s)",
+                       dt=0.01, dt_fine=0.001, cases=cases), f)
+    print(f"wrote {GOLDEN}: {len(cases)} scenarios from the reference's own tick loop")
 
 
 if __name__ == "__main__":

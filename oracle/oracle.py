@@ -14,8 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libabr_oracle.so")
 
-NUM_STATS = 10
-NUM_ACC = 10
+NUM_STATS = 11
+NUM_ACC = 11
 POLICY_FIXED, POLICY_RANDOM, POLICY_BBA = 0, 1, 2
 
 
@@ -23,15 +23,15 @@ class OrcParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "chunk_length", "max_buffer", "rtt", "payload", "sleep_quantum", "rebuf_penalty",
         "smooth_penalty", "utility_scale", "bba_reservoir", "bba_cushion", "start_up_length",
-        "startup_penalty", "latency_penalty")] + [
+        "startup_penalty", "latency_penalty", "latency_tick")] + [
         (n, C.c_int32) for n in ("utility_mode", "default_quality", "auto_reset", "hist_k",
-                                 "track_history", "reserved0", "live", "reserved2")]
+                                 "track_history", "reserved0", "live", "smooth_prev_ladder")]
 
 
 DEFAULTS = dict(chunk_length=4.0, max_buffer=60.0, rtt=0.08, payload=0.95, sleep_quantum=0.5,
                 rebuf_penalty=4.3, smooth_penalty=1.0, utility_scale=0.001, bba_reservoir=5.0,
-                bba_cushion=10.0, start_up_length=0.0, startup_penalty=0.0, latency_penalty=0.0, utility_mode=0,
-                default_quality=1, auto_reset=1, hist_k=5, track_history=0, live=0)
+                bba_cushion=10.0, start_up_length=0.0, startup_penalty=0.0, latency_penalty=0.0, latency_tick=0.01, utility_mode=0,
+                default_quality=1, auto_reset=1, hist_k=5, track_history=0, live=0, smooth_prev_ladder=0)
 
 
 def make_params(**kw) -> OrcParams:
@@ -125,7 +125,7 @@ class OracleEnv:
         lib().orc_env_reset(self._h, _p(t), _p(o))
 
     def step(self, action, want_next_sizes=True, speed=None, acc=None):
-        """One chunk step (SPEC §3, or §7 when live = 1).  ``speed``: playback speed per session (live mode);
+        """One chunk step (SPEC §3, or §7 when live = 1).  ``speed``: [V, N] playback-speed table (live mode);
         ``acc``: [NUM_ACC, N] accumulator table to add this step into."""
         N, A = self.N, self.A
         a = _i32(action)
@@ -139,7 +139,7 @@ class OracleEnv:
         return out
 
     def rollout(self, policy, steps, seed=0, session_base=0, actions=None, want_traj=True, speed=None):
-        """Fused-episode semantics (SPEC §3+§4; §7 with ``speed`` [steps, N] when live = 1)."""
+        """Fused-episode semantics (SPEC §3+§4; §7 with the ``speed`` table [V, N] when live = 1)."""
         N = self.N
         a_in = None if actions is None else _i32(actions)
         v = None if speed is None else _f64(speed)
@@ -168,7 +168,7 @@ class OracleEnv:
                    hist_len=(4, np.int32, 1), done=(5, np.uint8, 1), err_len=(6, np.int32, 1), phase=(10, np.float64, 1),
                    buffer=(11, np.float64, 1), bw_hist=(12, np.float64, self.K), last_pred=(13, np.float64, 1),
                    err_ring=(14, np.float64, self.K), t_now=(16, np.float64, 1), play_time=(17, np.float64, 1),
-                   started=(7, np.uint8, 1), pos=(18, np.float64, 1))
+                   started=(7, np.uint8, 1), pos=(18, np.float64, 1), play_id=(8, np.int32, 1), play_len=(19, np.float64, 1))
         fid, dt, w = ids[name]
         ptr = lib().orc_env_field(self._h, C.c_int(fid))
         n = self.N * w

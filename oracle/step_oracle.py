@@ -46,21 +46,79 @@ class Session:
         # live mode (SPEC §7)
         self.t_now = 0.0
         self.play_time = 0.0
+        self.play_id = 0           # content chunk being played, and how much of it has been played
+        self.play_len = 0.0
         self.started = P.get("start_up_length", 0.0) <= 0.0
+        self.speed = None          # playback speed per content chunk (list of V), None = 1.0
 
-    def _play(self, dt, v, acc):
-        """SPEC §7 play(Δ): returns the stall time; acc['startup'] collects start-up time."""
+    def _speed_of(self, k):
+        if self.speed is None:
+            return 1.0
+        return float(self.speed[k if k < self.V else self.V - 1])
+
+    def _piece(self, d, dw, v, acc):
+        """One stretch of playback: d seconds of content in dw seconds of wall time at speed v."""
+        # integral of the latency (wall clock - content played) over the stretch; it changes at the rate 1 - v
+        acc["area"] = acc["area"] + ((acc["tc"] - self.play_time) * dw + ((1.0 - v) * dw) * (dw * 0.5))
+        self.play_time = self.play_time + d
+        self.buffer = self.buffer - d
+        acc["tc"] = acc["tc"] + dw
+        acc["played"] = acc["played"] + d
+
+    def _play_wall(self, dt, acc):
+        """SPEC §7 play_wall(Δ): playback during Δ seconds of wall time; returns the stall time."""
+        L = self.P["chunk_length"]
         if not self.started:
             acc["startup"] = acc["startup"] + dt
+            acc["tc"] = acc["tc"] + dt
             return 0.0
-        need = v * dt
-        if self.buffer >= need:
-            drained, stall = need, 0.0
-        else:
-            drained, stall = self.buffer, dt - self.buffer / v
-        self.buffer = self.buffer - drained
-        self.play_time = self.play_time + drained
-        return stall
+        rem = dt
+        while rem > 0.0 and self.buffer > 0.0:
+            v = self._speed_of(self.play_id)
+            room = L - self.play_len
+            can = room if room < self.buffer else self.buffer
+            need = v * rem
+            if need < can:
+                self._piece(need, rem, v, acc)
+                self.play_len = self.play_len + need
+                rem = 0.0
+            else:
+                dw = can / v
+                finished = room <= self.buffer          # the chunk ends before the buffer does
+                self._piece(can, dw, v, acc)
+                rem = rem - dw
+                if finished:
+                    self.play_id += 1
+                    self.play_len = 0.0
+                else:
+                    self.play_len = self.play_len + can
+        if rem < 0.0:
+            rem = 0.0
+        acc["tc"] = acc["tc"] + rem
+        return rem
+
+    def _play_content(self, x, acc):
+        """SPEC §7 play_content(X): playback until X seconds of content have drained; returns the wall time."""
+        L = self.P["chunk_length"]
+        w = 0.0
+        while x > 0.0:
+            v = self._speed_of(self.play_id)
+            room = L - self.play_len
+            if room <= x:
+                d, finished = room, True
+            else:
+                d, finished = x, False
+            dw = d / v
+            self._piece(d, dw, v, acc)
+            w = w + dw
+            if finished:
+                self.play_id += 1
+                self.play_len = 0.0
+                x = x - d
+            else:
+                self.play_len = self.play_len + d
+                x = 0.0
+        return w
 
     def _position(self):
         C = self.C
@@ -94,22 +152,26 @@ class Session:
         self.phi = (tau + dt) / self.I
         return (0.0 if k == 0 else room0 + float(k - 1) * self.I) + dt
 
-    def step(self, q, v=1.0):
+    def step(self, q, speed=None):
+        """One chunk step.  ``speed`` (live mode): playback speed per content chunk, a list of V values (kept for the
+        following steps), or None to keep the table set before (1.0 initially)."""
         P = self.P
+        if speed is not None:
+            self.speed = list(speed)
         if self.done:
             return dict(delay=0.0, sleep=0.0, buffer=self.buffer, rebuf=0.0, reward=0.0, eov=1, inert=True,
-                        latency=0.0, startup=0.0)
+                        latency=0.0, startup=0.0, area=0.0, played=0.0)
         size = self.sizes[self.chunk][q]
         live = bool(P.get("live", 0))
-        acc = dict(startup=0.0)
+        acc = dict(startup=0.0, area=0.0, played=0.0, tc=self.t_now)
         idle = 0.0
         rebuf = 0.0
         if live:                                                              # SPEC 7.1
             w1 = (self.chunk + 1) * P["chunk_length"] - self.t_now
             w1 = w1 if w1 > 0 else 0.0
-            rebuf = self._play(w1, v, acc)
-            w2 = (self.buffer - P["max_buffer"]) / v if (self.started and self.buffer > P["max_buffer"]) else 0.0
-            rebuf = rebuf + self._play(w2, v, acc)
+            rebuf = self._play_wall(w1, acc)
+            w2 = self._play_content(self.buffer - P["max_buffer"], acc) \
+                if (self.started and self.buffer > P["max_buffer"]) else 0.0
             idle = w1 + w2
             if idle > 0:
                 self._advance(idle)
@@ -133,7 +195,7 @@ class Session:
         thr = size / delay
         latency = 0.0
         if live:                                                              # SPEC 7.2
-            rebuf = rebuf + self._play(delay, v, acc)
+            rebuf = rebuf + self._play_wall(delay, acc)
             self.buffer = self.buffer + P["chunk_length"]
             self.t_now = (self.t_now + idle) + delay
             if not self.started and self.buffer >= P.get("start_up_length", 0.0):
@@ -149,7 +211,10 @@ class Session:
             self.buffer = self.buffer - sleep
             self._advance(sleep)
         u = self.util[self.chunk][q]                                          # SPEC 3.4
-        smooth = abs(u - self.util[self.chunk][self.last_q]) if self.last_q >= 0 else 0.0
+        # the previous index is looked up in the current chunk's ladder (mpc.py:148-149) or, smooth_prev_ladder = 1, in
+        # the previous chunk's own ladder (Simulator.calculate_qoe, Simulator.py:81-82)
+        prow = self.chunk - 1 if (P.get("smooth_prev_ladder", 0) and self.chunk > 0) else self.chunk
+        smooth = abs(u - self.util[prow][self.last_q]) if self.last_q >= 0 else 0.0
         reward = (u - P["rebuf_penalty"] * rebuf) - P["smooth_penalty"] * smooth
         if live:
             reward = reward - P.get("latency_penalty", 0.0) * latency
@@ -158,7 +223,8 @@ class Session:
         self.chunk += 1
         eov = self.chunk >= self.V
         out = dict(delay=delay, sleep=sleep, buffer=self.buffer, rebuf=rebuf, reward=reward, eov=int(eov),
-                   throughput=thr, u=u, smooth=smooth, inert=False, latency=latency, startup=acc["startup"])
+                   throughput=thr, u=u, smooth=smooth, inert=False, latency=latency, startup=acc["startup"],
+                   area=acc["area"], played=acc["played"])
         if eov and P["auto_reset"]:
             self.chunk = 0
             self.buffer = 0.0
@@ -166,6 +232,8 @@ class Session:
             self.history = []
             self.t_now = 0.0
             self.play_time = 0.0
+            self.play_id = 0
+            self.play_len = 0.0
             self.started = P.get("start_up_length", 0.0) <= 0.0
         elif eov:
             self.done = True

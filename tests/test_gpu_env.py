@@ -18,7 +18,8 @@ from abrsimulator_b200.simulator import Simulator, BufferBasedPolicy, RandomPoli
 from abrsimulator_b200.mpc import MPCBitrateController
 from abrsimulator_b200 import _lib
 from oracle import oracle as orc
-from helpers import small_world, assert_close, bits_equal, load_step_golden
+from helpers import (small_world, assert_close, bits_equal, load_step_golden, speed_table, load_ref_tick_golden,
+                     ref_tick_params, ref_tick_world, check_against_ref_tick)
 
 STATE_I = ("seg", "chunk", "last_q", "trace_id")
 STATE_F = ("phase", "pos", "buffer")
@@ -365,14 +366,15 @@ LIVE = dict(live=1, start_up_length=8.0, max_buffer=16.0, latency_penalty=0.05, 
 
 @pytest.mark.parametrize("ragged", [False, True])
 def test_live_mode_step_matches_oracle(ragged):
-    """SPEC §7: live-edge gate, start-up latch, playback speed as a second action, latency — over two videos."""
+    """SPEC §7: live-edge gate, start-up latch, playback speed per played chunk as a second action, latency and its
+    integral — over two videos."""
     N, steps = 2048, 70
     env, ref = make_pair(N, dict(LIVE, track_history=1), V=30, ragged=ragged)
     rng = np.random.default_rng(17)
     acc = np.zeros((orc.NUM_ACC, N))
     for t in range(steps):
         a = rng.integers(0, env.A, size=N).astype(np.int32)
-        v = rng.choice([0.75, 1.0, 1.0, 1.25, 1.5], size=N)
+        v = rng.choice([0.75, 1.0, 1.0, 1.25, 1.5], size=(30, N))      # the table may be rewritten between steps
         got = env.step(a, speed=v, want_throughput=True)
         exp = ref.step(a, speed=v, acc=acc)
         for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
@@ -380,13 +382,15 @@ def test_live_mode_step_matches_oracle(ragged):
             assert_close(getattr(got, k_g).cpu().numpy(), exp[k_c], f"{k_g}@{t}")
         assert np.array_equal(got.end_of_video.cpu().numpy(), exp["eov"])
     check_state(env, ref)
-    for f in ("t_now", "play_time"):
+    for f in ("t_now", "play_time", "play_len"):
         assert bits_equal(env.state(f).cpu().numpy(), ref.field(f)) == 0, f
     assert np.array_equal(env.state("started").cpu().numpy(), ref.field("started"))
+    assert np.array_equal(env.state("play_id").cpu().numpy(), ref.field("play_id"))
     assert_close(env.session_acc().cpu().numpy(), acc, "acc")
-    assert acc[8].min() > 0 and acc[9].min() > 0 and (acc[1] > 0).any()
-    # session cost: rw*rebuf + vw*smooth + sw*startup + lw*latency/steps (Simulator.py:83-86)
-    want = 4.3 * acc[1] + 1.0 * acc[3] + 1.0 * acc[8] + 0.05 * (acc[9] / acc[6])
+    assert acc[8].min() > 0 and acc[9].min() > 0 and acc[10].min() > 0 and (acc[1] > 0).any()
+    # session cost: rw*rebuf + vw*smooth + sw*startup + lw*average_latency, the reference's average_latency being the
+    # latency integral over the playing time per tick and per second of content played (Simulator.py:83-86,179-180)
+    want = 4.3 * acc[1] + 1.0 * acc[3] + 1.0 * acc[8] + 0.05 * (acc[9] / (0.01 * acc[10]))
     np.testing.assert_allclose(env.qoe_cost().cpu().numpy(), want, rtol=1e-12)
     assert env.error_count() == 0
     with pytest.raises(_lib.AbrError):
@@ -395,7 +399,7 @@ def test_live_mode_step_matches_oracle(ragged):
 
 @pytest.mark.parametrize("policy", ["random", "bba", "fixed"])
 def test_fused_live_episode_matches_oracle(policy):
-    """SPEC §7 in the fused episode: speed table [steps][N], latency output, start-up / latency accumulators,
+    """SPEC §7 in the fused episode: speed table [V][N], latency output, start-up / latency / played accumulators,
     sorted (shared-memory path) and mixed blocks; and the same episode step by step."""
     N, steps = 64 * 9 + 21, 75
     bitrates, sizes, bw, tl, ti = small_world(n_traces=5, T=300, V=30, ragged=(policy == "bba"))
@@ -406,7 +410,7 @@ def test_fused_live_episode_matches_oracle(policy):
     tid = ((np.arange(N) // 64) % 5).astype(np.int32)
     tid[64 * 4:64 * 6] = rng.integers(0, 5, size=128)            # two mixed blocks -> global path
     off = rng.uniform(0, 500.0, size=N)
-    speed = rng.choice([0.75, 1.0, 1.0, 1.25, 1.5], size=(steps, N))
+    speed = rng.choice([0.75, 1.0, 1.0, 1.25, 1.5], size=(30, N))
     acts = rng.integers(0, env.A, size=(steps, N)).astype(np.int32) if policy == "fixed" else None
     pid = dict(random=orc.POLICY_RANDOM, bba=orc.POLICY_BBA, fixed=orc.POLICY_FIXED)[policy]
     env.reset(tid, off)
@@ -420,21 +424,22 @@ def test_fused_live_episode_matches_oracle(policy):
         assert_close(got[k_g].cpu().numpy(), exp[k_c], k_g)
     assert np.array_equal(got["end_of_video"].cpu().numpy(), exp["eov"])
     assert_close(env.session_acc().cpu().numpy(), exp["acc"], "acc")
-    assert exp["acc"][8].min() > 0 and exp["acc"][9].min() > 0
+    assert exp["acc"][8].min() > 0 and exp["acc"][9].min() > 0 and exp["acc"][10].min() > 0
     check_state(env, ref)
-    for f in ("t_now", "play_time"):
+    for f in ("t_now", "play_time", "play_len"):
         assert bits_equal(env.state(f).cpu().numpy(), ref.field(f)) == 0, f
     assert np.array_equal(env.state("started").cpu().numpy(), ref.field("started"))
+    assert np.array_equal(env.state("play_id").cpu().numpy(), ref.field("play_id"))
     # the same actions and speeds through the per-step kernel
     env.reset(tid, off)
     a_all = got["actions"]
     for t in range(steps):
-        r = env.step(a_all[t], speed=speed[t])
+        r = env.step(a_all[t], speed=speed)
         assert bits_equal(r.reward.cpu().numpy(), exp["reward"][t]) == 0, t
         assert bits_equal(r.latency.cpu().numpy(), exp["latency"][t]) == 0, t
-    # statistics vector carries the two live sums
+    # statistics vector carries the three live sums
     st = env.stats().cpu().numpy()
-    np.testing.assert_allclose(st[8:], [exp["acc"][8].sum(), exp["acc"][9].sum()], rtol=1e-9)
+    np.testing.assert_allclose(st[8:], [exp["acc"][8].sum(), exp["acc"][9].sum(), exp["acc"][10].sum()], rtol=1e-9)
     assert env.error_count() == 0
     # without a speed table every session plays at speed 1
     env.reset(tid, off)
@@ -467,14 +472,17 @@ def test_simulator_facade_live_mode():
     sim.set_mpd(4.0, 16.0, 8.0, [Chunk(list(b / 1000.0)) for b in bitrates])
     cost = sim.run()
     assert sp.n == 20
-    P = dict(chunk_length=4.0, max_buffer=16.0, rebuf_penalty=4.3, smooth_penalty=0.5, utility_scale=1.0,
+    # the façade's defaults are the reference's environment: no RTT, no payload factor, own-ladder variance term
+    P = dict(chunk_length=4.0, max_buffer=16.0, rebuf_penalty=4.3, smooth_penalty=0.5, utility_scale=1.0, rtt=0.0,
+             payload=1.0, sleep_quantum=0.01, smooth_prev_ladder=1, latency_tick=0.01,
              default_quality=-1, auto_reset=0, live=1, start_up_length=8.0, startup_penalty=2.0, latency_penalty=0.1)
     ref = orc.OracleEnv(bw, tl, ti, bitrates / 1000.0 * 4.0, bitrates / 1000.0, 1, **P)
     ref.reset(np.zeros(1, np.int32))
     acc = np.zeros((orc.NUM_ACC, 1))
+    table = np.array([1.25 if k >= 10 else 1.0 for k in range(20)])[:, None]     # speed of the k-th played chunk
     for k in range(20):
-        ref.step(np.ones(1, np.int32), speed=np.array([1.25 if k >= 10 else 1.0]), acc=acc)
-    want = 4.3 * acc[1, 0] + 0.5 * acc[3, 0] + 2.0 * acc[8, 0] + 0.1 * acc[9, 0] / 20
+        ref.step(np.ones(1, np.int32), speed=table, acc=acc)
+    want = 4.3 * acc[1, 0] + 0.5 * acc[3, 0] + 2.0 * acc[8, 0] + 0.1 * acc[9, 0] / (0.01 * acc[10, 0])
     assert cost == pytest.approx(want, rel=1e-12) and acc[8, 0] > 0 and acc[9, 0] > 0
     assert sim.last_run["startup"][0] == acc[8, 0]
     # built-in policy markers and the MPC controller also run in live mode
@@ -492,7 +500,8 @@ def test_simulator_facade_live_mode():
                                                                bba_cushion=ctrl.cushion))
             ref2.reset(((np.arange(64) * 2) // 64).astype(np.int32))
             a2 = ref2.rollout(orc.POLICY_BBA, 20)["acc"]
-            np.testing.assert_allclose(costs, 4.3 * a2[1] + 0.5 * a2[3] + 2.0 * a2[8] + 0.1 * a2[9] / 20, rtol=1e-12)
+            np.testing.assert_allclose(costs, 4.3 * a2[1] + 0.5 * a2[3] + 2.0 * a2[8] + 0.1 * a2[9] / (0.01 * a2[10]),
+                                       rtol=1e-12)
 
 
 def test_run_host_path_matches_oracle():
@@ -672,8 +681,9 @@ def test_simulator_facade_run():
     sim.set_network_info(1.0, list(bw[0]))
     sim.set_mpd(4.0, 60.0, None, [Chunk(list(b / 1000.0)) for b in bitrates])   # sizes = bitrate * chunk_length; no start_up_length: on-demand
     cost = sim.run()
+    # the façade's defaults are the reference's environment (no RTT, no payload factor, tick-sized pause quantum)
     P = dict(chunk_length=4.0, max_buffer=60.0, rebuf_penalty=4.3, smooth_penalty=0.001, utility_scale=1.0,
-             default_quality=-1, auto_reset=0)
+             default_quality=-1, auto_reset=0, rtt=0.0, payload=1.0, sleep_quantum=0.01, smooth_prev_ladder=1)
     ref = orc.OracleEnv(bw, tl, ti, bitrates / 1000.0 * 4.0, bitrates / 1000.0, 1, **P)
     ref.reset(np.zeros(1, np.int32))
     exp = ref.rollout(orc.POLICY_BBA, 30)
@@ -717,7 +727,7 @@ def test_kernels_reproduce_the_step_spec_fixture(case):
     env.reset(case["trace_id"], case["start_offset"])
     live = bool(P.get("live"))
     for t, a in enumerate(case["actions"]):
-        v = None if case["speeds"] is None else np.full(N, case["speeds"][t % len(case["speeds"])])
+        v = speed_table(case["speeds"], env.V, N)
         got = env.step(a, speed=v, want_throughput=True) if live else env.step(a, want_throughput=True)
         pairs = [("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"), ("reward", "reward"),
                  ("throughput", "throughput")] + ([("latency", "latency")] if live else [])
@@ -727,13 +737,84 @@ def test_kernels_reproduce_the_step_spec_fixture(case):
     assert np.array_equal(env.state("seg").cpu().numpy(), case["final"]["seg"])
     assert bits_equal(env.state("phase").cpu().numpy(), case["final"]["phase"]) == 0
     assert bits_equal(env.state("pos").cpu().numpy(), case["final"]["pos"]) == 0
-    if not live:
-        env.reset(case["trace_id"], case["start_offset"])
-        tr = env.rollout("fixed", len(case["actions"]), actions=case["actions"])
-        for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
-                         ("reward", "reward")):
-            assert bits_equal(tr[k_g].cpu().numpy(), case["outputs"][k_c]) == 0, (case["name"], k_g)
+    if live:
+        assert np.array_equal(env.state("play_id").cpu().numpy(), case["final"]["play_id"])
+        assert bits_equal(env.state("play_len").cpu().numpy(), case["final"]["play_len"]) == 0
+        assert bits_equal(env.state("play_time").cpu().numpy(), case["final"]["play_time"]) == 0
+    # the fused episode with the same action (and speed) table
+    env.reset(case["trace_id"], case["start_offset"])
+    want = ("delay", "sleep", "buffer", "rebuffer", "reward") + (("latency",) if live else ())
+    tr = env.rollout("fixed", len(case["actions"]), actions=case["actions"], want=want,
+                     speed=speed_table(case["speeds"], env.V, N) if live else None)
+    for k_g in want:
+        k_c = "rebuf" if k_g == "rebuffer" else k_g
+        assert bits_equal(tr[k_g].cpu().numpy(), case["outputs"][k_c]) == 0, (case["name"], k_g)
     assert env.error_count() == 0
+
+
+class _ScriptedAbr:
+    """get_next_bitrate of the controller protocol (Simulator.py:155): a fixed action per chunk."""
+
+    def __init__(self, actions):
+        self.actions = list(actions)
+
+    def get_next_bitrate(self, chunk_id, previous_bitrates, previous_bandwidths, buffer_level):
+        return int(self.actions[chunk_id])
+
+
+class _ScriptedSpeed:
+    """get_next_speed (Simulator.py:177): the k-th call returns speeds[k mod len]."""
+
+    def __init__(self, speeds):
+        self.speeds, self.n = list(speeds), 0
+
+    def get_next_speed(self):
+        v = self.speeds[self.n % len(self.speeds)]
+        self.n += 1
+        return float(v)
+
+
+def test_kernels_are_the_limit_of_the_references_own_tick_loop():
+    """The reference-derived pin of the chunk-step path, on the CUDA side (see the test of the same name in
+    tests/test_oracle_step.py): the 60 scripted live sessions that /root/reference/Simulator.py's own run() loop
+    played (tests/golden/sim_ref_tick_golden.json), through (a) the per-step kernel, timer by timer and chunk by
+    chunk, and (b) the drop-in ``Simulator`` façade with the reference's constructor / setters / controller protocol,
+    whose ``run()`` must return the reference's QoE cost within the loop's discretisation."""
+    doc = load_ref_tick_golden()
+    worst = {"reference": {}, "reference_fine": {}}
+    for sc in doc["cases"]:
+        br, sizes, bw, speed = ref_tick_world(sc)
+        V = sc["V"]
+        for name, tick in (("reference", doc["dt"]), ("reference_fine", doc["dt_fine"])):
+            env = BatchedABREnv(bw, sizes, br, 1, trace_interval=sc["interval"], track_acc=1, **ref_tick_params(sc, tick))
+            env.reset([0], [0.0])
+            t, reb, su, pt = np.zeros(V), np.zeros(V), np.zeros(V), np.zeros(V)
+            for k in range(V):
+                env.step([sc["actions"][k]], want_next_sizes=False, speed=speed)
+                acc = env.session_acc().cpu().numpy()[:, 0]
+                t[k], reb[k], su[k], pt[k] = env.state("t_now").item(), acc[1], acc[8], env.state("play_time").item()
+            calls = int(env.state("play_id").item()) + (1 if env.state("play_len").item() > 0 else 0)
+            dev = check_against_ref_tick(sc, name, tick, t, reb, su, pt, acc[3], acc[9], acc[10], calls)
+            for k_, d in dev.items():
+                worst[name][k_] = max(worst[name].get(k_, 0.0), float(d))
+            assert env.error_count() == 0
+            if name == "reference":
+                # the drop-in façade: reference constructor, setters and controller protocol (Simulator.py:46-77,155,177)
+                w = sc["weights"]
+                spd = _ScriptedSpeed(sc["speeds"])
+                sim = Simulator(_ScriptedAbr(sc["actions"]), spd)
+                sim.set_qoe_metric(QOEMetric(*w))
+                sim.set_network_info(sc["interval"], list(sc["bandwidths"]))
+                sim.set_mpd(sc["chunk_length"], sc["max_buffer"], sc["start_up_length"], [Chunk(list(b)) for b in sc["bitrates"]])
+                cost = sim.run()
+                want = w[0] * acc[1] + w[1] * acc[3] + w[2] * acc[8] + w[3] * (acc[9] / (tick * acc[10]))
+                assert cost == pytest.approx(want, rel=1e-12), sc["index"]       # same kernels, same numbers
+                ref = sc["reference"]
+                bound = (2 * V + 2) * tick
+                tol = (w[0] + w[2]) * bound + w[3] * 0.01 * max(ref["final"]["average_latency"], 1.0) + 1e-9 * abs(ref["qoe"])
+                assert abs(cost - ref["qoe"]) <= tol, (sc["index"], cost, ref["qoe"])
+    for k_ in worst["reference"]:
+        assert worst["reference_fine"][k_] <= worst["reference"][k_] / 4, (k_, worst)
 
 
 @pytest.mark.parametrize("seed", range(6))

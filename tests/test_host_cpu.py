@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert lib.abr_version() == 200
     p = _lib.default_params(chunk_length=2.0)
     assert p.chunk_length == 2.0 and p.max_buffer == 60.0 and p.hist_k == 5 and p.rebuf_penalty == 4.3
-    assert ctypes.sizeof(_lib.AbrParams) == 13 * 8 + 8 * 4
+    assert ctypes.sizeof(_lib.AbrParams) == 14 * 8 + 8 * 4
     with pytest.raises(TypeError):
         _lib.default_params(nonsense=1)
 

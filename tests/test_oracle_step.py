@@ -6,7 +6,8 @@ import pytest
 from oracle import mpc_oracle as mo
 from oracle import oracle as orc
 from oracle import step_oracle as so
-from helpers import small_world, bits_equal, load_step_golden
+from helpers import (small_world, bits_equal, load_step_golden, speed_table, load_ref_tick_golden, ref_tick_params,
+                     ref_tick_world, check_against_ref_tick)
 
 
 def test_philox_known_answer():
@@ -174,22 +175,27 @@ def test_live_mode_c_equals_python(ragged):
     util = orc.utility_table(bitrates, 0, P["utility_scale"])
     py = [so.Session(bw[tid[s], :tl[tid[s]]], ti[tid[s]], sizes.tolist(), util.tolist(), P, off[s]) for s in range(N)]
     acc = np.zeros((orc.NUM_ACC, N))
-    tot_startup = np.zeros(N)
+    tot = np.zeros((3, N))
     for t in range(steps):
         a = rng.integers(0, 6, size=N).astype(np.int32)
-        v = rng.choice([0.75, 1.0, 1.0, 1.25, 1.5], size=N)
+        v = rng.choice([0.75, 1.0, 1.0, 1.25, 1.5], size=(30, N))     # the speed controller may change its mind per step
         c = env.step(a, speed=v, acc=acc)
         for s in range(N):
-            r = py[s].step(int(a[s]), float(v[s]))
+            r = py[s].step(int(a[s]), v[:, s])
             for k in ("delay", "sleep", "buffer", "rebuf", "reward", "latency", "throughput"):
                 assert c[k][s] == r[k], (t, s, k)
             assert c["eov"][s] == r["eov"]
-            tot_startup[s] += r["startup"]
+            tot[0, s] += r["startup"]
+            tot[1, s] += r["area"]
+            tot[2, s] += r["played"]
     assert bits_equal(env.field("t_now"), np.array([p.t_now for p in py])) == 0
     assert bits_equal(env.field("play_time"), np.array([p.play_time for p in py])) == 0
+    assert bits_equal(env.field("play_len"), np.array([p.play_len for p in py])) == 0
+    assert np.array_equal(env.field("play_id"), np.array([p.play_id for p in py], np.int32))
     assert np.array_equal(env.field("started"), np.array([p.started for p in py], np.uint8))
-    np.testing.assert_allclose(acc[8], tot_startup, rtol=1e-12)
+    assert bits_equal(acc[8], tot[0]) == 0 and bits_equal(acc[9], tot[1]) == 0 and bits_equal(acc[10], tot[2]) == 0
     assert acc[8].min() > 0 and acc[9].min() > 0 and (acc[1] > 0).any()      # start-up, latency, rebuffering all occur
+    assert env.errors() == 0
 
 
 def test_live_mode_agrees_with_fixed_dt_loop():
@@ -204,7 +210,7 @@ def test_live_mode_agrees_with_fixed_dt_loop():
         rebuf = startup = 0.0
         delays = []
         for k in range(16):
-            r = sess.step(qs[k], speed)
+            r = sess.step(qs[k], [speed] * 16)
             rebuf += r["rebuf"]
             startup += r["startup"]
             delays.append(r["delay"])
@@ -223,8 +229,8 @@ def test_c_oracle_reproduces_the_step_spec_fixture(case):
     N = len(case["trace_id"])
     env = orc.OracleEnv(case["bw"], case["tl"], case["ti"], case["sizes"], case["bitrates"], N, **case["params"])
     env.reset(case["trace_id"], case["start_offset"])
+    v = speed_table(case["speeds"], case["sizes"].shape[0], N)
     for t, a in enumerate(case["actions"]):
-        v = None if case["speeds"] is None else np.full(N, case["speeds"][t % len(case["speeds"])])
         out = env.step(a, speed=v)
         for k in ("delay", "sleep", "buffer", "rebuf", "reward", "throughput", "latency"):
             assert bits_equal(out[k], case["outputs"][k][t]) == 0, (case["name"], t, k)
@@ -233,6 +239,9 @@ def test_c_oracle_reproduces_the_step_spec_fixture(case):
     assert bits_equal(env.field("phase"), case["final"]["phase"]) == 0
     assert bits_equal(env.field("pos"), case["final"]["pos"]) == 0
     assert bits_equal(env.field("buffer"), case["final"]["buffer"]) == 0
+    assert np.array_equal(env.field("play_id"), case["final"]["play_id"])
+    assert bits_equal(env.field("play_len"), case["final"]["play_len"]) == 0
+    assert bits_equal(env.field("play_time"), case["final"]["play_time"]) == 0
 
 
 def test_c_rollout_live_equals_python_steps():
@@ -244,17 +253,79 @@ def test_c_rollout_live_equals_python_steps():
     rng = np.random.default_rng(12)
     tid = rng.integers(0, 3, size=N).astype(np.int32)
     off = rng.uniform(0, 60, size=N)
-    speed = rng.choice([0.75, 1.0, 1.5], size=(steps, N))
+    speed = rng.choice([0.75, 1.0, 1.5], size=(16, N))           # [V, N]: speed of content chunk k in session s
     acts = rng.integers(0, 6, size=(steps, N)).astype(np.int32)
     env.reset(tid, off)
     tr = env.rollout(orc.POLICY_FIXED, steps, actions=acts, speed=speed)
     util = orc.utility_table(bitrates, 0, P["utility_scale"])
     for s in range(N):
         sess = so.Session(bw[tid[s]], ti[tid[s]], sizes.tolist(), util.tolist(), P, off[s])
-        su = lat = 0.0
+        su = area = played = 0.0
+        sess.speed = speed[:, s].tolist()
         for t in range(steps):
-            r = sess.step(int(acts[t, s]), float(speed[t, s]))
+            r = sess.step(int(acts[t, s]))
             for k in ("delay", "sleep", "buffer", "rebuf", "reward", "latency"):
                 assert tr[k][t, s] == r[k], (s, t, k)
-            su, lat = su + r["startup"], lat + r["latency"]
-        assert tr["acc"][8, s] == su and tr["acc"][9, s] == lat
+            su, area, played = su + r["startup"], area + r["area"], played + r["played"]
+        assert tr["acc"][8, s] == su and tr["acc"][9, s] == area and tr["acc"][10, s] == played
+
+
+def _run_closed_form(make, sc, tick):
+    """Play one scenario with a closed-form implementation; returns the arguments of check_against_ref_tick."""
+    step, state = make(sc, tick)
+    V = sc["V"]
+    t, reb, su, pt = np.zeros(V), np.zeros(V), np.zeros(V), np.zeros(V)
+    smooth = area = played = 0.0
+    a_reb = a_su = 0.0
+    for k in range(V):
+        r = step(sc["actions"][k])
+        a_reb, a_su = a_reb + r["rebuf"], a_su + r["startup"]
+        smooth, area, played = smooth + r["smooth"], area + r["area"], played + r["played"]
+        t_now, play_time, _, _ = state()
+        t[k], reb[k], su[k], pt[k] = t_now, a_reb, a_su, play_time
+    _, _, play_id, play_len = state()
+    return t, reb, su, pt, smooth, area, played, play_id + (1 if play_len > 0 else 0)
+
+
+def _python_session(sc, tick):
+    br, sizes, bw, speed = ref_tick_world(sc)
+    P = dict(orc.DEFAULTS, **ref_tick_params(sc, tick))
+    s = so.Session(bw[0].tolist(), sc["interval"], sizes.tolist(), br.tolist(), P, 0.0)
+    s.speed = speed[:, 0].tolist()
+    return (lambda q: s.step(int(q))), (lambda: (s.t_now, s.play_time, s.play_id, s.play_len))
+
+
+def _c_session(sc, tick):
+    br, sizes, bw, speed = ref_tick_world(sc)
+    env = orc.OracleEnv(bw, [bw.shape[1]], [sc["interval"]], sizes, br, 1, **ref_tick_params(sc, tick))
+    env.reset([0], [0.0])
+
+    def step(q):
+        acc = np.zeros((orc.NUM_ACC, 1))
+        r = env.step([q], want_next_sizes=False, speed=speed, acc=acc)
+        return dict(rebuf=r["rebuf"][0], startup=acc[8, 0], smooth=acc[3, 0], area=acc[9, 0], played=acc[10, 0])
+
+    return step, (lambda: (env.field("t_now")[0], env.field("play_time")[0], int(env.field("play_id")[0]),
+                           env.field("play_len")[0]))
+
+
+@pytest.mark.parametrize("impl", ["python", "c"])
+def test_closed_form_is_the_limit_of_the_references_own_tick_loop(impl):
+    """The reference-derived pin of the chunk-step path.  tests/golden/sim_ref_tick_golden.json holds what
+    /root/reference/Simulator.py's run() (Simulator.py:93-210, mechanically repaired by oracle/make_ref_simulator.py)
+    produced for 60 scripted live sessions — varying ladders, playback speeds per played chunk, start-up, rebuffering,
+    live-edge and buffer-full pauses — with its own 0.01 s tick and with a 0.001 s tick.  SPEC §7 (live = 1, no RTT,
+    payload 1) is the closed form of that loop: per-chunk wall clock, rebuffer time, start-up time and content played,
+    the average latency, the number of speed-controller calls and the QoE cost agree with the loop to within its
+    discretisation, and the deviation shrinks with the tick (first-order convergence)."""
+    doc = load_ref_tick_golden()
+    make = _python_session if impl == "python" else _c_session
+    worst = {"reference": {}, "reference_fine": {}}
+    for sc in doc["cases"]:
+        for name, tick in (("reference", doc["dt"]), ("reference_fine", doc["dt_fine"])):
+            dev = check_against_ref_tick(sc, name, tick, *_run_closed_form(make, sc, tick))
+            for k, d in dev.items():
+                worst[name][k] = max(worst[name].get(k, 0.0), float(d))
+    for k in worst["reference"]:      # ten times finer tick -> about ten times closer (at least four)
+        assert worst["reference_fine"][k] <= worst["reference"][k] / 4, (k, worst)
+    assert len(doc["cases"]) >= 60
