@@ -52,17 +52,34 @@ def is_stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Builds the library under an exclusive file lock: in a one-process-per-GPU launch every rank may find a stale
+    library at import; the first one builds (objects and the link go to a private directory, the finished .so is
+    moved into place with os.replace, so no process can ever dlopen a half-written file), the others wait on the lock
+    and find it fresh."""
     if not force and not is_stale():
         return LIB
+    import fcntl
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():      # another process built it while this one waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libabr_b200.so (set NVCC or add nvcc to PATH)")
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
     # one nvcc per source, in parallel (abr_step.cu alone holds ~50 kernel instantiations), then one link
     from concurrent.futures import ThreadPoolExecutor
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
-    obj_dir = os.path.join(os.path.dirname(LIB), "obj" + _SUFFIX)
+    obj_dir = os.path.join(os.path.dirname(LIB), "obj" + _SUFFIX, f"build.{os.getpid()}")
     os.makedirs(obj_dir, exist_ok=True)
+    tmp_lib = os.path.join(obj_dir, os.path.basename(LIB))
 
     def compile_one(src):
         obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
@@ -72,15 +89,22 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         results = list(pool.map(compile_one, SOURCES))
     log = ""
-    for obj, res in results:
-        log += res.stdout + res.stderr
+    try:
+        for obj, res in results:
+            log += res.stdout + res.stderr
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", tmp_lib] + [obj for obj, _ in results], capture_output=True, text=True)
         if res.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", LIB] + [obj for obj, _ in results], capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(log + res.stdout + res.stderr)
-    with open(STAMP, "w") as f:
-        f.write(_source_hash())
+            raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(log + res.stdout + res.stderr)
+        if os.path.exists(STAMP):
+            os.remove(STAMP)                      # never a fresh stamp next to an old library
+        os.replace(tmp_lib, LIB)
+        with open(STAMP + f".{os.getpid()}", "w") as f:
+            f.write(_source_hash())
+        os.replace(STAMP + f".{os.getpid()}", STAMP)
+    finally:
+        shutil.rmtree(obj_dir, ignore_errors=True)
     return LIB

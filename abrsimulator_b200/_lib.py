@@ -14,7 +14,7 @@ NUM_ACC = 11
 NUM_STATS = 11
 POLICY_FIXED, POLICY_RANDOM, POLICY_BBA = 0, 1, 2
 MPC_REF, MPC_ROBUST = 0, 1
-MPC_TRUNCATE, MPC_EMPTY_DEFAULT = 1, 2
+MPC_TRUNCATE, MPC_EMPTY_DEFAULT, MPC_PRED_SES = 1, 2, 4
 ACC_NAMES = ("reward", "rebuffer", "utility", "smooth", "sleep", "delay", "steps", "episodes", "startup", "latency",
              "played")
 FIELDS = dict(seg=(0, "int32"), chunk=(1, "int32"), last_q=(2, "int32"), trace_id=(3, "int32"),
@@ -46,7 +46,8 @@ SYMBOLS = ("abr_version", "abr_last_error", "abr_launch_count", "abr_device_info
            "abr_env_step", "abr_env_step_live", "abr_env_step_f32", "abr_env_qoe_cost", "abr_env_rollout_fused",
            "abr_env_rollout_fused_live", "abr_env_rollout_fused_f32", "abr_env_run", "abr_env_mpc_decide", "abr_stats_partial",
            "abr_env_state_ptr",
-           "abr_env_error_count", "abr_env_run_host", "abr_mpc_decide", "abr_mpc_decide_host", "abr_mpc_score_host",
+           "abr_env_error_count", "abr_env_run_host", "abr_mpc_decide", "abr_mpc_decide_host", "abr_mpc_decide_startup",
+           "abr_mpc_decide_startup_host", "abr_mpc_score_host",
            "abr_fp64_probe")
 
 _lib = None
@@ -64,7 +65,8 @@ def load():
     path = _build.LIB
     if _build.is_stale():
         # missing or built from other sources: rebuild (raises if there is no nvcc — loud failure, no fallback)
-        _build.build_library(force=True)
+        # under a file lock: concurrent ranks build once, the rest wait and load the finished file
+        _build.build_library()
     lib = C.CDLL(path)
     lib.abr_last_error.restype = C.c_char_p
     lib.abr_launch_count.restype = C.c_longlong

@@ -616,19 +616,26 @@ int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const in
     return ABR_OK;
 }
 
-int abr_mpc_decide(const double* d_sizes, const double* d_utility, int V, int A, const AbrParams* params, int N,
-                   const int32_t* d_chunk_idx, const int32_t* d_prev_q, const double* d_buffer, const double* d_bw_hist,
-                   const int32_t* d_hist_len, int K, double* d_last_pred, double* d_err_ring, int32_t* d_err_len,
-                   int horizon, int mode, int flags, int32_t* d_action, double* d_best_j, int32_t* d_best_seq,
-                   double* d_preds, int32_t* d_error_count, void* stream) {
+static int mpc_decide_impl(const double* d_sizes, const double* d_utility, int V, int A, const AbrParams* params, int N,
+                           const int32_t* d_chunk_idx, const int32_t* d_prev_q, const double* d_buffer,
+                           const double* d_bw_hist, const int32_t* d_hist_len, int K, double* d_last_pred,
+                           double* d_err_ring, int32_t* d_err_len, int horizon, int mode, int flags,
+                           const uint8_t* d_startup, int n_ts, double ts_step, int32_t* d_action,
+                           double* d_startup_delay, double* d_best_j, int32_t* d_best_seq, double* d_preds,
+                           int32_t* d_error_count, void* stream) {
     if (!d_sizes || !d_utility || !d_chunk_idx || !d_prev_q || !d_buffer || !d_bw_hist || !d_hist_len || !d_action)
         return fail(ABR_ERR_INVALID, "a required pointer is NULL");
     if (!params) return fail(ABR_ERR_INVALID, "params is NULL");
     if (N < 0 || V < 1) return fail(ABR_ERR_RANGE, "N must be >= 0 and V >= 1");
     if (K < 1) return fail(ABR_ERR_RANGE, "K must be >= 1");
     if (mode != ABR_MPC_REF && mode != ABR_MPC_ROBUST) return fail(ABR_ERR_INVALID, "unknown MPC mode %d", mode);
+    if ((flags & ABR_MPC_PRED_SES) && mode != ABR_MPC_REF)
+        return fail(ABR_ERR_INVALID, "ABR_MPC_PRED_SES (mpc.py:72-79) replaces the predictor of mode 0; the robust mode defines its own");
     if ((d_last_pred || d_err_ring || d_err_len) && !(d_last_pred && d_err_ring && d_err_len))
         return fail(ABR_ERR_INVALID, "last_pred, err_ring and err_len must be given together");
+    if (n_ts < 1 || n_ts > 4096) return fail(ABR_ERR_RANGE, "n_ts must be in [1, 4096] (got %d)", n_ts);
+    if (n_ts > 1 && !(ts_step > 0.0 && std::isfinite(ts_step))) return fail(ABR_ERR_RANGE, "ts_step must be finite and > 0");
+    if (n_ts > 1 && !std::isfinite(params->startup_penalty)) return fail(ABR_ERR_INVALID, "startup_penalty must be finite");
     int rc = check_mpc_shape(A, horizon);
     if (rc) return rc;
     MpcArgs a{};
@@ -640,15 +647,71 @@ int abr_mpc_decide(const double* d_sizes, const double* d_utility, int V, int A,
     a.H = horizon; a.mode = mode; a.flags = flags;
     a.action = d_action; a.best_j = d_best_j; a.best_seq = d_best_seq; a.preds = d_preds;
     a.error_count64 = nullptr; a.error_count32 = d_error_count;
+    a.startup = d_startup; a.n_ts = n_ts; a.ts_step = ts_step; a.startup_delay = d_startup_delay;
     CUDA_TRY(launch_mpc(a, (cudaStream_t)stream));
     return ABR_OK;
 }
 
-int abr_mpc_decide_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params, int N,
-                        const int32_t* h_chunk_idx, const int32_t* h_prev_q, const double* h_buffer,
-                        const double* h_bw_hist, const int32_t* h_hist_len, int K, double* h_last_pred,
-                        double* h_err_ring, int32_t* h_err_len, int horizon, int mode, int flags, int32_t* h_action,
-                        double* h_best_j, int32_t* h_best_seq, double* h_preds, int32_t* h_error_count) {
+int abr_mpc_decide(const double* d_sizes, const double* d_utility, int V, int A, const AbrParams* params, int N,
+                   const int32_t* d_chunk_idx, const int32_t* d_prev_q, const double* d_buffer, const double* d_bw_hist,
+                   const int32_t* d_hist_len, int K, double* d_last_pred, double* d_err_ring, int32_t* d_err_len,
+                   int horizon, int mode, int flags, int32_t* d_action, double* d_best_j, int32_t* d_best_seq,
+                   double* d_preds, int32_t* d_error_count, void* stream) {
+    return mpc_decide_impl(d_sizes, d_utility, V, A, params, N, d_chunk_idx, d_prev_q, d_buffer, d_bw_hist, d_hist_len, K,
+                           d_last_pred, d_err_ring, d_err_len, horizon, mode, flags, nullptr, 1, 0.0, d_action, nullptr,
+                           d_best_j, d_best_seq, d_preds, d_error_count, stream);
+}
+
+int abr_mpc_decide_startup(const double* d_sizes, const double* d_utility, int V, int A, const AbrParams* params, int N,
+                           const int32_t* d_chunk_idx, const int32_t* d_prev_q, const double* d_buffer,
+                           const double* d_bw_hist, const int32_t* d_hist_len, int K, double* d_last_pred,
+                           double* d_err_ring, int32_t* d_err_len, int horizon, int mode, int flags,
+                           const uint8_t* d_startup, int n_ts, double ts_step, int32_t* d_action,
+                           double* d_startup_delay, double* d_best_j, int32_t* d_best_seq, double* d_preds,
+                           int32_t* d_error_count, void* stream) {
+    if (!d_startup_delay) return fail(ABR_ERR_INVALID, "startup_delay is NULL");
+    return mpc_decide_impl(d_sizes, d_utility, V, A, params, N, d_chunk_idx, d_prev_q, d_buffer, d_bw_hist, d_hist_len, K,
+                           d_last_pred, d_err_ring, d_err_len, horizon, mode, flags, d_startup, n_ts, ts_step, d_action,
+                           d_startup_delay, d_best_j, d_best_seq, d_preds, d_error_count, stream);
+}
+
+// ---- host-buffer decisions: one staging arena per host thread (grow-only, released at thread exit), so that a
+//      decision is one host->device copy, one kernel and one device->host copy — no allocation on the call path ----
+namespace {
+struct HostArena {
+    char* dev = nullptr; char* pin = nullptr; size_t cap = 0; int device = -1;
+    ~HostArena() { release(); }
+    void release() {
+        if (dev) cudaFree(dev);
+        if (pin) cudaFreeHost(pin);
+        dev = pin = nullptr; cap = 0;
+    }
+    cudaError_t reserve(size_t bytes) {
+        int cur = 0;
+        cudaError_t e = cudaGetDevice(&cur);
+        if (e != cudaSuccess) return e;
+        if (cur == device && bytes <= cap) return cudaSuccess;
+        release();
+        size_t want = bytes < (64u << 10) ? (64u << 10) : bytes + bytes / 2;
+        e = cudaMalloc((void**)&dev, want);
+        if (e != cudaSuccess) { dev = nullptr; return e; }
+        e = cudaHostAlloc((void**)&pin, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) { cudaFree(dev); dev = pin = nullptr; return e; }
+        cap = want; device = cur;
+        return cudaSuccess;
+    }
+};
+thread_local HostArena t_arena;
+inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+}  // namespace
+
+static int mpc_decide_host_impl(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params,
+                                int N, const int32_t* h_chunk_idx, const int32_t* h_prev_q, const double* h_buffer,
+                                const double* h_bw_hist, const int32_t* h_hist_len, int K, double* h_last_pred,
+                                double* h_err_ring, int32_t* h_err_len, int horizon, int mode, int flags,
+                                const uint8_t* h_startup, int n_ts, double ts_step, int32_t* h_action,
+                                double* h_startup_delay, double* h_best_j, int32_t* h_best_seq, double* h_preds,
+                                int32_t* h_error_count) {
     if (!h_chunk_idx || !h_prev_q || !h_buffer || !h_bw_hist || !h_hist_len || !h_action)
         return fail(ABR_ERR_INVALID, "a required pointer is NULL");
     int rc = check_tables(h_sizes, h_bitrates, V, A);
@@ -664,51 +727,83 @@ int abr_mpc_decide_host(const double* h_sizes, const double* h_bitrates, int V, 
     }
     std::vector<double> util;
     utility_table(h_bitrates, V, A, params, util);
-    const size_t n = (size_t)(N > 0 ? N : 1), H = (size_t)horizon;
-    // one device arena: [sizes | util | buffer | hist | last_pred | err_ring | best_j | preds | ints...]
-    const size_t n_d = 2 * (size_t)V * A + n + n * K + n + n * K + n + n * H;
-    const size_t n_i = 3 * n + n + n + n * H + 1;  // chunk, prev_q, hist_len, err_len, action, best_seq, errcount
-    double* dd = nullptr;
-    int32_t* di = nullptr;
-    CUDA_TRY(cudaMalloc(&dd, sizeof(double) * n_d));
-    if (cudaMalloc(&di, sizeof(int32_t) * n_i) != cudaSuccess) { cudaFree(dd); return fail(ABR_ERR_CUDA, "cudaMalloc failed"); }
-    struct Free { double* a; int32_t* b; ~Free() { cudaFree(a); cudaFree(b); } } fr{dd, di};
-    double* d_sizes = dd; double* d_util = d_sizes + (size_t)V * A; double* d_buffer = d_util + (size_t)V * A;
-    double* d_hist = d_buffer + n; double* d_lp = d_hist + n * K; double* d_er = d_lp + n; double* d_bj = d_er + n * K;
-    double* d_pr = d_bj + n;
-    int32_t* d_chunk = di; int32_t* d_pq = d_chunk + n; int32_t* d_hl = d_pq + n; int32_t* d_el = d_hl + n;
-    int32_t* d_act = d_el + n; int32_t* d_seq = d_act + n; int32_t* d_ec = d_seq + n * H;
+    const size_t n = (size_t)(N > 0 ? N : 1), H = (size_t)horizon, VA = (size_t)V * A;
     const bool robust_state = h_last_pred && h_err_ring && h_err_len;
+    // arena layout: [inputs, copied host->device in one piece | outputs, copied back in one piece]
+    size_t off = 0;
+    auto take = [&off](size_t bytes) { const size_t o = off; off = align16(off + bytes); return o; };
+    const size_t o_sizes = take(8 * VA), o_util = take(8 * VA), o_buffer = take(8 * n), o_hist = take(8 * n * K);
+    const size_t o_chunk = take(4 * n), o_pq = take(4 * n), o_hl = take(4 * n), o_su = take(n);
+    const size_t o_out = off;          // robust state is both input and output: it sits at the start of the output part
+    const size_t o_lp = take(8 * n), o_er = take(8 * n * K), o_el = take(4 * n), o_ec = take(16);
+    const size_t in_bytes = off;       // inputs end here (the error counter is zeroed on the host side of the copy)
+    const size_t o_act = take(4 * n), o_ts = take(8 * n), o_bj = take(8 * n), o_seq = take(4 * n * H), o_pr = take(8 * n * H);
+    const size_t total = off;
+    CUDA_TRY(t_arena.reserve(total));
+    char* hp = t_arena.pin;
+    char* dp = t_arena.dev;
+    memcpy(hp + o_sizes, h_sizes, 8 * VA);
+    memcpy(hp + o_util, util.data(), 8 * VA);
+    memcpy(hp + o_buffer, h_buffer, 8 * (size_t)N);
+    memcpy(hp + o_hist, h_bw_hist, 8 * (size_t)N * K);
+    memcpy(hp + o_chunk, h_chunk_idx, 4 * (size_t)N);
+    memcpy(hp + o_pq, h_prev_q, 4 * (size_t)N);
+    memcpy(hp + o_hl, h_hist_len, 4 * (size_t)N);
+    if (h_startup) memcpy(hp + o_su, h_startup, (size_t)N);
+    if (robust_state) {
+        memcpy(hp + o_lp, h_last_pred, 8 * (size_t)N);
+        memcpy(hp + o_er, h_err_ring, 8 * (size_t)N * K);
+        memcpy(hp + o_el, h_err_len, 4 * (size_t)N);
+    }
+    memset(hp + o_ec, 0, 16);
     cudaStream_t st = 0;
-    CUDA_TRY(cudaMemcpyAsync(d_sizes, h_sizes, sizeof(double) * V * A, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_buffer, h_buffer, sizeof(double) * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_hist, h_bw_hist, sizeof(double) * (size_t)N * K, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_chunk, h_chunk_idx, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_pq, h_prev_q, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_hl, h_hist_len, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
-    if (robust_state) {
-        CUDA_TRY(cudaMemcpyAsync(d_lp, h_last_pred, sizeof(double) * N, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(d_er, h_err_ring, sizeof(double) * (size_t)N * K, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(d_el, h_err_len, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
-    }
-    CUDA_TRY(cudaMemsetAsync(d_ec, 0, sizeof(int32_t), st));
-    rc = abr_mpc_decide(d_sizes, d_util, V, A, params, N, d_chunk, d_pq, d_buffer, d_hist, d_hl, K,
-                        robust_state ? d_lp : nullptr, robust_state ? d_er : nullptr, robust_state ? d_el : nullptr,
-                        horizon, mode, flags, d_act, d_bj, d_seq, d_pr, d_ec, st);
+    CUDA_TRY(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+    rc = mpc_decide_impl((const double*)(dp + o_sizes), (const double*)(dp + o_util), V, A, params, N,
+                         (const int32_t*)(dp + o_chunk), (const int32_t*)(dp + o_pq), (const double*)(dp + o_buffer),
+                         (const double*)(dp + o_hist), (const int32_t*)(dp + o_hl), K,
+                         robust_state ? (double*)(dp + o_lp) : nullptr, robust_state ? (double*)(dp + o_er) : nullptr,
+                         robust_state ? (int32_t*)(dp + o_el) : nullptr, horizon, mode, flags,
+                         h_startup ? (const uint8_t*)(dp + o_su) : nullptr, n_ts, ts_step, (int32_t*)(dp + o_act),
+                         (double*)(dp + o_ts), (double*)(dp + o_bj), (int32_t*)(dp + o_seq), (double*)(dp + o_pr),
+                         (int32_t*)(dp + o_ec), st);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h_action, d_act, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
-    if (h_best_j) CUDA_TRY(cudaMemcpyAsync(h_best_j, d_bj, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
-    if (h_best_seq) CUDA_TRY(cudaMemcpyAsync(h_best_seq, d_seq, sizeof(int32_t) * (size_t)N * H, cudaMemcpyDeviceToHost, st));
-    if (h_preds) CUDA_TRY(cudaMemcpyAsync(h_preds, d_pr, sizeof(double) * (size_t)N * H, cudaMemcpyDeviceToHost, st));
-    if (h_error_count) CUDA_TRY(cudaMemcpyAsync(h_error_count, d_ec, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (robust_state) {
-        CUDA_TRY(cudaMemcpyAsync(h_last_pred, d_lp, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h_err_ring, d_er, sizeof(double) * (size_t)N * K, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h_err_len, d_el, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
-    }
+    CUDA_TRY(cudaMemcpyAsync(hp + o_out, dp + o_out, total - o_out, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(h_action, hp + o_act, 4 * (size_t)N);
+    if (h_startup_delay) memcpy(h_startup_delay, hp + o_ts, 8 * (size_t)N);
+    if (h_best_j) memcpy(h_best_j, hp + o_bj, 8 * (size_t)N);
+    if (h_best_seq) memcpy(h_best_seq, hp + o_seq, 4 * (size_t)N * H);
+    if (h_preds) memcpy(h_preds, hp + o_pr, 8 * (size_t)N * H);
+    if (h_error_count) memcpy(h_error_count, hp + o_ec, 4);
+    if (robust_state) {
+        memcpy(h_last_pred, hp + o_lp, 8 * (size_t)N);
+        memcpy(h_err_ring, hp + o_er, 8 * (size_t)N * K);
+        memcpy(h_err_len, hp + o_el, 4 * (size_t)N);
+    }
     return ABR_OK;
+}
+
+int abr_mpc_decide_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params, int N,
+                        const int32_t* h_chunk_idx, const int32_t* h_prev_q, const double* h_buffer,
+                        const double* h_bw_hist, const int32_t* h_hist_len, int K, double* h_last_pred,
+                        double* h_err_ring, int32_t* h_err_len, int horizon, int mode, int flags, int32_t* h_action,
+                        double* h_best_j, int32_t* h_best_seq, double* h_preds, int32_t* h_error_count) {
+    return mpc_decide_host_impl(h_sizes, h_bitrates, V, A, params, N, h_chunk_idx, h_prev_q, h_buffer, h_bw_hist,
+                                h_hist_len, K, h_last_pred, h_err_ring, h_err_len, horizon, mode, flags, nullptr, 1, 0.0,
+                                h_action, nullptr, h_best_j, h_best_seq, h_preds, h_error_count);
+}
+
+int abr_mpc_decide_startup_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params,
+                                int N, const int32_t* h_chunk_idx, const int32_t* h_prev_q, const double* h_buffer,
+                                const double* h_bw_hist, const int32_t* h_hist_len, int K, double* h_last_pred,
+                                double* h_err_ring, int32_t* h_err_len, int horizon, int mode, int flags,
+                                const uint8_t* h_startup, int n_ts, double ts_step, int32_t* h_action,
+                                double* h_startup_delay, double* h_best_j, int32_t* h_best_seq, double* h_preds,
+                                int32_t* h_error_count) {
+    if (!h_startup_delay) return fail(ABR_ERR_INVALID, "startup_delay is NULL");
+    return mpc_decide_host_impl(h_sizes, h_bitrates, V, A, params, N, h_chunk_idx, h_prev_q, h_buffer, h_bw_hist,
+                                h_hist_len, K, h_last_pred, h_err_ring, h_err_len, horizon, mode, flags, h_startup, n_ts,
+                                ts_step, h_action, h_startup_delay, h_best_j, h_best_seq, h_preds, h_error_count);
 }
 
 int abr_mpc_score_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params,

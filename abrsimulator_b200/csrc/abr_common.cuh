@@ -147,6 +147,8 @@ struct MpcArgs {
     int H, mode, flags;
     int32_t* action; double* best_j; int32_t* best_seq; double* preds;
     unsigned long long* error_count64; int32_t* error_count32; // either may be null
+    // start-up phase (SPEC §5.3): sessions with startup[s] != 0 also choose a start-up delay on the grid jt * ts_step
+    const uint8_t* startup = nullptr; int n_ts = 1; double ts_step = 0.0; double* startup_delay = nullptr;
 };
 cudaError_t launch_mpc(const MpcArgs& a, cudaStream_t st);
 cudaError_t launch_mpc_score(const double* d_sizes, const double* d_util, int V, int A, const AbrParams& p, int k,

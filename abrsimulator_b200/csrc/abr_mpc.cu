@@ -228,11 +228,28 @@ abr_mpc_kernel(const MpcArgs a) {
                 for (int jj = 0; jj < m; ++jj) Ssum = dadd(Ssum, __shfl_sync(0xffffffffu, inv, jj));
                 if (j0 + 32 >= n) newest = __shfl_sync(0xffffffffu, x, m - 1);
             }
+            // ---- predictor "expsmoothing" (mpc.py:72-79; SPEC §5.4): flat forecast l_n of simple exponential
+            //      smoothing with alpha = 0.5 and the least-squares initial level; sequential, every thread redundantly ----
+            double ses = 0.0;
+            const bool use_ses = a.mode == ABR_MPC_REF && (a.flags & ABR_MPC_PRED_SES) != 0;
+            if (use_ses && !bad) {
+                double la = 0.0, lb = 1.0, num = 0.0, den = 0.0;          // l_t = la + lb * l_0
+                for (int j = 0; j < n; ++j) {
+                    const double y = a.bw_hist[s * a.hist_session_stride + (long long)((start + j) % K) * a.hist_slot_stride];
+                    const double r = dsub(y, la);                           // one-step error with l_0 = 0
+                    num = dadd(num, dmul(lb, r));
+                    den = dadd(den, dmul(lb, lb));
+                    la = dadd(dmul(0.5, y), dmul(0.5, la));
+                    lb = dmul(0.5, lb);
+                }
+                ses = dadd(la, dmul(lb, ddiv(num, den)));
+                if (!(ses > 0.0)) bad = true;                               // a non-positive forecast cannot be divided by
+            }
             if (bad) status = 2;                                           // ZeroDivisionError, mpc.py:88
             else if (a.mode == ABR_MPC_REF) {
                 // p_i = (n+i)/S ; S += 1/p_i   (mpc.py:83-92 incl. the list mutation D10)
                 for (int i = 0; i < h; ++i) {
-                    const double pi = ddiv((double)(n + i), Ssum);
+                    const double pi = use_ses ? ses : ddiv((double)(n + i), Ssum);
                     Ssum = dadd(Ssum, ddiv(1.0, pi));
                     if (a.preds && tid == 0) a.preds[s * H + i] = pi;
                     // tables for step i: each thread of the session fills entries a = tid, tid+NT, ...
@@ -281,6 +298,7 @@ abr_mpc_kernel(const MpcArgs a) {
         // NOTE: status is identical in every thread of the session (all inputs are session-uniform).
         if (WPS > 1) __syncthreads(); else __syncwarp();
         SearchOut o; o.q = 0.0; o.idx = 0;
+        double ts_best = 0.0;
         if (status == 0) {
             const int i5 = h - 1;
             for (int e = tid; e < A * A; e += NT) {
@@ -288,43 +306,59 @@ abr_mpc_kernel(const MpcArgs a) {
                 S.AD[e] = fabs(dsub(S.U[i5 * A + a5], S.U[i5 * A + a4]));
             }
             if (WPS > 1) __syncthreads(); else __syncwarp();
-            if (h == 1) {
-                // single level: A leaves, thread 0 of the session scans them in order
-                double bq = __longlong_as_double(0xfff0000000000000ll);
-                int bi = 0x7fffffff;
-                if (tid == 0) {
-                    for (int a0 = 0; a0 < A; ++a0) {
-                        const double u = S.U[a0];
-                        const double qv = prev_q >= 0 ? fabs(dsub(u, S.U[prev_q])) : 0.0;
-                        const double d = dsub(S.RB[a0], buf0);
-                        const double rt = CLAMP ? max0(d) : d;
-                        // 0 + x is exact, so the running sums of mpc.py:146-152 reduce to the terms themselves
-                        const double q = dsub(dsub(u, dmul(p.smooth_penalty, qv)), dmul(p.rebuf_penalty, rt));
-                        if (q > bq) { bq = q; bi = a0; }
+            // Start-up phase (SPEC §5.3; f_st of mpc.py:7-18, the TODO of mpc.py:141): the start-up delay T_s is a second
+            // decision variable on the grid jt * ts_step; it is credited to the initial buffer and charged
+            // startup_weight * T_s (mpc.py:160).  T_s is the slowest axis of the enumeration: ties keep the smaller T_s.
+            const int n_ts = (a.n_ts > 1 && (!a.startup || a.startup[s])) ? a.n_ts : 1;   // session-uniform
+            double q_best = __longlong_as_double(0xfff0000000000000ll);
+            int idx_best = 0x7fffffff;
+            for (int jt = 0; jt < n_ts; ++jt) {
+                const double ts = jt == 0 ? 0.0 : dmul((double)jt, a.ts_step);
+                const double bufj = jt == 0 ? buf0 : dadd(buf0, ts);
+                if (h == 1) {
+                    // single level: A leaves, thread 0 of the session scans them in order
+                    double bq = __longlong_as_double(0xfff0000000000000ll);
+                    int bi = 0x7fffffff;
+                    if (tid == 0) {
+                        for (int a0 = 0; a0 < A; ++a0) {
+                            const double u = S.U[a0];
+                            const double qv = prev_q >= 0 ? fabs(dsub(u, S.U[prev_q])) : 0.0;
+                            const double d = dsub(S.RB[a0], bufj);
+                            const double rt = CLAMP ? max0(d) : d;
+                            // 0 + x is exact, so the running sums of mpc.py:146-152 reduce to the terms themselves
+                            const double q = dsub(dsub(u, dmul(p.smooth_penalty, qv)), dmul(p.rebuf_penalty, rt));
+                            if (q > bq) { bq = q; bi = a0; }
+                        }
                     }
+                    o.q = bq; o.idx = bi;
+                } else {
+                    if (p.smooth_penalty == 1.0)
+                        o = search<AT, CLAMP, true, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, bufj, 1.0, p.rebuf_penalty,
+                                                         L, B, tid, NT);
+                    else
+                        o = search<AT, CLAMP, false, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, bufj, p.smooth_penalty,
+                                                          p.rebuf_penalty, L, B, tid, NT);
                 }
-                o.q = bq; o.idx = bi;
-            } else {
-                if (p.smooth_penalty == 1.0)
-                    o = search<AT, CLAMP, true, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, buf0, 1.0, p.rebuf_penalty,
-                                                     L, B, tid, NT);
-                else
-                    o = search<AT, CLAMP, false, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, buf0, p.smooth_penalty,
-                                                      p.rebuf_penalty, L, B, tid, NT);
-            }
-            // ---- argmin over the session's threads: key (J, linear index) ----
+                // ---- argmin over the session's threads: key (J, linear index) ----
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double oq = __shfl_xor_sync(0xffffffffu, o.q, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, o.idx, off);
-                better(o.q, o.idx, oq, oi);
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double oq = __shfl_xor_sync(0xffffffffu, o.q, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, o.idx, off);
+                    better(o.q, o.idx, oq, oi);
+                }
+                if (WPS > 1) {
+                    if (lane == 0) { S.redq[wis] = o.q; S.redi[wis] = o.idx; }
+                    __syncthreads();
+                    o.q = S.redq[0]; o.idx = S.redi[0];
+                    for (int w = 1; w < WPS; ++w) better(o.q, o.idx, S.redq[w], S.redi[w]);
+                }
+                if (n_ts == 1) break;                                  // the usual decision: nothing else to do
+                // every thread of the session holds the same reduced (q, idx): the comparison below is uniform
+                const double qt = dsub(o.q, dmul(p.startup_penalty, ts));
+                if (qt > q_best) { q_best = qt; idx_best = o.idx; ts_best = ts; }
+                if (WPS > 1) __syncthreads(); else __syncwarp();       // the parent-state cache / redq are reused
             }
-            if (WPS > 1) {
-                if (lane == 0) { S.redq[wis] = o.q; S.redi[wis] = o.idx; }
-                __syncthreads();
-                o.q = S.redq[0]; o.idx = S.redi[0];
-                for (int w = 1; w < WPS; ++w) better(o.q, o.idx, S.redq[w], S.redi[w]);
-            }
+            if (n_ts > 1) { o.q = q_best; o.idx = idx_best; }
         }
         if (tid == 0) {
             if (status == 0) {
@@ -332,6 +366,7 @@ abr_mpc_kernel(const MpcArgs a) {
                 int div = 1;
                 for (int i = 1; i < h; ++i) div *= A;
                 a.action[s] = idx / div;
+                if (a.startup_delay) a.startup_delay[s] = ts_best;
                 if (a.best_j) a.best_j[s] = -o.q;
                 if (a.best_seq) {
                     int rem = idx, d = div;
@@ -342,6 +377,7 @@ abr_mpc_kernel(const MpcArgs a) {
                 }
             } else {
                 a.action[s] = status == 1 ? act : -1;
+                if (a.startup_delay) a.startup_delay[s] = 0.0;
                 if (a.best_j) a.best_j[s] = __longlong_as_double(0x7ff8000000000000ll);
                 if (a.best_seq) for (int i = 0; i < H; ++i) a.best_seq[s * H + i] = -1;
                 if (a.preds && status == 2) for (int i = 0; i < H; ++i) a.preds[s * H + i] = 0.0;

@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sessions", type=int, default=65536, help="sessions per GPU (configs[1])")
     ap.add_argument("--mpc-sessions", type=int, default=131072, help="MPC sessions per GPU (configs[2] / 8)")
+    ap.add_argument("--mpc-strong-total", type=int, default=1 << 20,
+                    help="configs[2] as written: a FIXED total of robust-MPC sessions sharded over the GPUs (strong "
+                         "scaling), whole 48-chunk episode + the statistics all-reduce inside the timed region (0 = skip)")
     ap.add_argument("--mpc-horizon", type=int, default=5)
     ap.add_argument("--mpc-h7-sessions", type=int, default=2048, help="sessions per GPU of the horizon-7 leg (0 = skip)")
     ap.add_argument("--no-mpc", action="store_true")
@@ -192,6 +195,74 @@ def run_reference(args):
         line["mpc"] = dict(metric="mpc_decisions_per_sec", value=r, unit="decisions/s", horizon=args.mpc_horizon,
                            cores=cores, sample=f"{n} robust-MPC decisions (oracle/mpc_oracle.py port of mpc.py)")
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# same-run parity: the benchmarked configuration's own outputs against the C oracle, on a sample
+# ------------------------------------------------------------------------------------------------
+def parity_chunk_steps(out, tid_h, off_h, base, n_windows=4, window=512):
+    """The trajectories the LAST timed step left in `out` ([V][N] device tensors) against oracle/abr_oracle.c run on
+    `n_windows` windows of `window` consecutive sessions of this rank's shard (same traces, offsets, seed and global
+    session indices).  Bit-exact is the bar (SPEC.md); the 1e-9 relative bar of BASELINE.json is reported beside it."""
+    import numpy as np
+    from abrsimulator_b200 import synth
+    from oracle import oracle as orc
+    N = tid_h.shape[0]
+    window = min(window, N)
+    starts = sorted({int(round(i * (N - window) / max(1, n_windows - 1))) for i in range(n_windows)})
+    bitrates, sizes = synth.make_video(V)
+    bw, tl, ti = synth.make_traces(N_TRACES, T_TRACE)
+    keys = (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"), ("reward", "reward"))
+    values = differ = 0
+    max_rel = 0.0
+    eov_ok = True
+    t0 = time.perf_counter()
+    for k0 in starts:
+        ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, window)
+        ref.reset(tid_h[k0:k0 + window], off_h[k0:k0 + window])
+        exp = ref.rollout(orc.POLICY_RANDOM, V, seed=SEED, session_base=base + k0)
+        for kg, kc in keys:
+            g = out[kg][:, k0:k0 + window].cpu().numpy()
+            e = exp[kc]
+            values += g.size
+            differ += int((g.view(np.uint64) != e.view(np.uint64)).sum())
+            max_rel = max(max_rel, float((np.abs(g - e) / np.maximum(np.abs(e), 1e-300)).max()))
+        eov_ok = eov_ok and bool(np.array_equal(out["end_of_video"][:, k0:k0 + window].cpu().numpy(), exp["eov"]))
+    return dict(checker="oracle/abr_oracle.c (SPEC.md restated; pinned to the reference's tick loop by tests/golden/sim_ref_tick_golden.json)",
+                sessions_checked=len(starts) * window, chunk_steps_checked=len(starts) * window * V,
+                values_checked=values, non_identical_values=differ, max_rel_err=max_rel, end_of_video_identical=eov_ok,
+                bar="bit-identical (SPEC.md); BASELINE.json: 1e-9 relative", ok=bool(differ == 0 and eov_ok),
+                seconds=time.perf_counter() - t0)
+
+
+def parity_mpc(menv, H, act, sample=2048):
+    """One robust-MPC launch at the benchmarked shape against the C oracle's exhaustive search on a strided sample of
+    sessions: the state the kernel is about to read is snapshotted, the launch runs, and the chosen actions must be
+    identical (SPEC §5.2: near-ties are resolved identically because nothing is reassociated)."""
+    import numpy as np
+    from oracle import oracle as orc
+    M = menv.n
+    idx = np.unique(np.linspace(0, M - 1, min(sample, M)).astype(np.int64))
+    import torch
+    ix = torch.from_numpy(idx).to(act.device)
+    snap = {f: menv.state(f).index_select(-1, ix).cpu().numpy().copy()
+            for f in ("chunk", "last_q", "buffer", "bw_hist", "hist_len", "last_pred", "err_ring", "err_len")}
+    menv.mpc_decide(H, "robust", out=act)
+    got = act.index_select(0, ix).cpu().numpy()
+    p = orc.make_params(**{k: getattr(menv.params, k) for k in ("chunk_length", "max_buffer", "rebuf_penalty",
+                                                               "smooth_penalty", "default_quality", "hist_k")})
+    sizes = menv.state("sizes").cpu().numpy()
+    util = menv.state("utility").cpu().numpy()
+    t0 = time.perf_counter()
+    lp = np.ascontiguousarray(snap["last_pred"])
+    er = np.ascontiguousarray(snap["err_ring"].T)
+    el = np.ascontiguousarray(snap["err_len"])
+    exp = orc.mpc_decide(sizes, util, snap["chunk"], snap["last_q"], snap["buffer"], np.ascontiguousarray(snap["bw_hist"].T),
+                         snap["hist_len"], H, 1, p, lp, er, el)
+    bad = int((got != exp["action"]).sum())
+    return dict(checker="oracle/abr_oracle.c exhaustive search (no prefix sharing)", decisions_checked=int(idx.size),
+                sequences_per_decision=A ** H, disagreements=bad, ok=bool(bad == 0 and exp["n_errors"] == 0),
+                seconds=time.perf_counter() - t0)
 
 
 def workload_config(args):
@@ -361,6 +432,7 @@ def run_ours(args):
     chunk_steps = world * N * V * args.steps
     value = chunk_steps / (total_ms * 1e-3)
     errors = env.error_count()
+    parity = parity_chunk_steps(out, tid_h, off_h, base) if rank == 0 else None
 
     # ---- optional fp32-output mode (fp64 arithmetic and state; 5 x 4 + 1 B of trajectory per chunk-step) ----
     out32 = {k: torch.empty(V, N, dtype=torch.float32, device=dev) for k in ("delay", "sleep", "buffer", "rebuffer", "reward")}
@@ -432,6 +504,30 @@ def run_ours(args):
     h2d = N * 4 + N * 8
     d2h = N * 8 + _lib.NUM_STATS * 8
 
+    # ---- e2e for a caller that wants the whole trajectory on the host (the north star's per-step outputs: delay, sleep,
+    #      buffer, rebuffer, reward, end_of_video for every chunk): host inputs -> device, abr_env_run, 41 B per chunk-step
+    #      back into pinned host buffers.  PCIe-bound by construction (129 MB per step). ----
+    traj_p = {k: torch.empty(V, N, dtype=t.dtype).pin_memory() for k, t in out.items()}
+    traj_ms = []
+    for it in range(2 + 5):
+        barrier()
+        t0 = time.perf_counter()
+        tid_d.copy_(tid_p, non_blocking=True)
+        off_d.copy_(off_p, non_blocking=True)
+        env.run("random", V, tid_d, off_d, seed=SEED, session_base=base, out=out, qoe_cost=False, stats=False)
+        for k in out:
+            traj_p[k].copy_(out[k], non_blocking=True)
+        torch.cuda.synchronize()
+        if it >= 2:
+            traj_ms.append(max_over_ranks(time.perf_counter() - t0, dev) * 1e3)
+    traj_ms.sort()
+    traj_bytes = sum(t.numel() * t.element_size() for t in traj_p.values())
+    e2e_traj = dict(value=world * N * V / (traj_ms[len(traj_ms) // 2] * 1e-3), unit="chunk-steps/s",
+                    ms_per_step=traj_ms[len(traj_ms) // 2], h2d_bytes_per_step=h2d, d2h_bytes_per_step=traj_bytes,
+                    d2h_gb_per_s=traj_bytes / (traj_ms[len(traj_ms) // 2] * 1e-3) / 1e9,
+                    call="abr_env_run + device->host copies of all six [48][N] trajectories into pinned buffers")
+    del traj_p
+
     # ---- MPC decisions/s (configs[2] sharded: robust MPC, horizon 5, 7 776 sequences per decision) ----
     mpc = None
     if not args.no_mpc:
@@ -481,9 +577,11 @@ def run_ours(args):
                          ms_per_step=1e3 * e2e_s / args.steps, timing="median of 5 blocks of K calls, wall clock, max over ranks",
                          blocks_ms_per_step=[1e3 * b / args.steps for b in blocks],
                          best_block_ms_per_step=1e3 * min(blocks) / args.steps,
-                         host_cores=(f"{len(cpus)} cores next to the GPU (NVML affinity)" if cpus else "unbound")),
+                         host_cores=(f"{len(cpus)} cores next to the GPU (NVML affinity)" if cpus else "unbound"),
+                         full_trajectory_to_host=e2e_traj),
                 gpu_launches=int(launches), clocks=clocks, wall_s_timed_region=wall,
-                qoe_stats=dict(zip(_lib.ACC_NAMES, [float(x) for x in tot_stats.cpu()])), flagged_sessions=errors)
+                qoe_stats=dict(zip(_lib.ACC_NAMES, [float(x) for x in tot_stats.cpu()])), flagged_sessions=errors,
+                parity=parity)
     if mpc:
         line["mpc"] = mpc
     line["bba_policy"] = bba
@@ -653,6 +751,7 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
     barrier()
     tot = max_over_ranks(sum(ms), dev)
     dec_per_s = world * M * reps / (tot * 1e-3)
+    mpc_parity = parity_mpc(menv, H, act) if rank == 0 else None     # outside the timed launches
     # reference-exact mode for comparison
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     menv.mpc_decide(H, "reference", out=act)
@@ -690,12 +789,65 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
         ms7 = max_over_ranks(e0.elapsed_time(e1), dev) / 3
         h7 = dict(horizon=7, sequences_per_decision=A ** 7, sessions_per_gpu=M7, ms_per_launch=ms7,
                   decisions_per_s=world * M7 / (ms7 * 1e-3), sequences_per_s=world * M7 * A ** 7 / (ms7 * 1e-3))
+    # configs[2] as BASELINE.json words it: "1M sessions sharded across 1/2/4/8 B200, final QoE all-reduce over NVLink" —
+    # a fixed total (strong scaling).  Timed region, CUDA events on the launching stream, max over ranks: reset + 48 x
+    # (decide + step) + statistics reduction + the all-gather of the per-rank statistics (the one collective).
+    strong = None
+    if args.mpc_strong_total > 0:
+        from abrsimulator_b200.distributed import allreduce_stats, shard_range
+        lo, hi = shard_range(args.mpc_strong_total, rank, world)
+        Ms = hi - lo
+        senv = menv if Ms <= M else BatchedABREnv(bw, sizes, bitrates, Ms, trace_len=tl, trace_interval=ti,
+                                                  track_history=1, track_acc=1)
+        tid_s, off_s = synth.make_sessions(Ms, N_TRACES, T_TRACE, session_base=lo, group=GROUP)
+        tid_sd, off_sd = torch.from_numpy(tid_s).to(dev), torch.from_numpy(off_s).to(dev)
+        coll_ms = []
+        tot_ms = []
+        for it in range(2):                                        # first pass warms up (NCCL communicator, allocator)
+            barrier()
+            e0.record(stream)
+            senv.reset(tid_sd, off_sd, session_base=lo)
+            senv.mpc_episode(V, H, "robust")
+            st_s = senv.stats()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            tot_s = allreduce_stats(st_s)
+            c1.record(stream)
+            e1.record(stream)
+            e1.synchronize()
+            tot_ms.append(max_over_ranks(e0.elapsed_time(e1), dev))
+            coll_ms.append(max_over_ranks(c0.elapsed_time(c1), dev))
+        strong = dict(workload="configs[2]: robust MPC, horizon 5, fixed total sharded over the GPUs, whole 48-chunk "
+                               "episode + final statistics all-reduce", scaling="strong",
+                      total_sessions=args.mpc_strong_total, sessions_per_gpu=Ms, chunks=V, ms=tot_ms[-1],
+                      decisions_per_s=args.mpc_strong_total * V / (tot_ms[-1] * 1e-3),
+                      collective=dict(op="all_gather of the per-rank statistics vector + rank-order sum (deterministic)",
+                                      bytes_per_rank=int(st_s.numel() * 8), ms=coll_ms[-1], inside_timed_region=True,
+                                      backend="nccl" if world > 1 else "none (one rank)"),
+                      mean_reward_per_chunk=float(tot_s[0] / tot_s[6]), steps_total=float(tot_s[6]))
+        if senv is not menv:
+            del senv
     res = dict(metric="mpc_decisions_per_sec", value=dec_per_s, unit="decisions/s", horizon=H, mode="robust",
                sequences_per_decision=A ** H, sessions_per_gpu=M, ms_per_launch=sum(ms) / len(ms),
                reference_exact_mode_decisions_per_s_per_gpu=ref_mode_rate,
                episode=dict(chunks=V, ms=ep_ms, decisions_per_s=world * M * V / (ep_ms * 1e-3),
-                            mean_reward_per_chunk=float(st[0] / st[6])), horizon7=h7)
+                            mean_reward_per_chunk=float(st[0] / st[6])), horizon7=h7, parity=mpc_parity, strong_scaling=strong)
     if rank == 0:
+        # drop-in controller latency: one next_bitrate() through abr_mpc_decide_host (mpc_test.py's scenario, horizon 5);
+        # the reference's own mpc.py + scipy.optimize.brute: 0.14-0.19 s per A=6, H=5 decision, 26 ms at A=4 (SURVEY.md:199)
+        from examples.mpc_dropin import reference_scenario
+        from abrsimulator_b200.mpc import MPCBitrateController
+        ctl = MPCBitrateController(reference_scenario()[0], horizon=H, strict_history=False)
+        lat = []
+        for it in range(60):
+            t0 = time.perf_counter()
+            ctl.next_bitrate()
+            if it >= 10:
+                lat.append((time.perf_counter() - t0) * 1e6)
+        lat.sort()
+        res["single_decision"] = dict(call="MPCBitrateController(player, horizon=5).next_bitrate() -> abr_mpc_decide_host "
+                                           "(one host->device copy, one kernel, one device->host copy; no allocation)",
+                                      median_us=lat[len(lat) // 2], p90_us=lat[int(len(lat) * 0.9)])
         lib = _lib.load()
         probe = {}
         for kind, name in ((0, "dadd"), (1, "dfma"), (2, "dadd_dmul_dsetp_mix")):
@@ -706,8 +858,10 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
         # fp64-pipe thread-instructions the search executes per decision, counted from the SASS of the
         # inner loops: per prefix slot (rounded up to whole warps) one interior step (9) + A interior steps (9 each) +
         # A^2 leaves (7 arithmetic + 1 compare with smooth_penalty == 1), plus the parent-state cache fill
-        rounds = -(-(A ** (H - 2)) // 32) * 32
-        executed = rounds * (9 + A * 9 + A * A * 8) + 64 * (H - 3) * 9
+        # useful work only: the A^(H-2) = 216 real prefixes (the 8 idle lane-slots of the seventh warp-round are not
+        # counted as achieved work)
+        prefixes = A ** (H - 2)
+        executed = prefixes * (9 + A * 9 + A * A * 8) + (A ** (H - 3) if H >= 3 else 0) * (H - 3) * 9
         naive = A ** H * (14 * (H - 1) + 13) + 4 * A * H
         peak = probe["dadd_gops"]
         res["roofline"] = dict(bound="fp64-issue", unit="Gop/s", peak=peak, peak_source="abr_fp64_probe (DADD chains, same run)",

@@ -36,7 +36,9 @@ enum { ABR_POLICY_FIXED = 0, ABR_POLICY_RANDOM = 1, ABR_POLICY_BBA = 2 };
 /* MPC modes (SPEC §5): 0 = reference-exact mpc.py, 1 = robust MPC */
 enum { ABR_MPC_REF = 0, ABR_MPC_ROBUST = 1 };
 /* abr_mpc_decide flags */
-enum { ABR_MPC_TRUNCATE = 1,        /* mode 0: k+H > V truncates the horizon instead of flagging IndexError (mpc.py:125-128, D13) */
+enum { ABR_MPC_PRED_SES = 4,        /* mode 0: predictor "expsmoothing" (mpc.py:72-79) instead of "harmonic": the flat forecast of simple
+                                      exponential smoothing, alpha = 0.5, least-squares initial level (SPEC 5.4) */
+       ABR_MPC_TRUNCATE = 1,        /* mode 0: k+H > V truncates the horizon instead of flagging IndexError (mpc.py:125-128, D13) */
        ABR_MPC_EMPTY_DEFAULT = 2 }; /* mode 0: empty history returns default_quality instead of flagging ZeroDivisionError (mpc.py:90, D14) */
 
 /* rows of the accumulator table / entries of the statistics vector (SPEC §6) */
@@ -203,6 +205,27 @@ int abr_mpc_decide(const double* d_sizes, const double* d_utility, int V, int A,
                    double* d_err_ring, int32_t* d_err_len, int horizon, int mode, int flags, int32_t* d_action,
                    double* d_best_j, int32_t* d_best_seq /*[N][H]*/, double* d_preds /*[N][H]*/,
                    int32_t* d_error_count, void* stream);
+/* Start-up phase of the controller (f_st of the pseudo-code at mpc.py:7-18; the reference leaves its start-up delay
+ * at 0, "TODO", mpc.py:141, and weighs it with startup_weight, mpc.py:160).  SPEC 5.3: sessions with d_startup[s] != 0
+ * (NULL = all) choose, besides the bitrate sequence, a start-up delay T_s on the grid {0, ts_step, ..., (n_ts-1)*ts_step}:
+ * T_s is credited to the initial buffer of the lookahead and charged params->startup_penalty * T_s; d_startup_delay[N]
+ * receives the chosen T_s ("start playback after T_s seconds"), 0 for sessions outside the start-up phase. */
+int abr_mpc_decide_startup(const double* d_sizes, const double* d_utility, int V, int A, const AbrParams* params, int N,
+                           const int32_t* d_chunk_idx, const int32_t* d_prev_q, const double* d_buffer,
+                           const double* d_bw_hist, const int32_t* d_hist_len, int K, double* d_last_pred,
+                           double* d_err_ring, int32_t* d_err_len, int horizon, int mode, int flags,
+                           const uint8_t* d_startup, int n_ts, double ts_step, int32_t* d_action,
+                           double* d_startup_delay, double* d_best_j, int32_t* d_best_seq, double* d_preds,
+                           int32_t* d_error_count, void* stream);
+int abr_mpc_decide_startup_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params,
+                                int N, const int32_t* h_chunk_idx, const int32_t* h_prev_q, const double* h_buffer,
+                                const double* h_bw_hist, const int32_t* h_hist_len, int K, double* h_last_pred,
+                                double* h_err_ring, int32_t* h_err_len, int horizon, int mode, int flags,
+                                const uint8_t* h_startup, int n_ts, double ts_step, int32_t* h_action,
+                                double* h_startup_delay, double* h_best_j, int32_t* h_best_seq, double* h_preds,
+                                int32_t* h_error_count);
+/* Host-buffer decisions stage through one arena per host thread (grow-only): a call is one host->device copy, one
+ * kernel launch and one device->host copy, without any allocation once the arena has its size. */
 int abr_mpc_decide_host(const double* h_sizes, const double* h_bitrates, int V, int A, const AbrParams* params, int N,
                         const int32_t* h_chunk_idx, const int32_t* h_prev_q, const double* h_buffer,
                         const double* h_bw_hist, const int32_t* h_hist_len, int K, double* h_last_pred,

@@ -446,11 +446,13 @@ static double rollout_j(const double* U /*[H][A]*/, const double* RB, const doub
 /* hist: n samples oldest first.  Returns 1 on input error (action = -1). */
 static int mpc_one(const double* sizes, const double* util, int V, int A, const OrcParams* p, int k, int prev_q,
                    double buffer, const double* hist, int n, int H, int mode, double* last_pred, double* err_ring,
-                   int32_t* err_len, int K, int32_t* action, double* best_j, int32_t* best_seq, double* preds_out) {
+                   int32_t* err_len, int K, int32_t* action, double* best_j, int32_t* best_seq, double* preds_out,
+                   int ses, int n_ts, double ts_step, double* ts_out) {
     double U[MAXH * 16], RB[MAXH * 16], DL[MAXH * 16];
     const double L = p->chunk_length, B = p->max_buffer;
     int h = H;
     *action = -1;
+    if (ts_out) *ts_out = 0.0;
     if (best_j) *best_j = NAN;
     if (best_seq) for (int i = 0; i < H; ++i) best_seq[i] = -1;
     if (H < 1 || H > MAXH || A > 16 || k < 0) return 1;
@@ -461,8 +463,22 @@ static int mpc_one(const double* sizes, const double* util, int V, int A, const 
             if (hist[j] == 0.0) return 1;                                  /* ZeroDivisionError, mpc.py:88 */
             S = S + 1.0 / hist[j];
         }
+        double l_n = 0.0;
+        if (ses) {   /* SPEC 5.4: predictor "expsmoothing", mpc.py:72-79 — flat forecast of simple exponential smoothing,
+                        alpha = 0.5, initial level = least-squares fit of the one-step errors (l_t = la + lb * l_0) */
+            double la = 0.0, lb = 1.0, num = 0.0, den = 0.0;
+            for (int j = 0; j < n; ++j) {
+                double r = hist[j] - la;
+                num = num + lb * r;
+                den = den + lb * lb;
+                la = 0.5 * hist[j] + 0.5 * la;
+                lb = 0.5 * lb;
+            }
+            l_n = la + lb * (num / den);
+            if (!(l_n > 0.0)) return 1;
+        }
         for (int i = 0; i < H; ++i) {                                      /* mpc.py:83-92 incl. D10 */
-            double pi = (double)(n + i) / S;
+            double pi = ses ? l_n : (double)(n + i) / S;
             S = S + 1.0 / pi;
             if (preds_out) preds_out[i] = pi;
             for (int a = 0; a < A; ++a) {
@@ -504,18 +520,33 @@ static int mpc_one(const double* sizes, const double* util, int V, int A, const 
                 U[i * A + a] = util[(k + i) * A + a];
             }
     }
-    int R[MAXH] = {0};
+    /* SPEC 5.3: in the start-up phase the start-up delay T_s = jt * ts_step is a second decision variable, slowest axis */
     double bj = 0.0;
     int have = 0;
-    for (;;) {
-        double j = rollout_j(U, RB, DL, A, h, R, prev_q, buffer, mode != 0, L, B, p->smooth_penalty, p->rebuf_penalty);
-        if (!have || j < bj) {                                             /* first minimum, C order */
-            have = 1; bj = j; *action = R[0];
-            if (best_seq) for (int i = 0; i < h; ++i) best_seq[i] = R[i];
+    if (n_ts < 1) n_ts = 1;
+    for (int jt = 0; jt < n_ts; ++jt) {
+        const double ts = jt == 0 ? 0.0 : (double)jt * ts_step;
+        const double b0 = jt == 0 ? buffer : buffer + ts;
+        int R[MAXH] = {0};
+        double bj_t = 0.0;
+        int have_t = 0, act_t = -1, seq_t[MAXH];
+        for (;;) {
+            double j = rollout_j(U, RB, DL, A, h, R, prev_q, b0, mode != 0, L, B, p->smooth_penalty, p->rebuf_penalty);
+            if (!have_t || j < bj_t) {                                         /* first minimum, C order */
+                have_t = 1; bj_t = j; act_t = R[0];
+                for (int i = 0; i < h; ++i) seq_t[i] = R[i];
+            }
+            int d = h - 1;
+            while (d >= 0 && ++R[d] == A) { R[d] = 0; --d; }
+            if (d < 0) break;
         }
-        int d = h - 1;
-        while (d >= 0 && ++R[d] == A) { R[d] = 0; --d; }
-        if (d < 0) break;
+        /* q = -J ; total = q - sw * T_s ; strict improvement keeps the smaller T_s on ties */
+        const double tot = n_ts == 1 ? bj_t : -((-bj_t) - p->startup_penalty * ts);
+        if (!have || tot < bj) {
+            have = 1; bj = tot; *action = act_t;
+            if (ts_out) *ts_out = ts;
+            if (best_seq) for (int i = 0; i < h; ++i) best_seq[i] = seq_t[i];
+        }
     }
     if (best_j) *best_j = bj;
     return 0;
@@ -528,23 +559,36 @@ static int gather_hist(const double* ring, int len, int K, double* out) {
     return n;
 }
 
+void orc_mpc_decide_ex(const double* sizes, const double* util, int V, int A, const OrcParams* p, int N,
+                       const int32_t* chunk_idx, const int32_t* prev_q, const double* buffer,
+                       const double* bw_hist, const int32_t* hist_len, int K,
+                       double* last_pred, double* err_ring, int32_t* err_len,
+                       int H, int mode, int ses, const uint8_t* startup, int n_ts, double ts_step,
+                       int32_t* action, double* startup_delay, double* best_j, int32_t* best_seq, double* preds,
+                       int32_t* n_errors) {
+    double* tmp = (double*)malloc(sizeof(double) * (K > 0 ? K : 1));
+    int errs = 0;
+    for (int s = 0; s < N; ++s) {
+        int n = gather_hist(bw_hist + (size_t)s * K, hist_len[s], K, tmp);
+        int nts = (n_ts > 1 && (!startup || startup[s])) ? n_ts : 1;
+        errs += mpc_one(sizes, util, V, A, p, chunk_idx[s], prev_q[s], buffer[s], tmp, n, H, mode,
+                        last_pred ? last_pred + s : 0, err_ring ? err_ring + (size_t)s * K : 0,
+                        err_len ? err_len + s : 0, K, action + s, best_j ? best_j + s : 0,
+                        best_seq ? best_seq + (size_t)s * H : 0, preds ? preds + (size_t)s * H : 0,
+                        ses, nts, ts_step, startup_delay ? startup_delay + s : 0);
+    }
+    free(tmp);
+    if (n_errors) *n_errors = errs;
+}
+
 void orc_mpc_decide(const double* sizes, const double* util, int V, int A, const OrcParams* p, int N,
                     const int32_t* chunk_idx, const int32_t* prev_q, const double* buffer,
                     const double* bw_hist, const int32_t* hist_len, int K,
                     double* last_pred, double* err_ring, int32_t* err_len,
                     int H, int mode, int32_t* action, double* best_j, int32_t* best_seq, double* preds,
                     int32_t* n_errors) {
-    double* tmp = (double*)malloc(sizeof(double) * (K > 0 ? K : 1));
-    int errs = 0;
-    for (int s = 0; s < N; ++s) {
-        int n = gather_hist(bw_hist + (size_t)s * K, hist_len[s], K, tmp);
-        errs += mpc_one(sizes, util, V, A, p, chunk_idx[s], prev_q[s], buffer[s], tmp, n, H, mode,
-                        last_pred ? last_pred + s : 0, err_ring ? err_ring + (size_t)s * K : 0,
-                        err_len ? err_len + s : 0, K, action + s, best_j ? best_j + s : 0,
-                        best_seq ? best_seq + (size_t)s * H : 0, preds ? preds + (size_t)s * H : 0);
-    }
-    free(tmp);
-    if (n_errors) *n_errors = errs;
+    orc_mpc_decide_ex(sizes, util, V, A, p, N, chunk_idx, prev_q, buffer, bw_hist, hist_len, K, last_pred, err_ring,
+                      err_len, H, mode, 0, 0, 1, 0.0, action, 0, best_j, best_seq, preds, n_errors);
 }
 
 void orc_env_mpc_decide(OrcEnv* e, int H, int mode, int32_t* action, double* best_j, int32_t* best_seq) {
@@ -558,11 +602,11 @@ void orc_env_mpc_decide(OrcEnv* e, int H, int mode, int32_t* action, double* bes
         if (mode == 0 && e->chunk[s] + H > e->V) { /* env flow never raises: truncate like mode 1 */
             int h = e->V - e->chunk[s];
             e->errors += mpc_one(e->sizes, e->util, e->V, e->A, &e->p, e->chunk[s], e->last_q[s], e->buffer[s], tmp, n,
-                                 h, 0, 0, 0, 0, e->K, action + s, best_j ? best_j + s : 0, 0, 0);
+                                 h, 0, 0, 0, 0, e->K, action + s, best_j ? best_j + s : 0, 0, 0, 0, 1, 0.0, 0);
             continue;
         }
         e->errors += mpc_one(e->sizes, e->util, e->V, e->A, &e->p, e->chunk[s], e->last_q[s], e->buffer[s], tmp, n, H,
                              mode, e->last_pred + s, e->err_ring + (size_t)s * e->K, e->err_len + s, e->K,
-                             action + s, best_j ? best_j + s : 0, best_seq ? best_seq + (size_t)s * H : 0, 0);
+                             action + s, best_j ? best_j + s : 0, best_seq ? best_seq + (size_t)s * H : 0, 0, 0, 1, 0.0, 0);
     }
 }

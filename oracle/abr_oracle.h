@@ -74,6 +74,17 @@ void orc_mpc_decide(const double* sizes, const double* util, int V, int A, const
                     int H, int mode, int32_t* action, double* best_j, int32_t* best_seq, double* preds,
                     int32_t* n_errors);
 
+/* the same with the two off-default features of SPEC 5.3 / 5.4: ses != 0 selects the "expsmoothing" predictor of
+ * mpc.py:72-79 (mode 0 only); n_ts > 1 adds the start-up delay T_s = jt * ts_step as a decision variable for the
+ * sessions with startup[s] != 0 (NULL = all), returned in startup_delay[N] */
+void orc_mpc_decide_ex(const double* sizes, const double* util, int V, int A, const OrcParams* p, int N,
+                       const int32_t* chunk_idx, const int32_t* prev_q, const double* buffer,
+                       const double* bw_hist, const int32_t* hist_len, int K,
+                       double* last_pred, double* err_ring, int32_t* err_len,
+                       int H, int mode, int ses, const uint8_t* startup, int n_ts, double ts_step,
+                       int32_t* action, double* startup_delay, double* best_j, int32_t* best_seq, double* preds,
+                       int32_t* n_errors);
+
 /* helpers exposed for unit tests */
 void orc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]);
 void orc_utility_table(const double* bitrates, int V, int A, int mode, double scale, double* util);

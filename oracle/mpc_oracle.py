@@ -114,6 +114,66 @@ def decide_ref(k, prev_q, buffer_level, history, H, bitrates, sizes,
 
 
 # ----------------------------------------------------------------------------
+# SPEC §5.4: predictor "expsmoothing" (mpc.py:72-79) — parity unpinned (statsmodels is not installed here)
+# ----------------------------------------------------------------------------
+
+def predict_ses(horizon, history, alpha=0.5):
+    """``SimpleExpSmoothing(data).fit(0.5).predict(n, n+horizon-1)`` (mpc.py:72-79) in closed form.
+
+    Simple exponential smoothing keeps a level ``l_t = alpha*y_t + (1-alpha)*l_{t-1}`` and forecasts it flat:
+    every one of the ``horizon`` predictions is ``l_n``.  statsmodels' ``fit`` with a fixed smoothing level estimates the
+    initial level ``l_0`` by minimising the sum of squared one-step errors ``sum_t (y_t - l_{t-1})**2``; with ``alpha``
+    fixed every ``l_t`` is affine in ``l_0`` (``l_t = la_t + lb_t*l_0``), so that minimisation is a one-dimensional
+    linear least-squares problem with the solution computed below (statsmodels reaches the same point with a numerical
+    optimiser, to its tolerance).  alpha = 0.5 here (``fit(0.5)``), so ``lb_t = 0.5**t`` exactly."""
+    if len(history) == 0:
+        raise ZeroDivisionError("empty throughput history")
+    la, lb, num, den = 0.0, 1.0, 0.0, 0.0
+    for y in history:
+        r = y - la
+        num = num + lb * r
+        den = den + lb * lb
+        la = alpha * y + (1.0 - alpha) * la
+        lb = (1.0 - alpha) * lb
+    l_n = la + lb * (num / den)
+    return [l_n] * horizon
+
+
+def decide_ref_ses(k, prev_q, buffer_level, history, H, bitrates, sizes, chunk_length, max_buffer, vw, rw, utility=None):
+    """Profile R's search (objective and enumeration of SPEC §5.1) over the "expsmoothing" predictions."""
+    A = len(bitrates[0])
+    preds = predict_ses(H, history)
+    best_j, best_seq = None, None
+    for R in itertools.product(range(A), repeat=H):
+        j = objective_ref(R, k, prev_q, buffer_level, preds, bitrates, sizes, chunk_length, max_buffer, vw, rw, utility)
+        if best_j is None or j < best_j:
+            best_j, best_seq = j, R
+    return dict(action=int(best_seq[0]), best_seq=list(best_seq), best_J=best_j, preds=preds)
+
+
+# ----------------------------------------------------------------------------
+# SPEC §5.3: start-up phase (f_st of mpc.py:7-18; the reference's TODO at mpc.py:141) — defined by SPEC.md
+# ----------------------------------------------------------------------------
+
+def decide_startup(objective_of_buffer, A, h, buffer_level, sw, n_ts, ts_step):
+    """``objective_of_buffer(R, b0) -> J`` is one of the two objectives above with the initial buffer exposed.
+    Start-up delay T_s = jt*ts_step is the slowest axis; total cost J + sw*T_s computed as -((-J) - sw*T_s)."""
+    best, best_seq, best_ts = None, None, 0.0
+    for jt in range(n_ts):
+        ts = 0.0 if jt == 0 else jt * ts_step
+        b0 = buffer_level if jt == 0 else buffer_level + ts
+        bj, bs = None, None
+        for R in itertools.product(range(A), repeat=h):
+            j = objective_of_buffer(R, b0)
+            if bj is None or j < bj:
+                bj, bs = j, R
+        tot = -((-bj) - sw * ts)
+        if best is None or tot < best:
+            best, best_seq, best_ts = tot, bs, ts
+    return dict(action=int(best_seq[0]), best_seq=list(best_seq), best_J=best, startup_delay=best_ts)
+
+
+# ----------------------------------------------------------------------------
 # Profile N: robust MPC (SPEC.md §5.2)
 # ----------------------------------------------------------------------------
 

@@ -188,8 +188,10 @@ def stats_from_acc(acc):
 
 
 def mpc_decide(sizes, util, chunk_idx, prev_q, buffer, bw_hist, hist_len, H, mode, params=None,
-               last_pred=None, err_ring=None, err_len=None):
-    """Standalone batched decision (orc_mpc_decide).  Returns dict of numpy arrays."""
+               last_pred=None, err_ring=None, err_len=None, ses=False, startup=None, n_ts=1, ts_step=0.0):
+    """Standalone batched decision (orc_mpc_decide_ex).  Returns dict of numpy arrays.  ``ses``: predictor
+    "expsmoothing" (SPEC 5.4); ``n_ts`` > 1: start-up phase with the delay grid jt * ts_step (SPEC 5.3) for the sessions
+    with ``startup`` != 0 (None = all)."""
     sizes, util = _f64(sizes), _f64(util)
     V, A = sizes.shape
     chunk_idx, prev_q, hist_len = _i32(chunk_idx), _i32(prev_q), _i32(hist_len)
@@ -201,7 +203,10 @@ def mpc_decide(sizes, util, chunk_idx, prev_q, buffer, bw_hist, hist_len, H, mod
     seq = np.empty((N, H), np.int32)
     preds = np.empty((N, H))
     nerr = C.c_int32(0)
-    lib().orc_mpc_decide(_p(sizes), _p(util), C.c_int(V), C.c_int(A), C.byref(p), C.c_int(N), _p(chunk_idx),
-                         _p(prev_q), _p(buffer), _p(bw_hist), _p(hist_len), C.c_int(K), _p(last_pred), _p(err_ring),
-                         _p(err_len), C.c_int(H), C.c_int(mode), _p(act), _p(bj), _p(seq), _p(preds), C.byref(nerr))
-    return dict(action=act, best_J=bj, best_seq=seq, preds=preds, n_errors=nerr.value)
+    ts = np.zeros(N)
+    su = None if startup is None else np.ascontiguousarray(startup, dtype=np.uint8)
+    lib().orc_mpc_decide_ex(_p(sizes), _p(util), C.c_int(V), C.c_int(A), C.byref(p), C.c_int(N), _p(chunk_idx),
+                            _p(prev_q), _p(buffer), _p(bw_hist), _p(hist_len), C.c_int(K), _p(last_pred), _p(err_ring),
+                            _p(err_len), C.c_int(H), C.c_int(mode), C.c_int(1 if ses else 0), _p(su), C.c_int(n_ts),
+                            C.c_double(ts_step), _p(act), _p(ts), _p(bj), _p(seq), _p(preds), C.byref(nerr))
+    return dict(action=act, best_J=bj, best_seq=seq, preds=preds, n_errors=nerr.value, startup_delay=ts)

@@ -109,7 +109,7 @@ def _random_batch(rng, N, V, A, K, ties):
                 buffer=np.round(rng.uniform(0, 40, size=N), 1 if ties else 9), bw_hist=bw_hist, hist_len=hist_len)
 
 
-def _run_both(b, V, A, K, H, mode, params_kw, flags=0, robust_state=False, N=None):
+def _run_both(b, V, A, K, H, mode, params_kw, flags=0, robust_state=False, N=None, startup=None, n_ts=1, ts_step=0.0):
     dev = torch.device("cuda")
     p_gpu = _lib.default_params(**params_kw)
     p_cpu = orc.make_params(**params_kw)
@@ -124,11 +124,12 @@ def _run_both(b, V, A, K, H, mode, params_kw, flags=0, robust_state=False, N=Non
         st_cpu = (lp.copy(), er.copy(), el.copy())
         st_gpu = tuple(torch.from_numpy(x.copy()).to(dev) for x in (lp, er, el))
     exp = orc.mpc_decide(b["sizes"], util, b["chunk"], b["prev_q"], b["buffer"], b["bw_hist"], b["hist_len"], H, mode,
-                         p_cpu, *st_cpu)
+                         p_cpu, *st_cpu, ses=bool(flags & _lib.MPC_PRED_SES), startup=startup, n_ts=n_ts, ts_step=ts_step)
     t = lambda x, dt: torch.from_numpy(np.ascontiguousarray(x)).to(dev, dt)
     got = decide_batch(t(b["sizes"], torch.float64), t(util, torch.float64), t(b["chunk"], torch.int32),
                        t(b["prev_q"], torch.int32), t(b["buffer"], torch.float64), t(b["bw_hist"], torch.float64),
-                       t(b["hist_len"], torch.int32), H, mode, flags, p_gpu, *st_gpu)
+                       t(b["hist_len"], torch.int32), H, mode, flags, p_gpu, *st_gpu,
+                       startup=None if startup is None else t(startup, torch.uint8), n_ts=n_ts, ts_step=ts_step)
     torch.cuda.synchronize()
     return exp, got, st_cpu, st_gpu
 
@@ -171,6 +172,107 @@ def test_mode1_robust_batch_matches_oracle(A, H):
     er_g, er_c = st_gpu[1].cpu().numpy(), st_cpu[1]
     for s in range(0, len(m), 37):
         assert bits_equal(er_g[s, :m[s]], er_c[s, :m[s]]) == 0
+
+
+@pytest.mark.parametrize("A,H", [(2, 5), (4, 3), (6, 5), (6, 1), (8, 2)])
+def test_expsmoothing_predictor_matches_oracle(A, H):
+    """SPEC §5.4 (mpc.py:72-79): flat forecast of simple exponential smoothing, least-squares initial level."""
+    rng = np.random.default_rng(3000 * A + H)
+    N, V, K = (1024 if A ** H <= 1300 else 256), 48, 9
+    b = _random_batch(rng, N, V, A, K, False)
+    b["chunk"] = rng.integers(0, V - H + 1, size=N).astype(np.int32)
+    b["hist_len"][:8] = 1                                              # one sample: the level is the sample
+    kw = dict(chunk_length=4.0, max_buffer=20.0, utility_scale=1.0)
+    exp, got, _, _ = _run_both(b, V, A, K, H, 0, kw, flags=_lib.MPC_PRED_SES)
+    assert exp["n_errors"] == 0 and int(got["errors"].item()) == 0
+    assert bits_equal(got["preds"].cpu().numpy(), exp["preds"]) == 0
+    assert np.array_equal(got["action"].cpu().numpy(), exp["action"])
+    assert np.array_equal(got["best_seq"].cpu().numpy(), exp["best_seq"])
+    assert bits_equal(got["best_j"].cpu().numpy(), exp["best_J"]) == 0
+    p = got["preds"].cpu().numpy()
+    assert np.all(p == p[:, :1])                                       # flat
+    first = b["bw_hist"][:8, 0]
+    assert np.array_equal(p[:8, 0], first)
+    # the robust mode has its own predictor
+    with pytest.raises(_lib.AbrError):
+        _run_both(b, V, A, K, H, 1, kw, flags=_lib.MPC_PRED_SES)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("A,H", [(3, 4), (6, 5), (6, 1), (6, 7)])
+def test_startup_phase_decision_matches_oracle(mode, A, H):
+    """SPEC §5.3 (f_st of mpc.py:7-18): the start-up delay on a grid as a second decision variable; sessions outside the
+    start-up phase take the plain decision; warp-per-session and block-per-session (horizon 7) kernels."""
+    rng = np.random.default_rng(4000 * A + 10 * H + mode)
+    N, V, K = (512 if A ** H <= 1300 else 96 if H < 7 else 4), 48, 5
+    b = _random_batch(rng, N, V, A, K, False)
+    b["chunk"] = rng.integers(0, V - H + 1, size=N).astype(np.int32)
+    b["buffer"] = np.round(rng.uniform(0, 6, size=N), 9)              # start-up: little buffered
+    startup = (rng.random(N) < 0.7).astype(np.uint8)
+    kw = dict(chunk_length=4.0, max_buffer=30.0, startup_penalty=0.5, hist_k=K)
+    n_ts, step = (6, 0.75) if H < 7 else (3, 1.5)
+    exp, got, _, _ = _run_both(b, V, A, K, H, mode, kw, startup=startup, n_ts=n_ts, ts_step=step)
+    assert exp["n_errors"] == 0 and int(got["errors"].item()) == 0
+    assert np.array_equal(got["action"].cpu().numpy(), exp["action"])
+    assert np.array_equal(got["best_seq"].cpu().numpy(), exp["best_seq"])
+    assert bits_equal(got["best_j"].cpu().numpy(), exp["best_J"]) == 0
+    ts = got["startup_delay"].cpu().numpy()
+    assert bits_equal(ts, exp["startup_delay"]) == 0
+    assert np.all(ts[startup == 0] == 0.0) and ((ts > 0).any() or N < 96)
+    # startup = None means every session; n_ts = 1 is the plain decision bit for bit
+    exp_all, got_all, _, _ = _run_both(b, V, A, K, H, mode, kw, n_ts=n_ts, ts_step=step)
+    assert bits_equal(got_all["startup_delay"].cpu().numpy(), exp_all["startup_delay"]) == 0
+    assert np.array_equal(got_all["action"].cpu().numpy(), exp_all["action"])
+    _, plain, _, _ = _run_both(b, V, A, K, H, mode, kw)
+    off = startup == 0
+    assert np.array_equal(got["action"].cpu().numpy()[off], plain["action"].cpu().numpy()[off])
+    assert bits_equal(got["best_j"].cpu().numpy()[off], plain["best_j"].cpu().numpy()[off]) == 0
+
+
+def test_facade_expsmoothing_and_startup():
+    """predict_throughput(method="expsmoothing") (mpc.py:72-79) and next_bitrate_startup() (mpc.py:7-18) of the drop-in
+    controller, against the Python restatement of SPEC §5.3 / §5.4."""
+    from oracle import mpc_oracle as mo
+    from abrsimulator_b200.datamodel import Chunk, MPD, QOEMetric, ChunkInfo
+    V = 20
+    ladder = [300.0, 750.0, 1200.0, 1850.0, 2850.0, 4300.0]
+    chunks = [Chunk(list(ladder), [b * 4.0 for b in ladder]) for _ in range(V)]
+    mpd = MPD(V, 4.0, 30.0, 8.0, chunks)
+    qoe = QOEMetric(4.3, 1.0, 25.0, 0.0)            # rebuffer, variance, startup, latency weights
+    hist = [1800.0, 2500.0, 900.0, 3100.0, 2200.0]
+
+    class Player:
+        def __init__(self):
+            self.info = ChunkInfo(2, 1, list(hist), 1.0)
+
+        def get_mpd(self):
+            return mpd
+
+        def get_qoe_metric(self):
+            return qoe
+
+        def get_next_chunk_info(self):
+            return self.info
+
+    ctl = MPCBitrateController(Player(), horizon=4, strict_history=False)
+    p = ctl.predict_throughput(4, list(hist), method="expsmoothing")
+    assert isinstance(p, np.ndarray) and list(p) == mo.predict_ses(4, hist)
+    with pytest.raises(ValueError):
+        ctl.predict_throughput(4, list(hist), method="arima")
+    # a controller that decides with that predictor
+    ctl_s = MPCBitrateController(Player(), horizon=4, predictor="expsmoothing")
+    bitrates = [list(ladder)] * V
+    sizes = [[b * 4.0 for b in ladder]] * V
+    r = mo.decide_ref_ses(2, 1, 1.0, hist, 4, bitrates, sizes, 4.0, 30.0, 1.0, 4.3)
+    assert ctl_s.next_bitrate() == r["action"]
+    assert ctl_s.predicted_bandwidths == r["preds"]
+    assert ctl_s.player.info.previous_bandwidths == hist             # the expsmoothing branch does not mutate (D10 is harmonic's)
+    # start-up branch
+    act, ts = ctl.next_bitrate_startup(n_ts=12, ts_step=0.5)
+    preds, _ = mo.predict_harmonic_ref(4, hist)
+    obj = lambda R, b0: mo.objective_ref(R, 2, 1, b0, preds, bitrates, sizes, 4.0, 30.0, 1.0, 4.3)
+    want = mo.decide_startup(obj, 6, 4, 1.0, 25.0, 12, 0.5)
+    assert (act, ts) == (want["action"], want["startup_delay"]) and ts > 0.0
 
 
 def test_horizon7_block_per_session():

@@ -111,3 +111,82 @@ def test_reference_error_behaviour(golden):
     for name in ("index_error_k56", "empty_history", "zero_sample"):
         r = _c_decide(by[name]["scenario"])
         assert r["action"][0] == -1 and r["n_errors"] == 1
+
+
+# ---- SPEC §5.4 / §5.3: the two parts of mpc.py the default path never reaches ----
+def test_ses_closed_form_is_the_least_squares_initial_level():
+    """mpc.py:72-79 calls statsmodels' SimpleExpSmoothing(data).fit(0.5): fixed smoothing level, initial level estimated
+    by minimising the sum of squared one-step errors.  statsmodels is not installed here (parity unpinned); this checks
+    that the closed form of SPEC §5.4 is the minimiser a numerical optimiser finds for that same objective, and the
+    textbook identities of simple exponential smoothing."""
+    from scipy.optimize import minimize_scalar
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 5, 8, 20, 60):
+        y = rng.uniform(0.2, 6.0, size=n)
+
+        def level_and_sse(l0):
+            lvl, sse = l0, 0.0
+            for v in y:
+                sse += (v - lvl) ** 2
+                lvl = 0.5 * v + 0.5 * lvl
+            return lvl, sse
+
+        pred = mo.predict_ses(4, list(y))
+        assert len(pred) == 4 and len(set(pred)) == 1                      # flat forecast
+        best = minimize_scalar(lambda l0: level_and_sse(l0)[1], bracket=(0.0, 6.0), tol=1e-14)
+        assert abs(level_and_sse(best.x)[0] - pred[0]) <= 1e-6 * max(1.0, abs(pred[0])), n
+        # perturbing the closed-form initial level never lowers the objective
+        la, lb, num, den = 0.0, 1.0, 0.0, 0.0
+        for v in y:
+            num, den = num + lb * (v - la), den + lb * lb
+            la, lb = 0.5 * v + 0.5 * la, 0.5 * lb
+        l0 = num / den
+        s0 = level_and_sse(l0)[1]
+        assert all(level_and_sse(l0 + d)[1] >= s0 - 1e-12 for d in (-1e-3, 1e-3, -0.5, 0.5))
+    assert mo.predict_ses(3, [2.5]) == [2.5, 2.5, 2.5]                       # one sample: the level is the sample
+    with pytest.raises(ZeroDivisionError):
+        mo.predict_ses(3, [])
+
+
+def test_c_oracle_ses_and_startup_equal_python():
+    """C restatement of SPEC §5.3 (start-up delay as a decision variable) and §5.4 (expsmoothing predictor) against the
+    pure-Python one, bit for bit; n_ts = 1 is the plain decision."""
+    rng = np.random.default_rng(21)
+    V, A, H, K = 16, 4, 3, 12
+    bitrates = np.tile(np.array([300.0, 1200.0, 2850.0, 4300.0]) / 1000.0, (V, 1))
+    sizes = bitrates * 4.0 * rng.uniform(0.8, 1.2, size=(V, A))
+    nonzero_ts = 0
+    for trial in range(30):
+        n = int(rng.integers(1, K + 1))
+        hist = [float(x) for x in rng.uniform(0.3, 5.0, size=n)]
+        k, prev_q, buf = int(rng.integers(0, V - H + 1)), int(rng.integers(0, A)), float(rng.uniform(0, 6))
+        sw = float(rng.choice([0.1, 0.5, 1.0, 3.0]))
+        P = orc.make_params(chunk_length=4.0, max_buffer=30.0, rebuf_penalty=4.3, smooth_penalty=1.0, startup_penalty=sw,
+                            utility_scale=1.0)
+        ring = np.zeros((1, K)); ring[0, :n] = hist
+        # §5.4
+        c = orc.mpc_decide(sizes, bitrates, [k], [prev_q], [buf], ring, [n], H, 0, P, ses=True)
+        r = mo.decide_ref_ses(k, prev_q, buf, hist, H, bitrates.tolist(), sizes.tolist(), 4.0, 30.0, 1.0, 4.3)
+        assert c["n_errors"] == 0 and c["action"][0] == r["action"] and c["best_J"][0] == r["best_J"]
+        assert list(c["preds"][0]) == r["preds"] and list(c["best_seq"][0]) == r["best_seq"]
+        # §5.3 over both objectives
+        for mode in (0, 1):
+            if mode == 0:
+                preds, _ = mo.predict_harmonic_ref(H, hist)
+                obj = lambda R, b0: mo.objective_ref(R, k, prev_q, b0, preds, bitrates.tolist(), sizes.tolist(), 4.0, 30.0, 1.0, 4.3)
+            else:
+                cc = mo.robust_predict(hist, mo.RobustState(K))
+                obj = lambda R, b0: mo.objective_robust(R, k, prev_q, b0, cc, bitrates.tolist(), sizes.tolist(), 4.0, 30.0, 1.0, 4.3)
+            r = mo.decide_startup(obj, A, H, buf, sw, 9, 0.75)
+            Pm = orc.make_params(chunk_length=4.0, max_buffer=30.0, rebuf_penalty=4.3, smooth_penalty=1.0,
+                                 startup_penalty=sw, utility_scale=1.0, hist_k=K)
+            c = orc.mpc_decide(sizes, bitrates, [k], [prev_q], [buf], ring, [n], H, mode, Pm, n_ts=9, ts_step=0.75)
+            assert c["action"][0] == r["action"] and c["best_J"][0] == r["best_J"], (trial, mode)
+            assert c["startup_delay"][0] == r["startup_delay"] and list(c["best_seq"][0]) == r["best_seq"]
+            nonzero_ts += r["startup_delay"] > 0
+            # sessions outside the start-up phase and n_ts = 1 take the plain decision
+            plain = orc.mpc_decide(sizes, bitrates, [k], [prev_q], [buf], ring, [n], H, mode, Pm)
+            off = orc.mpc_decide(sizes, bitrates, [k], [prev_q], [buf], ring, [n], H, mode, Pm, startup=[0], n_ts=9, ts_step=0.75)
+            assert off["action"][0] == plain["action"][0] and off["best_J"][0] == plain["best_J"][0]
+            assert off["startup_delay"][0] == 0.0
+    assert nonzero_ts >= 5        # the grid is exercised: waiting pays when the start-up weight is small
