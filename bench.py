@@ -886,6 +886,16 @@ def cpu_baseline(args):
         out["mpc"] = dict(value=r, unit="decisions/s", cores=1,
                           sample=f"pure-Python port of mpc.py's search (oracle/mpc_oracle.py), {n} horizon-"
                                  f"{args.mpc_horizon} decisions in {b:.1f} s")
+        try:    # the real thing cannot travel to the GPU box: the build-box record of oracle/time_reference_mpc.py
+            rec = json.load(open(os.path.join(ROOT, "profiles", "ref_mpc_cpu_baseline.json")))
+            out["mpc"]["reference_mpc_py_on_build_box"] = dict(
+                decisions_per_s_one_core=rec["reference_mpc_py"]["one_core"]["decisions_per_s"],
+                decisions_per_s_all_cores=rec["reference_mpc_py"]["all_cores"]["decisions_per_s"],
+                cores=rec["cores"], impl=rec["reference_mpc_py"]["impl"], port_over_reference=rec["port_over_reference"],
+                note="unmodified /root/reference/mpc.py + scipy.optimize.brute on the same inputs, measured in the build "
+                     "container by oracle/time_reference_mpc.py (committed record profiles/ref_mpc_cpu_baseline.json)")
+        except Exception:
+            pass
     return out
 
 

@@ -82,6 +82,28 @@ def test_all_golden_cases_through_facade(golden):
     assert n_grid >= 20
 
 
+def test_kernel_matches_10k_decisions_of_the_reference_itself():
+    """tests/golden/mpc_ref_bulk.json (oracle/gen_golden_bulk.py): 10 240 decisions of the unmodified reference
+    controller; every one through the drop-in controller's host path (abr_mpc_decide_host): identical best sequence,
+    bit-identical objective value and prediction."""
+    import json
+    import os
+    from oracle.gen_golden_bulk import bulk_scenario
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpc_ref_bulk.json")) as f:
+        doc = json.load(f)
+    assert doc["n"] >= 10000
+    bad = []
+    for i in range(doc["n"]):
+        sc = bulk_scenario(i)
+        abr = make_abr(sc)
+        act, seq, bj, preds = abr._decide(sc["k"], sc["prev_q"], sc["history"], sc["buffer"], sc["H"])
+        want_seq = [int(ch) for ch in doc["best_seq"][i]]
+        if (list(seq) != want_seq or bj != float.fromhex(doc["best_J"][i]) or preds[0] != float.fromhex(doc["pred0"][i])
+                or act != want_seq[0]):
+            bad.append((i, list(seq), want_seq, bj, float.fromhex(doc["best_J"][i])))
+    assert not bad, (len(bad), bad[:5])
+
+
 def test_reference_error_behaviour(golden):
     by = {e["scenario"]["name"]: e["scenario"] for e in golden["errors"]}
     with pytest.raises(IndexError):

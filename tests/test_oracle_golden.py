@@ -190,3 +190,32 @@ def test_c_oracle_ses_and_startup_equal_python():
             assert off["action"][0] == plain["action"][0] and off["best_J"][0] == plain["best_J"][0]
             assert off["startup_delay"][0] == 0.0
     assert nonzero_ts >= 5        # the grid is exercised: waiting pays when the start-up weight is small
+
+
+def _bulk():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpc_ref_bulk.json")) as f:
+        return json.load(f)
+
+
+def test_oracles_match_10k_decisions_of_the_reference_itself():
+    """tests/golden/mpc_ref_bulk.json: 10 240 decisions taken by the unmodified /root/reference/mpc.py (oracle/
+    gen_golden_bulk.py).  Scenario i is rebuilt from its index; the C oracle must return the reference's best sequence
+    (scipy.optimize.brute's first minimum), objective value and first prediction bit for bit on every one, the
+    pure-Python restatement on every 16th."""
+    from oracle.gen_golden_bulk import bulk_scenario
+    doc = _bulk()
+    assert doc["n"] >= 10000
+    for i in range(doc["n"]):
+        sc = bulk_scenario(i)
+        want_seq = [int(ch) for ch in doc["best_seq"][i]]
+        want_j, want_p0 = float.fromhex(doc["best_J"][i]), float.fromhex(doc["pred0"][i])
+        r = _c_decide(sc)
+        assert r["n_errors"] == 0
+        assert list(r["best_seq"][0]) == want_seq, i
+        assert r["best_J"][0] == want_j and r["preds"][0][0] == want_p0, i
+        assert r["action"][0] == want_seq[0]
+        if i % 16 == 0:
+            rp = _py_decide(sc)
+            assert rp["best_seq"] == want_seq and rp["best_J"] == want_j and rp["preds"][0] == want_p0, i
