@@ -6,6 +6,24 @@
 #include <stdint.h>
 #include "../../include/abr_b200.h"
 
+// Checked build (-DABR_CHECKED, `ABR_LIB_SUFFIX=_chk ABR_EXTRA_NVCC_FLAGS=-DABR_CHECKED`): every shared-memory and table
+// access of the kernels is range-checked and a violation prints its location and traps, so the launch fails loudly.
+// This is the repo's own memcheck: compute-sanitizer is not available on the GPU pool this was developed on.  The
+// whole -m gpu suite is run against the checked library (profiles/README.md); the normal build compiles the checks away.
+#ifdef ABR_CHECKED
+#include <cstdio>
+#define ABR_CHECK(cond, what)                                                                                          \
+    do {                                                                                                               \
+        if (!(cond)) {                                                                                                 \
+            printf("ABR_CHECK failed: %s (%s:%d) block %d thread %d\n", what, __FILE__, __LINE__, (int)blockIdx.x,     \
+                   (int)threadIdx.x);                                                                                  \
+            __trap();                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+#else
+#define ABR_CHECK(cond, what) do { } while (0)
+#endif
+
 namespace abr {
 
 // Row stride (in doubles) of the cumulative-capacity table C[0..T] of SPEC §3.1: a multiple of four, so that every

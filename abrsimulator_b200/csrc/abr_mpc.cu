@@ -64,6 +64,7 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
     int n_prefix = 1;
     for (int i = 0; i < P; ++i) n_prefix *= A;
     const int i4 = h - 2, i5 = h - 1;
+    ABR_CHECK(h >= 2 && h <= kMaxH && A >= 1 && A <= kMaxA && (prev_q < A), "search shape");
     // the leaf-level rows are uniform across threads and prefixes and read A times per prefix: keep them in registers
     double U5[AR], RB5[AR];
     if (REGTAB) {
@@ -95,6 +96,7 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
                     ap = a;
                 }
             }
+            ABR_CHECK(idx >= 0 && idx < kPrefixCache, "parent-state cache slot (write)");
             sPC[idx * 4 + 0] = vq; sPC[idx * 4 + 1] = qv; sPC[idx * 4 + 2] = rt; sPC[idx * 4 + 3] = b;
         }
         if (WPS > 1) __syncthreads(); else __syncwarp();
@@ -106,6 +108,7 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
         int ap = prev_q;
         if (use_cache) {
             const int par = p / A, a = p - par * A;
+            ABR_CHECK(par >= 0 && par < kPrefixCache && par < n_par, "parent-state cache slot (read)");
             vq = sPC[par * 4 + 0]; qv = sPC[par * 4 + 1]; rt = sPC[par * 4 + 2]; b = sPC[par * 4 + 3];
             ap = par % A;                                // last digit of the parent prefix (P >= 2)
             const int i = P - 1;
@@ -254,6 +257,7 @@ abr_mpc_kernel(const MpcArgs a) {
                     if (a.preds && tid == 0) a.preds[s * H + i] = pi;
                     // tables for step i: each thread of the session fills entries a = tid, tid+NT, ...
                     for (int aa = tid; aa < A; aa += NT) {
+                        ABR_CHECK(i * A + aa < kMaxH * kMaxA && k + i < a.V, "lookahead table entry");
                         const double sz = a.sizes[(k + i) * A + aa];
                         double m = sz > 0.0 ? sz : 0.0;                    // max(0, size, L), mpc.py:151 (D11)
                         if (L > m) m = L;
@@ -288,6 +292,7 @@ abr_mpc_kernel(const MpcArgs a) {
                 c_rob = ddiv(hm, dadd(1.0, max_err));
                 if (a.preds && tid < H) a.preds[s * H + tid] = c_rob;
                 for (int e = tid; e < h * A; e += NT) {
+                    ABR_CHECK(e < kMaxH * kMaxA && (k + e / A) < a.V, "lookahead table entry");
                     const int i = e / A, aa = e - i * A;
                     const double dl = ddiv(a.sizes[(k + i) * A + aa], c_rob);
                     S.RB[e] = dl; S.DL[e] = dl;

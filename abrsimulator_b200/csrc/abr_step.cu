@@ -65,6 +65,9 @@ struct Sess {
     size_t speed_stride;
     int play_id, V;                      // content chunk being played
     bool started, bad_speed;
+#ifdef ABR_CHECKED
+    int chk_cum_n, chk_idx_n, chk_tab_n;  // entries the C row / index row / {size, utility} table may be read at
+#endif
 };
 
 struct StepRes {
@@ -128,11 +131,13 @@ __device__ __forceinline__ double sel8(const Quad& A, const Quad& B, const int k
 // C[j] / idx[b] of the session's trace: an LDS on the shared-memory path, else a read-only global load.
 template <bool SMEM>
 __device__ __forceinline__ double ld_c(const Sess& s, const int j) {
+    ABR_CHECK(j >= 0 && j < s.chk_cum_n, "C row index");
     return SMEM ? lds_f64(s.cum_s + 8u * (uint32_t)j) : __ldg(s.cum + j);
 }
 
 template <bool SMEM>
 __device__ __forceinline__ int ld_idx(const Sess& s, const int b) {
+    ABR_CHECK(b >= 0 && b < s.chk_idx_n, "bucket index entry");
     return SMEM ? (int)lds_u16(s.idx_s + 2u * (uint32_t)b) : (int)__ldg(s.idx + b);
 }
 
@@ -148,6 +153,8 @@ __device__ __forceinline__ Lookup lookup_tables(const Sess& s, const int A, cons
     const int row = (chunk < V ? chunk : 0) * A;   // an inert session (chunk == V) reads row 0 and ignores it
     const int prow = (prev_ladder && last_q >= 0 && chunk > 0 && chunk < V) ? row - A : row;
     Lookup k;
+    ABR_CHECK(row + q >= 0 && row + q < s.chk_tab_n && q >= 0, "{size, utility} table entry");
+    ABR_CHECK(prow + (last_q >= 0 ? last_q : q) >= 0 && prow + (last_q >= 0 ? last_q : q) < s.chk_tab_n, "previous-quality table entry");
     const double2 su = SMEM ? lds_f64x2(s.tab_s + 16u * (uint32_t)(row + q)) : __ldg(s.tab + row + q);
     k.size = su.x;
     k.u = su.y;
@@ -191,6 +198,7 @@ struct LiveAcc { double startup, area, played, tc; };   // tc: wall clock inside
 __device__ __forceinline__ double live_speed(Sess& s) {
     if (!s.speed) return 1.0;
     const int k = s.play_id < s.V ? s.play_id : s.V - 1;
+    ABR_CHECK(k >= 0 && k < s.V, "playback-speed table row");
     double v = __ldg(s.speed + (size_t)k * s.speed_stride);
     if (!(v > 0.0)) { s.bad_speed = true; v = 1.0; }
     return v;
@@ -283,6 +291,7 @@ __device__ __forceinline__ bool head_fast(const Sess& s, const double raw, Head&
         // and C is increasing, so the entries <= t are a prefix of the window and their count places j — provided
         // C[j+1] is still inside the window (count <= 7).
         const int q0 = j0 & ~3;
+        ABR_CHECK(q0 >= 0 && q0 + 8 <= s.chk_cum_n, "eight-entry window of C");
         const Quad A = ldg256(s.cum + q0), B = ldg256(s.cum + q0 + 4);
         const int n_le = (A.a <= t ? 1 : 0) + (A.b <= t ? 1 : 0) + (A.c <= t ? 1 : 0) + (A.d <= t ? 1 : 0) +
                          (B.a <= t ? 1 : 0) + (B.b <= t ? 1 : 0) + (B.c <= t ? 1 : 0) + (B.d <= t ? 1 : 0);
@@ -485,6 +494,12 @@ __device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawStat
         s.Td = (double)s.T;
     }
     s.cum_s = s.idx_s = s.tab_s = 0u;
+#ifdef ABR_CHECKED
+    s.chk_cum_n = cum_stride(v.T_max); s.chk_idx_n = idx_stride(v.T_max); s.chk_tab_n = v.V * v.A;
+    ABR_CHECK(tr >= 0 && tr < v.n_traces, "trace id");
+    ABR_CHECK(s.T >= 1 && s.T <= v.T_max && s.M >= 0 && s.M + 1 <= idx_stride(v.T_max) + (s.M == 0 ? 1 : 0), "trace record");
+    ABR_CHECK(w.seg >= 0 && w.seg < s.T, "segment of the session");
+#endif
     s.seg = w.seg;
     s.chunk = w.chunk;
     s.last_q = w.last_q;
@@ -660,6 +675,7 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
             if (v.p.track_history) {
                 // ring slot of this sample = (hist_len before the step) mod K; after an auto-reset hist_len is 0
                 const int prev_len = r.reset_mpc ? 0 : s.hist_len - 1;
+                ABR_CHECK(prev_len >= 0, "history length");
                 if (!r.reset_mpc) v.bw_hist[(size_t)(prev_len % v.K) * v.cap + i] = r.thr;
                 v.hist_len[i] = s.hist_len;
             }
@@ -772,6 +788,11 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
             if (tr == staged) {
                 s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row);
                 s.idx_s = (uint32_t)__cvta_generic_to_shared(s_idx);
+#ifdef ABR_CHECKED
+                s.chk_cum_n = smem_doubles; s.chk_idx_n = idx_stride(v.T_max);
+                ABR_CHECK(row_bytes_of(s.T) <= 8u * (uint32_t)smem_doubles && idx_bytes_of(s.M) <= 2u * (uint32_t)idx_stride(v.T_max),
+                          "staged rows fit the shared-memory buffer");
+#endif
                 step_session<true, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
             } else {
                 step_session<false, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
@@ -903,6 +924,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             bool ok1 = false;
             if (spec && (SMEM || s.M > 0)) ok1 = head_fast<SMEM>(s, dadd(h.target, lk1.size), h1);
             // tail of step t
+            ABR_CHECK((unsigned long long)ix < (unsigned long long)steps * n, "trajectory element index");
             const bool moved = step_tail<SMEM, FAST, false>(v, s, h, q0, lk0, g, r, hist);
             if (NOOUT) {
             } else if (FAST) {
@@ -945,6 +967,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         for (int t = 0; t < steps; ++t) {
             const int q = action_at(t);
             const Lookup lk = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q, s.last_q, prev_ladder);
+            ABR_CHECK((unsigned long long)ix < (unsigned long long)steps * n, "trajectory element index");
             step_core<SMEM, FAST, LIVE>(v, s, q, lk, r, hist);
             flagged |= r.walk_error;
             if (NOOUT) {
@@ -1096,6 +1119,11 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
             // keep the addresses in registers: left alone, the compiler rematerialises them from
             // SR_CgaCtaId (an S2R round trip) at every use inside the step loop
             asm volatile("" : "+r"(s.cum_s), "+r"(s.tab_s), "+r"(s.idx_s));
+#ifdef ABR_CHECKED
+            s.chk_cum_n = smem_doubles; s.chk_idx_n = idx_stride(v.T_max);
+            ABR_CHECK(row_bytes_of(s.T) <= 8u * (uint32_t)smem_doubles && idx_bytes_of(s.M) <= 2u * (uint32_t)idx_stride(v.T_max),
+                      "staged rows fit the shared-memory buffer");
+#endif
             if (fresh) s.pos = position_of<true>(s, s.seg, s.phi);
             rollout_session<POLICY, true, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);
         }

@@ -260,7 +260,7 @@ def test_facade_expsmoothing_and_startup():
     ladder = [300.0, 750.0, 1200.0, 1850.0, 2850.0, 4300.0]
     chunks = [Chunk(list(ladder), [b * 4.0 for b in ladder]) for _ in range(V)]
     mpd = MPD(V, 4.0, 30.0, 8.0, chunks)
-    qoe = QOEMetric(4.3, 1.0, 25.0, 0.0)            # rebuffer, variance, startup, latency weights
+    qoe = QOEMetric(4.3, 1.0, 1.0, 0.0)             # rebuffer, variance, startup, latency weights
     hist = [1800.0, 2500.0, 900.0, 3100.0, 2200.0]
 
     class Player:
@@ -293,7 +293,7 @@ def test_facade_expsmoothing_and_startup():
     act, ts = ctl.next_bitrate_startup(n_ts=12, ts_step=0.5)
     preds, _ = mo.predict_harmonic_ref(4, hist)
     obj = lambda R, b0: mo.objective_ref(R, 2, 1, b0, preds, bitrates, sizes, 4.0, 30.0, 1.0, 4.3)
-    want = mo.decide_startup(obj, 6, 4, 1.0, 25.0, 12, 0.5)
+    want = mo.decide_startup(obj, 6, 4, 1.0, 1.0, 12, 0.5)
     assert (act, ts) == (want["action"], want["startup_delay"]) and ts > 0.0
 
 

@@ -45,20 +45,22 @@ def test_c_step_equals_python_step(ragged):
     assert np.array_equal(env.field("chunk"), [p.chunk for p in py])
 
 
-@pytest.mark.parametrize("ragged", [False, True])
-def test_cumulative_capacity_walk_equals_segment_walk_within_1e9(ragged):
+@pytest.mark.parametrize("ragged,T", [(False, 300), (True, 300), (False, 2048), (True, 2048), (False, 30000)])
+def test_cumulative_capacity_walk_equals_segment_walk_within_1e9(ragged, T):
     """SPEC §3.1 integrates against the trace's cumulative capacity C[j]; the segment-by-segment integration it is
     the closed form of restarts its running sum at the session's position, so the two differ by rounding only —
     far inside the 1e-9 relative bar of BASELINE.json (bounded here at 1e-11 of max(|x|, 1 s); rebuffer is a
-    difference of two such values, so only its absolute error is meaningful)."""
-    bitrates, sizes, bw, tl, ti = small_world(n_traces=8, T=300, V=48, ragged=ragged)
+    difference of two such values, so only its absolute error is meaningful).  T = 2 048 is the benchmark's trace
+    length and T = 30 000 the longest the GPU tests use: there `target - C[j]` cancels against a running sum 10^3-10^4
+    times larger than a chunk, which is where the table form loses the most bits."""
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=8, T=T, V=48, ragged=ragged)
     P = dict(orc.DEFAULTS, max_buffer=20.0)
     util = orc.utility_table(bitrates, 0, P["utility_scale"])
     rng = np.random.default_rng(6)
     worst = 0.0
     for s in range(16):
         tr = s % 8
-        off = float(rng.uniform(0, 400))
+        off = float(rng.uniform(0, 400 if T <= 300 else T * 1.5))      # long traces: positions deep inside the running sum
         a = so.Session(bw[tr, :tl[tr]], ti[tr], sizes.tolist(), util.tolist(), P, off)
         b = so.Session(bw[tr, :tl[tr]], ti[tr], sizes.tolist(), util.tolist(), P, off, walk="segments")
         for t in range(120):
@@ -68,7 +70,9 @@ def test_cumulative_capacity_walk_equals_segment_walk_within_1e9(ragged):
                 worst = max(worst, abs(ra[k] - rb[k]) / max(abs(rb[k]), 1.0))
             assert abs(ra["delay"] - rb["delay"]) <= 1e-10 * rb["delay"]
             assert ra["eov"] == rb["eov"]
-    assert worst < 1e-11, worst
+    # the deviation grows with the size of the running sum, i.e. linearly with T: 4-5e-12 at T = 300, 1.2e-11 at
+    # T = 2 048, 2.3e-10 at T = 30 000 (measured) — inside BASELINE.json's 1e-9 for every trace length the tests use
+    assert worst < max(1e-11, 1e-14 * T), worst
 
 
 def test_rollout_policies_and_acc():
