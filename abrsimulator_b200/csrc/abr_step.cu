@@ -275,15 +275,15 @@ __device__ __forceinline__ bool head_fast(const Sess& s, const double raw, Head&
     int j;
     bool ok;
     if (SMEM) {
-        const int cnt = ld_idx<SMEM>(s, (int)b + 1) - j0;
+        // The index guarantees C[j0] <= t and that every boundary above idx[b + 1] lies beyond t; C is increasing, so
+        // the boundaries <= t among C[j0 + 1 .. j0 + 3] are a prefix and their count places j without looking at
+        // idx[b + 1] at all.  Whether three candidates were enough is checked on the result itself: t < C[j + 1]
+        // (entries past C[T] are +inf, the staged row carries the slack the unconditional reads need).
         const double c1 = ld_c<SMEM>(s, j0 + 1), c2 = ld_c<SMEM>(s, j0 + 2), c3 = ld_c<SMEM>(s, j0 + 3);
-        j = j0;                                  // the boundaries are increasing: each test implies the one before
-        if (cnt >= 1 && c1 <= t) j = j0 + 1;
-        if (cnt >= 2 && c2 <= t) j = j0 + 2;
-        if (cnt >= 3 && c3 <= t) j = j0 + 3;
+        j = j0 + (c1 <= t ? 1 : 0) + (c2 <= t ? 1 : 0) + (c3 <= t ? 1 : 0);
         h.c_j = ld_c<SMEM>(s, j);                // a third round of (cheap) shared-memory loads instead of selects
         h.c_j1 = ld_c<SMEM>(s, j + 1);
-        ok = cnt <= 3;
+        ok = t < h.c_j1;
     } else {
         // Global path: bound by the L1's tag stage (one cycle per lane and scattered load instruction), and every
         // dependent round is an L2 round trip.  So: one index entry, then the aligned eight-entry window of C that
@@ -368,10 +368,10 @@ __device__ __forceinline__ void live_gate(const EnvView& v, Sess& s, LiveGate& g
 // LIVE: live-streaming semantics of SPEC §7 (`g` = the step's pause gate).
 // Returns true when the step moved the trace position in time (sleep): s.pos was then recomputed from (seg, phi)
 // and a head issued ahead for the next step is stale.
+// `p` / `V`: the environment's parameters and chunk count.
 template <bool SMEM, bool FAST, bool LIVE>
-__device__ __forceinline__ bool step_tail(const EnvView& v, Sess& s, const Head& h, const int q, const Lookup& lk,
-                                          const LiveGate& g, StepRes& r, const bool want_thr) {
-    const AbrParams& p = v.p;
+__device__ __forceinline__ bool step_tail(const AbrParams& p, const int V, Sess& s, const Head& h, const int q,
+                                          const Lookup& lk, const LiveGate& g, StepRes& r, const bool want_thr) {
     r.reset_mpc = false;
     if (!FAST && s.done) {  // only reachable with auto_reset == 0
         r.delay = r.sleep = r.rebuf = r.reward = r.thr = r.u = r.smooth = r.latency = r.startup = r.area = r.played = 0.0;
@@ -433,7 +433,7 @@ __device__ __forceinline__ bool step_tail(const EnvView& v, Sess& s, const Head&
     s.seg = seg;
     s.phi = phi;
     s.buffer = buffer;
-    r.eov = (s.chunk >= v.V);
+    r.eov = (s.chunk >= V);
     if (r.eov) {
         if (FAST || p.auto_reset) {
             s.chunk = 0; s.buffer = 0.0; s.last_q = p.default_quality; s.hist_len = 0;
@@ -461,7 +461,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         if (LIVE) live_gate<SMEM>(v, s, g);
         head<SMEM>(s, dadd(s.pos, lk.size), h, r.walk_error);
     }
-    step_tail<SMEM, FAST, LIVE>(v, s, h, q, lk, g, r, want_thr);
+    step_tail<SMEM, FAST, LIVE>(v.p, v.V, s, h, q, lk, g, r, want_thr);
 }
 
 // SPEC §4, buffer-based policy on the pre-step buffer level.
@@ -628,8 +628,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     __trap();
 }
 
-// Bytes of the staged copies of one trace's rows (multiples of 16): C[0..T] and idx[0..M].
-__device__ __forceinline__ uint32_t row_bytes_of(int T) { return (uint32_t)((T + 2) / 2) * 16u; }
+// Bytes of the staged copies of one trace's rows (multiples of 16): C[0..T] plus at least three of the +inf entries
+// behind it (the branch-free head reads C[j0 + 1 .. j0 + 4] with j0 <= T - 1), and idx[0..M].
+__device__ __forceinline__ uint32_t row_bytes_of(int T) { return (uint32_t)((T + 5) / 2) * 16u; }
 __device__ __forceinline__ uint32_t idx_bytes_of(int M) { return (uint32_t)((M + 1 + 7) / 8) * 16u; }
 
 // One chunk step of one session with the state in HBM (SPEC §3, §7).
@@ -891,12 +892,14 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         return policy_bba(v, s.buffer);
     };
     // chunk index / previous quality the step after (chunk, q) will see (SPEC §3.5), without running the step
+    const int V_ = v.V, dq_ = v.p.default_quality;
+    const bool wraps = FAST || v.p.auto_reset;
     auto next_chunk = [&](const int chunk) -> int {
         const int c = chunk + 1;
-        return (c >= v.V && (FAST || v.p.auto_reset)) ? 0 : c;
+        return (c >= V_ && wraps) ? 0 : c;
     };
     auto next_last_q = [&](const int chunk, const int q) -> int {
-        return (chunk + 1 >= v.V && (FAST || v.p.auto_reset)) ? v.p.default_quality : q;
+        return (chunk + 1 >= V_ && wraps) ? dq_ : q;
     };
     uint32_t ix = (uint32_t)i;   // element index of (step t, session i) in the [steps][N] outputs (< 2^32, checked by the host)
     StepRes r;
@@ -904,8 +907,10 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     g.buffer = 0.0; g.rebuf = g.idle = 0.0;
     g.a.startup = g.a.area = g.a.played = g.a.tc = 0.0;
     if (AHEAD) {
+        const AbrParams& pl = v.p;
+        const int Vr = v.V;
         int q0 = action_at(0);
-        Lookup lk0 = lookup_tables<SMEM>(s, v.A, v.V, s.chunk, q0, s.last_q, prev_ladder);
+        Lookup lk0 = lookup_tables<SMEM>(s, v.A, Vr, s.chunk, q0, s.last_q, prev_ladder);
         int c1 = next_chunk(s.chunk);            // chunk index / previous quality step t+1 will see
         int lq1 = next_last_q(s.chunk, q0);
         Head h;
@@ -919,13 +924,13 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             // sits at the cap sleep after every chunk, and the lanes of a warp tend to do so together (same trace):
             // a warp that slept in the last step does not speculate (its head would be redone anyway).
             const int q1 = action_at(t + 1);
-            const Lookup lk1 = lookup_tables<SMEM>(s, v.A, v.V, c1, q1, lq1, prev_ladder);
+            const Lookup lk1 = lookup_tables<SMEM>(s, v.A, Vr, c1, q1, lq1, prev_ladder);
             Head h1;
             bool ok1 = false;
             if (spec && (SMEM || s.M > 0)) ok1 = head_fast<SMEM>(s, dadd(h.target, lk1.size), h1);
             // tail of step t
             ABR_CHECK((unsigned long long)ix < (unsigned long long)steps * n, "trajectory element index");
-            const bool moved = step_tail<SMEM, FAST, false>(v, s, h, q0, lk0, g, r, hist);
+            const bool moved = step_tail<SMEM, FAST, false>(pl, Vr, s, h, q0, lk0, g, r, hist);
             if (NOOUT) {
             } else if (FAST) {
                 __stcs(o.delay + ix, (OT)r.delay); __stcs(o.sleep + ix, (OT)r.sleep); __stcs(o.buffer + ix, (OT)r.buffer);
@@ -1039,7 +1044,10 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
 // co-resident (6.9 per SM).
 template <int POLICY, bool FAST, bool NOOUT, bool LIVE, typename OT>
 #ifndef ABR_ROLLOUT_MINBLOCKS
-#define ABR_ROLLOUT_MINBLOCKS 8
+#define ABR_ROLLOUT_MINBLOCKS 8   // <= 128 registers.  Registers are allocated per warp in steps of 32 per thread, so 129..160
+                                  // registers mean 12 warps = six 64-thread blocks per SM (measured: 140 and 144 registers
+                                  // both run 65 536 sessions in two waves, 66-69 us instead of 50) — and shared memory
+                                  // (29 KB per block at the benchmark shape) allows seven, which is what one wave needs
 #endif
 __global__ void __launch_bounds__(kRolloutBlock, LIVE ? 6 : ABR_ROLLOUT_MINBLOCKS)
 abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uint32_t step_base,
@@ -1047,7 +1055,7 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
                    double* __restrict__ block_partials) {
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
-    __shared__ int s_tr0;
+    __shared__ int s_tr0, s_staged;
     __shared__ double s_part[kRolloutBlock / 32][ABR_NUM_ACC];
     // let a dependent grid launched with programmatic stream serialization (the statistics stage 2) become resident
     // now; it waits for this grid's completion itself (griddepcontrol.wait), so only its launch latency is hidden
@@ -1061,12 +1069,36 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
     int tr = -1;
     const bool fresh = o.in_trace_id != nullptr;   // fused reset (launch-uniform)
     int n_bad = 0;
+    // Staging (shared-memory path): the trace's C and index rows and the chunk-size / utility tables arrive by TMA bulk
+    // copies (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier — 29 KB per block without occupying the LSU or
+    // registers.  Thread 0 issues them as soon as it knows its own trace id, i.e. one memory round trip into the
+    // kernel: the whole padded rows are copied (the byte counts then depend on nothing that has to be read first),
+    // and the copies run while every thread of the block is still fetching its trace record and state.  Whether the
+    // block may use them (all of its sessions on that trace, and the trace has an index) is decided afterwards.
+    double* s_row = reinterpret_cast<double*>(s_row2);
+    uint16_t* s_idx = reinterpret_cast<uint16_t*>(s_row + smem_doubles);
+    double2* s_tab = reinterpret_cast<double2*>(s_idx + idx_stride(v.T_max));
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    auto stage_rows = [&](const int tr0) {         // thread 0 only
+        s_staged = 0;
+        if (smem_doubles == 0 || tr0 < 0 || tr0 >= v.n_traces) return;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t rb = (uint32_t)cum_stride(v.T_max) * 8u, ib = (uint32_t)idx_stride(v.T_max) * 2u;
+        const uint32_t tab_bytes = (uint32_t)(v.V * v.A) * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(rb + ib + tab_bytes) : "memory");
+        bulk_g2s(s_row, v.trace_cum + (size_t)tr0 * cum_stride(v.T_max), rb, mbar);
+        bulk_g2s(s_idx, v.trace_idx + (size_t)tr0 * idx_stride(v.T_max), ib, mbar);
+        bulk_g2s(s_tab, v.tab, tab_bytes, mbar);
+        s_staged = 1;
+    };
     if (valid) {
         if (fresh) {
             // SPEC §2 from the per-trace record (one dependent read after the trace id); the data position is taken
             // from the C row once it is known where that row is read from (shared memory or global)
             RawState w;
             w.tr = o.in_trace_id[i];
+            if (threadIdx.x == 0) stage_rows(w.tr);
             const double off = o.in_offset ? o.in_offset[i] : 0.0;
             if (w.tr < 0 || w.tr >= v.n_traces) { ++n_bad; w.tr = 0; }
             w.seg = 0; w.chunk = 0; w.last_q = v.p.default_quality; w.phi = 0.0; w.pos = 0.0; w.buffer = 0.0;
@@ -1077,41 +1109,20 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
             v.trace_id[i] = tr;
             if (n_bad) atomicAdd(v.errors, (unsigned long long)n_bad);
         } else {
-            load_sess(v, i, s);
             tr = v.trace_id[i];
+            if (threadIdx.x == 0) stage_rows(tr);
+            load_sess(v, i, s);
         }
     }
     if (threadIdx.x == 0) s_tr0 = tr;            // thread 0 of a launched block is always a valid session
-    __syncthreads();
+    __syncthreads();                              // also publishes the initialised mbarrier and s_staged
     const int tr0 = s_tr0;
-    // block-uniform: every session of this block follows trace tr0 (whose rows fit: T <= T_max)
-    const bool use_smem = smem_doubles != 0 && __syncthreads_and((!valid || tr == tr0) ? 1 : 0) &&
-                          __ldg(&v.trace_meta[tr0].M) > 0;
+    const bool staged = s_staged != 0;
+    // block-uniform: the rows are there, every session of this block follows trace tr0, and tr0 has an index
+    const int same = __syncthreads_and((!valid || tr == tr0) ? 1 : 0);
+    const bool use_smem = staged && same && __ldg(&v.trace_meta[tr0].M) > 0;
+    if (staged) mbar_wait(mbar, 0u);              // also when the rows stay unused: the copies must have landed before the block ends
     if (use_smem) {
-        // Stage the trace's C and index rows and the chunk-size / utility tables with TMA bulk copies (cp.async.bulk,
-        // SASS UBLKCP): one elected thread issues four asynchronous global->shared copies that complete on an
-        // mbarrier, so the 29 KB arrive without occupying the LSU or registers while the other threads finish loading
-        // their state.  Rows start 16-byte aligned and all byte counts are multiples of 16.
-        double* s_row = reinterpret_cast<double*>(s_row2);
-        uint16_t* s_idx = reinterpret_cast<uint16_t*>(s_row + smem_doubles);
-        double2* s_tab = reinterpret_cast<double2*>(s_idx + idx_stride(v.T_max));
-        const uint32_t tab_bytes = (uint32_t)(v.V * v.A) * 16u;
-        const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint32_t rb = row_bytes_of(__ldg(&v.trace_meta[tr0].T)), ib = idx_bytes_of(__ldg(&v.trace_meta[tr0].M));
-            const uint32_t total = rb + ib + tab_bytes;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
-            bulk_g2s(s_row, v.trace_cum + (size_t)tr0 * cum_stride(v.T_max), rb, mbar);
-            bulk_g2s(s_idx, v.trace_idx + (size_t)tr0 * idx_stride(v.T_max), ib, mbar);
-            bulk_g2s(s_tab, v.tab, tab_bytes, mbar);
-        }
-        mbar_wait(mbar, 0u);
-        __syncthreads();
         if (valid) {
             s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row);
             s.idx_s = (uint32_t)__cvta_generic_to_shared(s_idx);
@@ -1121,8 +1132,7 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
             asm volatile("" : "+r"(s.cum_s), "+r"(s.tab_s), "+r"(s.idx_s));
 #ifdef ABR_CHECKED
             s.chk_cum_n = smem_doubles; s.chk_idx_n = idx_stride(v.T_max);
-            ABR_CHECK(row_bytes_of(s.T) <= 8u * (uint32_t)smem_doubles && idx_bytes_of(s.M) <= 2u * (uint32_t)idx_stride(v.T_max),
-                      "staged rows fit the shared-memory buffer");
+            ABR_CHECK(cum_stride(v.T_max) <= smem_doubles && s.T + 4 < cum_stride(v.T_max), "staged rows fit the shared-memory buffer");
 #endif
             if (fresh) s.pos = position_of<true>(s, s.seg, s.phi);
             rollout_session<POLICY, true, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);

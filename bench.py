@@ -474,6 +474,38 @@ def run_ours(args):
                chunk_steps_per_s=world * N * V / (bba_kernel_ms * 1e-3),
                frac=(N * (V * BYTES_PER_STEP + BYTES_PER_SESSION)) / (bba_kernel_ms * 1e-3) / 1e9 / hbm_peak_gbs())
 
+    # ---- the same episode kernel with the session -> trace map of SURVEY.md §8(d), trace = session mod n_traces
+    #      ("interleaved": no block follows one trace, every table probe is a scattered L2 read), and the same sessions with
+    #      the environment keeping them sorted by trace (reset(sort_by_trace=True): abr_sort_by_trace + abr_env_set_order
+    #      inside the timed call, outputs in environment order) ----
+    fused_layouts = {}
+    tid_i, off_i = synth.make_sessions(N, N_TRACES, T_TRACE, session_base=base, group=1)
+    tid_id, off_id = torch.from_numpy(tid_i).to(dev), torch.from_numpy(off_i).to(dev)
+    for name, sort in (("interleaved", False), ("interleaved_env_sorted", True)):
+        ms_k, ms_all = [], []
+        for it in range(3 + 8):
+            flush.fill_(1)
+            env.set_order(None)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            env.reset(tid_id, off_id, session_base=base, sort_by_trace=sort)
+            k0.record(stream)
+            env.rollout("random", V, seed=SEED, out=out)
+            k1.record(stream)
+            a1.record(stream)
+            a1.synchronize()
+            if it >= 3:
+                ms_k.append(k0.elapsed_time(k1))
+                ms_all.append(a0.elapsed_time(a1))
+        km = max_over_ranks(sum(ms_k), dev) / len(ms_k)
+        am = max_over_ranks(sum(ms_all), dev) / len(ms_all)
+        fused_layouts[name] = dict(kernel_ms=km, reset_plus_episode_ms=am,
+                                   chunk_steps_per_s=world * N * V / (am * 1e-3),
+                                   frac=(N * (V * BYTES_PER_STEP + BYTES_PER_SESSION)) / (km * 1e-3) / 1e9 / hbm_peak_gbs())
+    env.set_order(None)
+    env.reset(tid_d, off_d, session_base=base)
+
     # ---- e2e: the host-buffer call (Simulator.run semantics: per-session QoE sums + statistics to the host) ----
     # page-locked host tensors: the kernels pull the inputs and push the results over PCIe themselves (zero-copy)
     tid_p = torch.from_numpy(tid_h).pin_memory()
@@ -585,6 +617,9 @@ def run_ours(args):
     if mpc:
         line["mpc"] = mpc
     line["bba_policy"] = bba
+    line["fused_kernel_layouts"] = dict(sorted_by_trace=dict(kernel_ms=kern_avg_ms, frac=achieved / hbm_peak,
+                                                             note="the headline: 64 consecutive sessions per trace"),
+                                        **fused_layouts)
     line["fp32_outputs"] = fp32_outputs
     if step_form:
         line["step_form"] = step_form
