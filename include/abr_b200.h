@@ -171,7 +171,8 @@ int abr_env_rollout_fused_f32(AbrEnv* env, int policy, uint64_t seed, int steps,
 int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, double* d_best_j /*nullable*/,
                        void* stream);
 /* Per-session QoE cost of Simulator.calculate_qoe (Simulator.py:83-86) from the accumulators into d_out[N]:
- * rw*rebuffer + vw*smooth + sw*startup + lw*(latency/steps). */
+ * rw*rebuffer + vw*smooth + sw*startup + lw*average_latency, average_latency = latency integral / (latency_tick * content
+ * played) as the reference's running mean defines it (Simulator.py:179-180; SPEC 7). */
 int abr_env_qoe_cost(AbrEnv* env, double* d_out, void* stream);
 /* SPEC §6: reduce the accumulators of the first n sessions into d_out[ABR_NUM_STATS]. */
 int abr_stats_partial(AbrEnv* env, double* d_out, void* stream);

@@ -6,8 +6,15 @@
  * (abrsimulator_b200) never links or calls it.
  *
  * Parity status: MPC mode 0 (Profile R) is pinned against the unmodified
- * reference through tests/golden/mpc_ref_golden.json; the chunk-step path and
- * MPC mode 1 are "parity unpinned" (no executable reference exists).
+ * reference (tests/golden/mpc_ref_golden.json, mpc_ref_bulk.json: 10 409 decisions).
+ * The dynamics of the chunk step (download against the square-wave trace, buffer
+ * drain, rebuffering, pause gate, start-up latch, playback speed, latency) are
+ * pinned by the reference's own tick loop, mechanically repaired and executed
+ * (oracle/make_ref_simulator.py -> tests/golden/sim_ref_tick_golden.json, within
+ * the loop's discretisation and converging with its tick).  The north-star
+ * constants layered on top (RTT, payload factor, sleep quantum, per-step reward),
+ * MPC mode 1, the expsmoothing predictor and the start-up phase are "parity
+ * unpinned": defined by SPEC.md, no executable reference exists for them.
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC (oracle/Makefile).
  */

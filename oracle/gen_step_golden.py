@@ -5,7 +5,8 @@
 The reference's environment loop (Simulator.py:93-210) does not run, so there is nothing to
 import: this fixture is produced by the repo's own pure-Python restatement of SPEC.md §2-§4 and §7
 (oracle/step_oracle.py) and pins *the SPEC* — a change of the arithmetic contract must regenerate it on purpose.
-Parity with the reference stays unpinned for this path.  Values are stored as IEEE-754 hex strings,
+(What pins the step's dynamics to the reference is the other fixture, tests/golden/sim_ref_tick_golden.json, produced
+by the reference's own repaired tick loop: oracle/make_ref_simulator.py.)  Values are stored as IEEE-754 hex strings,
 so the C oracle and the CUDA kernels are compared bit for bit.
 """
 from __future__ import annotations
@@ -87,7 +88,7 @@ def main():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as f:
         json.dump(dict(generator="oracle/gen_step_golden.py (oracle/step_oracle.py, SPEC.md §2-§4, §7)",
-                       pins="the SPEC, not the reference: parity unpinned for this path", cases=cases), f)
+                       pins="the SPEC bit for bit; the reference-derived pin of the dynamics is sim_ref_tick_golden.json", cases=cases), f)
     print(f"wrote {OUT}: {len(cases)} cases")
 
 

@@ -11,12 +11,15 @@ Pure-Python restatement (binary64, Python floats, loops) of:
   ``next_buffer`` mpc.py:111-118, ``objective`` mpc.py:120-162,
   ``optimize_qoe``/``scipy.optimize.brute`` mpc.py:171-179 (C-order grid, first
   minimum), ``next_bitrate`` mpc.py:181-186.
-* Profile N robust MPC (SPEC.md §5.2) — parity unpinned by the reference.
+* Profile N robust MPC (SPEC.md §5.2), the start-up phase (§5.3) and the
+  "expsmoothing" predictor (§5.4) — parity unpinned by the reference.
 
 Parity status: Profile R is PINNED — ``tests/test_oracle_golden.py`` checks this
 file against fixtures produced by importing the unmodified reference
-(``oracle/gen_golden.py`` → ``tests/golden/mpc_ref_golden.json``) and against
-the reference's only golden (``mpc_test.py:52-86`` → "Test next bitrate: 2").
+(``oracle/gen_golden.py`` → ``tests/golden/mpc_ref_golden.json``, 169 scenarios with
+full score grids; ``oracle/gen_golden_bulk.py`` → ``mpc_ref_bulk.json``, 10 240 more
+decisions) and against the reference's only golden (``mpc_test.py:52-86`` →
+"Test next bitrate: 2").
 Profile N: parity unpinned (defined by SPEC.md).
 """
 from __future__ import annotations

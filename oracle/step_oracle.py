@@ -2,8 +2,10 @@
 
 Small cases only; used to cross-check oracle/abr_oracle.c and as the timed
 "reference-style" CPU port of the chunk step (the reference's own step loop,
-Simulator.py:93-210, does not run: SURVEY.md D1-D6).  Parity unpinned by the
-reference; SPEC.md is the contract.  ``Session(..., walk="segments")`` replaces the
+Simulator.py:93-210, does not run as shipped: SURVEY.md D1-D6).  Parity: the live-mode
+dynamics (SPEC §7) are pinned by that loop itself, repaired in memory and executed
+(oracle/make_ref_simulator.py -> tests/golden/sim_ref_tick_golden.json); the north-star
+constants (RTT, payload factor, sleep quantum, per-step reward) are defined by SPEC.md.  ``Session(..., walk="segments")`` replaces the
 cumulative-capacity form of SPEC §3.1 by the segment-by-segment integration it is the
 closed form of (the running sum restarts at the session's position instead of the start
 of the trace), which tests use to bound the difference (≪ 1e-9 relative).  Also holds ``euler_session`` — the

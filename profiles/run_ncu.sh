@@ -7,7 +7,7 @@ CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline ${BENCH_EXTRA:-}"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain_$TAG.log; exit 1; }
 if [ -z "${SKIP_LIST:-}" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "launch list rc=$?"
 fi
 ncu --set full --clock-control none --import-source on -k regex:abr_rollout_kernel -s 4 -c 1 -f -o gpurun_out/rollout_$TAG $CMD > gpurun_out/ncu_rollout_$TAG.log 2>&1
@@ -17,7 +17,7 @@ ncu --set full --clock-control none --import-source on -k regex:abr_mpc_kernel -
 echo "mpc capture rc=$?"
 fi
 if [ -n "${WITH_STEP:-}" ]; then
-ncu --set full --clock-control none --import-source on -k regex:abr_step_kernel -s 60 -c 1 -f -o gpurun_out/step_$TAG $CMD > gpurun_out/ncu_step_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:abr_step_kernel -s 10 -c 1 -f -o gpurun_out/step_$TAG $CMD --no-mpc > gpurun_out/ncu_step_$TAG.log 2>&1
 echo "step capture rc=$?"
 fi
 ls -la gpurun_out/

@@ -1,6 +1,7 @@
 """GPU parity of the chunk-step kernels (per-step and fused episode), through the C-ABI — run with -m gpu.
 
-Oracle: oracle/abr_oracle.c (SPEC.md restated; parity unpinned by the reference).
+Oracle: oracle/abr_oracle.c (SPEC.md restated; its live-mode dynamics pinned by the reference's own tick loop,
+tests/golden/sim_ref_tick_golden.json — test_kernels_are_the_limit_of_the_references_own_tick_loop).
 Bar: 1e-9 relative (BASELINE.json) — and, because both sides execute the same IEEE operations in the
 same order without FMA contraction, bit-identical.
 """
