@@ -49,6 +49,7 @@ struct AbrEnv {
     int n_order = 0;
     int fresh_partials = 0;   // > 0: d_stats_partials holds that many block sums of the current accumulators
     double* d_stats_out = nullptr;
+    StatsScratch stats_scratch;               // group sums and the counters of finished blocks / groups (zero between launches)
     // scratch for the *_host entry points
     int32_t* d_trace_id = nullptr;
     double* d_offset = nullptr;
@@ -234,6 +235,12 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
                             ? stats_num_partials(max_sessions) : rollout_num_blocks(max_sessions);
     CUDA_TRY(e->alloc(&e->d_stats_partials, (size_t)e->n_partials_cap * ABR_NUM_ACC));
     CUDA_TRY(e->alloc(&e->d_stats_out, ABR_NUM_STATS));
+    {
+        const int n_groups = stats_num_groups(e->n_partials_cap);
+        CUDA_TRY(e->alloc(&e->stats_scratch.group_partials, (size_t)n_groups * ABR_NUM_ACC));
+        CUDA_TRY(e->alloc(&e->stats_scratch.counters, (size_t)n_groups + 1));
+        CUDA_TRY(cudaMemset(e->stats_scratch.counters, 0, sizeof(unsigned int) * ((size_t)n_groups + 1)));
+    }
     CUDA_TRY(e->alloc(&e->d_trace_id, cap));
     CUDA_TRY(e->alloc(&e->d_offset, cap));
     guard.e = nullptr;
@@ -449,7 +456,7 @@ int abr_stats_partial(AbrEnv* env, double* d_out, void* stream) {
     if (!env || !d_out) return fail(ABR_ERR_INVALID, "env or out is NULL");
     const bool fresh = env->fresh_partials > 0;
     const int np = fresh ? env->fresh_partials : stats_num_partials(env->v.n);
-    CUDA_TRY(launch_stats(env->v, env->d_stats_partials, np, fresh, d_out, (cudaStream_t)stream));
+    CUDA_TRY(launch_stats(env->v, env->d_stats_partials, np, fresh, d_out, env->stats_scratch, (cudaStream_t)stream));
     return ABR_OK;
 }
 
@@ -514,9 +521,10 @@ int abr_env_run(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t
         env->step_base = 0;
         RolloutFused fused;
         fused.in_trace_id = d_trace_id; fused.in_offset = d_start_offset; fused.out_cost = d_qoe_cost;
+        fused.out_stats = d_stats; fused.scratch = env->stats_scratch;   // statistics by the kernel's own blocks
         rc = env_rollout_any<double>(env, policy, seed, steps, d_actions_in, nullptr, d_delay, d_sleep, d_buffer, d_rebuf,
                                      d_reward, nullptr, d_end_of_video, d_actions_out, stream, fused);
-        if (rc) return rc;
+        return rc;
     } else {
         rc = abr_env_reset(env, d_trace_id, d_start_offset, n_sessions, session_base, stream);
         if (rc) return rc;
@@ -599,15 +607,20 @@ int abr_env_run_host(AbrEnv* env, int policy, uint64_t seed, int steps, const in
         env->d_reward_cap = traj;
     }
     RolloutFused fused;
-    if (fuse) { fused.in_trace_id = tid; fused.in_offset = off; fused.out_cost = z_cost; }
+    double* z_stats = h_stats ? (double*)device_alias(h_stats) : nullptr;
+    if (fuse) {
+        fused.in_trace_id = tid; fused.in_offset = off; fused.out_cost = z_cost;
+        if (h_stats) { fused.out_stats = z_stats ? z_stats : env->d_stats_out; fused.scratch = env->stats_scratch; }
+    }
     rc = env_rollout_any<double>(env, policy, seed, steps, policy == ABR_POLICY_FIXED ? env->d_actions : nullptr, nullptr,
                                  nullptr, nullptr, nullptr, nullptr, h_reward_traj ? env->d_reward_traj : nullptr,
                                  nullptr, nullptr, nullptr, stream, fused);
     if (rc) return rc;
     if (h_stats) {
-        double* z_stats = (double*)device_alias(h_stats);
-        rc = abr_stats_partial(env, z_stats ? z_stats : env->d_stats_out, stream);
-        if (rc) return rc;
+        if (!fuse) {   // no episode ran: the statistics of the reset state
+            rc = abr_stats_partial(env, z_stats ? z_stats : env->d_stats_out, stream);
+            if (rc) return rc;
+        }
         if (!z_stats)
             CUDA_TRY(cudaMemcpyAsync(h_stats, env->d_stats_out, sizeof(double) * ABR_NUM_STATS, cudaMemcpyDeviceToHost, st));
     }

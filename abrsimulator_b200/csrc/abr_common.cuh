@@ -132,7 +132,14 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
                         double* d_next_sizes, uint8_t* d_eov, double* d_thr, cudaStream_t st);
 // Fused reset + episode + session cost (abr_env_run_host): with in_trace_id the episode kernel resets every session
 // itself (SPEC §2) and out_cost receives Simulator.calculate_qoe per session; the pointers may alias pinned host memory.
-struct RolloutFused { const int32_t* in_trace_id = nullptr; const double* in_offset = nullptr; double* out_cost = nullptr; };
+// Scratch of the statistics reduction (SPEC §6): one sum per group of block partials, and the counters of finished
+// blocks / groups (counters[0]: groups, counters[1 + g]: blocks of group g; zero between launches).
+struct StatsScratch { double* group_partials = nullptr; unsigned int* counters = nullptr; };
+// out_stats (with scratch): the statistics vector of SPEC §6 is written by the episode kernel itself (its last block).
+struct RolloutFused {
+    const int32_t* in_trace_id = nullptr; const double* in_offset = nullptr; double* out_cost = nullptr;
+    double* out_stats = nullptr; StatsScratch scratch;
+};
 cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int steps, const int32_t* d_actions_in,
                            const double* d_speed, double* d_delay, double* d_sleep, double* d_buffer, double* d_rebuf,
                            double* d_reward, double* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
@@ -147,8 +154,10 @@ cudaError_t launch_rollout(const EnvView& v, int policy, uint64_t seed, int step
                            float* d_reward, float* d_latency, uint8_t* d_eov, int32_t* d_actions_out,
                            double* d_block_partials, cudaStream_t st, uint32_t step_base = 0);
 cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, bool have_partials, double* d_out,
+                         const StatsScratch& scratch,
                          cudaStream_t st);
 int stats_num_partials(int n);
+int stats_num_groups(int n_partials);
 cudaError_t launch_sort_by_trace(const int32_t* d_trace_id, int n, int n_traces, int32_t* d_perm, void* d_tmp,
                                  size_t* tmp_bytes, cudaStream_t st);
 cudaError_t launch_qoe_cost(const EnvView& v, double* d_out, cudaStream_t st);

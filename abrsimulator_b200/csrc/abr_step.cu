@@ -818,6 +818,87 @@ __device__ __forceinline__ double session_cost(const EnvView& v, const double re
     return c;
 }
 
+// ---- SPEC §6: the statistics vector from per-block partial sums, in a fixed order and without a serial tail ----
+// The block partials are cut into groups of kStatsGroup consecutive blocks.  A group's sum is formed by one block of
+// (at least) 64 threads: thread (q, j) adds the eight partials 8q .. 8q+7 of the group for statistic j in ascending
+// order (all eight loads issued before the first addition), then ((s0 + s1) + s2) + s3.  The final sum over the
+// groups: thread (q, j) adds the group sums q, q+4, q+8, ... in ascending order, then ((s0 + s1) + s2) + s3 again.
+// Who does the work does not change the order: in the fused episode the block that finishes last within a group
+// reduces the group (while other groups are still running) and the group that finishes last does the final sum, so
+// the tail behind the last episode is two short rounds of loads instead of a second launch; abr_stats_stage2 runs
+// the same two functions with one block per group.  Missing partials count as +0.0.
+constexpr int kStatsGroup = 32;
+constexpr int kStatsLanes = 4 * ABR_NUM_ACC;   // threads (q, j) at work
+
+__device__ __forceinline__ void stats_group_sum(const double* __restrict__ partials, const int n_partials, const int g,
+                                                double* __restrict__ group_partials, double (*sm)[ABR_NUM_ACC]) {
+    const int t = threadIdx.x;
+    if (t < kStatsLanes) {
+        const int q = t / ABR_NUM_ACC, j = t - q * ABR_NUM_ACC;
+        const int b0 = g * kStatsGroup + q * 8;
+        double x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // L1 is bypassed: the partials were written by other SMs
+            x[k] = b0 + k < n_partials ? __ldcg(partials + (size_t)(b0 + k) * ABR_NUM_ACC + j) : 0.0;
+        double s = x[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s = dadd(s, x[k]);
+        sm[q][j] = s;
+    }
+    __syncthreads();
+    if (t < ABR_NUM_ACC) group_partials[(size_t)g * ABR_NUM_ACC + t] = dadd(dadd(dadd(sm[0][t], sm[1][t]), sm[2][t]), sm[3][t]);
+}
+
+__device__ __forceinline__ void stats_final_sum(const double* __restrict__ group_partials, const int n_groups,
+                                                double* __restrict__ out, double (*sm)[ABR_NUM_ACC]) {
+    const int t = threadIdx.x;
+    __syncthreads();   // sm may still be read by stats_group_sum's last step
+    if (t < kStatsLanes) {
+        const int q = t / ABR_NUM_ACC, j = t - q * ABR_NUM_ACC;
+        double s = 0.0;
+        for (int g0 = q; g0 < n_groups; g0 += 32) {   // eight loads in flight per thread
+            double x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                x[k] = g0 + 4 * k < n_groups ? __ldcg(group_partials + (size_t)(g0 + 4 * k) * ABR_NUM_ACC + j) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = dadd(s, x[k]);
+        }
+        sm[q][j] = s;
+    }
+    __syncthreads();
+    if (t < ABR_NUM_ACC) out[t] = dadd(dadd(dadd(sm[0][t], sm[1][t]), sm[2][t]), sm[3][t]);
+}
+
+// Called by every thread of a block (>= 64 threads) once the block's partial `b` of `n_partials` is written (by threads
+// < ABR_NUM_ACC, each followed by a __threadfence): counts the block as finished; the last block of its group sums the
+// group, the last group sums the groups into `out`.  counters[0] counts finished groups, counters[1 + g] the
+// finished blocks of group g; all are left at zero.
+__device__ __forceinline__ void stats_finish(const double* __restrict__ partials, const int n_partials, const int b,
+                                             const StatsScratch sc, double* __restrict__ out,
+                                             double (*sm)[ABR_NUM_ACC], int* s_flag) {
+    const int g = b / kStatsGroup;
+    const int n_groups = (n_partials + kStatsGroup - 1) / kStatsGroup;
+    const int g_size = min(kStatsGroup, n_partials - g * kStatsGroup);
+    __syncthreads();
+    if (threadIdx.x == 0) *s_flag = atomicAdd(sc.counters + 1 + g, 1u) == (unsigned)(g_size - 1) ? 1 : 0;
+    __syncthreads();
+    if (!*s_flag) return;                       // block-uniform
+    __threadfence();                            // the other blocks' partials, published before their count
+    stats_group_sum(partials, n_partials, g, sc.group_partials, sm);
+    if (threadIdx.x < ABR_NUM_ACC) __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sc.counters[1 + g] = 0u;
+        *s_flag = atomicAdd(sc.counters, 1u) == (unsigned)(n_groups - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!*s_flag) return;
+    __threadfence();
+    stats_final_sum(sc.group_partials, n_groups, out, sm);
+    if (threadIdx.x == 0) sc.counters[0] = 0u;
+}
+
 template <typename OT>
 struct RolloutOut {
     OT* __restrict__ delay; OT* __restrict__ sleep; OT* __restrict__ buffer; OT* __restrict__ rebuf;
@@ -831,6 +912,10 @@ struct RolloutOut {
     const int32_t* __restrict__ in_trace_id; // nullable
     const double* __restrict__ in_offset;    // nullable = 0.0
     double* __restrict__ out_cost;           // nullable
+    // fused statistics (SPEC §6): with out_stats the kernel's own blocks add up the per-block partial sums (stats_finish
+    // above) and the block that finishes last writes the statistics vector — no second launch.
+    double* __restrict__ out_stats;          // nullable; may alias page-locked host memory
+    StatsScratch scratch;
 };
 
 // `steps` chunk steps of one session with the state in registers (SPEC §3+§4).
@@ -1056,7 +1141,8 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_tr0, s_staged;
-    __shared__ double s_part[kRolloutBlock / 32][ABR_NUM_ACC];
+    __shared__ double s_part[4][ABR_NUM_ACC];   // two warps' partial sums; four rows for stats_finish
+    __shared__ int s_flag;
     // let a dependent grid launched with programmatic stream serialization (the statistics stage 2) become resident
     // now; it waits for this grid's completion itself (griddepcontrol.wait), so only its launch latency is hidden
     asm volatile("griddepcontrol.launch_dependents;");
@@ -1156,6 +1242,11 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
             double x = s_part[0][threadIdx.x];
             for (int w = 1; w < kRolloutBlock / 32; ++w) x = dadd(x, s_part[w][threadIdx.x]);
             block_partials[(size_t)blockIdx.x * ABR_NUM_ACC + threadIdx.x] = x;
+            if (o.out_stats) __threadfence();          // the partial is visible device-wide before this block counts as done
+        }
+        if (o.out_stats) {   // launch-uniform
+            static_assert(kRolloutBlock >= kStatsLanes, "stats_finish needs 44 threads");
+            stats_finish(block_partials, (int)gridDim.x, (int)blockIdx.x, o.scratch, o.out_stats, s_part, &s_flag);
         }
     }
 }
@@ -1195,18 +1286,25 @@ abr_stats_stage1(EnvView v, double* __restrict__ partials) {
     }
 }
 
-// one block per statistic (same summation order per column as a single block walking the columns in turn)
-__global__ void __launch_bounds__(kStatsBlock)
-abr_stats_stage2(const double* __restrict__ partials, int n_partials, double* __restrict__ out) {
-    __shared__ double sm[32];
-    const int j = blockIdx.x;
+// one block per group of partials; the order of the additions is that of stats_finish, whoever runs it
+__global__ void __launch_bounds__(64)
+abr_stats_stage2(const double* __restrict__ partials, int n_partials, StatsScratch sc, double* __restrict__ out) {
+    __shared__ double sm[4][ABR_NUM_ACC];
+    __shared__ int s_flag;
     // launched with programmatic stream serialization: the grid may be resident before the kernel in front of it
     // in the stream (the episode) has finished; wait here for its completion and its writes
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    double x = 0.0;
-    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) x = dadd(x, partials[(size_t)i * ABR_NUM_ACC + j]);
-    x = block_sum(x, sm);
-    if (threadIdx.x == 0) out[j] = x;
+    const int g = blockIdx.x;
+    const int n_groups = (n_partials + kStatsGroup - 1) / kStatsGroup;
+    stats_group_sum(partials, n_partials, g, sc.group_partials, sm);
+    if (threadIdx.x < ABR_NUM_ACC) __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_flag = atomicAdd(sc.counters, 1u) == (unsigned)(n_groups - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    stats_final_sum(sc.group_partials, n_groups, out, sm);
+    if (threadIdx.x == 0) sc.counters[0] = 0u;
 }
 
 __global__ void __launch_bounds__(kStepBlock)
@@ -1310,7 +1408,7 @@ static cudaError_t launch_rollout_t(const EnvView& v, int policy, uint64_t seed,
     const dim3 grid((v.n + kRolloutBlock - 1) / kRolloutBlock), block(kRolloutBlock);
     const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
     RolloutOut<OT> o{d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_eov, d_actions_out, d_latency, d_speed,
-                     f.in_trace_id, f.in_offset, f.out_cost};
+                     f.in_trace_id, f.in_offset, f.out_cost, d_block_partials ? f.out_stats : nullptr, f.scratch};
     const bool live = v.p.live != 0;
     // shared-memory buffer: the longest C row, the longest index row and the two tables
     int smem_doubles = cum_smem_doubles(v.T_max);
@@ -1380,8 +1478,10 @@ cudaError_t launch_qoe_cost(const EnvView& v, double* d_out, cudaStream_t st) {
 int rollout_num_blocks(int n) { return n <= 0 ? 1 : (n + kRolloutBlock - 1) / kRolloutBlock; }
 
 // have_partials: d_partials already holds n_partials block sums (written by the fused episode kernel)
+int stats_num_groups(int n_partials) { return n_partials <= 0 ? 1 : (n_partials + kStatsGroup - 1) / kStatsGroup; }
+
 cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, bool have_partials, double* d_out,
-                         cudaStream_t st) {
+                         const StatsScratch& scratch, cudaStream_t st) {
     if (v.n == 0) return cudaMemsetAsync(d_out, 0, sizeof(double) * ABR_NUM_STATS, st);   // empty batch
     if (!have_partials) {
         abr_stats_stage1<<<n_partials, kStatsBlock, 0, st>>>(v, d_partials);
@@ -1389,8 +1489,8 @@ cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, b
     }
     {   // programmatic dependent launch: scheduled while the episode kernel still runs, starts working when it is done
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(ABR_NUM_ACC);
-        cfg.blockDim = dim3(kStatsBlock);
+        cfg.gridDim = dim3(stats_num_groups(n_partials));
+        cfg.blockDim = dim3(64);
         cfg.dynamicSmemBytes = 0;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -1399,7 +1499,7 @@ cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, b
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         const double* partials_c = d_partials;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, abr_stats_stage2, partials_c, n_partials, d_out);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, abr_stats_stage2, partials_c, n_partials, scratch, d_out);
         if (e != cudaSuccess) return e;
     }
     count_launch();
