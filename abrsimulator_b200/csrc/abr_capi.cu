@@ -190,6 +190,9 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
     CUDA_TRY(cudaMemcpy(d_sizes, h_sizes, sizeof(double) * V * A, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_util, util.data(), sizeof(double) * V * A, cudaMemcpyHostToDevice));
     v.trace_bw = d_bw; v.trace_len = d_len; v.trace_interval = d_int; v.sizes = d_sizes; v.util = d_util;
+    v.uniform_util = 1;   // bitwise: the kernels may then carry a step's utility over as the next step's "previous" one
+    for (size_t i = (size_t)A; i < (size_t)V * A; ++i)
+        if (memcmp(&util[i], &util[i % A], sizeof(double)) != 0) { v.uniform_util = 0; break; }
     {   // packed {size, utility} table for the step kernels
         std::vector<double> tab(2 * (size_t)V * A);
         for (size_t i = 0; i < (size_t)V * A; ++i) { tab[2 * i] = h_sizes[i]; tab[2 * i + 1] = util[i]; }

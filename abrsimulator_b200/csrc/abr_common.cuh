@@ -119,6 +119,7 @@ struct EnvView {
     const int32_t* perm;                        // session order (abr_env_set_order): caller's index of position i, or null
     unsigned long long* errors;                 // device counter of flagged sessions
     int n_traces, T_max, V, A, K, cap, n;       // n = active sessions
+    int uniform_util;                           // every chunk has the same utility row (the usual case: one bitrate ladder)
     long long session_base;
     AbrParams p;
 };

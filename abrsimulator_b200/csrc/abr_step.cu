@@ -106,6 +106,10 @@ __device__ __forceinline__ uint32_t cell_of(const double x, const double scale, 
 __device__ __forceinline__ double int2double(const int i) {
     return dsub(__hiloint2double(0x43300000, (int)((uint32_t)i ^ 0x80000000u)), 4503601774854144.0);
 }
+// (double)(a - b): the bias is folded into the subtraction (one three-input integer add)
+__device__ __forceinline__ double diff2double(const int a, const int b) {
+    return dsub(__hiloint2double(0x43300000, (int)((uint32_t)a - (uint32_t)b + 0x80000000u)), 4503601774854144.0);
+}
 
 // max(x, 0) = (x + |x|) / 2 on the FP64 pipe: exact (x + x and the halving never round; x - x = +0), two dependent
 // FP64 operations (16 cycles) where the sign-mask form of abr_common.cuh takes three on the busier integer pipe.
@@ -332,6 +336,8 @@ __device__ __forceinline__ void head_any(const Sess& s, double target, Head& h, 
     }
     double c_j = ld_c<SMEM>(s, j), c_j1 = ld_c<SMEM>(s, j + 1);
     while (j < j_hi && c_j1 <= target) { ++j; c_j = c_j1; c_j1 = ld_c<SMEM>(s, j + 1); }
+    if (!(target < c_j1)) walk_error = true;       // insurance: the candidates covered the download (head_fast
+                                                   // only reports success when they did)
     h.target = target; h.j = j; h.c_j = c_j; h.c_j1 = c_j1;
     h.kx = n == 0 ? 0.0 : dmul((double)n, s.Td);   // exact in fp64
 }
@@ -368,10 +374,11 @@ __device__ __forceinline__ void live_gate(const EnvView& v, Sess& s, LiveGate& g
 // LIVE: live-streaming semantics of SPEC §7 (`g` = the step's pause gate).
 // Returns true when the step moved the trace position in time (sleep): s.pos was then recomputed from (seg, phi)
 // and a head issued ahead for the next step is stale.
-// `p` / `V`: the environment's parameters and chunk count.
+// `p` / `V`: the environment's parameters and chunk count; inv_q = pow2_inverse(p.sleep_quantum).
 template <bool SMEM, bool FAST, bool LIVE>
 __device__ __forceinline__ bool step_tail(const AbrParams& p, const int V, Sess& s, const Head& h, const int q,
-                                          const Lookup& lk, const LiveGate& g, StepRes& r, const bool want_thr) {
+                                          const Lookup& lk, const LiveGate& g, StepRes& r, const bool want_thr,
+                                          const double inv_q) {
     r.reset_mpc = false;
     if (!FAST && s.done) {  // only reachable with auto_reset == 0
         r.delay = r.sleep = r.rebuf = r.reward = r.thr = r.u = r.smooth = r.latency = r.startup = r.area = r.played = 0.0;
@@ -383,9 +390,8 @@ __device__ __forceinline__ bool step_tail(const AbrParams& p, const int V, Sess&
     r.inert = false;
     const double size = lk.size, u = lk.u, u_prev = lk.u_prev;
     const int T = s.T;
-    if (!(h.target < h.c_j1)) r.walk_error = true;   // insurance: the index covered the download
     // segment boundaries crossed: (j - seg) + n*T (both terms and the sum are exact)
-    const double kd = dadd(int2double(h.j - s.seg), h.kx);
+    const double kd = dadd(diff2double(h.j, s.seg), h.kx);
     const double phi_new = ddiv(dsub(h.target, h.c_j), dsub(h.c_j1, h.c_j));   // fraction of segment j consumed
     const double delay = dadd(max0d(dmul(dadd(kd, dsub(phi_new, s.phi)), s.I)), p.rtt);
     int seg = h.j;
@@ -408,12 +414,19 @@ __device__ __forceinline__ bool step_tail(const AbrParams& p, const int V, Sess&
         sleep = g.idle;
     } else {
         // 3.2 buffer drain / rebuffer
-        rebuf = max0d(dsub(delay, s.buffer));
-        buffer = dadd(max0d(dsub(s.buffer, delay)), p.chunk_length);
+        // max(delay - buffer, 0) and max(buffer - delay, 0) from one subtraction: buffer - delay is exactly
+        // -(delay - buffer) and at most one of the two is positive, so both are sign-masked copies of the difference
+        // (five integer operations instead of five more on the FP64 pipe, whose instructions issue at half rate)
+        {
+            const double d = dsub(delay, s.buffer);
+            const int hi = __double2hiint(d), lo = __double2loint(d);
+            const int neg = hi >> 31;                      // all ones when the buffer outlasts the download
+            rebuf = __hiloint2double(hi & ~neg, lo & ~neg);
+            buffer = dadd(__hiloint2double((hi ^ (int)0x80000000u) & neg, lo & neg), p.chunk_length);
+        }
         // 3.3 sleep cap
         if (buffer > p.max_buffer) {
             const double over = dsub(buffer, p.max_buffer);
-            const double inv_q = pow2_inverse(p.sleep_quantum);
             sleep = dmul(ceil(inv_q != 0.0 ? dmul(over, inv_q) : ddiv(over, p.sleep_quantum)), p.sleep_quantum);
             buffer = dsub(buffer, sleep);
             advance_trace(seg, phi, sleep, s.I, T);
@@ -461,7 +474,7 @@ __device__ __forceinline__ void step_core(const EnvView& v, Sess& s, const int q
         if (LIVE) live_gate<SMEM>(v, s, g);
         head<SMEM>(s, dadd(s.pos, lk.size), h, r.walk_error);
     }
-    step_tail<SMEM, FAST, LIVE>(v.p, v.V, s, h, q, lk, g, r, want_thr);
+    step_tail<SMEM, FAST, LIVE>(v.p, v.V, s, h, q, lk, g, r, want_thr, pow2_inverse(v.p.sleep_quantum));
 }
 
 // SPEC §4, buffer-based policy on the pre-step buffer level.
@@ -926,11 +939,13 @@ struct RolloutOut {
 //
 // Software pipeline (policies whose action does not depend on the state: FIXED, RANDOM; not LIVE, whose pause gate
 // moves the position before every download): iteration t holds the finished head of step t and issues the head of
-// step t+1 from `head(t).target + size(t+1)` before running the tail of step t, so the index / C loads of the next
-// step overlap the division and the buffer / reward arithmetic of this one.  The assumption is that step t does not
+// step t+1 from `head(t).target + size(t+1)` next to the tail of step t, so the index / C loads of the next step
+// overlap the division and the buffer / reward arithmetic of this one.  The assumption is that step t does not
 // sleep; when it does (its position moved in time) the head of step t+1 is redone from the moved position.
 // The action and table reads run two steps ahead for the same reason.
-template <int POLICY, bool SMEM, bool FAST, bool NOOUT, bool LIVE, typename OT>
+// UNI (with FAST, policies that run ahead): every chunk has the same utility row, so the previous step's utility is
+// the next step's "previous utility" (SPEC §3.4) — carried in a register instead of looked up.
+template <int POLICY, bool SMEM, bool FAST, bool NOOUT, bool LIVE, bool UNI, typename OT>
 __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const int i, const uint32_t seed_lo,
                                                 const uint32_t seed_hi, const int steps, const uint32_t step_base,
                                                 const int32_t* __restrict__ actions_in, const RolloutOut<OT>& o,
@@ -940,6 +955,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     const unsigned long long gsession = (unsigned long long)(v.session_base + (v.perm ? __ldg(v.perm + i) : i));
     double a_rew = 0.0, a_reb = 0.0, a_u = 0.0, a_sm = 0.0, a_sl = 0.0, a_dl = 0.0, a_su = 0.0, a_lat = 0.0, a_pl = 0.0;
     int n_steps = 0, n_eps = 0;
+    const int chunk_in = s.chunk;
     bool flagged = false, reset_mpc = false;
     const uint32_t n = (uint32_t)v.n;
     const bool hist = !FAST && v.p.track_history != 0;
@@ -966,8 +982,12 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             const uint32_t tg = step_base + (uint32_t)t;   // step index since the last reset (SPEC §4)
             if ((tg & 7u) == 0u || t == 0) {   // one Philox block per eight steps: counter = (session, step / 8),
                                                // 16-bit slice step % 8 (low half of word 0 first)
+                // the key enters through an empty asm so that its ten-round schedule is recomputed here (18 additions
+                // per eight steps) instead of being hoisted out of the step loop into 18 live registers
+                uint32_t k_lo = seed_lo, k_hi = seed_hi;
+                asm volatile("" : "+r"(k_lo), "+r"(k_hi));
                 const uint4 r = philox4x32_10((uint32_t)gsession, (uint32_t)(gsession >> 32), tg >> 3, 0u,
-                                              seed_lo, seed_hi);
+                                              k_lo, k_hi);
                 const uint32_t A = (uint32_t)v.A;   // <= 16: an action fits a nibble, (x16 * A) >> 16 < A
                 auto two = [A](uint32_t x) { return (((x & 0xffffu) * A) >> 16) | ((((x >> 16) * A) >> 16) << 4); };
                 packed = two(r.x) | (two(r.y) << 8) | (two(r.z) << 16) | (two(r.w) << 24);
@@ -991,6 +1011,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
     LiveGate g;
     g.buffer = 0.0; g.rebuf = g.idle = 0.0;
     g.a.startup = g.a.area = g.a.played = g.a.tc = 0.0;
+    const double inv_q = pow2_inverse(v.p.sleep_quantum);   // launch-uniform
     if (AHEAD) {
         const AbrParams& pl = v.p;
         const int Vr = v.V;
@@ -998,10 +1019,14 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
         Lookup lk0 = lookup_tables<SMEM>(s, v.A, Vr, s.chunk, q0, s.last_q, prev_ladder);
         int c1 = next_chunk(s.chunk);            // chunk index / previous quality step t+1 will see
         int lq1 = next_last_q(s.chunk, q0);
+        // UNI: the utility an auto-reset leaves as "previous" (default_quality; none = no smoothness term)
+        double u_dq = 0.0;
+        if (UNI && dq_ >= 0) u_dq = SMEM ? lds_f64(s.tab_s + 16u * (uint32_t)dq_ + 8u) : __ldg(&s.tab[dq_].y);
         Head h;
-        r.walk_error = false;
-        head<SMEM>(s, dadd(s.pos, lk0.size), h, r.walk_error);
-        bool spec = true;   // warp-uniform: no lane of the warp slept in the previous step
+        bool werr = false;
+        head<SMEM>(s, dadd(s.pos, lk0.size), h, werr);
+        const bool can_speculate = SMEM || s.M > 0;   // head_fast needs the bucket index
+        bool calm = true;   // warp-uniform: no lane of the warp slept in the previous step
         const unsigned lanes = __activemask();   // the warp's sessions (converged here; all run `steps` iterations)
 #pragma unroll kRolloutUnroll
         for (int t = 0; t < steps; ++t) {
@@ -1009,13 +1034,22 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             // sits at the cap sleep after every chunk, and the lanes of a warp tend to do so together (same trace):
             // a warp that slept in the last step does not speculate (its head would be redone anyway).
             const int q1 = action_at(t + 1);
-            const Lookup lk1 = lookup_tables<SMEM>(s, v.A, Vr, c1, q1, lq1, prev_ladder);
+            Lookup lk1;
+            if (UNI) {
+                ABR_CHECK(c1 >= 0 && c1 < Vr && q1 >= 0 && c1 * v.A + q1 < s.chk_tab_n, "{size, utility} table entry");
+                const double2 su = SMEM ? lds_f64x2(s.tab_s + 16u * (uint32_t)(c1 * v.A + q1)) : __ldg(s.tab + c1 * v.A + q1);
+                lk1.size = su.x;
+                lk1.u = su.y;
+                lk1.u_prev = c1 != 0 ? lk0.u : (dq_ >= 0 ? u_dq : su.y);   // c1 == 0: step t ends an episode
+            } else {
+                lk1 = lookup_tables<SMEM>(s, v.A, Vr, c1, q1, lq1, prev_ladder);
+            }
             Head h1;
             bool ok1 = false;
-            if (spec && (SMEM || s.M > 0)) ok1 = head_fast<SMEM>(s, dadd(h.target, lk1.size), h1);
+            if (calm && can_speculate) ok1 = head_fast<SMEM>(s, dadd(h.target, lk1.size), h1);
             // tail of step t
             ABR_CHECK((unsigned long long)ix < (unsigned long long)steps * n, "trajectory element index");
-            const bool moved = step_tail<SMEM, FAST, false>(pl, Vr, s, h, q0, lk0, g, r, hist);
+            const bool moved = step_tail<SMEM, FAST, false>(pl, Vr, s, h, q0, lk0, g, r, hist, inv_q);
             if (NOOUT) {
             } else if (FAST) {
                 __stcs(o.delay + ix, (OT)r.delay); __stcs(o.sleep + ix, (OT)r.sleep); __stcs(o.buffer + ix, (OT)r.buffer);
@@ -1033,26 +1067,27 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             if (FAST || !r.inert) {
                 a_rew = dadd(a_rew, r.reward); a_reb = dadd(a_reb, r.rebuf); a_u = dadd(a_u, r.u);
                 a_sm = dadd(a_sm, r.smooth); a_sl = dadd(a_sl, r.sleep); a_dl = dadd(a_dl, r.delay);
-                n_steps += 1;
-                n_eps += r.eov ? 1 : 0;
-                if (r.reset_mpc) reset_mpc = true;   // an auto-reset also clears the robust-MPC predictor state
+                if (!FAST) {     // FAST: every step counts and every V-th ends an episode (closed form below)
+                    n_steps += 1;
+                    n_eps += r.eov ? 1 : 0;
+                }
+                if (FAST) {}                         // closed form below
+                else if (r.reset_mpc) reset_mpc = true;   // an auto-reset also clears the robust-MPC predictor state
                 else if (hist) v.bw_hist[(size_t)((s.hist_len - 1) % v.K) * v.cap + i] = r.thr;
             }
-            flagged |= r.walk_error;
-            r.walk_error = false;
-            spec = !__any_sync(lanes, moved);
+            calm = !__any_sync(lanes, moved);
             if (moved || !ok1) {   // s.pos: where step t left the session
                 const double raw = dadd(s.pos, lk1.size);
-                if (!(SMEM || s.M > 0) || !head_fast<SMEM>(s, raw, h1)) head_any<SMEM>(s, raw, h1, r.walk_error);
+                if (!can_speculate || !head_fast<SMEM>(s, raw, h1)) head_any<SMEM>(s, raw, h1, werr);
             }
             h = h1;
             lk0 = lk1;
             q0 = q1;
-            lq1 = next_last_q(c1, q1);
+            if (!UNI) lq1 = next_last_q(c1, q1);
             c1 = next_chunk(c1);
             ix += n;
         }
-        flagged |= r.walk_error;
+        flagged |= werr;
     } else {
         for (int t = 0; t < steps; ++t) {
             const int q = action_at(t);
@@ -1086,6 +1121,11 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
             }
             ix += n;
         }
+    }
+    if (FAST && AHEAD) {   // auto_reset is on: the session ran `steps` steps and wrapped every V chunks
+        n_steps = steps;
+        n_eps = (int)(((long long)chunk_in + steps) / v.V);
+        reset_mpc = n_eps > 0;
     }
     const double a_steps = (double)n_steps, a_eps = (double)n_eps;   // exact: counts below 2^31
     if (flagged || (LIVE && s.bad_speed)) atomicAdd(v.errors, 1ull);
@@ -1127,7 +1167,7 @@ __device__ __forceinline__ void rollout_session(const EnvView& v, Sess& s, const
 // is followed by the index row (idx_stride(T_max) 16-bit words, 16-byte aligned) and the sizes and utility tables.
 // 8 blocks (16 warps) per SM: <= 128 registers, so that the 1 024 blocks of the 65 536-session shape are all
 // co-resident (6.9 per SM).
-template <int POLICY, bool FAST, bool NOOUT, bool LIVE, typename OT>
+template <int POLICY, bool FAST, bool NOOUT, bool LIVE, bool UNI, typename OT>
 #ifndef ABR_ROLLOUT_MINBLOCKS
 #define ABR_ROLLOUT_MINBLOCKS 8   // <= 128 registers.  Registers are allocated per warp in steps of 32 per thread, so 129..160
                                   // registers mean 12 warps = six 64-thread blocks per SM (measured: 140 and 144 registers
@@ -1221,11 +1261,11 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
             ABR_CHECK(cum_stride(v.T_max) <= smem_doubles && s.T + 4 < cum_stride(v.T_max), "staged rows fit the shared-memory buffer");
 #endif
             if (fresh) s.pos = position_of<true>(s, s.seg, s.phi);
-            rollout_session<POLICY, true, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);
+            rollout_session<POLICY, true, FAST, NOOUT, LIVE, UNI, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);
         }
     } else if (valid) {
         if (fresh) s.pos = position_of<false>(s, s.seg, s.phi);
-        rollout_session<POLICY, false, FAST, NOOUT, LIVE, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);
+        rollout_session<POLICY, false, FAST, NOOUT, LIVE, UNI, OT>(v, s, i, seed_lo, seed_hi, steps, step_base, actions_in, o, acc_new, fresh);
     }
     // statistics stage 1 fused into the episode: per-block sums of the updated accumulators in a fixed order
     // (warp tree, then warps in ascending order), so abr_stats_partial only has to add the block partials
@@ -1422,20 +1462,24 @@ static cudaError_t launch_rollout_t(const EnvView& v, int policy, uint64_t seed,
     const bool none = !live && !d_delay && !d_sleep && !d_buffer && !d_rebuf && !d_reward && !d_eov && !d_actions_out &&
                       v.p.track_history == 0 && v.p.auto_reset != 0;
     cudaError_t e = cudaSuccess;
-#define ABR_LAUNCH_ROLLOUT_V(P, F, N, L)                                                                           \
+#define ABR_LAUNCH_ROLLOUT_V(P, F, N, L, U)                                                                        \
     do {                                                                                                           \
-        e = allow_smem(abr_rollout_kernel<P, F, N, L, OT>, smem_bytes);                                            \
+        e = allow_smem(abr_rollout_kernel<P, F, N, L, U, OT>, smem_bytes);                                         \
         if (e == cudaSuccess)                                                                                      \
-            abr_rollout_kernel<P, F, N, L, OT><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, step_base,        \
-                                                                                d_actions_in, o, smem_doubles,     \
-                                                                                d_block_partials);                 \
+            abr_rollout_kernel<P, F, N, L, U, OT><<<grid, block, smem_bytes, st>>>(v, lo, hi, steps, step_base,     \
+                                                                                   d_actions_in, o, smem_doubles,  \
+                                                                                   d_block_partials);              \
     } while (0)
+    // the carried-utility form only exists where it pays: the run-ahead loop (not the buffer-based policy)
 #define ABR_LAUNCH_ROLLOUT(P)                                                                                      \
     do {                                                                                                           \
-        if (live) ABR_LAUNCH_ROLLOUT_V(P, false, false, true);                                                     \
-        else if (fast) ABR_LAUNCH_ROLLOUT_V(P, true, false, false);                                                \
-        else if (none) ABR_LAUNCH_ROLLOUT_V(P, true, true, false);                                                 \
-        else ABR_LAUNCH_ROLLOUT_V(P, false, false, false);                                                         \
+        constexpr bool kAhead = P != ABR_POLICY_BBA;                                                               \
+        if (live) ABR_LAUNCH_ROLLOUT_V(P, false, false, true, false);                                              \
+        else if (fast && kAhead && v.uniform_util) ABR_LAUNCH_ROLLOUT_V(P, true, false, false, kAhead);            \
+        else if (fast) ABR_LAUNCH_ROLLOUT_V(P, true, false, false, false);                                         \
+        else if (none && kAhead && v.uniform_util) ABR_LAUNCH_ROLLOUT_V(P, true, true, false, kAhead);             \
+        else if (none) ABR_LAUNCH_ROLLOUT_V(P, true, true, false, false);                                          \
+        else ABR_LAUNCH_ROLLOUT_V(P, false, false, false, false);                                                  \
     } while (0)
     switch (policy) {
         case ABR_POLICY_FIXED: ABR_LAUNCH_ROLLOUT(ABR_POLICY_FIXED); break;

@@ -1,5 +1,6 @@
 """Fixed cost vs per-step cost of the fused episode kernel: CUDA-event time of abr_env_run for several episode lengths.
-usage: python profiles/time_steps.py [sessions ...]"""
+usage: python profiles/time_steps.py [sessions ...] [param=value ...]   (AbrParams fields, e.g. max_buffer=1e9: no session
+ever sleeps; max_buffer=0: every step sleeps)"""
 import sys
 
 import torch
@@ -13,8 +14,9 @@ bitrates, sizes = synth.make_video(V)
 bw, tl, ti = synth.make_traces(1024, 2048)
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for N in [int(x) for x in sys.argv[1:]] or [4736, 65536]:
-    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+params = {a.split("=")[0]: float(a.split("=")[1]) for a in sys.argv[1:] if "=" in a}
+for N in [int(x) for x in sys.argv[1:] if "=" not in x] or [4736, 65536]:
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, **params)
     tid, off = synth.make_sessions(N, 1024, 2048, group=64)
     tid_d, off_d = torch.from_numpy(tid).to(dev), torch.from_numpy(off).to(dev)
     row = []
