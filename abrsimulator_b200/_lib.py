@@ -40,10 +40,14 @@ class AbrParams(C.Structure):
                                  "track_history", "track_acc", "live", "smooth_prev_ladder")]
 
 
+class AbrObsSpec(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("buffer_scale", "throughput_scale", "delay_scale", "size_scale")]
+
+
 # every symbol include/abr_b200.h declares (tests check that the .so exports all of them)
 SYMBOLS = ("abr_version", "abr_last_error", "abr_launch_count", "abr_device_info", "abr_params_default",
            "abr_env_create", "abr_env_destroy", "abr_env_num_sessions", "abr_sort_by_trace", "abr_env_set_order", "abr_env_reset", "abr_env_reset_host",
-           "abr_env_step", "abr_env_step_live", "abr_env_step_f32", "abr_env_qoe_cost", "abr_env_rollout_fused",
+           "abr_env_step", "abr_env_step_live", "abr_env_step_f32", "abr_env_step_policy", "abr_env_qoe_cost", "abr_env_rollout_fused",
            "abr_env_rollout_fused_live", "abr_env_rollout_fused_f32", "abr_env_run", "abr_env_mpc_decide", "abr_stats_partial",
            "abr_env_state_ptr",
            "abr_env_error_count", "abr_env_run_host", "abr_mpc_decide", "abr_mpc_decide_host", "abr_mpc_decide_startup",
@@ -75,6 +79,8 @@ def load():
     vp = C.c_void_p
     lib.abr_env_run_host.argtypes = [vp, C.c_int, C.c_uint64, C.c_int, vp, vp, C.c_int, C.c_longlong, vp, vp, vp, vp, vp, vp]
     lib.abr_env_run_host.restype = C.c_int
+    lib.abr_env_step_policy.argtypes = [vp, vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.abr_env_step_policy.restype = C.c_int
     _lib = lib
     return lib
 

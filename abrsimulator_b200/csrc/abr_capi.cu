@@ -49,6 +49,7 @@ struct AbrEnv {
     int n_order = 0;
     int fresh_partials = 0;   // > 0: d_stats_partials holds that many block sums of the current accumulators
     double* d_stats_out = nullptr;
+    uint32_t* d_draw_counter = nullptr;       // draws of abr_env_step_policy since the last reset
     StatsScratch stats_scratch;               // group sums and the counters of finished blocks / groups (zero between launches)
     // scratch for the *_host entry points
     int32_t* d_trace_id = nullptr;
@@ -238,6 +239,8 @@ int abr_env_create(const double* h_trace_bw, const int32_t* h_trace_len, const d
                             ? stats_num_partials(max_sessions) : rollout_num_blocks(max_sessions);
     CUDA_TRY(e->alloc(&e->d_stats_partials, (size_t)e->n_partials_cap * ABR_NUM_ACC));
     CUDA_TRY(e->alloc(&e->d_stats_out, ABR_NUM_STATS));
+    CUDA_TRY(e->alloc(&e->d_draw_counter, 1));
+    CUDA_TRY(cudaMemset(e->d_draw_counter, 0, sizeof(uint32_t)));
     {
         const int n_groups = stats_num_groups(e->n_partials_cap);
         CUDA_TRY(e->alloc(&e->stats_scratch.group_partials, (size_t)n_groups * ABR_NUM_ACC));
@@ -308,6 +311,7 @@ int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_
     env->fresh_partials = 0;
     env->was_reset = true;
     env->step_base = 0;
+    CUDA_TRY(cudaMemsetAsync(env->d_draw_counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
     CUDA_TRY(launch_reset(env->v, d_trace_id, d_start_offset, (cudaStream_t)stream));
     return ABR_OK;
 }
@@ -344,6 +348,29 @@ int abr_env_step_live(AbrEnv* env, const int32_t* d_action, const double* d_spee
                       uint8_t* d_end_of_video, double* d_throughput, void* stream) {
     return env_step_any<double>(env, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency,
                                 d_next_sizes, d_end_of_video, d_throughput, stream);
+}
+
+int abr_env_step_policy(AbrEnv* env, const float* d_logits, int sample, uint64_t seed, const AbrObsSpec* spec,
+                        float* d_obs, int32_t* d_action_out, double* d_reward_sum, double* d_delay, double* d_sleep,
+                        double* d_buffer, double* d_rebuf, double* d_reward, uint8_t* d_end_of_video, void* stream) {
+    if (!env) return fail(ABR_ERR_INVALID, "env is NULL");
+    if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
+    if (env->v.p.live) return fail(ABR_ERR_STATE, "abr_env_step_policy is not available in live mode (SPEC 7)");
+    if (env->v.n == 0) return ABR_OK;
+    if (!d_logits) return fail(ABR_ERR_INVALID, "logits is NULL");
+    StepPolicy pol;
+    pol.logits = d_logits;
+    pol.draw = sample ? env->d_draw_counter : nullptr;
+    pol.seed_lo = (uint32_t)seed; pol.seed_hi = (uint32_t)(seed >> 32);
+    pol.action_out = d_action_out; pol.obs = d_obs; pol.reward_sum = d_reward_sum;
+    if (spec) {
+        pol.s_buffer = spec->buffer_scale; pol.s_thr = spec->throughput_scale;
+        pol.s_delay = spec->delay_scale; pol.s_size = spec->size_scale;
+    }
+    env->fresh_partials = 0;
+    CUDA_TRY(launch_step_policy(env->v, pol, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_end_of_video,
+                                env->d_draw_counter, (cudaStream_t)stream));
+    return ABR_OK;
 }
 
 int abr_env_step_f32(AbrEnv* env, const int32_t* d_action, const double* d_speed, float* d_delay, float* d_sleep,

@@ -128,6 +128,20 @@ struct EnvView {
 cudaError_t launch_trace_table(const EnvView& v, double* d_cum, uint16_t* d_idx, int32_t* d_ok, TraceMeta* d_meta,
                                cudaStream_t st);
 cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st);
+// Policy-in-the-loop step (abr_env_step_policy, SPEC §4.1): the action is drawn inside the step kernel from the
+// caller's logits and the next observation is written by the same kernel.
+struct StepPolicy {
+    const float* __restrict__ logits = nullptr;    // [N][A] row-major scores of the caller's policy
+    const uint32_t* __restrict__ draw = nullptr;   // device counter: index of this draw (Gumbel-max); null = greedy arg max
+    uint32_t seed_lo = 0, seed_hi = 0;
+    int32_t* __restrict__ action_out = nullptr;    // [N], nullable
+    float* __restrict__ obs = nullptr;             // [4 + A][N] feature-major, nullable
+    double s_buffer = 1.0, s_thr = 1.0, s_delay = 1.0, s_size = 1.0;   // observation scales
+    double* __restrict__ reward_sum = nullptr;     // [N]: += reward, nullable
+};
+cudaError_t launch_step_policy(const EnvView& v, const StepPolicy& pol, double* d_delay, double* d_sleep, double* d_buffer,
+                               double* d_rebuf, double* d_reward, uint8_t* d_eov, uint32_t* d_draw_counter,
+                               cudaStream_t st);
 cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double* d_speed, double* d_delay,
                         double* d_sleep, double* d_buffer, double* d_rebuf, double* d_reward, double* d_latency,
                         double* d_next_sizes, uint8_t* d_eov, double* d_thr, cudaStream_t st);

@@ -29,6 +29,8 @@
 //     copies and every probe is an LDS — the "traces staged in shared memory" design of the north star.
 //   * global path (any session order): read-only loads (ld.global.nc): one 32-byte record, one index pair and
 //     one or two sectors of C per step; the tables (25 MB at the benchmark shape) are L2-resident.
+#include <type_traits>
+
 #include "abr_common.cuh"
 
 namespace abr {
@@ -102,11 +104,8 @@ __device__ __forceinline__ uint32_t cell_of(const double x, const double scale, 
     return min((uint32_t)__double2loint(y), (uint32_t)(M - 1));
 }
 
-// (double)i for |i| < 2^31, exact, without the XU conversion: 2^52 + 2^31 + i has i + 2^31 in its low word.
-__device__ __forceinline__ double int2double(const int i) {
-    return dsub(__hiloint2double(0x43300000, (int)((uint32_t)i ^ 0x80000000u)), 4503601774854144.0);
-}
-// (double)(a - b): the bias is folded into the subtraction (one three-input integer add)
+// (double)(a - b) for |a - b| < 2^31, exact, without the XU conversion: 2^52 + 2^31 + i has i + 2^31 in its low word;
+// the bias is folded into the subtraction (one three-input integer add)
 __device__ __forceinline__ double diff2double(const int a, const int b) {
     return dsub(__hiloint2double(0x43300000, (int)((uint32_t)a - (uint32_t)b + 0x80000000u)), 4503601774854144.0);
 }
@@ -651,8 +650,39 @@ __device__ __forceinline__ uint32_t idx_bytes_of(int M) { return (uint32_t)((M +
 // compiled without the null checks and the inert/history/accumulator bookkeeping (next_sizes and throughput stay
 // optional in both variants).
 // OT: element type of the outputs (double, or float for the optional fp32-output mode: arithmetic stays fp64).
-template <bool SMEM, bool FAST, bool LIVE, typename OT>
-__device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const int i, const int q_in,
+// SPEC §4.1: the action of a policy-in-the-loop step.  Greedy: the first arg max of the session's logits.  Sampled:
+// Gumbel-max — arg max of logits[a] - ln(-ln(u_a)) is a draw from softmax(logits) — with u_a = (x_a + 0.5) / 2^23 in
+// (0, 1), x_a the upper 23 bits of word a mod 4 of the Philox4x32-10 block with counter (global session index,
+// draw index, a div 4) and the caller's seed as key; fp32 arithmetic.  A NaN score never wins; all-NaN gives 0.
+__device__ __forceinline__ int policy_action(const EnvView& v, const StepPolicy& pol, const int i) {
+    const int A = v.A;
+    const float* __restrict__ row = pol.logits + (size_t)i * A;
+    const bool sample = pol.draw != nullptr;
+    const uint32_t draw = sample ? __ldg(pol.draw) : 0u;
+    const unsigned long long g = (unsigned long long)(v.session_base + (v.perm ? __ldg(v.perm + i) : i));
+    float best = __int_as_float(0xff800000);   // -inf
+    int arg = 0;
+    for (int a0 = 0; a0 < A; a0 += 4) {
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        if (sample) r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), draw, (uint32_t)(a0 >> 2), pol.seed_lo, pol.seed_hi);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (a0 + k < A) {
+                float x = __ldg(row + a0 + k);
+                if (sample) {
+                    const float u = __fmul_rn(__fadd_rn((float)(w[k] >> 9), 0.5f), 1.1920928955078125e-07f);   // 2^-23
+                    x = __fsub_rn(x, logf(-logf(u)));
+                }
+                if (x > best) { best = x; arg = a0 + k; }
+            }
+        }
+    }
+    return arg;
+}
+
+template <bool SMEM, bool FAST, bool LIVE, bool POL, typename OT>
+__device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const int i, const int q_in, const StepPolicy& pol,
                                              const double* __restrict__ speed, OT* __restrict__ o_delay,
                                              OT* __restrict__ o_sleep, OT* __restrict__ o_buffer,
                                              OT* __restrict__ o_rebuf, OT* __restrict__ o_reward,
@@ -670,7 +700,7 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
     if (bad) atomicAdd(v.errors, 1ull);
     StepRes r;
     const Lookup lk = lookup_tables<false>(s, v.A, v.V, s.chunk, q, s.last_q, v.p.smooth_prev_ladder != 0);
-    step_core<SMEM, FAST, LIVE>(v, s, q, lk, r, (!FAST && v.p.track_history) || o_thr != nullptr);
+    step_core<SMEM, FAST, LIVE>(v, s, q, lk, r, (!FAST && v.p.track_history) || o_thr != nullptr || (POL && pol.obs));
     if (r.walk_error || (LIVE && s.bad_speed)) atomicAdd(v.errors, 1ull);
     if (FAST) {
         v.seg[i] = s.seg; v.chunk[i] = s.chunk; v.last_q[i] = s.last_q; v.phi[i] = s.phi; v.pos[i] = s.pos;
@@ -716,6 +746,22 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
         if (o_reward) __stcs(o_reward + i, (OT)r.reward);
         if (o_eov) o_eov[i] = r.eov ? 1 : 0;
     }
+    if (POL) {   // SPEC §4.1: the chosen action, the running reward and the next observation, feature-major fp32
+        if (pol.action_out) pol.action_out[i] = q;
+        if (pol.reward_sum) pol.reward_sum[i] = dadd(pol.reward_sum[i], r.reward);
+        if (pol.obs) {
+            float* __restrict__ ob = pol.obs + i;
+            const size_t n = (size_t)v.n;
+            const int A = v.A;
+            __stcs(ob, (float)dmul(r.buffer, pol.s_buffer));
+            __stcs(ob + n, (float)dmul(r.thr, pol.s_thr));
+            __stcs(ob + 2 * n, (float)dmul(r.delay, pol.s_delay));
+            __stcs(ob + 3 * n, (float)ddiv((double)q, (double)A));
+            for (int a = 0; a < A; ++a)
+                __stcs(ob + (size_t)(4 + a) * n,
+                       (float)((!FAST && s.done) ? 0.0 : dmul(__ldg(v.sizes + s.chunk * A + a), pol.s_size)));
+        }
+    }
     if (o_latency) __stcs(o_latency + i, (OT)r.latency);
     if (o_thr) __stcs(o_thr + i, (OT)r.thr);
     if (o_next_sizes) {
@@ -730,16 +776,18 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
 // index rows fit in the shared-memory buffer, the block stages them with two TMA bulk copies — once, for as long as
 // the following tiles stay on that trace; no barrier is needed while the rows stay — and the probes of the lanes on
 // that trace are LDS.  Every other lane reads the L2-resident tables directly (one index pair + one or two sectors of C).
-template <bool FAST, bool LIVE, typename OT>
-__global__ void __launch_bounds__(kTile, LIVE ? 4 : kTileBlocksPerSM)
+// POL: the actions come from the caller's logits (policy_action) instead of `action`, and the kernel also writes the
+// next observation (SPEC §4.1); never with FAST or LIVE.
+template <bool FAST, bool LIVE, bool POL, typename OT>
+__global__ void __launch_bounds__(kTile, (LIVE || POL) ? 4 : kTileBlocksPerSM)
 abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __restrict__ speed,
                 OT* __restrict__ o_delay, OT* __restrict__ o_sleep, OT* __restrict__ o_buffer,
                 OT* __restrict__ o_rebuf, OT* __restrict__ o_reward, OT* __restrict__ o_latency,
                 OT* __restrict__ o_next_sizes, uint8_t* __restrict__ o_eov, OT* __restrict__ o_thr,
-                int smem_doubles, int tiles_per_block) {
+                int smem_doubles, int tiles_per_block, const StepPolicy pol) {
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
-#define ABR_STEP_SESSION_ARGS v, s, i, q_cur, speed, o_delay, o_sleep, o_buffer, o_rebuf, o_reward, o_latency, o_next_sizes, o_eov, o_thr
+#define ABR_STEP_SESSION_ARGS v, s, i, q_cur, pol, speed, o_delay, o_sleep, o_buffer, o_rebuf, o_reward, o_latency, o_next_sizes, o_eov, o_thr
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
     if (smem_doubles != 0) {
         if (threadIdx.x == 0) {
@@ -759,7 +807,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     {
         const int t0 = blockIdx.x * tiles_per_block * kTile;
         const int i0 = t0 + threadIdx.x;
-        if (i0 < v.n) { w_next = load_raw(v, i0); q_next = action[i0]; }
+        if (i0 < v.n) { w_next = load_raw(v, i0); if (!POL) q_next = action[i0]; }
         if (t0 < v.n) { first_next = __ldg(v.trace_id + t0); last_next = __ldg(v.trace_id + min(t0 + kTile, v.n) - 1); }
     }
     for (int k = 0; k < tiles_per_block; ++k) {
@@ -768,13 +816,13 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
         const int i = tile0 + threadIdx.x;
         const bool valid = i < v.n;
         const RawState w = w_next;
-        const int q_cur = q_next;
+        const int q_cur = POL ? (valid ? policy_action(v, pol, i) : 0) : q_next;
         // traces of the first and the last session of the tile: the same words in every thread, so decisions taken
         // on them are block-uniform without a barrier.  Equal ends mean one trace for callers that keep sessions
         // sorted by trace; a lane that disagrees anyway simply takes the global path.
         const int tr_first = first_next, tr_last = last_next;
         if (k + 1 < tiles_per_block && tile0 + kTile < v.n) {
-            if (i + kTile < v.n) { w_next = load_raw(v, i + kTile); q_next = action[i + kTile]; }
+            if (i + kTile < v.n) { w_next = load_raw(v, i + kTile); if (!POL) q_next = action[i + kTile]; }
             first_next = __ldg(v.trace_id + tile0 + kTile);
             last_next = __ldg(v.trace_id + min(tile0 + 2 * kTile, v.n) - 1);
         }
@@ -782,7 +830,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
         int tr = -1;
         if (valid) { make_sess(v, i, w, s); tr = w.tr; }
         if (smem_doubles == 0) {                 // launch-uniform: no shared-memory row buffer
-            if (valid) step_session<false, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
+            if (valid) step_session<false, FAST, LIVE, POL, OT>(ABR_STEP_SESSION_ARGS);
             continue;
         }
         if (tr_first == tr_last && tr_first != staged) {   // block-uniform: stage another trace's rows
@@ -807,9 +855,9 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
                 ABR_CHECK(row_bytes_of(s.T) <= 8u * (uint32_t)smem_doubles && idx_bytes_of(s.M) <= 2u * (uint32_t)idx_stride(v.T_max),
                           "staged rows fit the shared-memory buffer");
 #endif
-                step_session<true, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
+                step_session<true, FAST, LIVE, POL, OT>(ABR_STEP_SESSION_ARGS);
             } else {
-                step_session<false, FAST, LIVE, OT>(ABR_STEP_SESSION_ARGS);
+                step_session<false, FAST, LIVE, POL, OT>(ABR_STEP_SESSION_ARGS);
             }
         }
     }
@@ -1385,10 +1433,12 @@ static cudaError_t allow_smem(Kernel kernel, size_t bytes) {
 template <typename OT>
 static cudaError_t launch_step_t(const EnvView& v, const int32_t* d_action, const double* d_speed, OT* d_delay,
                                  OT* d_sleep, OT* d_buffer, OT* d_rebuf, OT* d_reward, OT* d_latency,
-                                 OT* d_next_sizes, uint8_t* d_eov, OT* d_thr, cudaStream_t st) {
+                                 OT* d_next_sizes, uint8_t* d_eov, OT* d_thr, cudaStream_t st,
+                                 const StepPolicy* policy = nullptr) {
     if (v.n == 0) return cudaSuccess;
     const bool live = v.p.live != 0;
-    const bool fast = !live && d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov &&
+    const StepPolicy pol = policy ? *policy : StepPolicy{};
+    const bool fast = !policy && !live && d_delay && d_sleep && d_buffer && d_rebuf && d_reward && d_eov &&
                       v.p.track_history == 0 && v.p.track_acc == 0 && v.p.auto_reset != 0;
     // persistent-style grid: one wave of 3 blocks per SM, each walking an equal run of consecutive tiles (at least
     // kStepTiles, so that small batches still amortise the staging); no tail wave
@@ -1407,15 +1457,19 @@ static cudaError_t launch_step_t(const EnvView& v, const int32_t* d_action, cons
     size_t smem_bytes = (size_t)smem_doubles * sizeof(double) + (size_t)idx_stride(v.T_max) * sizeof(uint16_t);
     if (smem_bytes > kSmemOptInLimit || idx_stride(v.T_max) == 0) { smem_doubles = 0; smem_bytes = 0; }
     cudaError_t e = cudaSuccess;
-#define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr, smem_doubles, tiles_per_block
-#define ABR_LAUNCH_STEP(F, L)                                                                  \
+#define ABR_STEP_ARGS v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency, d_next_sizes, d_eov, d_thr, smem_doubles, tiles_per_block, pol
+#define ABR_LAUNCH_STEP(F, L, P)                                                               \
     do {                                                                                       \
-        e = allow_smem(abr_step_kernel<F, L, OT>, smem_bytes);                                 \
-        if (e == cudaSuccess) abr_step_kernel<F, L, OT><<<grid, kTile, smem_bytes, st>>>(ABR_STEP_ARGS); \
+        e = allow_smem(abr_step_kernel<F, L, P, OT>, smem_bytes);                              \
+        if (e == cudaSuccess) abr_step_kernel<F, L, P, OT><<<grid, kTile, smem_bytes, st>>>(ABR_STEP_ARGS); \
     } while (0)
-    if (live) ABR_LAUNCH_STEP(false, true);
-    else if (fast) ABR_LAUNCH_STEP(true, false);
-    else ABR_LAUNCH_STEP(false, false);
+    if (policy) {
+        if constexpr (std::is_same<OT, double>::value) ABR_LAUNCH_STEP(false, false, true);
+        else return cudaErrorInvalidValue;
+    }
+    else if (live) ABR_LAUNCH_STEP(false, true, false);
+    else if (fast) ABR_LAUNCH_STEP(true, false, false);
+    else ABR_LAUNCH_STEP(false, false, false);
 #undef ABR_LAUNCH_STEP
 #undef ABR_STEP_ARGS
     if (e != cudaSuccess) return e;
@@ -1428,6 +1482,25 @@ cudaError_t launch_step(const EnvView& v, const int32_t* d_action, const double*
                         double* d_next_sizes, uint8_t* d_eov, double* d_thr, cudaStream_t st) {
     return launch_step_t<double>(v, d_action, d_speed, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, d_latency,
                                  d_next_sizes, d_eov, d_thr, st);
+}
+
+__global__ void abr_bump_kernel(uint32_t* counter) { *counter += 1u; }
+
+// SPEC §4.1: the step with the action drawn from the caller's logits and the observation written by the same kernel;
+// the draw counter is advanced behind it (same stream: every thread has read it by then), so that a captured graph
+// replays with a new draw every time.
+cudaError_t launch_step_policy(const EnvView& v, const StepPolicy& pol, double* d_delay, double* d_sleep, double* d_buffer,
+                               double* d_rebuf, double* d_reward, uint8_t* d_eov, uint32_t* d_draw_counter,
+                               cudaStream_t st) {
+    if (v.n == 0) return cudaSuccess;
+    cudaError_t e = launch_step_t<double>(v, nullptr, nullptr, d_delay, d_sleep, d_buffer, d_rebuf, d_reward, nullptr,
+                                          nullptr, d_eov, nullptr, st, &pol);
+    if (e != cudaSuccess) return e;
+    if (pol.draw) {
+        abr_bump_kernel<<<1, 1, 0, st>>>(d_draw_counter);
+        count_launch();
+    }
+    return cudaGetLastError();
 }
 
 // fp32-output mode: same fp64 arithmetic, every floating-point output rounded once to float on the store

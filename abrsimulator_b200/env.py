@@ -136,6 +136,10 @@ def _hptr(a):
     return a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data
 
 
+def _hptr_dev(t):
+    return None if t is None else t.data_ptr()
+
+
 def _out_dtype(t, dtype):
     """float64 or float32: the dtype of a caller-given output tensor, else the requested one."""
     d = dtype if t is None else t.dtype
@@ -323,6 +327,44 @@ class BatchedABREnv:
                 _ptr(out.reward), _ptr(out.latency), _ptr(out.next_sizes), _ptr(out.end_of_video),
                 _ptr(out.throughput), _stream()))
         return out
+
+    # -- SPEC §4.1: policy in the loop (RL harness) --
+    def step_policy(self, logits, sample=True, seed=0, obs=None, action_out=None, reward_sum=None, out=None,
+                    obs_scales=(1.0, 1.0, 1.0, 1.0)):
+        """One chunk step with the action chosen inside the step kernel from the policy's ``logits`` (float32 [N, A] on
+        the device): arg max, or with ``sample`` a draw from softmax(logits) (Gumbel-max, Philox noise keyed by the seed,
+        the global session index and the environment's draw counter, which every sampled call advances and ``reset``
+        zeroes).  The same kernel writes the next observation into ``obs`` (float32 [4 + A, N], feature-major: buffer,
+        throughput, delay — each times its entry of ``obs_scales`` = (buffer, throughput, delay, size) — action / A,
+        and the scaled sizes of the next chunk), the chosen action into ``action_out`` (int32 [N]) and adds the reward
+        into ``reward_sum`` (float64 [N]).  ``out``: an optional StepResult whose delay / sleep / buffer / rebuffer /
+        reward / end_of_video tensors receive the per-step outputs.  All arguments are used in place (graph-capturable);
+        returns ``obs``."""
+        n = self.n
+        if logits.dtype != torch.float32 or logits.device != self.device or not logits.is_contiguous() or \
+                logits.numel() != n * self.A:
+            raise TypeError(f"logits must be a contiguous float32 [N, A] = [{n}, {self.A}] tensor on {self.device}")
+
+        def chk(t, dtype, size, name):
+            if t is not None and (t.dtype != dtype or t.device != self.device or not t.is_contiguous() or t.numel() != size):
+                raise TypeError(f"{name} must be a contiguous {dtype} tensor of {size} elements on {self.device}")
+
+        chk(obs, torch.float32, (4 + self.A) * n, "obs")
+        chk(action_out, torch.int32, n, "action_out")
+        chk(reward_sum, torch.float64, n, "reward_sum")
+        spec = self._obs_spec = _lib.AbrObsSpec(*[float(x) for x in obs_scales])
+        o = out
+        for name in ("delay", "sleep", "buffer", "rebuffer", "reward") if o is not None else ():
+            chk(getattr(o, name), torch.float64, n, name)
+        if o is not None:
+            chk(o.end_of_video, torch.uint8, n, "end_of_video")
+        g = (lambda name: _hptr_dev(getattr(o, name))) if o is not None else (lambda name: None)
+        with self._on:
+            _lib.check(self._lib.abr_env_step_policy(
+                self._h, logits.data_ptr(), int(bool(sample)), int(seed), C.addressof(spec), _hptr_dev(obs),
+                _hptr_dev(action_out), _hptr_dev(reward_sum), g("delay"), g("sleep"), g("buffer"), g("rebuffer"),
+                g("reward"), g("end_of_video"), torch.cuda.current_stream().cuda_stream))
+        return obs
 
     # -- SPEC §3+§4 --
     def rollout(self, policy, steps, seed=0, actions=None, want=("delay", "sleep", "buffer", "rebuffer", "reward",

@@ -269,7 +269,8 @@ def workload_config(args):
     return dict(workload="configs[1]: random-policy chunk-step sweep, fused 48-chunk episodes",
                 sessions_per_gpu=args.sessions, chunks=V, bitrates=A, n_traces=N_TRACES, trace_segments=T_TRACE,
                 policy="random(philox)", sessions_per_trace=GROUP, outputs="delay,sleep,buffer,rebuffer,reward,end_of_video",
-                l2="256 MiB buffer rewritten twice between timed steps (outside the timed region)")
+                l2="256 MiB buffer rewritten twice between timed steps (outside the timed intervals)",
+                timing="one CUDA-event interval per step, all K steps enqueued back to back, one host wait at the end")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -415,27 +416,39 @@ def run_ours(args):
     if rank == 0:
         sampler.mark_load()
     launches0 = _lib.launch_count()
-    step_ms, kern_ms = [], []
+    # The K timed steps are enqueued back to back — each behind two rewrites of the 256 MiB flush buffer (outside its
+    # timed interval) — and the host waits once, at the end: it runs ahead of the GPU (a step takes the host ~60 us to
+    # enqueue and the GPU ~200 us to execute with its flushes; a few flushes in front give it the head start), so every
+    # interval between a step's two events is device time of that step and nothing else, also with eight ranks sharing
+    # the host's cores.  Waiting for every step instead puts the host's launch path inside the interval as soon as
+    # enqueueing the step takes longer than its flush.
+    events = []
     barrier()
     wall0 = time.perf_counter()
+    for _ in range(4):
+        flush.fill_(3)
     for _ in range(args.steps):
-        flush.fill_(1)                                         # evict L2 (outside the timed region) ...
-        flush.fill_(2)                                         # ... twice: ~140 us of GPU work in front of the timed region, so that
-        #                                                        the step is fully enqueued when the GPU reaches it even with eight
-        #                                                        ranks sharing the host (one pass, 70 us, is about what the host needs)
+        flush.fill_(1)                                         # evict L2 (outside the timed interval)
+        flush.fill_(2)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         stats = one_step((k0, k1))
         e1.record(stream)
-        e1.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
-        kern_ms.append(k0.elapsed_time(k1))
+        events.append((e0, e1, k0, k1))
     barrier()
     wall = time.perf_counter() - wall0
+    step_ms = [e0.elapsed_time(e1) for e0, e1, _, _ in events]
+    kern_ms = [k0.elapsed_time(k1) for _, _, k0, k1 in events]
     launches = _lib.launch_count() - launches0
     total_ms = max_over_ranks(sum(step_ms), dev)
     kern_avg_ms = sum(kern_ms) / len(kern_ms)
+    per_rank = None
+    if world > 1:                                              # who is the slowest rank, and by how much
+        mine = torch.tensor([sum(step_ms) / len(step_ms), kern_avg_ms], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = dict(ms_per_step=[float(t[0]) for t in allr], kernel_ms=[float(t[1]) for t in allr])
     tot_stats = allreduce_stats(stats)                          # the one collective: final QoE statistics
     torch.cuda.synchronize()
     chunk_steps = world * N * V * args.steps
@@ -640,6 +653,8 @@ def run_ours(args):
                                             kernel_ms=step_form["ms_per_launch"])
     if rl:
         line["rl_harness"] = rl
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     if world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)
         line["cpu_baseline"] = cpu_baseline(args)
@@ -776,24 +791,32 @@ def bench_rl_harness(args, dev, rank, world, barrier, max_over_ranks):
     policy = Policy(4 + A, A).to(dev)
     stream = torch.cuda.current_stream()
     env.reset(tid, off, session_base=rank * M)
-    runner = GraphedEpisode(env, policy)
-    runner.run(1)                                   # capture outside the timed episodes
-    ms = []
-    for ep in range(3):
+    res = {}
+    for name, fused in (("fused", True), ("torch_glue", False)):
         env.reset(tid, off, session_base=rank * M)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        total = runner.run(V)
-        e1.record(stream)
-        e1.synchronize()
-        ms.append(max_over_ranks(e0.elapsed_time(e1), dev))
-    best = min(ms[1:])
-    return dict(sessions_per_gpu=M, chunks=V, ms_per_episode=best, env_steps_per_s=world * M * V / (best * 1e-3),
-                mean_episode_reward=float(total.mean().item()),
-                note="policy forward + Gumbel-max sampling (torch) + abr_env_step with throughput and next_sizes "
-                     "outputs + observation update; one chunk captured into a CUDA graph and replayed; state never "
-                     "leaves the device")
+        runner = GraphedEpisode(env, policy, fused=fused)
+        runner.run(1)                                   # capture outside the timed episodes
+        ms = []
+        for ep in range(3):
+            env.reset(tid, off, session_base=rank * M)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            total = runner.run(V)
+            e1.record(stream)
+            e1.synchronize()
+            ms.append(max_over_ranks(e0.elapsed_time(e1), dev))
+        best = min(ms[1:])
+        res[name] = dict(ms_per_episode=best, env_steps_per_s=world * M * V / (best * 1e-3),
+                         mean_episode_reward=float(total.mean().item()))
+        del runner
+    return dict(sessions_per_gpu=M, chunks=V, ms_per_episode=res["fused"]["ms_per_episode"],
+                env_steps_per_s=res["fused"]["env_steps_per_s"], mean_episode_reward=res["fused"]["mean_episode_reward"],
+                torch_glue=res["torch_glue"],
+                note="policy forward (torch MLP, tf32) + abr_env_step_policy: Gumbel-max sampling, step, reward sum and the "
+                     "fp32 feature-major observation in one library launch per chunk; one chunk captured into a CUDA graph "
+                     "and replayed; state never leaves the device.  torch_glue: the same episode with the sampling and the "
+                     "observation in eager PyTorch around abr_env_step (twelve more kernels per chunk)")
 
 
 def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):

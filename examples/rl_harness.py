@@ -4,9 +4,12 @@ state tensor kept on the device.
 
     python examples/rl_harness.py --sessions 524288 --chunks 48
 
-The observation is built on the device from the step outputs (buffer, last throughput, last delay, next-chunk
-sizes, last action); the policy is a small MLP; the action goes straight back into `env.step`.  No host
-round trip happens inside the episode loop.
+The policy is a small MLP; its logits go straight into `env.step_policy` (abr_env_step_policy, SPEC §4.1): the step
+kernel draws the action (Gumbel-max over Philox noise), steps the session, adds up the reward and writes the next
+observation (buffer, last throughput, last delay, last action, next-chunk sizes) as the feature-major fp32 matrix the
+first Linear reads — one library launch per chunk besides the policy's own kernels.  `--torch-glue` keeps the
+sampling and the observation in eager PyTorch around `env.step` (twelve more kernels per chunk) for comparison.
+No host round trip happens inside the episode loop.
 """
 from __future__ import annotations
 
@@ -42,21 +45,28 @@ def _step_outputs(env):
                       torch.empty(n, dtype=torch.float64, device=dev), None)
 
 
-def _one_chunk(env, policy, obs, action, total, out, sample):
+OBS_SCALES = (0.1, 1.0, 0.1, 1.0)      # buffer / 10, throughput, delay / 10, sizes
+
+
+def _one_chunk(env, policy, obs, action, total, out, sample, fused=True):
     """policy(obs) -> action -> env.step -> next observation, all on the device and all in place (so that the
     sequence can be captured into a CUDA graph once and replayed for every chunk).  ``obs`` is feature-major
-    [4 + A, N]: every feature row is written with one coalesced kernel and the first Linear reads it transposed."""
+    [4 + A, N]: every feature row is written coalesced and the first Linear reads it transposed."""
     A = env.A
     logits = policy(obs.t())
+    if fused:       # sampling, step, reward sum and observation in the step kernel
+        env.step_policy(logits, sample=sample, seed=0x5EED, obs=obs, action_out=action, reward_sum=total,
+                        obs_scales=OBS_SCALES)
+        return
     if sample:      # Gumbel-max: argmax(logits + G) is a draw from softmax(logits); three elementwise kernels
         u = torch.rand_like(logits).clamp_(1e-12, 1.0)
         logits = logits - torch.log(-torch.log(u))
     action.copy_(logits.argmax(dim=1))
     r = env.step(action, out=out, want_throughput=True)
     total += r.reward
-    obs[0] = r.buffer / 10.0
+    obs[0] = r.buffer * 0.1
     obs[1] = r.throughput
-    obs[2] = r.delay / 10.0
+    obs[2] = r.delay * 0.1
     obs[3] = action / float(A)
     obs[4:] = r.next_sizes.t()
 
@@ -71,8 +81,8 @@ class GraphedEpisode:
     """One chunk (policy kernels + abr_env_step + observation update) captured into a CUDA graph once; an episode is
     `chunks` replays.  Buffers are persistent, so the capture is reused across episodes (call after ``env.reset``)."""
 
-    def __init__(self, env, policy, sample=True):
-        self.env, self.policy, self.sample = env, policy, sample
+    def __init__(self, env, policy, sample=True, fused=True):
+        self.env, self.policy, self.sample, self.fused = env, policy, sample, fused
         n, dev = env.n, env.device
         self.out = _step_outputs(env)
         self.obs = _first_observation(env)
@@ -87,13 +97,13 @@ class GraphedEpisode:
         side = torch.cuda.Stream(device=env.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            _one_chunk(env, self.policy, self.obs, self.action, self.total, self.out, self.sample)
+            _one_chunk(env, self.policy, self.obs, self.action, self.total, self.out, self.sample, self.fused)
         torch.cuda.current_stream().wait_stream(side)
         for f, t in snap.items():
             env.state(f).copy_(t)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            _one_chunk(env, self.policy, self.obs, self.action, self.total, self.out, self.sample)
+            _one_chunk(env, self.policy, self.obs, self.action, self.total, self.out, self.sample, self.fused)
 
     def run(self, chunks):
         with torch.no_grad():
@@ -106,11 +116,11 @@ class GraphedEpisode:
         return self.total
 
 
-def run_episode(env, policy, chunks, sample=True, out=None, use_graph=False):
+def run_episode(env, policy, chunks, sample=True, out=None, use_graph=False, fused=True):
     """One episode of `chunks` steps for all sessions; returns the sum of rewards [N] (``use_graph``: through a
     freshly captured ``GraphedEpisode``; keep one around to reuse the capture across episodes)."""
     if use_graph:
-        return GraphedEpisode(env, policy, sample).run(chunks)
+        return GraphedEpisode(env, policy, sample, fused).run(chunks)
     n, dev = env.n, env.device
     out = out or _step_outputs(env)
     obs = _first_observation(env)
@@ -118,7 +128,7 @@ def run_episode(env, policy, chunks, sample=True, out=None, use_graph=False):
     action = torch.full((n,), 1, dtype=torch.int32, device=dev)
     with torch.no_grad():
         for _ in range(chunks):
-            _one_chunk(env, policy, obs, action, total, out, sample)
+            _one_chunk(env, policy, obs, action, total, out, sample, fused)
     return total
 
 
@@ -128,6 +138,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=48)
     ap.add_argument("--episodes", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of every chunk separately")
+    ap.add_argument("--torch-glue", action="store_true", help="sampling and observation in eager PyTorch around env.step")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
@@ -142,12 +153,12 @@ def main():
     for ep in range(args.episodes):
         env.reset(tid, off)
         if runner is None and not args.no_graph:
-            runner = GraphedEpisode(env, policy)      # buffers are sized by the reset; captured on first use
+            runner = GraphedEpisode(env, policy, fused=not args.torch_glue)      # buffers are sized by the reset; captured on first use
             runner.run(1)
             env.reset(tid, off)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        total = runner.run(args.chunks) if runner else run_episode(env, policy, args.chunks)
+        total = runner.run(args.chunks) if runner else run_episode(env, policy, args.chunks, fused=not args.torch_glue)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         print(f"episode {ep}: {args.sessions * args.chunks / dt:.3e} env steps/s "

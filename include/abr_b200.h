@@ -122,6 +122,19 @@ int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_s
 int abr_env_step(AbrEnv* env, const int32_t* d_action, double* d_delay, double* d_sleep, double* d_buffer,
                  double* d_rebuf, double* d_reward, double* d_next_sizes /*[N][A]*/, uint8_t* d_end_of_video,
                  double* d_throughput, void* stream);
+/* SPEC §4.1 — policy-in-the-loop step for RL harnesses (BASELINE.json configs[4]; the reference's controller protocol
+ * get_next_bitrate(...), Simulator.py:155, answered by a batched policy network): d_logits[N][A] are the policy's
+ * scores for every session; the step kernel itself picks the action — arg max (sample = 0), or a draw from
+ * softmax(logits) by Gumbel-max with Philox noise keyed by (seed, global session index, draw counter) (sample = 1; the
+ * environment's draw counter is advanced by every sampled call and zeroed by abr_env_reset) — steps the session, adds
+ * the reward into d_reward_sum[N] and writes the next observation d_obs[4 + A][N] (fp32, feature-major):
+ *   row 0 buffer * buffer_scale, row 1 throughput of the download (size / delay) * throughput_scale,
+ *   row 2 delay * delay_scale, row 3 action / A, rows 4.. sizes of the next chunk * size_scale.
+ * Everything but d_logits is nullable.  Not available in live mode. */
+typedef struct AbrObsSpec { double buffer_scale, throughput_scale, delay_scale, size_scale; } AbrObsSpec;
+int abr_env_step_policy(AbrEnv* env, const float* d_logits, int sample, uint64_t seed, const AbrObsSpec* spec,
+                        float* d_obs, int32_t* d_action_out, double* d_reward_sum, double* d_delay, double* d_sleep,
+                        double* d_buffer, double* d_rebuf, double* d_reward, uint8_t* d_end_of_video, void* stream);
 /* SPEC §7 (live = 1): like abr_env_step with the playback speeds as a second action and the latency output; d_sleep
  * receives the idle time before the download.  d_speed is a [V][N] table (nullable = 1.0): d_speed[k][s] is the speed
  * at which session s plays content chunk k — the reference asks its speed controller once per PLAYED chunk

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 from abrsimulator_b200 import synth
-from abrsimulator_b200.env import BatchedABREnv
+from abrsimulator_b200.env import BatchedABREnv, StepResult
 from abrsimulator_b200.datamodel import Chunk, NetworkInfo, QOEMetric
 from abrsimulator_b200.simulator import Simulator, BufferBasedPolicy, RandomPolicy
 from abrsimulator_b200.mpc import MPCBitrateController
@@ -1119,3 +1119,109 @@ def test_trace_sorted_order_is_bit_identical_to_the_callers_order():
         env_b.reset(tid[:100], off[:100])
     env_b.set_order(None)
     env_b.reset(tid[:100], off[:100])
+
+
+# ---- SPEC §4.1: policy-in-the-loop step (abr_env_step_policy) ----
+def _philox4x32_10(c, k):
+    """Philox4x32-10 on uint32 numpy arrays: counter words c[0..3], key words k[0..1] (SPEC §4)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [np.asarray(x, np.uint64) for x in c]
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = c[0] * np.uint64(M0), c[2] * np.uint64(M1)
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & mask, p1 & mask, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & mask, p0 & mask]
+        k0, k1 = (k0 + np.uint64(W0)) & mask, (k1 + np.uint64(W1)) & mask
+    return c
+
+
+def _perturbed_logits(logits, seed, draw, session_base=0):
+    """logits[a] - ln(-ln(u_a)) of SPEC §4.1 in float32 (numpy's logf; the device's differs in the last bits)."""
+    N, A = logits.shape
+    g = np.arange(N, dtype=np.uint64) + np.uint64(session_base)
+    out = np.empty((N, A), np.float32)
+    for b in range((A + 3) // 4):
+        w = _philox4x32_10([g & np.uint64(0xFFFFFFFF), g >> np.uint64(32), np.full(N, draw, np.uint64), np.full(N, b, np.uint64)],
+                           [seed & 0xFFFFFFFF, seed >> 32])
+        for k in range(4):
+            a = 4 * b + k
+            if a < A:
+                u = ((w[k] >> np.uint64(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
+                out[:, a] = logits[:, a] - np.log(-np.log(u)).astype(np.float32)
+    return out
+
+
+def test_step_policy_greedy_equals_step_with_argmax_and_writes_the_observation():
+    N = 3000
+    env_a, _ = make_pair(N, dict(track_history=0))
+    env_b, _ = make_pair(N, dict(track_history=0))
+    A = env_a.A
+    rng = np.random.default_rng(5)
+    scales = (0.1, 1e-3, 0.25, 1e-6)
+    obs = torch.zeros(4 + A, N, dtype=torch.float32, device="cuda")
+    act = torch.zeros(N, dtype=torch.int32, device="cuda")
+    total = torch.zeros(N, dtype=torch.float64, device="cuda")
+    total_b = np.zeros(N)
+    for t in range(60):                          # crosses an end of video
+        lg = rng.normal(size=(N, A)).astype(np.float32)
+        lg[::7, 2] = lg[::7, 4] = lg[::7].max(axis=1)        # exact ties: the first arg max wins
+        lg[5] = np.nan                                         # all NaN: action 0
+        logits = torch.from_numpy(lg).cuda()
+        res = StepResult(*[torch.empty(N, dtype=torch.float64, device="cuda") for _ in range(5)], None,
+                         torch.empty(N, dtype=torch.uint8, device="cuda"), None)
+        env_a.step_policy(logits, sample=False, obs=obs, action_out=act, reward_sum=total, out=res, obs_scales=scales)
+        exp_act = np.where(np.isnan(lg).all(axis=1), 0, np.nanargmax(np.where(np.isnan(lg), -np.inf, lg), axis=1)).astype(np.int32)
+        assert np.array_equal(act.cpu().numpy(), exp_act)
+        ref = env_b.step(exp_act, want_throughput=True)
+        for name in ("delay", "sleep", "buffer", "rebuffer", "reward"):
+            assert torch.equal(getattr(res, name), getattr(ref, name)), (t, name)
+        assert torch.equal(res.end_of_video, ref.end_of_video)
+        for f in STATE_I + STATE_F:
+            assert torch.equal(env_a.state(f)[:N], env_b.state(f)[:N]), f
+        total_b += ref.reward.cpu().numpy()
+        o = obs.cpu().numpy()
+        f32 = lambda x: np.asarray(x, np.float64).astype(np.float32)
+        assert np.array_equal(o[0], f32(ref.buffer.cpu().numpy() * scales[0]))
+        assert np.array_equal(o[1], f32(ref.throughput.cpu().numpy() * scales[1]))
+        assert np.array_equal(o[2], f32(ref.delay.cpu().numpy() * scales[2]))
+        assert np.array_equal(o[3], f32(exp_act.astype(np.float64) / A))
+        assert np.array_equal(o[4:], f32(ref.next_sizes.cpu().numpy().T * scales[3]))
+    assert bits_equal(total.cpu().numpy(), total_b) == 0
+
+
+def test_step_policy_sampling_is_gumbel_max_over_philox_noise():
+    N = 8192
+    env, _ = make_pair(N, dict(track_history=0))
+    A = env.A
+    rng = np.random.default_rng(9)
+    lg = rng.normal(scale=2.0, size=(N, A)).astype(np.float32)
+    logits = torch.from_numpy(lg).cuda()
+    act = torch.zeros(N, dtype=torch.int32, device="cuda")
+    seed = 0x1234_5678_9ABC
+    draws = []
+    for draw in range(3):                        # the draw counter advances with every sampled call
+        env.step_policy(logits, sample=True, seed=seed, action_out=act)
+        a = act.cpu().numpy()
+        draws.append(a.copy())
+        z = _perturbed_logits(lg, seed, draw)
+        # the device's logf may differ from numpy's in the last bits: the drawn action is an arg max up to that
+        assert np.all(z[np.arange(N), a] >= z.max(axis=1) - 1e-5), draw
+        assert np.mean(a == z.argmax(axis=1)) > 0.999
+    assert not np.array_equal(draws[0], draws[1]) and not np.array_equal(draws[1], draws[2])
+    # reset zeroes the counter: the same seed replays the same draws
+    tid = env.state("trace_id")[:N].clone()
+    env.reset(tid, None)
+    env.step_policy(logits, sample=True, seed=seed, action_out=act)
+    assert np.array_equal(act.cpu().numpy(), draws[0])
+    # the draws follow softmax(logits): chi-square over sessions sharing one row of logits
+    row = np.array([0.5, -1.0, 2.0, 0.0, 1.0, -0.5], np.float32)[:A]
+    logits = torch.from_numpy(np.repeat(row[None, :], N, 0).copy()).cuda()
+    counts = np.zeros(A)
+    for _ in range(8):
+        env.step_policy(logits, sample=True, seed=77, action_out=act)
+        counts += np.bincount(act.cpu().numpy(), minlength=A)
+    p = np.exp(row - row.max()); p /= p.sum()
+    chi2 = ((counts - counts.sum() * p) ** 2 / (counts.sum() * p)).sum()
+    assert chi2 < 30.0, (chi2, counts, p)        # 5 degrees of freedom: P(chi2 > 30) ~ 1e-5
+    with pytest.raises(TypeError):
+        env.step_policy(logits.double())

@@ -37,9 +37,9 @@ def test_rl_harness_episode_matches_manual_stepping():
             r = env.step(a, want_throughput=True)
             e = ref.step(a.cpu().numpy())
             tot_ref = tot_ref + e["reward"]
-            obs[0] = r.buffer / 10.0
+            obs[0] = r.buffer * 0.1
             obs[1] = r.throughput
-            obs[2] = r.delay / 10.0
+            obs[2] = r.delay * 0.1
             obs[3] = a / float(env.A)
             obs[4:] = r.next_sizes.t()
     np.testing.assert_allclose(total.cpu().numpy(), tot_ref, rtol=1e-9, atol=1e-9)
@@ -72,6 +72,32 @@ def test_rl_harness_cuda_graph_replay_equals_eager():
     env.reset(tid, off)
     sampled = run_episode(env, policy, V, sample=True, use_graph=True)
     assert bool(torch.isfinite(sampled).all()) and env.error_count() == 0
+
+
+def test_rl_harness_fused_step_policy_equals_torch_glue():
+    """abr_env_step_policy (sampling / arg max, step, reward sum and observation in the step kernel) gives the same
+    greedy episode, bit for bit, as env.step with the arg max and the observation built by eager PyTorch."""
+    import numpy as np
+    from abrsimulator_b200 import synth
+    from abrsimulator_b200.env import BatchedABREnv
+    from examples.rl_harness import Policy, run_episode
+
+    N, V = 4096, 30
+    bitrates, sizes = synth.make_video(20)                 # the episode crosses an end of video
+    bw, tl, ti = synth.make_traces(16, 128)
+    tid, off = synth.make_sessions(N, 16, 128, group=256)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    torch.manual_seed(0)
+    policy = Policy(4 + env.A, env.A).cuda()
+    env.reset(tid, off)
+    glue = run_episode(env, policy, V, sample=False, fused=False).cpu().numpy()
+    state = {f: env.state(f).cpu().numpy().copy() for f in ("seg", "chunk", "last_q", "phase", "pos", "buffer")}
+    env.reset(tid, off)
+    fused = run_episode(env, policy, V, sample=False, fused=True).cpu().numpy()
+    assert np.array_equal(glue, fused)
+    for f, want in state.items():
+        assert np.array_equal(env.state(f).cpu().numpy(), want), f
+    assert env.error_count() == 0
 
 
 def test_mpc_dropin_example_prints_the_reference_answer(capsys):
