@@ -22,7 +22,7 @@ FIELDS = dict(seg=(0, "int32"), chunk=(1, "int32"), last_q=(2, "int32"), trace_i
               buffer=(11, "float64"), bw_hist=(12, "float64"), last_pred=(13, "float64"),
               err_ring=(14, "float64"), acc=(15, "float64"), t_now=(16, "float64"), play_time=(17, "float64"),
               started=(7, "uint8"), play_id=(8, "int32"), play_len=(19, "float64"), sizes=(20, "float64"), utility=(21, "float64"),
-              trace_bw=(22, "float64"))
+              trace_bw=(22, "float64"), order=(23, "int32"))
 
 
 class AbrError(RuntimeError):
@@ -46,7 +46,7 @@ class AbrObsSpec(C.Structure):
 
 # every symbol include/abr_b200.h declares (tests check that the .so exports all of them)
 SYMBOLS = ("abr_version", "abr_last_error", "abr_launch_count", "abr_device_info", "abr_params_default",
-           "abr_env_create", "abr_env_destroy", "abr_env_num_sessions", "abr_sort_by_trace", "abr_env_set_order", "abr_env_reset", "abr_env_reset_host",
+           "abr_env_create", "abr_env_destroy", "abr_env_num_sessions", "abr_sort_by_trace", "abr_env_set_order", "abr_env_reset", "abr_env_reset_sorted", "abr_env_get_order", "abr_env_reset_host",
            "abr_env_step", "abr_env_step_live", "abr_env_step_f32", "abr_env_step_policy", "abr_env_qoe_cost", "abr_env_rollout_fused",
            "abr_env_rollout_fused_live", "abr_env_rollout_fused_f32", "abr_env_run", "abr_env_mpc_decide", "abr_stats_partial",
            "abr_env_state_ptr",

@@ -47,6 +47,8 @@ struct AbrEnv {
     uint32_t step_base = 0;   // fused-episode steps since the last reset: offsets the random policy's counter (SPEC §4)
     int32_t* d_perm = nullptr;   // session order installed by abr_env_set_order (capacity entries), v.perm points here when set
     int n_order = 0;
+    int32_t* d_sort_hist = nullptr;   // (trace, run) cells of abr_env_reset_sorted's counting sort, grow-only
+    size_t sort_hist_cap = 0, sort_scan_bytes = 0;
     int fresh_partials = 0;   // > 0: d_stats_partials holds that many block sums of the current accumulators
     double* d_stats_out = nullptr;
     uint32_t* d_draw_counter = nullptr;       // draws of abr_env_step_policy since the last reset
@@ -63,6 +65,7 @@ struct AbrEnv {
         for (void* p : allocs) cudaFree(p);
         if (d_actions) cudaFree(d_actions);
         if (d_reward_traj) cudaFree(d_reward_traj);
+        if (d_sort_hist) cudaFree(d_sort_hist);
     }
     template <typename T>
     cudaError_t alloc(T** out, size_t count) {
@@ -311,9 +314,52 @@ int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_
     env->fresh_partials = 0;
     env->was_reset = true;
     env->step_base = 0;
-    CUDA_TRY(cudaMemsetAsync(env->d_draw_counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
-    CUDA_TRY(launch_reset(env->v, d_trace_id, d_start_offset, (cudaStream_t)stream));
+    CUDA_TRY(launch_reset(env->v, d_trace_id, d_start_offset, env->d_draw_counter, (cudaStream_t)stream));
     return ABR_OK;
+}
+
+int abr_env_get_order(AbrEnv* env, int32_t* d_perm, int n_sessions, void* stream) {
+    if (!env || !d_perm) return fail(ABR_ERR_INVALID, "env or perm is NULL");
+    if (!env->v.perm) return fail(ABR_ERR_STATE, "no session order is installed");
+    if (n_sessions != env->n_order) return fail(ABR_ERR_RANGE, "the installed order has %d entries, not %d", env->n_order, n_sessions);
+    CUDA_TRY(cudaMemcpyAsync(d_perm, env->d_perm, sizeof(int32_t) * n_sessions, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return ABR_OK;
+}
+
+int abr_env_reset_sorted(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_offset, int n_sessions,
+                         long long session_base, void* stream) {
+    if (!env || (!d_trace_id && n_sessions > 0)) return fail(ABR_ERR_INVALID, "env or trace_id is NULL");
+    if (n_sessions < 0 || n_sessions > env->v.cap) return fail(ABR_ERR_RANGE, "n_sessions %d exceeds capacity %d", n_sessions, env->v.cap);
+    if (d_trace_id == env->d_trace_id || (d_start_offset && d_start_offset == env->d_offset))
+        return fail(ABR_ERR_INVALID, "the inputs alias the environment's own scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!env->d_perm) CUDA_TRY(env->alloc(&env->d_perm, (size_t)env->v.cap));
+    if (n_sessions > 0) {
+        int S = 0, n_blocks = 0;
+        sort_shape(n_sessions, env->v.n_traces, &S, &n_blocks);
+        if (n_blocks > 0) {
+            const size_t cells = (((size_t)env->v.n_traces * n_blocks) + 63) & ~(size_t)63;
+            const size_t scan_bytes = sort_scan_tmp_bytes((int)cells);
+            if (cells > env->sort_hist_cap) {
+                if (env->d_sort_hist) { cudaDeviceSynchronize(); cudaFree(env->d_sort_hist); env->d_sort_hist = nullptr; env->sort_hist_cap = 0; }
+                CUDA_TRY(cudaMalloc(&env->d_sort_hist, sizeof(int32_t) * cells + scan_bytes));
+                CUDA_TRY(cudaMemset(env->d_sort_hist, 0, sizeof(int32_t) * cells));   // the sort leaves it zero
+                env->sort_hist_cap = cells;
+                env->sort_scan_bytes = scan_bytes;
+            }
+            // the scan's scratch sits behind the capacity's cells (its size grows with the cell count)
+            CUDA_TRY(launch_sort_gather(d_trace_id, d_start_offset, n_sessions, env->v.n_traces, S, n_blocks, env->d_sort_hist,
+                                        env->d_sort_hist + env->sort_hist_cap, env->sort_scan_bytes,
+                                        env->d_perm, env->d_trace_id, env->d_offset, st));
+        } else {   // shapes the counting sort does not take: CUB's radix sort, then one gather
+            int rc = abr_sort_by_trace(d_trace_id, n_sessions, env->v.n_traces, env->d_perm, stream);
+            if (rc) return rc;
+            CUDA_TRY(launch_gather(d_trace_id, d_start_offset, env->d_perm, n_sessions, env->d_trace_id, env->d_offset, st));
+        }
+    }
+    env->v.perm = env->d_perm;
+    env->n_order = n_sessions;
+    return abr_env_reset(env, env->d_trace_id, env->d_offset, n_sessions, session_base, stream);
 }
 
 int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_start_offset, int n_sessions,
@@ -516,6 +562,9 @@ int abr_env_state_ptr(AbrEnv* env, int field, void** d_ptr) {
         case ABR_F_SIZES: *d_ptr = (void*)v.sizes; break;
         case ABR_F_UTILITY: *d_ptr = (void*)v.util; break;
         case ABR_F_TRACE_BW: *d_ptr = (void*)v.trace_bw; break;
+        case ABR_F_ORDER:
+            if (!v.perm) return fail(ABR_ERR_STATE, "no session order is installed");
+            *d_ptr = (void*)v.perm; break;
         default: return fail(ABR_ERR_INVALID, "unknown state field %d", field);
     }
     return ABR_OK;

@@ -127,7 +127,8 @@ struct EnvView {
 // launchers implemented in abr_step.cu / abr_mpc.cu (C++ linkage, internal)
 cudaError_t launch_trace_table(const EnvView& v, double* d_cum, uint16_t* d_idx, int32_t* d_ok, TraceMeta* d_meta,
                                cudaStream_t st);
-cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st);
+cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset,
+                         uint32_t* d_draw_counter, cudaStream_t st);
 // Policy-in-the-loop step (abr_env_step_policy, SPEC §4.1): the action is drawn inside the step kernel from the
 // caller's logits and the next observation is written by the same kernel.
 struct StepPolicy {
@@ -173,6 +174,13 @@ cudaError_t launch_stats(const EnvView& v, double* d_partials, int n_partials, b
                          cudaStream_t st);
 int stats_num_partials(int n);
 int stats_num_groups(int n_partials);
+void sort_shape(int n, int n_traces, int* S, int* n_blocks);
+cudaError_t launch_gather(const int32_t* d_trace_id, const double* d_off, const int32_t* d_perm, int n,
+                          int32_t* d_tid_sorted, double* d_off_sorted, cudaStream_t st);
+cudaError_t launch_sort_gather(const int32_t* d_trace_id, const double* d_off, int n, int n_traces, int S, int n_blocks,
+                               int32_t* d_hist, void* d_scan_tmp, size_t scan_tmp_bytes, int32_t* d_perm,
+                               int32_t* d_tid_sorted, double* d_off_sorted, cudaStream_t st);
+size_t sort_scan_tmp_bytes(int total);
 cudaError_t launch_sort_by_trace(const int32_t* d_trace_id, int n, int n_traces, int32_t* d_perm, void* d_tmp,
                                  size_t* tmp_bytes, cudaStream_t st);
 cudaError_t launch_qoe_cost(const EnvView& v, double* d_out, cudaStream_t st);

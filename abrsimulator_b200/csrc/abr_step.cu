@@ -605,9 +605,11 @@ __device__ __forceinline__ RawState reset_position(const EnvView& v, int tr, con
 }
 
 __global__ void __launch_bounds__(kStepBlock)
-abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* __restrict__ start_offset) {
+abr_reset_kernel(EnvView v, const int32_t* __restrict__ trace_id, const double* __restrict__ start_offset,
+                 uint32_t* __restrict__ draw_counter) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.n) return;
+    if (i == 0 && draw_counter) *draw_counter = 0u;   // SPEC §4.1: the draws of abr_env_step_policy count from the reset
     int n_bad = 0;
     const RawState w = reset_position(v, trace_id[i], start_offset ? start_offset[i] : 0.0, n_bad);
     if (n_bad) atomicAdd(v.errors, (unsigned long long)n_bad);
@@ -1413,9 +1415,10 @@ cudaError_t launch_trace_table(const EnvView& v, double* d_cum, uint16_t* d_idx,
     return cudaGetLastError();
 }
 
-cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset, cudaStream_t st) {
+cudaError_t launch_reset(const EnvView& v, const int32_t* d_trace_id, const double* d_start_offset,
+                         uint32_t* d_draw_counter, cudaStream_t st) {
     if (v.n == 0) return cudaSuccess;
-    abr_reset_kernel<<<(v.n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_trace_id, d_start_offset);
+    abr_reset_kernel<<<(v.n + kStepBlock - 1) / kStepBlock, kStepBlock, 0, st>>>(v, d_trace_id, d_start_offset, d_draw_counter);
     count_launch();
     return cudaGetLastError();
 }

@@ -283,10 +283,14 @@ class BatchedABREnv:
         n = tid.numel()
         if off is not None and off.numel() != n:
             raise ValueError("start_offset must have one entry per session")
-        if sort_by_trace:
-            self.set_order(self.sort_by_trace(tid))
-            tid = self.to_env_order(tid).contiguous()
-            off = None if off is None else self.to_env_order(off).contiguous()
+        if sort_by_trace:      # one call: counting sort by trace + gather of the inputs + reset (abr_env_reset_sorted)
+            with self._on:
+                _lib.check(self._lib.abr_env_reset_sorted(self._h, _ptr(tid), _ptr(off), C.c_int(n),
+                                                          C.c_longlong(session_base), _stream()))
+            self.n = n
+            self.session_base = int(session_base)
+            self.perm, self._inv_perm = self.state("order"), None    # a view of the environment's own copy
+            return
         with self._on:
             _lib.check(self._lib.abr_env_reset(self._h, _ptr(tid), _ptr(off), C.c_int(n), C.c_longlong(session_base),
                                                _stream()))

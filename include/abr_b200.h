@@ -53,7 +53,8 @@ enum { ABR_ACC_REWARD = 0, ABR_ACC_REBUF = 1, ABR_ACC_UTILITY = 2, ABR_ACC_SMOOT
 enum { ABR_F_SEG = 0, ABR_F_CHUNK = 1, ABR_F_LAST_Q = 2, ABR_F_TRACE_ID = 3, ABR_F_HIST_LEN = 4, ABR_F_DONE = 5,
        ABR_F_ERR_LEN = 6, ABR_F_PHASE = 10, ABR_F_POS = 18, ABR_F_BUFFER = 11, ABR_F_BW_HIST = 12, ABR_F_LAST_PRED = 13,
        ABR_F_ERR_RING = 14, ABR_F_ACC = 15, ABR_F_T_NOW = 16, ABR_F_PLAY_TIME = 17, ABR_F_STARTED = 7,
-       ABR_F_PLAY_ID = 8, ABR_F_PLAY_LEN = 19, ABR_F_SIZES = 20, ABR_F_UTILITY = 21, ABR_F_TRACE_BW = 22 };
+       ABR_F_PLAY_ID = 8, ABR_F_PLAY_LEN = 19, ABR_F_SIZES = 20, ABR_F_UTILITY = 21, ABR_F_TRACE_BW = 22,
+       ABR_F_ORDER = 23 /* the installed session order, int32 [N] (abr_env_set_order / abr_env_reset_sorted) */ };
 
 /* Replaces the attribute bags MPD / QOEMetric (Simulator.py:11-24, mpc_test.py:18-29) plus the
  * north-star constants (SPEC §1). */
@@ -116,6 +117,13 @@ int abr_env_set_order(AbrEnv* env, const int32_t* d_perm /*nullable*/, int n_ses
 /* SPEC §2.  session_base = global index of local session 0 (sharded runs; keys the random policy). */
 int abr_env_reset(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_offset /*nullable*/, int n_sessions,
                   long long session_base, void* stream);
+/* abr_sort_by_trace + abr_env_set_order + abr_env_reset in one call, for sessions given in the CALLER's order: a
+ * counting sort by trace (stable: the same order as abr_sort_by_trace) that gathers the trace ids and start offsets
+ * into that order on the way, then the reset.  The order is readable afterwards with abr_env_get_order. */
+int abr_env_reset_sorted(AbrEnv* env, const int32_t* d_trace_id, const double* d_start_offset /*nullable*/,
+                         int n_sessions, long long session_base, void* stream);
+/* Copies the installed order (n_sessions entries) to d_perm; ABR_ERR_STATE without one. */
+int abr_env_get_order(AbrEnv* env, int32_t* d_perm, int n_sessions, void* stream);
 int abr_env_reset_host(AbrEnv* env, const int32_t* h_trace_id, const double* h_start_offset /*nullable*/,
                        int n_sessions, long long session_base, void* stream);
 /* SPEC §3: one chunk step for every session.  Output pointers are nullable. */

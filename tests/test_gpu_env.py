@@ -1121,6 +1121,29 @@ def test_trace_sorted_order_is_bit_identical_to_the_callers_order():
     env_b.reset(tid[:100], off[:100])
 
 
+@pytest.mark.parametrize("N,n_traces,T", [(70001, 1024, 8), (5000, 13000, 4), (1, 3, 16), (33, 1, 16)])
+def test_reset_sorted_is_the_stable_sort_by_trace(N, n_traces, T):
+    """abr_env_reset_sorted (counting sort by trace + gather + reset in one call; CUB's radix sort for the shapes the
+    counting sort does not take: here more than 12 288 traces) installs the order abr_sort_by_trace computes — the
+    stable sort — and resets every session exactly like abr_env_reset on the reordered inputs."""
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=n_traces, T=T)
+    rng = np.random.default_rng(N)
+    tid = rng.integers(0, n_traces, size=N).astype(np.int32)
+    off = rng.uniform(0, 3.0 * T, size=N)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    env.reset(tid, off, sort_by_trace=True)
+    perm = env.perm.cpu().numpy()
+    assert np.array_equal(perm, np.argsort(tid, kind="stable").astype(np.int32))
+    assert np.array_equal(perm, env.sort_by_trace(tid).cpu().numpy())
+    ref = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    ref.reset(tid[perm], off[perm])
+    for f in STATE_I + STATE_F:
+        assert torch.equal(env.state(f), ref.state(f)), f
+    assert env.error_count() == 0
+    env.reset(tid, None, sort_by_trace=True)                 # no start offsets
+    assert float(env.state("phase").abs().sum()) == 0.0 and int(env.state("seg").abs().sum()) == 0
+
+
 # ---- SPEC §4.1: policy-in-the-loop step (abr_env_step_policy) ----
 def _philox4x32_10(c, k):
     """Philox4x32-10 on uint32 numpy arrays: counter words c[0..3], key words k[0..1] (SPEC §4)."""
