@@ -94,6 +94,7 @@ abr_sort_place(const int32_t* __restrict__ tid, const double* __restrict__ off, 
                 // first one to the others
                 const int leader = valid ? __ffs(peers) - 1 : lane;
                 int base = 0;
+                ABR_CHECK(bucket >= 0 && bucket < n_traces && (!valid || (peers >> lane) & 1u), "trace cursor / peer group");
                 if (valid && lane == leader) base = atomicAdd(&s_cur[bucket], __popc(peers));
                 base = __shfl_sync(0xffffffffu, base, leader);
                 s_pos[32 * k + lane] = base + rank;
@@ -105,6 +106,7 @@ abr_sort_place(const int32_t* __restrict__ tid, const double* __restrict__ off, 
             const int i = c0 + j;
             if (i < hi) {
                 const int pos = s_pos[j];
+                ABR_CHECK(pos >= 0 && pos < n, "position of a session in the sorted order");
                 perm[pos] = i;
                 tid_sorted[pos] = s_tid[j];
                 off_sorted[pos] = off ? off[i] : 0.0;

@@ -752,6 +752,7 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
         if (pol.action_out) pol.action_out[i] = q;
         if (pol.reward_sum) pol.reward_sum[i] = dadd(pol.reward_sum[i], r.reward);
         if (pol.obs) {
+            ABR_CHECK(i >= 0 && i < v.n && (s.chunk >= 0 && (s.chunk < v.V || s.done)), "observation column / next chunk");
             float* __restrict__ ob = pol.obs + i;
             const size_t n = (size_t)v.n;
             const int A = v.A;
@@ -943,6 +944,7 @@ __device__ __forceinline__ void stats_finish(const double* __restrict__ partials
     const int g = b / kStatsGroup;
     const int n_groups = (n_partials + kStatsGroup - 1) / kStatsGroup;
     const int g_size = min(kStatsGroup, n_partials - g * kStatsGroup);
+    ABR_CHECK(b >= 0 && b < n_partials && g_size >= 1 && blockDim.x >= kStatsLanes, "block partial / group of the statistics");
     __syncthreads();
     if (threadIdx.x == 0) *s_flag = atomicAdd(sc.counters + 1 + g, 1u) == (unsigned)(g_size - 1) ? 1 : 0;
     __syncthreads();

@@ -1055,6 +1055,28 @@ def test_env_run_equals_reset_rollout_cost_stats(policy):
     assert np.array_equal(env_a.state("chunk").cpu().numpy()[:N], np.zeros(N, np.int32))
 
 
+@pytest.mark.parametrize("N", [1, 63, 64, 65, 2049, 70001])
+def test_statistics_inside_the_episode_kernel_for_awkward_batch_sizes(N):
+    """abr_env_run with a statistics buffer reduces the statistics inside the episode kernel (block partials summed per
+    group of 32 blocks by the group's last block, the groups by the last group): one block, a partial group, several
+    groups (70 001 sessions = 1 094 blocks = 35 groups), repeated launches (the counters return to zero) — always the
+    bits that abr_stats_partial produces afterwards from the same partials, and the oracle's sums."""
+    steps = 20
+    bitrates, sizes, bw, tl, ti = small_world(n_traces=32, T=128)
+    tid, off = synth.make_sessions(N, 32, 128, group=64)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    for seed in (3, 4, 3):
+        out, cost, stats = env.run("random", steps, tid, off, seed=seed)
+        assert torch.equal(stats, env.stats()), seed          # the separate two-stage reduction: same order, same bits
+        acc = env.session_acc().cpu().numpy()
+        np.testing.assert_allclose(stats.cpu().numpy(), acc.sum(axis=1), rtol=1e-12)
+        assert stats[6].item() == N * steps
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
+    ref.reset(tid, off)
+    o = ref.rollout(orc.POLICY_RANDOM, steps, seed=3)
+    np.testing.assert_allclose(stats.cpu().numpy(), orc.stats_from_acc(o["acc"]), rtol=1e-9)
+
+
 def test_prepared_host_run_equals_run_host():
     N, steps = 2000, 48
     bitrates, sizes, bw, tl, ti = small_world(n_traces=16, T=128)
