@@ -43,6 +43,8 @@ def _source_hash() -> str:
 def is_stale() -> bool:
     """True when the .so is missing or was built from different sources (content hash, not mtimes: the
     snapshot that travels to the GPU box does not preserve a meaningful mtime order)."""
+    if os.environ.get("ABR_NO_REBUILD") and os.path.exists(LIB):
+        return False          # development only: A/B of libraries built from other revisions of the sources
     if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
     try:

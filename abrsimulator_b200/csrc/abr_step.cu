@@ -56,6 +56,7 @@ struct Sess {
     uint32_t cum_s, idx_s, tab_s;      // shared-memory addresses of the block's copies (SMEM path)
     const double2* __restrict__ tab;   // [V][A] {chunk size, utility} (global table)
     double I, phi, buffer;             // phi = fraction of segment `seg` already consumed (SPEC §1)
+    double inv_I;                      // pow2_inverse(I): 1/I when that is exact, else 0 (the sleeping step's chain starts with it)
     double pos;                        // the same position in data coordinates: C[seg] + (C[seg+1] - C[seg]) * phi
     double P, scale;                   // C[T]: capacity of one trace period; cells per unit of data
     double Td;                         // (double)T
@@ -169,10 +170,10 @@ __device__ __forceinline__ Lookup lookup_tables(const Sess& s, const int A, cons
 }
 
 // SPEC §3.3: move the trace position forward by dt seconds without downloading.
-__device__ __forceinline__ void advance_trace(int& seg, double& phi, const double dt, const double I, const int T) {
+__device__ __forceinline__ void advance_trace(int& seg, double& phi, const double dt, const double I, const double inv_i,
+                                              const int T) {
     // x / d == x * (1/d) bit for bit when d is a power of two (barring over/underflow, excluded by the range check in
-    // pow2_inverse), which saves the division for the usual 0.5 s / 1 s intervals
-    const double inv_i = pow2_inverse(I);
+    // pow2_inverse), which saves the division for the usual 0.5 s / 1 s intervals; inv_i = pow2_inverse(I)
     const double x = dadd(phi, inv_i != 0.0 ? dmul(dt, inv_i) : ddiv(dt, I));
     const double n = floor(x);
     phi = dsub(x, n);          // exact, in [0, 1)
@@ -362,7 +363,7 @@ __device__ __forceinline__ void live_gate(const EnvView& v, Sess& s, LiveGate& g
                           ? live_play_content(s, g.buffer, g.a, dsub(g.buffer, p.max_buffer), p.chunk_length) : 0.0;
     g.idle = dadd(w1, w2);
     if (g.idle > 0.0) {
-        advance_trace(s.seg, s.phi, g.idle, s.I, s.T);
+        advance_trace(s.seg, s.phi, g.idle, s.I, s.inv_I, s.T);
         s.pos = position_of<SMEM>(s, s.seg, s.phi);
     }
 }
@@ -428,7 +429,7 @@ __device__ __forceinline__ bool step_tail(const AbrParams& p, const int V, Sess&
             const double over = dsub(buffer, p.max_buffer);
             sleep = dmul(ceil(inv_q != 0.0 ? dmul(over, inv_q) : ddiv(over, p.sleep_quantum)), p.sleep_quantum);
             buffer = dsub(buffer, sleep);
-            advance_trace(seg, phi, sleep, s.I, T);
+            advance_trace(seg, phi, sleep, s.I, s.inv_I, T);
             s.pos = position_of<SMEM>(s, seg, phi);
             moved = true;
         }
@@ -504,6 +505,7 @@ __device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawStat
         const Quad m = ldg256(v.trace_meta + tr);
         s.I = m.a; s.P = m.b; s.scale = m.c; s.T = __double2loint(m.d); s.M = __double2hiint(m.d);
         s.Td = (double)s.T;
+        s.inv_I = pow2_inverse(s.I);
     }
     s.cum_s = s.idx_s = s.tab_s = 0u;
 #ifdef ABR_CHECKED
