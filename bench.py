@@ -451,6 +451,27 @@ def run_ours(args):
         per_rank = dict(ms_per_step=[float(t[0]) for t in allr], kernel_ms=[float(t[1]) for t in allr])
     tot_stats = allreduce_stats(stats)                          # the one collective: final QoE statistics
     torch.cuda.synchronize()
+    # ... and what it costs when it closes every step (BASELINE.json configs[2]: "final QoE all-reduce"): CUDA events
+    # around the call on the launching stream, max over ranks.  88 bytes per rank: pure latency.
+    collective = None
+    if world > 1:
+        cms = []
+        for it in range(3 + 10):
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            allreduce_stats(stats)
+            c1.record(stream)
+            c1.synchronize()
+            if it >= 3:
+                cms.append(c0.elapsed_time(c1))
+        cms.sort()
+        collective = dict(op="all_gather of the per-rank statistics vector + rank-order sum (deterministic)",
+                          bytes_per_rank=int(stats.numel() * 8), backend="nccl",
+                          us=max_over_ranks(1e3 * cms[len(cms) // 2], dev),
+                          step_with_collective_ms=total_ms / args.steps + max_over_ranks(cms[len(cms) // 2], dev),
+                          note="not inside value / e2e (one reduction closes a run, not a step); "
+                               "mpc.strong_scaling times it inside its region")
     chunk_steps = world * N * V * args.steps
     value = chunk_steps / (total_ms * 1e-3)
     errors = env.error_count()
@@ -669,6 +690,8 @@ def run_ours(args):
         line["rl_harness"] = rl
     if per_rank is not None:
         line["per_rank"] = per_rank
+    if collective is not None:
+        line["collective"] = collective
     if world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)
         line["cpu_baseline"] = cpu_baseline(args)
