@@ -409,12 +409,12 @@ class BatchedABREnv:
                 _ptr(out.get("latency")), _ptr(out.get("end_of_video")), _ptr(out.get("actions")), _stream()))
         return out
 
-    # -- SPEC §2+§3+§4+§6 in two launches --
+    # -- SPEC §2+§3+§4+§6 in one launch --
     def run(self, policy, steps, trace_id, start_offset=None, seed=0, session_base=0, actions=None,
             want=("delay", "sleep", "buffer", "rebuffer", "reward", "end_of_video"), out=None, qoe_cost=None,
             stats=None):
         """One whole run, device-resident (``abr_env_run``): reset + `steps` chunk steps + per-session QoE cost +
-        statistics; the episode kernel resets the sessions itself.  ``trace_id`` / ``start_offset``: device tensors
+        statistics in one kernel launch; the episode kernel resets the sessions itself and reduces the statistics.  ``trace_id`` / ``start_offset``: device tensors
         (or array-likes).  ``out``: dict of [steps, N] float64 device tensors as for ``rollout``; ``qoe_cost`` [N] and
         ``stats`` [NUM_STATS] are allocated when None (pass False to skip).  Returns (out, qoe_cost, stats)."""
         pid = _policy_id(policy)

@@ -166,8 +166,9 @@ int abr_env_rollout_fused_live(AbrEnv* env, int policy, uint64_t seed, int steps
                                double* d_rebuf, double* d_reward, double* d_latency, uint8_t* d_end_of_video,
                                int32_t* d_actions_out, void* stream);
 /* One whole run per call, device-resident: abr_env_reset + abr_env_rollout_fused + abr_env_qoe_cost +
- * abr_stats_partial in two launches — the episode kernel resets every session itself (SPEC §2, same operations as
- * abr_env_reset) and writes the per-session cost, so the state makes no round trip through HBM between the two.
+ * abr_stats_partial in ONE launch — the episode kernel resets every session itself (SPEC §2, same operations as
+ * abr_env_reset), writes the per-session cost and reduces the statistics (SPEC §6; the block that finishes last writes
+ * them), so the state makes no round trip through HBM in between.
  * This is Simulator.run() (Simulator.py:93-210) for a batch: d_qoe_cost[N] is what run() returns per session
  * (calculate_qoe, Simulator.py:83-86).  Trajectory outputs [steps][N], d_qoe_cost and d_stats are nullable. */
 int abr_env_run(AbrEnv* env, int policy, uint64_t seed, int steps, const int32_t* d_trace_id,

@@ -1024,7 +1024,7 @@ def test_run_host_fused_reset_equals_reset_then_rollout(params, policy):
 
 @pytest.mark.parametrize("policy", ["random", "bba", "fixed"])
 def test_env_run_equals_reset_rollout_cost_stats(policy):
-    """abr_env_run (two launches) against the four separate calls and against the oracle."""
+    """abr_env_run (one launch) against the four separate calls and against the oracle."""
     N, steps = 4000, 50
     bitrates, sizes, bw, tl, ti = small_world(n_traces=32, T=256)
     tid, off = synth.make_sessions(N, 32, 256, group=64)
