@@ -475,7 +475,8 @@ def run_ours(args):
     chunk_steps = world * N * V * args.steps
     value = chunk_steps / (total_ms * 1e-3)
     errors = env.error_count()
-    parity = parity_chunk_steps(out, tid_h, off_h, base) if rank == 0 else None
+    # every session of rank 0's shard: the C oracle replays the whole 65 536 x 48 batch in ~2 s
+    parity = parity_chunk_steps(out, tid_h, off_h, base, n_windows=max(1, N // 4096), window=min(N, 4096)) if rank == 0 else None
 
     # ---- optional fp32-output mode (fp64 arithmetic and state; 5 x 4 + 1 B of trajectory per chunk-step) ----
     out32 = {k: torch.empty(V, N, dtype=torch.float32, device=dev) for k in ("delay", "sleep", "buffer", "rebuffer", "reward")}
@@ -885,7 +886,7 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
     barrier()
     tot = max_over_ranks(sum(ms), dev)
     dec_per_s = world * M * reps / (tot * 1e-3)
-    mpc_parity = parity_mpc(menv, H, act) if rank == 0 else None     # outside the timed launches
+    mpc_parity = parity_mpc(menv, H, act, sample=32768) if rank == 0 else None     # outside the timed launches
     # reference-exact mode for comparison
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     menv.mpc_decide(H, "reference", out=act)

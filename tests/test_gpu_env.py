@@ -617,6 +617,29 @@ def test_calls_are_cuda_graph_capturable():
     assert torch.equal(out["reward"], ref_reward) and torch.equal(stats, ref_stats)
 
 
+@pytest.mark.parametrize("group", [64, 1])
+def test_full_size_bit_exact_against_the_c_oracle_65536x48(group):
+    """BASELINE configs[1] at its full size, every one of the 65 536 x 48 x 6 outputs, the final state and the
+    per-session sums against oracle/abr_oracle.c: bit-identical.  group = 64: the benchmark's layout (every block
+    follows one trace: shared-memory path); group = 1: trace = session mod n_traces (global path)."""
+    N, steps = 65536, 48
+    bitrates, sizes = synth.make_video(48)
+    bw, tl, ti = synth.make_traces(1024, 2048)
+    tid, off = synth.make_sessions(N, 1024, 2048, group=group)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti)
+    out, cost, stats = env.run("random", steps, tid, off, seed=20260101)
+    ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N)
+    ref.reset(tid, off)
+    exp = ref.rollout(orc.POLICY_RANDOM, steps, seed=20260101)
+    for kg, kc in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"), ("reward", "reward")):
+        assert bits_equal(out[kg].cpu().numpy(), exp[kc]) == 0, kg
+    assert np.array_equal(out["end_of_video"].cpu().numpy(), exp["eov"])
+    assert bits_equal(env.session_acc().cpu().numpy(), exp["acc"]) == 0
+    check_state(env, ref)
+    np.testing.assert_allclose(stats.cpu().numpy(), orc.stats_from_acc(exp["acc"]), rtol=1e-9)
+    assert env.error_count() == 0
+
+
 def test_full_size_properties_65536x48():
     """BASELINE config 2 at full size: properties that need no oracle."""
     N, steps = 65536, 48
