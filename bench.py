@@ -657,6 +657,7 @@ def run_ours(args):
                 vs_baseline=None, dtype="f64", data="synthetic", config=workload_config(args),
                 roofline=dict(kernel="abr_rollout_kernel<random>", bound="hbm", achieved=achieved, peak=hbm_peak,
                               unit="GB/s", frac=achieved / hbm_peak, traffic=traffic, peak_source=peak_src,
+                              frac_of_nominal_8000_gbs=achieved / 8000.0,
                               algorithmic_bytes_per_launch=alg_bytes, kernel_ms=kern_avg_ms,
                               bytes_per_chunk_step=BYTES_PER_STEP, bytes_per_session=per_session,
                               launch="abr_env_rollout_fused after abr_env_reset" if args.separate_reset else
