@@ -1293,3 +1293,73 @@ def test_step_policy_sampling_is_gumbel_max_over_philox_noise():
     assert chi2 < 30.0, (chi2, counts, p)        # 5 degrees of freedom: P(chi2 > 30) ~ 1e-5
     with pytest.raises(TypeError):
         env.step_policy(logits.double())
+
+
+def _fuzz_fast_worlds(seed, n_worlds):
+    """Random worlds through the FAST forms of the fused episode (abr_env_run: all six outputs, no action trace, reset and
+    statistics inside the kernel) — the kernels the benchmark runs — for the three policies, with one ladder for all
+    chunks (utility carried across steps) or one per chunk, sessions sorted by trace, shuffled, or sorted by the
+    environment.  Every output, the state, the per-session sums and the costs bit-identical to the C oracle."""
+    rng = np.random.default_rng(7000 + seed)
+    for w in range(n_worlds):
+        n_traces = int(rng.integers(1, 6))
+        T = int(rng.choice([1, 2, 3, 17, 64, 255, 400]))
+        V = int(rng.integers(1, 14))
+        A = int(rng.integers(1, 9))
+        scale = 10.0 ** rng.uniform(-2, 2)
+        bw = scale * 10.0 ** rng.uniform(-1.2, 1.2, size=(n_traces, T))
+        tl = rng.integers(1, T + 1, size=n_traces).astype(np.int32)
+        ti = rng.choice([0.25, 0.3, 0.5, 1.0, 1.7, 2.0], size=n_traces)
+        if rng.random() < 0.5:      # one ladder for the whole video
+            bitrates = np.tile(np.sort(rng.uniform(100.0, 5000.0, size=A)), (V, 1))
+        else:
+            bitrates = np.sort(rng.uniform(100.0, 5000.0, size=(V, A)), axis=1)
+        sizes = bitrates / 1000.0 * 4.0 * rng.uniform(0.5, 1.5, size=(V, A)) * 10.0 ** rng.uniform(-1, 1)
+        params = dict(rtt=float(rng.choice([0.0, 0.08])), payload=float(rng.choice([0.95, 1.0])),
+                      max_buffer=float(rng.choice([8.0, 20.0, 60.0])), sleep_quantum=float(rng.choice([0.3, 0.5])),
+                      default_quality=int(rng.integers(-1, A)), smooth_prev_ladder=int(rng.integers(0, 2)),
+                      utility_mode=int(rng.integers(0, 2)))
+        N = 64 * int(rng.integers(1, 5)) + int(rng.integers(0, 64))
+        tid = np.sort(rng.integers(0, n_traces, size=N)).astype(np.int32)
+        layout = w % 3
+        if layout:
+            tid = rng.permutation(tid)
+        off = rng.uniform(0, 3.0 * float(np.max(tl * ti)), size=N)
+        steps = int(rng.integers(1, 2 * V + 3))
+        policy = ("random", "bba", "fixed")[int(rng.integers(0, 3))]
+        acts = rng.integers(0, A, size=(steps, N)).astype(np.int32) if policy == "fixed" else None
+        env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, **params)
+        ref = orc.OracleEnv(bw, tl, ti, sizes, bitrates, N, **params)
+        tag = f"seed {seed} world {w} {policy} layout {layout}"
+        ref.reset(tid, off)
+        pid = dict(random=orc.POLICY_RANDOM, bba=orc.POLICY_BBA, fixed=orc.POLICY_FIXED)[policy]
+        exp = ref.rollout(pid, steps, seed=w, session_base=17, actions=acts)
+        if layout == 2:             # the environment sorts the shuffled sessions by trace; results mapped back
+            env.reset(tid, off, session_base=17, sort_by_trace=True)
+            got = env.rollout(policy, steps, seed=w, actions=None if acts is None else env.to_env_order(torch.from_numpy(acts)).contiguous(),
+                              want=("delay", "sleep", "buffer", "rebuffer", "reward", "end_of_video"))
+            got = {k: env.to_caller_order(x) for k, x in got.items()}
+            acc = env.to_caller_order(env.session_acc())
+        else:
+            got, cost, stats = env.run(policy, steps, tid, off, seed=w, session_base=17, actions=acts)
+            acc = env.session_acc()
+            assert torch.equal(stats, env.stats()), tag
+            np.testing.assert_allclose(stats.cpu().numpy(), orc.stats_from_acc(exp["acc"]), rtol=1e-9, atol=1e-300, err_msg=tag)
+            assert bits_equal(cost.cpu().numpy(), params_cost(exp["acc"])) == 0, tag
+            check_state(env, ref)
+        for k_g, k_c in (("delay", "delay"), ("sleep", "sleep"), ("buffer", "buffer"), ("rebuffer", "rebuf"),
+                         ("reward", "reward")):
+            assert bits_equal(got[k_g].cpu().numpy(), exp[k_c]) == 0, (tag, k_g)
+        assert np.array_equal(got["end_of_video"].cpu().numpy(), exp["eov"]), tag
+        assert bits_equal(acc.cpu().numpy(), exp["acc"]) == 0, tag
+        assert (env.error_count() == 0) == (ref.errors() == 0), tag
+
+
+def params_cost(acc, rw=4.3, vw=1.0):
+    """Simulator.calculate_qoe from the per-session sums (default weights): rw * sum(rebuffer) + vw * sum(smooth)."""
+    return rw * acc[1] + vw * acc[3]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_randomized_worlds_fast_kernels_match_oracle(seed):
+    _fuzz_fast_worlds(seed, 20)
