@@ -14,7 +14,8 @@ NUM_ACC = 11
 NUM_STATS = 11
 POLICY_FIXED, POLICY_RANDOM, POLICY_BBA = 0, 1, 2
 MPC_REF, MPC_ROBUST = 0, 1
-MPC_TRUNCATE, MPC_EMPTY_DEFAULT, MPC_PRED_SES = 1, 2, 4
+MPC_TRUNCATE, MPC_EMPTY_DEFAULT, MPC_PRED_SES, MPC_EXHAUSTIVE = 1, 2, 4, 8
+MPC_MODE_EXHAUSTIVE = 0x100
 ACC_NAMES = ("reward", "rebuffer", "utility", "smooth", "sleep", "delay", "steps", "episodes", "startup", "latency",
              "played")
 FIELDS = dict(seg=(0, "int32"), chunk=(1, "int32"), last_q=(2, "int32"), trace_id=(3, "int32"),

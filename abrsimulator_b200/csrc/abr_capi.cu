@@ -509,6 +509,8 @@ int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, do
     if (!env->was_reset) return fail(ABR_ERR_STATE, "abr_env_reset has not been called");
     if (env->v.n == 0) return ABR_OK;
     if (!d_action) return fail(ABR_ERR_INVALID, "action is NULL");
+    const bool exhaustive = (mode & ABR_MPC_MODE_EXHAUSTIVE) != 0;
+    mode &= ~ABR_MPC_MODE_EXHAUSTIVE;
     if (mode != ABR_MPC_REF && mode != ABR_MPC_ROBUST) return fail(ABR_ERR_INVALID, "unknown MPC mode %d", mode);
     if (!env->v.p.track_history)
         return fail(ABR_ERR_STATE, "abr_env_mpc_decide needs the throughput history: create the environment with track_history = 1");
@@ -521,7 +523,7 @@ int abr_env_mpc_decide(AbrEnv* env, int horizon, int mode, int32_t* d_action, do
     a.bw_hist = v.bw_hist; a.hist_len = v.hist_len; a.K = v.K;
     a.hist_session_stride = 1; a.hist_slot_stride = v.cap;     // env rings are [K][cap]
     a.last_pred = v.last_pred; a.err_ring = v.err_ring; a.err_len = v.err_len;
-    a.H = horizon; a.mode = mode; a.flags = ABR_MPC_TRUNCATE | ABR_MPC_EMPTY_DEFAULT;
+    a.H = horizon; a.mode = mode; a.flags = ABR_MPC_TRUNCATE | ABR_MPC_EMPTY_DEFAULT | (exhaustive ? ABR_MPC_EXHAUSTIVE : 0);
     a.action = d_action; a.best_j = d_best_j; a.best_seq = nullptr; a.preds = nullptr;
     a.error_count64 = v.errors; a.error_count32 = nullptr;
     CUDA_TRY(launch_mpc(a, (cudaStream_t)stream));

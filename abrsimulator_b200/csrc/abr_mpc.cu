@@ -22,12 +22,21 @@
 
 namespace abr {
 
+#ifdef ABR_MPC_COUNT   // development only: how much of the enumeration the bound leaves (abr_debug_mpc_counters)
+__device__ unsigned long long g_mpc_cnt[4];   // prefixes seen, prefixes evaluated (lane level), rows evaluated, warp rounds executed
+#define ABR_MPC_CNT(i, n) atomicAdd(&g_mpc_cnt[i], (unsigned long long)(n))
+#else
+#define ABR_MPC_CNT(i, n) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kMaxH = 8;
 constexpr int kMaxA = 16;
 constexpr int kMpcWarpsPerBlock = 4;
 constexpr int kPrefixCache = 64;   // parent states cached in shared memory per session (4 doubles each)
+constexpr int kMaxLivePrefix = 256;  // shapes search_compact takes: A^(h-2) prefixes and A^(h-1) rows at most
+constexpr int kMaxLiveRow = 1536;
 
 struct SearchOut { double q; int idx; };
 
@@ -51,12 +60,21 @@ __device__ __forceinline__ void interior(double& vq, double& qv, double& rt, dou
 // AT > 0: compile-time ladder size (loops fully unrolled); AT == 0: runtime A (generic path).
 // VW1: smooth_penalty == 1.0, so vw*qv == qv exactly and the multiply is dropped.
 // WPS: warps per session (selects the barrier that separates filling and reading the parent-state cache).
-template <int AT, bool CLAMP, bool VW1, int WPS>
+// prune (CLAMP only, penalties >= 0): branch and bound.  Every term still to come of a partial sequence is bounded
+// from the good side — the utility of a level by the level's largest, smoothness and rebuffering by zero — and because
+// floating-point addition, subtraction and multiplication by a non-negative constant are monotone, the bound computed
+// with the objective's own operations in the objective's own order is >= the value of EVERY completion, rounding
+// included.  A prefix (or a prefix + one more level) whose bound is strictly below a value some sequence is known to
+// reach cannot hold the optimum nor tie with it, and is skipped; the sequences that are evaluated are evaluated exactly
+// as before, so the result — first minimum of J in C order included — is that of the exhaustive enumeration.
+// `floor_q`: a value known to be reached (the best of the constant sequences, evaluated first).
+template <int AT, bool CLAMP, bool VW1, int WPS, bool PRUNE>
 __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const double* __restrict__ sRB,
                                             const double* __restrict__ sDL, const double* __restrict__ sAD,
                                             double* __restrict__ sPC, const int a_rt, const int h, const int prev_q,
                                             const double buf0, const double vw, const double rw, const double L,
-                                            const double B, const int tid, const int nthreads) {
+                                            const double B, const int tid, const int nthreads, const double floor_q) {
+    constexpr bool prune = PRUNE;
     const int A = AT > 0 ? AT : a_rt;
     constexpr bool REGTAB = AT > 0 && AT <= 6;   // larger ladders keep the rows in shared memory
     constexpr int AR = REGTAB ? AT : 1;         // register-array extent
@@ -103,7 +121,30 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
     }
     double best_q = __longlong_as_double(0xfff0000000000000ll);  // -inf
     int best_idx = 0x7fffffff;
-    for (int p = tid; p < n_prefix; p += nthreads) {
+    // largest utility of the last two levels (the bound's stand-in for the terms still to come)
+    double umax4 = 0.0, umax5 = 0.0;
+    if (CLAMP && prune) {
+        umax4 = sU[i4 * A]; umax5 = sU[i5 * A];
+        for (int a = 1; a < A; ++a) {
+            const double x4 = sU[i4 * A + a], x5 = sU[i5 * A + a];
+            umax4 = x4 > umax4 ? x4 : umax4;
+            umax5 = x5 > umax5 ? x5 : umax5;
+        }
+    }
+    double thresh = floor_q;   // a value the optimum is known to reach or exceed
+    for (int p0 = 0; p0 < n_prefix; p0 += nthreads) {   // uniform trip count: the warp shares its best value per round
+        if (CLAMP && prune) {
+            double m = best_q;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, m, off);
+                m = o > m ? o : m;
+            }
+            thresh = m > thresh ? m : thresh;
+        }
+        const int p = p0 + tid;
+        if (p >= n_prefix) continue;
+        ABR_MPC_CNT(0, 1);
         double vq = 0.0, qv = 0.0, rt = 0.0, b = buf0;
         int ap = prev_q;
         if (use_cache) {
@@ -134,6 +175,12 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
                 }
             }
         }
+        if (CLAMP && prune) {   // bound over the last two levels, in the objective's own order of operations
+            const double ub = dsub(dsub(dadd(dadd(vq, umax4), umax5), VW1 ? qv : dmul(vw, qv)), dmul(rw, rt));
+            if (ub < thresh) continue;
+        }
+        ABR_MPC_CNT(1, 1);
+        if ((__activemask() & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) ABR_MPC_CNT(3, 1);
         const double up4 = ap >= 0 ? sU[i4 * A + ap] : 0.0;
         const int base = p * A * A;
         // a4 is a rolled loop on purpose: unrolling both levels makes ptxas keep all A*A leaves in flight
@@ -144,6 +191,12 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
             double vq4 = vq, qv4 = qv, rt4 = rt, b4 = b;
             interior<CLAMP>(vq4, qv4, rt4, b4, u4, ap >= 0 ? fabs(dsub(u4, up4)) : 0.0,
                             sRB[i4 * A + a4], sDL[i4 * A + a4], L, B);
+            if (CLAMP && prune) {   // bound over the last level
+                const double t4 = best_q > thresh ? best_q : thresh;
+                const double ub = dsub(dsub(dadd(vq4, umax5), VW1 ? qv4 : dmul(vw, qv4)), dmul(rw, rt4));
+                if (ub < t4) continue;
+            }
+            ABR_MPC_CNT(2, 1);
 #pragma unroll
             for (int a5 = 0; a5 < A; ++a5) {
                 const double vq5 = dadd(vq4, REGTAB ? U5[a5] : sU[i5 * A + a5]);
@@ -159,6 +212,211 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
     return o;
 }
 
+
+// Branch and bound with compaction — the search of the benchmarked shape (robust mode, A^(h-2) <= 256 prefixes).
+// Measured on the benchmark's sessions, the bounds of `search` leave a fifth of the prefixes and a twentieth of the
+// (prefix, next action) rows alive, but a warp that walks the prefixes lane by lane still executes a round of them as
+// long as ONE of its 32 lanes survives: 3-4 of 7 rounds.  Here the survivors are compacted first (ballot + a
+// shared-memory cursor), so that every round of the expensive part works on 32 live items:
+//   1. every prefix: state after its last level from the parent cache, bound over the two levels to come -> live prefixes;
+//   2. every (live prefix, a4): one more level, bound over the last level -> live rows;
+//   3. every live row: its A leaves, with the warp's best value so far sharpening the bound from round to round.
+// The lists are not in index order, so the leaves compare (value, linear index) in full: the first minimum of J in C
+// order, as in the exhaustive enumeration.  States are recomputed rather than stored (one or two levels, ~60
+// instructions, against 4 doubles of shared memory per item).
+template <int AT, bool CLAMP, bool VW1, int WPS>
+__device__ __forceinline__ SearchOut search_compact(const double* __restrict__ sU, const double* __restrict__ sRB,
+                                                    const double* __restrict__ sDL, const double* __restrict__ sAD,
+                                                    double* __restrict__ sPC, int* __restrict__ n_live,
+                                                    uint16_t* __restrict__ live_prefix, uint16_t* __restrict__ live_row,
+                                                    const int a_rt, const int h, const int prev_q, const double buf0,
+                                                    const double vw, const double rw, const double L, const double B,
+                                                    const int tid, const int nthreads, const double floor_q) {
+    const int A = AT > 0 ? AT : a_rt;
+    const int P = h - 2;
+    int n_prefix = 1;
+    for (int i = 0; i < P; ++i) n_prefix *= A;
+    const int n_par = n_prefix / A;
+    const int i3 = P - 1, i4 = h - 2, i5 = h - 1;
+    const int lane = tid & 31;
+    auto barrier = [] { if (WPS > 1) __syncthreads(); else __syncwarp(); };
+    // parent states (the first P-1 levels), as in search()
+    if (tid < 2) n_live[tid] = 0;
+    for (int idx = tid; idx < n_par; idx += nthreads) {
+        int dig[kMaxH];
+        int rem = idx;
+#pragma unroll
+        for (int i = kMaxH - 4; i >= 0; --i) {
+            if (i < P - 1) { dig[i] = rem % A; rem /= A; }
+        }
+        double vq = 0.0, qv = 0.0, rt = 0.0, b = buf0;
+        int ap = prev_q;
+#pragma unroll
+        for (int i = 0; i < kMaxH - 3; ++i) {
+            if (i < P - 1) {
+                const int a = dig[i];
+                const double u = sU[i * A + a];
+                const double up = ap >= 0 ? sU[i * A + ap] : u;
+                interior<CLAMP>(vq, qv, rt, b, u, fabs(dsub(u, up)), sRB[i * A + a], sDL[i * A + a], L, B);
+                ap = a;
+            }
+        }
+        sPC[idx * 4 + 0] = vq; sPC[idx * 4 + 1] = qv; sPC[idx * 4 + 2] = rt; sPC[idx * 4 + 3] = b;
+    }
+    double umax4 = sU[i4 * A], umax5 = sU[i5 * A];
+    for (int a = 1; a < A; ++a) {
+        const double x4 = sU[i4 * A + a], x5 = sU[i5 * A + a];
+        umax4 = x4 > umax4 ? x4 : umax4;
+        umax5 = x5 > umax5 ? x5 : umax5;
+    }
+    barrier();
+    // state of prefix p after its last level (level i3) from its parent's cached state
+    auto prefix_state = [&](const int p, double& vq, double& qv, double& rt, double& b) -> int {
+        const int par = p / A, a = p - par * A;
+        ABR_CHECK(par >= 0 && par < kPrefixCache && par < n_par, "parent-state cache slot (read)");
+        vq = sPC[par * 4 + 0]; qv = sPC[par * 4 + 1]; rt = sPC[par * 4 + 2]; b = sPC[par * 4 + 3];
+        const int ap = par % A;
+        const double u = sU[i3 * A + a];
+        interior<CLAMP>(vq, qv, rt, b, u, fabs(dsub(u, sU[i3 * A + ap])), sRB[i3 * A + a], sDL[i3 * A + a], L, B);
+        return a;
+    };
+    // appends the items of the lanes with `live` to a list, in lane order within the warp
+    auto append = [&](const bool live, const int item, uint16_t* __restrict__ list, int* __restrict__ count, const int cap) {
+        const unsigned mask = __ballot_sync(0xffffffffu, live);
+        if (mask == 0u) return;
+        int base = 0;
+        const int leader = __ffs(mask) - 1;
+        if (lane == leader) base = atomicAdd(count, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live) {
+            const int pos = base + __popc(mask & ((1u << lane) - 1u));
+            ABR_CHECK(pos >= 0 && pos < cap, "live list slot");
+            list[pos] = (uint16_t)item;
+        }
+    };
+    // 1. live prefixes
+    for (int p0 = 0; p0 < n_prefix; p0 += nthreads) {
+        const int p = p0 + tid;
+        bool live = false;
+        if (p < n_prefix) {
+            double vq, qv, rt, b;
+            prefix_state(p, vq, qv, rt, b);
+            const double ub = dsub(dsub(dadd(dadd(vq, umax4), umax5), VW1 ? qv : dmul(vw, qv)), dmul(rw, rt));
+            live = !(ub < floor_q);
+            ABR_MPC_CNT(0, 1);
+        }
+        append(live, p, live_prefix, &n_live[0], kMaxLivePrefix);
+    }
+    barrier();
+    // 2. live rows: (live prefix, a4)
+    const int n1 = n_live[0];
+    for (int k0 = 0; k0 < n1 * A; k0 += nthreads) {
+        const int k = k0 + tid;
+        bool live = false;
+        int row = 0;
+        if (k < n1 * A) {
+            const int li = k / A, a4 = k - li * A;
+            const int p = live_prefix[li];
+            double vq, qv, rt, b;
+            const int ap = prefix_state(p, vq, qv, rt, b);
+            const double u4 = sU[i4 * A + a4];
+            interior<CLAMP>(vq, qv, rt, b, u4, fabs(dsub(u4, sU[i4 * A + ap])), sRB[i4 * A + a4], sDL[i4 * A + a4], L, B);
+            const double ub = dsub(dsub(dadd(vq, umax5), VW1 ? qv : dmul(vw, qv)), dmul(rw, rt));
+            live = !(ub < floor_q);
+            row = p * A + a4;
+            ABR_MPC_CNT(1, 1);
+        }
+        append(live, row, live_row, &n_live[1], kMaxLiveRow);
+    }
+    barrier();
+    // 3. the leaves of the live rows
+    const int n2 = n_live[1];
+    double best_q = __longlong_as_double(0xfff0000000000000ll);  // -inf
+    int best_idx = 0x7fffffff;
+    double thresh = floor_q;
+    for (int j0 = 0; j0 < n2; j0 += nthreads) {
+        {   // the warp's best value so far
+            double m = best_q;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, m, off);
+                m = o > m ? o : m;
+            }
+            thresh = m > thresh ? m : thresh;
+        }
+        const int j = j0 + tid;
+        if (j >= n2) continue;
+        const int row = live_row[j];
+        const int p = row / A, a4 = row - p * A;
+        double vq4, qv4, rt4, b4;
+        const int ap = prefix_state(p, vq4, qv4, rt4, b4);
+        const double u4 = sU[i4 * A + a4];
+        interior<CLAMP>(vq4, qv4, rt4, b4, u4, fabs(dsub(u4, sU[i4 * A + ap])), sRB[i4 * A + a4], sDL[i4 * A + a4], L, B);
+        const double ub = dsub(dsub(dadd(vq4, umax5), VW1 ? qv4 : dmul(vw, qv4)), dmul(rw, rt4));
+        if (ub < thresh) continue;
+        ABR_MPC_CNT(2, 1);
+        const int base = row * A;
+#pragma unroll
+        for (int a5 = 0; a5 < (AT > 0 ? AT : 1); ++a5) {
+            if (AT > 0) {
+                const double vq5 = dadd(vq4, sU[i5 * A + a5]);
+                const double qv5 = dadd(qv4, sAD[a5 * A + a4]);
+                const double d = dsub(sRB[i5 * A + a5], b4);
+                const double rt5 = dadd(rt4, CLAMP ? max0(d) : d);
+                const double q = dsub(dsub(vq5, VW1 ? qv5 : dmul(vw, qv5)), dmul(rw, rt5));
+                if (q > best_q || (q == best_q && base + a5 < best_idx)) { best_q = q; best_idx = base + a5; }
+            }
+        }
+        if (AT == 0) {
+            for (int a5 = 0; a5 < A; ++a5) {
+                const double vq5 = dadd(vq4, sU[i5 * A + a5]);
+                const double qv5 = dadd(qv4, sAD[a5 * A + a4]);
+                const double d = dsub(sRB[i5 * A + a5], b4);
+                const double rt5 = dadd(rt4, CLAMP ? max0(d) : d);
+                const double q = dsub(dsub(vq5, VW1 ? qv5 : dmul(vw, qv5)), dmul(rw, rt5));
+                if (q > best_q || (q == best_q && base + a5 < best_idx)) { best_q = q; best_idx = base + a5; }
+            }
+        }
+    }
+    SearchOut o; o.q = best_q; o.idx = best_idx;
+    return o;
+}
+
+// The best objective value among the A constant sequences (a, a, ..., a), lane a evaluating sequence a with exactly
+// the operations the search performs for it: a value the optimum reaches or exceeds, known before the search starts.
+template <bool CLAMP, bool VW1>
+__device__ __forceinline__ double probe_constant(const double* __restrict__ sU, const double* __restrict__ sRB,
+                                                 const double* __restrict__ sDL, const int A, const int h,
+                                                 const int prev_q, const double buf0, const double vw, const double rw,
+                                                 const double L, const double B, const int lane) {
+    double q = __longlong_as_double(0xfff0000000000000ll);  // -inf
+    if (lane < A) {
+        const int a = lane;
+        double vq = 0.0, qv = 0.0, rt = 0.0, b = buf0;
+        int ap = prev_q;
+        for (int i = 0; i < h - 1; ++i) {
+            const double u = sU[i * A + a];
+            const double up = ap >= 0 ? sU[i * A + ap] : u;
+            interior<CLAMP>(vq, qv, rt, b, u, fabs(dsub(u, up)), sRB[i * A + a], sDL[i * A + a], L, B);
+            ap = a;
+        }
+        const int i5 = h - 1;
+        const double u5 = sU[i5 * A + a];
+        const double vq5 = dadd(vq, u5);
+        const double qv5 = dadd(qv, ap >= 0 ? fabs(dsub(u5, sU[i5 * A + ap])) : 0.0);
+        const double d = dsub(sRB[i5 * A + a], b);
+        const double rt5 = dadd(rt, CLAMP ? max0(d) : d);
+        q = dsub(dsub(vq5, VW1 ? qv5 : dmul(vw, qv5)), dmul(rw, rt5));
+        if (!(q == q)) q = __longlong_as_double(0xfff0000000000000ll);   // a NaN bounds nothing
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, q, off);
+        q = o > q ? o : q;
+    }
+    return q;
+}
+
 __device__ __forceinline__ void better(double& q, int& idx, const double oq, const int oi) {
     if (oq > q || (oq == q && oi < idx)) { q = oq; idx = oi; }
 }
@@ -169,21 +427,36 @@ struct __align__(8) SessShared {
     double redq[kMpcWarpsPerBlock];
     int redi[kMpcWarpsPerBlock];
 };
+// branch and bound with compaction (search_compact): the prefixes, then the (prefix, next action) rows that survive
+// their bounds, and how many there are.  Only the pruning kernels carry the lists.
+template <bool PRUNE>
+struct LiveLists {
+    int n_live[2];
+    uint16_t live_prefix[PRUNE ? kMaxLivePrefix : 2];
+    uint16_t live_row[PRUNE ? kMaxLiveRow : 2];
+};
 
 // WPS warps per session; blockDim.x = 32 * kMpcWarpsPerBlock; sessions per block = kMpcWarpsPerBlock / WPS.
 // AT = compile-time ladder size (0 = runtime A), CLAMP = robust mode (SPEC §5.2) — one kernel per shape so
 // that each gets its own register allocation.
-template <int WPS, int AT, bool CLAMP>
-__global__ void __launch_bounds__(32 * kMpcWarpsPerBlock, 5)   // <= 96 registers: 20 warps per SM (A/B-tested: 4 -> 5 +3 %, 6 -3 %)
+// PRUNE (with CLAMP): branch and bound (search / search_compact); decided by the host (robust mode, non-negative
+// penalties, no ABR_MPC_EXHAUSTIVE).  A template parameter so that the enumerating kernel carries none of it.
+#ifndef ABR_MPC_PRUNE_BLOCKS
+#define ABR_MPC_PRUNE_BLOCKS 5
+#endif
+template <int WPS, int AT, bool CLAMP, bool PRUNE>
+__global__ void __launch_bounds__(32 * kMpcWarpsPerBlock, PRUNE ? ABR_MPC_PRUNE_BLOCKS : 5)   // <= 96 registers: 20 warps per SM (A/B-tested: 4 -> 5 +3 %, 6 -3 %)
 abr_mpc_kernel(const MpcArgs a) {
     constexpr int SPB = kMpcWarpsPerBlock / WPS;
     __shared__ SessShared sh[SPB];
+    __shared__ LiveLists<PRUNE> live[SPB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = warp / WPS;                 // session slot inside the block
     const int wis = warp % WPS;                  // warp index inside the session
     const int tid = wis * 32 + lane;             // thread index inside the session
     constexpr int NT = 32 * WPS;
     SessShared& S = sh[slot];
+    LiveLists<PRUNE>& LL = live[slot];
     const AbrParams& p = a.p;
     const int A = AT > 0 ? AT : a.A, H = a.H, K = a.K;
     const double L = p.chunk_length, B = p.max_buffer;
@@ -337,12 +610,32 @@ abr_mpc_kernel(const MpcArgs a) {
                     }
                     o.q = bq; o.idx = bi;
                 } else {
-                    if (p.smooth_penalty == 1.0)
-                        o = search<AT, CLAMP, true, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, bufj, 1.0, p.rebuf_penalty,
-                                                         L, B, tid, NT);
-                    else
-                        o = search<AT, CLAMP, false, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, bufj, p.smooth_penalty,
-                                                          p.rebuf_penalty, L, B, tid, NT);
+                    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+                    // the compacted form: shapes with a parent cache whose prefixes and rows fit the lists
+                    int n_pre = 1;
+                    for (int i = 0; i < h - 2; ++i) n_pre *= A;
+                    const bool compact = PRUNE && h >= 4 && n_pre / A <= kPrefixCache && n_pre <= kMaxLivePrefix &&
+                                         n_pre * A <= kMaxLiveRow;
+                    if (p.smooth_penalty == 1.0) {
+                        const double fl = PRUNE ? probe_constant<CLAMP, true>(S.U, S.RB, S.DL, A, h, prev_q, bufj, 1.0,
+                                                                              p.rebuf_penalty, L, B, lane) : ninf;
+                        if (PRUNE && compact)
+                            o = search_compact<AT, CLAMP, true, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, LL.n_live, LL.live_prefix, LL.live_row,
+                                                                     A, h, prev_q, bufj, 1.0, p.rebuf_penalty, L, B, tid, NT, fl);
+                        else
+                            o = search<AT, CLAMP, true, WPS, PRUNE>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, bufj, 1.0,
+                                                                    p.rebuf_penalty, L, B, tid, NT, fl);
+                    } else {
+                        const double fl = PRUNE ? probe_constant<CLAMP, false>(S.U, S.RB, S.DL, A, h, prev_q, bufj,
+                                                                               p.smooth_penalty, p.rebuf_penalty, L, B, lane) : ninf;
+                        if (PRUNE && compact)
+                            o = search_compact<AT, CLAMP, false, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, LL.n_live, LL.live_prefix, LL.live_row,
+                                                                      A, h, prev_q, bufj, p.smooth_penalty, p.rebuf_penalty, L, B, tid,
+                                                                      NT, fl);
+                        else
+                            o = search<AT, CLAMP, false, WPS, PRUNE>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, bufj, p.smooth_penalty,
+                                                                     p.rebuf_penalty, L, B, tid, NT, fl);
+                    }
                 }
                 // ---- argmin over the session's threads: key (J, linear index) ----
 #pragma unroll
@@ -488,6 +781,17 @@ __global__ void __launch_bounds__(32) abr_fp64_latency_kernel(int iters, double*
 
 }  // namespace
 
+#ifdef ABR_MPC_COUNT
+}  // namespace abr
+extern "C" int abr_debug_mpc_counters(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, abr::g_mpc_cnt, sizeof(unsigned long long) * 4);
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(abr::g_mpc_cnt, z, sizeof(z)); }
+    return 0;
+}
+namespace abr {
+#endif
+
 cudaError_t launch_fp64_latency(int kind, int iters, double* d_sink, long long* d_cycles, cudaStream_t st) {
     switch (kind) {
         case 0: abr_fp64_latency_kernel<0><<<1, 32, 0, st>>>(iters, d_sink, d_cycles); break;
@@ -513,15 +817,19 @@ cudaError_t launch_mpc(const MpcArgs& a, cudaStream_t st) {
     const long long max_blocks = (long long)sms * 64;
     if (blocks > max_blocks) blocks = max_blocks;
     const bool clamp = a.mode == ABR_MPC_ROBUST;
+    // branch and bound (SPEC §5.5): robust mode, non-negative penalties, unless the caller asks for the enumeration
+    const bool prune = clamp && !(a.flags & ABR_MPC_EXHAUSTIVE) && a.p.smooth_penalty >= 0.0 && a.p.rebuf_penalty >= 0.0;
     const unsigned g = (unsigned)blocks, t = 32 * kMpcWarpsPerBlock;
 #define ABR_MPC_LAUNCH(AT_)                                                                        \
     do {                                                                                           \
         if (wps == 1) {                                                                            \
-            if (clamp) abr_mpc_kernel<1, AT_, true><<<g, t, 0, st>>>(a);                           \
-            else abr_mpc_kernel<1, AT_, false><<<g, t, 0, st>>>(a);                                \
+            if (prune) abr_mpc_kernel<1, AT_, true, true><<<g, t, 0, st>>>(a);                     \
+            else if (clamp) abr_mpc_kernel<1, AT_, true, false><<<g, t, 0, st>>>(a);               \
+            else abr_mpc_kernel<1, AT_, false, false><<<g, t, 0, st>>>(a);                         \
         } else {                                                                                   \
-            if (clamp) abr_mpc_kernel<kMpcWarpsPerBlock, AT_, true><<<g, t, 0, st>>>(a);           \
-            else abr_mpc_kernel<kMpcWarpsPerBlock, AT_, false><<<g, t, 0, st>>>(a);                \
+            if (prune) abr_mpc_kernel<kMpcWarpsPerBlock, AT_, true, true><<<g, t, 0, st>>>(a);     \
+            else if (clamp) abr_mpc_kernel<kMpcWarpsPerBlock, AT_, true, false><<<g, t, 0, st>>>(a); \
+            else abr_mpc_kernel<kMpcWarpsPerBlock, AT_, false, false><<<g, t, 0, st>>>(a);         \
         }                                                                                          \
     } while (0)
     switch (a.A) {

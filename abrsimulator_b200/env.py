@@ -452,19 +452,23 @@ class BatchedABREnv:
         return out, qoe_cost, stats
 
     # -- SPEC §5 --
-    def mpc_decide(self, horizon=5, mode="robust", want_score=False, out=None):
+    def mpc_decide(self, horizon=5, mode="robust", want_score=False, out=None, exhaustive=False):
+        """MPC decision for every session (SPEC §5).  ``exhaustive``: evaluate all A^H sequences like the reference's
+        ``scipy.optimize.brute`` instead of skipping the partial sequences whose bound already loses (robust mode's
+        branch and bound; the decisions and objective values are identical either way)."""
         act = self._empty(self.n, dtype=torch.int32) if out is None else out
         bj = self._empty(self.n) if want_score else None
+        mode_id = _mode_id(mode) | (_lib.MPC_MODE_EXHAUSTIVE if exhaustive else 0)
         with self._on:
-            _lib.check(self._lib.abr_env_mpc_decide(self._h, C.c_int(horizon), C.c_int(_mode_id(mode)), _ptr(act),
+            _lib.check(self._lib.abr_env_mpc_decide(self._h, C.c_int(horizon), C.c_int(mode_id), _ptr(act),
                                                     _ptr(bj), _stream()))
         return (act, bj) if want_score else act
 
-    def mpc_episode(self, steps, horizon=5, mode="robust"):
+    def mpc_episode(self, steps, horizon=5, mode="robust", exhaustive=False):
         """decide -> step for `steps` chunks (needs track_history=1, track_acc=1 for statistics)."""
         act = self._empty(self.n, dtype=torch.int32)
         for _ in range(steps):
-            self.mpc_decide(horizon, mode, out=act)
+            self.mpc_decide(horizon, mode, out=act, exhaustive=exhaustive)
             with self._on:
                 _lib.check(self._lib.abr_env_step(self._h, _ptr(act), None, None, None, None, None, None, None, None,
                                                   _stream()))   # live mode: speed 1.0

@@ -888,6 +888,22 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
     tot = max_over_ranks(sum(ms), dev)
     dec_per_s = world * M * reps / (tot * 1e-3)
     mpc_parity = parity_mpc(menv, H, act, sample=32768) if rank == 0 else None     # outside the timed launches
+    # the same decisions by exhaustive enumeration (all A^H sequences, as scipy.optimize.brute does): the kernel the
+    # FP64-issue roofline below is about; the default above is branch and bound with identical results
+    act_x = torch.empty_like(act)
+    for _ in range(2):
+        menv.mpc_decide(H, "robust", out=act_x, exhaustive=True)
+    ms_x = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        menv.mpc_decide(H, "robust", out=act_x, exhaustive=True)
+        e1.record(stream)
+        e1.synchronize()
+        ms_x.append(e0.elapsed_time(e1))
+    menv.mpc_decide(H, "robust", out=act)
+    same_as_exhaustive = bool(torch.equal(act, act_x))
+    exh_per_s = world * M * reps / (max_over_ranks(sum(ms_x), dev) * 1e-3)
     # reference-exact mode for comparison
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     menv.mpc_decide(H, "reference", out=act)
@@ -964,6 +980,10 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
         if senv is not menv:
             del senv
     res = dict(metric="mpc_decisions_per_sec", value=dec_per_s, unit="decisions/s", horizon=H, mode="robust",
+               search="branch and bound over the A^H sequences (exact: the decisions of the exhaustive enumeration, "
+                      "checked in this run)",
+               exhaustive=dict(decisions_per_s=exh_per_s, ms_per_launch=sum(ms_x) / len(ms_x),
+                               identical_decisions=same_as_exhaustive),
                sequences_per_decision=A ** H, sessions_per_gpu=M, ms_per_launch=sum(ms) / len(ms),
                reference_exact_mode_decisions_per_s_per_gpu=ref_mode_rate,
                episode=dict(chunks=V, ms=ep_ms, decisions_per_s=world * M * V / (ep_ms * 1e-3),
@@ -1000,11 +1020,14 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
         executed = prefixes * (9 + A * 9 + A * A * 8) + (A ** (H - 3) if H >= 3 else 0) * (H - 3) * 9
         naive = A ** H * (14 * (H - 1) + 13) + 4 * A * H
         peak = probe["dadd_gops"]
-        res["roofline"] = dict(bound="fp64-issue", unit="Gop/s", peak=peak, peak_source="abr_fp64_probe (DADD chains, same run)",
+        res["roofline"] = dict(kernel="abr_mpc_kernel, exhaustive enumeration (ABR_MPC_EXHAUSTIVE)",
+                               bound="fp64-issue", unit="Gop/s", peak=peak, peak_source="abr_fp64_probe (DADD chains, same run)",
                                probe=probe, executed_fp64_ops_per_decision=executed,
-                               achieved=dec_per_s / world * executed / 1e9, frac=dec_per_s / world * executed / 1e9 / peak,
+                               achieved=exh_per_s / world * executed / 1e9, frac=exh_per_s / world * executed / 1e9 / peak,
                                naive_equivalent_ops_per_decision=naive,
-                               naive_equivalent_gops=dec_per_s / world * naive / 1e9)
+                               naive_equivalent_gops=dec_per_s / world * naive / 1e9,
+                               note="the default search (branch and bound) executes about half of these operations and is "
+                                    "bound by the latency of its phases, not by FP64 issue")
     return res
 
 

@@ -39,7 +39,12 @@ enum { ABR_MPC_REF = 0, ABR_MPC_ROBUST = 1 };
 enum { ABR_MPC_PRED_SES = 4,        /* mode 0: predictor "expsmoothing" (mpc.py:72-79) instead of "harmonic": the flat forecast of simple
                                       exponential smoothing, alpha = 0.5, least-squares initial level (SPEC 5.4) */
        ABR_MPC_TRUNCATE = 1,        /* mode 0: k+H > V truncates the horizon instead of flagging IndexError (mpc.py:125-128, D13) */
-       ABR_MPC_EMPTY_DEFAULT = 2 }; /* mode 0: empty history returns default_quality instead of flagging ZeroDivisionError (mpc.py:90, D14) */
+       ABR_MPC_EMPTY_DEFAULT = 2,   /* mode 0: empty history returns default_quality instead of flagging ZeroDivisionError (mpc.py:90, D14) */
+       ABR_MPC_EXHAUSTIVE = 8 };    /* mode 1: evaluate every one of the A^H sequences, as scipy.optimize.brute does (mpc.py:171-179),
+                                       instead of skipping the partial sequences whose bound already loses (branch and bound:
+                                       the decision, its objective value and the first-minimum tie-break are the same) */
+/* abr_env_mpc_decide takes the mode alone: OR this bit into it for the exhaustive enumeration */
+#define ABR_MPC_MODE_EXHAUSTIVE 0x100
 
 /* rows of the accumulator table / entries of the statistics vector (SPEC §6) */
 enum { ABR_ACC_REWARD = 0, ABR_ACC_REBUF = 1, ABR_ACC_UTILITY = 2, ABR_ACC_SMOOTH = 3, ABR_ACC_SLEEP = 4,

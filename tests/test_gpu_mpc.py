@@ -337,3 +337,56 @@ def test_shape_limits_are_rejected():
     with pytest.raises(_lib.AbrError):
         decide_batch(z(4, 4), z(4, 4), z(1, dt=torch.int32), z(1, dt=torch.int32), z(1), z(1, 5),
                      z(1, dt=torch.int32), 9, 0)
+
+
+@pytest.mark.parametrize("A,H", [(2, 4), (3, 5), (4, 5), (6, 4), (6, 5), (5, 6), (8, 4), (6, 2), (6, 3)])
+@pytest.mark.parametrize("ties,vw", [(False, 1.0), (True, 1.0), (False, 0.6), (True, 2.0)])
+def test_branch_and_bound_equals_exhaustive_enumeration(A, H, ties, vw):
+    """Robust mode skips the partial sequences whose bound already loses (SPEC §5.5): the decision, the whole best
+    sequence (first minimum in C order — ladders with exact ties included) and the objective value are those of the
+    exhaustive enumeration (ABR_MPC_EXHAUSTIVE) and of the oracle, for the compacted form (A^(H-2) <= 256 prefixes),
+    the plain form (larger shapes, H < 4) and penalties other than 1."""
+    rng = np.random.default_rng(31 * A + H + (5 if ties else 0) + int(10 * vw))
+    N, V, K = (3072 if A ** H <= 8000 else 512), 48, 5
+    b = _random_batch(rng, N, V, A, K, ties)
+    b["chunk"] = rng.integers(0, V, size=N).astype(np.int32)
+    b["prev_q"][:64] = -1
+    kw = dict(chunk_length=4.0 if not ties else 1.0, max_buffer=30.0, hist_k=K, smooth_penalty=vw,
+              rebuf_penalty=4.3 if not ties else 1.0, utility_scale=1.0)
+    exp, got, _, _ = _run_both(b, V, A, K, H, 1, kw)
+    _, got_x, _, _ = _run_both(b, V, A, K, H, 1, kw, flags=_lib.MPC_EXHAUSTIVE)
+    for g in (got, got_x):
+        assert np.array_equal(g["action"].cpu().numpy(), exp["action"])
+        assert np.array_equal(g["best_seq"].cpu().numpy(), exp["best_seq"])
+        ok = ~np.isnan(exp["best_J"])
+        assert bits_equal(g["best_j"].cpu().numpy()[ok], exp["best_J"][ok]) == 0
+
+
+def test_branch_and_bound_is_switched_off_for_negative_penalties():
+    """The bounds need non-negative penalties; with a negative one the search enumerates and still matches the oracle."""
+    rng = np.random.default_rng(77)
+    N, V, A, K, H = 1024, 48, 6, 5, 5
+    b = _random_batch(rng, N, V, A, K, False)
+    b["chunk"] = rng.integers(0, V - H, size=N).astype(np.int32)
+    kw = dict(chunk_length=4.0, max_buffer=30.0, hist_k=K, smooth_penalty=-0.5, rebuf_penalty=4.3, utility_scale=1.0)
+    exp, got, _, _ = _run_both(b, V, A, K, H, 1, kw)
+    assert np.array_equal(got["best_seq"].cpu().numpy(), exp["best_seq"])
+    assert bits_equal(got["best_j"].cpu().numpy(), exp["best_J"]) == 0
+
+
+def test_env_mpc_decide_exhaustive_flag():
+    from abrsimulator_b200 import synth
+    from abrsimulator_b200.env import BatchedABREnv
+    N = 8192
+    bitrates, sizes = synth.make_video(48)
+    bw, tl, ti = synth.make_traces(64, 256)
+    tid, off = synth.make_sessions(N, 64, 256, group=64)
+    env = BatchedABREnv(bw, sizes, bitrates, N, trace_len=tl, trace_interval=ti, track_history=1)
+    env.reset(tid, off)
+    env.rollout("random", 11, seed=3, want=())
+    snap = {f: env.state(f).clone() for f in ("last_pred", "err_ring", "err_len")}     # a decision updates the predictor
+    a, ja = env.mpc_decide(5, "robust", want_score=True)
+    for f, x in snap.items():
+        env.state(f).copy_(x)
+    b, jb = env.mpc_decide(5, "robust", want_score=True, exhaustive=True)
+    assert torch.equal(a, b) and torch.equal(ja, jb)
