@@ -55,25 +55,65 @@ __device__ __forceinline__ void interior(double& vq, double& qv, double& rt, dou
     b = max0(dsub(tl, w));
 }
 
+// ---- branch and bound: what the levels still to come can add at best, and the bound built from it ----
+// After action a at the level before,
+//   g5[a]  = max over a5 of U5[a5] - vw |U5[a5] - U5[a]|                       (the last level)
+//   g45[a] = max over a4 of U4[a4] - vw |U4[a4] - U4[a]| + g5[a4]              (the last two levels)
+// (rebuffering still to come is bounded by zero).  These combine utility and smoothness, which the objective
+// accumulates in separate sums, so a bound built from them holds in real arithmetic only; the slack in prune_bound
+// covers the rounding of the dozen operations in between a million times over.  Lanes a < A of every warp of the
+// session compute the same entries.
+__device__ __forceinline__ void bound_tables(const double* __restrict__ sU, const int A, const int h, const double vw,
+                                             double* __restrict__ g5, double* __restrict__ g45, const int lane) {
+    const int i4 = h - 2, i5 = h - 1;
+    if (lane < A) {
+        double m = __longlong_as_double(0xfff0000000000000ll);
+        for (int a5 = 0; a5 < A; ++a5) {
+            const double x = sU[i5 * A + a5] - vw * fabs(sU[i5 * A + a5] - sU[i5 * A + lane]);
+            m = x > m ? x : m;
+        }
+        g5[lane] = m;
+    }
+    __syncwarp();
+    if (lane < A) {
+        double m = __longlong_as_double(0xfff0000000000000ll);
+        for (int a4 = 0; a4 < A; ++a4) {
+            const double x = sU[i4 * A + a4] - vw * fabs(sU[i4 * A + a4] - sU[i4 * A + lane]) + g5[a4];
+            m = x > m ? x : m;
+        }
+        g45[lane] = m;
+    }
+    __syncwarp();
+}
+
+// upper bound of the value of every completion, from the sums so far and the best still to come (g5 / g45 entry)
+template <bool VW1>
+__device__ __forceinline__ double prune_bound(const double vq, const double qv, const double rt, const double g,
+                                              const double vw, const double rw) {
+    const double sq = VW1 ? qv : dmul(vw, qv), sr = dmul(rw, rt);
+    const double slack = 1e-9 * (fabs(vq) + sq + sr + fabs(g) + 1.0);
+    return (dsub(dsub(vq, sq), sr) + g) + slack;
+}
+
 // Search all A^h sequences for one session; h >= 2.  sU/sRB/sDL are [h][A] tables in shared memory,
 // sAD is |U[h-1][a] - U[h-1][a']| as [a][a'] (the leaf-level smoothness term).
 // AT > 0: compile-time ladder size (loops fully unrolled); AT == 0: runtime A (generic path).
 // VW1: smooth_penalty == 1.0, so vw*qv == qv exactly and the multiply is dropped.
 // WPS: warps per session (selects the barrier that separates filling and reading the parent-state cache).
-// prune (CLAMP only, penalties >= 0): branch and bound.  Every term still to come of a partial sequence is bounded
-// from the good side — the utility of a level by the level's largest, smoothness and rebuffering by zero — and because
-// floating-point addition, subtraction and multiplication by a non-negative constant are monotone, the bound computed
-// with the objective's own operations in the objective's own order is >= the value of EVERY completion, rounding
-// included.  A prefix (or a prefix + one more level) whose bound is strictly below a value some sequence is known to
-// reach cannot hold the optimum nor tie with it, and is skipped; the sequences that are evaluated are evaluated exactly
-// as before, so the result — first minimum of J in C order included — is that of the exhaustive enumeration.
-// `floor_q`: a value known to be reached (the best of the constant sequences, evaluated first).
+// PRUNE (CLAMP only, penalties >= 0): branch and bound.  The value of every completion of a partial sequence is at
+// most (sums so far, combined as the objective combines them) + (the best the levels still to come can add: utility
+// minus the smoothness it costs, bound_tables; rebuffering still to come >= 0) — prune_bound, with a slack that dwarfs
+// the rounding of the operations involved.  A prefix (or a prefix + one more level) whose bound is strictly below a
+// value some sequence is known to reach cannot hold the optimum nor tie with it, and is skipped; the sequences that are
+// evaluated are evaluated exactly as before, so the result — first minimum of J in C order included — is that of the
+// exhaustive enumeration.  `floor_q`: a value known to be reached (the best of the constant sequences, evaluated first).
 template <int AT, bool CLAMP, bool VW1, int WPS, bool PRUNE>
 __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const double* __restrict__ sRB,
                                             const double* __restrict__ sDL, const double* __restrict__ sAD,
                                             double* __restrict__ sPC, const int a_rt, const int h, const int prev_q,
                                             const double buf0, const double vw, const double rw, const double L,
-                                            const double B, const int tid, const int nthreads, const double floor_q) {
+                                            const double B, const int tid, const int nthreads, const double floor_q,
+                                            const double* __restrict__ g5, const double* __restrict__ g45) {
     constexpr bool prune = PRUNE;
     const int A = AT > 0 ? AT : a_rt;
     constexpr bool REGTAB = AT > 0 && AT <= 6;   // larger ladders keep the rows in shared memory
@@ -121,16 +161,6 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
     }
     double best_q = __longlong_as_double(0xfff0000000000000ll);  // -inf
     int best_idx = 0x7fffffff;
-    // largest utility of the last two levels (the bound's stand-in for the terms still to come)
-    double umax4 = 0.0, umax5 = 0.0;
-    if (CLAMP && prune) {
-        umax4 = sU[i4 * A]; umax5 = sU[i5 * A];
-        for (int a = 1; a < A; ++a) {
-            const double x4 = sU[i4 * A + a], x5 = sU[i5 * A + a];
-            umax4 = x4 > umax4 ? x4 : umax4;
-            umax5 = x5 > umax5 ? x5 : umax5;
-        }
-    }
     double thresh = floor_q;   // a value the optimum is known to reach or exceed
     for (int p0 = 0; p0 < n_prefix; p0 += nthreads) {   // uniform trip count: the warp shares its best value per round
         if (CLAMP && prune) {
@@ -175,9 +205,8 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
                 }
             }
         }
-        if (CLAMP && prune) {   // bound over the last two levels, in the objective's own order of operations
-            const double ub = dsub(dsub(dadd(dadd(vq, umax4), umax5), VW1 ? qv : dmul(vw, qv)), dmul(rw, rt));
-            if (ub < thresh) continue;
+        if (CLAMP && prune && ap >= 0) {   // bound over the last two levels
+            if (prune_bound<VW1>(vq, qv, rt, g45[ap], vw, rw) < thresh) continue;
         }
         ABR_MPC_CNT(1, 1);
         if ((__activemask() & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) ABR_MPC_CNT(3, 1);
@@ -193,8 +222,7 @@ __device__ __forceinline__ SearchOut search(const double* __restrict__ sU, const
                             sRB[i4 * A + a4], sDL[i4 * A + a4], L, B);
             if (CLAMP && prune) {   // bound over the last level
                 const double t4 = best_q > thresh ? best_q : thresh;
-                const double ub = dsub(dsub(dadd(vq4, umax5), VW1 ? qv4 : dmul(vw, qv4)), dmul(rw, rt4));
-                if (ub < t4) continue;
+                if (prune_bound<VW1>(vq4, qv4, rt4, g5[a4], vw, rw) < t4) continue;
             }
             ABR_MPC_CNT(2, 1);
 #pragma unroll
@@ -229,6 +257,7 @@ __device__ __forceinline__ SearchOut search_compact(const double* __restrict__ s
                                                     const double* __restrict__ sDL, const double* __restrict__ sAD,
                                                     double* __restrict__ sPC, int* __restrict__ n_live,
                                                     uint16_t* __restrict__ live_prefix, uint16_t* __restrict__ live_row,
+                                                    const double* __restrict__ g5, const double* __restrict__ g45,
                                                     const int a_rt, const int h, const int prev_q, const double buf0,
                                                     const double vw, const double rw, const double L, const double B,
                                                     const int tid, const int nthreads, const double floor_q) {
@@ -263,12 +292,6 @@ __device__ __forceinline__ SearchOut search_compact(const double* __restrict__ s
         }
         sPC[idx * 4 + 0] = vq; sPC[idx * 4 + 1] = qv; sPC[idx * 4 + 2] = rt; sPC[idx * 4 + 3] = b;
     }
-    double umax4 = sU[i4 * A], umax5 = sU[i5 * A];
-    for (int a = 1; a < A; ++a) {
-        const double x4 = sU[i4 * A + a], x5 = sU[i5 * A + a];
-        umax4 = x4 > umax4 ? x4 : umax4;
-        umax5 = x5 > umax5 ? x5 : umax5;
-    }
     barrier();
     // state of prefix p after its last level (level i3) from its parent's cached state
     auto prefix_state = [&](const int p, double& vq, double& qv, double& rt, double& b) -> int {
@@ -300,9 +323,8 @@ __device__ __forceinline__ SearchOut search_compact(const double* __restrict__ s
         bool live = false;
         if (p < n_prefix) {
             double vq, qv, rt, b;
-            prefix_state(p, vq, qv, rt, b);
-            const double ub = dsub(dsub(dadd(dadd(vq, umax4), umax5), VW1 ? qv : dmul(vw, qv)), dmul(rw, rt));
-            live = !(ub < floor_q);
+            const int a3 = prefix_state(p, vq, qv, rt, b);
+            live = !(prune_bound<VW1>(vq, qv, rt, g45[a3], vw, rw) < floor_q);
             ABR_MPC_CNT(0, 1);
         }
         append(live, p, live_prefix, &n_live[0], kMaxLivePrefix);
@@ -321,8 +343,7 @@ __device__ __forceinline__ SearchOut search_compact(const double* __restrict__ s
             const int ap = prefix_state(p, vq, qv, rt, b);
             const double u4 = sU[i4 * A + a4];
             interior<CLAMP>(vq, qv, rt, b, u4, fabs(dsub(u4, sU[i4 * A + ap])), sRB[i4 * A + a4], sDL[i4 * A + a4], L, B);
-            const double ub = dsub(dsub(dadd(vq, umax5), VW1 ? qv : dmul(vw, qv)), dmul(rw, rt));
-            live = !(ub < floor_q);
+            live = !(prune_bound<VW1>(vq, qv, rt, g5[a4], vw, rw) < floor_q);
             row = p * A + a4;
             ABR_MPC_CNT(1, 1);
         }
@@ -352,8 +373,7 @@ __device__ __forceinline__ SearchOut search_compact(const double* __restrict__ s
         const int ap = prefix_state(p, vq4, qv4, rt4, b4);
         const double u4 = sU[i4 * A + a4];
         interior<CLAMP>(vq4, qv4, rt4, b4, u4, fabs(dsub(u4, sU[i4 * A + ap])), sRB[i4 * A + a4], sDL[i4 * A + a4], L, B);
-        const double ub = dsub(dsub(dadd(vq4, umax5), VW1 ? qv4 : dmul(vw, qv4)), dmul(rw, rt4));
-        if (ub < thresh) continue;
+        if (prune_bound<VW1>(vq4, qv4, rt4, g5[a4], vw, rw) < thresh) continue;
         ABR_MPC_CNT(2, 1);
         const int base = row * A;
 #pragma unroll
@@ -434,6 +454,7 @@ struct LiveLists {
     int n_live[2];
     uint16_t live_prefix[PRUNE ? kMaxLivePrefix : 2];
     uint16_t live_row[PRUNE ? kMaxLiveRow : 2];
+    double g5[PRUNE ? kMaxA : 1], g45[PRUNE ? kMaxA : 1];   // best that the last level / the last two levels can still add
 };
 
 // WPS warps per session; blockDim.x = 32 * kMpcWarpsPerBlock; sessions per block = kMpcWarpsPerBlock / WPS.
@@ -616,25 +637,29 @@ abr_mpc_kernel(const MpcArgs a) {
                     for (int i = 0; i < h - 2; ++i) n_pre *= A;
                     const bool compact = PRUNE && h >= 4 && n_pre / A <= kPrefixCache && n_pre <= kMaxLivePrefix &&
                                          n_pre * A <= kMaxLiveRow;
+                    if (PRUNE) {
+                        bound_tables(S.U, A, h, p.smooth_penalty, LL.g5, LL.g45, lane);
+                        if (WPS > 1) __syncthreads();
+                    }
                     if (p.smooth_penalty == 1.0) {
                         const double fl = PRUNE ? probe_constant<CLAMP, true>(S.U, S.RB, S.DL, A, h, prev_q, bufj, 1.0,
                                                                               p.rebuf_penalty, L, B, lane) : ninf;
                         if (PRUNE && compact)
-                            o = search_compact<AT, CLAMP, true, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, LL.n_live, LL.live_prefix, LL.live_row,
+                            o = search_compact<AT, CLAMP, true, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, LL.n_live, LL.live_prefix, LL.live_row, LL.g5, LL.g45,
                                                                      A, h, prev_q, bufj, 1.0, p.rebuf_penalty, L, B, tid, NT, fl);
                         else
                             o = search<AT, CLAMP, true, WPS, PRUNE>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, bufj, 1.0,
-                                                                    p.rebuf_penalty, L, B, tid, NT, fl);
+                                                                    p.rebuf_penalty, L, B, tid, NT, fl, LL.g5, LL.g45);
                     } else {
                         const double fl = PRUNE ? probe_constant<CLAMP, false>(S.U, S.RB, S.DL, A, h, prev_q, bufj,
                                                                                p.smooth_penalty, p.rebuf_penalty, L, B, lane) : ninf;
                         if (PRUNE && compact)
-                            o = search_compact<AT, CLAMP, false, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, LL.n_live, LL.live_prefix, LL.live_row,
+                            o = search_compact<AT, CLAMP, false, WPS>(S.U, S.RB, S.DL, S.AD, S.PC, LL.n_live, LL.live_prefix, LL.live_row, LL.g5, LL.g45,
                                                                       A, h, prev_q, bufj, p.smooth_penalty, p.rebuf_penalty, L, B, tid,
                                                                       NT, fl);
                         else
                             o = search<AT, CLAMP, false, WPS, PRUNE>(S.U, S.RB, S.DL, S.AD, S.PC, A, h, prev_q, bufj, p.smooth_penalty,
-                                                                     p.rebuf_penalty, L, B, tid, NT, fl);
+                                                                     p.rebuf_penalty, L, B, tid, NT, fl, LL.g5, LL.g45);
                     }
                 }
                 // ---- argmin over the session's threads: key (J, linear index) ----

@@ -1026,7 +1026,7 @@ def bench_mpc(args, env, dev, rank, world, base, barrier, max_over_ranks):
                                achieved=exh_per_s / world * executed / 1e9, frac=exh_per_s / world * executed / 1e9 / peak,
                                naive_equivalent_ops_per_decision=naive,
                                naive_equivalent_gops=dec_per_s / world * naive / 1e9,
-                               note="the default search (branch and bound) executes about half of these operations and is "
+                               note="the default search (branch and bound) executes about a third of these operations and is "
                                     "bound by the latency of its phases, not by FP64 issue")
     return res
 
