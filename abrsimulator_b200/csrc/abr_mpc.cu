@@ -686,9 +686,9 @@ abr_mpc_kernel(const MpcArgs a) {
         if (tid == 0) {
             if (status == 0) {
                 int idx = o.idx == 0x7fffffff ? 0 : o.idx;   // all scores -inf/NaN: first sequence
-                int div = 1;
-                for (int i = 1; i < h; ++i) div *= A;
-                a.action[s] = idx / div;
+                int div = 1, first = idx;            // first action = idx / A^(h-1): h-1 divisions by A (a constant
+                for (int i = 1; i < h; ++i) { div *= A; first /= A; }   // when the ladder size is a template argument)
+                a.action[s] = first;
                 if (a.startup_delay) a.startup_delay[s] = ts_best;
                 if (a.best_j) a.best_j[s] = -o.q;
                 if (a.best_seq) {
