@@ -896,6 +896,18 @@ __device__ __forceinline__ double session_cost(const EnvView& v, const double re
 constexpr int kStatsGroup = 32;
 constexpr int kStatsLanes = 4 * ABR_NUM_ACC;   // threads (q, j) at work
 
+// The "I am done" count of the statistics reduction: one acq_rel atomic by one thread of the block, behind a block
+// barrier.  Release: the barrier puts the partials the block's other threads stored before this thread's atomic
+// (causality order is cumulative), so whoever reads the count they led to also sees them.  Acquire: the block that
+// reads the last count may — after its next block barrier — load every partial counted before (the loads bypass L1).
+// __threadfence() on both sides did the same job with four MEMBAR.SC.GPU + CCTL.IVALL sequences on the chain behind
+// the last episode, two of them executed by every thread of the block (each waits for its own trajectory stores).
+__device__ __forceinline__ unsigned count_done(unsigned* counter) {
+    unsigned old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ void stats_group_sum(const double* __restrict__ partials, const int n_partials, const int g,
                                                 double* __restrict__ group_partials, double (*sm)[ABR_NUM_ACC]) {
     const int t = threadIdx.x;
@@ -937,7 +949,7 @@ __device__ __forceinline__ void stats_final_sum(const double* __restrict__ group
 }
 
 // Called by every thread of a block (>= 64 threads) once the block's partial `b` of `n_partials` is written (by threads
-// < ABR_NUM_ACC, each followed by a __threadfence): counts the block as finished; the last block of its group sums the
+// < ABR_NUM_ACC): counts the block as finished (count_done); the last block of its group sums the
 // group, the last group sums the groups into `out`.  counters[0] counts finished groups, counters[1 + g] the
 // finished blocks of group g; all are left at zero.
 __device__ __forceinline__ void stats_finish(const double* __restrict__ partials, const int n_partials, const int b,
@@ -947,21 +959,18 @@ __device__ __forceinline__ void stats_finish(const double* __restrict__ partials
     const int n_groups = (n_partials + kStatsGroup - 1) / kStatsGroup;
     const int g_size = min(kStatsGroup, n_partials - g * kStatsGroup);
     ABR_CHECK(b >= 0 && b < n_partials && g_size >= 1 && blockDim.x >= kStatsLanes, "block partial / group of the statistics");
-    __syncthreads();
-    if (threadIdx.x == 0) *s_flag = atomicAdd(sc.counters + 1 + g, 1u) == (unsigned)(g_size - 1) ? 1 : 0;
+    __syncthreads();                            // the block's partial (threads < ABR_NUM_ACC) before the count
+    if (threadIdx.x == 0) *s_flag = count_done(sc.counters + 1 + g) == (unsigned)(g_size - 1) ? 1 : 0;
     __syncthreads();
     if (!*s_flag) return;                       // block-uniform
-    __threadfence();                            // the other blocks' partials, published before their count
     stats_group_sum(partials, n_partials, g, sc.group_partials, sm);
-    if (threadIdx.x < ABR_NUM_ACC) __threadfence();
-    __syncthreads();
+    __syncthreads();                            // the group's sum before its count
     if (threadIdx.x == 0) {
         sc.counters[1 + g] = 0u;
-        *s_flag = atomicAdd(sc.counters, 1u) == (unsigned)(n_groups - 1) ? 1 : 0;
+        *s_flag = count_done(sc.counters) == (unsigned)(n_groups - 1) ? 1 : 0;
     }
     __syncthreads();
     if (!*s_flag) return;
-    __threadfence();
     stats_final_sum(sc.group_partials, n_groups, out, sm);
     if (threadIdx.x == 0) sc.counters[0] = 0u;
 }
@@ -1336,7 +1345,6 @@ abr_rollout_kernel(EnvView v, uint32_t seed_lo, uint32_t seed_hi, int steps, uin
             double x = s_part[0][threadIdx.x];
             for (int w = 1; w < kRolloutBlock / 32; ++w) x = dadd(x, s_part[w][threadIdx.x]);
             block_partials[(size_t)blockIdx.x * ABR_NUM_ACC + threadIdx.x] = x;
-            if (o.out_stats) __threadfence();          // the partial is visible device-wide before this block counts as done
         }
         if (o.out_stats) {   // launch-uniform
             static_assert(kRolloutBlock >= kStatsLanes, "stats_finish needs 44 threads");
@@ -1391,12 +1399,10 @@ abr_stats_stage2(const double* __restrict__ partials, int n_partials, StatsScrat
     const int g = blockIdx.x;
     const int n_groups = (n_partials + kStatsGroup - 1) / kStatsGroup;
     stats_group_sum(partials, n_partials, g, sc.group_partials, sm);
-    if (threadIdx.x < ABR_NUM_ACC) __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_flag = atomicAdd(sc.counters, 1u) == (unsigned)(n_groups - 1) ? 1 : 0;
+    if (threadIdx.x == 0) s_flag = count_done(sc.counters) == (unsigned)(n_groups - 1) ? 1 : 0;
     __syncthreads();
     if (!s_flag) return;
-    __threadfence();
     stats_final_sum(sc.group_partials, n_groups, out, sm);
     if (threadIdx.x == 0) sc.counters[0] = 0u;
 }
