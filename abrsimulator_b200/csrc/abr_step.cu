@@ -496,17 +496,56 @@ __device__ __forceinline__ RawState load_raw(const EnvView& v, int i) {
     return w;
 }
 
-__device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawState& w, Sess& s) {
+// The per-step kernel's prefetch of the NEXT tile's state words and action: asynchronous copies (cp.async, SASS LDGSTS)
+// from the SoA arrays into a per-block staging buffer, every thread copying and later reading only its own session's
+// words, so no barrier is involved (cp.async.wait_group makes a thread's own copies visible to it).  Prefetching into
+// registers instead (the first form of this kernel) cost ten registers that do not exist under the 72-register budget
+// of seven blocks per SM: ptxas spilled them, a spill store has to wait for the load it spills, and 47 % of the
+// kernel's stall samples sat on those two STL instructions (ncu source page, profiles/r2z_summary.json) — the prefetch
+// waited for itself.
+struct NextTile {   // [kTile] columns: three doubles, five ints (the last one the action)
+    double phi[kTile], pos[kTile], buffer[kTile];
+    int tr[kTile], seg[kTile], chunk[kTile], last_q[kTile], action[kTile];
+};
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// session i's words into column t of the buffer (action == nullptr: none to fetch)
+__device__ __forceinline__ void request_next(NextTile& nx, const int t, const EnvView& v, const int i,
+                                             const int32_t* __restrict__ action) {
+    cp_async4(&nx.tr[t], v.trace_id + i); cp_async4(&nx.seg[t], v.seg + i); cp_async4(&nx.chunk[t], v.chunk + i);
+    cp_async4(&nx.last_q[t], v.last_q + i);
+    cp_async8(&nx.phi[t], v.phi + i); cp_async8(&nx.pos[t], v.pos + i); cp_async8(&nx.buffer[t], v.buffer + i);
+    if (action) cp_async4(&nx.action[t], action + i);
+}
+
+// waits for this thread's copies and reads its column; the values are pinned in registers before the caller may
+// issue the next request into the same column
+__device__ __forceinline__ RawState take_next(const NextTile& nx, const int t, int& q) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    RawState w;
+    w.tr = nx.tr[t]; w.seg = nx.seg[t]; w.chunk = nx.chunk[t]; w.last_q = nx.last_q[t];
+    w.phi = nx.phi[t]; w.pos = nx.pos[t]; w.buffer = nx.buffer[t];
+    q = nx.action[t];
+    asm volatile("" : "+r"(w.tr), "+r"(w.seg), "+r"(w.chunk), "+r"(w.last_q), "+d"(w.phi), "+d"(w.pos), "+d"(w.buffer), "+r"(q) :: "memory");
+    return w;
+}
+
+// `m`: the trace's 32-byte record (TraceMeta), read by the caller — one 256-bit read-only load, or the block's
+// shared-memory copy of it when the session follows the trace whose rows the block has staged.
+__device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawState& w, Sess& s, const Quad& m) {
     const int tr = w.tr;
     s.cum = v.trace_cum + (size_t)tr * cum_stride(v.T_max);
     s.idx = v.trace_idx + (size_t)tr * idx_stride(v.T_max);
     s.tab = v.tab;
-    {   // one 32-byte record, one 256-bit read-only load
-        const Quad m = ldg256(v.trace_meta + tr);
-        s.I = m.a; s.P = m.b; s.scale = m.c; s.T = __double2loint(m.d); s.M = __double2hiint(m.d);
-        s.Td = (double)s.T;
-        s.inv_I = pow2_inverse(s.I);
-    }
+    s.I = m.a; s.P = m.b; s.scale = m.c; s.T = __double2loint(m.d); s.M = __double2hiint(m.d);
+    s.Td = (double)s.T;
+    s.inv_I = pow2_inverse(s.I);
     s.cum_s = s.idx_s = s.tab_s = 0u;
 #ifdef ABR_CHECKED
     s.chk_cum_n = cum_stride(v.T_max); s.chk_idx_n = idx_stride(v.T_max); s.chk_tab_n = v.V * v.A;
@@ -522,6 +561,10 @@ __device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawStat
     s.buffer = w.buffer;
     s.done = v.p.auto_reset ? false : (v.done[i] != 0);
     s.hist_len = v.p.track_history ? v.hist_len[i] : 0;
+}
+
+__device__ __forceinline__ void make_sess(const EnvView& v, int i, const RawState& w, Sess& s) {
+    make_sess(v, i, w, s, ldg256(v.trace_meta + w.tr));
 }
 
 __device__ __forceinline__ void load_sess(const EnvView& v, int i, Sess& s) {
@@ -685,8 +728,11 @@ __device__ __forceinline__ int policy_action(const EnvView& v, const StepPolicy&
     return arg;
 }
 
+// `q`: the action, already clamped to [0, A); `lk`: the step's table reads (the caller issues them as soon as it holds
+// the session's state words, next to the read of the trace record, so that the two L2 round trips overlap).
 template <bool SMEM, bool FAST, bool LIVE, bool POL, typename OT>
-__device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const int i, const int q_in, const StepPolicy& pol,
+__device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const int i, const int q, const Lookup& lk,
+                                             const StepPolicy& pol,
                                              const double* __restrict__ speed, OT* __restrict__ o_delay,
                                              OT* __restrict__ o_sleep, OT* __restrict__ o_buffer,
                                              OT* __restrict__ o_rebuf, OT* __restrict__ o_reward,
@@ -698,12 +744,7 @@ __device__ __forceinline__ void step_session(const EnvView& v, Sess& s, const in
         s.speed = speed ? speed + i : nullptr;   // [V][N] table: the speed of content chunk k is speed[k][i]
         s.speed_stride = (size_t)v.n; s.V = v.V; s.bad_speed = false;
     }
-    int q = q_in;
-    bool bad = q < 0 || q >= v.A;
-    if (bad) q = q < 0 ? 0 : v.A - 1;
-    if (bad) atomicAdd(v.errors, 1ull);
     StepRes r;
-    const Lookup lk = lookup_tables<false>(s, v.A, v.V, s.chunk, q, s.last_q, v.p.smooth_prev_ladder != 0);
     step_core<SMEM, FAST, LIVE>(v, s, q, lk, r, (!FAST && v.p.track_history) || o_thr != nullptr || (POL && pol.obs));
     if (r.walk_error || (LIVE && s.bad_speed)) atomicAdd(v.errors, 1ull);
     if (FAST) {
@@ -792,7 +833,8 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
                 int smem_doubles, int tiles_per_block, const StepPolicy pol) {
     extern __shared__ __align__(16) double2 s_row2[];
     __shared__ __align__(8) unsigned long long s_mbar;
-#define ABR_STEP_SESSION_ARGS v, s, i, q_cur, pol, speed, o_delay, o_sleep, o_buffer, o_rebuf, o_reward, o_latency, o_next_sizes, o_eov, o_thr
+    __shared__ Quad s_meta;                      // the record of the trace whose rows are staged
+#define ABR_STEP_SESSION_ARGS v, s, i, q_cur, lk, pol, speed, o_delay, o_sleep, o_buffer, o_rebuf, o_reward, o_latency, o_next_sizes, o_eov, o_thr
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
     if (smem_doubles != 0) {
         if (threadIdx.x == 0) {
@@ -806,13 +848,15 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     uint32_t parity = 0u;                        // phase of the next staging copy (block-uniform)
     int staged = -1;                             // trace whose rows the buffer holds (block-uniform, kept per thread)
     // the state words and the action of the next tile are requested before the current tile is computed, so that
-    // two tiles of loads per warp are in flight (the kernel is bound by HBM latency x occupancy otherwise)
-    RawState w_next;
-    int q_next = 0, first_next = -1, last_next = -1;
+    // two tiles of loads per warp are in flight (the kernel is bound by HBM latency x occupancy otherwise); they
+    // travel through shared memory, not registers (NextTile)
+    __shared__ NextTile s_next;
+    const int32_t* __restrict__ act_src = POL ? nullptr : action;
+    int first_next = -1, last_next = -1;
     {
         const int t0 = blockIdx.x * tiles_per_block * kTile;
         const int i0 = t0 + threadIdx.x;
-        if (i0 < v.n) { w_next = load_raw(v, i0); if (!POL) q_next = action[i0]; }
+        if (i0 < v.n) request_next(s_next, threadIdx.x, v, i0, act_src);
         if (t0 < v.n) { first_next = __ldg(v.trace_id + t0); last_next = __ldg(v.trace_id + min(t0 + kTile, v.n) - 1); }
     }
     for (int k = 0; k < tiles_per_block; ++k) {
@@ -820,28 +864,44 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
         if (tile0 >= v.n) break;                 // block-uniform
         const int i = tile0 + threadIdx.x;
         const bool valid = i < v.n;
-        const RawState w = w_next;
-        const int q_cur = POL ? (valid ? policy_action(v, pol, i) : 0) : q_next;
+        int q_next = 0;
+        const RawState w = take_next(s_next, threadIdx.x, q_next);   // an invalid lane reads words nobody uses
+        int q_cur = POL ? (valid ? policy_action(v, pol, i) : 0) : q_next;
+        if (valid && (q_cur < 0 || q_cur >= v.A)) atomicAdd(v.errors, 1ull);
+        q_cur = q_cur < 0 ? 0 : (q_cur >= v.A ? v.A - 1 : q_cur);
+        // The table reads depend on nothing but the state words: issued here, ahead of the staging decision and the
+        // trace record (with seven blocks per SM the L1 is ~20 KB and streams state and outputs, so both are L2 round
+        // trips more often than not; back to back they were 33 % of the kernel's stall samples).
+        Sess s;
+        Lookup lk;
+        lk.size = lk.u = lk.u_prev = 0.0;
+        if (valid) {
+            s.tab = v.tab; s.tab_s = 0u;
+#ifdef ABR_CHECKED
+            s.chk_tab_n = v.V * v.A;
+#endif
+            lk = lookup_tables<false>(s, v.A, v.V, w.chunk, q_cur, w.last_q, v.p.smooth_prev_ladder != 0);
+        }
         // traces of the first and the last session of the tile: the same words in every thread, so decisions taken
         // on them are block-uniform without a barrier.  Equal ends mean one trace for callers that keep sessions
         // sorted by trace; a lane that disagrees anyway simply takes the global path.
         const int tr_first = first_next, tr_last = last_next;
         if (k + 1 < tiles_per_block && tile0 + kTile < v.n) {
-            if (i + kTile < v.n) { w_next = load_raw(v, i + kTile); if (!POL) q_next = action[i + kTile]; }
+            if (i + kTile < v.n) request_next(s_next, threadIdx.x, v, i + kTile, act_src);
             first_next = __ldg(v.trace_id + tile0 + kTile);
             last_next = __ldg(v.trace_id + min(tile0 + 2 * kTile, v.n) - 1);
         }
-        Sess s;
-        int tr = -1;
-        if (valid) { make_sess(v, i, w, s); tr = w.tr; }
+        const int tr = valid ? w.tr : -1;
         if (smem_doubles == 0) {                 // launch-uniform: no shared-memory row buffer
-            if (valid) step_session<false, FAST, LIVE, POL, OT>(ABR_STEP_SESSION_ARGS);
+            if (valid) { make_sess(v, i, w, s); step_session<false, FAST, LIVE, POL, OT>(ABR_STEP_SESSION_ARGS); }
             continue;
         }
         if (tr_first == tr_last && tr_first != staged) {   // block-uniform: stage another trace's rows
-            __syncthreads();                     // every warp is done with the rows the buffer holds
+            __syncthreads();                     // every warp is done with the rows (and the record) the buffer holds
             if (threadIdx.x == 0) {
-                const int T0 = __ldg(&v.trace_meta[tr_first].T), M0 = __ldg(&v.trace_meta[tr_first].M);
+                const Quad m0 = ldg256(v.trace_meta + tr_first);
+                s_meta = m0;                     // published by the arrive below (release), seen behind mbar_wait (acquire)
+                const int T0 = __double2loint(m0.d), M0 = __double2hiint(m0.d);
                 const uint32_t rb = row_bytes_of(T0), ib = idx_bytes_of(M0);   // T0 <= T_max: both fit the buffer
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(rb + ib) : "memory");
                 bulk_g2s(s_row, v.trace_cum + (size_t)tr_first * cum_stride(v.T_max), rb, mbar);
@@ -853,6 +913,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
         }
         if (valid) {
             if (tr == staged) {
+                make_sess(v, i, w, s, s_meta);
                 s.cum_s = (uint32_t)__cvta_generic_to_shared(s_row);
                 s.idx_s = (uint32_t)__cvta_generic_to_shared(s_idx);
 #ifdef ABR_CHECKED
@@ -862,6 +923,7 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
 #endif
                 step_session<true, FAST, LIVE, POL, OT>(ABR_STEP_SESSION_ARGS);
             } else {
+                make_sess(v, i, w, s);
                 step_session<false, FAST, LIVE, POL, OT>(ABR_STEP_SESSION_ARGS);
             }
         }
