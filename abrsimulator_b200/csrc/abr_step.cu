@@ -38,6 +38,13 @@ namespace abr {
 namespace {
 
 constexpr int kStepBlock = 256;      // helper kernels (reset, tables, cost)
+#ifndef ABR_STEP_PF_DIST
+#define ABR_STEP_PF_DIST 2           // the per-step kernel asks the tile this many tiles ahead into L2 (1: off)
+#endif
+// The per-step kernel's L2 prefetch is for batches that stream from HBM: state + outputs (121 B per session) well
+// beyond the 126 MB L2.  A batch that lives in L2 from one step to the next (back-to-back steps of 524 288 or 1 Mi
+// sessions) only pays for the instructions: 18.4 -> 20.5 us and 24.7 -> 26.2 us.
+constexpr long long kPrefetchMinBytes = 192ll << 20;
 constexpr int kTile = 128;           // threads per block = sessions per tile of the per-step kernel
 constexpr int kTileBlocksPerSM = 7;
 constexpr int kStepTiles = 8;         // least number of tiles per block of the per-step kernel
@@ -515,6 +522,10 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 
+__device__ __forceinline__ void l2_prefetch(const void* gmem_src, const uint32_t bytes) {   // 16-byte aligned, multiple of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // session i's words into column t of the buffer (action == nullptr: none to fetch)
 __device__ __forceinline__ void request_next(NextTile& nx, const int t, const EnvView& v, const int i,
                                              const int32_t* __restrict__ action) {
@@ -851,6 +862,8 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
     // two tiles of loads per warp are in flight (the kernel is bound by HBM latency x occupancy otherwise); they
     // travel through shared memory, not registers (NextTile)
     __shared__ NextTile s_next;
+    const bool stream_from_hbm = (long long)v.n * 121 >= kPrefetchMinBytes;   // launch-uniform
+    const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp index, known to be warp-uniform
     const int32_t* __restrict__ act_src = POL ? nullptr : action;
     int first_next = -1, last_next = -1;
     {
@@ -864,6 +877,12 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
         if (tile0 >= v.n) break;                 // block-uniform
         const int i = tile0 + threadIdx.x;
         const bool valid = i < v.n;
+        // traces of the first and the last session of the tile: the same words in every thread, so decisions taken
+        // on them are block-uniform without a barrier.  Equal ends mean one trace for callers that keep sessions
+        // sorted by trace; a lane that disagrees anyway simply takes the global path.  (Read here, ahead of this
+        // iteration's loads: a later read would wait on a scoreboard it shares with them.)
+        int tr_first = first_next, tr_last = last_next;
+        asm volatile("" : "+r"(tr_first), "+r"(tr_last));
         int q_next = 0;
         const RawState w = take_next(s_next, threadIdx.x, q_next);   // an invalid lane reads words nobody uses
         int q_cur = POL ? (valid ? policy_action(v, pol, i) : 0) : q_next;
@@ -882,12 +901,26 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
 #endif
             lk = lookup_tables<false>(s, v.A, v.V, w.chunk, q_cur, w.last_q, v.p.smooth_prev_ladder != 0);
         }
-        // traces of the first and the last session of the tile: the same words in every thread, so decisions taken
-        // on them are block-uniform without a barrier.  Equal ends mean one trace for callers that keep sessions
-        // sorted by trace; a lane that disagrees anyway simply takes the global path.
-        const int tr_first = first_next, tr_last = last_next;
         if (k + 1 < tiles_per_block && tile0 + kTile < v.n) {
             if (i + kTile < v.n) request_next(s_next, threadIdx.x, v, i + kTile, act_src);
+#if ABR_STEP_PF_DIST > 1
+            // a tile further ahead: its words are asked into L2 (one bulk prefetch per array and warp, SASS UBLKPF:
+            // handled by the copy engine, not the load/store pipe), so that more than one tile of reads per block
+            // is on its way from HBM — what a block keeps in flight, not the latency of one load, bounds this kernel
+            // (104 us instead of 117 per 4 Mi sessions; a distance of 3 or 4 tiles: 105 / 108 us; every lane
+            // prefetching its own word with prefetch.global.L2: 106.5 us; one prefetch per array and block: no gain).
+            // The addresses are built from the warp index as a shuffle result so that they live in uniform
+            // registers: from threadIdx they were walked there lane by lane, 146 instructions per warp and tile.
+            {
+                const int j = tile0 + ABR_STEP_PF_DIST * kTile + 32 * warp_u;
+                if (stream_from_hbm && k + ABR_STEP_PF_DIST < tiles_per_block && j + 32 <= v.n && (threadIdx.x & 31) == 0) {
+                    l2_prefetch(v.trace_id + j, 128); l2_prefetch(v.seg + j, 128); l2_prefetch(v.chunk + j, 128);
+                    l2_prefetch(v.last_q + j, 128); l2_prefetch(v.phi + j, 256); l2_prefetch(v.pos + j, 256);
+                    l2_prefetch(v.buffer + j, 256);
+                    if (act_src) l2_prefetch(act_src + j, 128);
+                }
+            }
+#endif
             first_next = __ldg(v.trace_id + tile0 + kTile);
             last_next = __ldg(v.trace_id + min(tile0 + 2 * kTile, v.n) - 1);
         }

@@ -1,5 +1,5 @@
 """Mean time of the per-step kernel (abr_env_step, 4 Mi trace-sorted sessions, fp64 outputs) over back-to-back launches —
-the A/B number for variants of abr_step_kernel.  usage: python profiles/time_step.py [launches] [sessions]"""
+the A/B number for variants of abr_step_kernel.  usage: python profiles/time_step.py [launches] [sessions] [sessions per trace run; 1 = interleaved]"""
 import sys
 
 import torch
@@ -20,7 +20,8 @@ g.manual_seed(1)
 acts = torch.randint(0, A, (8, M), dtype=torch.int32, device=dev, generator=g)
 out = StepResult(*[torch.empty(M, dtype=torch.float64, device=dev) for _ in range(5)], None,
                  torch.empty(M, dtype=torch.uint8, device=dev), None)
-tid, off = synth.make_sessions(M, 1024, 2048, group=max(256, M // 1024))
+group = int(sys.argv[3]) if len(sys.argv) > 3 else max(256, M // 1024)
+tid, off = synth.make_sessions(M, 1024, 2048, group=group)
 env.reset(tid, off)
 for t in range(8):
     env.step(acts[t % 8], out=out)
@@ -34,5 +35,5 @@ for block in range(3):
     e1.synchronize()
     res.append(e0.elapsed_time(e1) / reps)
 bytes_per = 40 + 4 + 36 + 41
-print(f"{M} sessions: " + " ".join(f"{1e3 * r:.2f}" for r in res) + f" us per launch; best {M * bytes_per / (min(res) * 1e-3) / 1e9:.0f} GB/s"
+print(f"{M} sessions (runs of {group}): " + " ".join(f"{1e3 * r:.2f}" for r in res) + f" us per launch; best {M * bytes_per / (min(res) * 1e-3) / 1e9:.0f} GB/s"
       f"   reward sum {float(out.reward.sum()):.6f}")
