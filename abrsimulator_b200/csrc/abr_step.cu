@@ -909,8 +909,8 @@ abr_step_kernel(EnvView v, const int32_t* __restrict__ action, const double* __r
             // is on its way from HBM — what a block keeps in flight, not the latency of one load, bounds this kernel
             // (104 us instead of 117 per 4 Mi sessions; a distance of 3 or 4 tiles: 105 / 108 us; every lane
             // prefetching its own word with prefetch.global.L2: 106.5 us; one prefetch per array and block: no gain).
-            // The addresses are built from the warp index as a shuffle result so that they live in uniform
-            // registers: from threadIdx they were walked there lane by lane, 146 instructions per warp and tile.
+            // UBLKPF takes its address from uniform registers; ptxas walks it there with an R2UR loop (one iteration:
+            // lane 0 alone is active) also when it is built from a shuffled warp index — ~18 instructions per prefetch.
             {
                 const int j = tile0 + ABR_STEP_PF_DIST * kTile + 32 * warp_u;
                 if (stream_from_hbm && k + ABR_STEP_PF_DIST < tiles_per_block && j + 32 <= v.n && (threadIdx.x & 31) == 0) {
